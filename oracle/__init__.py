@@ -1,0 +1,171 @@
+"""ctypes bindings for the CPU oracle (TEST INFRASTRUCTURE -- see oracle/orb_oracle.cpp header).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this package.  The product package ``airdos_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+assert KP_DTYPE.itemsize == 24
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle shared libraries with the committed Makefile."""
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-j4"], stdout=subprocess.DEVNULL)
+
+
+_libs = {}
+
+
+def _load(name: str) -> C.CDLL:
+    if name not in _libs:
+        path = os.path.join(_BUILD, name)
+        if not os.path.exists(path):
+            build()
+        _libs[name] = C.CDLL(path)
+    return _libs[name]
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------
+# ORB extractor oracle
+def orb_lib() -> C.CDLL:
+    lib = _load("liborb_oracle.so")
+    if not getattr(lib, "_typed", False):
+        lib.orb_oracle_fast_atan2.restype = C.c_float
+        lib.orb_oracle_fast_atan2.argtypes = [C.c_float, C.c_float]
+        lib.orb_oracle_extract_batch.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                                 C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.orb_oracle_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.orb_oracle_params.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        lib._typed = True
+    return lib
+
+
+def border101(src: np.ndarray, b: int = 19) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    orb_lib().orb_oracle_border101(_p(src), w, h, w, _p(dst), w + 2 * b, b)
+    return dst
+
+
+def erode10(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros_like(src)
+    orb_lib().orb_oracle_erode10(_p(src), w, h, w, _p(dst), w)
+    return dst
+
+
+def resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros((dh, dw), np.uint8)
+    orb_lib().orb_oracle_resize(_p(src), w, h, w, _p(dst), dw, dh, dw)
+    return dst
+
+
+def blur7(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros_like(src)
+    orb_lib().orb_oracle_blur7(_p(src), w, h, w, _p(dst), w)
+    return dst
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(orb_lib().orb_oracle_fast_atan2(float(y), float(x)))
+
+
+def fast(img: np.ndarray, threshold: int, mask: np.ndarray | None = None) -> np.ndarray:
+    """cv::FastFeatureDetector(threshold, True).detect(img, mask) -> int32 [n, 3] (x, y, score)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = max(16, w * h // 4)
+    out = np.zeros((cap, 3), np.int32)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+    n = orb_lib().orb_oracle_fast(_p(img), w, h, w, int(threshold), _p(mask) if mask is not None else None,
+                                  w, _p(out), cap)
+    return out[:n].copy()
+
+
+def distribute(cand: np.ndarray, min_x: int, max_x: int, min_y: int, max_y: int, n: int) -> np.ndarray:
+    """DistributeOctTree on float32 [m, 3] (x, y, response) -> float32 [k, 3] in the reference's list order."""
+    cand = np.ascontiguousarray(cand, np.float32)
+    cap = max(len(cand), 1) + 8
+    out = np.zeros((cap, 3), np.float32)
+    k = orb_lib().orb_oracle_distribute(_p(cand), len(cand), min_x, max_x, min_y, max_y, int(n), _p(out), cap)
+    return out[:k].copy()
+
+
+def orb_params(nfeatures: int, scale: float, nlevels: int, w: int, h: int):
+    lw = np.zeros(nlevels, np.int32); lh = np.zeros(nlevels, np.int32); q = np.zeros(nlevels, np.int32)
+    sc = np.zeros(nlevels, np.float32); um = np.zeros(16, np.int32)
+    orb_lib().orb_oracle_params(nfeatures, scale, nlevels, w, h, _p(lw), _p(lh), _p(q), _p(sc), _p(um))
+    return {"w": lw, "h": lh, "quota": q, "scale": sc, "umax": um}
+
+
+def orb_extract(img: np.ndarray, mask: np.ndarray | None = None, nfeatures: int = 1000, scale: float = 1.2,
+                nlevels: int = 8, ini_th: int = 20, min_th: int = 7, want_pyramid: bool = False):
+    """Full ORBextractor::operator() restatement.  Returns dict(kps, desc[, pyramid, cand_counts])."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = nfeatures + 8 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    cand = np.zeros(nlevels, np.int32)
+    pyr = None
+    if want_pyramid:
+        p = orb_params(nfeatures, scale, nlevels, w, h)
+        pyr = np.zeros(int((p["w"].astype(np.int64) * p["h"]).sum()), np.uint8)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+        assert mask.shape == img.shape
+    n = orb_lib().orb_oracle_extract(_p(img), w, h, w, _p(mask) if mask is not None else None, w,
+                                     nfeatures, scale, nlevels, ini_th, min_th, _p(kps), _p(desc), cap,
+                                     _p(pyr) if pyr is not None else None, _p(cand))
+    if n < 0:
+        raise RuntimeError("oracle key-point capacity exceeded")
+    out = {"kps": kps[:n].copy(), "desc": desc[:n].copy(), "cand_counts": cand}
+    if want_pyramid:
+        levels, o = [], 0
+        for l in range(nlevels):
+            sz = int(p["w"][l]) * int(p["h"][l])
+            levels.append(pyr[o:o + sz].reshape(int(p["h"][l]), int(p["w"][l])))
+            o += sz
+        out["pyramid"] = levels
+    return out
+
+
+def orb_extract_batch(imgs: np.ndarray, nfeatures: int, scale: float, nlevels: int, ini_th: int, min_th: int,
+                      threads: int = 1):
+    """imgs: u8 [F, H, W] contiguous.  Returns (kps [F, cap], desc [F, cap, 32], counts [F])."""
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    f, h, w = imgs.shape
+    cap = nfeatures + 8 * nlevels + 64
+    kps = np.zeros((f, cap), KP_DTYPE)
+    desc = np.zeros((f, cap, 32), np.uint8)
+    counts = np.zeros(f, np.int32)
+    orb_lib().orb_oracle_extract_batch(_p(imgs), f, h * w, w, h, w, nfeatures, scale, nlevels, ini_th, min_th,
+                                       _p(kps), _p(desc), cap, _p(counts), threads)
+    return kps, desc, counts
