@@ -1,0 +1,96 @@
+"""ctypes binding of libairdos_b200.so (the C-ABI in include/airdos_b200.h).
+
+This is the only way Python reaches the CUDA path; there is no fallback.  If the shared
+library is missing the import raises, and on a machine without a B200 every ``*_create``
+returns ADB_ERR_NO_DEVICE, which is surfaced as :class:`AdbError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libairdos_b200.so")
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_NOT_POSDEF, ERR_STOPPED = range(7)
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+assert KP_DTYPE.itemsize == 24
+
+
+class AdbError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"libairdos_b200 status {status}: {msg}")
+        self.status = status
+
+
+class OrbConfig(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+# every symbol include/airdos_b200.h declares: name -> (restype, argtypes)
+_vp, _i32, _f32, _sz = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
+_ip = C.POINTER(C.c_int32)
+_fp = C.POINTER(C.c_float)
+SYMBOLS = {
+    "adb_last_error": (C.c_char_p, []),
+    "adb_version": (C.c_int, []),
+    "adb_device_count": (C.c_int, []),
+    "adb_orb_create": (C.c_int, [C.POINTER(OrbConfig), C.POINTER(_vp)]),
+    "adb_orb_destroy": (C.c_int, [_vp]),
+    "adb_orb_levels": (_i32, [_vp]),
+    "adb_orb_capacity": (_i32, [_vp]),
+    "adb_orb_level_info": (C.c_int, [_vp, _i32, _ip, _ip, _ip, _fp, _fp, _fp, _fp, _ip]),
+    "adb_orb_extract": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _ip]),
+    "adb_orb_extract_batch": (C.c_int, [_vp, _i32, _vp, _sz, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _vp, _i32, _vp]),
+    "adb_orb_extract_batch_device": (C.c_int, [_vp, _i32, _vp, _sz, _i32, _i32, _i32, _vp, _sz, _i32]),
+    "adb_orb_sync": (C.c_int, [_vp]),
+    "adb_orb_stream": (_vp, [_vp]),
+    "adb_orb_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _ip]),
+    "adb_orb_download": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "adb_orb_get_pyramid": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32]),
+    "adb_orb_debug_candidates": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _ip]),
+    "adb_hamming_distance": (_i32, [_vp, _vp]),
+    "adb_matcher_create": (C.c_int, [_i32, C.POINTER(_vp)]),
+    "adb_matcher_destroy": (C.c_int, [_vp]),
+    "adb_match_best2": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "adb_match_best2_device": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "adb_stereo_match": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
+    "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),
+    "adb_stereo_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (raises if it has not been built: run ``make -C airdos_b200/csrc``
+    or ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: the CUDA extension has not been built, and there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)   # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise AdbError(status, lib().adb_last_error().decode(errors="replace"))
+
+
+def ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))

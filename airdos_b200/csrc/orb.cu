@@ -1,0 +1,1218 @@
+// orb.cu -- batched ORB extractor for sm_100a behind the C-ABI of include/airdos_b200.h.
+//
+// Replaces ORB_SLAM2::ORBextractor (src/ORBextractor.cc) for a batch of F frames:
+//
+//   pyr_resize_kernel        ComputePyramid                src/ORBextractor.cc:1121-1156
+//   fast_cells_kernel        per-cell FAST + ini/min rule  src/ORBextractor.cc:791-840
+//   quadtree_kernel          DistributeOctTree             src/ORBextractor.cc:541-765
+//   orient_describe_kernel   IC_Angle + GaussianBlur + computeOrbDescriptor
+//                                                          src/ORBextractor.cc:78-148, 1099-1104
+//
+// None of these is a translation of the reference's loops: the per-cell detector objects
+// become one CTA per cell fed by a TMA box load, the std::list quad-tree becomes a level
+// synchronous pass over a flat key array with node ids equal to the reference's creation
+// order (which is what fixes its output order), and the whole-level blur becomes a 43x43
+// patch staged by TMA per key-point.  The arithmetic (fixed-point resize and blur, FAST score,
+// float32 atan polynomial without contraction) is the one pinned in oracle/orb_oracle.cpp.
+//
+// Data layout in HBM: level l of all frames is one [max_batch][h_l][pitch_l] u8 array, pitch a
+// multiple of 16 B so each level is a 3-D TMA tensor {w, h, frame}.  No 19-px border is stored:
+// nothing on this path reads it (FAST starts at pixel 19; IC-angle / rBRIEF stay inside the
+// ROI; the blur reflects at the ROI edge because the reference blurs a clone of the ROI).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+
+#include "orb.cuh"
+#include "../../include/airdos_orb_pattern.h"
+
+namespace adb {
+
+// =========================================================================================
+// Pyramid: cv::resize INTER_LINEAR u8 (11-bit fixed point), oracle/orb_oracle.cpp:94-130.
+// One thread makes 4 horizontally adjacent output pixels (one 32-bit store).
+__global__ void __launch_bounds__(128) pyr_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                         size_t sfstride, uint8_t* __restrict__ dst, int dw, int dh,
+                                                         int dpitch, size_t dfstride, const int2* __restrict__ xtab,
+                                                         const int2* __restrict__ ytab) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= dw) return;
+    const int f = blockIdx.z;
+    const int2 cy = __ldg(&ytab[y]);
+    const int sy0 = cy.x, sy1 = min(sy0 + 1, sh - 1);
+    const int b0 = cy.y & 0xFFFF, b1 = cy.y >> 16;
+    const uint8_t* s0 = src + (size_t)f * sfstride + (size_t)sy0 * spitch;
+    const uint8_t* s1 = src + (size_t)f * sfstride + (size_t)sy1 * spitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        if (x < dw) {
+            const int2 cx = __ldg(&xtab[x]);
+            const int sx0 = cx.x, sx1 = min(sx0 + 1, sw - 1);
+            const int a0 = cx.y & 0xFFFF, a1 = cx.y >> 16;
+            const int r0 = (int)__ldg(s0 + sx0) * a0 + (int)__ldg(s0 + sx1) * a1;
+            const int r1 = (int)__ldg(s1 + sx0) * a0 + (int)__ldg(s1 + sx1) * a1;
+            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xFF) << (8 * k);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)f * dfstride + (size_t)y * dpitch + x4) = out;
+}
+
+// cv::erode(mask, ones(10,10)), anchor (5,5), outside = 255.  oracle/orb_oracle.cpp:70-92.  Parity-only path.
+__global__ void erode10_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, size_t sfstride,
+                               uint8_t* __restrict__ dst, int dpitch, size_t dfstride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= w) return;
+    const uint8_t* s = src + (size_t)f * sfstride;
+    int m = 255;
+    for (int dy = -5; dy <= 4; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dx = -5; dx <= 4; ++dx) {
+            const int xx = x + dx;
+            if (xx >= 0 && xx < w) m = min(m, (int)s[(size_t)yy * spitch + xx]);
+        }
+    }
+    dst[(size_t)f * dfstride + (size_t)y * dpitch + x] = (uint8_t)m;
+}
+
+// =========================================================================================
+// FAST-9/16 per cell.  One CTA per (cell, frame): the (cell + 6 px) tile arrives through one TMA
+// box load; scores only for the cell's own pixels (the 3-px frame of the sub-image is never
+// tested and counts as 0 in the NMS, which is what makes the reference's NMS blind across
+// cell seams); strict 3x3 NMS; mask post-filter; the ini / min threshold rule; row-major
+// ordered compaction into the cell's slot.
+struct MaskPtrs {
+    const uint8_t* p[kMaxLevels];
+};
+
+__device__ __forceinline__ bool has_run9(uint32_t m16) {
+    uint32_t x = m16 | (m16 << 16);
+    x &= x >> 1;
+    x &= x >> 2;
+    x &= x >> 4;   // bit i: bits i..i+7 set
+    x &= x >> 1;   // bits i..i+8 set
+    return (x & 0xFFFFu) != 0;
+}
+
+// max over the 16 circular windows of 9 of min(d) and of min(-d)
+__device__ __forceinline__ int fast_best(const int (&d)[16]) {
+    int lo2[16], hi2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo2[i] = min(d[i], d[(i + 1) & 15]); hi2[i] = max(d[i], d[(i + 1) & 15]); }
+    int lo4[16], hi4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo4[i] = min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = max(hi2[i], hi2[(i + 2) & 15]); }
+    int bestLo = -256, minHi = 256;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        bestLo = max(bestLo, min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]));
+        minHi = min(minHi, max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]));
+    }
+    // max(bestLo, -minHi), written as a select: ptxas 12.9 drops the negation when it folds
+    // max(a, -b) into a 3-input VIMNMX3 on sm_100a (measured, tools/probe/fast_probe2.cu).
+    const int best = (bestLo + minHi > 0) ? bestLo : (0 - minHi);
+    return best;
+}
+
+constexpr int kFastThreads = 256;
+
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ TmaMaps16 maps,
+                                                                 const LevelDev* __restrict__ levels,
+                                                                 const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
+                                                                 int ini_th, int min_th, uint32_t* __restrict__ cand,
+                                                                 int cand_total, uint16_t* __restrict__ cellcnt,
+                                                                 int ncells_total) {
+    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kCellBoxWMax];
+    __shared__ __align__(16) uint8_t score[kCellBoxHMax * kCellBoxWMax];
+    __shared__ uint64_t bar;
+    __shared__ int warp_tot[kFastThreads / 32];
+
+    const int tid = threadIdx.x, f = blockIdx.y;
+    const uint32_t ce = __ldg(&cell_table[blockIdx.x]);
+    const int level = ce >> 24, ci = (ce >> 12) & 0xFFF, cj = ce & 0xFFF;
+    const LevelDev& L = levels[level];
+    const int maxBX = L.w - kMinBorder, maxBY = L.h - kMinBorder;
+    const int iniY = kMinBorder + ci * L.hcell, iniX = kMinBorder + cj * L.wcell;
+    const int maxY = min(iniY + L.hcell + 6, maxBY), maxX = min(iniX + L.wcell + 6, maxBX);
+    const int cw = maxX - iniX, ch = maxY - iniY;
+    uint16_t* cnt_out = cellcnt + (size_t)f * ncells_total + blockIdx.x;
+    if (iniY >= maxBY - 3 || iniX >= maxBX - 6 || cw < 7 || ch < 7) {   // the reference's `continue`s
+        if (tid == 0) *cnt_out = 0;
+        return;
+    }
+    const int bw = L.box_w, bh = L.box_h;
+#ifdef ADB_FAST_NO_TMA
+    {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(masks.p[8 + level]) + (size_t)f * L.frame_stride;
+        for (int i = tid; i < bw * bh; i += kFastThreads) {
+            const int r = i / bw, cc = i - r * bw;
+            const int gx = (iniX & ~15) + cc, gy = iniY + r;
+            tile[i] = (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) ? src[(size_t)gy * L.pitch + gx] : 0;
+        }
+    }
+    if (false) {
+#else
+    if (tid == 0) {
+#endif
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+        mbar_expect_tx(&bar, (uint32_t)(bw * bh));
+        tma_load_3d(tile, &maps.m[level], &bar, iniX & ~15, iniY, f);   // box origin must be 16-B aligned in x
+    }
+    const int dx = iniX & 15;
+    // clear the score tile while the box is in flight
+    for (int i = tid; i < (bw * bh + 3) / 4; i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    __syncthreads();   // barrier init visible to all waiters
+#ifndef ADB_FAST_NO_TMA
+    mbar_wait(&bar, 0);
+#endif
+
+    const int iw = cw - 6, ih = ch - 6, npx = iw * ih;
+    const int t_low = min(ini_th, min_th);
+    for (int p = tid; p < npx; p += kFastThreads) {
+        const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+        const uint8_t* c = tile + y * bw + x + dx;
+        const int v = c[0];
+        int d[16];
+        // OpenCV circle order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+        d[0] = v - c[3 * bw];      d[1] = v - c[3 * bw + 1];  d[2] = v - c[2 * bw + 2];   d[3] = v - c[bw + 3];
+        d[4] = v - c[3];           d[5] = v - c[-bw + 3];     d[6] = v - c[-2 * bw + 2];  d[7] = v - c[-3 * bw + 1];
+        d[8] = v - c[-3 * bw];     d[9] = v - c[-3 * bw - 1]; d[10] = v - c[-2 * bw - 2]; d[11] = v - c[-bw - 3];
+        d[12] = v - c[-3];         d[13] = v - c[bw - 3];     d[14] = v - c[2 * bw - 2];  d[15] = v - c[3 * bw - 1];
+        uint32_t hi = 0, lo = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { hi |= (uint32_t)(d[i] > t_low) << i; lo |= (uint32_t)(d[i] < -t_low) << i; }
+        if (has_run9(hi) || has_run9(lo)) {
+            const int best = fast_best(d);
+            score[y * bw + x] = (uint8_t)(best - 1);   // response = best - 1 (0 never survives the NMS)
+        }
+    }
+    __syncthreads();
+
+    // NMS + mask; bit k of flags* = pixel tid + k*256
+    uint32_t flagsA = 0, flagsB = 0;
+    const uint8_t* ml = masks.p[level];
+    for (int k = 0, p = tid; p < npx; ++k, p += kFastThreads) {
+        const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+        const uint8_t* s = score + y * bw + x;
+        const int v = s[0];
+        if (v == 0) continue;
+        const bool peak = v > s[-1] && v > s[1] && v > s[-bw - 1] && v > s[-bw] && v > s[-bw + 1] && v > s[bw - 1] &&
+                          v > s[bw] && v > s[bw + 1];
+        if (!peak) continue;
+        if (ml && ml[(size_t)f * L.mframe_stride + (size_t)(iniY + y) * L.mpitch + iniX + x] == 0) continue;
+        if (v >= min_th) flagsA |= 1u << k;   // best > minTh
+        if (v >= ini_th) flagsB |= 1u << k;   // best > iniTh
+    }
+    const int anyB = __syncthreads_or(flagsB != 0);
+    const uint32_t sel = anyB ? flagsB : flagsA;
+    uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(blockIdx.x - L.cell_base) * L.slotcap;
+    const int lane = tid & 31, warp = tid >> 5;
+    int base = 0;
+    for (int k = 0; k * kFastThreads < npx; ++k) {
+        const bool pred = (sel >> k) & 1u;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pred);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kFastThreads / 32; ++w) {
+            const int t = warp_tot[w];
+            if (w < warp) off += t;
+            tot += t;
+        }
+        if (pred) {
+            const int p = tid + k * kFastThreads;
+            const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+            const int o = off + __popc(bal & ((1u << lane) - 1u));
+            if (o < L.slotcap)   // cannot trigger: slotcap is the strict-NMS bound
+                slot[o] = (uint32_t)(x + cj * L.wcell) | ((uint32_t)(y + ci * L.hcell) << 12) | ((uint32_t)score[y * bw + x] << 24);
+        }
+        base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) *cnt_out = (uint16_t)min(base, L.slotcap);
+}
+
+// =========================================================================================
+// Quad-tree distribution, one CTA per (level, frame).
+//
+// The reference keeps a std::list of nodes, pushes children to the front and erases parents
+// (src/ORBextractor.cc:596-741).  Two facts make a flat restatement possible:
+//   (1) the list is always sorted by node creation order, newest first (roots, pushed to the
+//       back in ascending order, are the only exception and stay at the tail), so the output
+//       order is "creation sequence descending";
+//   (2) after every pass the nodes that can still be split are exactly the children created in
+//       that pass with more than one key.
+// So each pass only needs, for the current set of splittable ("active") nodes, the four child
+// counts, the processing order (list order while the tree is far from the quota; (count, seq)
+// descending with an early stop once the next pass could overshoot), and a prefix sum that
+// hands out creation sequence numbers.  Keys never move: each carries (active slot, node seq).
+// Tie-break of the reference's (count, pointer) sort = creation sequence.
+constexpr int kQtThreads = 512;
+constexpr uint32_t kQtFinal = 0xFFFu;
+
+struct QtShared {
+    int na, nf, size, next_seq, mode, first, cur, done, kstar, tot_ch, tot_ex, ncand;
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __restrict__ levels, int nlevels,
+                                                             const uint32_t* __restrict__ cand, int cand_total,
+                                                             const uint16_t* __restrict__ cellcnt, int ncells_total,
+                                                             uint32_t* __restrict__ qkeys, uint32_t* __restrict__ qstate,
+                                                             int32_t* __restrict__ qcount, uint32_t* __restrict__ list,
+                                                             int list_total, int32_t* __restrict__ listcnt, int maxa,
+                                                             int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t qt_smem[];
+    // carve dynamic shared memory
+    short4* bnd0 = reinterpret_cast<short4*>(qt_smem);            // [2][maxa] node bounds ulx,uly,brx,bry
+    uint32_t* nseq0 = reinterpret_cast<uint32_t*>(bnd0 + 2 * maxa);   // [2][maxa]
+    uint32_t* ncnt0 = nseq0 + 2 * maxa;                                // [2][maxa]
+    uint32_t* child = ncnt0 + 2 * maxa;                                // [4*maxa] child counts, then child (slot,seq) map
+    uint32_t* sc_ch = child + 4 * maxa;                                // [maxa] exclusive scans in processing order
+    uint32_t* sc_ex = sc_ch + maxa;                                    // [maxa]
+    uint32_t* fseq = sc_ex + maxa;                                     // [maxa] final node seqs / sorted
+    uint32_t* best = fseq + maxa;                                      // [maxa]
+    uint32_t* fsorted = best + maxa;                                   // [maxa]
+    uint16_t* rank = reinterpret_cast<uint16_t*>(fsorted + maxa);     // [maxa] processing position of slot
+    uint16_t* r_slot = rank + maxa;                                    // [maxa] inverse
+    uint8_t* r_nch = reinterpret_cast<uint8_t*>(r_slot + maxa);        // [maxa] nonempty children, by rank
+    uint8_t* r_nex = r_nch + maxa;                                     // [maxa] children with > 1 key, by rank
+    __shared__ QtShared S;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int level = blockIdx.x, f = blockIdx.y;
+    const LevelDev& L = levels[level];
+    const uint32_t* cslots = cand + (size_t)f * cand_total + L.cand_base;
+    const uint16_t* ccnt = cellcnt + (size_t)f * ncells_total + L.cell_base;
+    uint32_t* keys = qkeys + (size_t)f * cand_total + L.cand_base;
+    uint32_t* state = qstate + (size_t)f * cand_total + L.cand_base;
+    uint32_t* out = list + (size_t)f * list_total + L.list_base;
+    const int N = L.quota, nIni = L.n_ini;
+
+    // ---- gather the cells' candidates in the reference's order (cell row-major, then pixel row-major)
+    // exclusive scan of the cell counts by warp 0 into `state` scratch (reused afterwards)
+    if (warp == 0) {
+        int run = 0;
+        for (int c0 = 0; c0 < L.ncells; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < L.ncells ? (int)ccnt[c] : 0;
+            const int inc = warp_incl_scan(v, lane);
+            if (c < L.ncells) state[c] = (uint32_t)(run + inc - v);   // cell offsets live in state[0..ncells)
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) S.ncand = run;
+    }
+    __syncthreads();
+    const int ncand = S.ncand;
+    if (tid == 0) qcount[f * nlevels + level] = ncand;
+    if (ncand == 0 || nIni <= 0) {
+        if (tid == 0) listcnt[f * nlevels + level] = 0;
+        return;
+    }
+    // cell offsets live in state[0..ncells) (ncells <= cand_cap); the gather writes keys[] only
+    for (int c = warp; c < L.ncells; c += kQtThreads / 32) {
+        const int n = ccnt[c];
+        const uint32_t o = state[c];
+        const uint32_t* src = cslots + (size_t)c * L.slotcap;
+        for (int s = lane; s < n; s += 32) keys[o + s] = src[s];
+    }
+    __syncthreads();
+
+    // ---- roots (src/ORBextractor.cc:547-590)
+    auto bnd = [&](int b) { return bnd0 + b * maxa; };
+    auto nseq = [&](int b) { return nseq0 + b * maxa; };
+    auto ncnt = [&](int b) { return ncnt0 + b * maxa; };
+    const float hx = L.hx;
+    const int bry_root = (L.h - kMinBorder) - kMinBorder;
+    for (int i = tid; i < nIni; i += kQtThreads) child[i] = 0;
+    __syncthreads();
+    if (nIni == 1) {
+        if (tid == 0) child[0] = (uint32_t)ncand;
+        for (int k = tid; k < ncand; k += kQtThreads) state[k] = 0;   // root index, fixed up below
+    } else {
+        for (int k = tid; k < ncand; k += kQtThreads) {
+            const int x = keys[k] & 0xFFF;
+            int r = (int)__fdiv_rn((float)x, hx);
+            r = min(r, nIni - 1);
+            atomicAdd(&child[r], 1u);
+            state[k] = (uint32_t)r;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int na = 0, nf = 0, size = 0;
+        for (int i = 0; i < nIni; ++i) {
+            const uint32_t c = child[i];
+            if (c == 0) { child[i] = 0xFFFFFFFFu; continue; }
+            ++size;
+            if (c == 1) {
+                fseq[nf++] = (uint32_t)i;
+                child[i] = (kQtFinal << 20) | (uint32_t)i;
+            } else {
+                bnd(0)[na] = make_short4((short)(int)__fmul_rn(hx, (float)i), 0, (short)(int)__fmul_rn(hx, (float)(i + 1)), (short)bry_root);
+                nseq(0)[na] = (uint32_t)i;
+                ncnt(0)[na] = c;
+                child[i] = ((uint32_t)na << 20) | (uint32_t)i;
+                ++na;
+            }
+        }
+        S.na = na; S.nf = nf; S.size = size; S.next_seq = nIni; S.mode = 0; S.first = 1; S.cur = 0; S.done = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < ncand; k += kQtThreads) state[k] = child[state[k]];
+    __syncthreads();
+
+    // ---- passes
+    int guard = 0;
+    while (true) {
+        const int na = S.na, cur = S.cur, mode = S.mode, first = S.first, size = S.size;
+        if (na == 0 || S.done) break;
+        if (++guard > 64) {   // cannot happen for distinct integer pixels; never loop forever on the device
+            if (tid == 0) atomicExch(status, 2);
+            break;
+        }
+        const short4* B = bnd(cur);
+        for (int i = tid; i < 4 * na; i += kQtThreads) child[i] = 0;
+        __syncthreads();
+        // child counts
+        for (int k = tid; k < ncand; k += kQtThreads) {
+            const uint32_t st = state[k];
+            const uint32_t s = st >> 20;
+            if (s == kQtFinal) continue;
+            const uint32_t key = keys[k];
+            const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
+            const short4 b = B[s];
+            const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+            const int q = (x < mx) ? (y < my ? 0 : 2) : (y < my ? 1 : 3);
+            atomicAdd(&child[4 * s + q], 1u);
+        }
+        __syncthreads();
+        // processing order
+        for (int s = tid; s < na; s += kQtThreads) {
+            int r;
+            if (mode == 0) {
+                r = first ? s : na - 1 - s;
+            } else {
+                const uint32_t c = ncnt(cur)[s], q = nseq(cur)[s];
+                r = 0;
+                for (int t = 0; t < na; ++t) {
+                    const uint32_t ct = ncnt(cur)[t], qt = nseq(cur)[t];
+                    r += (ct > c) || (ct == c && qt > q);
+                }
+            }
+            rank[s] = (uint16_t)r;
+            r_slot[r] = (uint16_t)s;
+            int nch = 0, nex = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const uint32_t c = child[4 * s + q]; nch += c > 0; nex += c > 1; }
+            r_nch[r] = (uint8_t)nch;
+            r_nex[r] = (uint8_t)nex;
+        }
+        __syncthreads();
+        // scans in processing order + stop position (warp 0)
+        if (warp == 0) {
+            int run_ch = 0, run_ex = 0, kstar = na - 1, found = 0;
+            for (int r0 = 0; r0 < na; r0 += 32) {
+                const int r = r0 + lane;
+                const int vch = r < na ? (int)r_nch[r] : 0, vex = r < na ? (int)r_nex[r] : 0;
+                const int ich = warp_incl_scan(vch, lane), iex = warp_incl_scan(vex, lane);
+                if (r < na) { sc_ch[r] = (uint32_t)(run_ch + ich - vch); sc_ex[r] = (uint32_t)(run_ex + iex - vex); }
+                if (mode == 1 && !found) {
+                    const bool hit = r < na && (size + run_ch + ich - (r + 1) >= N);
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (bal) { kstar = r0 + __ffs(bal) - 1; found = 1; }
+                }
+                run_ch += __shfl_sync(0xFFFFFFFFu, ich, 31);
+                run_ex += __shfl_sync(0xFFFFFFFFu, iex, 31);
+            }
+            if (lane == 0) S.kstar = kstar;
+        }
+        __syncthreads();
+        const int kstar = S.kstar;
+        if (tid == 0) {
+            S.tot_ch = (int)sc_ch[kstar] + r_nch[kstar];
+            S.tot_ex = (int)sc_ex[kstar] + r_nex[kstar];
+        }
+        const int next_seq = S.next_seq;
+        // create children
+        const int nxt = cur ^ 1;
+        for (int s = tid; s < na; s += kQtThreads) {
+            const int r = rank[s];
+            if (r > kstar) {   // left unsplit by the early stop: stays in the list as it is
+                const int fi = atomicAdd(&S.nf, 1);
+                fseq[fi] = nseq(cur)[s];
+                continue;
+            }
+            const short4 b = B[s];
+            const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+            uint32_t cseq = (uint32_t)next_seq + sc_ch[r];
+            uint32_t nslot = sc_ex[r];
+            uint32_t c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = child[4 * s + q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c[q] == 0) { child[4 * s + q] = 0; continue; }
+                if (c[q] > 1) {
+                    short4 nb;
+                    nb.x = (q & 1) ? (short)mx : b.x;
+                    nb.z = (q & 1) ? b.z : (short)mx;
+                    nb.y = (q & 2) ? (short)my : b.y;
+                    nb.w = (q & 2) ? b.w : (short)my;
+                    bnd(nxt)[nslot] = nb;
+                    nseq(nxt)[nslot] = cseq;
+                    ncnt(nxt)[nslot] = c[q];
+                    child[4 * s + q] = (nslot << 20) | cseq;
+                    ++nslot;
+                } else {
+                    const int fi = atomicAdd(&S.nf, 1);
+                    fseq[fi] = cseq;
+                    child[4 * s + q] = (kQtFinal << 20) | cseq;
+                }
+                ++cseq;
+            }
+        }
+        __syncthreads();
+        // move the keys
+        for (int k = tid; k < ncand; k += kQtThreads) {
+            const uint32_t st = state[k];
+            const uint32_t s = st >> 20;
+            if (s == kQtFinal) continue;
+            if ((int)rank[s] > kstar) {
+                state[k] = (kQtFinal << 20) | (st & 0xFFFFFu);
+                continue;
+            }
+            const uint32_t key = keys[k];
+            const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
+            const short4 b = B[s];
+            const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+            const int q = (x < mx) ? (y < my ? 0 : 2) : (y < my ? 1 : 3);
+            state[k] = child[4 * s + q];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int nsplit = kstar + 1;
+            const int new_size = size - nsplit + S.tot_ch;
+            const int n_exp = S.tot_ex;
+            S.next_seq = next_seq + S.tot_ch;
+            S.size = new_size;
+            S.na = n_exp;
+            S.cur = nxt;
+            S.first = 0;
+            if (new_size >= N || new_size == size) S.done = 1;
+            else if (mode == 0 && new_size + n_exp * 3 > N) S.mode = 1;
+            if (S.nf + n_exp > maxa || S.next_seq >= (1 << 20)) { atomicExch(status, 3); S.done = 1; S.na = 0; }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // remaining splittable nodes stay in the list
+    {
+        const int na = S.na, cur = S.cur;
+        const int nf = S.nf + na;
+        for (int s = tid; s < na; s += kQtThreads) fseq[nf - na + s] = nseq(cur)[s];
+        __syncthreads();
+        // ---- order = list order: creation sequence descending, roots (ascending) at the tail
+        for (int i = tid; i < nf; i += kQtThreads) {
+            const uint32_t qi = fseq[i];
+            const uint32_t ki = qi >= (uint32_t)nIni ? qi : (uint32_t)(nIni - 1) - qi;
+            int r = 0;
+            for (int j = 0; j < nf; ++j) {
+                const uint32_t qj = fseq[j];
+                const uint32_t kj = qj >= (uint32_t)nIni ? qj : (uint32_t)(nIni - 1) - qj;
+                r += kj > ki;
+            }
+            fsorted[r] = ki;
+            best[r] = 0;
+        }
+        __syncthreads();
+        // max response per node, first key in candidate order wins ties (src/ORBextractor.cc:745-762)
+        for (int k = tid; k < ncand; k += kQtThreads) {
+            const uint32_t q = state[k] & 0xFFFFFu;
+            const uint32_t kq = q >= (uint32_t)nIni ? q : (uint32_t)(nIni - 1) - q;
+            int lo = 0, hi = nf - 1;   // fsorted is descending
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (fsorted[mid] > kq) lo = mid + 1; else hi = mid;
+            }
+            atomicMax(&best[lo], ((keys[k] >> 24) << 24) | (0xFFFFFFu - (uint32_t)k));
+        }
+        __syncthreads();
+        const int nout = min(nf, L.list_cap);
+        for (int r = tid; r < nout; r += kQtThreads) {
+            const uint32_t k = 0xFFFFFFu - (best[r] & 0xFFFFFFu);
+            const uint32_t key = keys[k];
+            const uint32_t x = (key & 0xFFF) + kMinBorder, y = ((key >> 12) & 0xFFF) + kMinBorder;
+            out[r] = x | (y << 12) | (key & 0xFF000000u);
+        }
+        if (tid == 0) {
+            listcnt[f * nlevels + level] = nout;
+            if (nf > L.list_cap) atomicExch(status, 4);
+        }
+    }
+}
+
+// =========================================================================================
+// Orientation + descriptor, one warp per key-point.  A 48 x 43-byte box around the key-point
+// arrives by TMA (out-of-image bytes zero-filled, then mirrored per BORDER_REFLECT_101 at the
+// ROI edge); IC-angle on the raw patch; 7x7 fixed-point Gaussian on the 37 x 37 core; the 256
+// rotated tests read the blurred core.
+constexpr int kDescWarps = 8;
+constexpr int kRawBytes = 2816;          // 43 rows x 64 B, padded to a multiple of 128 B
+constexpr int kHPitch = 40;              // u16 row-pass buffer: 43 rows x 40
+constexpr int kBPitch = 40;              // blurred core: 37 rows x 40
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// cv::fastAtan2 in degrees, every operation rounded to float32, no contraction (oracle/orb_oracle.cpp:153-177)
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, s), p3 = __fmul_rn(-0.3258083974640975f, s);
+    const float p5 = __fmul_rn(0.1555786518463281f, s), p7 = __fmul_rn(-0.04432655554792128f, s);
+    const float eps = (float)DBL_EPSILON;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        float t = __fmul_rn(p7, c2); t = __fadd_rn(t, p5); t = __fmul_rn(t, c2); t = __fadd_rn(t, p3);
+        t = __fmul_rn(t, c2); t = __fadd_rn(t, p1);
+        a = __fmul_rn(t, c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        float t = __fmul_rn(p7, c2); t = __fadd_rn(t, p5); t = __fmul_rn(t, c2); t = __fadd_rn(t, p3);
+        t = __fmul_rn(t, c2); t = __fadd_rn(t, p1);
+        t = __fmul_rn(t, c);
+        a = __fsub_rn(90.f, t);
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (p < 0) p = -p;
+    if (p >= len) p = 2 * (len - 1) - p;
+    return p;
+}
+
+struct DescSmem {
+    uint8_t raw[kDescWarps][kRawBytes];
+    uint16_t hrow[kDescWarps][kPatchBoxH * kHPitch];
+    uint8_t blur[kDescWarps][37 * kBPitch];
+    char2 pat[16 * 32];
+    uint64_t bar[kDescWarps];
+};
+
+__global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const __grid_constant__ TmaMaps16 maps,
+                                                                         const LevelDev* __restrict__ levels, int nlevels,
+                                                                         const uint32_t* __restrict__ list, int list_total,
+                                                                         const int32_t* __restrict__ listcnt,
+                                                                         const int8_t* __restrict__ pattern,
+                                                                         adb_keypoint* __restrict__ kps,
+                                                                         uint8_t* __restrict__ desc,
+                                                                         int32_t* __restrict__ counts, int cap) {
+    extern __shared__ __align__(128) uint8_t desc_smem_raw[];
+    DescSmem& sm = *reinterpret_cast<DescSmem*>((reinterpret_cast<uintptr_t>(desc_smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y;
+    for (int i = tid; i < 512; i += kDescWarps * 32) sm.pat[i] = make_char2(pattern[2 * i], pattern[2 * i + 1]);
+    if (lane == 0) mbar_init(&sm.bar[warp], 1);
+    if (tid == 0) mbar_fence_init();
+    __syncthreads();
+
+    const int i = blockIdx.x * kDescWarps + warp;
+    int base = 0, lvl = -1, total = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const int c = listcnt[f * nlevels + l];
+        if (lvl < 0 && i < total + c) { lvl = l; base = total; }
+        total += c;
+    }
+    if (i == 0 && lane == 0) counts[f] = total;
+    if (lvl < 0 || i >= cap) return;
+    const LevelDev& L = levels[lvl];
+    const uint32_t e = list[(size_t)f * list_total + L.list_base + (i - base)];
+    const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;
+
+    uint8_t* raw = sm.raw[warp];
+    uint64_t* bar = &sm.bar[warp];
+    if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, kPatchBoxW * kPatchBoxH);
+        tma_load_3d(raw, &maps.m[lvl], bar, (cx - kPatchR) & ~15, cy - kPatchR, f);   // 16-B aligned box origin
+    }
+    mbar_wait(bar, 0);
+    raw += (cx - kPatchR) & 15;   // column 0 of the 43 x 43 patch
+    // BORDER_REFLECT_101 at the ROI edge (only key-points within 21 px of it; at most 2 rows / columns)
+    const int x0 = cx - kPatchR, y0 = cy - kPatchR;
+    if (y0 < 0 || y0 + 42 >= L.h) {
+        for (int r = 0; r < kPatchBoxH; ++r) {
+            const int gy = y0 + r;
+            if (gy >= 0 && gy < L.h) continue;
+            const int sr = reflect101(gy, L.h) - y0;
+            for (int c = lane; c < 43; c += 32) raw[r * kPatchBoxW + c] = raw[sr * kPatchBoxW + c];
+        }
+        __syncwarp();
+    }
+    if (x0 < 0 || x0 + 42 >= L.w) {
+        for (int c = 0; c < 43; ++c) {
+            const int gx = x0 + c;
+            if (gx >= 0 && gx < L.w) continue;
+            const int sc = reflect101(gx, L.w) - x0;
+            for (int r = lane; r < kPatchBoxH; r += 32) raw[r * kPatchBoxW + c] = raw[r * kPatchBoxW + sc];
+        }
+        __syncwarp();
+    }
+
+    // ---- IC_Angle (src/ORBextractor.cc:78-105): m10 = sum u*I, m01 = sum v*I over the r=15 disc
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - 15, au = abs(u);
+        for (int v = -15; v <= 15; ++v) {
+            if (au <= c_umax[abs(v)]) {
+                const int val = raw[(kPatchR + v) * kPatchBoxW + kPatchR + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
+        m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- GaussianBlur 7x7 sigma 2, fixed point {18,34,48,56,48,34,18}/256 twice, (v + 2^15) >> 16
+    uint16_t* hrow = sm.hrow[warp];
+    for (int o = lane; o < kPatchBoxH * 37; o += 32) {
+        const int r = o / 37, c = o - r * 37;   // output column c <-> patch column c + 3
+        const uint8_t* p = raw + r * kPatchBoxW + c;
+        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
+        hrow[r * kHPitch + c] = (uint16_t)acc;
+    }
+    __syncwarp();
+    uint8_t* bl = sm.blur[warp];
+    for (int o = lane; o < 37 * 37; o += 32) {
+        const int r = o / 37, c = o - r * 37;
+        const uint16_t* p = hrow + r * kHPitch + c;
+        const uint32_t acc = 18u * (p[0] + p[6 * kHPitch]) + 34u * (p[kHPitch] + p[5 * kHPitch]) +
+                             48u * (p[2 * kHPitch] + p[4 * kHPitch]) + 56u * p[3 * kHPitch];
+        bl[r * kBPitch + c] = (uint8_t)((acc + 32768u) >> 16);
+    }
+    __syncwarp();
+
+    // ---- steered rBRIEF (src/ORBextractor.cc:109-148); lane = descriptor byte
+    const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* ctr = bl + 18 * kBPitch + 18;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const char2 p0 = sm.pat[(2 * k) * 32 + lane], p1 = sm.pat[(2 * k + 1) * 32 + lane];
+        const float x0f = (float)p0.x, y0f = (float)p0.y, x1f = (float)p1.x, y1f = (float)p1.y;
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0f, b), __fmul_rn(y0f, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0f, a), __fmul_rn(y0f, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1f, b), __fmul_rn(y1f, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1f, a), __fmul_rn(y1f, b)));
+        const int t0 = ctr[r0 * kBPitch + q0], t1 = ctr[r1 * kBPitch + q1];
+        byte |= (uint32_t)(t0 < t1) << k;
+    }
+    desc[((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
+    if (lane == 0) {
+        adb_keypoint kp;
+        kp.x = lvl ? __fmul_rn((float)cx, L.scale) : (float)cx;
+        kp.y = lvl ? __fmul_rn((float)cy, L.scale) : (float)cy;
+        kp.size = (float)L.patch_size;
+        kp.angle = angle;
+        kp.response = (float)resp;
+        kp.octave = lvl;
+        kps[(size_t)f * cap + i] = kp;
+    }
+}
+
+// Debug: candidates of (frame, level) in reference order -> int32 triples.
+__global__ void unpack_candidates_kernel(const uint32_t* __restrict__ keys, int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    out[3 * i] = k & 0xFFF; out[3 * i + 1] = (k >> 12) & 0xFFF; out[3 * i + 2] = k >> 24;
+}
+
+// =========================================================================================
+// Host side.
+static inline int round_even_f(float v) { return (int)nearbyintf(v); }
+
+// oracle/orb_oracle.cpp:96-110 (cv::resize coefficient rule)
+static void linear_coeffs(int src, int dst, std::vector<int2>& c) {
+    c.resize(dst);
+    const double scale = (double)src / dst;
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src - 1) { s = src - 1; f = 0.f; }
+        const int a0 = round_even_f((1.f - f) * 2048.f), a1 = round_even_f(f * 2048.f);
+        c[d] = make_int2(s, a0 | (a1 << 16));
+    }
+}
+
+static size_t qt_smem_bytes(int maxa) {
+    return (size_t)maxa * (2 * sizeof(short4) + 2 * 4 + 2 * 4 + 4 * 4 + 4 + 4 + 4 + 4 + 4 + 2 + 2 + 1 + 1) + 64;
+}
+
+static void free_handle(adb_orb* h) {
+    if (!h) return;
+    for (auto& l : h->lv) {
+        cudaFree(l.img); cudaFree(l.mask); cudaFree(l.xtab); cudaFree(l.ytab);
+    }
+    cudaFree(h->d_levels); cudaFree(h->d_cell_table); cudaFree(h->d_pattern); cudaFree(h->d_cand); cudaFree(h->d_cellcnt);
+    cudaFree(h->d_qkeys); cudaFree(h->d_qstate); cudaFree(h->d_qcount); cudaFree(h->d_list); cudaFree(h->d_listcnt);
+    cudaFree(h->d_status); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
+    cudaFree(h->d_uright); cudaFree(h->d_depth); cudaFree(h->d_best_idx); cudaFree(h->d_best_dist); cudaFree(h->d_sad);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->ev) cudaEventDestroy(h->ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
+    h->cfg = *cfg;
+    const int nl = cfg->nlevels, W = cfg->width, H = cfg->height, B = cfg->max_batch;
+    h->nlevels = nl;
+    h->lv.resize(nl);
+    // ---- scale tables and quotas: src/ORBextractor.cc:411-445
+    std::vector<float> scale(nl), inv(nl);
+    h->sigma2.resize(nl); h->inv_sigma2.resize(nl);
+    scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < nl; ++i) { scale[i] = scale[i - 1] * cfg->scale_factor; h->sigma2[i] = scale[i] * scale[i]; }
+    for (int i = 0; i < nl; ++i) { inv[i] = 1.0f / scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    std::vector<int> quota(nl);
+    {
+        const float factor = 1.0f / cfg->scale_factor;
+        float per = cfg->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; ++l) { quota[l] = round_even_f(per); sum += quota[l]; per *= factor; }
+        quota[nl - 1] = std::max(cfg->nfeatures - sum, 0);
+    }
+    int cell_base = 0, cand_base = 0, list_base = 0, maxq = 0;
+    std::vector<uint32_t> cell_table;
+    for (int l = 0; l < nl; ++l) {
+        LevelDev& d = h->lv[l].d;
+        d.w = round_even_f((float)W * inv[l]);
+        d.h = round_even_f((float)H * inv[l]);
+        ADB_CHECK(d.w >= 1 && d.h >= 1, ADB_ERR_INVALID, "level %d is empty (%dx%d)", l, d.w, d.h);
+        d.pitch = (d.w + 15) & ~15;
+        d.frame_stride = (unsigned)(d.pitch * d.h);
+        d.mpitch = d.pitch; d.mframe_stride = d.frame_stride;
+        d.scale = scale[l]; d.inv_scale = inv[l];
+        d.patch_size = (int)(31 * scale[l]);
+        d.quota = quota[l];
+        // cell grid: src/ORBextractor.cc:775-789
+        const int maxBX = d.w - kMinBorder, maxBY = d.h - kMinBorder;
+        const float width = (float)(maxBX - kMinBorder), height = (float)(maxBY - kMinBorder);
+        d.ncols = (int)(width / 30.f); d.nrows = (int)(height / 30.f);
+        if (d.ncols <= 0 || d.nrows <= 0) { d.ncols = d.nrows = 0; d.wcell = d.hcell = 1; }
+        else { d.wcell = (int)ceilf(width / d.ncols); d.hcell = (int)ceilf(height / d.nrows); }
+        d.ncells = d.ncols * d.nrows;
+        d.cell_base = cell_base;
+        d.box_w = (15 + d.wcell + 6 + 15) & ~15; d.box_h = d.hcell + 6;
+        ADB_CHECK(d.box_w <= kCellBoxWMax && d.box_h <= kCellBoxHMax, ADB_ERR_INVALID, "level %d: cell box %dx%d too large", l, d.box_w, d.box_h);
+        ADB_CHECK(d.nrows < 4096 && d.ncols < 4096 && d.w < 4096 && d.h < 4096, ADB_ERR_INVALID, "image too large (max 4095 px per side)");
+        d.slotcap = ((d.wcell + 1) / 2) * ((d.hcell + 1) / 2);
+        d.cand_base = cand_base; d.cand_cap = d.ncells * d.slotcap;
+        // quad-tree roots: src/ORBextractor.cc:545-549
+        d.n_ini = d.ncells ? (int)roundf(width / height) : 0;
+        d.hx = d.n_ini > 0 ? width / d.n_ini : 1.f;
+        d.list_base = list_base;
+        d.list_cap = std::max(d.quota + 3, 4 * std::max(d.n_ini, 1));
+        for (int i = 0; i < d.nrows; ++i)
+            for (int j = 0; j < d.ncols; ++j) cell_table.push_back(((uint32_t)l << 24) | ((uint32_t)i << 12) | (uint32_t)j);
+        cell_base += d.ncells; cand_base += d.cand_cap; list_base += d.list_cap;
+        maxq = std::max(maxq, d.list_cap);
+    }
+    h->ncells_total = cell_base; h->cand_total = std::max(cand_base, 1); h->list_total = list_base;
+    h->capacity = list_base;
+    h->qt_maxa = ((maxq + 16) + 31) & ~31;
+    ADB_CHECK(h->qt_maxa < (int)kQtFinal, ADB_ERR_INVALID, "nfeatures too large for the quad-tree node table (%d)", h->qt_maxa);
+    h->qt_smem = qt_smem_bytes(h->qt_maxa);
+    ADB_CHECK(h->qt_smem <= 200 * 1024, ADB_ERR_INVALID, "quad-tree shared memory %zu too large", h->qt_smem);
+
+    ADB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    ADB_CUDA(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
+    for (int l = 0; l < nl; ++l) {
+        LevelHost& lh = h->lv[l];
+        ADB_CUDA(cudaMalloc(&lh.img, (size_t)B * lh.d.frame_stride));
+        if (l > 0) {
+            std::vector<int2> cx, cy;
+            linear_coeffs(h->lv[l - 1].d.w, lh.d.w, cx);
+            linear_coeffs(h->lv[l - 1].d.h, lh.d.h, cy);
+            ADB_CUDA(cudaMalloc(&lh.xtab, cx.size() * sizeof(int2)));
+            ADB_CUDA(cudaMalloc(&lh.ytab, cy.size() * sizeof(int2)));
+            ADB_CUDA(cudaMemcpy(lh.xtab, cx.data(), cx.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            ADB_CUDA(cudaMemcpy(lh.ytab, cy.data(), cy.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        }
+    }
+    std::vector<LevelDev> ld(nl);
+    for (int l = 0; l < nl; ++l) ld[l] = h->lv[l].d;
+    ADB_CUDA(cudaMalloc(&h->d_levels, nl * sizeof(LevelDev)));
+    ADB_CUDA(cudaMemcpy(h->d_levels, ld.data(), nl * sizeof(LevelDev), cudaMemcpyHostToDevice));
+    ADB_CUDA(cudaMalloc(&h->d_cell_table, std::max<size_t>(cell_table.size(), 1) * 4));
+    if (!cell_table.empty()) ADB_CUDA(cudaMemcpy(h->d_cell_table, cell_table.data(), cell_table.size() * 4, cudaMemcpyHostToDevice));
+    {
+        static const signed char px[512] = AIRDOS_ORB_PATTERN_X;
+        static const signed char py[512] = AIRDOS_ORB_PATTERN_Y;
+        std::vector<int8_t> pat(1024);
+        for (int s = 0; s < 16; ++s)
+            for (int lane = 0; lane < 32; ++lane) {
+                pat[2 * (s * 32 + lane)] = px[16 * lane + s];
+                pat[2 * (s * 32 + lane) + 1] = py[16 * lane + s];
+            }
+        ADB_CUDA(cudaMalloc(&h->d_pattern, 1024));
+        ADB_CUDA(cudaMemcpy(h->d_pattern, pat.data(), 1024, cudaMemcpyHostToDevice));
+    }
+    const size_t cb = (size_t)B * h->cand_total * 4;
+    ADB_CUDA(cudaMalloc(&h->d_cand, cb));
+    ADB_CUDA(cudaMalloc(&h->d_qkeys, cb));
+    ADB_CUDA(cudaMalloc(&h->d_qstate, cb));
+    ADB_CUDA(cudaMalloc(&h->d_cellcnt, (size_t)B * std::max(h->ncells_total, 1) * 2));
+    ADB_CUDA(cudaMalloc(&h->d_qcount, (size_t)B * nl * 4));
+    ADB_CUDA(cudaMalloc(&h->d_list, (size_t)B * h->list_total * 4));
+    ADB_CUDA(cudaMalloc(&h->d_listcnt, (size_t)B * nl * 4));
+    ADB_CUDA(cudaMalloc(&h->d_status, 4));
+    ADB_CUDA(cudaMemset(h->d_status, 0, 4));
+    ADB_CUDA(cudaMalloc(&h->d_kps, (size_t)B * h->capacity * sizeof(adb_keypoint)));
+    ADB_CUDA(cudaMalloc(&h->d_desc, (size_t)B * h->capacity * 32));
+    ADB_CUDA(cudaMalloc(&h->d_counts, (size_t)B * 4));
+    ADB_CUDA(cudaMemset(h->d_counts, 0, (size_t)B * 4));
+    ADB_CUDA(cudaMallocHost(&h->h_counts, (size_t)B * 4));
+    ADB_CUDA(cudaMallocHost(&h->h_status, 4));
+    // TMA descriptors for levels >= 1 (level 0 is encoded per call: it may alias the caller's buffer)
+    for (int l = 1; l < nl; ++l) {
+        const LevelDev& d = h->lv[l].d;
+        adb_status s = encode_tma_u8_3d(&h->cell_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, d.box_w, d.box_h);
+        if (s != ADB_OK) return s;
+        s = encode_tma_u8_3d(&h->patch_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, kPatchBoxW, kPatchBoxH);
+        if (s != ADB_OK) return s;
+    }
+    ADB_CUDA(cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qt_smem));
+    ADB_CUDA(cudaFuncSetAttribute(orient_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem) + 128));
+    return ADB_OK;
+}
+
+static adb_status ensure_mask_buffers(adb_orb* h) {
+    for (auto& l : h->lv)
+        if (!l.mask) ADB_CUDA(cudaMalloc(&l.mask, (size_t)h->cfg.max_batch * l.d.mframe_stride));
+    return ADB_OK;
+}
+
+// Copy n frames of w x h bytes between arbitrary pitched layouts (kind decides the direction).
+static adb_status copy_frames(void* dst, size_t dpitch, size_t dfstride, const void* src, size_t spitch, size_t sfstride,
+                              int w, int h, int n, cudaMemcpyKind kind, cudaStream_t st) {
+    if (dpitch == (size_t)w && spitch == (size_t)w && dfstride == (size_t)w * h && sfstride == (size_t)w * h) {
+        ADB_CUDA(cudaMemcpyAsync(dst, src, (size_t)w * h * n, kind, st));
+    } else if (dfstride == dpitch * h && sfstride == spitch * h) {
+        ADB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, w, (size_t)h * n, kind, st));
+    } else {
+        for (int f = 0; f < n; ++f)
+            ADB_CUDA(cudaMemcpy2DAsync((uint8_t*)dst + f * dfstride, dpitch, (const uint8_t*)src + f * sfstride, spitch, w, h, kind, st));
+    }
+    return ADB_OK;
+}
+
+// Launch the whole pipeline on frames whose level 0 is at (l0, pitch, fstride) in device memory.
+static bool debug_sync() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADB_DEBUG_SYNC"); v = (e && *e == '1') ? 1 : 0; }
+    return v == 1;
+}
+#define ADB_STAGE(name)                                                                      \
+    do {                                                                                     \
+        ADB_CUDA(cudaGetLastError());                                                        \
+        if (debug_sync()) {                                                                  \
+            cudaError_t _e = cudaStreamSynchronize(st);                                      \
+            if (_e != cudaSuccess) { set_error("stage %s failed: %s", name, cudaGetErrorString(_e)); return ADB_ERR_CUDA; } \
+        }                                                                                    \
+    } while (0)
+
+static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitch, size_t l0_fstride, bool masked) {
+    cudaStream_t st = h->stream;
+    const int nl = h->nlevels;
+    h->l0_base = l0; h->l0_pitch = l0_pitch; h->l0_fstride = l0_fstride; h->have_mask = masked; h->last_frames = n;
+    {
+        const LevelDev& d = h->lv[0].d;
+        adb_status s = encode_tma_u8_3d(&h->cell_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, d.box_w, d.box_h);
+        if (s != ADB_OK) return s;
+        s = encode_tma_u8_3d(&h->patch_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, kPatchBoxW, kPatchBoxH);
+        if (s != ADB_OK) return s;
+    }
+    // level table with the per-call level-0 geometry
+    if (h->lv[0].d.pitch != l0_pitch || h->lv[0].d.frame_stride != (unsigned)l0_fstride) {
+        LevelDev d0 = h->lv[0].d;
+        d0.pitch = l0_pitch; d0.frame_stride = (unsigned)l0_fstride;
+        ADB_CUDA(cudaMemcpyAsync(h->d_levels, &d0, sizeof(LevelDev), cudaMemcpyHostToDevice, st));
+        h->lv[0].d = d0;
+    }
+    // ---- pyramid
+    for (int l = 1; l < nl; ++l) {
+        const LevelDev& s = h->lv[l - 1].d;
+        const LevelDev& d = h->lv[l].d;
+        const uint8_t* src = l == 1 ? l0 : h->lv[l - 1].img;
+        dim3 grid((d.pitch / 4 + 127) / 128, d.h, n);
+        pyr_resize_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
+                                               d.frame_stride, h->lv[l].xtab, h->lv[l].ytab);
+        if (masked)
+            pyr_resize_kernel<<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w, d.h,
+                                                   d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab);
+    }
+    ADB_STAGE("pyramid");
+    // ---- FAST per cell
+    MaskPtrs mp;
+    for (int l = 0; l < kMaxLevels; ++l) mp.p[l] = (masked && l < nl) ? h->lv[l].mask : nullptr;
+#ifdef ADB_FAST_NO_TMA
+    for (int l = 0; l < nl && l < 8; ++l) mp.p[8 + l] = l == 0 ? l0 : h->lv[l].img;
+#endif
+    if (h->ncells_total > 0) {
+        dim3 grid(h->ncells_total, n);
+        fast_cells_kernel<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast,
+                                                        h->cfg.min_th_fast, h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total);
+        ADB_STAGE("fast_cells");
+    }
+    // ---- quad-tree
+    {
+        dim3 grid(nl, n);
+        quadtree_kernel<<<grid, kQtThreads, h->qt_smem, st>>>(h->d_levels, nl, h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total,
+                                                             h->d_qkeys, h->d_qstate, h->d_qcount, h->d_list, h->list_total,
+                                                             h->d_listcnt, h->qt_maxa, h->d_status);
+        ADB_STAGE("quadtree");
+    }
+    // ---- orientation + descriptors
+    {
+        dim3 grid((h->capacity + kDescWarps - 1) / kDescWarps, n);
+        orient_describe_kernel<<<grid, kDescWarps * 32, sizeof(DescSmem) + 128, st>>>(h->patch_maps, h->d_levels, nl, h->d_list, h->list_total,
+                                                                                     h->d_listcnt, h->d_pattern, h->d_kps, h->d_desc,
+                                                                                     h->d_counts, h->capacity);
+        ADB_STAGE("orient_describe");
+    }
+    return ADB_OK;
+}
+
+static adb_status check_device_status(adb_orb* h) {
+    ADB_CUDA(cudaMemcpyAsync(h->h_status, h->d_status, 4, cudaMemcpyDeviceToHost, h->stream));
+    ADB_CUDA(cudaStreamSynchronize(h->stream));
+    if (*h->h_status != 0) {
+        const int s = *h->h_status;
+        cudaMemsetAsync(h->d_status, 0, 4, h->stream);
+        set_error("extractor device status %d (2 = quad-tree pass guard, 3 = node table overflow, 4 = level list overflow)", s);
+        return ADB_ERR_CAPACITY;
+    }
+    return ADB_OK;
+}
+
+}  // namespace adb
+
+using namespace adb;
+
+extern "C" {
+
+adb_status adb_orb_create(const adb_orb_config* cfg, adb_orb_t* out) {
+    ADB_CHECK(cfg && out, ADB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    ADB_CHECK(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, ADB_ERR_INVALID, "nlevels %d out of range 1..%d", cfg->nlevels, kMaxLevels);
+    ADB_CHECK(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->width >= 1 && cfg->height >= 1 && cfg->max_batch >= 1 &&
+                  cfg->ini_th_fast >= 0 && cfg->min_th_fast >= 0 && cfg->ini_th_fast < 255 && cfg->min_th_fast < 255,
+              ADB_ERR_INVALID, "bad extractor configuration");
+    adb_status s = select_device(cfg->device);
+    if (s != ADB_OK) return s;
+    adb_orb* h = new adb_orb();
+    s = create_impl(cfg, h);
+    if (s != ADB_OK) { free_handle(h); return s; }
+    *out = h;
+    return ADB_OK;
+}
+
+adb_status adb_orb_destroy(adb_orb_t h) {
+    if (!h) return ADB_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    free_handle(h);
+    return ADB_OK;
+}
+
+int32_t adb_orb_levels(adb_orb_t h) { return h ? h->nlevels : 0; }
+int32_t adb_orb_capacity(adb_orb_t h) { return h ? h->capacity : 0; }
+
+adb_status adb_orb_level_info(adb_orb_t h, int32_t level, int32_t* w, int32_t* h_, int32_t* pitch, float* scale,
+                              float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* quota) {
+    ADB_CHECK(h && level >= 0 && level < h->nlevels, ADB_ERR_INVALID, "bad level");
+    const LevelDev& d = h->lv[level].d;
+    if (w) *w = d.w;
+    if (h_) *h_ = d.h;
+    if (pitch) *pitch = d.pitch;
+    if (scale) *scale = d.scale;
+    if (inv_scale) *inv_scale = d.inv_scale;
+    if (sigma2) *sigma2 = h->sigma2[level];
+    if (inv_sigma2) *inv_sigma2 = h->inv_sigma2[level];
+    if (quota) *quota = d.quota;
+    return ADB_OK;
+}
+
+void* adb_orb_stream(adb_orb_t h) { return h ? (void*)h->stream : nullptr; }
+
+adb_status adb_orb_sync(adb_orb_t h) {
+    ADB_CHECK(h, ADB_ERR_INVALID, "null handle");
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    return check_device_status(h);
+}
+
+static adb_status prepare_masks(adb_orb* h, int n, const uint8_t* d_masks, size_t mfstride, int mpitch) {
+    adb_status s = ensure_mask_buffers(h);
+    if (s != ADB_OK) return s;
+    const LevelDev& d = h->lv[0].d;
+    dim3 grid((d.w + 127) / 128, d.h, n);
+    erode10_kernel<<<grid, 128, 0, h->stream>>>(d_masks, d.w, d.h, mpitch, mfstride, h->lv[0].mask, d.mpitch, d.mframe_stride);
+    ADB_CUDA(cudaGetLastError());
+    return ADB_OK;
+}
+
+adb_status adb_orb_extract_batch_device(adb_orb_t h, int32_t n, const uint8_t* d_images, size_t fstride, int32_t w, int32_t hh,
+                                        int32_t pitch, const uint8_t* d_masks, size_t mfstride, int32_t mpitch) {
+    ADB_CHECK(h && d_images, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK(n >= 1 && n <= h->cfg.max_batch, ADB_ERR_INVALID, "n_frames %d exceeds max_batch %d", n, h->cfg.max_batch);
+    ADB_CHECK(w == h->cfg.width && hh == h->cfg.height && pitch >= w, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    const uint8_t* l0 = d_images; int l0p = pitch; size_t l0s = fstride;
+    if (((uintptr_t)d_images & 15) || (pitch & 15) || (fstride & 15)) {   // not TMA-addressable: stage a copy
+        const int p0 = (w + 15) & ~15;
+        adb_status s = copy_frames(h->lv[0].img, p0, (size_t)p0 * hh, d_images, pitch, fstride, w, hh, n, cudaMemcpyDeviceToDevice, h->stream);
+        if (s != ADB_OK) return s;
+        l0 = h->lv[0].img; l0p = p0; l0s = (size_t)p0 * hh;
+    }
+    if (d_masks) {
+        adb_status s = prepare_masks(h, n, d_masks, mfstride, mpitch);
+        if (s != ADB_OK) return s;
+    }
+    return run_pipeline(h, n, l0, l0p, l0s, d_masks != nullptr);
+}
+
+adb_status adb_orb_results_device(adb_orb_t h, const adb_keypoint** d_kps, const uint8_t** d_desc, const int32_t** d_counts, int32_t* capacity) {
+    ADB_CHECK(h, ADB_ERR_INVALID, "null handle");
+    if (d_kps) *d_kps = h->d_kps;
+    if (d_desc) *d_desc = h->d_desc;
+    if (d_counts) *d_counts = h->d_counts;
+    if (capacity) *capacity = h->capacity;
+    return ADB_OK;
+}
+
+adb_status adb_orb_download(adb_orb_t h, int32_t first, int32_t n, adb_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* counts) {
+    ADB_CHECK(h && counts, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK(first >= 0 && n >= 0 && first + n <= h->cfg.max_batch, ADB_ERR_INVALID, "bad frame range");
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    ADB_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts + first, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    const int rows = std::min(cap, h->capacity);
+    if (kps && rows > 0)
+        ADB_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(adb_keypoint), h->d_kps + (size_t)first * h->capacity,
+                                   (size_t)h->capacity * sizeof(adb_keypoint), (size_t)rows * sizeof(adb_keypoint), n, cudaMemcpyDeviceToHost, h->stream));
+    if (desc && rows > 0)
+        ADB_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc + (size_t)first * h->capacity * 32, (size_t)h->capacity * 32,
+                                   (size_t)rows * 32, n, cudaMemcpyDeviceToHost, h->stream));
+    adb_status s = check_device_status(h);
+    if (s != ADB_OK) return s;
+    for (int i = 0; i < n; ++i) {
+        counts[i] = h->h_counts[i];
+        ADB_CHECK(counts[i] <= cap, ADB_ERR_CAPACITY, "frame %d holds %d key-points, caller capacity %d", first + i, counts[i], cap);
+    }
+    return ADB_OK;
+}
+
+adb_status adb_orb_extract_batch(adb_orb_t h, int32_t n, const uint8_t* images, size_t fstride, int32_t w, int32_t hh, int32_t pitch,
+                                 const uint8_t* masks, size_t mfstride, int32_t mpitch, adb_keypoint* kps, uint8_t* desc,
+                                 int32_t cap, int32_t* counts) {
+    ADB_CHECK(h && counts, ADB_ERR_INVALID, "null argument");
+    if (w == 0 || hh == 0 || !images) {   // src/ORBextractor.cc:1057-1058: empty image -> silent return
+        for (int i = 0; i < n; ++i) counts[i] = 0;
+        return ADB_OK;
+    }
+    ADB_CHECK(n >= 1 && n <= h->cfg.max_batch, ADB_ERR_INVALID, "n_frames %d exceeds max_batch %d", n, h->cfg.max_batch);
+    ADB_CHECK(w == h->cfg.width && hh == h->cfg.height && pitch >= w, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    const int p0 = (w + 15) & ~15;
+    adb_status s = copy_frames(h->lv[0].img, p0, (size_t)p0 * hh, images, pitch, fstride, w, hh, n, cudaMemcpyHostToDevice, h->stream);
+    if (s != ADB_OK) return s;
+    if (masks) {
+        s = ensure_mask_buffers(h);
+        if (s != ADB_OK) return s;
+        uint8_t* stage = nullptr;
+        ADB_CUDA(cudaMallocAsync((void**)&stage, (size_t)n * p0 * hh, h->stream));
+        s = copy_frames(stage, p0, (size_t)p0 * hh, masks, mpitch, mfstride, w, hh, n, cudaMemcpyHostToDevice, h->stream);
+        if (s == ADB_OK) s = prepare_masks(h, n, stage, (size_t)p0 * hh, p0);
+        cudaFreeAsync(stage, h->stream);
+        if (s != ADB_OK) return s;
+    }
+    s = run_pipeline(h, n, h->lv[0].img, p0, (size_t)p0 * hh, masks != nullptr);
+    if (s != ADB_OK) return s;
+    return adb_orb_download(h, 0, n, kps, desc, cap, counts);
+}
+
+adb_status adb_orb_extract(adb_orb_t h, const uint8_t* image, int32_t w, int32_t hh, int32_t pitch, const uint8_t* mask,
+                           int32_t mpitch, adb_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* n_out) {
+    ADB_CHECK(n_out, ADB_ERR_INVALID, "null argument");
+    return adb_orb_extract_batch(h, 1, image, (size_t)pitch * hh, w, hh, pitch, mask, (size_t)mpitch * hh, mpitch, kps, desc, cap, n_out);
+}
+
+adb_status adb_orb_get_pyramid(adb_orb_t h, int32_t frame, int32_t level, int32_t which, uint8_t* dst, int32_t dpitch) {
+    ADB_CHECK(h && dst && level >= 0 && level < h->nlevels && frame >= 0 && frame < h->last_frames, ADB_ERR_INVALID, "bad argument");
+    ADB_CHECK(which == 0 || (which == 1 && h->have_mask), ADB_ERR_INVALID, "no mask pyramid resident");
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    const LevelDev& d = h->lv[level].d;
+    const uint8_t* src; size_t sp, fs;
+    if (which == 0) {
+        if (level == 0) { src = h->l0_base; sp = h->l0_pitch; fs = h->l0_fstride; }
+        else { src = h->lv[level].img; sp = d.pitch; fs = d.frame_stride; }
+    } else {
+        src = h->lv[level].mask; sp = d.mpitch; fs = d.mframe_stride;
+    }
+    ADB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src + frame * fs, sp, d.w, d.h, cudaMemcpyDeviceToHost, h->stream));
+    ADB_CUDA(cudaStreamSynchronize(h->stream));
+    return ADB_OK;
+}
+
+adb_status adb_orb_debug_candidates(adb_orb_t h, int32_t frame, int32_t level, int32_t* xys, int32_t cap, int32_t* n) {
+    ADB_CHECK(h && n && level >= 0 && level < h->nlevels && frame >= 0 && frame < h->last_frames, ADB_ERR_INVALID, "bad argument");
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    int32_t cnt = 0;
+    ADB_CUDA(cudaMemcpyAsync(&cnt, h->d_qcount + frame * h->nlevels + level, 4, cudaMemcpyDeviceToHost, h->stream));
+    ADB_CUDA(cudaStreamSynchronize(h->stream));
+    *n = cnt;
+    const int m = std::min(cnt, cap);
+    if (m > 0 && xys) {
+        int32_t* tmp = nullptr;
+        ADB_CUDA(cudaMalloc(&tmp, (size_t)m * 12));
+        unpack_candidates_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(h->d_qkeys + (size_t)frame * h->cand_total + h->lv[level].d.cand_base, m, tmp);
+        cudaError_t e = cudaMemcpyAsync(xys, tmp, (size_t)m * 12, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        ADB_CUDA(e);
+    }
+    return ADB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// orb.cuh -- internal definition of the extractor handle (shared by orb.cu and stereo.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace adb {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;        // EDGE_THRESHOLD   src/ORBextractor.cc:75
+constexpr int kMinBorder = 16;   // EDGE_THRESHOLD-3 src/ORBextractor.cc:775
+constexpr int kCellBoxWMax = 96; // FAST cell tile: 15 B alignment slack + cell + 6 px, rounded up to 16 B
+                                 // (TMA needs the box origin 16-byte aligned in x: measured on B200, tools/probe)
+constexpr int kCellBoxHMax = 66;
+constexpr int kPatchBoxW = 64;   // descriptor patch: 43 x 43 px (+-18 sample reach, +-3 blur reach) + <= 15 B alignment slack
+constexpr int kPatchBoxH = 43;
+constexpr int kPatchR = 21;
+
+// Per-level constants, one array per handle in device memory.
+struct LevelDev {
+    int w, h, pitch;
+    unsigned frame_stride;   // bytes between frames of this level
+    int mpitch; unsigned mframe_stride;   // mask pyramid layout (always the handle's own buffers)
+    int ncols, nrows, wcell, hcell;
+    int cell_base, ncells;   // position in the flattened cell table
+    int slotcap;             // candidate slots per cell = ceil(wcell/2) * ceil(hcell/2) (3x3 strict-NMS bound)
+    int cand_base, cand_cap; // u32 offset of this level's slots inside one frame's candidate area
+    int quota;               // mnFeaturesPerLevel
+    int list_base, list_cap; // position of this level's kept list inside one frame's list area
+    int n_ini;               // quad-tree roots
+    float hx;                // root width
+    float scale;             // mvScaleFactor
+    float inv_scale;
+    int patch_size;          // (int)(31 * scale)
+    int box_w, box_h;        // FAST cell TMA box
+};
+
+struct LevelHost {
+    LevelDev d;
+    uint8_t* img = nullptr;    // [max_batch][h][pitch]   (level 0: internal staging copy)
+    uint8_t* mask = nullptr;   // same layout, allocated on first masked call
+    int2* xtab = nullptr;      // resize tables for producing this level from level-1: {src index, a0 | a1 << 16}
+    int2* ytab = nullptr;
+};
+
+}  // namespace adb
+
+struct adb_orb {
+    adb_orb_config cfg;
+    int nlevels = 0;
+    int capacity = 0;               // key-points per frame
+    int ncells_total = 0;
+    int cand_total = 0;             // u32 entries per frame
+    int list_total = 0;             // entries per frame
+    int qt_maxa = 0;                // quad-tree node capacity
+    size_t qt_smem = 0;
+    std::vector<adb::LevelHost> lv;
+    std::vector<float> sigma2, inv_sigma2;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    adb::LevelDev* d_levels = nullptr;
+    uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col
+    int8_t* d_pattern = nullptr;        // [16][32][2] rBRIEF points, lane-major
+    uint32_t* d_cand = nullptr;         // [max_batch][cand_total] per-cell slots
+    uint16_t* d_cellcnt = nullptr;      // [max_batch][ncells_total]
+    uint32_t* d_qkeys = nullptr;        // [max_batch][cand_total] gathered candidates (reference order)
+    uint32_t* d_qstate = nullptr;       // [max_batch][cand_total] node slot << 20 | node seq
+    int32_t* d_qcount = nullptr;        // [max_batch][nlevels] candidates per (frame, level)
+    uint32_t* d_list = nullptr;         // [max_batch][list_total] kept key-points per level
+    int32_t* d_listcnt = nullptr;       // [max_batch][nlevels]
+    int32_t* d_status = nullptr;        // device-side error flag
+    adb_keypoint* d_kps = nullptr;      // [max_batch][capacity]
+    uint8_t* d_desc = nullptr;          // [max_batch][capacity][32]
+    int32_t* d_counts = nullptr;        // [max_batch]
+    // stereo outputs (owned by the left handle)
+    float* d_uright = nullptr;
+    float* d_depth = nullptr;
+    int32_t* d_best_idx = nullptr;
+    int32_t* d_best_dist = nullptr;
+    int32_t* d_sad = nullptr;
+    // level-0 view of the last call (caller's buffer when it is TMA-addressable, else lv[0].img)
+    const uint8_t* l0_base = nullptr;
+    int l0_pitch = 0;
+    size_t l0_fstride = 0;
+    bool have_mask = false;
+    int last_frames = 0;
+    adb::TmaMaps16 cell_maps;    // FAST cell boxes
+    adb::TmaMaps16 patch_maps;   // descriptor patches
+    int32_t* h_counts = nullptr; // pinned
+    int32_t* h_status = nullptr; // pinned
+};

@@ -1,0 +1,172 @@
+"""Host-side mirror of ORB_SLAM2::ORBextractor / ORBmatcher over the C-ABI.
+
+Names and argument meaning follow include/ORBextractor.h:51-86 and include/ORBmatcher.h:41-83
+of the reference so that the parity tests read like calls into the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import KP_DTYPE, check, lib, ptr
+
+
+class ORBextractor:
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) bound to one image
+    size and a maximum batch (the device buffers are provisioned once per handle)."""
+
+    def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int,
+                 width: int = 640, height: int = 480, max_batch: int = 1, device: int = 0):
+        cfg = capi.OrbConfig(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width, height, max_batch, device)
+        self._h = C.c_void_p()
+        check(lib().adb_orb_create(C.byref(cfg), C.byref(self._h)))
+        self.width, self.height, self.max_batch = width, height, max_batch
+        self.nlevels = lib().adb_orb_levels(self._h)
+        self.capacity = lib().adb_orb_capacity(self._h)
+        self._info = [self._level_info(l) for l in range(self.nlevels)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().adb_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _level_info(self, l):
+        w, h, p, q = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        s, i, s2, i2 = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        check(lib().adb_orb_level_info(self._h, l, C.byref(w), C.byref(h), C.byref(p), C.byref(s), C.byref(i),
+                                       C.byref(s2), C.byref(i2), C.byref(q)))
+        return dict(w=w.value, h=h.value, pitch=p.value, scale=s.value, inv_scale=i.value, sigma2=s2.value,
+                    inv_sigma2=i2.value, quota=q.value)
+
+    # include/ORBextractor.h:63-85
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactors(self): return [i["scale"] for i in self._info]
+    def GetInverseScaleFactors(self): return [i["inv_scale"] for i in self._info]
+    def GetScaleSigmaSquares(self): return [i["sigma2"] for i in self._info]
+    def GetInverseScaleSigmaSquares(self): return [i["inv_sigma2"] for i in self._info]
+    def level_sizes(self): return [(i["w"], i["h"]) for i in self._info]
+    def quotas(self): return [i["quota"] for i in self._info]
+
+    def __call__(self, image: np.ndarray, mask: np.ndarray | None = None):
+        """operator()(image, mask, keypoints, descriptors) for one CV_8UC1 image -> (kps, desc)."""
+        image = np.ascontiguousarray(image, np.uint8)
+        if image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        k, d, c = self.extract_batch(image[None], None if mask is None else np.ascontiguousarray(mask, np.uint8)[None])
+        return k[0, :c[0]].copy(), d[0, :c[0]].copy()
+
+    def extract_batch(self, images: np.ndarray, masks: np.ndarray | None = None):
+        """images u8 [F, H, W] (host) -> kps [F, cap], desc [F, cap, 32], counts [F]."""
+        images = np.ascontiguousarray(images, np.uint8)
+        f, h, w = images.shape
+        kps = np.zeros((f, self.capacity), KP_DTYPE)
+        desc = np.zeros((f, self.capacity, 32), np.uint8)
+        counts = np.zeros(f, np.int32)
+        if masks is not None:
+            masks = np.ascontiguousarray(masks, np.uint8)
+            assert masks.shape == images.shape
+        check(lib().adb_orb_extract_batch(self._h, f, ptr(images), h * w, w, h, w, ptr(masks), h * w, w,
+                                          ptr(kps), ptr(desc), self.capacity, ptr(counts)))
+        return kps, desc, counts
+
+    def extract_batch_device(self, d_images: int, n_frames: int, frame_stride: int | None = None, pitch: int | None = None,
+                             d_masks: int | None = None):
+        """Device-resident inputs (raw device pointer); asynchronous, results stay in HBM."""
+        pitch = pitch or self.width
+        frame_stride = frame_stride or pitch * self.height
+        check(lib().adb_orb_extract_batch_device(self._h, n_frames, ptr(d_images), frame_stride, self.width, self.height,
+                                                 pitch, ptr(d_masks), frame_stride, pitch))
+
+    def sync(self):
+        check(lib().adb_orb_sync(self._h))
+
+    def stream(self) -> int:
+        return int(lib().adb_orb_stream(self._h) or 0)
+
+    def results_device(self):
+        k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cap = C.c_int32()
+        check(lib().adb_orb_results_device(self._h, C.byref(k), C.byref(d), C.byref(c), C.byref(cap)))
+        return k.value, d.value, c.value, cap.value
+
+    def download(self, first: int, n: int):
+        kps = np.zeros((n, self.capacity), KP_DTYPE)
+        desc = np.zeros((n, self.capacity, 32), np.uint8)
+        counts = np.zeros(n, np.int32)
+        check(lib().adb_orb_download(self._h, first, n, ptr(kps), ptr(desc), self.capacity, ptr(counts)))
+        return kps, desc, counts
+
+    def pyramid(self, frame: int = 0, which: int = 0):
+        """mvImagePyramid (which=0) / mvMaskPyramid (which=1) of `frame` of the last call."""
+        out = []
+        for l, (w, h) in enumerate(self.level_sizes()):
+            a = np.zeros((h, w), np.uint8)
+            check(lib().adb_orb_get_pyramid(self._h, frame, l, which, ptr(a), w))
+            out.append(a)
+        return out
+
+    def debug_candidates(self, frame: int, level: int):
+        n = C.c_int32()
+        check(lib().adb_orb_debug_candidates(self._h, frame, level, None, 0, C.byref(n)))
+        a = np.zeros((max(n.value, 1), 3), np.int32)
+        check(lib().adb_orb_debug_candidates(self._h, frame, level, ptr(a), n.value, C.byref(n)))
+        return a[:n.value]
+
+
+class ORBmatcher:
+    """The Hamming primitives of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:41-83)."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # src/ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, device: int = 0):
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+        self._m = C.c_void_p()
+        check(lib().adb_matcher_create(device, C.byref(self._m)))
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m:
+            lib().adb_matcher_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        assert a.size == 32 and b.size == 32
+        return int(lib().adb_hamming_distance(ptr(a), ptr(b)))
+
+    def best2(self, q_desc: np.ndarray, t_desc: np.ndarray, cand_off: np.ndarray | None = None,
+              cand_idx: np.ndarray | None = None):
+        """best / second-best Hamming scan over candidate lists -> (best_idx, best_d, second_d)."""
+        q = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t_desc, np.uint8).reshape(-1, 32)
+        nq, nt = len(q), len(t)
+        bi = np.full(nq, -1, np.int32); bd = np.full(nq, 256, np.int32); sd = np.full(nq, 256, np.int32)
+        if cand_off is not None:
+            cand_off = np.ascontiguousarray(cand_off, np.int32); cand_idx = np.ascontiguousarray(cand_idx, np.int32)
+            assert len(cand_off) == nq + 1
+        if nq:
+            check(lib().adb_match_best2(self._m, ptr(q), nq, ptr(t), nt, ptr(cand_off), ptr(cand_idx), ptr(bi), ptr(bd), ptr(sd)))
+        return bi, bd, sd
+
+
+def compute_stereo_matches(left: ORBextractor, right: ORBextractor, n_frames: int, mb: float, mbf: float):
+    """Frame::ComputeStereoMatches for the frames resident in two extractor handles ->
+    (uRight [F, cap], depth [F, cap], best_idx [F, cap], best_dist [F, cap])."""
+    cap = left.capacity
+    ur = np.zeros((n_frames, cap), np.float32); dp = np.zeros((n_frames, cap), np.float32)
+    bi = np.zeros((n_frames, cap), np.int32); bd = np.zeros((n_frames, cap), np.int32)
+    check(lib().adb_stereo_match(left._h, right._h, n_frames, mb, mbf, ptr(ur), ptr(dp), ptr(bi), ptr(bd), cap))
+    return ur, dp, bi, bd

@@ -1,0 +1,171 @@
+/* airdos_b200.h -- C-ABI of libairdos_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the three numeric classes on AirDOS's hot path.  The reference has no
+ * FFI of its own; the seam is the C++ interface of ORB_SLAM2::ORBextractor / ORBmatcher /
+ * Optimizer (namespace ORB_SLAM2, libORB_SLAM2.so).  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference tree).  INTEGRATION.md
+ * shows the shim a maintainer drops into src/ORBextractor.cc, src/Frame.cc and
+ * src/Optimizer.cc to forward those methods here.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an adb_status (0 = ok) and never aborts;
+ *   - "host" entry points take host pointers and do the H2D / D2H copies themselves;
+ *     "_device" entry points take device pointers (inputs already resident in HBM) and leave
+ *     their results resident; results are fetched with the *_results / *_download calls;
+ *   - handles are not thread-safe but independent: one handle per calling thread, each owns
+ *     its CUDA stream and scratch (the reference runs one extractor per image thread,
+ *     src/Frame.cc:81-84);
+ *   - there is NO CPU fallback: without a CUDA device every create call returns
+ *     ADB_ERR_NO_DEVICE.
+ */
+#ifndef AIRDOS_B200_H
+#define AIRDOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADB_VERSION 100
+
+typedef enum adb_status {
+    ADB_OK = 0,
+    ADB_ERR_INVALID = 1,     /* bad argument / unsupported shape */
+    ADB_ERR_NO_DEVICE = 2,   /* no CUDA device, or not sm_100 */
+    ADB_ERR_CUDA = 3,        /* a CUDA call failed; see adb_last_error() */
+    ADB_ERR_CAPACITY = 4,    /* an output or scratch capacity was exceeded (nothing silently dropped) */
+    ADB_ERR_NOT_POSDEF = 5,  /* BA: reduced system not positive definite in every LM trial */
+    ADB_ERR_STOPPED = 6      /* BA: stop flag was set before optimisation started (no write-back) */
+} adb_status;
+
+const char* adb_last_error(void);   /* thread-local message of the last non-OK status */
+int adb_version(void);
+int adb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Key-point record: the cv::KeyPoint fields the SLAM code reads (pt, size, angle, response,
+ * octave); 24 bytes, little endian.  Replaces std::vector<cv::KeyPoint>& _keypoints of
+ * ORBextractor::operator() (include/ORBextractor.h:59-61). */
+typedef struct adb_keypoint {
+    float x, y;      /* pt, level-0 pixel coordinates */
+    float size;      /* 31 * scale[octave], truncated to int as the reference does */
+    float angle;     /* degrees [0, 360) */
+    float response;  /* FAST score */
+    int32_t octave;
+} adb_keypoint;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (include/ORBextractor.h:51-52, src/ORBextractor.cc:411-472) plus the sizes the handle must
+ * provision device memory for. */
+typedef struct adb_orb_config {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;       /* 1..16 */
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t width, height; /* image size this handle is built for (fixed per handle) */
+    int32_t max_batch;     /* frames processed per call (>= 1) */
+    int32_t device;        /* CUDA device ordinal */
+} adb_orb_config;
+
+typedef struct adb_orb* adb_orb_t;
+
+/* ctor / dtor of ORBextractor. */
+adb_status adb_orb_create(const adb_orb_config* cfg, adb_orb_t* out);
+adb_status adb_orb_destroy(adb_orb_t h);
+
+/* Getters: GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:63-85) and the per-level quota
+ * mnFeaturesPerLevel (src/ORBextractor.cc:433-445). */
+int32_t adb_orb_levels(adb_orb_t h);
+int32_t adb_orb_capacity(adb_orb_t h); /* max key-points per frame the extractor can emit */
+adb_status adb_orb_level_info(adb_orb_t h, int32_t level, int32_t* w, int32_t* h_, int32_t* pitch,
+                              float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                              int32_t* quota);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors)  (src/ORBextractor.cc:1054-1119)
+ * for one frame, host buffers.  mask may be NULL (= all 255); otherwise CV_8UC1 semantics of
+ * Frame::ExtractORB (src/Frame.cc:551-571): 0 = rejected.  kps / desc receive at most `cap`
+ * records (desc is cap x 32 bytes); *n_out the count.  An empty image (w == 0 || h == 0)
+ * returns ADB_OK with *n_out = 0, as the reference silently returns. */
+adb_status adb_orb_extract(adb_orb_t h, const uint8_t* image, int32_t w, int32_t h_, int32_t pitch,
+                           const uint8_t* mask, int32_t mask_pitch,
+                           adb_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* n_out);
+
+/* Same for n_frames frames stored frame_stride bytes apart (host memory; pinned memory makes
+ * the copies asynchronous).  masks may be NULL.  kps: [n_frames][cap], desc: [n_frames][cap][32],
+ * counts: [n_frames]. */
+adb_status adb_orb_extract_batch(adb_orb_t h, int32_t n_frames, const uint8_t* images, size_t frame_stride,
+                                 int32_t w, int32_t h_, int32_t pitch,
+                                 const uint8_t* masks, size_t mask_frame_stride, int32_t mask_pitch,
+                                 adb_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* counts);
+
+/* Device-resident variant: images (and masks) are device pointers; results stay in HBM.
+ * Asynchronous on the handle's stream; adb_orb_sync waits for it. */
+adb_status adb_orb_extract_batch_device(adb_orb_t h, int32_t n_frames, const uint8_t* d_images, size_t frame_stride,
+                                        int32_t w, int32_t h_, int32_t pitch,
+                                        const uint8_t* d_masks, size_t mask_frame_stride, int32_t mask_pitch);
+adb_status adb_orb_sync(adb_orb_t h);
+void* adb_orb_stream(adb_orb_t h); /* cudaStream_t of the handle */
+
+/* Device pointers to the resident results of the last extract call:
+ * kps [max_batch][capacity], desc [max_batch][capacity][32], counts [max_batch]. */
+adb_status adb_orb_results_device(adb_orb_t h, const adb_keypoint** d_kps, const uint8_t** d_desc,
+                                  const int32_t** d_counts, int32_t* capacity);
+/* Copy the resident results of frames [first, first + n) to host buffers laid out as in
+ * adb_orb_extract_batch.  Returns ADB_ERR_CAPACITY if a frame holds more than cap key-points. */
+adb_status adb_orb_download(adb_orb_t h, int32_t first, int32_t n, adb_keypoint* kps, uint8_t* desc,
+                            int32_t cap, int32_t* counts);
+
+/* ORBextractor::mvImagePyramid[level] (public member read by Frame::ComputeStereoMatches,
+ * src/Frame.cc:836,926-943; include/ORBextractor.h:86): copy level `level` of frame `frame` of the
+ * last extract call to a host buffer (rows dst_pitch apart).  which = 0 image, 1 mask pyramid. */
+adb_status adb_orb_get_pyramid(adb_orb_t h, int32_t frame, int32_t level, int32_t which, uint8_t* dst, int32_t dst_pitch);
+
+/* Diagnostics for the parity tests: FAST candidates handed to the quad-tree for (frame, level),
+ * in the reference's vToDistributeKeys order, as int32 triples (x, y, score) relative to the
+ * (16,16) cell origin.  *n receives the count (<= cap written). */
+adb_status adb_orb_debug_candidates(adb_orb_t h, int32_t frame, int32_t level, int32_t* xys, int32_t cap, int32_t* n);
+
+/* ---------------------------------------------------------------------------------------
+ * ORBmatcher::DescriptorDistance(a, b)  (src/ORBmatcher.cc:1647-1663): 256-bit Hamming
+ * distance of two 32-byte descriptors; host inline helper, identical on every platform. */
+int32_t adb_hamming_distance(const uint8_t* a, const uint8_t* b);
+
+typedef struct adb_matcher* adb_matcher_t;
+adb_status adb_matcher_create(int32_t device, adb_matcher_t* out);
+adb_status adb_matcher_destroy(adb_matcher_t m);
+
+/* The best / second-best scan every ORBmatcher::Search* / Fuse runs over its candidate list
+ * (src/ORBmatcher.cc:85-114, 216-225 and the other nine call sites): for query q the candidates
+ * are targets cand_idx[cand_off[q] .. cand_off[q+1]) in list order (cand_off == NULL: all nt
+ * targets 0..nt-1).  Update rule: strict '<', i.e. the first candidate in list order wins
+ * ties.  Outputs start at best = second = 256, idx = -1.  Host buffers. */
+adb_status adb_match_best2(adb_matcher_t m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt,
+                           const int32_t* cand_off, const int32_t* cand_idx,
+                           int32_t* best_idx, int32_t* best_d, int32_t* second_d);
+/* Device-resident variant (all pointers in HBM; asynchronous on `stream`, a cudaStream_t or NULL). */
+adb_status adb_match_best2_device(adb_matcher_t m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt,
+                                  const int32_t* cand_off, const int32_t* cand_idx,
+                                  int32_t* best_idx, int32_t* best_d, int32_t* second_d, void* stream);
+
+/* Frame::ComputeStereoMatches()  (src/Frame.cc:829-1003) for the n_frames frames resident in
+ * the two extractor handles (frame i of `left` against frame i of `right`): row-band Hamming
+ * match, 11x11 SAD sub-pixel refinement on the pyramids, median-distance cut.
+ * mb = baseline (mbf / fx), mbf = baseline * fx.  Outputs, host, [n_frames][cap] (cap >= the
+ * left frame's key-point count, else ADB_ERR_CAPACITY): u_right = mvuRight, depth = mvDepth
+ * (-1 where unmatched); best_idx / best_dist (optional, may be NULL) = right index and Hamming
+ * distance of the row-band stage (-1 / 100 where no candidate beat TH_HIGH). */
+adb_status adb_stereo_match(adb_orb_t left, adb_orb_t right, int32_t n_frames, float mb, float mbf,
+                            float* u_right, float* depth, int32_t* best_idx, int32_t* best_dist, int32_t cap);
+/* Device-resident variant: results stay in HBM ([max_batch][capacity] arrays owned by `left`). */
+adb_status adb_stereo_match_device(adb_orb_t left, adb_orb_t right, int32_t n_frames, float mb, float mbf);
+adb_status adb_stereo_results_device(adb_orb_t left, const float** d_u_right, const float** d_depth,
+                                     const int32_t** d_best_idx, const int32_t** d_best_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIRDOS_B200_H */
