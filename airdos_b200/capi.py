@@ -51,6 +51,9 @@ SYMBOLS = {
     "adb_orb_extract_batch_device": (C.c_int, [_vp, _i32, _vp, _sz, _i32, _i32, _i32, _vp, _sz, _i32]),
     "adb_orb_sync": (C.c_int, [_vp]),
     "adb_orb_stream": (_vp, [_vp]),
+    "adb_orb_profile": (C.c_int, [_vp, _i32]),
+    "adb_orb_stage_ms": (C.c_int, [_vp, _fp]),
+    "adb_orb_launch_count": (C.c_int64, [_vp]),
     "adb_orb_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _ip]),
     "adb_orb_download": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "adb_orb_get_pyramid": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32]),

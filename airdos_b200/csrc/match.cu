@@ -401,6 +401,7 @@ adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb
     ADB_CUDA(cudaGetLastError());
     stereo_median_kernel<<<n, 256, 0, L->stream>>>(L->d_counts, cap, L->d_sad, L->d_uright, L->d_depth);
     ADB_CUDA(cudaGetLastError());
+    L->launches += 2;
     return ADB_OK;
 }
 

@@ -789,6 +789,7 @@ static void free_handle(adb_orb* h) {
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->ev) cudaEventDestroy(h->ev);
+    for (auto& e : h->pev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -947,6 +948,7 @@ static bool debug_sync() {
 #define ADB_STAGE(name)                                                                      \
     do {                                                                                     \
         ADB_CUDA(cudaGetLastError());                                                        \
+        if (h->profiling && h->pev_n < 8) ADB_CUDA(cudaEventRecord(h->pev[h->pev_n++], st)); \
         if (debug_sync()) {                                                                  \
             cudaError_t _e = cudaStreamSynchronize(st);                                      \
             if (_e != cudaSuccess) { set_error("stage %s failed: %s", name, cudaGetErrorString(_e)); return ADB_ERR_CUDA; } \
@@ -957,6 +959,9 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
     cudaStream_t st = h->stream;
     const int nl = h->nlevels;
     h->l0_base = l0; h->l0_pitch = l0_pitch; h->l0_fstride = l0_fstride; h->have_mask = masked; h->last_frames = n;
+    h->pev_n = 0;
+    if (h->profiling) ADB_CUDA(cudaEventRecord(h->pev[h->pev_n++], st));
+    h->launches += (masked ? 2 : 1) * (nl - 1) + (h->ncells_total > 0 ? 1 : 0) + 2;
     {
         const LevelDev& d = h->lv[0].d;
         adb_status s = encode_tma_u8_3d(&h->cell_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, d.box_w, d.box_h);
@@ -1076,6 +1081,27 @@ adb_status adb_orb_level_info(adb_orb_t h, int32_t level, int32_t* w, int32_t* h
 }
 
 void* adb_orb_stream(adb_orb_t h) { return h ? (void*)h->stream : nullptr; }
+
+adb_status adb_orb_profile(adb_orb_t h, int32_t enable) {
+    ADB_CHECK(h, ADB_ERR_INVALID, "null handle");
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    if (enable && !h->pev[0])
+        for (auto& e : h->pev) ADB_CUDA(cudaEventCreate(&e));
+    h->profiling = enable != 0;
+    h->pev_n = 0;
+    return ADB_OK;
+}
+
+adb_status adb_orb_stage_ms(adb_orb_t h, float* ms4) {
+    ADB_CHECK(h && ms4, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK(h->profiling && h->pev_n == 5, ADB_ERR_INVALID, "no profiled call recorded (enable adb_orb_profile, then extract)");
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    ADB_CUDA(cudaEventSynchronize(h->pev[4]));
+    for (int i = 0; i < 4; ++i) ADB_CUDA(cudaEventElapsedTime(&ms4[i], h->pev[i], h->pev[i + 1]));
+    return ADB_OK;
+}
+
+int64_t adb_orb_launch_count(adb_orb_t h) { return h ? h->launches : 0; }
 
 adb_status adb_orb_sync(adb_orb_t h) {
     ADB_CHECK(h, ADB_ERR_INVALID, "null handle");

@@ -86,6 +86,11 @@ struct adb_orb {
     int last_frames = 0;
     adb::TmaMaps16 cell_maps;    // FAST cell boxes
     adb::TmaMaps16 patch_maps;   // descriptor patches
+    // profiling: CUDA events on the handle's stream around each stage of the last call
+    bool profiling = false;
+    cudaEvent_t pev[8] = {};
+    int pev_n = 0;
+    long long launches = 0;         // kernels launched by this handle since creation
     int32_t* h_counts = nullptr; // pinned
     int32_t* h_status = nullptr; // pinned
 };

@@ -13,6 +13,40 @@ from . import capi
 from .capi import KP_DTYPE, check, lib, ptr
 
 
+class HostResults:
+    """Reusable host buffers for extract_batch (pinned: the D2H copies run at full PCIe rate)."""
+
+    def __init__(self, n_frames: int, cap: int, pinned: bool = False):
+        self._keep = []
+        def mk(shape, dtype):
+            if pinned:
+                import torch
+                nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                t = torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory()
+                self._keep.append(t)
+                return t.numpy()[:nbytes].view(dtype).reshape(shape)
+            return np.zeros(shape, dtype)
+        self.kps = mk((n_frames, cap), KP_DTYPE)
+        self.desc = mk((n_frames, cap, 32), np.uint8)
+        self.counts = mk((n_frames,), np.int32)
+        self.cap = cap
+
+
+class HostStereo:
+    def __init__(self, n_frames: int, cap: int, pinned: bool = False):
+        self._keep = []
+        def mk(dtype):
+            if pinned:
+                import torch
+                t = torch.empty(n_frames * cap * 4, dtype=torch.uint8).pin_memory()
+                self._keep.append(t)
+                return t.numpy().view(dtype).reshape(n_frames, cap)
+            return np.zeros((n_frames, cap), dtype)
+        self.u_right, self.depth = mk(np.float32), mk(np.float32)
+        self.best_idx, self.best_dist = mk(np.int32), mk(np.int32)
+        self.cap = cap
+
+
 class ORBextractor:
     """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) bound to one image
     size and a maximum batch (the device buffers are provisioned once per handle)."""
@@ -63,13 +97,13 @@ class ORBextractor:
         k, d, c = self.extract_batch(image[None], None if mask is None else np.ascontiguousarray(mask, np.uint8)[None])
         return k[0, :c[0]].copy(), d[0, :c[0]].copy()
 
-    def extract_batch(self, images: np.ndarray, masks: np.ndarray | None = None):
+    def extract_batch(self, images: np.ndarray, masks: np.ndarray | None = None, out: HostResults | None = None):
         """images u8 [F, H, W] (host) -> kps [F, cap], desc [F, cap, 32], counts [F]."""
         images = np.ascontiguousarray(images, np.uint8)
         f, h, w = images.shape
-        kps = np.zeros((f, self.capacity), KP_DTYPE)
-        desc = np.zeros((f, self.capacity, 32), np.uint8)
-        counts = np.zeros(f, np.int32)
+        if out is None:
+            out = HostResults(f, self.capacity)
+        kps, desc, counts = out.kps[:f], out.desc[:f], out.counts[:f]
         if masks is not None:
             masks = np.ascontiguousarray(masks, np.uint8)
             assert masks.shape == images.shape
@@ -90,6 +124,18 @@ class ORBextractor:
 
     def stream(self) -> int:
         return int(lib().adb_orb_stream(self._h) or 0)
+
+    def profile(self, enable: bool = True):
+        check(lib().adb_orb_profile(self._h, int(enable)))
+
+    def stage_ms(self):
+        """Device ms of the last profiled call: (pyramid, fast_cells, quadtree, orient_describe)."""
+        ms = (C.c_float * 4)()
+        check(lib().adb_orb_stage_ms(self._h, ms))
+        return tuple(ms)
+
+    def launch_count(self) -> int:
+        return int(lib().adb_orb_launch_count(self._h))
 
     def results_device(self):
         k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -162,11 +208,18 @@ class ORBmatcher:
         return bi, bd, sd
 
 
-def compute_stereo_matches(left: ORBextractor, right: ORBextractor, n_frames: int, mb: float, mbf: float):
+def compute_stereo_matches(left: ORBextractor, right: ORBextractor, n_frames: int, mb: float, mbf: float,
+                           out: HostStereo | None = None):
     """Frame::ComputeStereoMatches for the frames resident in two extractor handles ->
     (uRight [F, cap], depth [F, cap], best_idx [F, cap], best_dist [F, cap])."""
     cap = left.capacity
-    ur = np.zeros((n_frames, cap), np.float32); dp = np.zeros((n_frames, cap), np.float32)
-    bi = np.zeros((n_frames, cap), np.int32); bd = np.zeros((n_frames, cap), np.int32)
+    if out is None:
+        out = HostStereo(n_frames, cap)
+    ur, dp, bi, bd = out.u_right[:n_frames], out.depth[:n_frames], out.best_idx[:n_frames], out.best_dist[:n_frames]
     check(lib().adb_stereo_match(left._h, right._h, n_frames, mb, mbf, ptr(ur), ptr(dp), ptr(bi), ptr(bd), cap))
     return ur, dp, bi, bd
+
+
+def stereo_match_device(left: ORBextractor, right: ORBextractor, n_frames: int, mb: float, mbf: float):
+    """Device-resident ComputeStereoMatches (asynchronous on the left handle's stream)."""
+    check(lib().adb_stereo_match_device(left._h, right._h, n_frames, mb, mbf))

@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the AirDOS hot path on B200 (contract: see README / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU restatement, all host threads
+
+Workload (BASELINE.json configs[1]): a stream of 640x480 stereo pairs, 8-level pyramid, 2000
+features per frame; one step = ORB extraction of the left and right images of `pairs` stereo
+pairs + Frame::ComputeStereoMatches on every pair.  Metric: output key-points per second.
+At N > 1 every rank processes its own `pairs` pairs (weak scaling) and one NCCL all-gather of the
+fixed-stride (key-point, descriptor, count) records per step makes every rank hold all results
+(BASELINE.json configs[2]).  A second section (`ba`) reports the LocalBundleAdjustment metric
+(edges/s per LM iteration, configs[3]) when the BA solver is built.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 2000, 8, 1.2, 12, 7
+# algorithmic bytes per 640x480 frame at 2000 features
+PYR_PX = 950532
+BYTES_PER_FRAME = 307200 + PYR_PX + PYR_PX + PYR_PX + 2000 * (32 + 24)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(pairs_arr, threads, steps, warmup):
+    """Reference CPU path (oracle port) on the host cores: kp/s over `steps` passes of the sample."""
+    import oracle
+    from airdos_b200 import synth
+    oracle.build()
+    mbf = synth.BF; mb = mbf / synth.FX
+    for _ in range(warmup):
+        oracle.stereo_pipeline_batch(pairs_arr[:max(1, threads // 2)], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, mb, mbf, threads)
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(steps):
+        _, _, n = oracle.stereo_pipeline_batch(pairs_arr, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, mb, mbf, threads)
+        tot += n
+    dt = time.perf_counter() - t0
+    return tot / dt, dt / steps * 1e3, tot // max(steps, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from airdos_b200 import synth
+    threads = os.cpu_count() or 1
+    n_pairs = max(threads, 8)
+    pairs = synth.make_stereo_batch(n_pairs)
+    v, ms, kp = cpu_reference_run(pairs, threads, args.steps, min(args.warmup, 1))
+    sample = f"{n_pairs} stereo pairs ({2 * n_pairs} frames 640x480) per step, extract L+R + stereo match, {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "orb_keypoints_per_s", "value": v, "unit": "keypoints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "640x480 stereo stream, 8 levels, 2000 feat/frame, ORB extract L+R + stereo match (CPU path)",
+                   "pairs_per_step": n_pairs},
+        "cpu_baseline": {"value": v, "unit": "keypoints/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import airdos_b200 as adb
+    from airdos_b200 import dist as adist, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = args.pairs
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic stream: 16 distinct seeded pairs per rank tiled to P pairs (generation is numpy, slow)
+    base = synth.make_stereo_batch(16, W, H, start=100 * rank)
+    host = np.concatenate([base] * ((P + 15) // 16))[:P]                      # [P, 2, H, W]
+    hostL = torch.from_numpy(np.ascontiguousarray(host[:, 0])).pin_memory()
+    hostR = torch.from_numpy(np.ascontiguousarray(host[:, 1])).pin_memory()
+    dL, dR = hostL.to(dev), hostR.to(dev)
+    exL = adb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=P, device=local)
+    exR = adb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=P, device=local)
+    cap = exL.capacity
+    mbf = synth.BF; mb = mbf / synth.FX
+    sL = torch.cuda.ExternalStream(exL.stream(), device=dev)
+    kp_ptr, desc_ptr, cnt_ptr, _ = exL.results_device()
+    kpsL_t = adist.as_tensor(kp_ptr, (P, cap, 24), "|u1", dev)
+    descL_t = adist.as_tensor(desc_ptr, (P, cap, 32), "|u1", dev)
+    cntL_t = adist.as_tensor(cnt_ptr, (P,), "<i4", dev)
+    kp_ptrR, desc_ptrR, cnt_ptrR, _ = exR.results_device()
+    cntR_t = adist.as_tensor(cnt_ptrR, (P,), "<i4", dev)
+    gather_bufs = None
+
+    def step():
+        exL.extract_batch_device(dL.data_ptr(), P)
+        exR.extract_batch_device(dR.data_ptr(), P)
+        adb.orb.stereo_match_device(exL, exR, P, mb, mbf)
+        if world > 1:
+            with torch.cuda.stream(sL):
+                return adist.all_gather_records(kpsL_t, descL_t, cntL_t)
+        return None
+
+    def sync_all():
+        exL.sync(); exR.sync()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(Wm):
+        gather_bufs = step()
+    sync_all()
+    n_kp_step = int(cntL_t.sum().item() + cntR_t.sum().item())
+    launches0 = exL.launch_count() + exR.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(sL)
+    for _ in range(K):
+        gather_bufs = step()
+    ev1.record(sL)
+    sync_all()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = exL.launch_count() + exR.launch_count() - launches0
+    tmax = torch.tensor([ms_total], device=dev)
+    nkp = torch.tensor([float(n_kp_step)], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nkp, op=dist.ReduceOp.SUM)
+    ms_step = float(tmax.item()) / K
+    value = float(nkp.item()) / (ms_step * 1e-3)
+
+    # ---- per-stage device times (CUDA events on the handles' own streams), same workload, K steps
+    exL.profile(True); exR.profile(True)
+    stage = np.zeros(4)
+    for _ in range(K):
+        exL.extract_batch_device(dL.data_ptr(), P); exL.sync()
+        stage += np.array(exL.stage_ms())
+    stage /= K
+    exL.profile(False); exR.profile(False)
+    names = ["pyr_resize_kernel(x7)", "fast_cells_kernel", "quadtree_kernel", "orient_describe_kernel"]
+    ncand = 0
+    for l in range(NLEVELS):
+        ncand += len(exL.debug_candidates(0, l))
+    nkp_frame = n_kp_step / (2 * P)
+    alg_bytes = [307200 + (PYR_PX - 307200),                      # level 0 read + levels 1..7 written
+                 PYR_PX + 4 * ncand + 2 * 815,                    # pyramid read once + candidate records + cell counts
+                 4 * ncand * 3 + 4 * nkp_frame,                   # candidates read, key/state scratch, kept list
+                 1849 * nkp_frame + 56 * nkp_frame]               # 43x43 patch per key-point + 32-B descriptor + 24-B record
+    dom = int(np.argmax(stage))
+    peak, peak_src = peaks()
+    achieved = alg_bytes[dom] * P / (stage[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom] * P,
+                "kernel_ms": float(stage[dom]),
+                "stage_ms": {n: float(s) for n, s in zip(names, stage)},
+                "pipeline_achieved_GBps": BYTES_PER_FRAME * 2 * P / (ms_step * 1e-3) / 1e9,
+                "pipeline_frac": BYTES_PER_FRAME * 2 * P / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the host-buffer C-ABI (pinned host images in, key-points/descriptors/matches out)
+    outL = adb.orb.HostResults(P, cap, pinned=True); outR = adb.orb.HostResults(P, cap, pinned=True)
+    outS = adb.orb.HostStereo(P, cap, pinned=True)
+    npL, npR = hostL.numpy(), hostR.numpy()
+
+    def e2e_step():
+        # the reference runs the two extractors on two host threads (src/Frame.cc:81-84); ctypes drops the GIL
+        tR = threading.Thread(target=exR.extract_batch, args=(npR,), kwargs={"out": outR})
+        tR.start()
+        exL.extract_batch(npL, out=outL)
+        tR.join()
+        adb.compute_stereo_matches(exL, exR, P, mb, mbf, out=outS)
+        return int(outL.counts.sum() + outR.counts.sum())
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(K):
+        tot += e2e_step()
+    torch.cuda.synchronize(dev)
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    tot_t = torch.tensor([float(tot)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_t, op=dist.ReduceOp.SUM)
+    e2e = {"value": float(tot_t.item()) / float(t_e2e.item()), "unit": "keypoints/s",
+           "h2d_bytes_per_step": int(2 * P * W * H),
+           "d2h_bytes_per_step": int(2 * (P * cap * (24 + 32) + P * 4) + 4 * P * cap * 4 + P * 4)}
+
+    out = {
+        "metric": "orb_keypoints_per_s", "value": value, "unit": "keypoints/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "640x480 stereo stream, 8-level pyramid, 2000 feat/frame, ORB extract L+R + stereo match"
+                               + (" + NCCL all-gather of descriptor records" if world > 1 else ""),
+                   "pairs_per_step_per_gpu": P, "frames_per_step": 2 * P * world, "keypoints_per_step": int(nkp.item()),
+                   "frames_per_s": 2 * P * world / (ms_step * 1e-3),
+                   "l2_policy": "inputs larger than L2: %.0f MB of images + %.0f MB of pyramid per step vs 126 MB L2"
+                                % (2 * P * W * H / 1e6, 2 * P * (PYR_PX - W * H) / 1e6)},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        n_s = max(8, threads)
+        sample = synth.make_stereo_batch(n_s)
+        v, ms, _ = cpu_reference_run(sample, threads, 2, 1)
+        out["cpu_baseline"] = {"value": v, "unit": "keypoints/s", "cores": threads, "kind": "port",
+                               "sample": f"2 passes over {n_s} stereo pairs ({2 * n_s} frames) of the same workload, oracle port, {threads} host threads"}
+    if not args.no_ba and rank == 0:
+        try:
+            from airdos_b200 import ba_bench
+            out["ba"] = ba_bench.run(local, steps=max(3, K // 2))
+        except ImportError:
+            pass
+        except Exception as e:   # the headline metric must still print
+            out["ba"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(out))
+    exL.close(); exR.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,14 @@ adb_status adb_orb_extract_batch_device(adb_orb_t h, int32_t n_frames, const uin
 adb_status adb_orb_sync(adb_orb_t h);
 void* adb_orb_stream(adb_orb_t h); /* cudaStream_t of the handle */
 
+/* Measurement hooks.  adb_orb_profile(h, 1) makes every following extract call record CUDA events
+ * on the handle's stream around its four stages; adb_orb_stage_ms then returns the device time
+ * of the last call's stages {pyramid, FAST cells, quad-tree, orientation + descriptors} in ms.
+ * adb_orb_launch_count = kernels this handle has launched since it was created. */
+adb_status adb_orb_profile(adb_orb_t h, int32_t enable);
+adb_status adb_orb_stage_ms(adb_orb_t h, float* ms4);
+int64_t adb_orb_launch_count(adb_orb_t h);
+
 /* Device pointers to the resident results of the last extract call:
  * kps [max_batch][capacity], desc [max_batch][capacity][32], counts [max_batch]. */
 adb_status adb_orb_results_device(adb_orb_t h, const adb_keypoint** d_kps, const uint8_t** d_desc,

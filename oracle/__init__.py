@@ -169,3 +169,71 @@ def orb_extract_batch(imgs: np.ndarray, nfeatures: int, scale: float, nlevels: i
     orb_lib().orb_oracle_extract_batch(_p(imgs), f, h * w, w, h, w, nfeatures, scale, nlevels, ini_th, min_th,
                                        _p(kps), _p(desc), cap, _p(counts), threads)
     return kps, desc, counts
+
+
+# ------------------------------------------------------------------------------------------
+# Matcher oracle (oracle/match_oracle.cpp)
+def _match_lib() -> C.CDLL:
+    lib = orb_lib()
+    if not getattr(lib, "_mtyped", False):
+        lib.match_oracle_distance.restype = C.c_int
+        lib.match_oracle_distance.argtypes = [C.c_void_p, C.c_void_p]
+        lib.match_oracle_best2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        lib.match_oracle_stereo.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] +
+                                            [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int] +
+                                            [C.c_void_p] * 4)
+        lib._mtyped = True
+    return lib
+
+
+def hamming(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(_match_lib().match_oracle_distance(_p(a), _p(b)))
+
+
+def best2(q: np.ndarray, t: np.ndarray, cand_off: np.ndarray | None = None, cand_idx: np.ndarray | None = None):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    nq = len(q)
+    bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32); sd = np.zeros(nq, np.int32)
+    if cand_off is not None:
+        cand_off = np.ascontiguousarray(cand_off, np.int32); cand_idx = np.ascontiguousarray(cand_idx, np.int32)
+    _match_lib().match_oracle_best2(_p(q), nq, _p(t), len(t), _p(cand_off) if cand_off is not None else None,
+                                    _p(cand_idx) if cand_idx is not None else None, _p(bi), _p(bd), _p(sd))
+    return bi, bd, sd
+
+
+def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, scale, mb: float, mbf: float, stage: int = 0):
+    """Frame::ComputeStereoMatches restatement.  pyr_l / pyr_r: lists of level ROIs (u8 2-D).
+    Returns (uRight, depth, ham_idx, ham_dist)."""
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    nl = len(pyr_l)
+    lw = np.array([p.shape[1] for p in pyr_l], np.int32); lh = np.array([p.shape[0] for p in pyr_l], np.int32)
+    off = np.zeros(nl, np.int64)
+    off[1:] = np.cumsum(lw.astype(np.int64) * lh)[:-1]
+    pl = np.concatenate([np.ascontiguousarray(p, np.uint8).ravel() for p in pyr_l])
+    pr = np.concatenate([np.ascontiguousarray(p, np.uint8).ravel() for p in pyr_r])
+    sc = np.ascontiguousarray(scale, np.float32)
+    inv = (np.float32(1.0) / sc).astype(np.float32)
+    n = len(kl)
+    ur = np.zeros(n, np.float32); dp = np.zeros(n, np.float32); hi = np.zeros(n, np.int32); hd = np.zeros(n, np.int32)
+    _match_lib().match_oracle_stereo(_p(kl), _p(dl), n, _p(kr), _p(dr), len(kr), _p(pl), _p(pr), _p(off), _p(lw), _p(lh), nl,
+                                     _p(sc), _p(inv), mb, mbf, stage, _p(ur), _p(dp), _p(hi), _p(hd))
+    return ur, dp, hi, hd
+
+
+def stereo_pipeline_batch(pairs: np.ndarray, nfeatures: int, scale: float, nlevels: int, ini_th: int, min_th: int,
+                          mb: float, mbf: float, threads: int = 1):
+    """ExtractORB(left) + ExtractORB(right) + ComputeStereoMatches for u8 [P, 2, H, W] pairs on
+    `threads` host threads -> (counts [P, 2], matched [P], total key-points)."""
+    pairs = np.ascontiguousarray(pairs, np.uint8)
+    p, two, h, w = pairs.shape
+    assert two == 2
+    lib = orb_lib()
+    lib.pipeline_oracle_stereo_batch.restype = C.c_long
+    lib.pipeline_oracle_stereo_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                                 C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    counts = np.zeros((p, 2), np.int32); matched = np.zeros(p, np.int32)
+    total = lib.pipeline_oracle_stereo_batch(_p(pairs), p, w, h, nfeatures, scale, nlevels, ini_th, min_th, mb, mbf, threads,
+                                             _p(counts), _p(matched))
+    return counts, matched, int(total)

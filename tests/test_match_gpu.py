@@ -1,0 +1,72 @@
+"""GPU parity tests of the Hamming kernels and the stereo matcher against the oracle (bit-exact,
+float outputs compared by bit pattern)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def adb():
+    import airdos_b200
+    return airdos_b200
+
+
+def test_best2_all_pairs_lists_ties_and_empty(adb, oracle_mod):
+    rng = np.random.default_rng(0)
+    m = adb.ORBmatcher()
+    q = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (2111, 32), dtype=np.uint8)
+    t[100:140] = t[7]            # duplicates: first in list order must win
+    q[:20] = t[7]
+    for a, b in zip(m.best2(q, t), oracle_mod.best2(q, t)):
+        assert (a == b).all()
+    lens = rng.integers(0, 60, len(q)); lens[::7] = 0
+    off = np.zeros(len(q) + 1, np.int32); off[1:] = np.cumsum(lens)
+    idx = rng.integers(0, len(t), off[-1]).astype(np.int32)
+    idx[rng.integers(0, len(idx), 500)] = 7
+    got, ref = m.best2(q, t, off, idx), oracle_mod.best2(q, t, off, idx)
+    for a, b in zip(got, ref):
+        assert (a == b).all()
+    assert (got[0][::7] == -1).all() and (got[1][::7] == 256).all() and (got[2][::7] == 256).all()
+    # no targets at all
+    bi, bd, sd = m.best2(q[:5], np.zeros((0, 32), np.uint8))
+    assert (bi == -1).all() and (bd == 256).all() and (sd == 256).all()
+    # linearity-style property at size: distance to self is 0 and symmetric argmin of a permutation
+    perm = rng.permutation(len(t))
+    bi, bd, _ = m.best2(t[perm], t)
+    assert (bd == 0).all() and (t[bi] == t[perm]).all()
+    m.close()
+
+
+@pytest.mark.parametrize("nf,w,h", [(2000, 640, 480), (1000, 640, 480), (1500, 640, 360)])
+def test_stereo_matches_oracle(adb, oracle_mod, nf, w, h):
+    from airdos_b200 import synth
+    F = 3
+    pairs = synth.make_stereo_batch(F, w, h, start=40)
+    exL = adb.ORBextractor(nf, 1.2, 8, 12, 7, w, h, max_batch=F)
+    exR = adb.ORBextractor(nf, 1.2, 8, 12, 7, w, h, max_batch=F)
+    kl, dl, cl = exL.extract_batch(pairs[:, 0])
+    kr, dr, cr = exR.extract_batch(pairs[:, 1])
+    mbf = synth.BF; mb = mbf / synth.FX
+    ur, dp, bi, bd = adb.compute_stereo_matches(exL, exR, F, mb, mbf)
+    sc = np.array(exL.GetScaleFactors(), np.float32)
+    for f in range(F):
+        nl, nr = cl[f], cr[f]
+        o = oracle_mod.stereo_match(kl[f, :nl], dl[f, :nl], kr[f, :nr], dr[f, :nr], exL.pyramid(f), exR.pyramid(f), sc, mb, mbf)
+        assert (o[1] > 0).sum() > 100
+        for got, ref in zip((ur, dp, bi, bd), o):
+            assert (got[f, :nl].view(np.uint32) == ref.view(np.uint32)).all()
+    exL.close(); exR.close()
+
+
+def test_stereo_no_matches_is_a_noop(adb):
+    """Unrelated left / right images: few or no matches; the empty median cut must not crash (D.8)."""
+    from airdos_b200 import synth
+    L = synth.make_stereo_pair(1)[0]
+    R = np.full_like(L, 90)
+    exL = adb.ORBextractor(1000, 1.2, 8, 12, 7); exR = adb.ORBextractor(1000, 1.2, 8, 12, 7)
+    exL.extract_batch(L[None]); exR.extract_batch(R[None])
+    ur, dp, bi, bd = adb.compute_stereo_matches(exL, exR, 1, 0.25, 193.137)
+    assert (ur == -1).all() and (dp == -1).all() and (bi == -1).all()
+    exL.close(); exR.close()

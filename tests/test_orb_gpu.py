@@ -1,0 +1,142 @@
+"""GPU parity tests of the CUDA extractor (through the C-ABI) against the CPU oracle and the
+committed cv2-derived golden fixtures.  Bar: bit-exact key-points (incl. float angle patterns),
+descriptors, pyramids and FAST candidate lists."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def adb():
+    import airdos_b200
+    return airdos_b200
+
+
+def _same(kps, desc, ref):
+    return len(kps) == len(ref["kps"]) and kps.tobytes() == ref["kps"].tobytes() and bool((desc == ref["desc"]).all())
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "orb_*.npz"))), ids=os.path.basename)
+def test_cuda_matches_golden_fixture(adb, path):
+    g = np.load(path, allow_pickle=False)
+    nf, nl, ini, mn = [int(v) for v in g["params"]]
+    img = g["image"]
+    mask = g["mask"] if g["mask"].size else None
+    ex = adb.ORBextractor(nf, float(g["scale"]), nl, ini, mn, img.shape[1], img.shape[0])
+    kps, desc = ex(img, mask)
+    assert len(kps) == len(g["kps"])
+    assert kps.tobytes() == g["kps"].tobytes()
+    assert (desc == g["desc"]).all()
+    pyr = ex.pyramid(0)
+    assert [p.shape for p in pyr] == [tuple(s) for s in g["pyramid_sizes"]]
+    assert [int(p.astype(np.int64).sum()) for p in pyr] == [int(v) for v in g["pyramid_sums"]]
+    ex.close()
+
+
+@pytest.mark.parametrize("w,h,nf,ini,mn,masked", [(640, 480, 1000, 12, 7, False), (640, 480, 2000, 12, 7, False),
+                                                  (640, 480, 1000, 12, 7, True), (640, 360, 1500, 12, 7, False),
+                                                  (320, 240, 500, 20, 7, True), (333, 251, 700, 20, 7, False),
+                                                  (752, 480, 1200, 20, 7, False), (1241, 376, 2000, 20, 7, False)])
+def test_cuda_matches_oracle_batch(adb, oracle_mod, w, h, nf, ini, mn, masked):
+    """Seeded frames, batched (ragged sizes, odd pitches, two quad-tree roots for wide images)."""
+    from airdos_b200 import synth
+    F = 3
+    imgs = np.stack([synth.make_stereo_pair(10 + f, w, h)[f % 2] for f in range(F)])
+    masks = np.stack([synth.make_mask(20 + f, w, h, 3) for f in range(F)]) if masked else None
+    ex = adb.ORBextractor(nf, 1.2, 8, ini, mn, w, h, max_batch=F)
+    kps, desc, cnt = ex.extract_batch(imgs, masks)
+    for f in range(F):
+        o = oracle_mod.orb_extract(imgs[f], None if masks is None else masks[f], nf, 1.2, 8, ini, mn, want_pyramid=True)
+        for a, b in zip(ex.pyramid(f), o["pyramid"]):
+            assert (a == b).all()
+        assert [len(ex.debug_candidates(f, l)) for l in range(8)] == list(o["cand_counts"])
+        assert _same(kps[f, :cnt[f]], desc[f, :cnt[f]], o), f"frame {f}"
+    # single-frame call on the same handle gives the same answer as the batch (idempotence)
+    k1, d1 = ex(imgs[1], None if masks is None else masks[1])
+    assert k1.tobytes() == kps[1, :cnt[1]].tobytes() and (d1 == desc[1, :cnt[1]]).all()
+    ex.close()
+
+
+def test_device_resident_path_and_unaligned_input(adb, oracle_mod):
+    import torch
+    from airdos_b200 import synth
+    F, w, h = 4, 640, 480
+    imgs = np.stack([synth.make_stereo_pair(30 + f)[0] for f in range(F)])
+    ex = adb.ORBextractor(2000, 1.2, 8, 12, 7, w, h, max_batch=F)
+    ref_k, ref_d, ref_c = ex.extract_batch(imgs)
+    # aligned device buffer: level 0 is read in place
+    t = torch.from_numpy(imgs).cuda()
+    ex.extract_batch_device(t.data_ptr(), F)
+    ex.sync()
+    k, d, c = ex.download(0, F)
+    assert (c == ref_c).all() and k.tobytes() == ref_k.tobytes() and (d == ref_d).all()
+    # unaligned base pointer (+1 byte): staged through the internal copy
+    buf = torch.zeros(F * w * h + 64, dtype=torch.uint8, device="cuda")
+    buf[1:1 + F * w * h] = t.flatten()
+    ex.extract_batch_device(buf.data_ptr() + 1, F)
+    ex.sync()
+    k, d, c = ex.download(0, F)
+    assert (c == ref_c).all() and k.tobytes() == ref_k.tobytes() and (d == ref_d).all()
+    o = oracle_mod.orb_extract(imgs[2], None, 2000, 1.2, 8, 12, 7)
+    assert _same(k[2, :c[2]], d[2, :c[2]], o)
+    ex.close()
+
+
+def test_edge_cases(adb, oracle_mod):
+    ex = adb.ORBextractor(1000, 1.2, 8, 12, 7, 640, 480)
+    # flat image: no corners anywhere, count 0 (and the ini -> min fallback runs in every cell)
+    k, d = ex(np.full((480, 640), 128, np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # empty image: silent return like src/ORBextractor.cc:1057-1058
+    k, d = ex(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0
+    # all-zero mask rejects everything
+    from airdos_b200 import synth
+    img = synth.make_stereo_pair(3)[0]
+    k, d = ex(img, np.zeros_like(img))
+    assert len(k) == 0
+    # saturated noise: maximum candidate density (exercises slot capacity and a deep quad-tree)
+    noise = np.random.default_rng(0).integers(0, 2, (480, 640)).astype(np.uint8) * 255
+    k, d = ex(noise)
+    o = oracle_mod.orb_extract(noise, None, 1000, 1.2, 8, 12, 7)
+    assert _same(k, d, o)
+    # wrong size is refused, not silently resized
+    with pytest.raises(adb.AdbError):
+        ex(np.zeros((100, 100), np.uint8))
+    ex.close()
+    # tiny image: upper levels have no FAST cells at all
+    small = synth.make_stereo_pair(5, 96, 80)[0]
+    ex = adb.ORBextractor(200, 1.2, 8, 20, 7, 96, 80)
+    k, d = ex(small)
+    o = oracle_mod.orb_extract(small, None, 200, 1.2, 8, 20, 7)
+    assert _same(k, d, o)
+    ex.close()
+
+
+def test_full_size_batch_properties(adb, oracle_mod):
+    """BASELINE config 2 shape at a full batch: size-independent properties + spot checks vs the oracle."""
+    from airdos_b200 import synth
+    F = 64
+    base = synth.make_stereo_batch(4).reshape(8, 480, 640)
+    imgs = np.concatenate([base] * (F // 8))
+    ex = adb.ORBextractor(2000, 1.2, 8, 12, 7, 640, 480, max_batch=F)
+    kps, desc, cnt = ex.extract_batch(imgs)
+    q = np.array(ex.quotas())
+    for f in range(F):
+        # identical frames give identical results wherever they sit in the batch
+        assert cnt[f] == cnt[f % 8]
+        assert kps[f, :cnt[f]].tobytes() == kps[f % 8, :cnt[f]].tobytes()
+        assert (desc[f, :cnt[f]] == desc[f % 8, :cnt[f]]).all()
+        k = kps[f, :cnt[f]]
+        assert (np.diff(k["octave"]) >= 0).all()                        # levels concatenated in order
+        per = np.bincount(k["octave"], minlength=8)
+        assert (per <= q + 2).all() and per.sum() >= 1900
+        assert (k["angle"] >= 0).all() and (k["angle"] < 360).all()
+    for f in (0, 5):
+        assert _same(kps[f, :cnt[f]], desc[f, :cnt[f]], oracle_mod.orb_extract(imgs[f], None, 2000, 1.2, 8, 12, 7))
+    ex.close()
