@@ -96,3 +96,181 @@ def make_mask(seed: int, width: int = 640, height: int = 480, n_rect: int = 3) -
         y = int(rng.integers(0, height - 60))
         m[y:y + h, x:x + w] = 0
     return m
+
+
+# ------------------------------------------------------------------------------------------
+# Bundle-adjustment windows (BASELINE.json configs[3] / configs[4])
+ORB_QUOTA_2000 = np.array([434, 362, 302, 251, 209, 175, 145, 122], np.float64)
+
+
+def _rot_y(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def _small_rot(w):
+    th = np.linalg.norm(w)
+    if th < 1e-12:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def tcw_to_pose(T):
+    """Converter::toSE3Quat on a float32 4x4 (src/Converter.cc:37-47): Eigen::Quaterniond(R) then
+    normalise with w >= 0.  Returns (q[x,y,z,w], t) in float64."""
+    T = np.asarray(T, np.float32).astype(np.float64)
+    m = T[:3, :3]
+    tr = m[0, 0] + m[1, 1] + m[2, 2]
+    q = np.zeros(4)
+    if tr > 0:
+        s = np.sqrt(tr + 1.0)
+        q[3] = 0.5 * s
+        s = 0.5 / s
+        q[0], q[1], q[2] = (m[2, 1] - m[1, 2]) * s, (m[0, 2] - m[2, 0]) * s, (m[1, 0] - m[0, 1]) * s
+    else:
+        i = 0
+        if m[1, 1] > m[0, 0]:
+            i = 1
+        if m[2, 2] > m[i, i]:
+            i = 2
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0)
+        q[i] = 0.5 * s
+        s = 0.5 / s
+        q[3] = (m[k, j] - m[j, k]) * s
+        q[j] = (m[j, i] + m[i, j]) * s
+        q[k] = (m[k, i] + m[i, k]) * s
+    if q[3] < 0:
+        q = -q
+    return q / np.linalg.norm(q), T[:3, 3].copy()
+
+
+def make_ba_problem(n_kf: int = 50, n_points: int = 20000, obs_per_point: int = 6, seed: int = 4000,
+                    outlier_frac: float = 0.03, mono_frac: float = 0.0, n_fixed_extra: int = 0,
+                    noise: bool = True, humans: int = 0, human_poses: int = 4):
+    """Synthetic local-BA window.  Returns a dict of numpy arrays laid out like adb_ba_problem plus
+    the ground truth ('gt_pose_t', 'gt_points').  KF 0 is fixed (+ n_fixed_extra trailing fixed observers)."""
+    rng = np.random.default_rng(seed)
+    K = n_kf + n_fixed_extra
+    yaw = np.cumsum(rng.normal(0, np.deg2rad(2.0), K)); yaw[0] = 0
+    centers = np.zeros((K, 3)); Rwc = np.zeros((K, 3, 3))
+    for k in range(K):
+        Rwc[k] = _rot_y(yaw[k])
+        if k:
+            centers[k] = centers[k - 1] + 0.5 * np.array([np.sin(yaw[k]), 0, np.cos(yaw[k])])
+    Rcw = np.transpose(Rwc, (0, 2, 1))
+    tcw = -np.einsum("kij,kj->ki", Rcw, centers)
+    W, H = 640, 480
+    quota = ORB_QUOTA_2000 / ORB_QUOTA_2000.sum()
+    pts, e_pose, e_point, e_obs, e_info = [], [], [], [], []
+    n_done = 0
+    while n_done < n_points:
+        m = max(1024, (n_points - n_done) * 2)
+        anchor = rng.integers(0, K, m)
+        u = rng.uniform(20, W - 20, m); v = rng.uniform(20, H - 20, m); z = rng.uniform(3.0, 40.0, m)
+        Xc = np.stack([(u - CX) / FX * z, (v - CY) / FY * z, z], 1)
+        Xw = np.einsum("mij,mj->mi", Rwc[anchor], Xc) + centers[anchor]
+        for i in range(m):
+            lo, hi = max(0, anchor[i] - 8), min(K - 1, anchor[i] + 8)
+            win = np.arange(lo, hi + 1)
+            pc = np.einsum("kij,j->ki", Rcw[win], Xw[i]) + tcw[win]
+            zz = pc[:, 2]
+            ok = zz > 1.0
+            uu = np.where(ok, pc[:, 0] / np.where(ok, zz, 1) * FX + CX, -1)
+            vv = np.where(ok, pc[:, 1] / np.where(ok, zz, 1) * FY + CY, -1)
+            ok &= (uu > 5) & (uu < W - 5) & (vv > 5) & (vv < H - 5)
+            vis = win[ok]
+            if len(vis) < obs_per_point:
+                continue
+            sel = np.sort(rng.choice(vis, obs_per_point, replace=False))
+            for k in sel:
+                p = Rcw[k] @ Xw[i] + tcw[k]
+                lvl = rng.choice(8, p=quota)
+                sig = 1.2 ** lvl if noise else 0.0
+                uo, vo = p[0] / p[2] * FX + CX, p[1] / p[2] * FY + CY
+                uro = uo - BF / p[2]
+                n3 = rng.normal(0, 1, 3) * sig
+                if noise and rng.random() < outlier_frac:
+                    n3 = n3 + rng.uniform(-30, 30, 3)
+                mono = rng.random() < mono_frac
+                e_pose.append(k); e_point.append(n_done)
+                uro_n = uro + n3[2]
+                # a negative right-image coordinate means 'not seen by the right camera': monocular edge (mvuRight < 0)
+                e_obs.append([uo + n3[0], vo + n3[1], -1.0 if (mono or uro_n < 0) else uro_n])
+                e_info.append(np.float32(1.0) / (np.float32(1.2 ** lvl) * np.float32(1.2 ** lvl)))
+            pts.append(Xw[i]); n_done += 1
+            if n_done >= n_points:
+                break
+    gt_points = np.array(pts)
+    # initial estimates: perturbed, then through float32 (the map stores cv::Mat float)
+    pose_q = np.zeros((K, 4)); pose_t = np.zeros((K, 3))
+    for k in range(K):
+        R, t = Rcw[k], tcw[k]
+        if k > 0 and noise:
+            R = _small_rot(rng.normal(0, np.deg2rad(0.2), 3)) @ R
+            t = t + rng.normal(0, 0.01, 3)
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+        pose_q[k], pose_t[k] = tcw_to_pose(T.astype(np.float32))
+    points = (gt_points + (rng.normal(0, 0.05, gt_points.shape) if noise else 0)).astype(np.float32).astype(np.float64)
+    fixed = np.zeros(K, np.uint8); fixed[0] = 1; fixed[n_kf:] = 1
+    prob = dict(fx=FX, fy=FY, cx=CX, cy=CY, bf=BF, pose_q=pose_q, pose_t=pose_t, pose_fixed=fixed, points=points,
+                edge_pose=np.array(e_pose, np.int32), edge_point=np.array(e_point, np.int32),
+                edge_obs=np.array(e_obs, np.float32).astype(np.float64), edge_info=np.array(e_info, np.float32).astype(np.float64),
+                gt_pose_t=tcw.copy(), gt_pose_R=Rcw.copy(), gt_points=gt_points)
+    if humans:
+        _add_humans(prob, rng, humans, human_poses, Rcw, tcw, centers, Rwc, noise)
+    return prob
+
+
+# Map.h:49-56 topology of the reference: 14 bones over 14 of the 18 AlphaPose joints, 5 motion joints
+BODY1 = [1, 1, 8, 2, 5, 2, 3, 5, 6, 8, 9, 11, 12, 1]
+BODY2 = [2, 5, 11, 8, 11, 3, 4, 6, 7, 9, 10, 12, 13, 0]
+MAIN_SKELETON = [1, 2, 5, 11, 8]
+_CANON = np.array([[0, -1.60, 0], [0, -1.45, 0], [-0.18, -1.42, 0], [-0.25, -1.15, 0], [-0.27, -0.90, 0], [0.18, -1.42, 0],
+                   [0.25, -1.15, 0], [0.27, -0.90, 0], [-0.10, -0.92, 0], [-0.11, -0.50, 0], [-0.11, -0.08, 0],
+                   [0.10, -0.92, 0], [0.11, -0.50, 0], [0.11, -0.08, 0]])   # 1.7 m skeleton, y down
+
+
+def _add_humans(prob, rng, n_tracks, n_poses, Rcw, tcw, centers, Rwc, noise):
+    """n_tracks trajectories x n_poses consecutive skeletons (14 joints), walking 1.2 m/s, dt = 1."""
+    K = len(tcw)
+    joints, jedge_pose, jedge_joint, jedge_obs, jedge_info = [], [], [], [], []
+    dists, r_i, r_j, r_d = [], [], [], []
+    m_p1, m_p2, m_m, m_dt = [], [], [], []
+    for tr in range(n_tracks):
+        k0 = int(rng.integers(2, max(3, K - n_poses - 2)))
+        heading = rng.uniform(0, 2 * np.pi)
+        vel = 1.2 * np.array([np.cos(heading), 0, np.sin(heading)])
+        base = centers[k0] + Rwc[k0] @ np.array([rng.uniform(-1.5, 1.5), 1.0, rng.uniform(6, 12)])
+        bone_len = [np.linalg.norm(_CANON[a] - _CANON[b]) for a, b in zip(BODY1, BODY2)]
+        d0 = len(dists)
+        dists += [l + (rng.normal(0, 0.02) if noise else 0) for l in bone_len]
+        prev = None
+        for s in range(n_poses):
+            kf = min(k0 + s, K - 1)
+            sk = _CANON + base + vel * s
+            j0 = len(joints)
+            for j in range(14):
+                p = Rcw[kf] @ sk[j] + tcw[kf]
+                uo, vo = p[0] / p[2] * FX + CX, p[1] / p[2] * FY + CY
+                n3 = rng.normal(0, 2.0, 3) if noise else np.zeros(3)
+                joints.append(sk[j] + (rng.normal(0, 0.05, 3) if noise else 0))
+                jedge_pose.append(kf); jedge_joint.append(j0 + j)
+                jedge_obs.append([uo + n3[0], vo + n3[1], max(uo - BF / p[2] + n3[2], 0.0)])   # joints sit 6-12 m away: always positive
+                jedge_info.append(0.5)
+            for b in range(14):
+                r_i.append(j0 + BODY1[b]); r_j.append(j0 + BODY2[b]); r_d.append(d0 + b)
+            if prev is not None:
+                for j in MAIN_SKELETON:
+                    m_p1.append(prev + j); m_p2.append(j0 + j); m_m.append(tr); m_dt.append(1.0)
+            prev = j0
+    nm = n_tracks
+    prob.update(joints=np.array(joints, np.float32).astype(np.float64), jedge_pose=np.array(jedge_pose, np.int32),
+                jedge_joint=np.array(jedge_joint, np.int32), jedge_obs=np.array(jedge_obs, np.float32).astype(np.float64),
+                jedge_info=np.array(jedge_info, np.float64), dists=np.array(dists, np.float32).astype(np.float64),
+                redge_i=np.array(r_i, np.int32), redge_j=np.array(r_j, np.int32), redge_dist=np.array(r_d, np.int32),
+                redge_info=np.full(len(r_i), 20.0), motion_q=np.tile(np.array([0, 0, 0, 1.0]), (nm, 1)), motion_t=np.zeros((nm, 3)),
+                medge_p1=np.array(m_p1, np.int32), medge_p2=np.array(m_p2, np.int32), medge_motion=np.array(m_m, np.int32),
+                medge_dt=np.array(m_dt, np.float64), medge_info=np.full(len(m_p1), 20.0))

@@ -173,6 +173,113 @@ adb_status adb_stereo_match_device(adb_orb_t left, adb_orb_t right, int32_t n_fr
 adb_status adb_stereo_results_device(adb_orb_t left, const float** d_u_right, const float** d_depth,
                                      const int32_t** d_best_idx, const int32_t** d_best_dist);
 
+
+/* ---------------------------------------------------------------------------------------
+ * Bundle adjustment: Optimizer::LocalBundleAdjustment (src/Optimizer.cc:431-731) and
+ * Optimizer::LocalBundleAdjustmentHumanTrajactory (src/Optimizer.cc:1496-2222) as one flat
+ * problem.  The g2o graph (vertices looked up by id, edges with virtual linearizeOplus) becomes
+ * index arrays; what stays identical is the arithmetic: g2o::EdgeStereoSE3ProjectXYZ /
+ * EdgeSE3ProjectXYZ residuals and Jacobians (Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:
+ * 103-234), Huber IRLS (core/robust_kernel_impl.cpp:78-92, core/base_binary_edge.hpp:55-121),
+ * Schur complement on the marginalised points (core/block_solver.hpp:354-486), Levenberg-
+ * Marquardt control (core/optimization_algorithm_levenberg.cpp:61-189) and the two-round
+ * schedule with chi2 gates of the two Optimizer functions.
+ *
+ * Poses are g2o::SE3Quat (unit quaternion x,y,z,w + translation, world -> camera), exactly
+ * what Converter::toSE3Quat (src/Converter.cc:37-47) hands to g2o; adb_ba_pose_from_tcw /
+ * adb_ba_pose_to_tcw do that float <-> double conversion for the shim.
+ * All arrays are host memory; in/out arrays are updated in place on success. */
+typedef struct adb_ba_problem {
+    double fx, fy, cx, cy, bf;       /* KeyFrame::fx.. mbf (src/Optimizer.cc:571-575, 596-600) */
+    /* g2o::VertexSE3Expmap per key-frame (local + fixed), src/Optimizer.cc:494-516 */
+    int32_t n_poses;
+    double* pose_q;                  /* [n_poses][4] in/out */
+    double* pose_t;                  /* [n_poses][3] in/out */
+    const uint8_t* pose_fixed;       /* [n_poses] */
+    /* g2o::VertexSBAPointXYZ, marginalised, per static MapPoint, src/Optimizer.cc:541-548 */
+    int32_t n_points;
+    double* points;                  /* [n_points][3] in/out */
+    /* EdgeStereoSE3ProjectXYZ (obs[2] >= 0) / EdgeSE3ProjectXYZ (obs[2] < 0), src/Optimizer.cc:550-618 */
+    int32_t n_edges;
+    const int32_t* edge_pose;        /* [n_edges] */
+    const int32_t* edge_point;       /* [n_edges] */
+    const double* edge_obs;          /* [n_edges][3] u, v, u_right */
+    const double* edge_info;         /* [n_edges] invSigma2 (information = invSigma2 * I) */
+    /* ---- articulated-human part (all counts may be 0), src/Optimizer.cc:1732-1957 ---- */
+    int32_t n_joints;                /* MapHumanKey vertices: VertexSBAPointXYZ, NOT marginalised */
+    double* joints;                  /* [n_joints][3] in/out */
+    int32_t n_joint_edges;           /* EdgeStereoSE3ProjectXYZ pose <-> joint, information SigmaHuman * I */
+    const int32_t* jedge_pose;
+    const int32_t* jedge_joint;
+    const double* jedge_obs;         /* [n_joint_edges][3] */
+    const double* jedge_info;        /* [n_joint_edges] */
+    int32_t n_dists;                 /* VertexDistanceDouble (include/g2o_vertex_distance.h:28-45) */
+    double* dists;                   /* [n_dists] in/out */
+    int32_t n_rigid_edges;           /* EdgeRigidBodyDouble (include/g2o_edge_rigidbody.h:67-149) */
+    const int32_t* redge_i;
+    const int32_t* redge_j;
+    const int32_t* redge_dist;
+    const double* redge_info;        /* [n_rigid_edges] SigmaRigidity */
+    int32_t n_motions;               /* VertexSE3 (include/g2o_vertex_se3.h:65-133): Isometry3 as quaternion + translation */
+    double* motion_q;                /* [n_motions][4] in/out */
+    double* motion_t;                /* [n_motions][3] in/out */
+    int32_t n_motion_edges;          /* LandmarkMotionTernaryEdge (include/g2o_dyn_slam3d.h:11-101) */
+    const int32_t* medge_p1;
+    const int32_t* medge_p2;
+    const int32_t* medge_motion;
+    const double* medge_dt;          /* [n_motion_edges] delta_t */
+    const double* medge_info;        /* [n_motion_edges] SigmaMotion */
+} adb_ba_problem;
+
+typedef struct adb_ba_options {
+    int32_t iterations[2];           /* optimize(5), optimize(10): src/Optimizer.cc:625,667; round 2 skipped when 0 */
+    int32_t max_trials;              /* maxTrialsAfterFailure = 10 */
+    double tau;                      /* 1e-5: lambda_0 = tau * max diag(H) */
+    double chi2_mono, chi2_stereo;   /* 5.991 / 7.815 gates (src/Optimizer.cc:640,653) */
+    double chi2_rigid, chi2_motion;  /* thRanSacRigidity / thRanSacMotion gates (src/Optimizer.cc:2002,2011) */
+    double huber_mono, huber_stereo; /* (float)sqrt(5.991), (float)sqrt(7.815) (src/Optimizer.cc:538-539) */
+    double huber_rigid, huber_motion;/* thRanSacRigidity (not rooted, D.11), (float)sqrt(thRanSacMotion) */
+} adb_ba_options;
+
+#define ADB_BA_TRACE_COLS 5          /* lambda, chi2 before, chi2 after, rho, accepted (0/1) per LM trial */
+typedef struct adb_ba_result {
+    int32_t iterations_run[2];       /* outer LM iterations executed per round */
+    int32_t trials_run;              /* LM trials (= reduced-system solves) over both rounds */
+    int32_t stopped;                 /* 1 if the stop flag ended optimisation early */
+    double chi2_initial;             /* robust chi2 before the first iteration */
+    double chi2_round[2];            /* robust chi2 of the accepted state at the end of each round */
+    double lambda_final;
+    /* optional caller-allocated outputs (NULL to skip) */
+    uint8_t* edge_outlier;           /* [n_edges]  1 = erase list entry (src/Optimizer.cc:671-699) */
+    uint8_t* jedge_outlier;          /* [n_joint_edges] */
+    uint8_t* redge_outlier;          /* [n_rigid_edges] */
+    uint8_t* medge_outlier;          /* [n_motion_edges] */
+    double* edge_chi2;               /* [n_edges] chi2 as the gates saw it */
+    double* trace;                   /* [trace_cap][ADB_BA_TRACE_COLS] */
+    int32_t trace_cap, trace_len;
+} adb_ba_result;
+
+void adb_ba_default_options(adb_ba_options* opt);   /* the constants of Optimizer::LocalBundleAdjustment */
+
+/* Converter::toSE3Quat (src/Converter.cc:37-47) / Converter::toCvMat(SE3Quat) (src/Converter.cc:74-82):
+ * row-major 4x4 float Tcw <-> quaternion (x,y,z,w) + translation in double. */
+void adb_ba_pose_from_tcw(const float* tcw16, double* q4, double* t3);
+void adb_ba_pose_to_tcw(const double* q4, const double* t3, float* tcw16);
+
+typedef struct adb_ba* adb_ba_t;
+adb_status adb_ba_create(int32_t device, adb_ba_t* out);
+adb_status adb_ba_destroy(adb_ba_t s);
+/* Runs the two-round schedule.  `stop` is Optimizer's bool* pbStopFlag (may be NULL), polled before
+ * optimisation and between LM iterations / trials: set before the start -> ADB_ERR_STOPPED and
+ * nothing is written (src/Optimizer.cc:620-622); set during round 1 -> round 2 is skipped but
+ * gates and write-back still run (src/Optimizer.cc:627-631). */
+adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* prob, const adb_ba_options* opt, volatile const uint8_t* stop,
+                        adb_ba_result* res);
+/* Device time in ms of the stages of the last adb_ba_solve: {linearise, schur, reduced solve,
+ * back-substitution + evaluation, everything else}; and the kernel launches it made. */
+adb_status adb_ba_stage_ms(adb_ba_t s, float* ms5);
+int64_t adb_ba_launch_count(adb_ba_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,3 +237,37 @@ def stereo_pipeline_batch(pairs: np.ndarray, nfeatures: int, scale: float, nleve
     total = lib.pipeline_oracle_stereo_batch(_p(pairs), p, w, h, nfeatures, scale, nlevels, ini_th, min_th, mb, mbf, threads,
                                              _p(counts), _p(matched))
     return counts, matched, int(total)
+
+
+# ------------------------------------------------------------------------------------------
+# Bundle-adjustment oracle (oracle/ba_oracle.cpp)
+def ba_lib() -> C.CDLL:
+    from airdos_b200 import ba_types as T
+    lib = _load("libba_oracle.so")
+    if not getattr(lib, "_typed", False):
+        lib.ba_oracle_solve.restype = C.c_int
+        lib.ba_oracle_solve.argtypes = [C.POINTER(T.BAProblem), C.POINTER(T.BAOptions), C.c_void_p, C.POINTER(T.BAResult)]
+        lib.ba_oracle_default_options.argtypes = [C.POINTER(T.BAOptions)]
+        lib.ba_oracle_reproj.restype = C.c_int
+        lib.ba_oracle_reproj.argtypes = [C.POINTER(T.BAProblem)] + [C.c_void_p] * 7
+        lib.ba_oracle_first_step.restype = C.c_int
+        lib.ba_oracle_first_step.argtypes = [C.POINTER(T.BAProblem), C.POINTER(T.BAOptions), C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        lib._typed = True
+    return lib
+
+
+def ba_default_options():
+    from airdos_b200 import ba_types as T
+    o = T.BAOptions()
+    ba_lib().ba_oracle_default_options(C.byref(o))
+    return o
+
+
+def ba_solve(problem_dict: dict, options=None, stop: np.ndarray | None = None, trace_cap: int = 256):
+    """Two-round LM on a copy of `problem_dict` -> (Problem with updated state, Result, status)."""
+    from airdos_b200 import ba_types as T
+    p = T.Problem(problem_dict)
+    r = T.Result(p, trace_cap)
+    o = options or ba_default_options()
+    st = ba_lib().ba_oracle_solve(C.byref(p.c), C.byref(o), _p(stop) if stop is not None else None, C.byref(r.c))
+    return p, r, st
