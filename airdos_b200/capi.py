@@ -66,6 +66,14 @@ SYMBOLS = {
     "adb_stereo_match": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
     "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),
     "adb_stereo_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "adb_ba_default_options": (None, [_vp]),
+    "adb_ba_pose_from_tcw": (None, [_vp, _vp, _vp]),
+    "adb_ba_pose_to_tcw": (None, [_vp, _vp, _vp]),
+    "adb_ba_create": (C.c_int, [_i32, C.POINTER(_vp)]),
+    "adb_ba_destroy": (C.c_int, [_vp]),
+    "adb_ba_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "adb_ba_stage_ms": (C.c_int, [_vp, _fp]),
+    "adb_ba_launch_count": (C.c_int64, [_vp]),
 }
 
 _lib = None

@@ -1,0 +1,1116 @@
+// ba.cu -- sparse bundle adjustment on sm_100a behind adb_ba_solve (include/airdos_b200.h).
+//
+// Replaces Optimizer::LocalBundleAdjustment / LocalBundleAdjustmentHumanTrajactory + the g2o
+// machinery under them (SparseOptimizer, BlockSolver, OptimizationAlgorithmLevenberg, the edge
+// and vertex types) with flat arrays and a handful of kernels per LM trial:
+//
+//   ba_linearize_kernel     computeError + linearizeOplus + constructQuadraticForm for the
+//                           reprojection edges (edges sorted by map point): Hll / bl, one 6x3
+//                           Hpl block per edge, Hpp / bp, robust chi2
+//   ba_dyn_linearize_kernel the same for joint reprojection, rigidity and motion edges, all of
+//                           which live in the dense (non-marginalised) block
+//   ba_dinv_kernel          (Hll + lambda I)^-1 per point, bschur -= Hpl Dinv bl
+//   ba_schur_kernel         Hschur -= Hpl_i Dinv Hpl_j^T over the per-point edge pairs
+//   cusolverDnDpotrf/potrs  dense FP64 Cholesky of the reduced system (bring-up baseline)
+//   ba_pose_update_kernel   exp(dx) * T, additive / right-multiplicative updates of the rest
+//   ba_backsub_kernel       xl = Dinv (bl - Hpl^T xp), trial points, landmark part of the gain ratio
+//   ba_eval_kernel          residuals + robust chi2 of the trial state
+//
+// State is double buffered (current / trial): accepting an LM step swaps two pointers, rejecting
+// it costs nothing (g2o's push / pop copies every vertex).  The LM decision itself is taken on
+// the host from one 48-byte read-back per trial.
+// Accumulation uses FP64 atomics in L2 (RED.ADD.F64): sums are order-dependent at the 1e-16
+// level, far below the 1e-4 parity bar.
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "common.cuh"
+
+namespace adb {
+
+// ----------------------------------------------------------------------------------------
+// small device math (same formulas as oracle/ba_oracle.cpp; Eigen conventions, q = x,y,z,w)
+__host__ __device__ inline void quat_to_rot(const double* q, double* R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+__host__ __device__ inline void rot_to_quat(const double* m, double* q) {
+    double t = m[0] + m[4] + m[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (m[7] - m[5]) * t; q[1] = (m[2] - m[6]) * t; q[2] = (m[3] - m[1]) * t;
+    } else {
+        int i = 0;
+        if (m[4] > m[0]) i = 1;
+        if (m[8] > m[i * 3 + i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+        double qq[3];
+        qq[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (m[k * 3 + j] - m[j * 3 + k]) * t;
+        qq[j] = (m[j * 3 + i] + m[i * 3 + j]) * t;
+        qq[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2];
+    }
+}
+__host__ __device__ inline void quat_normalize_pos(double* q) {
+    if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+__host__ __device__ inline void mat3_mul(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+// VertexSE3Expmap::oplusImpl: T <- exp(d) T  (se3quat.h:217-257, 104-110)
+__device__ inline void pose_oplus(const double* q, const double* t, const double* d, double* qo, double* to) {
+    const double wx = d[0], wy = d[1], wz = d[2];
+    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double O2[9], R[9], V[9];
+    mat3_mul(O, O, O2);
+    if (theta < 0.00001) {
+        for (int i = 0; i < 9; ++i) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+    } else {
+        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3.0);
+        for (int i = 0; i < 9; ++i) {
+            R[i] = (i % 4 == 0 ? 1.0 : 0.0) + a * O[i] + b * O2[i];
+            V[i] = (i % 4 == 0 ? 1.0 : 0.0) + b * O[i] + c * O2[i];
+        }
+    }
+    double qe[4], te[3], Re[9];
+    rot_to_quat(R, qe);
+    quat_normalize_pos(qe);
+    for (int i = 0; i < 3; ++i) te[i] = V[i * 3] * d[3] + V[i * 3 + 1] * d[4] + V[i * 3 + 2] * d[5];
+    quat_to_rot(qe, Re);
+    for (int i = 0; i < 3; ++i) to[i] = te[i] + Re[i * 3] * t[0] + Re[i * 3 + 1] * t[1] + Re[i * 3 + 2] * t[2];
+    const double ax = qe[0], ay = qe[1], az = qe[2], aw = qe[3], bx = q[0], by = q[1], bz = q[2], bw = q[3];
+    qo[3] = aw * bw - ax * bx - ay * by - az * bz;
+    qo[0] = aw * bx + ax * bw + ay * bz - az * by;
+    qo[1] = aw * by + ay * bw + az * bx - ax * bz;
+    qo[2] = aw * bz + az * bw + ax * by - ay * bx;
+    quat_normalize_pos(qo);
+}
+// VertexSE3::oplusImpl (include/g2o_vertex_se3.h:113-122): H <- H * (t = d[0:3], compact quaternion d[3:6])
+__device__ inline void motion_oplus(const double* q, const double* t, const double* d, double* qo, double* to) {
+    double R[9], Ri[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Rn[9];
+    quat_to_rot(q, R);
+    const double w = 1 - (d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    if (!(w < 0)) {
+        const double qi[4] = {d[3], d[4], d[5], sqrt(w)};
+        quat_to_rot(qi, Ri);
+    }
+    mat3_mul(R, Ri, Rn);
+    for (int i = 0; i < 3; ++i) to[i] = t[i] + R[i * 3] * d[0] + R[i * 3 + 1] * d[1] + R[i * 3 + 2] * d[2];
+    rot_to_quat(Rn, qo);
+    const double n = sqrt(qo[0] * qo[0] + qo[1] * qo[1] + qo[2] * qo[2] + qo[3] * qo[3]);
+    qo[0] /= n; qo[1] /= n; qo[2] /= n; qo[3] /= n;
+}
+
+struct Cam { double fx, fy, cx, cy, bf; };
+
+// residual of Edge(Stereo)SE3ProjectXYZ (types_six_dof_expmap.cpp:141-157): float invz and float bf in the stereo model
+__device__ inline int reproj_error(const Cam& C, const double* R, const double* t, const double* X, const double* obs, double* e, double* Xc) {
+    for (int i = 0; i < 3; ++i) Xc[i] = R[i * 3] * X[0] + R[i * 3 + 1] * X[1] + R[i * 3 + 2] * X[2] + t[i];
+    if (obs[2] >= 0) {
+        const float invz = (float)(1.0 / Xc[2]);
+        const float bf = (float)C.bf;
+        const double u = Xc[0] * invz * C.fx + C.cx, v = Xc[1] * invz * C.fy + C.cy;
+        const double ur = u - (double)__fmul_rn(bf, invz);
+        e[0] = obs[0] - u; e[1] = obs[1] - v; e[2] = obs[2] - ur;
+        return 3;
+    }
+    e[0] = obs[0] - (Xc[0] / Xc[2] * C.fx + C.cx);
+    e[1] = obs[1] - (Xc[1] / Xc[2] * C.fy + C.cy);
+    e[2] = 0;
+    return 2;
+}
+__device__ inline void reproj_jacobians(const Cam& C, const double* R, const double* Xc, int dim, double* Ji, double* Jj) {
+    const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = C.fx, fy = C.fy, bf = C.bf;
+    for (int c = 0; c < 3; ++c) {
+        Ji[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
+        Ji[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
+        Ji[6 + c] = dim == 3 ? Ji[c] - bf * R[6 + c] / z2 : 0.0;
+    }
+    Jj[0] = x * y / z2 * fx; Jj[1] = -(1 + (x * x / z2)) * fx; Jj[2] = y / z * fx; Jj[3] = -1. / z * fx; Jj[4] = 0; Jj[5] = x / z2 * fx;
+    Jj[6] = (1 + y * y / z2) * fy; Jj[7] = -x * y / z2 * fy; Jj[8] = -x / z * fy; Jj[9] = 0; Jj[10] = -1. / z * fy; Jj[11] = y / z2 * fy;
+    if (dim == 3) {
+        Jj[12] = Jj[0] - bf * y / z2; Jj[13] = Jj[1] + bf * x / z2; Jj[14] = Jj[2]; Jj[15] = Jj[3]; Jj[16] = 0; Jj[17] = Jj[5] - bf / z2;
+    } else {
+        for (int i = 12; i < 18; ++i) Jj[i] = 0;
+    }
+}
+__device__ inline void huber(double delta, bool robust, double e2, double* rho0, double* rho1) {
+    const double dsqr = delta * delta;
+    if (!robust || e2 <= dsqr) { *rho0 = e2; *rho1 = 1.0; }
+    else { const double s = sqrt(e2); *rho0 = 2 * s * delta - dsqr; *rho1 = delta / s; }
+}
+
+// scalars shared between the kernels and the host LM loop
+struct Scalars {
+    double chi_cur, chi_trial, scale, maxdiag;
+    int info, pad;
+};
+
+struct Opt {
+    double huber_mono, huber_stereo, huber_rigid, huber_motion;
+    int robust;
+};
+
+__device__ inline double block_sum_to(double v, double* target) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0 && v != 0.0) atomicAdd(target, v);
+    }
+    return v;
+}
+
+// ----------------------------------------------------------------------------------------
+// Reprojection edges pose <-> marginalised point, one thread per edge.
+struct StaticEdges {
+    int n;
+    const int* pose; const int* point; const double* obs; const double* info; const uint8_t* level;
+};
+struct State {
+    const double* pq; const double* pt; const double* X; const double* J; const double* D; const double* mq; const double* mt;
+};
+
+constexpr int kBaThreads = 128;
+
+__global__ void __launch_bounds__(kBaThreads) ba_linearize_kernel(Cam C, Opt O, StaticEdges E, State S, const int* __restrict__ off_pose,
+                                                                 int nd, double* __restrict__ H, double* __restrict__ b,
+                                                                 double* __restrict__ Hll, double* __restrict__ bl,
+                                                                 double* __restrict__ W, double* __restrict__ chi_e, Scalars* sc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double rho0 = 0;
+    if (e < E.n && !E.level[e]) {
+        const int ip = E.pose[e], il = E.point[e];
+        double R[9], er[3], Xc[3], Ji[9], Jj[18], rho1;
+        quat_to_rot(S.pq + 4 * ip, R);
+        const int dim = reproj_error(C, R, S.pt + 3 * ip, S.X + 3 * il, E.obs + 3 * e, er, Xc);
+        reproj_jacobians(C, R, Xc, dim, Ji, Jj);
+        const double w0 = E.info[e];
+        const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+        chi_e[e] = c;
+        huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, c, &rho0, &rho1);
+        const double w = rho1 * w0;
+        const double wr[3] = {-w0 * er[0] * rho1, -w0 * er[1] * rho1, -w0 * er[2] * rho1};
+        // Hll (symmetric, 6 unique) and bl
+        double* hl = Hll + 6 * (size_t)il;
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = i; j < 3; ++j, ++u) {
+                double s = 0;
+                for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * w * Ji[k * 3 + j];
+                atomicAdd(hl + u, s);
+            }
+            double s = 0;
+            for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * wr[k];
+            atomicAdd(bl + 3 * (size_t)il + i, s);
+        }
+        const int op = off_pose[ip];
+        double* We = W + 18 * (size_t)e;
+        if (op >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                for (int j = 0; j <= i; ++j) {   // lower triangle of the 6x6 pose block
+                    double s = 0;
+                    for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * w * Jj[k * 6 + j];
+                    atomicAdd(H + (size_t)(op + i) * nd + op + j, s);
+                }
+                double s = 0;
+                for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * wr[k];
+                atomicAdd(b + op + i, s);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double s2 = 0;
+                    for (int k = 0; k < dim; ++k) s2 += Jj[k * 6 + i] * w * Ji[k * 3 + j];
+                    We[i * 3 + j] = s2;
+                }
+            }
+        }
+    }
+    block_sum_to(rho0, &sc->chi_cur);
+}
+
+// Dense-block edges: joint reprojection (type 0), rigidity (1), motion (2); one thread per edge.
+struct DynEdges {
+    int nj, nr, nm;
+    const int* j_pose; const int* j_joint; const double* j_obs; const double* j_info; const uint8_t* j_level;
+    const int* r_i; const int* r_j; const int* r_d; const double* r_info; const uint8_t* r_level;
+    const int* m_p1; const int* m_p2; const int* m_m; const double* m_dt; const double* m_info; const uint8_t* m_level;
+};
+struct DynOff { const int* pose; const int* joint; const int* dist; const int* motion; };
+
+// H(oa.., ob..) += A^T w B restricted to the lower triangle (row >= col); blocks are dim x da / dim x db row-major
+__device__ inline void add_block_lower(double* H, int nd, int oa, int da, const double* A, int ob, int db, const double* B, int dim, double w) {
+    if (oa < 0 || ob < 0) return;
+    for (int i = 0; i < da; ++i)
+        for (int j = 0; j < db; ++j) {
+            if (oa + i < ob + j) continue;
+            double s = 0;
+            for (int k = 0; k < dim; ++k) s += A[k * da + i] * w * B[k * db + j];
+            if (s != 0.0) atomicAdd(H + (size_t)(oa + i) * nd + ob + j, s);
+        }
+}
+__device__ inline void add_rhs(double* b, int oa, int da, const double* A, int dim, const double* wr) {
+    if (oa < 0) return;
+    for (int i = 0; i < da; ++i) {
+        double s = 0;
+        for (int k = 0; k < dim; ++k) s += A[k * da + i] * wr[k];
+        if (s != 0.0) atomicAdd(b + oa + i, s);
+    }
+}
+__device__ inline void motion_error(const State& S, int m, double dt, const double* p1, const double* p2, double* er, double* Rm) {
+    quat_to_rot(S.mq + 4 * m, Rm);
+    const double d[3] = {p2[0] - dt * S.mt[3 * m], p2[1] - dt * S.mt[3 * m + 1], p2[2] - dt * S.mt[3 * m + 2]};
+    for (int i = 0; i < 3; ++i) er[i] = p1[i] - (Rm[i] * d[0] + Rm[3 + i] * d[1] + Rm[6 + i] * d[2]);
+}
+
+// mode 0: linearise into H / b and accumulate chi_cur; mode 1: evaluate only, accumulate chi_trial
+__global__ void __launch_bounds__(kBaThreads) ba_dyn_kernel(Cam C, Opt O, DynEdges E, State S, DynOff off, int nd, double* __restrict__ H,
+                                                           double* __restrict__ b, double* __restrict__ chi_j, double* __restrict__ chi_r,
+                                                           double* __restrict__ chi_m, Scalars* sc, int mode) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double rho0 = 0, rho1 = 1;
+    if (t < E.nj) {
+        const int e = t;
+        if (!E.j_level[e]) {
+            const int ip = E.j_pose[e], ij = E.j_joint[e];
+            double R[9], er[3], Xc[3];
+            quat_to_rot(S.pq + 4 * ip, R);
+            const int dim = reproj_error(C, R, S.pt + 3 * ip, S.J + 3 * ij, E.j_obs + 3 * e, er, Xc);
+            const double w0 = E.j_info[e];
+            const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+            chi_j[e] = c;
+            huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, c, &rho0, &rho1);
+            if (mode == 0) {
+                double Ji[9], Jj[18];
+                reproj_jacobians(C, R, Xc, dim, Ji, Jj);
+                const double w = rho1 * w0;
+                const double wr[3] = {-w0 * er[0] * rho1, -w0 * er[1] * rho1, -w0 * er[2] * rho1};
+                const int op = off.pose[ip], oj = off.joint[ij];
+                add_block_lower(H, nd, oj, 3, Ji, oj, 3, Ji, dim, w); add_rhs(b, oj, 3, Ji, dim, wr);
+                add_block_lower(H, nd, op, 6, Jj, op, 6, Jj, dim, w); add_rhs(b, op, 6, Jj, dim, wr);
+                add_block_lower(H, nd, op, 6, Jj, oj, 3, Ji, dim, w); add_block_lower(H, nd, oj, 3, Ji, op, 6, Jj, dim, w);
+            }
+        }
+    } else if (t < E.nj + E.nr) {
+        const int e = t - E.nj;
+        if (!E.r_level[e]) {
+            const int i1 = E.r_i[e], i2 = E.r_j[e], id = E.r_d[e];
+            const double* a = S.J + 3 * i1; const double* c2 = S.J + 3 * i2;
+            const double d[3] = {a[0] - c2[0], a[1] - c2[1], a[2] - c2[2]};
+            const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            const double er = n - S.D[id];
+            const double w0 = E.r_info[e];
+            const double c = er * (w0 * er);
+            chi_r[e] = c;
+            huber(O.huber_rigid, O.robust, c, &rho0, &rho1);
+            if (mode == 0) {
+                const double w = rho1 * w0;
+                const double wr[1] = {-w0 * er * rho1};
+                double Ja[3] = {0, 0, 0}, Jb[3] = {0, 0, 0};
+                if (n >= 1e-12) for (int k = 0; k < 3; ++k) { Ja[k] = d[k] / n; Jb[k] = -d[k] / n; }
+                const double Jd[1] = {-1.0};
+                const int offs[3] = {off.joint[i1], off.joint[i2], off.dist[id]};
+                const int dims[3] = {3, 3, 1};
+                const double* Js[3] = {Ja, Jb, Jd};
+                for (int u = 0; u < 3; ++u) {
+                    add_rhs(b, offs[u], dims[u], Js[u], 1, wr);
+                    for (int v = 0; v < 3; ++v) add_block_lower(H, nd, offs[u], dims[u], Js[u], offs[v], dims[v], Js[v], 1, w);
+                }
+            }
+        }
+    } else if (t < E.nj + E.nr + E.nm) {
+        const int e = t - E.nj - E.nr;
+        if (!E.m_level[e]) {
+            double er[3], Rm[9];
+            const int m = E.m_m[e];
+            motion_error(S, m, E.m_dt[e], S.J + 3 * E.m_p1[e], S.J + 3 * E.m_p2[e], er, Rm);
+            const double w0 = E.m_info[e];
+            const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+            chi_m[e] = c;
+            huber(O.huber_motion, O.robust, c, &rho0, &rho1);
+            if (mode == 0) {
+                const double w = rho1 * w0;
+                const double wr[3] = {-w0 * er[0] * rho1, -w0 * er[1] * rho1, -w0 * er[2] * rho1};
+                const double J1[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                double J2[9], Jm[18];
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J2[i * 3 + j] = -Rm[j * 3 + i];
+                for (int i = 0; i < 18; ++i) Jm[i] = 0;
+                Jm[0] = E.m_dt[e]; Jm[7] = E.m_dt[e]; Jm[14] = E.m_dt[e];   // convention D.6
+                const int offs[3] = {off.joint[E.m_p1[e]], off.joint[E.m_p2[e]], off.motion[m]};
+                const int dims[3] = {3, 3, 6};
+                const double* Js[3] = {J1, J2, Jm};
+                for (int u = 0; u < 3; ++u) {
+                    add_rhs(b, offs[u], dims[u], Js[u], 3, wr);
+                    for (int v = 0; v < 3; ++v) add_block_lower(H, nd, offs[u], dims[u], Js[u], offs[v], dims[v], Js[v], 3, w);
+                }
+            }
+        }
+    }
+    block_sum_to(rho0, mode == 0 ? &sc->chi_cur : &sc->chi_trial);
+}
+
+// max |diag| over the dense block and the landmark blocks (computeLambdaInit, levenberg.cpp:166-180)
+__global__ void ba_maxdiag_kernel(const double* __restrict__ H, int nd, const double* __restrict__ Hll, const uint8_t* __restrict__ act_point,
+                                  int np, Scalars* sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0;
+    if (i < nd) m = fabs(H[(size_t)i * nd + i]);
+    else if (i - nd < np && act_point[i - nd]) {
+        const double* h = Hll + 6 * (size_t)(i - nd);
+        m = fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5])));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(&sc->maxdiag), (unsigned long long)__double_as_longlong(m));   // m >= 0: order preserved
+}
+
+// S = H (lower) + lambda I, bs = b
+__global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __restrict__ b, int nd, double lambda, double* __restrict__ Sm,
+                                  double* __restrict__ bs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)nd * nd) {
+        const int r = (int)(i / nd), c = (int)(i - (size_t)r * nd);
+        Sm[i] = H[i] + (r == c ? lambda : 0.0);
+    }
+    if (i < (size_t)nd) bs[i] = b[i];
+}
+
+// per point: Dinv = (Hll + lambda I)^-1 by cofactors (Eigen fixed-size inverse), db = Dinv bl
+__global__ void ba_dinv_kernel(const double* __restrict__ Hll, const double* __restrict__ bl, const uint8_t* __restrict__ act_point, int np,
+                               double lambda, double* __restrict__ Dinv, double* __restrict__ db) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= np || !act_point[l]) return;
+    const double* h = Hll + 6 * (size_t)l;
+    const double A[9] = {h[0] + lambda, h[1], h[2], h[1], h[3] + lambda, h[4], h[2], h[4], h[5] + lambda};
+    const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    const double id = 1.0 / det;
+    double B[9];
+    B[0] = c00 * id; B[1] = (A[2] * A[7] - A[1] * A[8]) * id; B[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    B[3] = c01 * id; B[4] = (A[0] * A[8] - A[2] * A[6]) * id; B[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    B[6] = c02 * id; B[7] = (A[1] * A[6] - A[0] * A[7]) * id; B[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+    for (int i = 0; i < 9; ++i) Dinv[9 * (size_t)l + i] = B[i];
+    for (int i = 0; i < 3; ++i) db[3 * (size_t)l + i] = B[i * 3] * bl[3 * l] + B[i * 3 + 1] * bl[3 * l + 1] + B[i * 3 + 2] * bl[3 * l + 2];
+}
+
+// Schur pairs: pair p = (e1, e2) of active edges of one point with off(e1) >= off(e2);
+// S(o1.., o2..) -= W1 Dinv W2^T (lower triangle); when e1 == e2 also bs(o1) -= W1 db.
+__global__ void __launch_bounds__(kBaThreads) ba_schur_kernel(const int2* __restrict__ pairs, int npairs, const int* __restrict__ e_pose,
+                                                             const int* __restrict__ e_point, const int* __restrict__ off_pose,
+                                                             const double* __restrict__ W, const double* __restrict__ Dinv,
+                                                             const double* __restrict__ db, int nd, double* __restrict__ Sm,
+                                                             double* __restrict__ bs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const int2 pr = pairs[p];
+    const int e1 = pr.x, e2 = pr.y;
+    const int l = e_point[e1];
+    const int o1 = off_pose[e_pose[e1]], o2 = off_pose[e_pose[e2]];
+    const double* W1 = W + 18 * (size_t)e1;
+    const double* W2 = W + 18 * (size_t)e2;
+    const double* Di = Dinv + 9 * (size_t)l;
+    double BD[18];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) BD[i * 3 + j] = W1[i * 3] * Di[j] + W1[i * 3 + 1] * Di[3 + j] + W1[i * 3 + 2] * Di[6 + j];
+    double w2[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) w2[i] = W2[i];
+    const bool diag = o1 == o2;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            if (diag && j > i) continue;
+            const double s = BD[i * 3] * w2[j * 3] + BD[i * 3 + 1] * w2[j * 3 + 1] + BD[i * 3 + 2] * w2[j * 3 + 2];
+            atomicAdd(Sm + (size_t)(o1 + i) * nd + o2 + j, -s);
+        }
+    if (e1 == e2) {
+        const double* d = db + 3 * (size_t)l;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) atomicAdd(bs + o1 + i, -(W1[i * 3] * d[0] + W1[i * 3 + 1] * d[1] + W1[i * 3 + 2] * d[2]));
+    }
+}
+
+// dense updates: poses (exp), bone lengths (+), motions (right multiply), joints (+); also the dense
+// part of the gain-ratio denominator sum x (lambda x + b)
+struct DenseSizes { int n_poses, n_dists, n_motions, n_joints; };
+__global__ void ba_dense_update_kernel(DenseSizes N, DynOff off, const double* __restrict__ x, const double* __restrict__ b, double lambda,
+                                       int nd, State cur, double* __restrict__ pq, double* __restrict__ pt, double* __restrict__ D,
+                                       double* __restrict__ mq, double* __restrict__ mt, double* __restrict__ J, Scalars* sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N.n_poses) {
+        const int o = off.pose[i];
+        if (o >= 0) pose_oplus(cur.pq + 4 * i, cur.pt + 3 * i, x + o, pq + 4 * i, pt + 3 * i);
+        else { for (int k = 0; k < 4; ++k) pq[4 * i + k] = cur.pq[4 * i + k]; for (int k = 0; k < 3; ++k) pt[3 * i + k] = cur.pt[3 * i + k]; }
+    } else if (i < N.n_poses + N.n_dists) {
+        const int j = i - N.n_poses, o = off.dist[j];
+        D[j] = cur.D[j] + (o >= 0 ? x[o] : 0.0);
+    } else if (i < N.n_poses + N.n_dists + N.n_motions) {
+        const int j = i - N.n_poses - N.n_dists, o = off.motion[j];
+        if (o >= 0) motion_oplus(cur.mq + 4 * j, cur.mt + 3 * j, x + o, mq + 4 * j, mt + 3 * j);
+        else { for (int k = 0; k < 4; ++k) mq[4 * j + k] = cur.mq[4 * j + k]; for (int k = 0; k < 3; ++k) mt[3 * j + k] = cur.mt[3 * j + k]; }
+    } else if (i < N.n_poses + N.n_dists + N.n_motions + N.n_joints) {
+        const int j = i - N.n_poses - N.n_dists - N.n_motions, o = off.joint[j];
+        for (int k = 0; k < 3; ++k) J[3 * j + k] = cur.J[3 * j + k] + (o >= 0 ? x[o + k] : 0.0);
+    }
+    double s = 0;
+    if (i < nd) s = x[i] * (lambda * x[i] + b[i]);
+    block_sum_to(s, &sc->scale);
+}
+
+// xl = Dinv (bl - W^T xp) per point (edges of a point are contiguous), trial point, landmark part of the scale
+__global__ void __launch_bounds__(kBaThreads) ba_backsub_kernel(const int* __restrict__ point_ptr, const int* __restrict__ e_pose,
+                                                               const uint8_t* __restrict__ e_level, const int* __restrict__ off_pose,
+                                                               const uint8_t* __restrict__ act_point, int np, const double* __restrict__ W,
+                                                               const double* __restrict__ Dinv, const double* __restrict__ bl,
+                                                               const double* __restrict__ x, double lambda, const double* __restrict__ Xcur,
+                                                               double* __restrict__ Xtrial, Scalars* sc) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (l < np) {
+        if (!act_point[l]) {
+            for (int k = 0; k < 3; ++k) Xtrial[3 * (size_t)l + k] = Xcur[3 * (size_t)l + k];
+        } else {
+            double c[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
+            for (int e = point_ptr[l]; e < point_ptr[l + 1]; ++e) {
+                if (e_level[e]) continue;
+                const int o = off_pose[e_pose[e]];
+                if (o < 0) continue;
+                const double* We = W + 18 * (size_t)e;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const double xi = x[o + i];
+                    c[0] -= We[i * 3] * xi; c[1] -= We[i * 3 + 1] * xi; c[2] -= We[i * 3 + 2] * xi;
+                }
+            }
+            const double* Di = Dinv + 9 * (size_t)l;
+            for (int i = 0; i < 3; ++i) {
+                const double xl = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
+                Xtrial[3 * (size_t)l + i] = Xcur[3 * (size_t)l + i] + xl;
+                s += xl * (lambda * xl + bl[3 * (size_t)l + i]);
+            }
+        }
+    }
+    block_sum_to(s, &sc->scale);
+}
+
+// computeActiveErrors + activeRobustChi2 on the trial state (static edges)
+__global__ void __launch_bounds__(kBaThreads) ba_eval_kernel(Cam C, Opt O, StaticEdges E, State S, double* __restrict__ chi_e, Scalars* sc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double rho0 = 0, rho1;
+    if (e < E.n && !E.level[e]) {
+        const int ip = E.pose[e];
+        double R[9], er[3], Xc[3];
+        quat_to_rot(S.pq + 4 * ip, R);
+        const int dim = reproj_error(C, R, S.pt + 3 * ip, S.X + 3 * E.point[e], E.obs + 3 * e, er, Xc);
+        const double w0 = E.info[e];
+        const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+        chi_e[e] = c;
+        huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, c, &rho0, &rho1);
+    }
+    block_sum_to(rho0, &sc->chi_trial);
+}
+
+// chi2 gates + live depth test (src/Optimizer.cc:633-662, 671-699): flag = chi2 > gate || z <= 0
+__global__ void ba_gate_kernel(StaticEdges E, State S, const double* __restrict__ chi_e, double gate_mono, double gate_stereo,
+                               uint8_t* __restrict__ flag) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n) return;
+    const int ip = E.pose[e];
+    double R[9];
+    quat_to_rot(S.pq + 4 * ip, R);
+    const double* X = S.X + 3 * E.point[e];
+    const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + S.pt[3 * ip + 2];
+    const bool stereo = E.obs[3 * e + 2] >= 0;
+    flag[e] = (chi_e[e] > (stereo ? gate_stereo : gate_mono)) || !(z > 0);
+}
+
+// ----------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    adb_status ensure(size_t bytes) {
+        if (bytes <= cap) return ADB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        ADB_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return ADB_OK;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace adb
+
+using namespace adb;
+
+struct adb_ba {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // device buffers
+    DevBuf pq[2], pt[2], X[2], Jt[2], Dd[2], mq[2], mt[2];                         // double-buffered state
+    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, off_pose, act_point;
+    DevBuf j_pose, j_joint, j_obs, j_info, j_level, r_i, r_j, r_d, r_info, r_level, m_p1, m_p2, m_m, m_dt, m_info, m_level;
+    DevBuf off_joint, off_dist, off_motion;
+    DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work;
+    Scalars* h_scal = nullptr;   // pinned
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    long long launches = 0;
+    std::vector<cudaEvent_t> tev;   // per-stage timing events
+};
+
+namespace {
+
+struct Timer {   // accumulates device time per stage with event pairs (only when profiling is on)
+    adb_ba* s;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    size_t next = 0;
+    explicit Timer(adb_ba* s_) : s(s_) {}
+    cudaEvent_t get() {
+        if (next == s->tev.size()) { cudaEvent_t e; cudaEventCreate(&e); s->tev.push_back(e); }
+        return s->tev[next++];
+    }
+    void begin(int stage) { cudaEvent_t a = get(); cudaEventRecord(a, s->stream); spans.push_back({stage, {a, nullptr}}); }
+    void end() { cudaEvent_t b = get(); cudaEventRecord(b, s->stream); spans.back().second.second = b; }
+    void collect() {
+        for (int i = 0; i < 5; ++i) s->stage_ms[i] = 0;
+        for (auto& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.second.first, sp.second.second); s->stage_ms[sp.first] += ms; }
+    }
+};
+
+template <typename T>
+adb_status upload(DevBuf& d, const T* src, size_t n, cudaStream_t st) {
+    adb_status s = d.ensure(std::max<size_t>(n, 1) * sizeof(T));
+    if (s != ADB_OK) return s;
+    if (n) ADB_CUDA(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return ADB_OK;
+}
+
+inline int grid_for(size_t n, int threads) { return (int)std::max<size_t>(1, (n + threads - 1) / threads); }
+
+struct Ctx {
+    adb_ba* s;
+    adb_ba_problem* P;
+    const adb_ba_options* O;
+    adb_ba_result* R;
+    volatile const uint8_t* stop;
+    Timer tm;
+    // host-side derived structure
+    std::vector<int> perm;            // sorted position -> original edge index
+    std::vector<int> se_pose, se_point, ptr;
+    std::vector<double> se_obs, se_info;
+    std::vector<uint8_t> lvl_e, lvl_j, lvl_r, lvl_m, act_point;
+    std::vector<int> off_pose, off_dist, off_motion, off_joint;
+    std::vector<int2> pairs;
+    int nd = 0, cur = 0, chi_last = 0;
+    double lambda = 0, ni = 2;
+    int trace_len = 0;
+    int potrf_lwork = 0;
+    Ctx(adb_ba* s_, adb_ba_problem* p, const adb_ba_options* o, adb_ba_result* r, volatile const uint8_t* st) : s(s_), P(p), O(o), R(r), stop(st), tm(s_) {}
+
+    bool stopped() const { return stop && *stop; }
+
+    State state(int i) const {
+        return State{s->pq[i].as<double>(), s->pt[i].as<double>(), s->X[i].as<double>(), s->Jt[i].as<double>(), s->Dd[i].as<double>(),
+                     s->mq[i].as<double>(), s->mt[i].as<double>()};
+    }
+    StaticEdges sedges() const {
+        return StaticEdges{P->n_edges, s->e_pose.as<int>(), s->e_point.as<int>(), s->e_obs.as<double>(), s->e_info.as<double>(), s->e_level.as<uint8_t>()};
+    }
+    DynEdges dedges() const {
+        return DynEdges{P->n_joint_edges, P->n_rigid_edges, P->n_motion_edges,
+                        s->j_pose.as<int>(), s->j_joint.as<int>(), s->j_obs.as<double>(), s->j_info.as<double>(), s->j_level.as<uint8_t>(),
+                        s->r_i.as<int>(), s->r_j.as<int>(), s->r_d.as<int>(), s->r_info.as<double>(), s->r_level.as<uint8_t>(),
+                        s->m_p1.as<int>(), s->m_p2.as<int>(), s->m_m.as<int>(), s->m_dt.as<double>(), s->m_info.as<double>(), s->m_level.as<uint8_t>()};
+    }
+    DynOff doff() const { return DynOff{s->off_pose.as<int>(), s->off_joint.as<int>(), s->off_dist.as<int>(), s->off_motion.as<int>()}; }
+    Cam cam() const { return Cam{P->fx, P->fy, P->cx, P->cy, P->bf}; }
+    Opt opt(bool robust) const { return Opt{O->huber_mono, O->huber_stereo, O->huber_rigid, O->huber_motion, robust ? 1 : 0}; }
+    int n_dyn() const { return P->n_joint_edges + P->n_rigid_edges + P->n_motion_edges; }
+
+    // ---- one-time upload: edges sorted by point (stable), state
+    adb_status upload_problem() {
+        const int E = P->n_edges, NP = P->n_points;
+        ptr.assign(NP + 1, 0);
+        for (int e = 0; e < E; ++e) {
+            ADB_CHECK(P->edge_point[e] >= 0 && P->edge_point[e] < NP && P->edge_pose[e] >= 0 && P->edge_pose[e] < P->n_poses, ADB_ERR_INVALID,
+                      "edge %d references pose %d / point %d out of range", e, P->edge_pose[e], P->edge_point[e]);
+            ptr[P->edge_point[e] + 1]++;
+        }
+        for (int l = 0; l < NP; ++l) ptr[l + 1] += ptr[l];
+        perm.assign(E, 0);
+        {
+            std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+            for (int e = 0; e < E; ++e) perm[fill[P->edge_point[e]]++] = e;
+        }
+        se_pose.resize(E); se_point.resize(E); se_obs.resize((size_t)3 * E); se_info.resize(E);
+        for (int k = 0; k < E; ++k) {
+            const int e = perm[k];
+            se_pose[k] = P->edge_pose[e]; se_point[k] = P->edge_point[e]; se_info[k] = P->edge_info[e];
+            for (int c = 0; c < 3; ++c) se_obs[(size_t)3 * k + c] = P->edge_obs[(size_t)3 * e + c];
+        }
+        cudaStream_t st = s->stream;
+        adb_status r;
+#define UP(buf, ptr_, n) if ((r = upload(buf, ptr_, (size_t)(n), st)) != ADB_OK) return r
+        UP(s->e_pose, se_pose.data(), E); UP(s->e_point, se_point.data(), E); UP(s->e_obs, se_obs.data(), 3 * (size_t)E);
+        UP(s->e_info, se_info.data(), E); UP(s->point_ptr, ptr.data(), NP + 1);
+        UP(s->pq[0], P->pose_q, 4 * (size_t)P->n_poses); UP(s->pt[0], P->pose_t, 3 * (size_t)P->n_poses); UP(s->X[0], P->points, 3 * (size_t)NP);
+        UP(s->Jt[0], P->joints, 3 * (size_t)P->n_joints); UP(s->Dd[0], P->dists, P->n_dists);
+        UP(s->mq[0], P->motion_q, 4 * (size_t)P->n_motions); UP(s->mt[0], P->motion_t, 3 * (size_t)P->n_motions);
+        UP(s->j_pose, P->jedge_pose, P->n_joint_edges); UP(s->j_joint, P->jedge_joint, P->n_joint_edges);
+        UP(s->j_obs, P->jedge_obs, 3 * (size_t)P->n_joint_edges); UP(s->j_info, P->jedge_info, P->n_joint_edges);
+        UP(s->r_i, P->redge_i, P->n_rigid_edges); UP(s->r_j, P->redge_j, P->n_rigid_edges); UP(s->r_d, P->redge_dist, P->n_rigid_edges);
+        UP(s->r_info, P->redge_info, P->n_rigid_edges);
+        UP(s->m_p1, P->medge_p1, P->n_motion_edges); UP(s->m_p2, P->medge_p2, P->n_motion_edges); UP(s->m_m, P->medge_motion, P->n_motion_edges);
+        UP(s->m_dt, P->medge_dt, P->n_motion_edges); UP(s->m_info, P->medge_info, P->n_motion_edges);
+#undef UP
+        // trial buffers + work arrays
+        DevBuf* pairs2[] = {&s->pq[1], &s->pt[1], &s->X[1], &s->Jt[1], &s->Dd[1], &s->mq[1], &s->mt[1]};
+        const size_t sz2[] = {4 * (size_t)P->n_poses, 3 * (size_t)P->n_poses, 3 * (size_t)NP, 3 * (size_t)P->n_joints, (size_t)P->n_dists,
+                              4 * (size_t)P->n_motions, 3 * (size_t)P->n_motions};
+        for (int i = 0; i < 7; ++i) if ((r = pairs2[i]->ensure(std::max<size_t>(sz2[i], 1) * 8)) != ADB_OK) return r;
+        if ((r = s->Hll.ensure(std::max<size_t>(NP, 1) * 48)) != ADB_OK) return r;
+        if ((r = s->bl.ensure(std::max<size_t>(NP, 1) * 24)) != ADB_OK) return r;
+        if ((r = s->W.ensure(std::max<size_t>(E, 1) * 144)) != ADB_OK) return r;
+        if ((r = s->Dinv.ensure(std::max<size_t>(NP, 1) * 72)) != ADB_OK) return r;
+        if ((r = s->db.ensure(std::max<size_t>(NP, 1) * 24)) != ADB_OK) return r;
+        for (int i = 0; i < 2; ++i) {
+            if ((r = s->chi_e[i].ensure(std::max<size_t>(E, 1) * 8)) != ADB_OK) return r;
+            if ((r = s->chi_j[i].ensure(std::max<size_t>(P->n_joint_edges, 1) * 8)) != ADB_OK) return r;
+            if ((r = s->chi_r[i].ensure(std::max<size_t>(P->n_rigid_edges, 1) * 8)) != ADB_OK) return r;
+            if ((r = s->chi_m[i].ensure(std::max<size_t>(P->n_motion_edges, 1) * 8)) != ADB_OK) return r;
+            ADB_CUDA(cudaMemsetAsync(s->chi_e[i].p, 0, std::max<size_t>(E, 1) * 8, st));
+            ADB_CUDA(cudaMemsetAsync(s->chi_j[i].p, 0, std::max<size_t>(P->n_joint_edges, 1) * 8, st));
+            ADB_CUDA(cudaMemsetAsync(s->chi_r[i].p, 0, std::max<size_t>(P->n_rigid_edges, 1) * 8, st));
+            ADB_CUDA(cudaMemsetAsync(s->chi_m[i].p, 0, std::max<size_t>(P->n_motion_edges, 1) * 8, st));
+        }
+        if ((r = s->flag.ensure(std::max<size_t>(std::max(E, n_dyn()), 1))) != ADB_OK) return r;
+        if ((r = s->scal.ensure(sizeof(Scalars))) != ADB_OK) return r;
+        lvl_e.assign(E, 0); lvl_j.assign(P->n_joint_edges, 0); lvl_r.assign(P->n_rigid_edges, 0); lvl_m.assign(P->n_motion_edges, 0);
+        return ADB_OK;
+    }
+
+    // SparseOptimizer::initializeOptimization(0): active sets, dense layout, Schur pair list; uploads them
+    adb_status build_layout() {
+        const int E = P->n_edges, NP = P->n_points;
+        std::vector<uint8_t> ap(P->n_poses, 0), aj(P->n_joints, 0), ad(P->n_dists, 0), am(P->n_motions, 0);
+        act_point.assign(NP, 0);
+        for (int k = 0; k < E; ++k) if (!lvl_e[k]) { ap[se_pose[k]] = 1; act_point[se_point[k]] = 1; }
+        for (int e = 0; e < P->n_joint_edges; ++e) if (!lvl_j[e]) { ap[P->jedge_pose[e]] = 1; aj[P->jedge_joint[e]] = 1; }
+        for (int e = 0; e < P->n_rigid_edges; ++e) if (!lvl_r[e]) { aj[P->redge_i[e]] = 1; aj[P->redge_j[e]] = 1; ad[P->redge_dist[e]] = 1; }
+        for (int e = 0; e < P->n_motion_edges; ++e) if (!lvl_m[e]) { aj[P->medge_p1[e]] = 1; aj[P->medge_p2[e]] = 1; am[P->medge_motion[e]] = 1; }
+        int o = 0;
+        off_pose.assign(P->n_poses, -1); off_dist.assign(P->n_dists, -1); off_motion.assign(P->n_motions, -1); off_joint.assign(P->n_joints, -1);
+        for (int i = 0; i < P->n_poses; ++i) if (ap[i] && !P->pose_fixed[i]) { off_pose[i] = o; o += 6; }
+        for (int i = 0; i < P->n_dists; ++i) if (ad[i]) { off_dist[i] = o; o += 1; }
+        for (int i = 0; i < P->n_motions; ++i) if (am[i]) { off_motion[i] = o; o += 6; }
+        for (int i = 0; i < P->n_joints; ++i) if (aj[i]) { off_joint[i] = o; o += 3; }
+        nd = o;
+        pairs.clear();
+        for (int l = 0; l < NP; ++l)
+            for (int a = ptr[l]; a < ptr[l + 1]; ++a) {
+                if (lvl_e[a] || off_pose[se_pose[a]] < 0) continue;
+                for (int c = ptr[l]; c < ptr[l + 1]; ++c) {
+                    if (lvl_e[c] || off_pose[se_pose[c]] < 0) continue;
+                    if (off_pose[se_pose[a]] >= off_pose[se_pose[c]]) pairs.push_back(make_int2(a, c));
+                }
+            }
+        cudaStream_t st = s->stream;
+        adb_status r;
+#define UP(buf, v) if ((r = upload(buf, (v).data(), (v).size(), st)) != ADB_OK) return r
+        UP(s->e_level, lvl_e); UP(s->j_level, lvl_j); UP(s->r_level, lvl_r); UP(s->m_level, lvl_m); UP(s->act_point, act_point);
+        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs);
+#undef UP
+        const size_t n2 = std::max<size_t>((size_t)nd * nd, 1);
+        if ((r = s->H.ensure(n2 * 8)) != ADB_OK) return r;
+        if ((r = s->Sm.ensure(n2 * 8)) != ADB_OK) return r;
+        if ((r = s->b.ensure(std::max(nd, 1) * 8)) != ADB_OK) return r;
+        if ((r = s->bs.ensure(std::max(nd, 1) * 8)) != ADB_OK) return r;
+        if (nd > 0) {
+            int lwork = 0;
+            cusolverStatus_t cs = cusolverDnDpotrf_bufferSize(s->solver, CUBLAS_FILL_MODE_UPPER, nd, s->Sm.as<double>(), nd, &lwork);
+            ADB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, ADB_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed (%d)", (int)cs);
+            potrf_lwork = lwork;
+            if ((r = s->work.ensure(std::max<size_t>(lwork, 1) * 8)) != ADB_OK) return r;
+        }
+        return ADB_OK;
+    }
+
+    adb_status read_scalars() {
+        ADB_CUDA(cudaMemcpyAsync(s->h_scal, s->scal.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+        ADB_CUDA(cudaStreamSynchronize(s->stream));
+        return ADB_OK;
+    }
+
+    // buildSystem at the current state (+ chi2 of the current state into chi_*[chi_last])
+    adb_status linearize(bool robust) {
+        cudaStream_t st = s->stream;
+        const int E = P->n_edges, NP = P->n_points;
+        tm.begin(0);
+        ADB_CUDA(cudaMemsetAsync(s->H.p, 0, std::max<size_t>((size_t)nd * nd, 1) * 8, st));
+        ADB_CUDA(cudaMemsetAsync(s->b.p, 0, std::max(nd, 1) * 8, st));
+        ADB_CUDA(cudaMemsetAsync(s->Hll.p, 0, std::max<size_t>(NP, 1) * 48, st));
+        ADB_CUDA(cudaMemsetAsync(s->bl.p, 0, std::max<size_t>(NP, 1) * 24, st));
+        ADB_CUDA(cudaMemsetAsync(s->scal.p, 0, sizeof(Scalars), st));
+        chi_last = cur;
+        if (E > 0) {
+            ba_linearize_kernel<<<grid_for(E, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), state(cur), s->off_pose.as<int>(), nd,
+                                                                               s->H.as<double>(), s->b.as<double>(), s->Hll.as<double>(),
+                                                                               s->bl.as<double>(), s->W.as<double>(), s->chi_e[chi_last].as<double>(),
+                                                                               s->scal.as<Scalars>());
+            ++s->launches;
+        }
+        if (n_dyn() > 0) {
+            ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), state(cur), doff(), nd, s->H.as<double>(),
+                                                                               s->b.as<double>(), s->chi_j[chi_last].as<double>(),
+                                                                               s->chi_r[chi_last].as<double>(), s->chi_m[chi_last].as<double>(),
+                                                                               s->scal.as<Scalars>(), 0);
+            ++s->launches;
+        }
+        ADB_CUDA(cudaGetLastError());
+        tm.end();
+        return ADB_OK;
+    }
+
+    // one LM trial: solve with the current lambda, form the trial state in buffer cur^1, evaluate it
+    adb_status trial(bool robust) {
+        cudaStream_t st = s->stream;
+        const int E = P->n_edges, NP = P->n_points, tr = cur ^ 1;
+        Scalars* sc = s->scal.as<Scalars>();
+        tm.begin(1);
+        // keep chi_cur / maxdiag, reset the rest
+        ADB_CUDA(cudaMemsetAsync(&sc->chi_trial, 0, 2 * sizeof(double), st));
+        ADB_CUDA(cudaMemsetAsync(&sc->info, 0, sizeof(int), st));
+        if (nd > 0) {
+            ba_prepare_kernel<<<grid_for((size_t)nd * nd, 256), 256, 0, st>>>(s->H.as<double>(), s->b.as<double>(), nd, lambda, s->Sm.as<double>(),
+                                                                             s->bs.as<double>());
+            ++s->launches;
+        }
+        if (NP > 0) {
+            ba_dinv_kernel<<<grid_for(NP, 128), 128, 0, st>>>(s->Hll.as<double>(), s->bl.as<double>(), s->act_point.as<uint8_t>(), NP, lambda,
+                                                              s->Dinv.as<double>(), s->db.as<double>());
+            ++s->launches;
+        }
+        if (!pairs.empty()) {
+            ba_schur_kernel<<<grid_for(pairs.size(), kBaThreads), kBaThreads, 0, st>>>(s->pairs.as<int2>(), (int)pairs.size(), s->e_pose.as<int>(),
+                                                                                      s->e_point.as<int>(), s->off_pose.as<int>(), s->W.as<double>(),
+                                                                                      s->Dinv.as<double>(), s->db.as<double>(), nd,
+                                                                                      s->Sm.as<double>(), s->bs.as<double>());
+            ++s->launches;
+        }
+        ADB_CUDA(cudaGetLastError());
+        tm.end();
+        tm.begin(2);
+        if (nd > 0) {
+            // Sm holds the lower triangle in row-major = the upper triangle in cuSOLVER's column-major view
+            cusolverStatus_t cs = cusolverDnDpotrf(s->solver, CUBLAS_FILL_MODE_UPPER, nd, s->Sm.as<double>(), nd, s->work.as<double>(), potrf_lwork, &sc->info);
+            ADB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, ADB_ERR_CUDA, "cusolverDnDpotrf failed (%d)", (int)cs);
+            cs = cusolverDnDpotrs(s->solver, CUBLAS_FILL_MODE_UPPER, nd, 1, s->Sm.as<double>(), nd, s->bs.as<double>(), nd, &sc->pad);
+            ADB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, ADB_ERR_CUDA, "cusolverDnDpotrs failed (%d)", (int)cs);
+            s->launches += 2;
+        }
+        tm.end();
+        tm.begin(3);
+        {
+            const DenseSizes N{P->n_poses, P->n_dists, P->n_motions, P->n_joints};
+            const int nthreads = std::max(nd, P->n_poses + P->n_dists + P->n_motions + P->n_joints);
+            ba_dense_update_kernel<<<grid_for(nthreads, 128), 128, 0, st>>>(N, doff(), s->bs.as<double>(), s->b.as<double>(), lambda, nd, state(cur),
+                                                                           s->pq[tr].as<double>(), s->pt[tr].as<double>(), s->Dd[tr].as<double>(),
+                                                                           s->mq[tr].as<double>(), s->mt[tr].as<double>(), s->Jt[tr].as<double>(), sc);
+            ++s->launches;
+        }
+        if (NP > 0) {
+            ba_backsub_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(s->point_ptr.as<int>(), s->e_pose.as<int>(), s->e_level.as<uint8_t>(),
+                                                                              s->off_pose.as<int>(), s->act_point.as<uint8_t>(), NP, s->W.as<double>(),
+                                                                              s->Dinv.as<double>(), s->bl.as<double>(), s->bs.as<double>(), lambda,
+                                                                              s->X[cur].as<double>(), s->X[tr].as<double>(), sc);
+            ++s->launches;
+        }
+        chi_last = tr;
+        if (E > 0) {
+            // level-1 edges keep their last chi2: copy-forward is not needed because both chi buffers are only
+            // ever written for active edges and gates read the buffer of the last evaluation; seed it first
+            ADB_CUDA(cudaMemcpyAsync(s->chi_e[tr].p, s->chi_e[cur].p, (size_t)E * 8, cudaMemcpyDeviceToDevice, st));
+            ba_eval_kernel<<<grid_for(E, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), state(tr), s->chi_e[tr].as<double>(), sc);
+            ++s->launches;
+        }
+        if (n_dyn() > 0) {
+            if (P->n_joint_edges) ADB_CUDA(cudaMemcpyAsync(s->chi_j[tr].p, s->chi_j[cur].p, (size_t)P->n_joint_edges * 8, cudaMemcpyDeviceToDevice, st));
+            if (P->n_rigid_edges) ADB_CUDA(cudaMemcpyAsync(s->chi_r[tr].p, s->chi_r[cur].p, (size_t)P->n_rigid_edges * 8, cudaMemcpyDeviceToDevice, st));
+            if (P->n_motion_edges) ADB_CUDA(cudaMemcpyAsync(s->chi_m[tr].p, s->chi_m[cur].p, (size_t)P->n_motion_edges * 8, cudaMemcpyDeviceToDevice, st));
+            ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), state(tr), doff(), nd, nullptr, nullptr,
+                                                                               s->chi_j[tr].as<double>(), s->chi_r[tr].as<double>(),
+                                                                               s->chi_m[tr].as<double>(), sc, 1);
+            ++s->launches;
+        }
+        ADB_CUDA(cudaGetLastError());
+        tm.end();
+        return ADB_OK;
+    }
+
+    // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
+    adb_status optimize(int iterations, bool robust, int round, double* chi_out) {
+        int nbad = 0, it_run = 0;
+        double current = 0;
+        adb_status r;
+        for (int it = 0; it < iterations && !stopped(); ++it) {
+            if ((r = linearize(robust)) != ADB_OK) return r;
+            if (it == 0) {
+                tm.begin(4);
+                ba_maxdiag_kernel<<<grid_for(nd + P->n_points, 256), 256, 0, s->stream>>>(s->H.as<double>(), nd, s->Hll.as<double>(),
+                                                                                         s->act_point.as<uint8_t>(), P->n_points, s->scal.as<Scalars>());
+                ++s->launches;
+                tm.end();
+            }
+            if ((r = read_scalars()) != ADB_OK) return r;
+            current = s->h_scal->chi_cur;
+            if (it == 0) {
+                lambda = O->tau * s->h_scal->maxdiag; ni = 2; nbad = 0;
+                if (round == 0) R->chi2_initial = current;
+            }
+            const double ini = current;
+            double rho = 0;
+            int q = 0;
+            do {
+                if ((r = trial(robust)) != ADB_OK) return r;
+                if ((r = read_scalars()) != ADB_OK) return r;
+                const bool ok = s->h_scal->info == 0;
+                double temp = s->h_scal->chi_trial;
+                if (!ok) temp = std::numeric_limits<double>::max();
+                rho = current - temp;
+                double scale = ok ? s->h_scal->scale : 0.0;
+                scale += 1e-3;
+                rho /= scale;
+                const bool good = rho > 0 && std::isfinite(temp);
+                if (R->trace && trace_len < R->trace_cap) {
+                    double* t = R->trace + (size_t)ADB_BA_TRACE_COLS * trace_len++;
+                    t[0] = lambda; t[1] = current; t[2] = temp; t[3] = rho; t[4] = good ? 1 : 0;
+                }
+                R->trials_run++;
+                if (good) {
+                    double alpha = 1. - std::pow((2 * rho - 1), 3);
+                    alpha = std::min(alpha, 2. / 3.);
+                    lambda *= std::max(1. / 3., alpha);
+                    ni = 2;
+                    current = temp;
+                    cur ^= 1;          // accept: the trial buffers become the state (g2o: discardTop)
+                } else {
+                    lambda *= ni;
+                    ni *= 2;           // reject: nothing to restore (g2o: pop)
+                }
+                ++q;
+            } while (rho < 0 && q < O->max_trials && !stopped());
+            ++it_run;
+            if (q == O->max_trials || rho == 0) break;
+            if ((ini - current) * 1e3 < ini) ++nbad; else nbad = 0;
+            if (nbad >= 3) break;
+        }
+        R->iterations_run[round] = it_run;
+        *chi_out = current;
+        return ADB_OK;
+    }
+
+    // gates of all four edge families from the chi2 of the last evaluation; result in host vectors (sorted order for static edges)
+    adb_status gates(std::vector<uint8_t>& fe, std::vector<uint8_t>& fj, std::vector<uint8_t>& fr, std::vector<uint8_t>& fm, std::vector<double>* chi_out) {
+        cudaStream_t st = s->stream;
+        const int E = P->n_edges;
+        fe.assign(E, 0);
+        if (E > 0) {
+            ba_gate_kernel<<<grid_for(E, 256), 256, 0, st>>>(sedges(), state(cur), s->chi_e[chi_last].as<double>(), O->chi2_mono, O->chi2_stereo,
+                                                             s->flag.as<uint8_t>());
+            ++s->launches;
+            ADB_CUDA(cudaGetLastError());
+            ADB_CUDA(cudaMemcpyAsync(fe.data(), s->flag.p, E, cudaMemcpyDeviceToHost, st));
+            if (chi_out) { chi_out->assign(E, 0); ADB_CUDA(cudaMemcpyAsync(chi_out->data(), s->chi_e[chi_last].p, (size_t)E * 8, cudaMemcpyDeviceToHost, st)); }
+        }
+        // the few hundred dense-block edges are gated on the host from their chi2 and the current state
+        std::vector<double> cj(P->n_joint_edges), cr(P->n_rigid_edges), cm(P->n_motion_edges), hq, ht, hj;
+        if (P->n_joint_edges) {
+            ADB_CUDA(cudaMemcpyAsync(cj.data(), s->chi_j[chi_last].p, cj.size() * 8, cudaMemcpyDeviceToHost, st));
+            hq.resize(4 * (size_t)P->n_poses); ht.resize(3 * (size_t)P->n_poses); hj.resize(3 * (size_t)P->n_joints);
+            ADB_CUDA(cudaMemcpyAsync(hq.data(), s->pq[cur].p, hq.size() * 8, cudaMemcpyDeviceToHost, st));
+            ADB_CUDA(cudaMemcpyAsync(ht.data(), s->pt[cur].p, ht.size() * 8, cudaMemcpyDeviceToHost, st));
+            ADB_CUDA(cudaMemcpyAsync(hj.data(), s->Jt[cur].p, hj.size() * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (P->n_rigid_edges) ADB_CUDA(cudaMemcpyAsync(cr.data(), s->chi_r[chi_last].p, cr.size() * 8, cudaMemcpyDeviceToHost, st));
+        if (P->n_motion_edges) ADB_CUDA(cudaMemcpyAsync(cm.data(), s->chi_m[chi_last].p, cm.size() * 8, cudaMemcpyDeviceToHost, st));
+        ADB_CUDA(cudaStreamSynchronize(st));
+        fj.assign(P->n_joint_edges, 0); fr.assign(P->n_rigid_edges, 0); fm.assign(P->n_motion_edges, 0);
+        for (int e = 0; e < P->n_joint_edges; ++e) {
+            double Rm[9];
+            const int ip = P->jedge_pose[e];
+            quat_to_rot(&hq[4 * ip], Rm);
+            const double* X = &hj[3 * (size_t)P->jedge_joint[e]];
+            const double z = Rm[6] * X[0] + Rm[7] * X[1] + Rm[8] * X[2] + ht[3 * ip + 2];
+            fj[e] = cj[e] > O->chi2_stereo || !(z > 0);
+        }
+        for (int e = 0; e < P->n_rigid_edges; ++e) fr[e] = cr[e] > O->chi2_rigid;
+        for (int e = 0; e < P->n_motion_edges; ++e) fm[e] = cm[e] > O->chi2_motion;
+        return ADB_OK;
+    }
+
+    adb_status download_state() {
+        cudaStream_t st = s->stream;
+#define DN(dst, buf, n) if ((n) > 0) ADB_CUDA(cudaMemcpyAsync(dst, buf.p, (size_t)(n) * 8, cudaMemcpyDeviceToHost, st))
+        DN(P->pose_q, s->pq[cur], 4 * (size_t)P->n_poses); DN(P->pose_t, s->pt[cur], 3 * (size_t)P->n_poses); DN(P->points, s->X[cur], 3 * (size_t)P->n_points);
+        DN(P->joints, s->Jt[cur], 3 * (size_t)P->n_joints); DN(P->dists, s->Dd[cur], P->n_dists);
+        DN(P->motion_q, s->mq[cur], 4 * (size_t)P->n_motions); DN(P->motion_t, s->mt[cur], 3 * (size_t)P->n_motions);
+#undef DN
+        ADB_CUDA(cudaStreamSynchronize(st));
+        return ADB_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void adb_ba_default_options(adb_ba_options* o) {
+    if (!o) return;
+    o->iterations[0] = 5; o->iterations[1] = 10; o->max_trials = 10; o->tau = 1e-5;
+    o->chi2_mono = 5.991; o->chi2_stereo = 7.815; o->chi2_rigid = 1.0; o->chi2_motion = 4.0;
+    o->huber_mono = (double)(float)std::sqrt(5.991); o->huber_stereo = (double)(float)std::sqrt(7.815);
+    o->huber_rigid = 1.0; o->huber_motion = (double)(float)std::sqrt(4.0);
+}
+
+void adb_ba_pose_from_tcw(const float* T, double* q, double* t) {
+    double R[9];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)T[i * 4 + j]; t[i] = (double)T[i * 4 + 3]; }
+    rot_to_quat(R, q);
+    quat_normalize_pos(q);
+}
+
+void adb_ba_pose_to_tcw(const double* q, const double* t, float* T) {
+    double R[9];
+    quat_to_rot(q, R);
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T[i * 4 + j] = (float)R[i * 3 + j]; T[i * 4 + 3] = (float)t[i]; }
+    T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+}
+
+adb_status adb_ba_create(int32_t device, adb_ba_t* out) {
+    ADB_CHECK(out, ADB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    adb_status st = select_device(device);
+    if (st != ADB_OK) return st;
+    adb_ba* s = new adb_ba();
+    s->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_scal, sizeof(Scalars));
+    if (e != cudaSuccess) { delete s; return cuda_fail(e, "ba create", __FILE__, __LINE__); }
+    if (cusolverDnCreate(&s->solver) != CUSOLVER_STATUS_SUCCESS || cusolverDnSetStream(s->solver, s->stream) != CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnCreate failed");
+        cudaStreamDestroy(s->stream);
+        delete s;
+        return ADB_ERR_CUDA;
+    }
+    *out = s;
+    return ADB_OK;
+}
+
+adb_status adb_ba_destroy(adb_ba_t s) {
+    if (!s) return ADB_OK;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    DevBuf* all[] = {&s->pq[0], &s->pq[1], &s->pt[0], &s->pt[1], &s->X[0], &s->X[1], &s->Jt[0], &s->Jt[1], &s->Dd[0], &s->Dd[1], &s->mq[0], &s->mq[1],
+                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->off_pose,
+                     &s->act_point, &s->j_pose, &s->j_joint, &s->j_obs, &s->j_info, &s->j_level, &s->r_i, &s->r_j, &s->r_d, &s->r_info, &s->r_level,
+                     &s->m_p1, &s->m_p2, &s->m_m, &s->m_dt, &s->m_info, &s->m_level, &s->off_joint, &s->off_dist, &s->off_motion, &s->H, &s->b,
+                     &s->Sm, &s->bs, &s->Hll, &s->bl, &s->W, &s->Dinv, &s->db, &s->chi_e[0], &s->chi_e[1], &s->chi_j[0], &s->chi_j[1], &s->chi_r[0],
+                     &s->chi_r[1], &s->chi_m[0], &s->chi_m[1], &s->flag, &s->scal, &s->work};
+    for (DevBuf* b : all) b->release();
+    for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
+    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->solver) cusolverDnDestroy(s->solver);
+    cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+    return ADB_OK;
+}
+
+adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, volatile const uint8_t* stop, adb_ba_result* R) {
+    ADB_CHECK(s && P && O && R, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK(P->n_poses >= 1 && P->n_points >= 0 && P->n_edges >= 0, ADB_ERR_INVALID, "empty problem");
+    if (stop && *stop) { set_error("stop flag set before optimisation"); return ADB_ERR_STOPPED; }
+    ADB_CUDA(cudaSetDevice(s->device));
+    Ctx c(s, P, O, R, stop);
+    R->iterations_run[0] = R->iterations_run[1] = 0; R->trials_run = 0; R->stopped = 0; R->trace_len = 0;
+    R->chi2_initial = 0; R->chi2_round[0] = R->chi2_round[1] = 0; R->lambda_final = 0;
+    adb_status r;
+    if ((r = c.upload_problem()) != ADB_OK) return r;
+    if ((r = c.build_layout()) != ADB_OK) return r;
+    double chi = 0;
+    if ((r = c.optimize(O->iterations[0], true, 0, &chi)) != ADB_OK) return r;
+    R->chi2_round[0] = chi;
+    std::vector<uint8_t> fe, fj, fr, fm;
+    const bool more = !c.stopped() && O->iterations[1] > 0;
+    if (c.stopped()) R->stopped = 1;
+    if (more) {
+        if ((r = c.gates(fe, fj, fr, fm, nullptr)) != ADB_OK) return r;
+        for (size_t k = 0; k < fe.size(); ++k) if (fe[k]) c.lvl_e[k] = 1;
+        for (size_t k = 0; k < fj.size(); ++k) if (fj[k]) c.lvl_j[k] = 1;
+        for (size_t k = 0; k < fr.size(); ++k) if (fr[k]) c.lvl_r[k] = 1;
+        for (size_t k = 0; k < fm.size(); ++k) if (fm[k]) c.lvl_m[k] = 1;
+        // the dense layout may shrink: H offsets change, but the state buffers and chi2 arrays stay
+        if ((r = c.build_layout()) != ADB_OK) return r;
+        if ((r = c.optimize(O->iterations[1], false, 1, &chi)) != ADB_OK) return r;
+        R->chi2_round[1] = chi;
+        if (c.stopped()) R->stopped = 1;
+    }
+    R->lambda_final = c.lambda;
+    R->trace_len = c.trace_len;
+    std::vector<double> chi_sorted;
+    if ((r = c.gates(fe, fj, fr, fm, R->edge_chi2 ? &chi_sorted : nullptr)) != ADB_OK) return r;
+    for (int k = 0; k < P->n_edges; ++k) {
+        if (R->edge_outlier) R->edge_outlier[c.perm[k]] = fe[k];
+        if (R->edge_chi2) R->edge_chi2[c.perm[k]] = chi_sorted[k];
+    }
+    if (R->jedge_outlier) for (int e = 0; e < P->n_joint_edges; ++e) R->jedge_outlier[e] = fj[e];
+    if (R->redge_outlier) for (int e = 0; e < P->n_rigid_edges; ++e) R->redge_outlier[e] = fr[e];
+    if (R->medge_outlier) for (int e = 0; e < P->n_motion_edges; ++e) R->medge_outlier[e] = fm[e];
+    if ((r = c.download_state()) != ADB_OK) return r;
+    c.tm.collect();
+    return ADB_OK;
+}
+
+adb_status adb_ba_stage_ms(adb_ba_t s, float* ms5) {
+    ADB_CHECK(s && ms5, ADB_ERR_INVALID, "null argument");
+    for (int i = 0; i < 5; ++i) ms5[i] = s->stage_ms[i];
+    return ADB_OK;
+}
+
+int64_t adb_ba_launch_count(adb_ba_t s) { return s ? s->launches : 0; }
+
+}  // extern "C"
