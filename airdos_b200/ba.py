@@ -66,9 +66,10 @@ class Optimizer:
     LocalBundleAdjustmentHumanTrajactory = LocalBundleAdjustment
 
     def stage_ms(self):
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 6)()
         check(lib().adb_ba_stage_ms(self._s, ms))
-        return dict(zip(("linearize", "schur", "reduced_solve", "backsub_eval", "other"), ms))
+        return dict(zip(("linearize", "schur", "reduced_solve", "backsub_eval", "other", "lm_loop"), ms))
 
     def launch_count(self) -> int:
         return int(lib().adb_ba_launch_count(self._s))
+

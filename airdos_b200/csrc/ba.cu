@@ -587,7 +587,7 @@ struct adb_ba {
     DevBuf off_joint, off_dist, off_motion;
     DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work;
     Scalars* h_scal = nullptr;   // pinned
-    float stage_ms[5] = {0, 0, 0, 0, 0};
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
     std::vector<cudaEvent_t> tev;   // per-stage timing events
 };
@@ -606,8 +606,9 @@ struct Timer {   // accumulates device time per stage with event pairs (only whe
     void begin(int stage) { cudaEvent_t a = get(); cudaEventRecord(a, s->stream); spans.push_back({stage, {a, nullptr}}); }
     void end() { cudaEvent_t b = get(); cudaEventRecord(b, s->stream); spans.back().second.second = b; }
     void collect() {
-        for (int i = 0; i < 5; ++i) s->stage_ms[i] = 0;
+        for (int i = 0; i < 6; ++i) s->stage_ms[i] = 0;
         for (auto& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.second.first, sp.second.second); s->stage_ms[sp.first] += ms; }
+        if (!spans.empty()) cudaEventElapsedTime(&s->stage_ms[5], spans.front().second.first, spans.back().second.second);
     }
 };
 
@@ -1105,9 +1106,9 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
     return ADB_OK;
 }
 
-adb_status adb_ba_stage_ms(adb_ba_t s, float* ms5) {
-    ADB_CHECK(s && ms5, ADB_ERR_INVALID, "null argument");
-    for (int i = 0; i < 5; ++i) ms5[i] = s->stage_ms[i];
+adb_status adb_ba_stage_ms(adb_ba_t s, float* ms6) {
+    ADB_CHECK(s && ms6, ADB_ERR_INVALID, "null argument");
+    for (int i = 0; i < 6; ++i) ms6[i] = s->stage_ms[i];
     return ADB_OK;
 }
 

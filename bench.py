@@ -294,8 +294,8 @@ def main():
                                "sample": f"2 passes over {n_s} stereo pairs ({2 * n_s} frames) of the same workload, oracle port, {threads} host threads"}
     if not args.no_ba and rank == 0:
         try:
-            from airdos_b200 import ba_bench
-            out["ba"] = ba_bench.run(local, steps=max(3, K // 2))
+            import bench_ba
+            out["ba"] = bench_ba.run(local, steps=max(3, K // 2))
         except ImportError:
             pass
         except Exception as e:   # the headline metric must still print

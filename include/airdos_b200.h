@@ -276,8 +276,10 @@ adb_status adb_ba_destroy(adb_ba_t s);
 adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* prob, const adb_ba_options* opt, volatile const uint8_t* stop,
                         adb_ba_result* res);
 /* Device time in ms of the stages of the last adb_ba_solve: {linearise, schur, reduced solve,
- * back-substitution + evaluation, everything else}; and the kernel launches it made. */
-adb_status adb_ba_stage_ms(adb_ba_t s, float* ms5);
+ * back-substitution + evaluation, everything else, whole LM loop from the first linearisation to the
+ * last trial (device events, includes the host's LM decisions between trials)}; and the kernel
+ * launches this handle has made. */
+adb_status adb_ba_stage_ms(adb_ba_t s, float* ms6);
 int64_t adb_ba_launch_count(adb_ba_t s);
 
 #ifdef __cplusplus
