@@ -120,17 +120,33 @@ __device__ __forceinline__ int fast_best(const int (&d)[16]) {
 }
 
 constexpr int kFastThreads = 256;
+constexpr int kMaxCorners = 4608;   // >= inner pixels of the largest supported cell (75 x 60)
 
+__device__ __forceinline__ void load_circle_diffs(const uint8_t* c, int bw, int v, int (&d)[16]) {
+    // OpenCV circle order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+    d[0] = v - c[3 * bw];      d[1] = v - c[3 * bw + 1];  d[2] = v - c[2 * bw + 2];   d[3] = v - c[bw + 3];
+    d[4] = v - c[3];           d[5] = v - c[-bw + 3];     d[6] = v - c[-2 * bw + 2];  d[7] = v - c[-3 * bw + 1];
+    d[8] = v - c[-3 * bw];     d[9] = v - c[-3 * bw - 1]; d[10] = v - c[-2 * bw - 2]; d[11] = v - c[-bw - 3];
+    d[12] = v - c[-3];         d[13] = v - c[bw - 3];     d[14] = v - c[2 * bw - 2];  d[15] = v - c[3 * bw - 1];
+}
+
+// Four phases per (cell, frame) CTA, each a dense loop (no divergent heavy branch):
+//   1 corner test at min(iniTh, minTh) for every pixel of the cell -> unordered corner list in smem
+//   2 exact FAST score for the listed corners only
+//   3 strict 3x3 NMS + mask post-filter for the listed corners -> keep flags
+//   4 row-major ordered compaction of the kept corners into the cell's slot (ini / min rule)
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                  const LevelDev* __restrict__ levels,
                                                                  const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
                                                                  int ini_th, int min_th, uint32_t* __restrict__ cand,
                                                                  int cand_total, uint16_t* __restrict__ cellcnt,
                                                                  int ncells_total) {
-    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kCellBoxWMax];
+    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kCellBoxWMax];    // pixels; reused for the keep flags in phase 3
     __shared__ __align__(16) uint8_t score[kCellBoxHMax * kCellBoxWMax];
+    __shared__ uint16_t clist[kMaxCorners];
     __shared__ uint64_t bar;
     __shared__ int warp_tot[kFastThreads / 32];
+    __shared__ int n_corner;
 
     const int tid = threadIdx.x, f = blockIdx.y;
     const uint32_t ce = __ldg(&cell_table[blockIdx.x]);
@@ -146,19 +162,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
         return;
     }
     const int bw = L.box_w, bh = L.box_h;
-#ifdef ADB_FAST_NO_TMA
-    {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(masks.p[8 + level]) + (size_t)f * L.frame_stride;
-        for (int i = tid; i < bw * bh; i += kFastThreads) {
-            const int r = i / bw, cc = i - r * bw;
-            const int gx = (iniX & ~15) + cc, gy = iniY + r;
-            tile[i] = (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) ? src[(size_t)gy * L.pitch + gx] : 0;
-        }
-    }
-    if (false) {
-#else
     if (tid == 0) {
-#endif
+        n_corner = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
         fence_proxy_async();
@@ -169,75 +174,110 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     // clear the score tile while the box is in flight
     for (int i = tid; i < (bw * bh + 3) / 4; i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0;
     __syncthreads();   // barrier init visible to all waiters
-#ifndef ADB_FAST_NO_TMA
     mbar_wait(&bar, 0);
-#endif
 
     const int iw = cw - 6, ih = ch - 6, npx = iw * ih;
+    const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)iw + 1u;   // p / iw == umulhi(p, rcp) for p < 65536
     const int t_low = min(ini_th, min_th);
+
+    // ---- phase 1: corner test.  Sign bits of (c - (v - t)) and ((v + t) - c) are shifted into two 16-bit rings.
     for (int p = tid; p < npx; p += kFastThreads) {
-        const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+        const int y0 = (int)__umulhi((uint32_t)p, rcp);
+        const int y = y0 + 3, x = p - y0 * iw + 3;
         const uint8_t* c = tile + y * bw + x + dx;
-        const int v = c[0];
-        int d[16];
-        // OpenCV circle order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-        d[0] = v - c[3 * bw];      d[1] = v - c[3 * bw + 1];  d[2] = v - c[2 * bw + 2];   d[3] = v - c[bw + 3];
-        d[4] = v - c[3];           d[5] = v - c[-bw + 3];     d[6] = v - c[-2 * bw + 2];  d[7] = v - c[-3 * bw + 1];
-        d[8] = v - c[-3 * bw];     d[9] = v - c[-3 * bw - 1]; d[10] = v - c[-2 * bw - 2]; d[11] = v - c[-bw - 3];
-        d[12] = v - c[-3];         d[13] = v - c[bw - 3];     d[14] = v - c[2 * bw - 2];  d[15] = v - c[3 * bw - 1];
+        const int v = c[0], vlo = v - t_low, vhi = v + t_low;
         uint32_t hi = 0, lo = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { hi |= (uint32_t)(d[i] > t_low) << i; lo |= (uint32_t)(d[i] < -t_low) << i; }
+#define ADB_RING(off)                                                      \
+        {                                                                  \
+            const int q = c[off];                                          \
+            hi = __funnelshift_l((uint32_t)(q - vlo), hi, 1);              \
+            lo = __funnelshift_l((uint32_t)(vhi - q), lo, 1);              \
+        }
+        ADB_RING(3 * bw) ADB_RING(3 * bw + 1) ADB_RING(2 * bw + 2) ADB_RING(bw + 3) ADB_RING(3) ADB_RING(-bw + 3) ADB_RING(-2 * bw + 2)
+        ADB_RING(-3 * bw + 1) ADB_RING(-3 * bw) ADB_RING(-3 * bw - 1) ADB_RING(-2 * bw - 2) ADB_RING(-bw - 3) ADB_RING(-3) ADB_RING(bw - 3)
+        ADB_RING(2 * bw - 2) ADB_RING(3 * bw - 1)
+#undef ADB_RING
         if (has_run9(hi) || has_run9(lo)) {
-            const int best = fast_best(d);
-            score[y * bw + x] = (uint8_t)(best - 1);   // response = best - 1 (0 never survives the NMS)
+            const int slot = atomicAdd(&n_corner, 1);
+            if (slot < kMaxCorners) clist[slot] = (uint16_t)p;
         }
     }
     __syncthreads();
+    const int nc = min(n_corner, kMaxCorners);
 
-    // NMS + mask; bit k of flags* = pixel tid + k*256
-    uint32_t flagsA = 0, flagsB = 0;
+    // ---- phase 2: exact score of the corners
+    for (int i = tid; i < nc; i += kFastThreads) {
+        const int p = clist[i];
+        const int y0 = (int)__umulhi((uint32_t)p, rcp);
+        const int y = y0 + 3, x = p - y0 * iw + 3;
+        const uint8_t* c = tile + y * bw + x + dx;
+        int d[16];
+        load_circle_diffs(c, bw, c[0], d);
+        score[y * bw + x] = (uint8_t)(fast_best(d) - 1);   // response = best - 1 (0 never survives the NMS)
+    }
+    __syncthreads();
+
+    // ---- phase 3: NMS + mask; flags go where the pixel was (bit 0: kept at minTh, bit 1: kept at iniTh)
     const uint8_t* ml = masks.p[level];
-    for (int k = 0, p = tid; p < npx; ++k, p += kFastThreads) {
-        const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
+    int mineB = 0;
+    for (int i = tid; i < nc; i += kFastThreads) {
+        const int p = clist[i];
+        const int y0 = (int)__umulhi((uint32_t)p, rcp);
+        const int y = y0 + 3, x = p - y0 * iw + 3;
         const uint8_t* s = score + y * bw + x;
         const int v = s[0];
-        if (v == 0) continue;
-        const bool peak = v > s[-1] && v > s[1] && v > s[-bw - 1] && v > s[-bw] && v > s[-bw + 1] && v > s[bw - 1] &&
-                          v > s[bw] && v > s[bw + 1];
-        if (!peak) continue;
-        if (ml && ml[(size_t)f * L.mframe_stride + (size_t)(iniY + y) * L.mpitch + iniX + x] == 0) continue;
-        if (v >= min_th) flagsA |= 1u << k;   // best > minTh
-        if (v >= ini_th) flagsB |= 1u << k;   // best > iniTh
+        bool keep = v > s[-1] && v > s[1] && v > s[-bw - 1] && v > s[-bw] && v > s[-bw + 1] && v > s[bw - 1] && v > s[bw] && v > s[bw + 1];
+        if (keep && ml) keep = ml[(size_t)f * L.mframe_stride + (size_t)(iniY + y) * L.mpitch + iniX + x] != 0;
+        const int fl = keep ? ((v >= min_th ? 1 : 0) | (v >= ini_th ? 2 : 0)) : 0;
+        tile[y * bw + x + dx] = (uint8_t)fl;
+        mineB |= fl & 2;
     }
-    const int anyB = __syncthreads_or(flagsB != 0);
-    const uint32_t sel = anyB ? flagsB : flagsA;
-    uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(blockIdx.x - L.cell_base) * L.slotcap;
+    const int anyB = __syncthreads_or(mineB);
+    const int selbit = anyB ? 2 : 1;
+
+    // ---- phase 4: ordered compaction; warp w owns the contiguous pixel range [w * R, (w + 1) * R)
     const int lane = tid & 31, warp = tid >> 5;
-    int base = 0;
-    for (int k = 0; k * kFastThreads < npx; ++k) {
-        const bool pred = (sel >> k) & 1u;
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pred);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int off = base, tot = 0;
-#pragma unroll
-        for (int w = 0; w < kFastThreads / 32; ++w) {
-            const int t = warp_tot[w];
-            if (w < warp) off += t;
-            tot += t;
+    const int R = (((npx + kFastThreads / 32 - 1) / (kFastThreads / 32)) + 31) & ~31;
+    const int p_begin = warp * R, p_end = min(p_begin + R, npx);
+    int mine = 0;
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+        const int p = p0 + lane;
+        bool pred = false;
+        if (p < p_end) {
+            const int y0 = (int)__umulhi((uint32_t)p, rcp);
+            const int y = y0 + 3, x = p - y0 * iw + 3;
+            pred = score[y * bw + x] != 0 && (tile[y * bw + x + dx] & selbit);
         }
+        mine += __popc(__ballot_sync(0xFFFFFFFFu, pred));
+    }
+    if (lane == 0) warp_tot[warp] = mine;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kFastThreads / 32; ++w) {
+        const int t = warp_tot[w];
+        if (w < warp) off += t;
+        tot += t;
+    }
+    uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(blockIdx.x - L.cell_base) * L.slotcap;
+    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+        const int p = p0 + lane;
+        bool pred = false;
+        int y = 0, x = 0;
+        if (p < p_end) {
+            const int y0 = (int)__umulhi((uint32_t)p, rcp);
+            y = y0 + 3; x = p - y0 * iw + 3;
+            pred = score[y * bw + x] != 0 && (tile[y * bw + x + dx] & selbit);
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pred);
         if (pred) {
-            const int p = tid + k * kFastThreads;
-            const int y = p / iw + 3, x = p - (y - 3) * iw + 3;
             const int o = off + __popc(bal & ((1u << lane) - 1u));
             if (o < L.slotcap)   // cannot trigger: slotcap is the strict-NMS bound
                 slot[o] = (uint32_t)(x + cj * L.wcell) | ((uint32_t)(y + ci * L.hcell) << 12) | ((uint32_t)score[y * bw + x] << 24);
         }
-        base += tot;
-        __syncthreads();
+        off += __popc(bal);
     }
-    if (tid == 0) *cnt_out = (uint16_t)min(base, L.slotcap);
+    if (tid == 0) *cnt_out = (uint16_t)min(tot, L.slotcap);
 }
 
 // =========================================================================================
@@ -575,7 +615,6 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
 // rotated tests read the blurred core.
 constexpr int kDescWarps = 8;
 constexpr int kRawBytes = 2816;          // 43 rows x 64 B, padded to a multiple of 128 B
-constexpr int kHPitch = 40;              // u16 row-pass buffer: 43 rows x 40
 constexpr int kBPitch = 40;              // blurred core: 37 rows x 40
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
@@ -612,10 +651,10 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
+constexpr int kVPitchW = 24;            // 32-bit words per row of the column-pass buffer (48 u16 columns)
 struct DescSmem {
-    uint8_t raw[kDescWarps][kRawBytes];
-    uint16_t hrow[kDescWarps][kPatchBoxH * kHPitch];
-    uint8_t blur[kDescWarps][37 * kBPitch];
+    uint8_t raw[kDescWarps][kRawBytes];               // 43 x 64 B patch; reused for the blurred 37 x 37 core (pitch kBPitch)
+    uint32_t vert[kDescWarps][37 * kVPitchW];         // column pass: 37 rows x 48 u16
     char2 pat[16 * 32];
     uint64_t bar[kDescWarps];
 };
@@ -649,17 +688,18 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     const uint32_t e = list[(size_t)f * list_total + L.list_base + (i - base)];
     const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;
 
-    uint8_t* raw = sm.raw[warp];
+    uint8_t* raw0 = sm.raw[warp];
     uint64_t* bar = &sm.bar[warp];
+    const int x0 = cx - kPatchR, y0 = cy - kPatchR;
     if (lane == 0) {
         fence_proxy_async();
         mbar_expect_tx(bar, kPatchBoxW * kPatchBoxH);
-        tma_load_3d(raw, &maps.m[lvl], bar, (cx - kPatchR) & ~15, cy - kPatchR, f);   // 16-B aligned box origin
+        tma_load_3d(raw0, &maps.m[lvl], bar, x0 & ~15, y0, f);   // 16-B aligned box origin
     }
     mbar_wait(bar, 0);
-    raw += (cx - kPatchR) & 15;   // column 0 of the 43 x 43 patch
+    const int dxp = x0 & 15;
+    uint8_t* raw = raw0 + dxp;   // column 0 of the 43 x 43 patch
     // BORDER_REFLECT_101 at the ROI edge (only key-points within 21 px of it; at most 2 rows / columns)
-    const int x0 = cx - kPatchR, y0 = cy - kPatchR;
     if (y0 < 0 || y0 + 42 >= L.h) {
         for (int r = 0; r < kPatchBoxH; ++r) {
             const int gy = y0 + r;
@@ -683,9 +723,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15, au = abs(u);
+        const uint8_t* col = raw + kPatchR * kPatchBoxW + kPatchR + u;
+#pragma unroll
         for (int v = -15; v <= 15; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = raw[(kPatchR + v) * kPatchBoxW + kPatchR + u];
+            if (au <= c_umax[v < 0 ? -v : v]) {
+                const int val = col[v * kPatchBoxW];
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -698,28 +740,59 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- GaussianBlur 7x7 sigma 2, fixed point {18,34,48,56,48,34,18}/256 twice, (v + 2^15) >> 16
-    uint16_t* hrow = sm.hrow[warp];
-    for (int o = lane; o < kPatchBoxH * 37; o += 32) {
-        const int r = o / 37, c = o - r * 37;   // output column c <-> patch column c + 3
-        const uint8_t* p = raw + r * kPatchBoxW + c;
-        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        hrow[r * kHPitch + c] = (uint16_t)acc;
+    // ---- GaussianBlur 7x7 sigma 2 = fixed-point {18,34,48,56,48,34,18}/256 on both axes, (v + 2^15) >> 16.
+    // Integer and exact, so the pass order is free: columns first, two pixels per 32-bit multiply
+    // (7 x 255 x 56 < 2^16 per 16-bit lane), then rows with DP2A on the 16-bit sums.
+    uint32_t* vert = sm.vert[warp];
+    const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw0) + (dxp >> 2);   // aligned words covering the patch columns
+    const int sh = dxp & 3;                                                         // patch column c sits at u16 column c + sh
+    for (int o = lane; o < 37 * 12; o += 32) {
+        const int r = o / 12, wd = o - r * 12;
+        const uint32_t* p = raw32 + r * (kPatchBoxW / 4) + wd;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const uint32_t k = t == 0 || t == 6 ? 18u : (t == 1 || t == 5 ? 34u : (t == 2 || t == 4 ? 48u : 56u));
+            const uint32_t w = p[t * (kPatchBoxW / 4)];
+            lo += k * (w & 0x00FF00FFu);
+            hi += k * ((w >> 8) & 0x00FF00FFu);
+        }
+        // lo = {col0, col2}, hi = {col1, col3} as 16-bit lanes -> {col0, col1}, {col2, col3}
+        uint2 out;
+        out.x = __byte_perm(lo, hi, 0x5410);
+        out.y = __byte_perm(lo, hi, 0x7632);
+        *reinterpret_cast<uint2*>(vert + r * kVPitchW + 2 * wd) = out;
     }
     __syncwarp();
-    uint8_t* bl = sm.blur[warp];
-    for (int o = lane; o < 37 * 37; o += 32) {
-        const int r = o / 37, c = o - r * 37;
-        const uint16_t* p = hrow + r * kHPitch + c;
-        const uint32_t acc = 18u * (p[0] + p[6 * kHPitch]) + 34u * (p[kHPitch] + p[5 * kHPitch]) +
-                             48u * (p[2 * kHPitch] + p[4 * kHPitch]) + 56u * p[3 * kHPitch];
-        bl[r * kBPitch + c] = (uint8_t)((acc + 32768u) >> 16);
+    uint8_t* bl = raw0;   // the raw patch is dead from here on: blurred core, 37 rows x kBPitch
+    {
+        const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
+        for (int o = lane; o < 37 * 19; o += 32) {
+            const int r = o / 19, pr = o - r * 19;      // outputs c = 2 pr, 2 pr + 1
+            const int j0 = 2 * pr + sh;                 // first u16 column of the window of output c = 2 pr
+            const uint32_t* p = vert + r * kVPitchW + (j0 >> 1);
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;   // a*: windows starting at an even column, b*: at the next (odd) one
+            if (j0 & 1) {
+                a0 = __funnelshift_r(w0, w1, 16); a1 = __funnelshift_r(w1, w2, 16); a2 = __funnelshift_r(w2, w3, 16); a3 = __funnelshift_r(w3, w4, 16);
+                b0 = w1; b1 = w2; b2 = w3; b3 = w4;
+            } else {
+                a0 = w0; a1 = w1; a2 = w2; a3 = w3;
+                b0 = __funnelshift_r(w0, w1, 16); b1 = __funnelshift_r(w1, w2, 16); b2 = __funnelshift_r(w2, w3, 16); b3 = __funnelshift_r(w3, w4, 16);
+            }
+            uint32_t va = __dp2a_lo(a0, kw0, 0u); va = __dp2a_hi(a1, kw0, va); va = __dp2a_lo(a2, kw1, va); va = __dp2a_hi(a3, kw1, va);
+            uint32_t vb = __dp2a_lo(b0, kw0, 0u); vb = __dp2a_hi(b1, kw0, vb); vb = __dp2a_lo(b2, kw1, vb); vb = __dp2a_hi(b3, kw1, vb);
+            bl[r * kBPitch + 2 * pr] = (uint8_t)((va + 32768u) >> 16);
+            if (2 * pr + 1 < 37) bl[r * kBPitch + 2 * pr + 1] = (uint8_t)((vb + 32768u) >> 16);
+        }
     }
     __syncwarp();
 
     // ---- steered rBRIEF (src/ORBextractor.cc:109-148); lane = descriptor byte
     const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
     const uint8_t* ctr = bl + 18 * kBPitch + 18;
     uint32_t byte = 0;
 #pragma unroll
