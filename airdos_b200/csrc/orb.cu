@@ -120,6 +120,7 @@ __device__ __forceinline__ int fast_best(const int (&d)[16]) {
 }
 
 constexpr int kFastThreads = 256;
+constexpr int kMaxKeep = 1152;      // >= ceil(75 / 2) * ceil(60 / 2): strict 3x3 NMS keeps at most one pixel per 2x2 block
 constexpr int kMaxCorners = 4608;   // >= inner pixels of the largest supported cell (75 x 60)
 
 __device__ __forceinline__ void load_circle_diffs(const uint8_t* c, int bw, int v, int (&d)[16]) {
@@ -133,20 +134,20 @@ __device__ __forceinline__ void load_circle_diffs(const uint8_t* c, int bw, int 
 // Four phases per (cell, frame) CTA, each a dense loop (no divergent heavy branch):
 //   1 corner test at min(iniTh, minTh) for every pixel of the cell -> unordered corner list in smem
 //   2 exact FAST score for the listed corners only
-//   3 strict 3x3 NMS + mask post-filter for the listed corners -> keep flags
-//   4 row-major ordered compaction of the kept corners into the cell's slot (ini / min rule)
+//   3 strict 3x3 NMS + mask post-filter for the listed corners -> unordered kept list
+//   4 ini / min rule, then each kept corner's rank in row-major order places it in the cell's slot
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                  const LevelDev* __restrict__ levels,
                                                                  const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
                                                                  int ini_th, int min_th, uint32_t* __restrict__ cand,
                                                                  int cand_total, uint16_t* __restrict__ cellcnt,
                                                                  int ncells_total) {
-    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kCellBoxWMax];    // pixels; reused for the keep flags in phase 3
+    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kCellBoxWMax];
     __shared__ __align__(16) uint8_t score[kCellBoxHMax * kCellBoxWMax];
     __shared__ uint16_t clist[kMaxCorners];
     __shared__ uint64_t bar;
-    __shared__ int warp_tot[kFastThreads / 32];
-    __shared__ int n_corner;
+    __shared__ uint32_t klist[kMaxKeep];
+    __shared__ int n_corner, n_keep, n_sel;
 
     const int tid = threadIdx.x, f = blockIdx.y;
     const uint32_t ce = __ldg(&cell_table[blockIdx.x]);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     }
     const int bw = L.box_w, bh = L.box_h;
     if (tid == 0) {
-        n_corner = 0;
+        n_corner = 0; n_keep = 0; n_sel = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
         fence_proxy_async();
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     }
     __syncthreads();
 
-    // ---- phase 3: NMS + mask; flags go where the pixel was (bit 0: kept at minTh, bit 1: kept at iniTh)
+    // ---- phase 3: NMS + mask for the listed corners -> unordered kept list (p | score << 16 | flags << 24;
+    //      flag bit 0: kept at minTh, bit 1: kept at iniTh)
     const uint8_t* ml = masks.p[level];
     int mineB = 0;
     for (int i = tid; i < nc; i += kFastThreads) {
@@ -229,55 +231,37 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
         bool keep = v > s[-1] && v > s[1] && v > s[-bw - 1] && v > s[-bw] && v > s[-bw + 1] && v > s[bw - 1] && v > s[bw] && v > s[bw + 1];
         if (keep && ml) keep = ml[(size_t)f * L.mframe_stride + (size_t)(iniY + y) * L.mpitch + iniX + x] != 0;
         const int fl = keep ? ((v >= min_th ? 1 : 0) | (v >= ini_th ? 2 : 0)) : 0;
-        tile[y * bw + x + dx] = (uint8_t)fl;
+        if (fl) {
+            const int k = atomicAdd(&n_keep, 1);
+            if (k < kMaxKeep) klist[k] = (uint32_t)p | ((uint32_t)v << 16) | ((uint32_t)fl << 24);
+        }
         mineB |= fl & 2;
     }
     const int anyB = __syncthreads_or(mineB);
-    const int selbit = anyB ? 2 : 1;
+    const uint32_t selmask = (anyB ? 2u : 1u) << 24;
 
-    // ---- phase 4: ordered compaction; warp w owns the contiguous pixel range [w * R, (w + 1) * R)
-    const int lane = tid & 31, warp = tid >> 5;
-    const int R = (((npx + kFastThreads / 32 - 1) / (kFastThreads / 32)) + 31) & ~31;
-    const int p_begin = warp * R, p_end = min(p_begin + R, npx);
-    int mine = 0;
-    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-        const int p = p0 + lane;
-        bool pred = false;
-        if (p < p_end) {
-            const int y0 = (int)__umulhi((uint32_t)p, rcp);
-            const int y = y0 + 3, x = p - y0 * iw + 3;
-            pred = score[y * bw + x] != 0 && (tile[y * bw + x + dx] & selbit);
-        }
-        mine += __popc(__ballot_sync(0xFFFFFFFFu, pred));
-    }
-    if (lane == 0) warp_tot[warp] = mine;
-    __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kFastThreads / 32; ++w) {
-        const int t = warp_tot[w];
-        if (w < warp) off += t;
-        tot += t;
-    }
+    // ---- phase 4: the reference's row-major order = rank of p among the selected entries (a few dozen per cell)
+    const int nk = min(n_keep, kMaxKeep);
     uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(blockIdx.x - L.cell_base) * L.slotcap;
-    for (int p0 = p_begin; p0 < p_end; p0 += 32) {
-        const int p = p0 + lane;
-        bool pred = false;
-        int y = 0, x = 0;
-        if (p < p_end) {
-            const int y0 = (int)__umulhi((uint32_t)p, rcp);
-            y = y0 + 3; x = p - y0 * iw + 3;
-            pred = score[y * bw + x] != 0 && (tile[y * bw + x + dx] & selbit);
+    int nsel = 0;
+    for (int i = tid; i < nk; i += kFastThreads) {
+        const uint32_t me = klist[i];
+        if (!(me & selmask)) continue;
+        const uint32_t myp = me & 0xFFFFu;
+        int rank = 0;
+        for (int j = 0; j < nk; ++j) {
+            const uint32_t o = klist[j];
+            rank += ((o & selmask) != 0) & ((o & 0xFFFFu) < myp);
         }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pred);
-        if (pred) {
-            const int o = off + __popc(bal & ((1u << lane) - 1u));
-            if (o < L.slotcap)   // cannot trigger: slotcap is the strict-NMS bound
-                slot[o] = (uint32_t)(x + cj * L.wcell) | ((uint32_t)(y + ci * L.hcell) << 12) | ((uint32_t)score[y * bw + x] << 24);
-        }
-        off += __popc(bal);
+        const int y0 = (int)__umulhi(myp, rcp);
+        const int y = y0 + 3, x = (int)myp - y0 * iw + 3;
+        if (rank < L.slotcap)   // cannot trigger: slotcap is the strict-NMS bound
+            slot[rank] = (uint32_t)(x + cj * L.wcell) | ((uint32_t)(y + ci * L.hcell) << 12) | (((me >> 16) & 0xFFu) << 24);
+        ++nsel;
     }
-    if (tid == 0) *cnt_out = (uint16_t)min(tot, L.slotcap);
+    if (nsel) atomicAdd(&n_sel, nsel);
+    __syncthreads();
+    if (tid == 0) *cnt_out = (uint16_t)min(n_sel, L.slotcap);
 }
 
 // =========================================================================================
