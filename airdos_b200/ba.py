@@ -65,6 +65,13 @@ class Optimizer:
     # the dynamic window is the same call: the human arrays of the problem dict switch it on
     LocalBundleAdjustmentHumanTrajactory = LocalBundleAdjustment
 
+    def PoseOptimization(self, cam: dict, frames: list):
+        """Optimizer::PoseOptimization for a batch of frames (dicts with pose_q, pose_t, xw, obs, inv_sigma2).
+        Returns a PoseBatch whose pose_q / pose_t / outlier / n_inliers hold the results."""
+        pb = T.PoseBatch(cam, frames)
+        check(lib().adb_pose_optimize(self._s, C.byref(pb.c)))
+        return pb
+
     def stage_ms(self):
         ms = (C.c_float * 6)()
         check(lib().adb_ba_stage_ms(self._s, ms))

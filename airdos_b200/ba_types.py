@@ -86,3 +86,32 @@ class Result:
     @property
     def trace_rows(self):
         return self.trace[:self.c.trace_len]
+
+
+class PoseProblem(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
+                ("n_frames", C.c_int32), ("frame_ptr", _ip), ("pose_q", _dp), ("pose_t", _dp),
+                ("xw", C.POINTER(C.c_float)), ("obs", C.POINTER(C.c_float)), ("inv_sigma2", C.POINTER(C.c_float)),
+                ("outlier", _bp), ("n_inliers", _ip)]
+
+
+class PoseBatch:
+    """Owns the arrays of an adb_pose_problem: frames = list of dicts(pose_q, pose_t, xw[n,3], obs[n,3], inv_sigma2[n])."""
+
+    def __init__(self, cam: dict, frames: list):
+        n = [len(f["xw"]) for f in frames]
+        self.frame_ptr = np.zeros(len(frames) + 1, np.int32); self.frame_ptr[1:] = np.cumsum(n)
+        self.pose_q = np.ascontiguousarray([f["pose_q"] for f in frames], np.float64).reshape(-1, 4)
+        self.pose_t = np.ascontiguousarray([f["pose_t"] for f in frames], np.float64).reshape(-1, 3)
+        cat = lambda k, w: np.ascontiguousarray(np.concatenate([np.asarray(f[k], np.float32).reshape(-1, w) for f in frames]) if frames else np.zeros((0, w)), np.float32)
+        self.xw, self.obs, self.inv_sigma2 = cat("xw", 3), cat("obs", 3), cat("inv_sigma2", 1).reshape(-1)
+        self.outlier = np.zeros(max(int(self.frame_ptr[-1]), 1), np.uint8)
+        self.n_inliers = np.zeros(len(frames), np.int32)
+        s = PoseProblem()
+        s.fx, s.fy, s.cx, s.cy, s.bf = cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam["bf"]
+        s.n_frames = len(frames)
+        s.frame_ptr = self.frame_ptr.ctypes.data_as(_ip); s.pose_q = self.pose_q.ctypes.data_as(_dp); s.pose_t = self.pose_t.ctypes.data_as(_dp)
+        fp = C.POINTER(C.c_float)
+        s.xw = self.xw.ctypes.data_as(fp); s.obs = self.obs.ctypes.data_as(fp); s.inv_sigma2 = self.inv_sigma2.ctypes.data_as(fp)
+        s.outlier = self.outlier.ctypes.data_as(_bp); s.n_inliers = self.n_inliers.ctypes.data_as(_ip)
+        self.c = s

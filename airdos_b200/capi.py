@@ -74,6 +74,7 @@ SYMBOLS = {
     "adb_ba_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "adb_ba_stage_ms": (C.c_int, [_vp, _fp]),
     "adb_ba_launch_count": (C.c_int64, [_vp]),
+    "adb_pose_optimize": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None

@@ -554,6 +554,234 @@ __global__ void ba_gate_kernel(StaticEdges E, State S, const double* __restrict_
     flag[e] = (chi_e[e] > (stereo ? gate_stereo : gate_mono)) || !(z > 0);
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization (src/Optimizer.cc:232-429), one CTA per frame: the whole 4 x 10 LM
+// schedule runs inside the kernel (6x6 system, deterministic block reductions, no host round trip).
+struct PoseArgs {
+    Cam C;
+    const int* frame_ptr; double* pose_q; double* pose_t;
+    const float* xw; const float* obs; const float* inv_sigma2;
+    uint8_t* outlier; int* n_inliers;
+};
+constexpr int kPoseThreads = 256;
+
+__device__ inline void pose_edge_error(const Cam& C, const double* R, const double* t, const float* xw, const float* ob, bool stereo, double* er,
+                                       double* Xc) {
+    const double X0 = (double)xw[0], X1 = (double)xw[1], X2 = (double)xw[2];
+    for (int i = 0; i < 3; ++i) Xc[i] = R[i * 3] * X0 + R[i * 3 + 1] * X1 + R[i * 3 + 2] * X2 + t[i];
+    if (stereo) {
+        const float invz = (float)(1.0 / Xc[2]);
+        const double u = Xc[0] * invz * C.fx + C.cx, v = Xc[1] * invz * C.fy + C.cy;
+        er[0] = (double)ob[0] - u; er[1] = (double)ob[1] - v; er[2] = (double)ob[2] - (u - C.bf * invz);   // double bf in the OnlyPose edge
+    } else {
+        er[0] = (double)ob[0] - (Xc[0] / Xc[2] * C.fx + C.cx); er[1] = (double)ob[1] - (Xc[1] / Xc[2] * C.fy + C.cy); er[2] = 0;
+    }
+}
+
+// sums `nv` doubles per thread over the block in a fixed order; result in out[0..nv) (shared), valid after the call
+template <int NV>
+__device__ inline void block_reduce_fixed(double (&v)[NV], double* scratch /*[8][NV]*/, double* out /*[NV]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0) scratch[warp * NV + k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < kPoseThreads / 32; ++w) s += scratch[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+__device__ inline bool chol6_solve(const double* H, double lambda, const double* b, double* x) {
+    double L[36];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) L[i * 6 + j] = H[i * 6 + j] + (i == j ? lambda : 0.0);
+    for (int j = 0; j < 6; ++j) {
+        double d = L[j * 6 + j];
+        for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > 0) || !isfinite(d)) return false;
+        d = sqrt(d);
+        L[j * 6 + j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = L[i * 6 + j];
+            for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = s / d;
+        }
+    }
+    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * x[k]; x[i] = s / L[i * 6 + i]; }
+    for (int i = 5; i >= 0; --i) { double s = x[i]; for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k]; x[i] = s / L[i * 6 + i]; }
+    return true;
+}
+
+__global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A, double* __restrict__ chi_scratch, uint8_t* __restrict__ lvl_scratch) {
+    __shared__ double scratch[(kPoseThreads / 32) * 28], red[28];
+    __shared__ double sq[4], st[3], tq[4], tt[3], sH[36], sb[6];
+    __shared__ double s_lambda, s_ni, s_current, s_rho;
+    __shared__ int s_flag, s_nbad_it, s_q;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int a = A.frame_ptr[f], n = A.frame_ptr[f + 1] - a;
+    double* chi = chi_scratch + a;
+    uint8_t* level = lvl_scratch + a;
+    for (int i = tid; i < n; i += kPoseThreads) { A.outlier[a + i] = 0; level[i] = 0; chi[i] = 0; }
+    if (n < 3) { if (tid == 0) A.n_inliers[f] = 0; return; }
+    const double dm = (double)(float)sqrt(5.991), ds = (double)(float)sqrt(7.815);
+    double q0[4], t0[3];
+    for (int k = 0; k < 4; ++k) q0[k] = A.pose_q[4 * f + k];
+    for (int k = 0; k < 3; ++k) t0[k] = A.pose_t[3 * f + k];
+    bool robust = true;
+    int nBad = 0;
+    __syncthreads();
+
+    auto evaluate = [&](const double* qq, const double* tt_) -> double {   // robust chi2 of the active edges, result broadcast
+        double R[9], v[1] = {0.0}, r0, r1;
+        quat_to_rot(qq, R);
+        for (int i = tid; i < n; i += kPoseThreads) {
+            if (level[i]) continue;
+            const bool stereo = !(A.obs[3 * (size_t)(a + i) + 2] < 0);
+            double er[3], Xc[3];
+            pose_edge_error(A.C, R, tt_, A.xw + 3 * (size_t)(a + i), A.obs + 3 * (size_t)(a + i), stereo, er, Xc);
+            const double w = (double)A.inv_sigma2[a + i];
+            const double c = er[0] * (w * er[0]) + er[1] * (w * er[1]) + er[2] * (w * er[2]);
+            chi[i] = c;
+            huber(stereo ? ds : dm, robust, c, &r0, &r1);
+            v[0] += r0;
+        }
+        block_reduce_fixed<1>(v, scratch, red);
+        return red[0];
+    };
+
+    for (int round = 0; round < 4; ++round) {
+        if (tid == 0) { for (int k = 0; k < 4; ++k) sq[k] = q0[k]; for (int k = 0; k < 3; ++k) st[k] = t0[k]; }
+        int mine = 0;
+        for (int i = tid; i < n; i += kPoseThreads) mine += !level[i];
+        const int nact = __syncthreads_count(mine > 0) ? 1 : 0;   // any active edge?
+        if (nact) {
+            if (tid == 0) { s_lambda = 0; s_ni = 2; s_nbad_it = 0; }
+            __syncthreads();
+            for (int it = 0; it < 10; ++it) {
+                double q[4] = {sq[0], sq[1], sq[2], sq[3]}, t[3] = {st[0], st[1], st[2]};
+                const double current0 = evaluate(q, t);
+                // buildSystem
+                double v[27];
+#pragma unroll
+                for (int k = 0; k < 27; ++k) v[k] = 0;
+                double R[9], r0, r1;
+                quat_to_rot(q, R);
+                for (int i = tid; i < n; i += kPoseThreads) {
+                    if (level[i]) continue;
+                    const bool stereo = !(A.obs[3 * (size_t)(a + i) + 2] < 0);
+                    double er[3], Xc[3], J[18];
+                    pose_edge_error(A.C, R, t, A.xw + 3 * (size_t)(a + i), A.obs + 3 * (size_t)(a + i), stereo, er, Xc);
+                    const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = A.C.fx, fy = A.C.fy, bf = A.C.bf;
+                    J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+                    J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+                    if (stereo) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
+                    else { for (int k = 12; k < 18; ++k) J[k] = 0; }
+                    const int dim = stereo ? 3 : 2;
+                    const double w0 = (double)A.inv_sigma2[a + i];
+                    huber(stereo ? ds : dm, robust, chi[i], &r0, &r1);
+                    const double w = r1 * w0;
+                    int u = 0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = 0; c <= r; ++c, ++u) { double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + r] * w * J[k * 6 + c]; v[u] += s; }
+                        double s = 0;
+                        for (int k = 0; k < dim; ++k) s += J[k * 6 + r] * (-w0 * er[k] * r1);
+                        v[21 + r] += s;
+                    }
+                }
+                block_reduce_fixed<27>(v, scratch, red);
+                if (tid == 0) {
+                    int u = 0;
+                    for (int r = 0; r < 6; ++r) for (int c = 0; c <= r; ++c, ++u) { sH[r * 6 + c] = red[u]; sH[c * 6 + r] = red[u]; }
+                    for (int r = 0; r < 6; ++r) sb[r] = red[21 + r];
+                    if (it == 0) { double m = 0; for (int r = 0; r < 6; ++r) m = fmax(m, fabs(sH[r * 7])); s_lambda = 1e-5 * m; s_ni = 2; s_nbad_it = 0; }
+                    s_current = current0; s_q = 0;
+                }
+                __syncthreads();
+                const double ini = current0;
+                while (true) {   // LM trials
+                    if (tid == 0) {
+                        double x[6];
+                        const bool ok = chol6_solve(sH, s_lambda, sb, x);
+                        if (ok) pose_oplus(sq, st, x, tq, tt);
+                        else { for (int k = 0; k < 4; ++k) tq[k] = sq[k]; for (int k = 0; k < 3; ++k) tt[k] = st[k]; }
+                        double scale = 0;
+                        if (ok) for (int k = 0; k < 6; ++k) scale += x[k] * (s_lambda * x[k] + sb[k]);
+                        s_rho = scale + 1e-3;      // denominator, completed below
+                        s_flag = ok ? 1 : 0;
+                    }
+                    __syncthreads();
+                    const double qq[4] = {tq[0], tq[1], tq[2], tq[3]}, tt2[3] = {tt[0], tt[1], tt[2]};
+                    double temp = evaluate(qq, tt2);
+                    if (tid == 0) {
+                        if (!s_flag) temp = DBL_MAX;
+                        const double rho = (s_current - temp) / s_rho;
+                        if (rho > 0 && isfinite(temp)) {
+                            double alpha = 1. - pow((2 * rho - 1), 3.0);
+                            alpha = fmin(alpha, 2. / 3.);
+                            s_lambda *= fmax(1. / 3., alpha); s_ni = 2; s_current = temp;
+                            for (int k = 0; k < 4; ++k) sq[k] = tq[k];
+                            for (int k = 0; k < 3; ++k) st[k] = tt[k];
+                        } else { s_lambda *= s_ni; s_ni *= 2; }
+                        s_rho = rho;
+                        s_q += 1;
+                    }
+                    __syncthreads();
+                    if (!(s_rho < 0 && s_q < 10)) break;
+                }
+                bool stop_it = (s_q == 10 || s_rho == 0);
+                if (!stop_it) {
+                    if (tid == 0) { if ((ini - s_current) * 1e3 < ini) s_nbad_it++; else s_nbad_it = 0; }
+                    __syncthreads();
+                    stop_it = s_nbad_it >= 3;
+                }
+                __syncthreads();
+                if (stop_it) break;
+            }
+        }
+        __syncthreads();
+        // classification at the round's final pose
+        {
+            const double q[4] = {sq[0], sq[1], sq[2], sq[3]}, t[3] = {st[0], st[1], st[2]};
+            double R[9];
+            quat_to_rot(q, R);
+            int bad = 0;
+            for (int i = tid; i < n; i += kPoseThreads) {
+                const bool stereo = !(A.obs[3 * (size_t)(a + i) + 2] < 0);
+                if (A.outlier[a + i]) {
+                    double er[3], Xc[3];
+                    pose_edge_error(A.C, R, t, A.xw + 3 * (size_t)(a + i), A.obs + 3 * (size_t)(a + i), stereo, er, Xc);
+                    const double w = (double)A.inv_sigma2[a + i];
+                    chi[i] = er[0] * (w * er[0]) + er[1] * (w * er[1]) + er[2] * (w * er[2]);
+                }
+                const float c = (float)chi[i];
+                const bool out = c > (stereo ? 7.815f : 5.991f);
+                A.outlier[a + i] = out; level[i] = out; bad += out;
+            }
+            nBad = __syncthreads_count(0);   // barrier
+            double v[1] = {(double)bad};
+            block_reduce_fixed<1>(v, scratch, red);
+            nBad = (int)red[0];
+        }
+        if (round == 2) robust = false;
+        if (n < 10) break;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int k = 0; k < 4; ++k) A.pose_q[4 * f + k] = sq[k];
+        for (int k = 0; k < 3; ++k) A.pose_t[3 * f + k] = st[k];
+        A.n_inliers[f] = n - nBad;
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
@@ -1103,6 +1331,46 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
     if (R->medge_outlier) for (int e = 0; e < P->n_motion_edges; ++e) R->medge_outlier[e] = fm[e];
     if ((r = c.download_state()) != ADB_OK) return r;
     c.tm.collect();
+    return ADB_OK;
+}
+
+
+adb_status adb_pose_optimize(adb_ba_t s, adb_pose_problem* P) {
+    ADB_CHECK(s && P && P->frame_ptr && P->pose_q && P->pose_t && P->outlier && P->n_inliers, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK(P->n_frames >= 1, ADB_ERR_INVALID, "no frames");
+    ADB_CUDA(cudaSetDevice(s->device));
+    const int F = P->n_frames, n = P->frame_ptr[F];
+    ADB_CHECK(n >= 0 && P->frame_ptr[0] == 0, ADB_ERR_INVALID, "bad frame_ptr");
+    cudaStream_t st = s->stream;
+    // reuse BA buffers as scratch: e_pose = frame_ptr, pq/pt[0] = poses, e_obs = xw | obs | inv_sigma2 (float), chi_e[0], flag, e_level, off_pose = n_inliers
+    adb_status r;
+    if ((r = upload(s->e_pose, P->frame_ptr, (size_t)F + 1, st)) != ADB_OK) return r;
+    if ((r = upload(s->pq[0], P->pose_q, 4 * (size_t)F, st)) != ADB_OK) return r;
+    if ((r = upload(s->pt[0], P->pose_t, 3 * (size_t)F, st)) != ADB_OK) return r;
+    if ((r = s->e_obs.ensure(std::max<size_t>(n, 1) * 7 * sizeof(float))) != ADB_OK) return r;
+    float* d_xw = s->e_obs.as<float>();
+    float* d_obs = d_xw + 3 * (size_t)std::max(n, 1);
+    float* d_w = d_obs + 3 * (size_t)std::max(n, 1);
+    if (n > 0) {
+        ADB_CHECK(P->xw && P->obs && P->inv_sigma2, ADB_ERR_INVALID, "null correspondence arrays");
+        ADB_CUDA(cudaMemcpyAsync(d_xw, P->xw, 3 * (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        ADB_CUDA(cudaMemcpyAsync(d_obs, P->obs, 3 * (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        ADB_CUDA(cudaMemcpyAsync(d_w, P->inv_sigma2, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    if ((r = s->chi_e[0].ensure(std::max<size_t>(n, 1) * 8)) != ADB_OK) return r;
+    if ((r = s->flag.ensure(std::max<size_t>(n, 1))) != ADB_OK) return r;
+    if ((r = s->e_level.ensure(std::max<size_t>(n, 1))) != ADB_OK) return r;
+    if ((r = s->off_pose.ensure((size_t)F * 4)) != ADB_OK) return r;
+    PoseArgs A{Cam{P->fx, P->fy, P->cx, P->cy, P->bf}, s->e_pose.as<int>(), s->pq[0].as<double>(), s->pt[0].as<double>(), d_xw, d_obs, d_w,
+               s->flag.as<uint8_t>(), s->off_pose.as<int>()};
+    pose_optimize_kernel<<<F, kPoseThreads, 0, st>>>(A, s->chi_e[0].as<double>(), s->e_level.as<uint8_t>());
+    ++s->launches;
+    ADB_CUDA(cudaGetLastError());
+    ADB_CUDA(cudaMemcpyAsync(P->pose_q, s->pq[0].p, 4 * (size_t)F * 8, cudaMemcpyDeviceToHost, st));
+    ADB_CUDA(cudaMemcpyAsync(P->pose_t, s->pt[0].p, 3 * (size_t)F * 8, cudaMemcpyDeviceToHost, st));
+    if (n > 0) ADB_CUDA(cudaMemcpyAsync(P->outlier, s->flag.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    ADB_CUDA(cudaMemcpyAsync(P->n_inliers, s->off_pose.p, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+    ADB_CUDA(cudaStreamSynchronize(st));
     return ADB_OK;
 }
 

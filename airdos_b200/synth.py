@@ -274,3 +274,32 @@ def _add_humans(prob, rng, n_tracks, n_poses, Rcw, tcw, centers, Rwc, noise):
                 redge_info=np.full(len(r_i), 20.0), motion_q=np.tile(np.array([0, 0, 0, 1.0]), (nm, 1)), motion_t=np.zeros((nm, 3)),
                 medge_p1=np.array(m_p1, np.int32), medge_p2=np.array(m_p2, np.int32), medge_motion=np.array(m_m, np.int32),
                 medge_dt=np.array(m_dt, np.float64), medge_info=np.full(len(m_p1), 20.0))
+
+
+def make_pose_frames(n_frames: int = 4, n_points: int = 600, seed: int = 7, outlier_frac: float = 0.1, mono_frac: float = 0.2):
+    """Frames for Optimizer::PoseOptimization: each sees its own MapPoints (float32 world positions), stereo / mono
+    observations with octave noise and gross outliers, and starts from a perturbed pose.  Returns (cam, frames, gt_t)."""
+    rng = np.random.default_rng(seed)
+    cam = dict(fx=FX, fy=FY, cx=CX, cy=CY, bf=BF)
+    frames, gts = [], []
+    for f in range(n_frames):
+        n = n_points if f != 1 else 7            # one frame below the 10-edge early exit
+        R = _small_rot(rng.normal(0, 0.1, 3)); t = rng.normal(0, 0.5, 3)
+        u = rng.uniform(20, 620, n); v = rng.uniform(20, 460, n); z = rng.uniform(3, 40, n)
+        Xc = np.stack([(u - CX) / FX * z, (v - CY) / FY * z, z], 1)
+        Xw = ((Xc - t) @ R).astype(np.float32)                     # Xc = R Xw + t
+        Xc = Xw.astype(np.float64) @ R.T + t
+        lvl = rng.choice(8, n, p=ORB_QUOTA_2000 / ORB_QUOTA_2000.sum())
+        sig = 1.2 ** lvl
+        uo = Xc[:, 0] / Xc[:, 2] * FX + CX + rng.normal(0, 1, n) * sig
+        vo = Xc[:, 1] / Xc[:, 2] * FY + CY + rng.normal(0, 1, n) * sig
+        ur = uo - BF / Xc[:, 2] + rng.normal(0, 1, n) * sig
+        bad = rng.random(n) < outlier_frac
+        uo[bad] += rng.uniform(-40, 40, bad.sum()); vo[bad] += rng.uniform(-40, 40, bad.sum())
+        ur[(rng.random(n) < mono_frac) | (ur < 0)] = -1.0
+        T = np.eye(4); T[:3, :3] = _small_rot(rng.normal(0, 0.01, 3)) @ R; T[:3, 3] = t + rng.normal(0, 0.05, 3)
+        q, tt = tcw_to_pose(T.astype(np.float32))
+        frames.append(dict(pose_q=q, pose_t=tt, xw=Xw, obs=np.stack([uo, vo, ur], 1).astype(np.float32),
+                           inv_sigma2=(np.float32(1) / (np.float32(1.2) ** lvl.astype(np.float32)) ** 2).astype(np.float32)))
+        gts.append(t)
+    return cam, frames, np.array(gts)

@@ -282,6 +282,25 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* prob, const adb_ba_options* 
 adb_status adb_ba_stage_ms(adb_ba_t s, float* ms6);
 int64_t adb_ba_launch_count(adb_ba_t s);
 
+/* Optimizer::PoseOptimization(Frame*)  (src/Optimizer.cc:232-429): pose-only robust LM over the frame's
+ * MapPoint correspondences (g2o::Edge(Stereo)SE3ProjectXYZOnlyPose), 4 rounds x 10 iterations with
+ * chi2 re-classification between rounds, batched over frames (the reference calls it once per frame:
+ * n_frames = 1).  Correspondence arrays are CSR over frames and float like the Frame / MapPoint members
+ * they come from.  All pointers are host memory. */
+typedef struct adb_pose_problem {
+    double fx, fy, cx, cy, bf;       /* Frame::fx .. mbf */
+    int32_t n_frames;
+    const int32_t* frame_ptr;        /* [n_frames + 1] */
+    double* pose_q;                  /* [n_frames][4] Converter::toSE3Quat(pFrame->mTcw), in/out */
+    double* pose_t;                  /* [n_frames][3] in/out */
+    const float* xw;                 /* [n][3] MapPoint::GetWorldPos() */
+    const float* obs;                /* [n][3] mvKeysUn[i].pt.x, .pt.y, mvuRight[i] (< 0: monocular) */
+    const float* inv_sigma2;         /* [n] mvInvLevelSigma2[octave] */
+    uint8_t* outlier;                /* [n] out: mvbOutlier */
+    int32_t* n_inliers;              /* [n_frames] out: return value (nInitialCorrespondences - nBad; 0 if < 3 correspondences) */
+} adb_pose_problem;
+adb_status adb_pose_optimize(adb_ba_t s, adb_pose_problem* prob);
+
 #ifdef __cplusplus
 }
 #endif

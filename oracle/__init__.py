@@ -271,3 +271,14 @@ def ba_solve(problem_dict: dict, options=None, stop: np.ndarray | None = None, t
     o = options or ba_default_options()
     st = ba_lib().ba_oracle_solve(C.byref(p.c), C.byref(o), _p(stop) if stop is not None else None, C.byref(r.c))
     return p, r, st
+
+
+def pose_optimize(cam: dict, frames: list):
+    """Optimizer::PoseOptimization restatement on a batch of frames -> PoseBatch with results."""
+    from airdos_b200 import ba_types as T
+    pb = T.PoseBatch(cam, frames)
+    lib = ba_lib()
+    lib.ba_oracle_pose_optimize.restype = C.c_int
+    lib.ba_oracle_pose_optimize.argtypes = [C.POINTER(T.PoseProblem)]
+    lib.ba_oracle_pose_optimize(C.byref(pb.c))
+    return pb

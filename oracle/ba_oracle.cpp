@@ -698,3 +698,144 @@ int ba_oracle_first_step(adb_ba_problem* prob, const adb_ba_options* opt, double
     return S.n_dense;
 }
 }
+
+// ---------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization (src/Optimizer.cc:232-429): one free pose, unary OnlyPose edges
+// (types_six_dof_expmap.cpp:266-364, .h:150-202), 4 rounds x 10 LM iterations, each round restarted
+// from the initial pose with the inlier set of the previous one, robust kernel off in round 4.
+namespace {
+struct PoseEdge { double X[3], obs[3], w; bool stereo; };
+
+inline void pose_edge_error(const adb_pose_problem& P, const double* R, const double* t, const PoseEdge& e, double* er, double* Xc) {
+    for (int i = 0; i < 3; ++i) Xc[i] = R[i * 3] * e.X[0] + R[i * 3 + 1] * e.X[1] + R[i * 3 + 2] * e.X[2] + t[i];
+    if (e.stereo) {
+        const float invz = (float)(1.0 / Xc[2]);
+        const double u = Xc[0] * invz * P.fx + P.cx, v = Xc[1] * invz * P.fy + P.cy;
+        er[0] = e.obs[0] - u; er[1] = e.obs[1] - v; er[2] = e.obs[2] - (u - P.bf * invz);   // member bf is double here
+    } else {
+        er[0] = e.obs[0] - (Xc[0] / Xc[2] * P.fx + P.cx); er[1] = e.obs[1] - (Xc[1] / Xc[2] * P.fy + P.cy); er[2] = 0;
+    }
+}
+inline void pose_edge_jac(const adb_pose_problem& P, const double* Xc, bool stereo, double* J) {
+    const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = P.fx, fy = P.fy;
+    J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+    J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+    if (stereo) { J[12] = J[0] - P.bf * y * invz_2; J[13] = J[1] + P.bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - P.bf * invz_2; }
+    else for (int i = 12; i < 18; ++i) J[i] = 0;
+}
+
+int pose_optimize_one(const adb_pose_problem& P, int f) {
+    const int a = P.frame_ptr[f], n = P.frame_ptr[f + 1] - a;
+    std::vector<PoseEdge> E(n);
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) { E[i].X[k] = (double)P.xw[3 * (size_t)(a + i) + k]; E[i].obs[k] = (double)P.obs[3 * (size_t)(a + i) + k]; }
+        E[i].w = (double)P.inv_sigma2[a + i];
+        E[i].stereo = !(P.obs[3 * (size_t)(a + i) + 2] < 0);
+        P.outlier[a + i] = 0;
+    }
+    if (n < 3) return 0;
+    const Huber hm{(double)(float)std::sqrt(5.991), 0}, hs{(double)(float)std::sqrt(7.815), 0};
+    const Huber hmono{hm.delta, hm.delta * hm.delta}, hstereo{hs.delta, hs.delta * hs.delta};
+    double q0[4], t0[3];
+    std::memcpy(q0, P.pose_q + 4 * f, sizeof(q0)); std::memcpy(t0, P.pose_t + 3 * f, sizeof(t0));
+    double q[4], t[3];
+    std::vector<uint8_t> level(n, 0);
+    std::vector<double> chi(n, 0.0);
+    bool robust = true;
+    int nBad = 0;
+    for (int round = 0; round < 4; ++round) {
+        std::memcpy(q, q0, sizeof(q)); std::memcpy(t, t0, sizeof(t));
+        int nact = 0;
+        for (int i = 0; i < n; ++i) nact += !level[i];
+        auto evaluate = [&](const double* qq, const double* tt) {
+            double R[9], s = 0, r0, r1;
+            quat_to_rot(qq, R);
+            for (int i = 0; i < n; ++i) {
+                if (level[i]) continue;
+                double er[3], Xc[3];
+                pose_edge_error(P, R, tt, E[i], er, Xc);
+                const double c = er[0] * (E[i].w * er[0]) + er[1] * (E[i].w * er[1]) + er[2] * (E[i].w * er[2]);
+                chi[i] = c;
+                robustify(E[i].stereo ? hstereo : hmono, robust, c, &r0, &r1);
+                s += r0;
+            }
+            return s;
+        };
+        if (nact > 0) {   // optimizer.optimize(10) with 0 active vertices returns immediately
+            double lambda = 0, ni = 2;
+            int nbad_it = 0;
+            for (int it = 0; it < 10; ++it) {
+                double current = evaluate(q, t);
+                const double ini = current;
+                double H[36] = {0}, b[6] = {0}, R[9], r0, r1;
+                quat_to_rot(q, R);
+                for (int i = 0; i < n; ++i) {
+                    if (level[i]) continue;
+                    double er[3], Xc[3], J[18];
+                    pose_edge_error(P, R, t, E[i], er, Xc);
+                    pose_edge_jac(P, Xc, E[i].stereo, J);
+                    const int dim = E[i].stereo ? 3 : 2;
+                    robustify(E[i].stereo ? hstereo : hmono, robust, chi[i], &r0, &r1);
+                    const double w = r1 * E[i].w;
+                    for (int u = 0; u < 6; ++u) {
+                        for (int v = 0; v < 6; ++v) { double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + u] * w * J[k * 6 + v]; H[u * 6 + v] += s; }
+                        double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + u] * (-E[i].w * er[k] * r1); b[u] += s;
+                    }
+                }
+                if (it == 0) { double m = 0; for (int u = 0; u < 6; ++u) m = std::max(m, std::fabs(H[u * 7])); lambda = 1e-5 * m; ni = 2; nbad_it = 0; }
+                double rho = 0; int qn = 0;
+                do {
+                    std::vector<double> S(H, H + 36);
+                    for (int u = 0; u < 6; ++u) S[u * 7] += lambda;
+                    double x[6]; std::memcpy(x, b, sizeof(x));
+                    const bool ok = cholesky(S, 6);
+                    double qn4[4], tn[3];
+                    std::memcpy(qn4, q, sizeof(qn4)); std::memcpy(tn, t, sizeof(tn));
+                    if (ok) { chol_solve(S, 6, x); pose_oplus(qn4, tn, x); }
+                    double temp = evaluate(qn4, tn);
+                    if (!ok) temp = std::numeric_limits<double>::max();
+                    rho = current - temp;
+                    double scale = 0;
+                    if (ok) for (int u = 0; u < 6; ++u) scale += x[u] * (lambda * x[u] + b[u]);
+                    scale += 1e-3;
+                    rho /= scale;
+                    if (rho > 0 && std::isfinite(temp)) {
+                        double alpha = 1. - std::pow((2 * rho - 1), 3);
+                        alpha = std::min(alpha, 2. / 3.);
+                        lambda *= std::max(1. / 3., alpha); ni = 2; current = temp;
+                        std::memcpy(q, qn4, sizeof(q)); std::memcpy(t, tn, sizeof(t));
+                    } else { lambda *= ni; ni *= 2; }
+                    ++qn;
+                } while (rho < 0 && qn < 10);
+                if (qn == 10 || rho == 0) break;
+                if ((ini - current) * 1e3 < ini) ++nbad_it; else nbad_it = 0;
+                if (nbad_it >= 3) break;
+            }
+        }
+        // classification (src/Optimizer.cc:361-416): outlier edges are re-evaluated at the round's final pose,
+        // inlier edges keep the error of the last evaluated trial; float comparison
+        double R[9];
+        quat_to_rot(q, R);
+        nBad = 0;
+        for (int i = 0; i < n; ++i) {
+            if (P.outlier[a + i]) {
+                double er[3], Xc[3];
+                pose_edge_error(P, R, t, E[i], er, Xc);
+                chi[i] = er[0] * (E[i].w * er[0]) + er[1] * (E[i].w * er[1]) + er[2] * (E[i].w * er[2]);
+            }
+            const float c = (float)chi[i];
+            if (c > (E[i].stereo ? 7.815f : 5.991f)) { P.outlier[a + i] = 1; level[i] = 1; ++nBad; }
+            else { P.outlier[a + i] = 0; level[i] = 0; }
+        }
+        if (round == 2) robust = false;
+        if (n < 10) break;
+    }
+    std::memcpy(P.pose_q + 4 * f, q, sizeof(q)); std::memcpy(P.pose_t + 3 * f, t, sizeof(t));
+    return n - nBad;
+}
+}  // namespace
+
+extern "C" int ba_oracle_pose_optimize(adb_pose_problem* P) {
+    for (int f = 0; f < P->n_frames; ++f) P->n_inliers[f] = pose_optimize_one(*P, f);
+    return ADB_OK;
+}

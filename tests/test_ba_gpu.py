@@ -93,3 +93,20 @@ def test_single_round_and_degenerate_inputs(opt, oracle_mod):
     q2, t2 = synth.tcw_to_pose(T)
     assert np.allclose(q, q2, atol=1e-15) and np.allclose(t, t2)
     assert np.allclose(ba.pose_to_tcw(q, t), T, atol=1e-7)
+
+
+def test_pose_optimization_matches_oracle(opt, oracle_mod):
+    """Optimizer::PoseOptimization: optimised translations within 1e-4, identical mvbOutlier and inlier counts."""
+    from airdos_b200 import synth
+    for kw in (dict(n_frames=4, n_points=600, seed=7), dict(n_frames=9, n_points=1500, seed=8, outlier_frac=0.3, mono_frac=0.5),
+               dict(n_frames=2, n_points=40, seed=9, outlier_frac=0.0, mono_frac=1.0)):
+        cam, frames, gt = synth.make_pose_frames(**kw)
+        g = opt.PoseOptimization(cam, frames)
+        o = oracle_mod.pose_optimize(cam, frames)
+        assert (g.n_inliers == o.n_inliers).all()
+        assert (g.outlier == o.outlier).all()
+        assert np.abs(g.pose_t - o.pose_t).max() < 1e-4 and np.abs(g.pose_q - o.pose_q).max() < 1e-6
+    # fewer than 3 correspondences: returns 0, pose untouched
+    tiny = dict(frames[0]); tiny["xw"] = tiny["xw"][:2]; tiny["obs"] = tiny["obs"][:2]; tiny["inv_sigma2"] = tiny["inv_sigma2"][:2]
+    g = opt.PoseOptimization(cam, [tiny, frames[1]])
+    assert g.n_inliers[0] == 0 and (g.pose_t[0] == frames[0]["pose_t"]).all() and g.n_inliers[1] > 0

@@ -155,3 +155,21 @@ def test_dynamic_problem_runs_and_improves(oracle_mod):
     # bone lengths stay near the 1.7 m skeleton's, motions near 1.2 m/s
     assert np.abs(p["dists"] - d["dists"]).max() < 1.5   # rigidity information 20 is weak against pixel residuals
     assert np.all(np.linalg.norm(p["motion_t"].reshape(-1, 3), axis=1) < 3.0)
+
+
+def test_pose_optimization_oracle(oracle_mod):
+    cam, frames, gt = synth.make_pose_frames(4, 600, seed=7)
+    pb = oracle_mod.pose_optimize(cam, frames)
+    init = np.array([f["pose_t"] for f in frames])
+    big = [0, 2, 3]
+    assert (np.abs(pb.pose_t[big] - gt[big]).max(1) < 0.02).all()
+    assert (np.abs(pb.pose_t[big] - gt[big]).max(1) < np.abs(init[big] - gt[big]).max(1)).all()
+    # ~10 % gross outliers + the chi2 tail; the return value is nInitialCorrespondences - nBad
+    for f in big:
+        a, b = pb.frame_ptr[f], pb.frame_ptr[f + 1]
+        assert pb.n_inliers[f] == (b - a) - pb.outlier[a:b].sum()
+        assert 0.08 < pb.outlier[a:b].mean() < 0.3
+    # fewer than 3 correspondences: returns 0 and leaves the pose alone (src/Optimizer.cc:345-346)
+    tiny = dict(frames[0]); tiny["xw"] = tiny["xw"][:2]; tiny["obs"] = tiny["obs"][:2]; tiny["inv_sigma2"] = tiny["inv_sigma2"][:2]
+    pb2 = oracle_mod.pose_optimize(cam, [tiny])
+    assert pb2.n_inliers[0] == 0 and (pb2.pose_t[0] == frames[0]["pose_t"]).all()
