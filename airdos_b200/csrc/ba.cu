@@ -11,7 +11,8 @@
 //                           which live in the dense (non-marginalised) block
 //   ba_dinv_kernel          (Hll + lambda I)^-1 per point, bschur -= Hpl Dinv bl
 //   ba_schur_kernel         Hschur -= Hpl_i Dinv Hpl_j^T over the per-point edge pairs
-//   cusolverDnDpotrf/potrs  dense FP64 Cholesky of the reduced system (bring-up baseline)
+//   chol_left_kernel,       dense FP64 Cholesky of the reduced system: left-looking, one launch per 32-wide panel,
+//   chol_solve_kernel       then forward / backward substitution (cuSOLVER potrf/potrs was the bring-up baseline)
 //   ba_pose_update_kernel   exp(dx) * T, additive / right-multiplicative updates of the rest
 //   ba_backsub_kernel       xl = Dinv (bl - Hpl^T xp), trial points, landmark part of the gain ratio
 //   ba_eval_kernel          residuals + robust chi2 of the trial state
@@ -21,11 +22,10 @@
 // the host from one 48-byte read-back per trial.
 // Accumulation uses FP64 atomics in L2 (RED.ADD.F64): sums are order-dependent at the 1e-16
 // level, far below the 1e-4 parity bar.
-#include <cusolverDn.h>
-
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
@@ -399,7 +399,7 @@ __global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __
         const int r = (int)(i / nd), c = (int)(i - (size_t)r * nd);
         Sm[i] = H[i] + (r == c ? lambda : 0.0);
     }
-    if (i < (size_t)nd) bs[i] = b[i];
+    if (i < (size_t)nd) { bs[i] = b[i]; Sm[(size_t)nd * nd + i] = b[i]; }   // row nd of Sm carries the right-hand side through the factorisation
 }
 
 // per point: Dinv = (Hll + lambda I)^-1 by cofactors (Eigen fixed-size inverse), db = Dinv bl
@@ -420,43 +420,77 @@ __global__ void ba_dinv_kernel(const double* __restrict__ Hll, const double* __r
     for (int i = 0; i < 3; ++i) db[3 * (size_t)l + i] = B[i * 3] * bl[3 * l] + B[i * 3 + 1] * bl[3 * l + 1] + B[i * 3 + 2] * bl[3 * l + 2];
 }
 
-// Schur pairs: pair p = (e1, e2) of active edges of one point with off(e1) >= off(e2);
-// S(o1.., o2..) -= W1 Dinv W2^T (lower triangle); when e1 == e2 also bs(o1) -= W1 db.
-__global__ void __launch_bounds__(kBaThreads) ba_schur_kernel(const int2* __restrict__ pairs, int npairs, const int* __restrict__ e_pose,
-                                                             const int* __restrict__ e_point, const int* __restrict__ off_pose,
-                                                             const double* __restrict__ W, const double* __restrict__ Dinv,
-                                                             const double* __restrict__ db, int nd, double* __restrict__ Sm,
-                                                             double* __restrict__ bs) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    const int2 pr = pairs[p];
-    const int e1 = pr.x, e2 = pr.y;
-    const int l = e_point[e1];
-    const int o1 = off_pose[e_pose[e1]], o2 = off_pose[e_pose[e2]];
-    const double* W1 = W + 18 * (size_t)e1;
-    const double* W2 = W + 18 * (size_t)e2;
-    const double* Di = Dinv + 9 * (size_t)l;
-    double BD[18];
+// Schur complement by destination block: the pair list is sorted by (pose block i, pose block j) on the host and cut into
+// chunks of <= 128 pairs; one warp sums a chunk in registers, reduces with shuffles and issues 36 (+6) atomics per chunk
+// instead of 36 per pair.
+constexpr int kSchurChunk = 128;
+__global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* __restrict__ pairs, const int2* __restrict__ chunks, int nchunks,
+                                                                   const int* __restrict__ e_pose, const int* __restrict__ e_point,
+                                                                   const int* __restrict__ off_pose, const double* __restrict__ W,
+                                                                   const double* __restrict__ Dinv, const double* __restrict__ db, int nd,
+                                                                   double* __restrict__ Sm, double* __restrict__ bs) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (kBaThreads / 32) + (threadIdx.x >> 5);
+    if (c >= nchunks) return;
+    const int2 ch = chunks[c];
+    double acc[36], rhs[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) BD[i * 3 + j] = W1[i * 3] * Di[j] + W1[i * 3 + 1] * Di[3 + j] + W1[i * 3 + 2] * Di[6 + j];
-    double w2[18];
+    for (int i = 0; i < 6; ++i) rhs[i] = 0.0;
+    for (int p = ch.x + lane; p < ch.x + ch.y; p += 32) {
+        const int2 pr = pairs[p];
+        const int l = e_point[pr.x];
+        const double* W1 = W + 18 * (size_t)pr.x;
+        const double* W2 = W + 18 * (size_t)pr.y;
+        const double* Di = Dinv + 9 * (size_t)l;
+        double BD[18], w2[18];
 #pragma unroll
-    for (int i = 0; i < 18; ++i) w2[i] = W2[i];
-    const bool diag = o1 == o2;
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 3; ++j) BD[i * 3 + j] = W1[i * 3] * Di[j] + W1[i * 3 + 1] * Di[3 + j] + W1[i * 3 + 2] * Di[6 + j];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            if (diag && j > i) continue;
-            const double s = BD[i * 3] * w2[j * 3] + BD[i * 3 + 1] * w2[j * 3 + 1] + BD[i * 3 + 2] * w2[j * 3 + 2];
-            atomicAdd(Sm + (size_t)(o1 + i) * nd + o2 + j, -s);
+        for (int i = 0; i < 18; ++i) w2[i] = W2[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[i * 6 + j] += BD[i * 3] * w2[j * 3] + BD[i * 3 + 1] * w2[j * 3 + 1] + BD[i * 3 + 2] * w2[j * 3 + 2];
+        if (pr.x == pr.y) {
+            const double* d = db + 3 * (size_t)l;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) rhs[i] += W1[i * 3] * d[0] + W1[i * 3 + 1] * d[1] + W1[i * 3 + 2] * d[2];
         }
-    if (e1 == e2) {
-        const double* d = db + 3 * (size_t)l;
+    }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) atomicAdd(bs + o1 + i, -(W1[i * 3] * d[0] + W1[i * 3 + 1] * d[1] + W1[i * 3 + 2] * d[2]));
+    for (int i = 0; i < 36; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xFFFFFFFFu, acc[i], o);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rhs[i] += __shfl_xor_sync(0xFFFFFFFFu, rhs[i], o);
+    const int2 p0 = pairs[ch.x];
+    const int o1 = off_pose[e_pose[p0.x]], o2 = off_pose[e_pose[p0.y]];
+    // lanes 0..35 own one entry of the 6 x 6 block each (static register indexing via the unrolled select)
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) if (lane == i) mine = acc[i];
+    if (lane < 32) {
+        const int i = lane / 6, j = lane % 6;
+        if (!(o1 == o2 && j > i)) atomicAdd(Sm + (size_t)(o1 + i) * nd + o2 + j, -mine);
+    }
+    if (lane < 4) {   // entries 32..35
+        const int e = 32 + lane, i = e / 6, j = e % 6;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 32; k < 36; ++k) if (e == k) v = acc[k];
+        if (!(o1 == o2 && j > i)) atomicAdd(Sm + (size_t)(o1 + i) * nd + o2 + j, -v);
+    }
+    if (lane >= 8 && lane < 14) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (lane - 8 == k) v = rhs[k];
+        if (v != 0.0) atomicAdd(bs + o1 + (lane - 8), -v);
     }
 }
 
@@ -782,6 +816,117 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Dense FP64 Cholesky of the reduced system (row-major lower triangle), left-looking with 32-wide panels and ONE
+// launch per panel: CTA `ib` owns row block ib >= kb.  It forms its 32 x 32 block of the panel,
+//     U = A[ib, kb] - L[ib, 0:kb] L[kb, 0:kb]^T,
+// and (redundantly, to avoid any grid-wide synchronisation) the diagonal block D = A[kb, kb] - L[kb, 0:kb] L[kb, 0:kb]^T,
+// factors D in registers (one warp, column broadcast by shuffles) and solves U L_kk^-T for its rows.  Factored diagonal
+// blocks go to a side buffer (Ldiag) so no CTA ever reads a block another CTA is writing.  chol_solve_kernel then does the
+// forward / backward substitution.  Replaces cuSOLVER potrf + potrs (LinearSolverEigen / LinearSolverDense of g2o).
+constexpr int kCholNB = 32;
+
+// n = matrix order (columns), n_rows >= n: rows n..n_rows-1 are extra right-hand-side rows carried through the factorisation
+// (row n = b^T turns into y^T = (L^-1 b)^T, i.e. the forward substitution comes for free).  pitch = n.
+__global__ void __launch_bounds__(1024) chol_left_kernel(double* __restrict__ A, int n, int n_rows, int kb, double* __restrict__ Ldiag,
+                                                        int* __restrict__ info) {
+    __shared__ double Ta[kCholNB][kCholNB + 1], Tb[kCholNB][kCholNB + 1];   // operand tiles, then U and D / L
+    __shared__ double col[kCholNB];
+    __shared__ double s_isd;
+    const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;
+    const int k = kb * kCholNB, ib = kb + blockIdx.x, i0 = ib * kCholNB;
+    const int nbk = min(kCholNB, n - k);
+    double accU = 0.0, accD = 0.0;
+    // software-pipelined tile loads: the next tiles are fetched while the current ones are multiplied
+    double na = 0.0, nb = 0.0;
+    if (k > 0) {
+        na = (i0 + r < n_rows) ? A[(size_t)(i0 + r) * n + c] : 0.0;
+        nb = A[(size_t)(k + r) * n + c];
+    }
+    for (int p0 = 0; p0 < k; p0 += kCholNB) {
+        Ta[r][c] = na; Tb[r][c] = nb;
+        __syncthreads();
+        if (p0 + kCholNB < k) {
+            na = (i0 + r < n_rows) ? A[(size_t)(i0 + r) * n + p0 + kCholNB + c] : 0.0;
+            nb = A[(size_t)(k + r) * n + p0 + kCholNB + c];
+        }
+#pragma unroll
+        for (int p = 0; p < kCholNB; ++p) {
+            const double b = Tb[c][p];
+            accU += Ta[r][p] * b;
+            accD += Tb[r][p] * b;
+        }
+        __syncthreads();
+    }
+    double u = (i0 + r < n_rows && c < nbk) ? A[(size_t)(i0 + r) * n + k + c] - accU : 0.0;
+    double t = (r < nbk && c < nbk) ? ((c <= r) ? A[(size_t)(k + r) * n + k + c] - accD : 0.0) : (r == c ? 1.0 : 0.0);
+    // ---- factor D: thread (r, c) owns element (r, c); two barriers per column
+    for (int j = 0; j < kCholNB; ++j) {
+        if (r == j && c == j) {
+            double d = t;
+            if (!(d > 0.0) || !isfinite(d)) { if (blockIdx.x == 0 && *info == 0) *info = k + j + 1; d = 1.0; }
+            const double sd = sqrt(d);
+            t = sd;
+            s_isd = 1.0 / sd;
+        }
+        __syncthreads();
+        if (c == j) {
+            if (r > j) t *= s_isd;
+            col[r] = r >= j ? t : 0.0;     // column j of L (col[j] = L[j][j])
+        }
+        __syncthreads();
+        if (c > j && c <= r) t -= col[r] * col[c];
+    }
+    Tb[r][c] = c <= r ? t : 0.0;
+    if (r == c) col[r] = 1.0 / t;          // 1 / L[j][j] (no hazard: the loop's last read of col is behind a barrier below)
+    __syncthreads();
+    // the diagonal block's CTA publishes the factor (A keeps the unfactored block: nobody reads it again); of its rows only
+    // the extra right-hand-side rows (>= n) that share the row block still need the triangular solve
+    if (blockIdx.x == 0) Ldiag[(size_t)kb * kCholNB * kCholNB + tid] = Tb[r][c];
+    // ---- x L_kk^T = u: warp r owns row r, lane c holds x[c]; right-looking, no block barriers
+#pragma unroll
+    for (int j = 0; j < kCholNB; ++j) {
+        double xj = __shfl_sync(0xFFFFFFFFu, u, j) * col[j];
+        if (c == j) u = xj;
+        if (c > j) u -= xj * Tb[c][j];
+    }
+    if (i0 + r < n_rows && c < nbk && (blockIdx.x > 0 || i0 + r >= n)) A[(size_t)(i0 + r) * n + k + c] = u;
+}
+
+// backward substitution L^T x = y, y = row n of the factored array; x -> out.  One CTA, 32-wide blocks.
+__global__ void __launch_bounds__(1024) chol_back_kernel(const double* __restrict__ A, const double* __restrict__ Ldiag, int n, double* __restrict__ out) {
+    extern __shared__ double yb[];       // [n] working copy of y
+    __shared__ double xb[kCholNB];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += blockDim.x) yb[i] = A[(size_t)n * n + i];
+    __syncthreads();
+    const int nblk = (n + kCholNB - 1) / kCholNB;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k = kb * kCholNB, nbk = min(kCholNB, n - k);
+        if (tid < 32) {
+            const int lane = tid;
+            const double* Ld = Ldiag + (size_t)kb * kCholNB * kCholNB;
+            double part = (lane < nbk) ? yb[k + lane] : 0.0;
+            for (int j = nbk - 1; j >= 0; --j) {
+                double xj = 0.0;
+                if (lane == j) xj = part / Ld[j * kCholNB + j];
+                xj = __shfl_sync(0xFFFFFFFFu, xj, j);
+                if (lane == j) xb[j] = xj;
+                if (lane < j) part -= Ld[j * kCholNB + lane] * xj;
+            }
+        }
+        __syncthreads();
+        if (tid < nbk) out[k + tid] = xb[tid];
+        for (int i = tid; i < k; i += blockDim.x) {   // y[i] -= sum_j L[k+j][i] x[j]
+            double sacc = yb[i];
+            for (int j = 0; j < nbk; ++j) sacc -= A[(size_t)(k + j) * n + i] * xb[j];
+            yb[i] = sacc;
+        }
+        __syncthreads();
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
@@ -806,11 +951,10 @@ using namespace adb;
 struct adb_ba {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cusolverDnHandle_t solver = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // device buffers
     DevBuf pq[2], pt[2], X[2], Jt[2], Dd[2], mq[2], mt[2];                         // double-buffered state
-    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, off_pose, act_point;
+    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, off_pose, act_point;
     DevBuf j_pose, j_joint, j_obs, j_info, j_level, r_i, r_j, r_d, r_info, r_level, m_p1, m_p2, m_m, m_dt, m_info, m_level;
     DevBuf off_joint, off_dist, off_motion;
     DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work;
@@ -863,11 +1007,10 @@ struct Ctx {
     std::vector<double> se_obs, se_info;
     std::vector<uint8_t> lvl_e, lvl_j, lvl_r, lvl_m, act_point;
     std::vector<int> off_pose, off_dist, off_motion, off_joint;
-    std::vector<int2> pairs;
+    std::vector<int2> pairs, chunks;
     int nd = 0, cur = 0, chi_last = 0;
     double lambda = 0, ni = 2;
     int trace_len = 0;
-    int potrf_lwork = 0;
     Ctx(adb_ba* s_, adb_ba_problem* p, const adb_ba_options* o, adb_ba_result* r, volatile const uint8_t* st) : s(s_), P(p), O(o), R(r), stop(st), tm(s_) {}
 
     bool stopped() const { return stop && *stop; }
@@ -968,32 +1111,59 @@ struct Ctx {
         for (int i = 0; i < P->n_motions; ++i) if (am[i]) { off_motion[i] = o; o += 6; }
         for (int i = 0; i < P->n_joints; ++i) if (aj[i]) { off_joint[i] = o; o += 3; }
         nd = o;
-        pairs.clear();
-        for (int l = 0; l < NP; ++l)
-            for (int a = ptr[l]; a < ptr[l + 1]; ++a) {
-                if (lvl_e[a] || off_pose[se_pose[a]] < 0) continue;
-                for (int c = ptr[l]; c < ptr[l + 1]; ++c) {
-                    if (lvl_e[c] || off_pose[se_pose[c]] < 0) continue;
-                    if (off_pose[se_pose[a]] >= off_pose[se_pose[c]]) pairs.push_back(make_int2(a, c));
+        // Schur pair list: (e1, e2) of one point with block(e1) >= block(e2), counting-sorted by destination block
+        // (pose offsets are multiples of 6 and come first in the dense layout), then cut into chunks
+        {
+            int nblk = 0;
+            for (int i = 0; i < P->n_poses; ++i) if (off_pose[i] >= 0) nblk = std::max(nblk, off_pose[i] / 6 + 1);
+            const size_t nkeys = (size_t)nblk * (nblk + 1) / 2;
+            std::vector<int> cnt(nkeys + 1, 0);
+            std::vector<int> blk(E);   // pose block of every (sorted) edge, -1 = inactive or fixed pose
+            for (int e = 0; e < E; ++e) blk[e] = (lvl_e[e] || off_pose[se_pose[e]] < 0) ? -1 : off_pose[se_pose[e]] / 6;
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) {
+                    size_t run = 0;
+                    for (size_t k = 0; k <= nkeys; ++k) { const size_t c = cnt[k]; cnt[k] = (int)run; run += c; }
+                    pairs.resize(run);
+                }
+                for (int l = 0; l < NP; ++l) {
+                    const int lo = ptr[l], hi = ptr[l + 1];
+                    for (int a = lo; a < hi; ++a) {
+                        const int b1 = blk[a];
+                        if (b1 < 0) continue;
+                        const size_t base = (size_t)b1 * (b1 + 1) / 2;
+                        for (int c = lo; c < hi; ++c) {
+                            const int b2 = blk[c];
+                            if (b2 < 0 || b2 > b1) continue;
+                            if (pass == 0) cnt[base + b2]++;
+                            else pairs[cnt[base + b2]++] = make_int2(a, c);
+                        }
+                    }
                 }
             }
+            // after the fill pass cnt[k] = end of block k
+            chunks.clear();
+            size_t begin = 0;
+            for (size_t k = 0; k < nkeys; ++k) {
+                const size_t end = cnt[k];
+                for (size_t b = begin; b < end; b += kSchurChunk) chunks.push_back(make_int2((int)b, (int)std::min<size_t>(kSchurChunk, end - b)));
+                begin = end;
+            }
+        }
         cudaStream_t st = s->stream;
         adb_status r;
 #define UP(buf, v) if ((r = upload(buf, (v).data(), (v).size(), st)) != ADB_OK) return r
         UP(s->e_level, lvl_e); UP(s->j_level, lvl_j); UP(s->r_level, lvl_r); UP(s->m_level, lvl_m); UP(s->act_point, act_point);
-        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs);
+        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs); UP(s->chunks, chunks);
 #undef UP
         const size_t n2 = std::max<size_t>((size_t)nd * nd, 1);
         if ((r = s->H.ensure(n2 * 8)) != ADB_OK) return r;
-        if ((r = s->Sm.ensure(n2 * 8)) != ADB_OK) return r;
+        if ((r = s->Sm.ensure((n2 + (size_t)std::max(nd, 1)) * 8)) != ADB_OK) return r;
         if ((r = s->b.ensure(std::max(nd, 1) * 8)) != ADB_OK) return r;
         if ((r = s->bs.ensure(std::max(nd, 1) * 8)) != ADB_OK) return r;
         if (nd > 0) {
-            int lwork = 0;
-            cusolverStatus_t cs = cusolverDnDpotrf_bufferSize(s->solver, CUBLAS_FILL_MODE_UPPER, nd, s->Sm.as<double>(), nd, &lwork);
-            ADB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, ADB_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed (%d)", (int)cs);
-            potrf_lwork = lwork;
-            if ((r = s->work.ensure(std::max<size_t>(lwork, 1) * 8)) != ADB_OK) return r;
+            const size_t ldiag = (size_t)((nd + kCholNB - 1) / kCholNB) * kCholNB * kCholNB;   // factored diagonal blocks
+            if ((r = s->work.ensure(ldiag * 8)) != ADB_OK) return r;
         }
         return ADB_OK;
     }
@@ -1053,23 +1223,28 @@ struct Ctx {
                                                               s->Dinv.as<double>(), s->db.as<double>());
             ++s->launches;
         }
-        if (!pairs.empty()) {
-            ba_schur_kernel<<<grid_for(pairs.size(), kBaThreads), kBaThreads, 0, st>>>(s->pairs.as<int2>(), (int)pairs.size(), s->e_pose.as<int>(),
-                                                                                      s->e_point.as<int>(), s->off_pose.as<int>(), s->W.as<double>(),
-                                                                                      s->Dinv.as<double>(), s->db.as<double>(), nd,
-                                                                                      s->Sm.as<double>(), s->bs.as<double>());
+        if (!chunks.empty()) {
+            const int nch = (int)chunks.size();
+            ba_schur_block_kernel<<<grid_for(nch, kBaThreads / 32), kBaThreads, 0, st>>>(s->pairs.as<int2>(), s->chunks.as<int2>(), nch,
+                                                                                        s->e_pose.as<int>(), s->e_point.as<int>(), s->off_pose.as<int>(),
+                                                                                        s->W.as<double>(), s->Dinv.as<double>(), s->db.as<double>(), nd,
+                                                                                        s->Sm.as<double>(), s->Sm.as<double>() + (size_t)nd * nd);   // rhs row
             ++s->launches;
         }
         ADB_CUDA(cudaGetLastError());
         tm.end();
         tm.begin(2);
         if (nd > 0) {
-            // Sm holds the lower triangle in row-major = the upper triangle in cuSOLVER's column-major view
-            cusolverStatus_t cs = cusolverDnDpotrf(s->solver, CUBLAS_FILL_MODE_UPPER, nd, s->Sm.as<double>(), nd, s->work.as<double>(), potrf_lwork, &sc->info);
-            ADB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, ADB_ERR_CUDA, "cusolverDnDpotrf failed (%d)", (int)cs);
-            cs = cusolverDnDpotrs(s->solver, CUBLAS_FILL_MODE_UPPER, nd, 1, s->Sm.as<double>(), nd, s->bs.as<double>(), nd, &sc->pad);
-            ADB_CHECK(cs == CUSOLVER_STATUS_SUCCESS, ADB_ERR_CUDA, "cusolverDnDpotrs failed (%d)", (int)cs);
-            s->launches += 2;
+            {
+                const int nblk = (nd + kCholNB - 1) / kCholNB, nrb = (nd + 1 + kCholNB - 1) / kCholNB;   // row blocks incl. the rhs row
+                for (int kb = 0; kb < nblk; ++kb) {
+                    chol_left_kernel<<<nrb - kb, 1024, 0, st>>>(s->Sm.as<double>(), nd, nd + 1, kb, s->work.as<double>(), &sc->info);
+                    ++s->launches;
+                }
+                chol_back_kernel<<<1, 1024, (size_t)nd * 8, st>>>(s->Sm.as<double>(), s->work.as<double>(), nd, s->bs.as<double>());
+                ++s->launches;
+                ADB_CUDA(cudaGetLastError());
+            }
         }
         tm.end();
         tm.begin(3);
@@ -1259,12 +1434,6 @@ adb_status adb_ba_create(int32_t device, adb_ba_t* out) {
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_scal, sizeof(Scalars));
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "ba create", __FILE__, __LINE__); }
-    if (cusolverDnCreate(&s->solver) != CUSOLVER_STATUS_SUCCESS || cusolverDnSetStream(s->solver, s->stream) != CUSOLVER_STATUS_SUCCESS) {
-        set_error("cusolverDnCreate failed");
-        cudaStreamDestroy(s->stream);
-        delete s;
-        return ADB_ERR_CUDA;
-    }
     *out = s;
     return ADB_OK;
 }
@@ -1274,7 +1443,7 @@ adb_status adb_ba_destroy(adb_ba_t s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     DevBuf* all[] = {&s->pq[0], &s->pq[1], &s->pt[0], &s->pt[1], &s->X[0], &s->X[1], &s->Jt[0], &s->Jt[1], &s->Dd[0], &s->Dd[1], &s->mq[0], &s->mq[1],
-                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->off_pose,
+                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->chunks, &s->off_pose,
                      &s->act_point, &s->j_pose, &s->j_joint, &s->j_obs, &s->j_info, &s->j_level, &s->r_i, &s->r_j, &s->r_d, &s->r_info, &s->r_level,
                      &s->m_p1, &s->m_p2, &s->m_m, &s->m_dt, &s->m_info, &s->m_level, &s->off_joint, &s->off_dist, &s->off_motion, &s->H, &s->b,
                      &s->Sm, &s->bs, &s->Hll, &s->bl, &s->W, &s->Dinv, &s->db, &s->chi_e[0], &s->chi_e[1], &s->chi_j[0], &s->chi_j[1], &s->chi_r[0],
@@ -1282,7 +1451,6 @@ adb_status adb_ba_destroy(adb_ba_t s) {
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     if (s->h_scal) cudaFreeHost(s->h_scal);
-    if (s->solver) cusolverDnDestroy(s->solver);
     cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
