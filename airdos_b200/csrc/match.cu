@@ -76,6 +76,7 @@ struct StereoLevels {
 };
 
 constexpr int kStereoWarps = 8;
+constexpr int kStereoPerWarp = 8;   // left key-points per warp: amortises the per-CTA band table of the right key-points
 constexpr int TH_HIGH = 100, TH_LOW = 50;   // src/ORBmatcher.cc:37-38
 
 __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
@@ -100,12 +101,13 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
         rband[i] = (uint32_t)minr | ((uint32_t)maxr << 12) | ((uint32_t)k.octave << 24);
     }
     __syncthreads();
-    const int iL = blockIdx.x * kStereoWarps + warp;
+    for (int sub = 0; sub < kStereoPerWarp; ++sub) {
+    const int iL = (blockIdx.x * kStereoWarps + warp) * kStereoPerWarp + sub;
     if (iL >= cap) return;
     const size_t o = (size_t)f * cap + iL;
     if (iL >= nL) {
         if (lane == 0) { uRight[o] = -1.f; depth[o] = -1.f; best_idx[o] = -1; best_dist[o] = TH_HIGH; sad_out[o] = -1; }
-        return;
+        continue;
     }
     const adb_keypoint kp = kpsL[o];
     const int levelL = kp.octave, vL = (int)kp.y;
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
         uRight[o] = ur; depth[o] = dp; sad_out[o] = sad;
         best_idx[o] = idx == INT_MAX ? -1 : idx;
         best_dist[o] = best;
+    }
     }
 }
 
@@ -394,7 +397,7 @@ adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb
         attr_set = true;
     }
     ADB_CHECK(smem <= 200 * 1024, ADB_ERR_INVALID, "capacity %d too large for the stereo matcher", cap);
-    dim3 grid((cap + kStereoWarps - 1) / kStereoWarps, n);
+    dim3 grid((cap + kStereoWarps * kStereoPerWarp - 1) / (kStereoWarps * kStereoPerWarp), n);
     stereo_match_kernel<<<grid, kStereoWarps * 32, smem, L->stream>>>(sl, L->cfg.height, L->d_kps, L->d_desc, L->d_counts, R->d_kps,
                                                                      R->d_desc, R->d_counts, cap, mbf, maxD, L->d_uright, L->d_depth,
                                                                      L->d_best_idx, L->d_best_dist, L->d_sad);

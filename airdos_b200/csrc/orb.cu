@@ -635,7 +635,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-constexpr int kVPitchW = 24;            // 32-bit words per row of the column-pass buffer (48 u16 columns)
+constexpr int kVPitchW = 26;            // 32-bit words per row of the column-pass buffer (48 u16 columns + slack for the last quad)
 struct DescSmem {
     uint8_t raw[kDescWarps][kRawBytes];               // 43 x 64 B patch; reused for the blurred 37 x 37 core (pitch kBPitch)
     uint32_t vert[kDescWarps][37 * kVPitchW];         // column pass: 37 rows x 48 u16
@@ -730,44 +730,66 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     uint32_t* vert = sm.vert[warp];
     const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw0) + (dxp >> 2);   // aligned words covering the patch columns
     const int sh = dxp & 3;                                                         // patch column c sits at u16 column c + sh
-    for (int o = lane; o < 37 * 12; o += 32) {
-        const int r = o / 12, wd = o - r * 12;
-        const uint32_t* p = raw32 + r * (kPatchBoxW / 4) + wd;
-        uint32_t lo = 0, hi = 0;
+    // column pass as a sliding window: a lane owns one 4-pixel word column and half of the rows; every input row is
+    // loaded once and scattered into the seven running sums it contributes to.
+    if (lane < 24) {
+        const int wd = lane < 12 ? lane : lane - 12;
+        const int r_begin = lane < 12 ? 0 : 19, r_end = lane < 12 ? 19 : 37;        // output rows [r_begin, r_end)
+        uint32_t lo[7], hi[7];
 #pragma unroll
-        for (int t = 0; t < 7; ++t) {
-            const uint32_t k = t == 0 || t == 6 ? 18u : (t == 1 || t == 5 ? 34u : (t == 2 || t == 4 ? 48u : 56u));
-            const uint32_t w = p[t * (kPatchBoxW / 4)];
-            lo += k * (w & 0x00FF00FFu);
-            hi += k * ((w >> 8) & 0x00FF00FFu);
+        for (int t = 0; t < 7; ++t) { lo[t] = 0; hi[t] = 0; }
+        // input row (r_begin + i) adds tap t to the output in slot t; the output in slot 6 is complete after its 7th row.
+        // Fully unrolled (25 rows) so the slot rotation is pure register renaming.
+#pragma unroll
+        for (int i = 0; i < 25; ++i) {
+            const int ri = min(r_begin + i, kPatchBoxH - 1);
+            const uint32_t w = raw32[ri * (kPatchBoxW / 4) + wd];
+            const uint32_t e = w & 0x00FF00FFu, o = (w >> 8) & 0x00FF00FFu;
+            lo[0] += 18u * e; hi[0] += 18u * o;
+            lo[1] += 34u * e; hi[1] += 34u * o;
+            lo[2] += 48u * e; hi[2] += 48u * o;
+            lo[3] += 56u * e; hi[3] += 56u * o;
+            lo[4] += 48u * e; hi[4] += 48u * o;
+            lo[5] += 34u * e; hi[5] += 34u * o;
+            lo[6] += 18u * e; hi[6] += 18u * o;
+            if (i >= 6 && r_begin + i - 6 < r_end) {
+                uint2 out;
+                out.x = __byte_perm(lo[6], hi[6], 0x5410);
+                out.y = __byte_perm(lo[6], hi[6], 0x7632);
+                *reinterpret_cast<uint2*>(vert + (r_begin + i - 6) * kVPitchW + 2 * wd) = out;
+            }
+#pragma unroll
+            for (int t = 6; t > 0; --t) { lo[t] = lo[t - 1]; hi[t] = hi[t - 1]; }
+            lo[0] = 0; hi[0] = 0;
         }
-        // lo = {col0, col2}, hi = {col1, col3} as 16-bit lanes -> {col0, col1}, {col2, col3}
-        uint2 out;
-        out.x = __byte_perm(lo, hi, 0x5410);
-        out.y = __byte_perm(lo, hi, 0x7632);
-        *reinterpret_cast<uint2*>(vert + r * kVPitchW + 2 * wd) = out;
     }
     __syncwarp();
     uint8_t* bl = raw0;   // the raw patch is dead from here on: blurred core, 37 rows x kBPitch
     {
+        // row pass: a lane makes 4 adjacent outputs from 6 words of 16-bit column sums; DP2A does two taps per instruction
         const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
-        for (int o = lane; o < 37 * 19; o += 32) {
-            const int r = o / 19, pr = o - r * 19;      // outputs c = 2 pr, 2 pr + 1
-            const int j0 = 2 * pr + sh;                 // first u16 column of the window of output c = 2 pr
-            const uint32_t* p = vert + r * kVPitchW + (j0 >> 1);
-            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
-            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;   // a*: windows starting at an even column, b*: at the next (odd) one
-            if (j0 & 1) {
-                a0 = __funnelshift_r(w0, w1, 16); a1 = __funnelshift_r(w1, w2, 16); a2 = __funnelshift_r(w2, w3, 16); a3 = __funnelshift_r(w3, w4, 16);
-                b0 = w1; b1 = w2; b2 = w3; b3 = w4;
-            } else {
-                a0 = w0; a1 = w1; a2 = w2; a3 = w3;
-                b0 = __funnelshift_r(w0, w1, 16); b1 = __funnelshift_r(w1, w2, 16); b2 = __funnelshift_r(w2, w3, 16); b3 = __funnelshift_r(w3, w4, 16);
+        const bool odd = sh & 1;
+        const int wsh = sh >> 1;
+        for (int o = lane; o < 37 * 10; o += 32) {
+            const int r = o / 10, qd = o - r * 10;      // outputs c = 4 qd .. 4 qd + 3
+            const uint32_t* p = vert + r * kVPitchW + 2 * qd + wsh;
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4], w5 = p[5];
+            const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16), s2 = __funnelshift_r(w2, w3, 16),
+                           s3 = __funnelshift_r(w3, w4, 16), s4 = __funnelshift_r(w4, w5, 16);
+            uint32_t v0, v1, v2, v3;
+            if (!odd) {   // windows start at u16 columns 4qd+sh (even), +1, +2, +3
+                v0 = __dp2a_hi(w3, kw1, __dp2a_lo(w2, kw1, __dp2a_hi(w1, kw0, __dp2a_lo(w0, kw0, 0u))));
+                v1 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 0u))));
+                v2 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 0u))));
+                v3 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 0u))));
+            } else {      // first window starts in the upper half of w0
+                v0 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 0u))));
+                v1 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 0u))));
+                v2 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 0u))));
+                v3 = __dp2a_hi(w5, kw1, __dp2a_lo(w4, kw1, __dp2a_hi(w3, kw0, __dp2a_lo(w2, kw0, 0u))));
             }
-            uint32_t va = __dp2a_lo(a0, kw0, 0u); va = __dp2a_hi(a1, kw0, va); va = __dp2a_lo(a2, kw1, va); va = __dp2a_hi(a3, kw1, va);
-            uint32_t vb = __dp2a_lo(b0, kw0, 0u); vb = __dp2a_hi(b1, kw0, vb); vb = __dp2a_lo(b2, kw1, vb); vb = __dp2a_hi(b3, kw1, vb);
-            bl[r * kBPitch + 2 * pr] = (uint8_t)((va + 32768u) >> 16);
-            if (2 * pr + 1 < 37) bl[r * kBPitch + 2 * pr + 1] = (uint8_t)((vb + 32768u) >> 16);
+            const uint32_t packed = ((v0 + 32768u) >> 16) | (((v1 + 32768u) >> 16) << 8) | (((v2 + 32768u) >> 16) << 16) | (((v3 + 32768u) >> 16) << 24);
+            *reinterpret_cast<uint32_t*>(bl + r * kBPitch + 4 * qd) = packed;   // columns 37..39 of the last quad are padding
         }
     }
     __syncwarp();
