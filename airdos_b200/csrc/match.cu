@@ -10,6 +10,7 @@
 // disjoint candidate subsets and merge with shuffles.
 #include <algorithm>
 #include <climits>
+#include <cmath>
 
 #include "orb.cuh"
 
@@ -79,28 +80,71 @@ constexpr int kStereoWarps = 8;
 constexpr int kStereoPerWarp = 8;   // left key-points per warp: amortises the per-CTA band table of the right key-points
 constexpr int TH_HIGH = 100, TH_LOW = 50;   // src/ORBmatcher.cc:37-38
 
-__global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
-    const __grid_constant__ StereoLevels lv, int n_rows, const adb_keypoint* __restrict__ kpsL,
-    const uint8_t* __restrict__ descL, const int32_t* __restrict__ cntL, const adb_keypoint* __restrict__ kpsR,
-    const uint8_t* __restrict__ descR, const int32_t* __restrict__ cntR, int cap, float mbf, float maxD,
-    float* __restrict__ uRight, float* __restrict__ depth, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist,
-    int32_t* __restrict__ sad_out) {
-    extern __shared__ __align__(16) uint8_t st_smem[];
-    float* rx = reinterpret_cast<float*>(st_smem);            // [cap] right x
-    uint32_t* rband = reinterpret_cast<uint32_t*>(rx + cap);  // [cap] minr | maxr << 12 | octave << 24
-    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nL = min(cntL[f], cap), nR = min(cntR[f], cap);
+// Row buckets of the right key-points (src/Frame.cc:846-856): CSR over image rows, one CTA per frame.  The order inside a
+// bucket is arbitrary: the consumer takes the arg-min over (distance, index), which is what "first candidate wins" means
+// for the reference's ascending-index buckets.
+constexpr int kBucketThreads = 512;
+__global__ void __launch_bounds__(kBucketThreads) stereo_bucket_kernel(const __grid_constant__ StereoLevels lv, int n_rows,
+                                                                      const adb_keypoint* __restrict__ kpsR, const int32_t* __restrict__ cntR,
+                                                                      int cap, int maxband, int32_t* __restrict__ row_ptr,
+                                                                      uint16_t* __restrict__ row_items, float2* __restrict__ rinfo) {
+    extern __shared__ int bk_smem[];     // [n_rows + 1] counts -> offsets -> cursors
+    __shared__ int s_run;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int nR = min(cntR[f], cap);
     const adb_keypoint* kR = kpsR + (size_t)f * cap;
-    // row band of every right key-point: src/Frame.cc:846-856 (clamped: DESIGN.md convention D.9)
-    for (int i = tid; i < nR; i += kStereoWarps * 32) {
+    for (int i = tid; i <= n_rows; i += kBucketThreads) bk_smem[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nR; i += kBucketThreads) {
+        const adb_keypoint k = kR[i];
+        const float r = __fmul_rn(2.0f, lv.l[k.octave].scale);
+        const int maxr = min((int)ceilf(__fadd_rn(k.y, r)), n_rows - 1);      // clamped: DESIGN.md convention D.9
+        const int minr = max((int)floorf(__fsub_rn(k.y, r)), 0);
+        for (int y = minr; y <= maxr; ++y) atomicAdd(&bk_smem[y], 1);
+        rinfo[(size_t)f * cap + i] = make_float2(k.x, __int_as_float(k.octave));
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan over the rows
+        int run = 0;
+        for (int y0 = 0; y0 <= n_rows; y0 += 32) {
+            const int y = y0 + lane;
+            const int v = y <= n_rows ? bk_smem[y] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+            if (y <= n_rows) bk_smem[y] = run + inc - v;
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) s_run = run;
+    }
+    __syncthreads();
+    int32_t* rp = row_ptr + (size_t)f * (n_rows + 1);
+    for (int i = tid; i <= n_rows; i += kBucketThreads) rp[i] = bk_smem[i];
+    __syncthreads();
+    uint16_t* items = row_items + (size_t)f * cap * maxband;
+    for (int i = tid; i < nR; i += kBucketThreads) {
         const adb_keypoint k = kR[i];
         const float r = __fmul_rn(2.0f, lv.l[k.octave].scale);
         const int maxr = min((int)ceilf(__fadd_rn(k.y, r)), n_rows - 1);
         const int minr = max((int)floorf(__fsub_rn(k.y, r)), 0);
-        rx[i] = k.x;
-        rband[i] = (uint32_t)minr | ((uint32_t)maxr << 12) | ((uint32_t)k.octave << 24);
+        for (int y = minr; y <= maxr; ++y) {
+            const int pos = atomicAdd(&bk_smem[y], 1);
+            if (pos < cap * maxband) items[pos] = (uint16_t)i;
+        }
     }
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
+    const __grid_constant__ StereoLevels lv, int n_rows, const adb_keypoint* __restrict__ kpsL,
+    const uint8_t* __restrict__ descL, const int32_t* __restrict__ cntL, const uint8_t* __restrict__ descR, int cap, int maxband,
+    const int32_t* __restrict__ row_ptr, const uint16_t* __restrict__ row_items, const float2* __restrict__ rinfo, float mbf, float maxD,
+    float* __restrict__ uRight, float* __restrict__ depth, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist,
+    int32_t* __restrict__ sad_out) {
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nL = min(cntL[f], cap);
+    const int32_t* rp = row_ptr + (size_t)f * (n_rows + 1);
+    const uint16_t* items = row_items + (size_t)f * cap * maxband;
+    const float2* ri = rinfo + (size_t)f * cap;
     for (int sub = 0; sub < kStereoPerWarp; ++sub) {
     const int iL = (blockIdx.x * kStereoWarps + warp) * kStereoPerWarp + sub;
     if (iL >= cap) return;
@@ -121,15 +165,16 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
     int best = TH_HIGH, idx = INT_MAX;
     if (!(maxU < 0)) {
         const uint8_t* dR = descR + (size_t)f * cap * 32;
-        for (int iR = lane; iR < nR; iR += 32) {
-            const uint32_t bnd = rband[iR];
-            const int minr = bnd & 0xFFF, maxr = (bnd >> 12) & 0xFFF, oct = bnd >> 24;
-            if (vL < minr || vL > maxr) continue;
+        const int c_end = rp[vL + 1];
+        for (int c = rp[vL] + lane; c < c_end; c += 32) {
+            const int iR = items[c];
+            const float2 info = ri[iR];
+            const int oct = __float_as_int(info.y);
             if (oct < levelL - 1 || oct > levelL + 1) continue;
-            const float uR = rx[iR];
+            const float uR = info.x;
             if (uR >= minU && uR <= maxU) {
                 const int d = hamming8(qd, reinterpret_cast<const uint4*>(dR + (size_t)iR * 32));
-                if (d < best) { best = d; idx = iR; }
+                if (d < best || (d == best && idx != INT_MAX && iR < idx)) { best = d; idx = iR; }   // buckets are unordered
             }
         }
     }
@@ -143,7 +188,7 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
     if (idx != INT_MAX && best < (TH_HIGH + TH_LOW) / 2) {
         // sub-pixel refinement by 11x11 SAD on the key-point's pyramid level: src/Frame.cc:915-986
         const StereoLevel& S = lv.l[levelL];
-        const float uR0 = rx[idx];
+        const float uR0 = ri[idx].x;
         const float sf = S.inv_scale;
         const float scaleduL = roundf(__fmul_rn(kp.x, sf)), scaledvL = roundf(__fmul_rn(kp.y, sf));
         const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
@@ -389,22 +434,26 @@ adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb
         s.scale = a.scale; s.inv_scale = a.inv_scale;
     }
     const float maxD = mbf / mb;   // src/Frame.cc:859-861: minZ = mb, minD = 0, maxD = mbf / minZ
-    const int cap = L->capacity;
-    const size_t smem = (size_t)cap * 8;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        ADB_CUDA(cudaFuncSetAttribute(stereo_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+    const int cap = L->capacity, n_rows = L->cfg.height;
+    const int maxband = 2 * (int)std::ceil(2.0f * L->lv[L->nlevels - 1].d.scale) + 3;   // rows a right key-point's band can cover
+    ADB_CHECK(cap < 65536 && n_rows < 4096, ADB_ERR_INVALID, "capacity %d / height %d too large for the stereo matcher", cap, n_rows);
+    if (!L->d_row_ptr) {
+        const size_t B = (size_t)L->cfg.max_batch;
+        ADB_CUDA(cudaMalloc(&L->d_row_ptr, B * (n_rows + 1) * 4));
+        ADB_CUDA(cudaMalloc(&L->d_row_items, B * cap * maxband * 2));
+        ADB_CUDA(cudaMalloc(&L->d_rinfo, B * cap * 8));
     }
-    ADB_CHECK(smem <= 200 * 1024, ADB_ERR_INVALID, "capacity %d too large for the stereo matcher", cap);
+    stereo_bucket_kernel<<<n, kBucketThreads, (size_t)(n_rows + 1) * 4, L->stream>>>(sl, n_rows, R->d_kps, R->d_counts, cap, maxband, L->d_row_ptr,
+                                                                                    L->d_row_items, (float2*)L->d_rinfo);
+    ADB_CUDA(cudaGetLastError());
     dim3 grid((cap + kStereoWarps * kStereoPerWarp - 1) / (kStereoWarps * kStereoPerWarp), n);
-    stereo_match_kernel<<<grid, kStereoWarps * 32, smem, L->stream>>>(sl, L->cfg.height, L->d_kps, L->d_desc, L->d_counts, R->d_kps,
-                                                                     R->d_desc, R->d_counts, cap, mbf, maxD, L->d_uright, L->d_depth,
-                                                                     L->d_best_idx, L->d_best_dist, L->d_sad);
+    stereo_match_kernel<<<grid, kStereoWarps * 32, 0, L->stream>>>(sl, n_rows, L->d_kps, L->d_desc, L->d_counts, R->d_desc, cap, maxband,
+                                                                  L->d_row_ptr, L->d_row_items, (const float2*)L->d_rinfo, mbf, maxD, L->d_uright,
+                                                                  L->d_depth, L->d_best_idx, L->d_best_dist, L->d_sad);
     ADB_CUDA(cudaGetLastError());
     stereo_median_kernel<<<n, 256, 0, L->stream>>>(L->d_counts, cap, L->d_sad, L->d_uright, L->d_depth);
     ADB_CUDA(cudaGetLastError());
-    L->launches += 2;
+    L->launches += 3;
     return ADB_OK;
 }
 

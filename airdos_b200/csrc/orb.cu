@@ -865,6 +865,7 @@ static void free_handle(adb_orb* h) {
     cudaFree(h->d_qkeys); cudaFree(h->d_qstate); cudaFree(h->d_qcount); cudaFree(h->d_list); cudaFree(h->d_listcnt);
     cudaFree(h->d_status); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
     cudaFree(h->d_uright); cudaFree(h->d_depth); cudaFree(h->d_best_idx); cudaFree(h->d_best_dist); cudaFree(h->d_sad);
+    cudaFree(h->d_row_ptr); cudaFree(h->d_row_items); cudaFree(h->d_rinfo);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->ev) cudaEventDestroy(h->ev);

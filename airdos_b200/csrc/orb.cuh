@@ -78,6 +78,9 @@ struct adb_orb {
     int32_t* d_best_idx = nullptr;
     int32_t* d_best_dist = nullptr;
     int32_t* d_sad = nullptr;
+    int32_t* d_row_ptr = nullptr;     // stereo row buckets of the right key-points (CSR over image rows)
+    uint16_t* d_row_items = nullptr;
+    void* d_rinfo = nullptr;          // float2 {x, octave} per right key-point
     // level-0 view of the last call (caller's buffer when it is TMA-addressable, else lv[0].img)
     const uint8_t* l0_base = nullptr;
     int l0_pitch = 0;
