@@ -195,64 +195,132 @@ struct State {
     const double* pq; const double* pt; const double* X; const double* J; const double* D; const double* mq; const double* mt;
 };
 
+// sums `nv` doubles per thread over the block in a fixed order; result in out[0..nv) (shared), valid after the call
+template <int NV>
+__device__ inline void block_reduce_fixed(double (&v)[NV], double* scratch /*[8][NV]*/, double* out /*[NV]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0) scratch[warp * NV + k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += scratch[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
 constexpr int kBaThreads = 128;
 
-__global__ void __launch_bounds__(kBaThreads) ba_linearize_kernel(Cam C, Opt O, StaticEdges E, State S, const int* __restrict__ off_pose,
-                                                                 int nd, double* __restrict__ H, double* __restrict__ b,
-                                                                 double* __restrict__ Hll, double* __restrict__ bl,
-                                                                 double* __restrict__ W, double* __restrict__ chi_e, Scalars* sc) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    double rho0 = 0;
-    if (e < E.n && !E.level[e]) {
-        const int ip = E.pose[e], il = E.point[e];
-        double R[9], er[3], Xc[3], Ji[9], Jj[18], rho1;
-        quat_to_rot(S.pq + 4 * ip, R);
-        const int dim = reproj_error(C, R, S.pt + 3 * ip, S.X + 3 * il, E.obs + 3 * e, er, Xc);
+// buildSystem, landmark side: one thread per map point walks the point's (contiguous) edges: residual, Jacobians, Huber
+// weight; Hll / bl accumulate in registers and are stored once (no atomics, fixed order); one 6x3 Hpl block per edge.
+__global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, Opt O, StaticEdges E, State S, const int* __restrict__ point_ptr,
+                                                                       int np, const int* __restrict__ off_pose, double* __restrict__ Hll,
+                                                                       double* __restrict__ bl, double* __restrict__ W,
+                                                                       double* __restrict__ chi_e, Scalars* sc) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    double rho_sum = 0;
+    if (l < np) {
+        double hl[6] = {0, 0, 0, 0, 0, 0}, bv[3] = {0, 0, 0};
+        const double X[3] = {S.X[3 * (size_t)l], S.X[3 * (size_t)l + 1], S.X[3 * (size_t)l + 2]};
+        for (int e = point_ptr[l]; e < point_ptr[l + 1]; ++e) {
+            if (E.level[e]) continue;
+            const int ip = E.pose[e];
+            double R[9], er[3], Xc[3], Ji[9], Jj[18], rho0, rho1;
+            quat_to_rot(S.pq + 4 * ip, R);
+            const int dim = reproj_error(C, R, S.pt + 3 * ip, X, E.obs + 3 * (size_t)e, er, Xc);
+            reproj_jacobians(C, R, Xc, dim, Ji, Jj);
+            const double w0 = E.info[e];
+            const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+            chi_e[e] = c;
+            huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, c, &rho0, &rho1);
+            rho_sum += rho0;
+            const double w = rho1 * w0;
+            int u = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = i; j < 3; ++j, ++u) {
+                    double s = 0;
+                    for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * w * Ji[k * 3 + j];
+                    hl[u] += s;
+                }
+                double s = 0;
+                for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * (-w0 * er[k] * rho1);
+                bv[i] += s;
+            }
+            if (off_pose[ip] >= 0) {
+                double* We = W + 18 * (size_t)e;
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        double s2 = 0;
+                        for (int k = 0; k < dim; ++k) s2 += Jj[k * 6 + i] * w * Ji[k * 3 + j];
+                        We[i * 3 + j] = s2;
+                    }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) Hll[6 * (size_t)l + u] = hl[u];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) bl[3 * (size_t)l + i] = bv[i];
+    }
+    block_sum_to(rho_sum, &sc->chi_cur);
+}
+
+// buildSystem, pose side: one CTA per free pose sums J_pose^T (w Omega) J_pose and -J_pose^T w Omega e over the pose's edges
+// (index list built once per solve) with a fixed-order block reduction and stores its 6x6 block: no atomics.
+// Runs after ba_point_linearize_kernel (reads the chi2 it stored) and before the dense-edge kernel adds to H atomically.
+__global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, StaticEdges E, State S, const int* __restrict__ pose_ptr,
+                                                               const int* __restrict__ pose_edges, const int* __restrict__ free_pose,
+                                                               const int* __restrict__ off_pose, int nd, const double* __restrict__ chi_e,
+                                                               double* __restrict__ H, double* __restrict__ b) {
+    __shared__ double scratch[8 * 27], red[27];
+    const int ip = free_pose[blockIdx.x], op = off_pose[ip];
+    double v[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) v[k] = 0;
+    double R[9];
+    quat_to_rot(S.pq + 4 * ip, R);
+    const double t[3] = {S.pt[3 * ip], S.pt[3 * ip + 1], S.pt[3 * ip + 2]};
+    for (int q = pose_ptr[ip] + threadIdx.x; q < pose_ptr[ip + 1]; q += 256) {
+        const int e = pose_edges[q];
+        if (E.level[e]) continue;
+        double er[3], Xc[3], Ji[9], Jj[18], rho0, rho1;
+        const int dim = reproj_error(C, R, t, S.X + 3 * (size_t)E.point[e], E.obs + 3 * (size_t)e, er, Xc);
         reproj_jacobians(C, R, Xc, dim, Ji, Jj);
         const double w0 = E.info[e];
-        const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
-        chi_e[e] = c;
-        huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, c, &rho0, &rho1);
+        huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, chi_e[e], &rho0, &rho1);
         const double w = rho1 * w0;
-        const double wr[3] = {-w0 * er[0] * rho1, -w0 * er[1] * rho1, -w0 * er[2] * rho1};
-        // Hll (symmetric, 6 unique) and bl
-        double* hl = Hll + 6 * (size_t)il;
         int u = 0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int r = 0; r < 6; ++r) {
 #pragma unroll
-            for (int j = i; j < 3; ++j, ++u) {
+            for (int c = 0; c <= r; ++c, ++u) {
                 double s = 0;
-                for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * w * Ji[k * 3 + j];
-                atomicAdd(hl + u, s);
+                for (int k = 0; k < dim; ++k) s += Jj[k * 6 + r] * w * Jj[k * 6 + c];
+                v[u] += s;
             }
             double s = 0;
-            for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * wr[k];
-            atomicAdd(bl + 3 * (size_t)il + i, s);
-        }
-        const int op = off_pose[ip];
-        double* We = W + 18 * (size_t)e;
-        if (op >= 0) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                for (int j = 0; j <= i; ++j) {   // lower triangle of the 6x6 pose block
-                    double s = 0;
-                    for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * w * Jj[k * 6 + j];
-                    atomicAdd(H + (size_t)(op + i) * nd + op + j, s);
-                }
-                double s = 0;
-                for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * wr[k];
-                atomicAdd(b + op + i, s);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    double s2 = 0;
-                    for (int k = 0; k < dim; ++k) s2 += Jj[k * 6 + i] * w * Ji[k * 3 + j];
-                    We[i * 3 + j] = s2;
-                }
-            }
+            for (int k = 0; k < dim; ++k) s += Jj[k * 6 + r] * (-w0 * er[k] * rho1);
+            v[21 + r] += s;
         }
     }
-    block_sum_to(rho0, &sc->chi_cur);
+    block_reduce_fixed<27>(v, scratch, red);
+    if (threadIdx.x < 21) {
+        int r = 0, acc = 0;
+        while (acc + r + 1 <= (int)threadIdx.x) { acc += r + 1; ++r; }
+        const int c = threadIdx.x - acc;
+        H[(size_t)(op + r) * nd + op + c] = red[threadIdx.x];
+    } else if (threadIdx.x < 27) {
+        b[op + threadIdx.x - 21] = red[threadIdx.x];
+    }
 }
 
 // Dense-block edges: joint reprojection (type 0), rigidity (1), motion (2); one thread per edge.
@@ -613,26 +681,6 @@ __device__ inline void pose_edge_error(const Cam& C, const double* R, const doub
     }
 }
 
-// sums `nv` doubles per thread over the block in a fixed order; result in out[0..nv) (shared), valid after the call
-template <int NV>
-__device__ inline void block_reduce_fixed(double (&v)[NV], double* scratch /*[8][NV]*/, double* out /*[NV]*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double x = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-        if (lane == 0) scratch[warp * NV + k] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double s = 0;
-        for (int w = 0; w < kPoseThreads / 32; ++w) s += scratch[w * NV + threadIdx.x];
-        out[threadIdx.x] = s;
-    }
-    __syncthreads();
-}
-
 __device__ inline bool chol6_solve(const double* H, double lambda, const double* b, double* x) {
     double L[36];
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) L[i * 6 + j] = H[i * 6 + j] + (i == j ? lambda : 0.0);
@@ -829,98 +877,130 @@ constexpr int kCholNB = 32;
 
 // n = matrix order (columns), n_rows >= n: rows n..n_rows-1 are extra right-hand-side rows carried through the factorisation
 // (row n = b^T turns into y^T = (L^-1 b)^T, i.e. the forward substitution comes for free).  pitch = n.
-__global__ void __launch_bounds__(1024) chol_left_kernel(double* __restrict__ A, int n, int n_rows, int kb, double* __restrict__ Ldiag,
-                                                        int* __restrict__ info) {
+constexpr int kCholThreads = 512;   // 16 warps: thread (r, c) owns elements (r, c) and (r + 16, c) of the 32 x 32 tiles
+__global__ void __launch_bounds__(kCholThreads) chol_left_kernel(double* __restrict__ A, int n, int n_rows, int kb, double* __restrict__ Ldiag,
+                                                                int* __restrict__ info) {
     __shared__ double Ta[kCholNB][kCholNB + 1], Tb[kCholNB][kCholNB + 1];   // operand tiles, then U and D / L
-    __shared__ double col[kCholNB];
-    __shared__ double s_isd;
-    const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;
+    __shared__ double col[kCholNB];                                          // 1 / L[j][j]
+    const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;                 // r in 0..15
     const int k = kb * kCholNB, ib = kb + blockIdx.x, i0 = ib * kCholNB;
     const int nbk = min(kCholNB, n - k);
-    double accU = 0.0, accD = 0.0;
+    double accU[2] = {0.0, 0.0}, accD[2] = {0.0, 0.0};
     // software-pipelined tile loads: the next tiles are fetched while the current ones are multiplied
-    double na = 0.0, nb = 0.0;
+    double na[2] = {0.0, 0.0}, nb[2] = {0.0, 0.0};
     if (k > 0) {
-        na = (i0 + r < n_rows) ? A[(size_t)(i0 + r) * n + c] : 0.0;
-        nb = A[(size_t)(k + r) * n + c];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            na[h] = (i0 + r + 16 * h < n_rows) ? A[(size_t)(i0 + r + 16 * h) * n + c] : 0.0;
+            nb[h] = A[(size_t)(k + r + 16 * h) * n + c];
+        }
     }
     for (int p0 = 0; p0 < k; p0 += kCholNB) {
-        Ta[r][c] = na; Tb[r][c] = nb;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { Ta[r + 16 * h][c] = na[h]; Tb[r + 16 * h][c] = nb[h]; }
         __syncthreads();
         if (p0 + kCholNB < k) {
-            na = (i0 + r < n_rows) ? A[(size_t)(i0 + r) * n + p0 + kCholNB + c] : 0.0;
-            nb = A[(size_t)(k + r) * n + p0 + kCholNB + c];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                na[h] = (i0 + r + 16 * h < n_rows) ? A[(size_t)(i0 + r + 16 * h) * n + p0 + kCholNB + c] : 0.0;
+                nb[h] = A[(size_t)(k + r + 16 * h) * n + p0 + kCholNB + c];
+            }
         }
 #pragma unroll
         for (int p = 0; p < kCholNB; ++p) {
             const double b = Tb[c][p];
-            accU += Ta[r][p] * b;
-            accD += Tb[r][p] * b;
+            accU[0] += Ta[r][p] * b; accU[1] += Ta[r + 16][p] * b;
+            accD[0] += Tb[r][p] * b; accD[1] += Tb[r + 16][p] * b;
         }
         __syncthreads();
     }
-    double u = (i0 + r < n_rows && c < nbk) ? A[(size_t)(i0 + r) * n + k + c] - accU : 0.0;
-    double t = (r < nbk && c < nbk) ? ((c <= r) ? A[(size_t)(k + r) * n + k + c] - accD : 0.0) : (r == c ? 1.0 : 0.0);
-    // ---- factor D: thread (r, c) owns element (r, c); two barriers per column
-    for (int j = 0; j < kCholNB; ++j) {
-        if (r == j && c == j) {
-            double d = t;
-            if (!(d > 0.0) || !isfinite(d)) { if (blockIdx.x == 0 && *info == 0) *info = k + j + 1; d = 1.0; }
-            const double sd = sqrt(d);
-            t = sd;
-            s_isd = 1.0 / sd;
-        }
-        __syncthreads();
-        if (c == j) {
-            if (r > j) t *= s_isd;
-            col[r] = r >= j ? t : 0.0;     // column j of L (col[j] = L[j][j])
-        }
-        __syncthreads();
-        if (c > j && c <= r) t -= col[r] * col[c];
+    double u[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int rr = r + 16 * h;
+        u[h] = (i0 + rr < n_rows && c < nbk) ? A[(size_t)(i0 + rr) * n + k + c] - accU[h] : 0.0;
+        Tb[rr][c] = (rr < nbk && c < nbk) ? ((c <= rr) ? A[(size_t)(k + rr) * n + k + c] - accD[h] : 0.0) : (rr == c ? 1.0 : 0.0);
     }
-    Tb[r][c] = c <= r ? t : 0.0;
-    if (r == c) col[r] = 1.0 / t;          // 1 / L[j][j] (no hazard: the loop's last read of col is behind a barrier below)
+    __syncthreads();
+    // ---- factor D with one warp and no block barriers: lane = row held in registers, column j broadcast by shuffles
+    if (tid < 32) {
+        const int lane = tid;
+        double row[kCholNB];
+#pragma unroll
+        for (int q = 0; q < kCholNB; ++q) row[q] = Tb[lane][q];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < kCholNB; ++j) {
+            double d = __shfl_sync(0xFFFFFFFFu, row[j], j);
+            if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
+            const double sd = sqrt(d), isd = 1.0 / sd;
+            double v = 0.0;
+            if (lane == j) { row[j] = sd; col[j] = isd; }
+            else if (lane > j) { v = row[j] * isd; row[j] = v; }
+#pragma unroll
+            for (int q = j + 1; q < kCholNB; ++q) {
+                const double vq = __shfl_sync(0xFFFFFFFFu, v, q);
+                if (lane >= q) row[q] -= v * vq;
+            }
+        }
+        if (bad && lane == 0 && blockIdx.x == 0 && *info == 0) *info = k + 1;
+#pragma unroll
+        for (int q = 0; q < kCholNB; ++q) Tb[lane][q] = q <= lane ? row[q] : 0.0;
+    }
     __syncthreads();
     // the diagonal block's CTA publishes the factor (A keeps the unfactored block: nobody reads it again); of its rows only
     // the extra right-hand-side rows (>= n) that share the row block still need the triangular solve
-    if (blockIdx.x == 0) Ldiag[(size_t)kb * kCholNB * kCholNB + tid] = Tb[r][c];
-    // ---- x L_kk^T = u: warp r owns row r, lane c holds x[c]; right-looking, no block barriers
+    if (blockIdx.x == 0) { Ldiag[(size_t)kb * kCholNB * kCholNB + tid] = Tb[r][c]; Ldiag[(size_t)kb * kCholNB * kCholNB + tid + 512] = Tb[r + 16][c]; }
+    // ---- x L_kk^T = u: a warp owns rows r and r + 16, lane c holds x[c]; right-looking, no block barriers
 #pragma unroll
-    for (int j = 0; j < kCholNB; ++j) {
-        double xj = __shfl_sync(0xFFFFFFFFu, u, j) * col[j];
-        if (c == j) u = xj;
-        if (c > j) u -= xj * Tb[c][j];
+    for (int h = 0; h < 2; ++h) {
+        double x = u[h];
+#pragma unroll
+        for (int j = 0; j < kCholNB; ++j) {
+            const double xj = __shfl_sync(0xFFFFFFFFu, x, j) * col[j];
+            if (c == j) x = xj;
+            if (c > j) x -= xj * Tb[c][j];
+        }
+        const int rr = r + 16 * h;
+        if (i0 + rr < n_rows && c < nbk && (blockIdx.x > 0 || i0 + rr >= n)) A[(size_t)(i0 + rr) * n + k + c] = x;
     }
-    if (i0 + r < n_rows && c < nbk && (blockIdx.x > 0 || i0 + r >= n)) A[(size_t)(i0 + r) * n + k + c] = u;
 }
 
-// backward substitution L^T x = y, y = row n of the factored array; x -> out.  One CTA, 32-wide blocks.
+// backward substitution L^T x = y, y = row n of the factored array; x -> out.  One CTA, 32-wide blocks.  Every block step
+// first stages its diagonal factor in shared memory (one coalesced load) so that the 32 serial pivots never wait on L2.
 __global__ void __launch_bounds__(1024) chol_back_kernel(const double* __restrict__ A, const double* __restrict__ Ldiag, int n, double* __restrict__ out) {
     extern __shared__ double yb[];       // [n] working copy of y
+    __shared__ double Ld[kCholNB][kCholNB + 1];
     __shared__ double xb[kCholNB];
     const int tid = threadIdx.x;
     for (int i = tid; i < n; i += blockDim.x) yb[i] = A[(size_t)n * n + i];
-    __syncthreads();
+    if (tid < kCholNB) xb[tid] = 0.0;
     const int nblk = (n + kCholNB - 1) / kCholNB;
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int k = kb * kCholNB, nbk = min(kCholNB, n - k);
+        Ld[tid >> 5][tid & 31] = Ldiag[(size_t)kb * kCholNB * kCholNB + tid];
+        __syncthreads();
         if (tid < 32) {
             const int lane = tid;
-            const double* Ld = Ldiag + (size_t)kb * kCholNB * kCholNB;
             double part = (lane < nbk) ? yb[k + lane] : 0.0;
             for (int j = nbk - 1; j >= 0; --j) {
                 double xj = 0.0;
-                if (lane == j) xj = part / Ld[j * kCholNB + j];
+                if (lane == j) xj = part / Ld[j][j];
                 xj = __shfl_sync(0xFFFFFFFFu, xj, j);
                 if (lane == j) xb[j] = xj;
-                if (lane < j) part -= Ld[j * kCholNB + lane] * xj;
+                if (lane < j) part -= Ld[j][lane] * xj;
             }
         }
         __syncthreads();
         if (tid < nbk) out[k + tid] = xb[tid];
-        for (int i = tid; i < k; i += blockDim.x) {   // y[i] -= sum_j L[k+j][i] x[j]
+        for (int i = tid; i < k; i += blockDim.x) {   // y[i] -= sum_j L[k+j][i] x[j]: 32 independent coalesced loads per thread
+            const double* col = A + (size_t)k * n + i;
+            double a[kCholNB];
+#pragma unroll
+            for (int j = 0; j < kCholNB; ++j) a[j] = j < nbk ? col[(size_t)j * n] : 0.0;
             double sacc = yb[i];
-            for (int j = 0; j < nbk; ++j) sacc -= A[(size_t)(k + j) * n + i] * xb[j];
+#pragma unroll
+            for (int j = 0; j < kCholNB; ++j) sacc -= a[j] * xb[j];
             yb[i] = sacc;
         }
         __syncthreads();
@@ -954,7 +1034,7 @@ struct adb_ba {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // device buffers
     DevBuf pq[2], pt[2], X[2], Jt[2], Dd[2], mq[2], mt[2];                         // double-buffered state
-    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, off_pose, act_point;
+    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, off_pose, act_point, pose_ptr, pose_edges, free_pose;
     DevBuf j_pose, j_joint, j_obs, j_info, j_level, r_i, r_j, r_d, r_info, r_level, m_p1, m_p2, m_m, m_dt, m_info, m_level;
     DevBuf off_joint, off_dist, off_motion;
     DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work;
@@ -1008,6 +1088,7 @@ struct Ctx {
     std::vector<uint8_t> lvl_e, lvl_j, lvl_r, lvl_m, act_point;
     std::vector<int> off_pose, off_dist, off_motion, off_joint;
     std::vector<int2> pairs, chunks;
+    std::vector<int> pose_ptr, pose_edges, free_pose;
     int nd = 0, cur = 0, chi_last = 0;
     double lambda = 0, ni = 2;
     int trace_len = 0;
@@ -1054,11 +1135,21 @@ struct Ctx {
             se_pose[k] = P->edge_pose[e]; se_point[k] = P->edge_point[e]; se_info[k] = P->edge_info[e];
             for (int c = 0; c < 3; ++c) se_obs[(size_t)3 * k + c] = P->edge_obs[(size_t)3 * e + c];
         }
+        // CSR of the (sorted) edges by pose, for the atomic-free pose-block accumulation
+        pose_ptr.assign(P->n_poses + 1, 0);
+        for (int k = 0; k < E; ++k) pose_ptr[se_pose[k] + 1]++;
+        for (int i = 0; i < P->n_poses; ++i) pose_ptr[i + 1] += pose_ptr[i];
+        pose_edges.assign(E, 0);
+        {
+            std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
+            for (int k = 0; k < E; ++k) pose_edges[fill[se_pose[k]]++] = k;
+        }
         cudaStream_t st = s->stream;
         adb_status r;
 #define UP(buf, ptr_, n) if ((r = upload(buf, ptr_, (size_t)(n), st)) != ADB_OK) return r
         UP(s->e_pose, se_pose.data(), E); UP(s->e_point, se_point.data(), E); UP(s->e_obs, se_obs.data(), 3 * (size_t)E);
         UP(s->e_info, se_info.data(), E); UP(s->point_ptr, ptr.data(), NP + 1);
+        UP(s->pose_ptr, pose_ptr.data(), P->n_poses + 1); UP(s->pose_edges, pose_edges.data(), E);
         UP(s->pq[0], P->pose_q, 4 * (size_t)P->n_poses); UP(s->pt[0], P->pose_t, 3 * (size_t)P->n_poses); UP(s->X[0], P->points, 3 * (size_t)NP);
         UP(s->Jt[0], P->joints, 3 * (size_t)P->n_joints); UP(s->Dd[0], P->dists, P->n_dists);
         UP(s->mq[0], P->motion_q, 4 * (size_t)P->n_motions); UP(s->mt[0], P->motion_t, 3 * (size_t)P->n_motions);
@@ -1111,6 +1202,8 @@ struct Ctx {
         for (int i = 0; i < P->n_motions; ++i) if (am[i]) { off_motion[i] = o; o += 6; }
         for (int i = 0; i < P->n_joints; ++i) if (aj[i]) { off_joint[i] = o; o += 3; }
         nd = o;
+        free_pose.clear();
+        for (int i = 0; i < P->n_poses; ++i) if (off_pose[i] >= 0) free_pose.push_back(i);
         // Schur pair list: (e1, e2) of one point with block(e1) >= block(e2), counting-sorted by destination block
         // (pose offsets are multiples of 6 and come first in the dense layout), then cut into chunks
         {
@@ -1154,7 +1247,7 @@ struct Ctx {
         adb_status r;
 #define UP(buf, v) if ((r = upload(buf, (v).data(), (v).size(), st)) != ADB_OK) return r
         UP(s->e_level, lvl_e); UP(s->j_level, lvl_j); UP(s->r_level, lvl_r); UP(s->m_level, lvl_m); UP(s->act_point, act_point);
-        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs); UP(s->chunks, chunks);
+        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs); UP(s->chunks, chunks); UP(s->free_pose, free_pose);
 #undef UP
         const size_t n2 = std::max<size_t>((size_t)nd * nd, 1);
         if ((r = s->H.ensure(n2 * 8)) != ADB_OK) return r;
@@ -1181,15 +1274,18 @@ struct Ctx {
         tm.begin(0);
         ADB_CUDA(cudaMemsetAsync(s->H.p, 0, std::max<size_t>((size_t)nd * nd, 1) * 8, st));
         ADB_CUDA(cudaMemsetAsync(s->b.p, 0, std::max(nd, 1) * 8, st));
-        ADB_CUDA(cudaMemsetAsync(s->Hll.p, 0, std::max<size_t>(NP, 1) * 48, st));
-        ADB_CUDA(cudaMemsetAsync(s->bl.p, 0, std::max<size_t>(NP, 1) * 24, st));
         ADB_CUDA(cudaMemsetAsync(s->scal.p, 0, sizeof(Scalars), st));
         chi_last = cur;
-        if (E > 0) {
-            ba_linearize_kernel<<<grid_for(E, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), state(cur), s->off_pose.as<int>(), nd,
-                                                                               s->H.as<double>(), s->b.as<double>(), s->Hll.as<double>(),
-                                                                               s->bl.as<double>(), s->W.as<double>(), s->chi_e[chi_last].as<double>(),
-                                                                               s->scal.as<Scalars>());
+        if (NP > 0) {
+            ba_point_linearize_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), state(cur), s->point_ptr.as<int>(), NP,
+                                                                                      s->off_pose.as<int>(), s->Hll.as<double>(), s->bl.as<double>(),
+                                                                                      s->W.as<double>(), s->chi_e[chi_last].as<double>(), s->scal.as<Scalars>());
+            ++s->launches;
+        }
+        if (E > 0 && !free_pose.empty()) {
+            ba_pose_linearize_kernel<<<(int)free_pose.size(), 256, 0, st>>>(cam(), opt(robust), sedges(), state(cur), s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
+                                                                           s->free_pose.as<int>(), s->off_pose.as<int>(), nd, s->chi_e[chi_last].as<double>(),
+                                                                           s->H.as<double>(), s->b.as<double>());
             ++s->launches;
         }
         if (n_dyn() > 0) {
@@ -1238,7 +1334,7 @@ struct Ctx {
             {
                 const int nblk = (nd + kCholNB - 1) / kCholNB, nrb = (nd + 1 + kCholNB - 1) / kCholNB;   // row blocks incl. the rhs row
                 for (int kb = 0; kb < nblk; ++kb) {
-                    chol_left_kernel<<<nrb - kb, 1024, 0, st>>>(s->Sm.as<double>(), nd, nd + 1, kb, s->work.as<double>(), &sc->info);
+                    chol_left_kernel<<<nrb - kb, kCholThreads, 0, st>>>(s->Sm.as<double>(), nd, nd + 1, kb, s->work.as<double>(), &sc->info);
                     ++s->launches;
                 }
                 chol_back_kernel<<<1, 1024, (size_t)nd * 8, st>>>(s->Sm.as<double>(), s->work.as<double>(), nd, s->bs.as<double>());
@@ -1443,7 +1539,7 @@ adb_status adb_ba_destroy(adb_ba_t s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     DevBuf* all[] = {&s->pq[0], &s->pq[1], &s->pt[0], &s->pt[1], &s->X[0], &s->X[1], &s->Jt[0], &s->Jt[1], &s->Dd[0], &s->Dd[1], &s->mq[0], &s->mq[1],
-                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->chunks, &s->off_pose,
+                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->chunks, &s->pose_ptr, &s->pose_edges, &s->free_pose, &s->off_pose,
                      &s->act_point, &s->j_pose, &s->j_joint, &s->j_obs, &s->j_info, &s->j_level, &s->r_i, &s->r_j, &s->r_d, &s->r_info, &s->r_level,
                      &s->m_p1, &s->m_p2, &s->m_m, &s->m_dt, &s->m_info, &s->m_level, &s->off_joint, &s->off_dist, &s->off_motion, &s->H, &s->b,
                      &s->Sm, &s->bs, &s->Hll, &s->bl, &s->W, &s->Dinv, &s->db, &s->chi_e[0], &s->chi_e[1], &s->chi_j[0], &s->chi_j[1], &s->chi_r[0],
