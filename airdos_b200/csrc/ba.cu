@@ -24,6 +24,7 @@
 // level, far below the 1e-4 parity bar.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <limits>
@@ -1562,10 +1563,18 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
     R->iterations_run[0] = R->iterations_run[1] = 0; R->trials_run = 0; R->stopped = 0; R->trace_len = 0;
     R->chi2_initial = 0; R->chi2_round[0] = R->chi2_round[1] = 0; R->lambda_final = 0;
     adb_status r;
+    const bool timing = getenv("ADB_BA_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t0 = now();
     if ((r = c.upload_problem()) != ADB_OK) return r;
+    auto t1 = now();
     if ((r = c.build_layout()) != ADB_OK) return r;
+    auto t2 = now();
     double chi = 0;
     if ((r = c.optimize(O->iterations[0], true, 0, &chi)) != ADB_OK) return r;
+    auto t3 = now();
+    if (timing) fprintf(stderr, "[adb_ba] upload %.2f ms, layout %.2f ms, round-1 optimise %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
     R->chi2_round[0] = chi;
     std::vector<uint8_t> fe, fj, fr, fm;
     const bool more = !c.stopped() && O->iterations[1] > 0;

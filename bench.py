@@ -236,8 +236,19 @@ def main():
     dom = int(np.argmax(stage))
     peak, peak_src = peaks()
     achieved = alg_bytes[dom] * P / (stage[dom] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), scaled to this launch's frames
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_dram_traffic.json")))
+        key = names[dom].split("(")[0]
+        if key in tj and key != "pyr_resize_kernel":
+            traffic = float(np.mean([e["dram_bytes"] for e in tj[key]])) / 128.0 * P     # captured at 128 frames per launch
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom] * P,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom] * P,
+                "note": "FAST / descriptor kernels are issue-bound integer work (ncu: 70-80 % of issue slots, <2 % of DRAM bandwidth); the HBM "
+                        "fraction is reported because the contract asks for it, DRAM traffic ~= algorithmic bytes (no re-reads)",
                 "kernel_ms": float(stage[dom]),
                 "stage_ms": {n: float(s) for n, s in zip(names, stage)},
                 "pipeline_achieved_GBps": BYTES_PER_FRAME * 2 * P / (ms_step * 1e-3) / 1e9,
