@@ -27,6 +27,10 @@ class AdbError(RuntimeError):
         self.status = status
 
 
+class GatherTargets(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p * 8), ("desc", C.c_void_p * 8), ("counts", C.c_void_p * 8)]
+
+
 class OrbConfig(C.Structure):
     _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("width", C.c_int32),
@@ -51,6 +55,7 @@ SYMBOLS = {
     "adb_orb_extract_batch_device": (C.c_int, [_vp, _i32, _vp, _sz, _i32, _i32, _i32, _vp, _sz, _i32]),
     "adb_orb_sync": (C.c_int, [_vp]),
     "adb_orb_stream": (_vp, [_vp]),
+    "adb_orb_set_gather": (C.c_int, [_vp, _vp]),
     "adb_orb_profile": (C.c_int, [_vp, _i32]),
     "adb_orb_stage_ms": (C.c_int, [_vp, _fp]),
     "adb_orb_launch_count": (C.c_int64, [_vp]),

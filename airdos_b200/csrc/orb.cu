@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
                                                                          const int8_t* __restrict__ pattern,
                                                                          adb_keypoint* __restrict__ kps,
                                                                          uint8_t* __restrict__ desc,
-                                                                         int32_t* __restrict__ counts, int cap) {
+                                                                         int32_t* __restrict__ counts, int cap,
+                                                                         const __grid_constant__ adb_gather_targets gather) {
     extern __shared__ __align__(128) uint8_t desc_smem_raw[];
     DescSmem& sm = *reinterpret_cast<DescSmem*>((reinterpret_cast<uintptr_t>(desc_smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y;
@@ -666,7 +667,10 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         if (lvl < 0 && i < total + c) { lvl = l; base = total; }
         total += c;
     }
-    if (i == 0 && lane == 0) counts[f] = total;
+    if (i == 0 && lane == 0) {
+        counts[f] = total;
+        for (int g = 0; g < gather.n; ++g) gather.counts[g][f] = total;   // peer-mapped over NVLink
+    }
     if (lvl < 0 || i >= cap) return;
     const LevelDev& L = levels[lvl];
     const uint32_t e = list[(size_t)f * list_total + L.list_base + (i - base)];
@@ -813,6 +817,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         byte |= (uint32_t)(t0 < t1) << k;
     }
     desc[((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
+    // fused all-gather: the same 32 B go to every peer's buffer (one NVLink write transaction per peer)
+    for (int g = 0; g < gather.n; ++g) gather.desc[g][((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
     if (lane == 0) {
         adb_keypoint kp;
         kp.x = lvl ? __fmul_rn((float)cx, L.scale) : (float)cx;
@@ -822,6 +828,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         kp.response = (float)resp;
         kp.octave = lvl;
         kps[(size_t)f * cap + i] = kp;
+        for (int g = 0; g < gather.n; ++g) gather.kps[g][(size_t)f * cap + i] = kp;
     }
 }
 
@@ -1094,7 +1101,7 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         dim3 grid((h->capacity + kDescWarps - 1) / kDescWarps, n);
         orient_describe_kernel<<<grid, kDescWarps * 32, sizeof(DescSmem) + 128, st>>>(h->patch_maps, h->d_levels, nl, h->d_list, h->list_total,
                                                                                      h->d_listcnt, h->d_pattern, h->d_kps, h->d_desc,
-                                                                                     h->d_counts, h->capacity);
+                                                                                     h->d_counts, h->capacity, h->gather);
         ADB_STAGE("orient_describe");
     }
     return ADB_OK;
@@ -1161,6 +1168,15 @@ adb_status adb_orb_level_info(adb_orb_t h, int32_t level, int32_t* w, int32_t* h
 }
 
 void* adb_orb_stream(adb_orb_t h) { return h ? (void*)h->stream : nullptr; }
+
+adb_status adb_orb_set_gather(adb_orb_t h, const adb_gather_targets* t) {
+    ADB_CHECK(h, ADB_ERR_INVALID, "null handle");
+    if (!t || t->n == 0) { h->gather.n = 0; return ADB_OK; }
+    ADB_CHECK(t->n > 0 && t->n <= ADB_MAX_GATHER, ADB_ERR_INVALID, "gather target count %d out of range", t->n);
+    for (int g = 0; g < t->n; ++g) ADB_CHECK(t->kps[g] && t->desc[g] && t->counts[g], ADB_ERR_INVALID, "null gather target %d", g);
+    h->gather = *t;
+    return ADB_OK;
+}
 
 adb_status adb_orb_profile(adb_orb_t h, int32_t enable) {
     ADB_CHECK(h, ADB_ERR_INVALID, "null handle");

@@ -90,6 +90,7 @@ struct adb_orb {
     adb::TmaMaps16 cell_maps;    // FAST cell boxes
     adb::TmaMaps16 patch_maps;   // descriptor patches
     // profiling: CUDA events on the handle's stream around each stage of the last call
+    adb_gather_targets gather = {};   // peer buffers the descriptor kernel also writes to (n = 0: off)
     bool profiling = false;
     cudaEvent_t pev[8] = {};
     int pev_n = 0;

@@ -48,3 +48,39 @@ def gathered_frame(kps_all: torch.Tensor, desc_all: torch.Tensor, counts_all: to
     k = kps_all[frame, :n].cpu().numpy().copy().view(np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                                                               ("response", "<f4"), ("octave", "<i4")])).reshape(n)
     return k, desc_all[frame, :n].cpu().numpy()
+
+
+class SymmetricGather:
+    """Gathered result buffers in symmetric memory (torch.distributed._symmetric_memory): every rank owns
+    [world][P][cap] key-point / descriptor / count arrays and maps every peer's copy over NVLink, so that the
+    extractor's descriptor kernel can store each record straight into all of them (adb_orb_set_gather)."""
+
+    def __init__(self, world: int, rank: int, frames: int, cap: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank, self.P, self.cap = world, rank, frames, cap
+        self.kp_bytes = world * frames * cap * 24
+        self.desc_bytes = world * frames * cap * 32
+        self.cnt_bytes = world * frames * 4
+        total = self.kp_bytes + self.desc_bytes + self.cnt_bytes
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.peers = [self.hdl.get_buffer(r, (total,), torch.uint8) for r in range(world)]
+        dist.barrier()
+
+    def targets(self):
+        """Pointer triples (one per peer, offset to this rank's slot) for ORBextractor.set_gather."""
+        slot_kp, slot_desc, slot_cnt = self.P * self.cap * 24, self.P * self.cap * 32, self.P * 4
+        kps = [p.data_ptr() + self.rank * slot_kp for p in self.peers]
+        desc = [p.data_ptr() + self.kp_bytes + self.rank * slot_desc for p in self.peers]
+        cnts = [p.data_ptr() + self.kp_bytes + self.desc_bytes + self.rank * slot_cnt for p in self.peers]
+        return kps, desc, cnts
+
+    def kps_view(self):
+        return self.buf[:self.kp_bytes].view(self.world, self.P, self.cap, 24)
+
+    def desc_view(self):
+        return self.buf[self.kp_bytes:self.kp_bytes + self.desc_bytes].view(self.world, self.P, self.cap, 32)
+
+    def counts_view(self):
+        return self.buf[self.kp_bytes + self.desc_bytes:].view(torch.int32).view(self.world, self.P)

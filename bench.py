@@ -136,6 +136,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = descriptor kernel stores records into every peer's buffer over NVLink (symmetric memory); "
+                         "'nccl' = separate ncclAllGather per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -173,12 +176,24 @@ def main():
     kp_ptrR, desc_ptrR, cnt_ptrR, _ = exR.results_device()
     cntR_t = adist.as_tensor(cnt_ptrR, (P,), "<i4", dev)
     gather_bufs = None
+    gather_mode = "none"
+    symm = None
+    if world > 1 and args.gather == "fused":
+        try:
+            symm = adist.SymmetricGather(world, rank, P, cap, dev)      # rendezvous + peer-mapped buffers
+            exL.set_gather(*symm.targets())
+            gather_mode = "fused: orient_describe_kernel stores every record to all peers over NVLink (symmetric memory)"
+        except Exception as e:   # symmetric memory unavailable: separate collective
+            symm = None
+            gather_mode = "nccl all_gather_into_tensor (symmetric memory unavailable: %r)" % (e,)
+    elif world > 1:
+        gather_mode = "nccl all_gather_into_tensor"
 
     def step():
         exL.extract_batch_device(dL.data_ptr(), P)
         exR.extract_batch_device(dR.data_ptr(), P)
         adb.orb.stereo_match_device(exL, exR, P, mb, mbf)
-        if world > 1:
+        if world > 1 and symm is None:
             with torch.cuda.stream(sL):
                 return adist.all_gather_records(kpsL_t, descL_t, cntL_t)
         return None
@@ -192,6 +207,13 @@ def main():
     for _ in range(Wm):
         gather_bufs = step()
     sync_all()
+    if symm is not None:   # every rank now holds every rank's left-image records: check the counts against the owners'
+        allc = [torch.zeros(P, dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(allc, cntL_t.clone())
+        got = symm.counts_view()
+        for r in range(world):
+            assert torch.equal(got[r], allc[r]), "fused gather: counts of rank %d differ" % r
+        assert torch.equal(symm.desc_view()[rank], descL_t), "fused gather: own descriptors differ"
     n_kp_step = int(cntL_t.sum().item() + cntR_t.sum().item())
     launches0 = exL.launch_count() + exR.launch_count()
     sampler = ClockSampler(local)
@@ -285,13 +307,35 @@ def main():
            "h2d_bytes_per_step": int(2 * P * W * H),
            "d2h_bytes_per_step": int(2 * (P * cap * (24 + 32) + P * 4) + 4 * P * cap * 4 + P * 4)}
 
+    # ---- drop-in latency: one stereo pair per call through the host-buffer C-ABI, as Frame::Frame would call it
+    lat_ms = None
+    if rank == 0:
+        e1L = adb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=1, device=local)
+        e1R = adb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=1, device=local)
+        o1L = adb.orb.HostResults(1, cap, pinned=True); o1R = adb.orb.HostResults(1, cap, pinned=True); o1S = adb.orb.HostStereo(1, cap, pinned=True)
+
+        def one_pair(i):
+            tR = threading.Thread(target=e1R.extract_batch, args=(npR[i:i + 1],), kwargs={"out": o1R})
+            tR.start()
+            e1L.extract_batch(npL[i:i + 1], out=o1L)
+            tR.join()
+            adb.compute_stereo_matches(e1L, e1R, 1, mb, mbf, out=o1S)
+
+        for i in range(5):
+            one_pair(i % P)
+        t0 = time.perf_counter()
+        for i in range(50):
+            one_pair(i % P)
+        lat_ms = (time.perf_counter() - t0) / 50 * 1e3
+        e1L.close(); e1R.close()
+
     out = {
         "metric": "orb_keypoints_per_s", "value": value, "unit": "keypoints/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "640x480 stereo stream, 8-level pyramid, 2000 feat/frame, ORB extract L+R + stereo match"
-                               + (" + NCCL all-gather of descriptor records" if world > 1 else ""),
-                   "pairs_per_step_per_gpu": P, "frames_per_step": 2 * P * world, "keypoints_per_step": int(nkp.item()),
-                   "frames_per_s": 2 * P * world / (ms_step * 1e-3),
+                               + (" + all-gather of descriptor records" if world > 1 else ""),
+                   "pairs_per_step_per_gpu": P, "gather": gather_mode, "frames_per_step": 2 * P * world, "keypoints_per_step": int(nkp.item()),
+                   "frames_per_s": 2 * P * world / (ms_step * 1e-3), "single_pair_latency_ms_host_api": lat_ms,
                    "l2_policy": "inputs larger than L2: %.0f MB of images + %.0f MB of pyramid per step vs 126 MB L2"
                                 % (2 * P * W * H / 1e6, 2 * P * (PYR_PX - W * H) / 1e6)},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -118,6 +118,22 @@ adb_status adb_orb_profile(adb_orb_t h, int32_t enable);
 adb_status adb_orb_stage_ms(adb_orb_t h, float* ms4);
 int64_t adb_orb_launch_count(adb_orb_t h);
 
+/* Multi-GPU fusion of the descriptor all-gather (BASELINE configs[2]) into the extraction: besides its own result
+ * buffers the handle scatters every record it produces straight into up to ADB_MAX_GATHER peer buffers -- device
+ * pointers mapped over NVLink (CUDA IPC / symmetric memory), each laid out like the handle's own results
+ * ([max_batch][capacity] key-points, [max_batch][capacity][32] descriptors, [max_batch] counts) and already offset to
+ * this rank's slot.  The stores are issued by the descriptor kernel's epilogue, so the transfer overlaps the compute
+ * tile by tile and no separate collective runs.  t == NULL or t->n == 0 switches it off.  The caller synchronises the
+ * ranks (barrier) before reading the gathered buffers. */
+#define ADB_MAX_GATHER 8
+typedef struct adb_gather_targets {
+    int32_t n;
+    adb_keypoint* kps[ADB_MAX_GATHER];
+    uint8_t* desc[ADB_MAX_GATHER];
+    int32_t* counts[ADB_MAX_GATHER];
+} adb_gather_targets;
+adb_status adb_orb_set_gather(adb_orb_t h, const adb_gather_targets* t);
+
 /* Device pointers to the resident results of the last extract call:
  * kps [max_batch][capacity], desc [max_batch][capacity][32], counts [max_batch]. */
 adb_status adb_orb_results_device(adb_orb_t h, const adb_keypoint** d_kps, const uint8_t** d_desc,

@@ -140,3 +140,30 @@ def test_full_size_batch_properties(adb, oracle_mod):
     for f in (0, 5):
         assert _same(kps[f, :cnt[f]], desc[f, :cnt[f]], oracle_mod.orb_extract(imgs[f], None, 2000, 1.2, 8, 12, 7))
     ex.close()
+
+
+def test_fused_gather_targets(adb, oracle_mod):
+    """adb_orb_set_gather: the descriptor kernel also stores every record into the given target buffers (on one GPU
+    the 'peers' are two local buffers; over NVLink they are peer-mapped symmetric memory, exercised by bench.py --gpus 2)."""
+    import torch
+    from airdos_b200 import synth
+    F = 3
+    imgs = np.stack([synth.make_stereo_pair(50 + f)[0] for f in range(F)])
+    ex = adb.ORBextractor(1000, 1.2, 8, 12, 7, 640, 480, max_batch=F)
+    cap = ex.capacity
+    tk = [torch.zeros(F, cap, 24, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    td = [torch.zeros(F, cap, 32, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    tc = [torch.zeros(F, dtype=torch.int32, device="cuda") for _ in range(2)]
+    ex.set_gather([t.data_ptr() for t in tk], [t.data_ptr() for t in td], [t.data_ptr() for t in tc])
+    kps, desc, cnt = ex.extract_batch(imgs)
+    for g in range(2):
+        assert (tc[g].cpu().numpy() == cnt).all()
+        for f in range(F):
+            n = cnt[f]
+            assert tk[g][f, :n].cpu().numpy().tobytes() == kps[f, :n].tobytes()
+            assert (td[g][f, :n].cpu().numpy() == desc[f, :n]).all()
+    ex.set_gather()                      # off again
+    tk[0].zero_()
+    ex.extract_batch(imgs)
+    assert int(tk[0].sum()) == 0
+    ex.close()
