@@ -68,6 +68,7 @@ SYMBOLS = {
     "adb_matcher_destroy": (C.c_int, [_vp]),
     "adb_match_best2": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "adb_match_best2_device": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "adb_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "adb_stereo_match": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
     "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),
     "adb_stereo_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),

@@ -20,8 +20,9 @@
 // State is double buffered (current / trial): accepting an LM step swaps two pointers, rejecting
 // it costs nothing (g2o's push / pop copies every vertex).  The LM decision itself is taken on
 // the host from one 48-byte read-back per trial.
-// Accumulation uses FP64 atomics in L2 (RED.ADD.F64): sums are order-dependent at the 1e-16
-// level, far below the 1e-4 parity bar.
+// The landmark and pose blocks are accumulated without atomics (fixed order); the Schur chunks, the chi2 sums and the few
+// dense-block edges use FP64 atomics in L2 (RED.ADD.F64): those sums are order-dependent at the 1e-16 level, far below
+// the 1e-4 parity bar.
 #include <algorithm>
 #include <cfloat>
 #include <chrono>

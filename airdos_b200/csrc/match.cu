@@ -305,6 +305,52 @@ __global__ void __launch_bounds__(256) stereo_median_kernel(const int32_t* __res
     }
 }
 
+
+// -----------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors, one CTA (4 warps) per map point: N x N Hamming matrix in shared memory,
+// per-row median by a counting binary search over the 257 possible distances, arg-min over (median, row).
+constexpr int kDistinctThreads = 128;
+__global__ void __launch_bounds__(kDistinctThreads) distinctive_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ point_ptr,
+                                                                      int32_t* __restrict__ best_idx, uint8_t* __restrict__ best_desc) {
+    extern __shared__ uint16_t dmat[];   // [N][N]
+    __shared__ int s_best;               // median << 8 | row, reduced with atomicMin
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int a = point_ptr[p], N = point_ptr[p + 1] - a;
+    if (N <= 0) { if (tid == 0) best_idx[p] = -1; return; }
+    if (tid == 0) s_best = INT_MAX;
+    for (int e = tid; e < N * N; e += kDistinctThreads) {
+        const int i = e / N, j = e - i * N;
+        if (j < i) continue;
+        int d = 0;
+        if (j > i) {
+            uint32_t q[8];
+            const uint4* qp = reinterpret_cast<const uint4*>(desc + (size_t)(a + i) * 32);
+            const uint4 x = __ldg(qp), y = __ldg(qp + 1);
+            q[0] = x.x; q[1] = x.y; q[2] = x.z; q[3] = x.w; q[4] = y.x; q[5] = y.y; q[6] = y.z; q[7] = y.w;
+            d = hamming8(q, reinterpret_cast<const uint4*>(desc + (size_t)(a + j) * 32));
+        }
+        dmat[i * N + j] = (uint16_t)d;
+        dmat[j * N + i] = (uint16_t)d;
+    }
+    __syncthreads();
+    const int k = (int)(0.5 * (N - 1));   // index of the median in the sorted row
+    for (int i = tid; i < N; i += kDistinctThreads) {
+        const uint16_t* row = dmat + i * N;
+        int lo = 0, hi = 256;             // smallest v with #{d <= v} >= k + 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j = 0; j < N; ++j) c += row[j] <= mid;
+            if (c >= k + 1) hi = mid; else lo = mid + 1;
+        }
+        atomicMin(&s_best, (lo << 8) | i);   // N <= 128 < 256: the row index breaks ties towards the first row
+    }
+    __syncthreads();
+    const int b = s_best & 0xFF;
+    if (tid == 0) best_idx[p] = b;
+    if (best_desc && tid < 32) best_desc[(size_t)p * 32 + tid] = desc[(size_t)(a + b) * 32 + tid];
+}
+
 }  // namespace adb
 
 using namespace adb;
@@ -397,6 +443,41 @@ adb_status adb_match_best2(adb_matcher_t m, const uint8_t* q, int32_t nq, const 
     s = body();
     cudaFree(dq); cudaFree(dt); cudaFree(doff); cudaFree(didx); cudaFree(dout);
     return s;
+}
+
+
+adb_status adb_distinctive_descriptors(adb_matcher_t m, const uint8_t* desc, const int32_t* point_ptr, int32_t n_points, int32_t* best_idx,
+                                       uint8_t* best_desc) {
+    ADB_CHECK(m && point_ptr && best_idx, ADB_ERR_INVALID, "null argument");
+    if (n_points <= 0) return ADB_OK;
+    const int n = point_ptr[n_points];
+    int maxN = 0;
+    for (int p = 0; p < n_points; ++p) {
+        ADB_CHECK(point_ptr[p + 1] >= point_ptr[p], ADB_ERR_INVALID, "point_ptr is not monotone at %d", p);
+        maxN = std::max(maxN, point_ptr[p + 1] - point_ptr[p]);
+    }
+    ADB_CHECK(maxN <= ADB_MAX_OBSERVATIONS, ADB_ERR_CAPACITY, "a map point has %d observations (max %d)", maxN, ADB_MAX_OBSERVATIONS);
+    ADB_CHECK(n == 0 || desc, ADB_ERR_INVALID, "null descriptors");
+    ADB_CUDA(cudaSetDevice(m->device));
+    uint8_t *dd = nullptr, *dbd = nullptr;
+    int32_t *dp = nullptr, *dbi = nullptr;
+    auto body = [&]() -> adb_status {
+        ADB_CUDA(cudaMalloc(&dd, std::max<size_t>((size_t)n * 32, 32)));
+        ADB_CUDA(cudaMalloc(&dp, (size_t)(n_points + 1) * 4));
+        ADB_CUDA(cudaMalloc(&dbi, (size_t)n_points * 4));
+        if (best_desc) ADB_CUDA(cudaMalloc(&dbd, (size_t)n_points * 32));
+        if (n > 0) ADB_CUDA(cudaMemcpyAsync(dd, desc, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+        ADB_CUDA(cudaMemcpyAsync(dp, point_ptr, (size_t)(n_points + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+        distinctive_kernel<<<n_points, kDistinctThreads, (size_t)std::max(maxN * maxN, 1) * 2, m->stream>>>(dd, dp, dbi, dbd);
+        ADB_CUDA(cudaGetLastError());
+        ADB_CUDA(cudaMemcpyAsync(best_idx, dbi, (size_t)n_points * 4, cudaMemcpyDeviceToHost, m->stream));
+        if (best_desc) ADB_CUDA(cudaMemcpyAsync(best_desc, dbd, (size_t)n_points * 32, cudaMemcpyDeviceToHost, m->stream));
+        ADB_CUDA(cudaStreamSynchronize(m->stream));
+        return ADB_OK;
+    };
+    const adb_status st = body();
+    cudaFree(dd); cudaFree(dp); cudaFree(dbi); cudaFree(dbd);
+    return st;
 }
 
 adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb, float mbf) {

@@ -217,6 +217,17 @@ class ORBmatcher:
         return bi, bd, sd
 
 
+def compute_distinctive_descriptors(matcher: ORBmatcher, desc: np.ndarray, point_ptr: np.ndarray):
+    """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (CSR over observation descriptors) ->
+    (best_idx [P], best_desc [P, 32])."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    point_ptr = np.ascontiguousarray(point_ptr, np.int32)
+    npts = len(point_ptr) - 1
+    bi = np.zeros(npts, np.int32); bd = np.zeros((npts, 32), np.uint8)
+    check(lib().adb_distinctive_descriptors(matcher._m, ptr(desc), ptr(point_ptr), npts, ptr(bi), ptr(bd)))
+    return bi, bd
+
+
 def compute_stereo_matches(left: ORBextractor, right: ORBextractor, n_frames: int, mb: float, mbf: float,
                            out: HostStereo | None = None):
     """Frame::ComputeStereoMatches for the frames resident in two extractor handles ->

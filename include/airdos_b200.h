@@ -175,6 +175,15 @@ adb_status adb_match_best2_device(adb_matcher_t m, const uint8_t* q_desc, int32_
                                   const int32_t* cand_off, const int32_t* cand_idx,
                                   int32_t* best_idx, int32_t* best_d, int32_t* second_d, void* stream);
 
+/* MapPoint::ComputeDistinctiveDescriptors()  (src/MapPoint.cc:245-310), batched over map points: `desc` holds the
+ * descriptors of all observations, point p owning rows point_ptr[p] .. point_ptr[p+1]).  Per point the observation whose
+ * sorted Hamming distances to all observations of the point (itself included) have the least median (element
+ * 0.5 * (N - 1)) wins, the first one on ties.  best_idx[p] = index within the point's rows (-1: no observations);
+ * best_desc (optional) receives the winning 32 bytes.  At most ADB_MAX_OBSERVATIONS rows per point.  Host buffers. */
+#define ADB_MAX_OBSERVATIONS 128
+adb_status adb_distinctive_descriptors(adb_matcher_t m, const uint8_t* desc, const int32_t* point_ptr, int32_t n_points,
+                                       int32_t* best_idx, uint8_t* best_desc);
+
 /* Frame::ComputeStereoMatches()  (src/Frame.cc:829-1003) for the n_frames frames resident in
  * the two extractor handles (frame i of `left` against frame i of `right`): row-band Hamming
  * match, 11x11 SAD sub-pixel refinement on the pyramids, median-distance cut.

@@ -202,6 +202,17 @@ def best2(q: np.ndarray, t: np.ndarray, cand_off: np.ndarray | None = None, cand
     return bi, bd, sd
 
 
+def distinctive(desc: np.ndarray, point_ptr: np.ndarray) -> np.ndarray:
+    """MapPoint::ComputeDistinctiveDescriptors restatement -> best index per point."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    point_ptr = np.ascontiguousarray(point_ptr, np.int32)
+    out = np.zeros(len(point_ptr) - 1, np.int32)
+    lib = _match_lib()
+    lib.match_oracle_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.match_oracle_distinctive(_p(desc), _p(point_ptr), len(out), _p(out))
+    return out
+
+
 def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, scale, mb: float, mbf: float, stage: int = 0):
     """Frame::ComputeStereoMatches restatement.  pyr_l / pyr_r: lists of level ROIs (u8 2-D).
     Returns (uRight, depth, ham_idx, ham_dist)."""

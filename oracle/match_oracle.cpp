@@ -165,3 +165,28 @@ void match_oracle_stereo(const void* kl_, const uint8_t* dl, int nl, const void*
 }
 
 }  // extern "C"
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:245-310), batched: descriptors of all observations in CSR
+// form (point_ptr); per point the row of the N x N Hamming matrix with the least median (sorted[0.5 * (N - 1)], self
+// distance 0 included) wins, first row on ties.  best_idx = -1 for a point without observations.
+extern "C" void match_oracle_distinctive(const uint8_t* desc, const int32_t* point_ptr, int n_points, int32_t* best_idx) {
+    std::vector<int> d, row;
+    for (int p = 0; p < n_points; ++p) {
+        const int a = point_ptr[p], N = point_ptr[p + 1] - a;
+        if (N <= 0) { best_idx[p] = -1; continue; }
+        d.assign((size_t)N * N, 0);
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                const int v = hamming256(desc + (size_t)(a + i) * 32, desc + (size_t)(a + j) * 32);
+                d[(size_t)i * N + j] = v; d[(size_t)j * N + i] = v;
+            }
+        int bestMedian = INT_MAX, bestIdx = 0;
+        for (int i = 0; i < N; ++i) {
+            row.assign(d.begin() + (size_t)i * N, d.begin() + (size_t)(i + 1) * N);
+            std::sort(row.begin(), row.end());
+            const int median = row[(size_t)(0.5 * (N - 1))];
+            if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+        }
+        best_idx[p] = bestIdx;
+    }
+}

@@ -70,3 +70,21 @@ def test_stereo_no_matches_is_a_noop(adb):
     ur, dp, bi, bd = adb.compute_stereo_matches(exL, exR, 1, 0.25, 193.137)
     assert (ur == -1).all() and (dp == -1).all() and (bi == -1).all()
     exL.close(); exR.close()
+
+
+def test_distinctive_descriptors_match_oracle(adb, oracle_mod):
+    """MapPoint::ComputeDistinctiveDescriptors batched: identical winner index and descriptor."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle_match import _distinct_case
+    m = adb.ORBmatcher()
+    for seed in (2, 3):
+        desc, ptr = _distinct_case(np.random.default_rng(seed), 500)
+        bi, bd = adb.compute_distinctive_descriptors(m, desc, ptr)
+        ref = oracle_mod.distinctive(desc, ptr)
+        assert (bi == ref).all()
+        ok = ref >= 0
+        assert (bd[ok] == desc[ptr[:-1][ok] + ref[ok]]).all()
+    with pytest.raises(adb.AdbError):                       # more observations than ADB_MAX_OBSERVATIONS: refused, never truncated
+        adb.compute_distinctive_descriptors(m, np.zeros((129, 32), np.uint8), np.array([0, 129], np.int32))
+    m.close()

@@ -55,3 +55,28 @@ def test_stereo_oracle_on_synthetic_pair(oracle_mod):
     assert (hd[m] < 75).all() and (hi[m] >= 0).all()
     # the true disparity of the generator is bf / Z with Z in [3, 40]: matches must sit in that range mostly
     assert np.median(disp) > synth.BF / 40 * 0.8
+
+
+def _distinct_case(rng, n_points=200):
+    lens = rng.integers(0, 40, n_points); lens[:4] = [0, 1, 2, 128]
+    ptr = np.zeros(n_points + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    base = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+    desc = np.repeat(base, lens, axis=0)
+    flip = rng.random(desc.shape) < 0.04                      # observations = noisy copies of the point's descriptor
+    desc = desc ^ (flip * rng.integers(1, 256, desc.shape)).astype(np.uint8)
+    desc[ptr[5]:ptr[6]] = desc[ptr[5]]                        # all identical: every median is 0, the first row wins
+    return desc, ptr
+
+
+def test_distinctive_descriptor_rule(oracle_mod):
+    rng = np.random.default_rng(2)
+    desc, ptr = _distinct_case(rng)
+    got = oracle_mod.distinctive(desc, ptr)
+    for p in range(len(ptr) - 1):
+        d = desc[ptr[p]:ptr[p + 1]]
+        if len(d) == 0:
+            assert got[p] == -1
+            continue
+        m = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
+        med = np.sort(m, 1)[:, int(0.5 * (len(d) - 1))]
+        assert got[p] == int(np.argmin(med))                  # least median, first on ties
