@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
 // Tie-break of the reference's (count, pointer) sort = creation sequence.
 constexpr int kQtThreads = 512;
 constexpr uint32_t kQtFinal = 0xFFFu;
+constexpr int kQtSeqWords = 1024;           // node creation sequence numbers are limited to 32768 per (frame, level)
 
 struct QtShared {
     int na, nf, size, next_seq, mode, first, cur, done, kstar, tot_ch, tot_ex, ncand;
@@ -318,6 +319,8 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
     uint8_t* r_nch = reinterpret_cast<uint8_t*>(r_slot + maxa);        // [maxa] nonempty children, by rank
     uint8_t* r_nex = r_nch + maxa;                                     // [maxa] children with > 1 key, by rank
     __shared__ QtShared S;
+    __shared__ uint32_t bm[kQtSeqWords];     // surviving node keys (final ordering)
+    __shared__ uint16_t suf[kQtSeqWords];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int level = blockIdx.x, f = blockIdx.y;
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
             S.first = 0;
             if (new_size >= N || new_size == size) S.done = 1;
             else if (mode == 0 && new_size + n_exp * 3 > N) S.mode = 1;
-            if (S.nf + n_exp > maxa || S.next_seq >= (1 << 20)) { atomicExch(status, 3); S.done = 1; S.na = 0; }
+            if (S.nf + n_exp > maxa || S.next_seq >= 32 * kQtSeqWords) { atomicExch(status, 3); S.done = 1; S.na = 0; }
         }
         __syncthreads();
     }
@@ -552,30 +555,36 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
         const int nf = S.nf + na;
         for (int s = tid; s < na; s += kQtThreads) fseq[nf - na + s] = nseq(cur)[s];
         __syncthreads();
-        // ---- order = list order: creation sequence descending, roots (ascending) at the tail
+        // ---- order = list order: creation sequence descending, roots (ascending) at the tail.  Rank of a node =
+        // number of surviving nodes with a larger key: a bitmap over the key space + suffix popcounts make it O(1) per
+        // node and per candidate (no sort, no search).
+        for (int w = tid; w < kQtSeqWords; w += kQtThreads) bm[w] = 0;
+        for (int r = tid; r < nf; r += kQtThreads) best[r] = 0;
+        __syncthreads();
         for (int i = tid; i < nf; i += kQtThreads) {
             const uint32_t qi = fseq[i];
             const uint32_t ki = qi >= (uint32_t)nIni ? qi : (uint32_t)(nIni - 1) - qi;
-            int r = 0;
-            for (int j = 0; j < nf; ++j) {
-                const uint32_t qj = fseq[j];
-                const uint32_t kj = qj >= (uint32_t)nIni ? qj : (uint32_t)(nIni - 1) - qj;
-                r += kj > ki;
+            atomicOr(&bm[ki >> 5], 1u << (ki & 31));
+        }
+        __syncthreads();
+        if (warp == 0) {   // suf[w] = set bits in words above w
+            int run = 0;
+            for (int w0 = kQtSeqWords - 32; w0 >= 0; w0 -= 32) {
+                const int w = w0 + (31 - lane);              // lane 0 takes the highest word of the chunk
+                const int v = __popc(bm[w]);
+                const int inc = warp_incl_scan(v, lane);
+                suf[w] = (uint16_t)(run + inc - v);
+                run += __shfl_sync(0xFFFFFFFFu, inc, 31);
             }
-            fsorted[r] = ki;
-            best[r] = 0;
         }
         __syncthreads();
         // max response per node, first key in candidate order wins ties (src/ORBextractor.cc:745-762)
         for (int k = tid; k < ncand; k += kQtThreads) {
             const uint32_t q = state[k] & 0xFFFFFu;
             const uint32_t kq = q >= (uint32_t)nIni ? q : (uint32_t)(nIni - 1) - q;
-            int lo = 0, hi = nf - 1;   // fsorted is descending
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (fsorted[mid] > kq) lo = mid + 1; else hi = mid;
-            }
-            atomicMax(&best[lo], ((keys[k] >> 24) << 24) | (0xFFFFFFu - (uint32_t)k));
+            const uint32_t word = bm[kq >> 5], bit = kq & 31;
+            const int r = suf[kq >> 5] + (bit == 31 ? 0 : __popc(word >> (bit + 1)));
+            atomicMax(&best[r], ((keys[k] >> 24) << 24) | (0xFFFFFFu - (uint32_t)k));
         }
         __syncthreads();
         const int nout = min(nf, L.list_cap);
