@@ -119,7 +119,8 @@ def run_reference(args):
         "impl": "reference", "metric": "orb_keypoints_per_s", "value": v, "unit": "keypoints/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "640x480 stereo stream, 8 levels, 2000 feat/frame, ORB extract L+R + stereo match (CPU path)",
+        "config": {"workload": "640x480 stereo stream, 8-level pyramid, 2000 feat/frame, ORB extract L+R + stereo match",
+                   "arm": "reference CPU path (oracle port of the reference algorithm, all host threads)",
                    "pairs_per_step": n_pairs},
         "cpu_baseline": {"value": v, "unit": "keypoints/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -133,21 +133,27 @@ void resize_linear_u8(const uint8_t* src, int sw, int sh, int spitch, uint8_t* d
 // separable kernel {18,34,48,56,48,34,18}/256, result (v + 2^15) >> 16.  src/ORBextractor.cc:1100
 const int kBlurK[7] = {18, 34, 48, 56, 48, 34, 18};
 void blur7_u8(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch) {
-    std::vector<uint16_t> rows((size_t)w * h);
-    for (int y = 0; y < h; ++y) {
-        const uint8_t* s = src + (size_t)y * spitch;
+    // row pass into a buffer with 3 reflected rows above and below, so the column pass needs no index mapping
+    std::vector<uint16_t> rows((size_t)w * (h + 6));
+    std::vector<uint8_t> line((size_t)w + 6);
+    for (int y = -3; y < h + 3; ++y) {
+        const uint8_t* s = src + (size_t)reflect101(y, h) * spitch;
+        for (int x = -3; x < w + 3; ++x) line[x + 3] = s[reflect101(x, w)];
+        uint16_t* r = &rows[(size_t)(y + 3) * w];
         for (int x = 0; x < w; ++x) {
-            int acc = 0;
-            for (int k = -3; k <= 3; ++k) acc += kBlurK[k + 3] * s[reflect101(x + k, w)];
-            rows[(size_t)y * w + x] = (uint16_t)acc;
+            const uint8_t* p = &line[x];
+            r[x] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
         }
     }
-    for (int y = 0; y < h; ++y)
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* r = &rows[(size_t)y * w];
+        uint8_t* d = dst + (size_t)y * dpitch;
         for (int x = 0; x < w; ++x) {
-            uint32_t acc = 0;
-            for (int k = -3; k <= 3; ++k) acc += (uint32_t)kBlurK[k + 3] * rows[(size_t)reflect101(y + k, h) * w + x];
-            dst[(size_t)y * dpitch + x] = (uint8_t)((acc + 32768u) >> 16);
+            const uint32_t acc = 18u * (r[x] + r[x + 6 * (size_t)w]) + 34u * (r[x + w] + r[x + 5 * (size_t)w]) +
+                                 48u * (r[x + 2 * (size_t)w] + r[x + 4 * (size_t)w]) + 56u * r[x + 3 * (size_t)w];
+            d[x] = (uint8_t)((acc + 32768u) >> 16);
         }
+    }
 }
 
 // cv::fastAtan2 (degrees): degree-7 odd polynomial, every operation rounded to float32.
@@ -186,14 +192,17 @@ const int kCircleDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3
 
 // best = max over the 16 arcs of 9 contiguous circle pixels of max(min(d), min(-d)), d = centre - circle.
 inline int fast_best(const uint8_t* p, const int* off) {
-    int d[25];
+    int d[16];
     const int v = p[0];
     for (int i = 0; i < 16; ++i) d[i] = v - p[off[i]];
-    for (int i = 16; i < 25; ++i) d[i] = d[i - 16];
+    // window minima / maxima of length 9 by doubling (2, 4, 8, +1): same value as scanning all 16 arcs
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+    for (int i = 0; i < 16; ++i) { lo2[i] = std::min(d[i], d[(i + 1) & 15]); hi2[i] = std::max(d[i], d[(i + 1) & 15]); }
+    for (int i = 0; i < 16; ++i) { lo4[i] = std::min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = std::max(hi2[i], hi2[(i + 2) & 15]); }
     int best = -256;
-    for (int s = 0; s < 16; ++s) {
-        int lo = d[s], hi = d[s];
-        for (int k = 1; k < 9; ++k) { lo = std::min(lo, d[s + k]); hi = std::max(hi, d[s + k]); }
+    for (int i = 0; i < 16; ++i) {
+        const int lo = std::min(std::min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
+        const int hi = std::max(std::max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
         best = std::max(best, std::max(lo, -hi));
     }
     return best;
