@@ -63,7 +63,7 @@ def run(device: int = 0, steps: int = 5, with_cpu: bool = True, n_kf: int = 50, 
                        "unit": "GB/s", "frac": alg / (sparse_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src,
                        "reduced_solve": {"n": 6 * (n_kf - 1), "ms_per_trial": stages["reduced_solve"] / trials,
                                          "gflops": (6 * (n_kf - 1)) ** 3 / 3 / (stages["reduced_solve"] / trials * 1e-3) / 1e9,
-                                         "note": "cuSOLVER FP64 potrf + potrs (bring-up baseline)"}}
+                                         "note": "own left-looking FP64 Cholesky (chol_left_kernel x ceil(n/32) + chol_back_kernel); latency bound: n sequential pivots"}}
     # parity on the reference's own 5 + 10 schedule, and the CPU baseline (oracle port, 1 thread like g2o without OpenMP)
     if with_cpu:
         import oracle
