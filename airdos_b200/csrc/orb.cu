@@ -62,6 +62,74 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const uint8_t* __restri
     *reinterpret_cast<uint32_t*>(dst + (size_t)f * dfstride + (size_t)y * dpitch + x4) = out;
 }
 
+// The same resize as a strip walk (the hot variant; pyr_resize_kernel above stays as the fallback for scale factors
+// above 2).  A thread owns 4 adjacent output columns and walks `rows` output rows downwards.  Per source row it loads
+// three aligned words, funnel-shifts them into an 8-byte window that starts at its first source pixel, and picks each
+// output's two neighbours with one PRMT (selectors are loop invariant); the horizontally interpolated row is kept in
+// registers and reused by the next output row (consecutive output rows share a source row), so a source row is
+// interpolated ~1.2 times per output row instead of 2 and no byte-wide loads are issued.
+__global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                               size_t sfstride, uint8_t* __restrict__ dst, int dw, int dh,
+                                                               int dpitch, size_t dfstride, const int2* __restrict__ xtab,
+                                                               const int2* __restrict__ ytab, int nq, int rows, int nchunks) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= nq * nchunks) return;
+    const int chunk = t / nq, q = t - chunk * nq, f = blockIdx.y;
+    uint32_t sel[4], a0[4], a1[4];
+    const int base = __ldg(&xtab[4 * q]).x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int2 cx = __ldg(&xtab[min(4 * q + k, dw - 1)]);
+        const int o0 = cx.x - base, o1 = min(cx.x + 1, sw - 1) - base;   // <= 7 (checked on the host)
+        sel[k] = (uint32_t)(o0 | (o1 << 4));
+        a0[k] = (uint32_t)cx.y & 0xFFFFu; a1[k] = (uint32_t)cx.y >> 16;
+    }
+    const int maxw = (spitch >> 2) - 1;
+    const int w0i = base >> 2, w1i = min(w0i + 1, maxw), w2i = min(w0i + 2, maxw);
+    const uint32_t sft = (uint32_t)(base & 3) * 8u;
+    const uint8_t* sf = src + (size_t)f * sfstride;
+    auto hrow = [&](int sy, uint32_t (&H)[4]) {   // (S[sx0] * a0 + S[sx1] * a1) >> 4 for the 4 columns
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(sf + (size_t)sy * spitch);
+        const uint32_t w0 = __ldg(sp + w0i), w1 = __ldg(sp + w1i), w2 = __ldg(sp + w2i);
+        const uint32_t W0 = __funnelshift_r(w0, w1, sft), W1 = __funnelshift_r(w1, w2, sft);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t T = __byte_perm(W0, W1, sel[k]);
+            H[k] = ((T & 0xFFu) * a0[k] + ((T >> 8) & 0xFFu) * a1[k]) >> 4;
+        }
+    };
+    uint32_t A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0};
+    int ia = -1, ib = -1;
+    const int y_end = min(dh, (chunk + 1) * rows);
+    uint8_t* dp = dst + (size_t)f * dfstride + 4 * q;
+    for (int y = chunk * rows; y < y_end; ++y) {
+        const int2 cy = __ldg(&ytab[y]);
+        const int sy0 = cy.x, sy1 = min(sy0 + 1, sh - 1);
+        const uint32_t b0 = (uint32_t)cy.y & 0xFFFFu, b1 = (uint32_t)cy.y >> 16;
+        if (sy0 != ia) {
+            if (sy0 == ib) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) A[k] = B[k];
+            } else hrow(sy0, A);
+            ia = sy0;
+        }
+        if (sy1 != ib) {
+            if (sy1 == ia) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) B[k] = A[k];
+            } else hrow(sy1, B);
+            ib = sy1;
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (((b0 * A[k]) >> 16) + ((b1 * B[k]) >> 16) + 2u) >> 2;
+            out |= (v & 0xFFu) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dp + (size_t)y * dpitch) = out;
+    }
+}
+
 // cv::erode(mask, ones(10,10)), anchor (5,5), outside = 255.  oracle/orb_oracle.cpp:70-92.  Parity-only path.
 __global__ void erode10_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, size_t sfstride,
                                uint8_t* __restrict__ dst, int dpitch, size_t dfstride) {
@@ -90,61 +158,77 @@ struct MaskPtrs {
     const uint8_t* p[kMaxLevels];
 };
 
-__device__ __forceinline__ bool has_run9(uint32_t m16) {
-    uint32_t x = m16 | (m16 << 16);
-    x &= x >> 1;
-    x &= x >> 2;
-    x &= x >> 4;   // bit i: bits i..i+7 set
-    x &= x >> 1;   // bits i..i+8 set
-    return (x & 0xFFFFu) != 0;
+// The 16 ring pixels q_i of centre v as two 16-bit lanes per word, made by one IMAD each (fma pipe; everything
+// after it is one alu-pipe op per three words): x_i = a + q_i * 0xFFFF = (a.lo - q_i) | (a.hi + q_i) << 16.  The
+// lanes stay inside (0, 0x10000) for the two choices of `a` below, so nothing carries across.
+// OpenCV circle order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+__device__ __forceinline__ void load_ring_packed(const uint8_t* c, int bw, uint32_t a, uint32_t (&x)[16]) {
+#define ADB_Q(off) ((uint32_t)c[off] * 0xFFFFu + a)
+    x[0] = ADB_Q(3 * bw);      x[1] = ADB_Q(3 * bw + 1);  x[2] = ADB_Q(2 * bw + 2);   x[3] = ADB_Q(bw + 3);
+    x[4] = ADB_Q(3);           x[5] = ADB_Q(-bw + 3);     x[6] = ADB_Q(-2 * bw + 2);  x[7] = ADB_Q(-3 * bw + 1);
+    x[8] = ADB_Q(-3 * bw);     x[9] = ADB_Q(-3 * bw - 1); x[10] = ADB_Q(-2 * bw - 2); x[11] = ADB_Q(-bw - 3);
+    x[12] = ADB_Q(-3);         x[13] = ADB_Q(bw - 3);     x[14] = ADB_Q(2 * bw - 2);  x[15] = ADB_Q(3 * bw - 1);
+#undef ADB_Q
 }
 
-// max over the 16 circular windows of 9 of min(d) and of min(-d)
-__device__ __forceinline__ int fast_best(const int (&d)[16]) {
-    int lo2[16], hi2[16];
+// Corner test at threshold t for both polarities at once.  a = (0x8000 + v - t - 1) | (0x8000 - v - t - 1) << 16 puts
+// "v - q > t" into bit 15 and "q - v > t" into bit 31 of x_i; a run of 9 set flags = AND over 9 consecutive words,
+// built from 3-input ANDs (40 LOP3 for all 16 arcs).
+__device__ __forceinline__ uint32_t fast_corner_a(int v, int t) {
+    return (uint32_t)(0x8000 + v - t - 1) | ((uint32_t)(0x8000 - v - t - 1) << 16);
+}
+__device__ __forceinline__ bool fast_is_corner(const uint32_t (&x)[16]) {
+    uint32_t a3[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { lo2[i] = min(d[i], d[(i + 1) & 15]); hi2[i] = max(d[i], d[(i + 1) & 15]); }
-    int lo4[16], hi4[16];
+    for (int i = 0; i < 16; ++i) a3[i] = x[i] & x[(i + 1) & 15] & x[(i + 2) & 15];
+    uint32_t any = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { lo4[i] = min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = max(hi2[i], hi2[(i + 2) & 15]); }
-    int bestLo = -256, minHi = 256;
+    for (int i = 0; i < 16; i += 2)
+        any |= (a3[i] & a3[(i + 3) & 15] & a3[(i + 6) & 15]) | (a3[i + 1] & a3[(i + 4) & 15] & a3[(i + 7) & 15]);
+    return (any & 0x80008000u) != 0;
+}
+
+// Exact score: max over the 16 arcs of 9 of min(v - q) and of min(q - v) (cv::cornerScore<16>), again both
+// polarities at once: a = (256 + v) | (256 - v) << 16 makes the lanes 256 + d and 256 - d, and the arc minima / the
+// final maximum are packed 3-input min / max (VIMNMX3.U16x2): 40 of them per pixel.
+__device__ __forceinline__ uint32_t fast_score_a(int v) { return (uint32_t)(256 + v) | ((uint32_t)(256 - v) << 16); }
+__device__ __forceinline__ int fast_best(const uint32_t (&x)[16]) {
+    uint32_t m3[16], m9[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        bestLo = max(bestLo, min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]));
-        minHi = min(minHi, max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]));
-    }
-    // max(bestLo, -minHi), written as a select: ptxas 12.9 drops the negation when it folds
-    // max(a, -b) into a 3-input VIMNMX3 on sm_100a (measured, tools/probe/fast_probe2.cu).
-    const int best = (bestLo + minHi > 0) ? bestLo : (0 - minHi);
-    return best;
+    for (int i = 0; i < 16; ++i) m3[i] = __vimin3_u16x2(x[i], x[(i + 1) & 15], x[(i + 2) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m9[i] = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
+    uint32_t r0 = __vimax3_u16x2(m9[0], m9[1], m9[2]), r1 = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+    uint32_t r2 = __vimax3_u16x2(m9[6], m9[7], m9[8]), r3 = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+    uint32_t r4 = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+    r0 = __vimax3_u16x2(r0, r1, r2);
+    r3 = __vimax3_u16x2(r3, r4, m9[15]);
+    r0 = __vmaxu2(r0, r3);
+    return (int)max(r0 & 0xFFFFu, r0 >> 16) - 256;
 }
 
 constexpr int kFastThreads = 256;
 constexpr int kMaxKeep = 1152;      // >= ceil(75 / 2) * ceil(60 / 2): strict 3x3 NMS keeps at most one pixel per 2x2 block
 constexpr int kMaxCorners = 4608;   // >= inner pixels of the largest supported cell (75 x 60)
 
-__device__ __forceinline__ void load_circle_diffs(const uint8_t* c, int bw, int v, int (&d)[16]) {
-    // OpenCV circle order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-    d[0] = v - c[3 * bw];      d[1] = v - c[3 * bw + 1];  d[2] = v - c[2 * bw + 2];   d[3] = v - c[bw + 3];
-    d[4] = v - c[3];           d[5] = v - c[-bw + 3];     d[6] = v - c[-2 * bw + 2];  d[7] = v - c[-3 * bw + 1];
-    d[8] = v - c[-3 * bw];     d[9] = v - c[-3 * bw - 1]; d[10] = v - c[-2 * bw - 2]; d[11] = v - c[-bw - 3];
-    d[12] = v - c[-3];         d[13] = v - c[bw - 3];     d[14] = v - c[2 * bw - 2];  d[15] = v - c[3 * bw - 1];
-}
-
-// Four phases per (cell, frame) CTA, each a dense loop (no divergent heavy branch):
-//   1 corner test at min(iniTh, minTh) for every pixel of the cell -> unordered corner list in smem
-//   2 exact FAST score for the listed corners only
-//   3 strict 3x3 NMS + mask post-filter for the listed corners -> unordered kept list
+// Phases per (cell, frame) CTA, each a dense loop (no divergent heavy branch):
+//   1 exact FAST score of every pixel of the cell (packed, branch free); a corner at min(iniTh, minTh) keeps
+//     score - 1 in the score tile, everything else 0
+//     [kDirect == false, measurement variant: packed corner test -> corner list -> exact score of the listed corners]
+//   3 strict 3x3 NMS + mask post-filter of the corners -> unordered kept list
 //   4 ini / min rule, then each kept corner's rank in row-major order places it in the cell's slot
+// kBW = pitch of the TMA box in shared memory (one value per handle), a compile-time constant so that the 16 ring
+// loads are immediate offsets from one address register.
+template <bool kDirect, int kBW>
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                  const LevelDev* __restrict__ levels,
                                                                  const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
                                                                  int ini_th, int min_th, uint32_t* __restrict__ cand,
                                                                  int cand_total, uint16_t* __restrict__ cellcnt,
                                                                  int ncells_total) {
-    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kCellBoxWMax];
-    __shared__ __align__(16) uint8_t score[kCellBoxHMax * kCellBoxWMax];
-    __shared__ uint16_t clist[kMaxCorners];
+    __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kBW];
+    __shared__ __align__(16) uint8_t score[kCellBoxHMax * kBW];
+    __shared__ uint16_t clist[kDirect ? 1 : kMaxCorners];
     __shared__ uint64_t bar;
     __shared__ uint32_t klist[kMaxKeep];
     __shared__ int n_corner, n_keep, n_sel;
@@ -162,7 +246,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
         if (tid == 0) *cnt_out = 0;
         return;
     }
-    const int bw = L.box_w, bh = L.box_h;
+    constexpr int bw = kBW;
+    const int bh = L.box_h;
     if (tid == 0) {
         n_corner = 0; n_keep = 0; n_sel = 0;
         mbar_init(&bar, 1);
@@ -172,8 +257,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
         tma_load_3d(tile, &maps.m[level], &bar, iniX & ~15, iniY, f);   // box origin must be 16-B aligned in x
     }
     const int dx = iniX & 15;
-    // clear the score tile while the box is in flight
-    for (int i = tid; i < (bw * bh + 3) / 4; i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    // clear the score tile while the box is in flight (its 3-px frame must read 0 in the NMS)
+    for (int i = tid; i < bw * bh / 4; i += kFastThreads) reinterpret_cast<uint32_t*>(score)[i] = 0;
     __syncthreads();   // barrier init visible to all waiters
     mbar_wait(&bar, 0);
 
@@ -181,53 +266,55 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)iw + 1u;   // p / iw == umulhi(p, rcp) for p < 65536
     const int t_low = min(ini_th, min_th);
 
-    // ---- phase 1: corner test.  Sign bits of (c - (v - t)) and ((v + t) - c) are shifted into two 16-bit rings.
-    for (int p = tid; p < npx; p += kFastThreads) {
-        const int y0 = (int)__umulhi((uint32_t)p, rcp);
-        const int y = y0 + 3, x = p - y0 * iw + 3;
-        const uint8_t* c = tile + y * bw + x + dx;
-        const int v = c[0], vlo = v - t_low, vhi = v + t_low;
-        uint32_t hi = 0, lo = 0;
-#define ADB_RING(off)                                                      \
-        {                                                                  \
-            const int q = c[off];                                          \
-            hi = __funnelshift_l((uint32_t)(q - vlo), hi, 1);              \
-            lo = __funnelshift_l((uint32_t)(vhi - q), lo, 1);              \
+    // ---- phase 1 (+ 2)
+    if (kDirect) {
+        for (int p = tid; p < npx; p += kFastThreads) {
+            const int y0 = (int)__umulhi((uint32_t)p, rcp);
+            const int o = (y0 + 3) * bw + (p - y0 * iw + 3);
+            const uint8_t* c = tile + o + dx;
+            uint32_t ring[16];
+            load_ring_packed(c, bw, fast_score_a(c[0]), ring);
+            const int best = fast_best(ring);
+            score[o] = (uint8_t)(best > t_low ? best - 1 : 0);   // response = best - 1 (>= 1 for every corner)
         }
-        ADB_RING(3 * bw) ADB_RING(3 * bw + 1) ADB_RING(2 * bw + 2) ADB_RING(bw + 3) ADB_RING(3) ADB_RING(-bw + 3) ADB_RING(-2 * bw + 2)
-        ADB_RING(-3 * bw + 1) ADB_RING(-3 * bw) ADB_RING(-3 * bw - 1) ADB_RING(-2 * bw - 2) ADB_RING(-bw - 3) ADB_RING(-3) ADB_RING(bw - 3)
-        ADB_RING(2 * bw - 2) ADB_RING(3 * bw - 1)
-#undef ADB_RING
-        if (has_run9(hi) || has_run9(lo)) {
-            const int slot = atomicAdd(&n_corner, 1);
-            if (slot < kMaxCorners) clist[slot] = (uint16_t)p;
+        __syncthreads();
+    } else {
+        for (int p = tid; p < npx; p += kFastThreads) {
+            const int y0 = (int)__umulhi((uint32_t)p, rcp);
+            const uint8_t* c = tile + (y0 + 3) * bw + (p - y0 * iw + 3) + dx;
+            uint32_t ring[16];
+            load_ring_packed(c, bw, fast_corner_a(c[0], t_low), ring);
+            if (fast_is_corner(ring)) {
+                const int slot = atomicAdd(&n_corner, 1);
+                if (slot < kMaxCorners) clist[slot] = (uint16_t)p;
+            }
         }
+        __syncthreads();
+        const int nc = min(n_corner, kMaxCorners);
+        for (int i = tid; i < nc; i += kFastThreads) {
+            const int p = clist[i];
+            const int y0 = (int)__umulhi((uint32_t)p, rcp);
+            const int o = (y0 + 3) * bw + (p - y0 * iw + 3);
+            const uint8_t* c = tile + o + dx;
+            uint32_t ring[16];
+            load_ring_packed(c, bw, fast_score_a(c[0]), ring);
+            score[o] = (uint8_t)(fast_best(ring) - 1);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int nc = min(n_corner, kMaxCorners);
 
-    // ---- phase 2: exact score of the corners
-    for (int i = tid; i < nc; i += kFastThreads) {
-        const int p = clist[i];
-        const int y0 = (int)__umulhi((uint32_t)p, rcp);
-        const int y = y0 + 3, x = p - y0 * iw + 3;
-        const uint8_t* c = tile + y * bw + x + dx;
-        int d[16];
-        load_circle_diffs(c, bw, c[0], d);
-        score[y * bw + x] = (uint8_t)(fast_best(d) - 1);   // response = best - 1 (0 never survives the NMS)
-    }
-    __syncthreads();
-
-    // ---- phase 3: NMS + mask for the listed corners -> unordered kept list (p | score << 16 | flags << 24;
+    // ---- phase 3: NMS + mask for the corners -> unordered kept list (p | score << 16 | flags << 24;
     //      flag bit 0: kept at minTh, bit 1: kept at iniTh)
     const uint8_t* ml = masks.p[level];
     int mineB = 0;
-    for (int i = tid; i < nc; i += kFastThreads) {
-        const int p = clist[i];
+    const int n3 = kDirect ? npx : min(n_corner, kMaxCorners);
+    for (int i = tid; i < n3; i += kFastThreads) {
+        const int p = kDirect ? i : (int)clist[i];
         const int y0 = (int)__umulhi((uint32_t)p, rcp);
         const int y = y0 + 3, x = p - y0 * iw + 3;
         const uint8_t* s = score + y * bw + x;
         const int v = s[0];
+        if (kDirect && v == 0) continue;
         bool keep = v > s[-1] && v > s[1] && v > s[-bw - 1] && v > s[-bw] && v > s[-bw + 1] && v > s[bw - 1] && v > s[bw] && v > s[bw + 1];
         if (keep && ml) keep = ml[(size_t)f * L.mframe_stride + (size_t)(iniY + y) * L.mpitch + iniX + x] != 0;
         const int fl = keep ? ((v >= min_th ? 1 : 0) | (v >= ini_th ? 2 : 0)) : 0;
@@ -933,6 +1020,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         d.cell_base = cell_base;
         d.box_w = (15 + d.wcell + 6 + 15) & ~15; d.box_h = d.hcell + 6;
         ADB_CHECK(d.box_w <= kCellBoxWMax && d.box_h <= kCellBoxHMax, ADB_ERR_INVALID, "level %d: cell box %dx%d too large", l, d.box_w, d.box_h);
+        h->cell_box_w = std::max(h->cell_box_w, d.box_w <= 64 ? 64 : kCellBoxWMax);
         ADB_CHECK(d.nrows < 4096 && d.ncols < 4096 && d.w < 4096 && d.h < 4096, ADB_ERR_INVALID, "image too large (max 4095 px per side)");
         d.slotcap = ((d.wcell + 1) / 2) * ((d.hcell + 1) / 2);
         d.cand_base = cand_base; d.cand_cap = d.ncells * d.slotcap;
@@ -962,6 +1050,12 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
             std::vector<int2> cx, cy;
             linear_coeffs(h->lv[l - 1].d.w, lh.d.w, cx);
             linear_coeffs(h->lv[l - 1].d.h, lh.d.h, cy);
+            // the strip kernel's 8-byte source window must cover the neighbours of 4 adjacent outputs
+            lh.strip_ok = getenv("ADB_PYR_SIMPLE") == nullptr;
+            for (int q4 = 0; q4 < lh.d.w; q4 += 4) {
+                const int last = std::min(q4 + 3, lh.d.w - 1);
+                if (std::min(cx[last].x + 1, h->lv[l - 1].d.w - 1) - cx[q4].x > 7) lh.strip_ok = false;
+            }
             ADB_CUDA(cudaMalloc(&lh.xtab, cx.size() * sizeof(int2)));
             ADB_CUDA(cudaMalloc(&lh.ytab, cy.size() * sizeof(int2)));
             ADB_CUDA(cudaMemcpy(lh.xtab, cx.data(), cx.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -1005,7 +1099,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     // TMA descriptors for levels >= 1 (level 0 is encoded per call: it may alias the caller's buffer)
     for (int l = 1; l < nl; ++l) {
         const LevelDev& d = h->lv[l].d;
-        adb_status s = encode_tma_u8_3d(&h->cell_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, d.box_w, d.box_h);
+        adb_status s = encode_tma_u8_3d(&h->cell_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, h->cell_box_w, d.box_h);
         if (s != ADB_OK) return s;
         s = encode_tma_u8_3d(&h->patch_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, kPatchBoxW, kPatchBoxH);
         if (s != ADB_OK) return s;
@@ -1060,7 +1154,7 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
     h->launches += (masked ? 2 : 1) * (nl - 1) + (h->ncells_total > 0 ? 1 : 0) + 2;
     {
         const LevelDev& d = h->lv[0].d;
-        adb_status s = encode_tma_u8_3d(&h->cell_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, d.box_w, d.box_h);
+        adb_status s = encode_tma_u8_3d(&h->cell_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, h->cell_box_w, d.box_h);
         if (s != ADB_OK) return s;
         s = encode_tma_u8_3d(&h->patch_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, kPatchBoxW, kPatchBoxH);
         if (s != ADB_OK) return s;
@@ -1077,6 +1171,19 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         const LevelDev& s = h->lv[l - 1].d;
         const LevelDev& d = h->lv[l].d;
         const uint8_t* src = l == 1 ? l0 : h->lv[l - 1].img;
+        if (h->lv[l].strip_ok) {
+            // rows per thread: enough threads to fill the machine, long enough strips to amortise the first source row
+            const int nq = (d.w + 3) / 4;
+            const int rows = std::max(4, std::min(16, (int)((long long)nq * d.h * n / 300000)));
+            const int nchunks = (d.h + rows - 1) / rows;
+            dim3 grid((nq * nchunks + 127) / 128, n);
+            pyr_resize_strip_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
+                                                         d.frame_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks);
+            if (masked)
+                pyr_resize_strip_kernel<<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w,
+                                                             d.h, d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks);
+            continue;
+        }
         dim3 grid((d.pitch / 4 + 127) / 128, d.h, n);
         pyr_resize_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
                                                d.frame_stride, h->lv[l].xtab, h->lv[l].ytab);
@@ -1093,8 +1200,11 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
 #endif
     if (h->ncells_total > 0) {
         dim3 grid(h->ncells_total, n);
-        fast_cells_kernel<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast,
-                                                        h->cfg.min_th_fast, h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total);
+        static const bool two_phase = getenv("ADB_FAST_TWO_PHASE") != nullptr;   // measurement switch: test first, score the corners
+        auto kern = h->cell_box_w == 64 ? (two_phase ? fast_cells_kernel<false, 64> : fast_cells_kernel<true, 64>)
+                                        : (two_phase ? fast_cells_kernel<false, kCellBoxWMax> : fast_cells_kernel<true, kCellBoxWMax>);
+        kern<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
+                                            h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total);
         ADB_STAGE("fast_cells");
     }
     // ---- quad-tree

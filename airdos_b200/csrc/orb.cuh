@@ -41,6 +41,7 @@ struct LevelHost {
     uint8_t* mask = nullptr;   // same layout, allocated on first masked call
     int2* xtab = nullptr;      // resize tables for producing this level from level-1: {src index, a0 | a1 << 16}
     int2* ytab = nullptr;
+    bool strip_ok = false;     // pyr_resize_strip_kernel applies (scale factor <= 2)
 };
 
 }  // namespace adb
@@ -50,6 +51,7 @@ struct adb_orb {
     int nlevels = 0;
     int capacity = 0;               // key-points per frame
     int ncells_total = 0;
+    int cell_box_w = 64;                // shared-memory pitch of the FAST cell box (64 or kCellBoxWMax), one per handle
     int cand_total = 0;             // u32 entries per frame
     int list_total = 0;             // entries per frame
     int qt_maxa = 0;                // quad-tree node capacity
