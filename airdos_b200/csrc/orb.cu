@@ -749,7 +749,9 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
                                                                          int32_t* __restrict__ counts, int cap,
                                                                          const __grid_constant__ adb_gather_targets gather) {
     extern __shared__ __align__(128) uint8_t desc_smem_raw[];
-    DescSmem& sm = *reinterpret_cast<DescSmem*>((reinterpret_cast<uintptr_t>(desc_smem_raw) + 127) & ~(uintptr_t)127);
+    // 128-B alignment for the TMA destinations; the offset is added to the shared array itself (not to a uintptr_t) so the
+    // compiler keeps the shared address space: LDS / STS with 32-bit addresses instead of generic LD / ST
+    DescSmem& sm = *reinterpret_cast<DescSmem*>(desc_smem_raw + ((128u - (smem_u32(desc_smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y;
     for (int i = tid; i < 512; i += kDescWarps * 32) sm.pat[i] = make_char2(pattern[2 * i], pattern[2 * i + 1]);
     if (lane == 0) mbar_init(&sm.bar[warp], 1);
@@ -870,8 +872,9 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
         const bool odd = sh & 1;
         const int wsh = sh >> 1;
-        for (int o = lane; o < 37 * 10; o += 32) {
-            const int r = o / 10, qd = o - r * 10;      // outputs c = 4 qd .. 4 qd + 3
+        // 30 lanes = 3 rows x 10 quads per step (no index arithmetic inside the loop)
+        const int r3 = lane / 10, qd = lane - r3 * 10;      // outputs c = 4 qd .. 4 qd + 3
+        for (int r = r3; r < 37 && lane < 30; r += 3) {
             const uint32_t* p = vert + r * kVPitchW + 2 * qd + wsh;
             const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4], w5 = p[5];
             const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16), s2 = __funnelshift_r(w2, w3, 16),
