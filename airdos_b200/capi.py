@@ -37,6 +37,20 @@ class OrbConfig(C.Structure):
                 ("height", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
 
 
+class ProjSearch(C.Structure):
+    """adb_proj_search (include/airdos_b200.h)."""
+    _fields_ = [("n_kp", C.c_int32), ("kps", C.c_void_p), ("u_right", C.c_void_p), ("desc", C.c_void_p), ("taken", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
+                ("n_q", C.c_int32), ("q_u", C.c_void_p), ("q_v", C.c_void_p), ("q_ur", C.c_void_p), ("q_radius", C.c_void_p),
+                ("q_min_level", C.c_void_p), ("q_max_level", C.c_void_p), ("q_flags", C.c_void_p), ("q_desc", C.c_void_p),
+                ("q_angle", C.c_void_p), ("use_ratio", C.c_int32), ("nn_ratio", C.c_float), ("check_orientation", C.c_int32),
+                ("last_xw", C.c_void_p), ("last_octave", C.c_void_p), ("tcw_cur", C.c_void_p), ("tcw_last", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float), ("mb", C.c_float),
+                ("scale_factors", C.c_void_p), ("n_levels", C.c_int32), ("th", C.c_float), ("mono", C.c_int32),
+                ("kp_match", C.c_void_p), ("q_best_idx", C.c_void_p), ("q_best_dist", C.c_void_p), ("n_matches", C.c_int32)]
+
+
 # every symbol include/airdos_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _f32, _sz = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
 _ip = C.POINTER(C.c_int32)
@@ -68,6 +82,8 @@ SYMBOLS = {
     "adb_matcher_destroy": (C.c_int, [_vp]),
     "adb_match_best2": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "adb_match_best2_device": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "adb_search_by_projection": (C.c_int, [_vp, _vp, _i32]),
+    "adb_search_last_ms": (C.c_int, [_vp, _fp]),
     "adb_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "adb_stereo_match": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
     "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),

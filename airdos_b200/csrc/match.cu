@@ -13,6 +13,7 @@
 #include <cmath>
 
 #include "orb.cuh"
+#include "matcher.cuh"
 
 namespace adb {
 
@@ -355,10 +356,6 @@ __global__ void __launch_bounds__(kDistinctThreads) distinctive_kernel(const uin
 
 using namespace adb;
 
-struct adb_matcher {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-};
 
 extern "C" {
 
@@ -391,6 +388,9 @@ adb_status adb_matcher_destroy(adb_matcher_t m) {
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
     cudaStreamDestroy(m->stream);
+    cudaFree(m->d_scratch);
+    if (m->h_scratch) cudaFreeHost(m->h_scratch);
+    if (m->ev[0]) { cudaEventDestroy(m->ev[0]); cudaEventDestroy(m->ev[1]); }
     delete m;
     return ADB_OK;
 }

@@ -837,32 +837,25 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     if (lane < 24) {
         const int wd = lane < 12 ? lane : lane - 12;
         const int r_begin = lane < 12 ? 0 : 19, r_end = lane < 12 ? 19 : 37;        // output rows [r_begin, r_end)
-        uint32_t lo[7], hi[7];
-#pragma unroll
-        for (int t = 0; t < 7; ++t) { lo[t] = 0; hi[t] = 0; }
-        // input row (r_begin + i) adds tap t to the output in slot t; the output in slot 6 is complete after its 7th row.
-        // Fully unrolled (25 rows) so the slot rotation is pure register renaming.
+        // sliding window of the last 7 input rows (even / odd pixels as two 16-bit lanes each); the kernel is symmetric, so an
+        // output row costs 3 adds (alu pipe) + 4 multiply-adds (fma pipe) per register instead of 7 multiply-adds.
+        // Fully unrolled (25 rows) so the window rotation is pure register renaming.
+        uint32_t we[7], wo[7];
 #pragma unroll
         for (int i = 0; i < 25; ++i) {
             const int ri = min(r_begin + i, kPatchBoxH - 1);
             const uint32_t w = raw32[ri * (kPatchBoxW / 4) + wd];
-            const uint32_t e = w & 0x00FF00FFu, o = (w >> 8) & 0x00FF00FFu;
-            lo[0] += 18u * e; hi[0] += 18u * o;
-            lo[1] += 34u * e; hi[1] += 34u * o;
-            lo[2] += 48u * e; hi[2] += 48u * o;
-            lo[3] += 56u * e; hi[3] += 56u * o;
-            lo[4] += 48u * e; hi[4] += 48u * o;
-            lo[5] += 34u * e; hi[5] += 34u * o;
-            lo[6] += 18u * e; hi[6] += 18u * o;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) { we[t] = we[t + 1]; wo[t] = wo[t + 1]; }
+            we[6] = w & 0x00FF00FFu; wo[6] = (w >> 8) & 0x00FF00FFu;
             if (i >= 6 && r_begin + i - 6 < r_end) {
+                const uint32_t lo = 18u * (we[0] + we[6]) + 34u * (we[1] + we[5]) + 48u * (we[2] + we[4]) + 56u * we[3];
+                const uint32_t hi = 18u * (wo[0] + wo[6]) + 34u * (wo[1] + wo[5]) + 48u * (wo[2] + wo[4]) + 56u * wo[3];
                 uint2 out;
-                out.x = __byte_perm(lo[6], hi[6], 0x5410);
-                out.y = __byte_perm(lo[6], hi[6], 0x7632);
+                out.x = __byte_perm(lo, hi, 0x5410);
+                out.y = __byte_perm(lo, hi, 0x7632);
                 *reinterpret_cast<uint2*>(vert + (r_begin + i - 6) * kVPitchW + 2 * wd) = out;
             }
-#pragma unroll
-            for (int t = 6; t > 0; --t) { lo[t] = lo[t - 1]; hi[t] = hi[t - 1]; }
-            lo[0] = 0; hi[0] = 0;
         }
     }
     __syncwarp();

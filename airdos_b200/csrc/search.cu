@@ -1,0 +1,467 @@
+// search.cu -- guided window searches on the Frame grid (candidate generation on the device).
+//
+//   project_last_kernel    head of SearchByProjection(Current, Last)     src/ORBmatcher.cc:1338-1393
+//   proj_search_kernel     Frame::AssignFeaturesToGrid / PosInGrid       src/Frame.cc:534-549, 700-712
+//                          Frame::GetFeaturesInArea                      src/Frame.cc:645-698
+//                          SearchByProjection(Frame, vpMapPoints, th)    src/ORBmatcher.cc:45-129
+//                          SearchByProjection(Current, Last, th, bMono)  src/ORBmatcher.cc:1395-1467
+//                          ComputeThreeMaxima                            src/ORBmatcher.cc:1601-1642
+//
+// The reference walks the queries one after the other because a query whose map point is already observed closes the
+// key-point it takes to every later query.  That dependence only runs from lower to higher query indices, so the
+// sequential result is the unique fixed point of "every query searches with the closures of the previous round"; one
+// thread block per frame iterates rounds (all queries in parallel, one warp per query) until the closures stop
+// changing -- query 0 is final after round 1, query 1 after round 2 at the latest, in practice two or three rounds.
+// Candidate order (cell column, cell row, insertion order) and the strict '<' updates make best / second-best the two
+// smallest (distance, position) pairs, which lanes compute on disjoint cells and merge with shuffles.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "matcher.cuh"
+
+namespace adb {
+
+constexpr int kGridCols = 64, kGridRows = 48, kGridCells = kGridCols * kGridRows;   // include/Frame.h:38-39
+constexpr int kHisto = 30;                                                          // HISTO_LENGTH src/ORBmatcher.cc:39
+constexpr int kThHigh = 100;                                                        // TH_HIGH src/ORBmatcher.cc:37
+constexpr int kSearchThreads = 1024;
+constexpr uint32_t kNoBlock = 0x7FFFFFFFu;
+
+// Device view of one problem: every pointer is device memory inside the call's scratch block.
+struct SearchDev {
+    int n_kp, n_q;
+    const adb_keypoint* kps;
+    const float* u_right;
+    const uint8_t* desc;
+    const uint8_t* taken;
+    float min_x, min_y, max_x, max_y, inv_w, inv_h;
+    float* q_u; float* q_v; float* q_ur; float* q_radius;
+    int32_t* q_minl; int32_t* q_maxl;
+    uint8_t* q_flags;
+    const uint8_t* q_desc;
+    const float* q_angle;
+    int use_ratio; float nn_ratio; int check_ori;
+    // projection (variant 2)
+    const float* last_xw; const int32_t* last_octave; const uint8_t* last_flags;
+    float Rcw[9], tcw[3];
+    float fx, fy, cx, cy, mbf, th;
+    const float* scale_factors;
+    int forward, backward;
+    // results
+    int32_t* kp_match; int32_t* q_best_idx; int32_t* q_best_dist; int32_t* q_choice; int32_t* n_matches;
+};
+
+// Rcw * x + tcw as cv::gemm does it for float matrices: products and sums in double, one rounding (oracle:
+// match_oracle_project_last).  Everything after it is float, no contraction.
+__global__ void project_last_kernel(const SearchDev* __restrict__ probs) {
+    const SearchDev& P = probs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!P.last_xw || i >= P.n_q) return;
+    float u = 0.f, v = 0.f, ur = 0.f, rad = 0.f;
+    int minl = 0, maxl = -1;
+    uint8_t fl = 0;
+    const uint8_t lf = P.last_flags[i];
+    if (lf & 1) {
+        const double x = P.last_xw[3 * i], y = P.last_xw[3 * i + 1], z = P.last_xw[3 * i + 2];
+        float c[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double s = __dmul_rn((double)P.Rcw[3 * r], x);
+            s = __dadd_rn(s, __dmul_rn((double)P.Rcw[3 * r + 1], y));
+            s = __dadd_rn(s, __dmul_rn((double)P.Rcw[3 * r + 2], z));
+            c[r] = (float)__dadd_rn(s, (double)P.tcw[r]);
+        }
+        const float invz = (float)__ddiv_rn(1.0, (double)c[2]);
+        if (!(invz < 0)) {
+            u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c[0]), invz), P.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c[1]), invz), P.cy);
+            if (!(u < P.min_x || u > P.max_x) && !(v < P.min_y || v > P.max_y)) {
+                const int lo = P.last_octave[i];
+                ur = __fsub_rn(u, __fmul_rn(P.mbf, invz));
+                rad = __fmul_rn(P.th, P.scale_factors[lo]);
+                if (P.forward) { minl = lo; maxl = -1; }
+                else if (P.backward) { minl = 0; maxl = lo; }
+                else { minl = lo - 1; maxl = lo + 1; }
+                fl = (uint8_t)(1 | (lf & 2));
+            } else { u = 0.f; v = 0.f; }
+        }
+    }
+    P.q_u[i] = u; P.q_v[i] = v; P.q_ur[i] = ur; P.q_radius[i] = rad; P.q_minl[i] = minl; P.q_maxl[i] = maxl; P.q_flags[i] = fl;
+}
+
+// 64-bit search key: distance << 43 | cell sequence << 31 | position in cell << 18 | key-point index << 5 | octave.
+// Unique per candidate and ordered by (distance, position in the reference's candidate list).
+__device__ __forceinline__ void key_insert(uint64_t k, uint64_t& best, uint64_t& second) {
+    if (k < best) { second = best; best = k; }
+    else if (k < second) second = k;
+}
+
+__global__ void __launch_bounds__(kSearchThreads) proj_search_kernel(const SearchDev* __restrict__ probs) {
+    extern __shared__ __align__(16) uint8_t search_smem[];
+    const SearchDev& P = probs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSearchThreads / 32;
+    const int nk = P.n_kp, nq = P.n_q;
+    // shared layout: cell_start[kGridCells + 1] | fill[kGridCells] | blk[2][nk] | items[nk] (u16) | cellid[nk] (u16)
+    uint32_t* cell_start = reinterpret_cast<uint32_t*>(search_smem);
+    uint32_t* fill = cell_start + kGridCells + 1;
+    uint32_t* blk0 = fill + kGridCells;
+    uint32_t* blk1 = blk0 + nk;
+    uint16_t* items = reinterpret_cast<uint16_t*>(blk1 + nk);
+    uint16_t* cellid = items + ((nk + 1) & ~1);
+    __shared__ int s_hist[kHisto];
+    __shared__ int s_keep[3];
+    __shared__ int s_acc, s_removed;
+    __shared__ uint32_t s_scan[kSearchThreads / 32];
+
+    // ---- Frame::AssignFeaturesToGrid: counting sort of the key-points by cell, insertion (= index) order inside a cell
+    for (int c = tid; c < kGridCells; c += kSearchThreads) { cell_start[c] = 0; fill[c] = 0; }
+    if (tid < kHisto) s_hist[tid] = 0;
+    if (tid == 0) { s_acc = 0; s_removed = 0; cell_start[kGridCells] = 0; }
+    __syncthreads();
+    for (int i = tid; i < nk; i += kSearchThreads) {
+        const adb_keypoint kp = P.kps[i];
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, P.min_x), P.inv_w));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, P.min_y), P.inv_h));
+        int c = 0xFFFF;
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) { c = px * kGridRows + py; atomicAdd(&cell_start[c], 1u); }
+        cellid[i] = (uint16_t)c;
+    }
+    __syncthreads();
+    {   // exclusive scan of the 3072 counts: 3 per thread
+        const int base = tid * 3;
+        const uint32_t a = cell_start[base], b = cell_start[base + 1], c = cell_start[base + 2];
+        const uint32_t mine = a + b + c;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_scan[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += t; }
+            s_scan[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t ex = s_scan[warp] + incl - mine;
+        cell_start[base] = ex; cell_start[base + 1] = ex + a; cell_start[base + 2] = ex + a + b;
+        if (tid == kSearchThreads - 1) cell_start[kGridCells] = ex + mine;
+    }
+    __syncthreads();
+    for (int i = tid; i < nk; i += kSearchThreads) {
+        const int c = cellid[i];
+        if (c != 0xFFFF) items[cell_start[c] + atomicAdd(&fill[c], 1u)] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int c = tid; c < kGridCells; c += kSearchThreads) {   // restore index order inside each cell (a handful of items)
+        const int a = cell_start[c], b = cell_start[c + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const uint16_t v = items[i];
+            int j = i - 1;
+            while (j >= a && items[j] > v) { items[j + 1] = items[j]; --j; }
+            items[j + 1] = v;
+        }
+    }
+    for (int i = tid; i < nk; i += kSearchThreads) blk0[i] = (P.taken && P.taken[i]) ? 0u : kNoBlock;
+    __syncthreads();
+
+    // ---- rounds.  blk[c] = 1 + the lowest blocking query that holds key-point c (0: closed on entry): query q may not
+    //      take c when blk[c] <= q.
+    uint32_t* prev = blk0;
+    uint32_t* cur = blk1;
+    for (int round = 0; round <= nq; ++round) {
+        for (int i = tid; i < nk; i += kSearchThreads) cur[i] = (P.taken && P.taken[i]) ? 0u : kNoBlock;
+        __syncthreads();
+        for (int q = warp; q < nq; q += nwarps) {
+            const uint8_t fl = P.q_flags[q];
+            uint64_t best = ~0ull, second = ~0ull;
+            if (fl & 1) {
+                const float x = P.q_u[q], y = P.q_v[q], r = P.q_radius[q], urq = P.q_ur[q];
+                const int minl = P.q_minl[q], maxl = P.q_maxl[q];
+                // Frame::GetFeaturesInArea cell range, float arithmetic in the reference's order
+                const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, P.min_x), r), P.inv_w)));
+                const int cx1 = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, P.min_x), r), P.inv_w)));
+                const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, P.min_y), r), P.inv_h)));
+                const int cy1 = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, P.min_y), r), P.inv_h)));
+                if (cx0 < kGridCols && cx1 >= 0 && cy0 < kGridRows && cy1 >= 0 && cx1 >= cx0 && cy1 >= cy0) {
+                    const bool check_levels = (minl > 0) || (maxl >= 0);
+                    const int ncy = cy1 - cy0 + 1, ncell = (cx1 - cx0 + 1) * ncy;
+                    uint32_t qd[8];
+                    {
+                        const uint4* qp = reinterpret_cast<const uint4*>(P.q_desc + (size_t)q * 32);
+                        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+                        qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+                    }
+                    for (int k = lane; k < ncell; k += 32) {
+                        const int ix = cx0 + k / ncy, iy = cy0 + k % ncy;
+                        const int c = ix * kGridRows + iy;
+                        const int a = cell_start[c], b = cell_start[c + 1];
+                        for (int j = a; j < b; ++j) {
+                            const int idx = items[j];
+                            const adb_keypoint kp = P.kps[idx];
+                            if (check_levels) {
+                                if (kp.octave < minl) continue;
+                                if (maxl >= 0 && kp.octave > maxl) continue;
+                            }
+                            if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+                            if (prev[idx] <= (uint32_t)q) continue;                  // held by an observed map point
+                            const float ur = P.u_right[idx];
+                            if (ur > 0 && fabsf(__fsub_rn(urq, ur)) > r) continue;
+                            const uint4* tp = reinterpret_cast<const uint4*>(P.desc + (size_t)idx * 32);
+                            const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+                            const int d = __popc(qd[0] ^ ta.x) + __popc(qd[1] ^ ta.y) + __popc(qd[2] ^ ta.z) + __popc(qd[3] ^ ta.w) +
+                                          __popc(qd[4] ^ tb.x) + __popc(qd[5] ^ tb.y) + __popc(qd[6] ^ tb.z) + __popc(qd[7] ^ tb.w);
+                            const uint64_t key = ((uint64_t)d << 43) | ((uint64_t)k << 31) | ((uint64_t)(j - a) << 18) |
+                                                 ((uint64_t)idx << 5) | (uint64_t)(kp.octave & 31);
+                            key_insert(key, best, second);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, o), os = __shfl_xor_sync(0xFFFFFFFFu, second, o);
+                const uint64_t lo = min(best, ob), hi = max(best, ob);
+                second = min(hi, min(second, os));
+                best = lo;
+            }
+            if (lane == 0) {
+                int choice = -1, bidx = -1, bdist = 256;
+                if (best != ~0ull) {
+                    bdist = (int)(best >> 43); bidx = (int)((best >> 5) & 0x1FFF);
+                    if (bdist <= kThHigh) {
+                        bool ok = true;
+                        if (P.use_ratio) {
+                            const int lvl = (int)(best & 31), lvl2 = second != ~0ull ? (int)(second & 31) : -1;
+                            const int d2 = second != ~0ull ? (int)(second >> 43) : 256;
+                            if (lvl == lvl2 && (float)bdist > __fmul_rn(P.nn_ratio, (float)d2)) ok = false;
+                        }
+                        if (ok) {
+                            choice = bidx;
+                            if (fl & 2) atomicMin(&cur[bidx], (uint32_t)q + 1u);
+                        }
+                    }
+                }
+                P.q_choice[q] = choice;
+                if (P.q_best_idx) P.q_best_idx[q] = bidx;
+                if (P.q_best_dist) P.q_best_dist[q] = bdist;
+            }
+        }
+        __syncthreads();
+        int changed = 0;
+        for (int i = tid; i < nk; i += kSearchThreads) changed |= (cur[i] != prev[i]);
+        uint32_t* t = prev; prev = cur; cur = t;
+        if (!__syncthreads_or(changed)) break;
+    }
+
+    // ---- write-back: mvpMapPoints[c] = the last query that took c; rotation histogram on the accepted queries
+    int32_t* owner = reinterpret_cast<int32_t*>(cur);      // both closure arrays are free now
+    uint32_t* cleared = prev;
+    for (int i = tid; i < nk; i += kSearchThreads) { owner[i] = -1; cleared[i] = 0; }
+    __syncthreads();
+    int my_acc = 0;
+    for (int q = tid; q < nq; q += kSearchThreads) {
+        const int c = P.q_choice[q];
+        if (c < 0) continue;
+        ++my_acc;
+        atomicMax(&owner[c], q);
+        if (P.check_ori) {
+            float rot = __fsub_rn(P.q_angle[q], P.kps[c].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
+            if (bin == kHisto) bin = 0;
+            atomicAdd(&s_hist[bin], 1);
+        }
+    }
+    if (my_acc) atomicAdd(&s_acc, my_acc);
+    __syncthreads();
+    if (P.check_ori) {
+        if (tid == 0) {   // ORBmatcher::ComputeThreeMaxima
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < kHisto; ++i) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+            s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        }
+        __syncthreads();
+        int my_rm = 0;
+        for (int q = tid; q < nq; q += kSearchThreads) {
+            const int c = P.q_choice[q];
+            if (c < 0) continue;
+            float rot = __fsub_rn(P.q_angle[q], P.kps[c].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
+            if (bin == kHisto) bin = 0;
+            if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { cleared[c] = 1; ++my_rm; }
+        }
+        if (my_rm) atomicAdd(&s_removed, my_rm);
+        __syncthreads();
+    }
+    for (int i = tid; i < nk; i += kSearchThreads) P.kp_match[i] = cleared[i] ? -2 : owner[i];
+    if (tid == 0) *P.n_matches = s_acc - s_removed;
+}
+
+static size_t search_smem_bytes(int nk) {
+    return (size_t)(2 * kGridCells + 1) * 4 + (size_t)2 * nk * 4 + (size_t)((nk + 1) & ~1) * 2 + (size_t)nk * 2 + 16;
+}
+
+}  // namespace adb
+
+using namespace adb;
+
+namespace {
+
+struct Packer {   // lays host arrays out in one staging block; device pointers are base + offset
+    uint8_t* h = nullptr;
+    uint8_t* d = nullptr;
+    size_t off = 0;
+    size_t reserve(size_t bytes) { off = (off + 15) & ~(size_t)15; const size_t o = off; off += bytes; return o; }
+    template <typename T>
+    T* put(const T* src, size_t n) {   // copies when h is set (second pass), returns the device address
+        const size_t o = reserve(n * sizeof(T));
+        if (h && src) memcpy(h + o, src, n * sizeof(T));
+        return reinterpret_cast<T*>(d + o);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+adb_status adb_search_last_ms(adb_matcher_t m, float* ms) {
+    ADB_CHECK(m && ms, ADB_ERR_INVALID, "null argument");
+    *ms = m->last_ms;
+    return ADB_OK;
+}
+
+adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int32_t n) {
+    ADB_CHECK(m && (probs || n == 0) && n >= 0, ADB_ERR_INVALID, "null argument");
+    if (n == 0) return ADB_OK;
+    ADB_CUDA(cudaSetDevice(m->device));
+    int max_nk = 0, max_nq = 0;
+    for (int p = 0; p < n; ++p) {
+        const adb_proj_search& s = probs[p];
+        ADB_CHECK(s.n_kp >= 0 && s.n_kp <= ADB_SEARCH_MAX && s.n_q >= 0 && s.n_q <= ADB_SEARCH_MAX, ADB_ERR_INVALID,
+                  "problem %d: sizes out of range (max %d)", p, ADB_SEARCH_MAX);
+        ADB_CHECK(s.kp_match || s.n_kp == 0, ADB_ERR_INVALID, "problem %d: kp_match is NULL", p);
+        ADB_CHECK(s.n_kp == 0 || (s.kps && s.u_right && s.desc), ADB_ERR_INVALID, "problem %d: frame arrays missing", p);
+        ADB_CHECK(s.n_q == 0 || (s.q_flags && s.q_desc), ADB_ERR_INVALID, "problem %d: query arrays missing", p);
+        ADB_CHECK(s.n_q == 0 || s.last_xw || (s.q_u && s.q_v && s.q_ur && s.q_radius && s.q_min_level && s.q_max_level),
+                  ADB_ERR_INVALID, "problem %d: neither projected queries nor last-frame points given", p);
+        ADB_CHECK(!s.last_xw || (s.last_octave && s.tcw_cur && s.tcw_last && s.scale_factors && s.n_levels > 0), ADB_ERR_INVALID,
+                  "problem %d: last-frame projection inputs missing", p);
+        ADB_CHECK(!s.check_orientation || s.q_angle, ADB_ERR_INVALID, "problem %d: q_angle missing", p);
+        max_nk = std::max(max_nk, s.n_kp); max_nq = std::max(max_nq, s.n_q);
+    }
+    // two passes over the same layout code: size, then copy
+    std::vector<SearchDev> dev(n);
+    size_t out_begin = 0, total = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        Packer pk;
+        if (pass == 1) { pk.h = m->h_scratch; pk.d = m->d_scratch; }
+        pk.reserve((size_t)n * sizeof(SearchDev));
+        for (int p = 0; p < n; ++p) {
+            const adb_proj_search& s = probs[p];
+            SearchDev& D = dev[p];
+            memset(&D, 0, sizeof(D));
+            D.n_kp = s.n_kp; D.n_q = s.n_q;
+            D.kps = pk.put(s.kps, s.n_kp); D.u_right = pk.put(s.u_right, s.n_kp); D.desc = pk.put(s.desc, (size_t)s.n_kp * 32);
+            D.taken = s.taken ? pk.put(s.taken, s.n_kp) : nullptr;
+            D.min_x = s.min_x; D.min_y = s.min_y; D.max_x = s.max_x; D.max_y = s.max_y; D.inv_w = s.grid_inv_w; D.inv_h = s.grid_inv_h;
+            const bool proj = s.last_xw != nullptr;
+            D.q_u = pk.put(proj ? nullptr : s.q_u, s.n_q); D.q_v = pk.put(proj ? nullptr : s.q_v, s.n_q);
+            D.q_ur = pk.put(proj ? nullptr : s.q_ur, s.n_q); D.q_radius = pk.put(proj ? nullptr : s.q_radius, s.n_q);
+            D.q_minl = pk.put(proj ? nullptr : s.q_min_level, s.n_q); D.q_maxl = pk.put(proj ? nullptr : s.q_max_level, s.n_q);
+            D.q_flags = pk.put(proj ? nullptr : s.q_flags, s.n_q);
+            D.q_desc = pk.put(s.q_desc, (size_t)s.n_q * 32);
+            D.q_angle = s.check_orientation ? pk.put(s.q_angle, s.n_q) : nullptr;
+            D.use_ratio = s.use_ratio; D.nn_ratio = s.nn_ratio; D.check_ori = s.check_orientation;
+            if (proj) {
+                D.last_xw = pk.put(s.last_xw, (size_t)s.n_q * 3); D.last_octave = pk.put(s.last_octave, s.n_q);
+                D.last_flags = pk.put(s.q_flags, s.n_q);
+                D.scale_factors = pk.put(s.scale_factors, s.n_levels);
+                for (int r = 0; r < 3; ++r) {
+                    for (int c = 0; c < 3; ++c) D.Rcw[3 * r + c] = s.tcw_cur[4 * r + c];
+                    D.tcw[r] = s.tcw_cur[4 * r + 3];
+                }
+                D.fx = s.fx; D.fy = s.fy; D.cx = s.cx; D.cy = s.cy; D.mbf = s.mbf; D.th = s.th;
+                // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw (cv::gemm: double accumulation, one rounding) -> bForward / bBackward
+                float twc[3], tlc[3];
+                for (int i = 0; i < 3; ++i) {
+                    double a = 0;
+                    for (int k = 0; k < 3; ++k) a += (-(double)s.tcw_cur[4 * k + i]) * (double)s.tcw_cur[4 * k + 3];
+                    twc[i] = (float)a;
+                }
+                for (int i = 0; i < 3; ++i) {
+                    double a = 0;
+                    for (int k = 0; k < 3; ++k) a += (double)s.tcw_last[4 * i + k] * (double)twc[k];
+                    tlc[i] = (float)(a + (double)s.tcw_last[4 * i + 3]);
+                }
+                D.forward = (tlc[2] > s.mb && !s.mono) ? 1 : 0;
+                D.backward = (-tlc[2] > s.mb && !s.mono) ? 1 : 0;
+            }
+        }
+        out_begin = pk.reserve(0);
+        for (int p = 0; p < n; ++p) {   // results: contiguous tail of the block, copied back in one piece
+            const adb_proj_search& s = probs[p];
+            SearchDev& D = dev[p];
+            D.kp_match = pk.put((const int32_t*)nullptr, s.n_kp);
+            D.q_best_idx = pk.put((const int32_t*)nullptr, s.n_q);
+            D.q_best_dist = pk.put((const int32_t*)nullptr, s.n_q);
+            D.q_choice = pk.put((const int32_t*)nullptr, s.n_q);
+            D.n_matches = pk.put((const int32_t*)nullptr, 1);
+        }
+        total = pk.reserve(0);
+        if (pass == 0 && total > m->scratch_bytes) {
+            cudaFree(m->d_scratch); m->d_scratch = nullptr;
+            if (m->h_scratch) { cudaFreeHost(m->h_scratch); m->h_scratch = nullptr; }
+            m->scratch_bytes = 0;
+            const size_t want = total + total / 4;
+            ADB_CUDA(cudaMalloc(&m->d_scratch, want));
+            ADB_CUDA(cudaMallocHost(&m->h_scratch, want));
+            m->scratch_bytes = want;
+        }
+    }
+    memcpy(m->h_scratch, dev.data(), (size_t)n * sizeof(SearchDev));
+    if (!m->ev[0]) { ADB_CUDA(cudaEventCreate(&m->ev[0])); ADB_CUDA(cudaEventCreate(&m->ev[1])); }
+    const size_t smem = search_smem_bytes(max_nk);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADB_CUDA(cudaFuncSetAttribute(proj_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes(ADB_SEARCH_MAX)));
+        attr_set = true;
+    }
+    ADB_CUDA(cudaMemcpyAsync(m->d_scratch, m->h_scratch, out_begin, cudaMemcpyHostToDevice, m->stream));
+    const SearchDev* dprobs = reinterpret_cast<const SearchDev*>(m->d_scratch);
+    ADB_CUDA(cudaEventRecord(m->ev[0], m->stream));
+    bool any_proj = false;
+    for (int p = 0; p < n; ++p) any_proj |= probs[p].last_xw != nullptr;
+    if (any_proj && max_nq > 0) {
+        dim3 grid((max_nq + 255) / 256, n);
+        project_last_kernel<<<grid, 256, 0, m->stream>>>(dprobs);
+    }
+    proj_search_kernel<<<n, kSearchThreads, smem, m->stream>>>(dprobs);
+    ADB_CUDA(cudaGetLastError());
+    ADB_CUDA(cudaEventRecord(m->ev[1], m->stream));
+    ADB_CUDA(cudaMemcpyAsync(m->h_scratch + out_begin, m->d_scratch + out_begin, total - out_begin, cudaMemcpyDeviceToHost, m->stream));
+    ADB_CUDA(cudaStreamSynchronize(m->stream));
+    ADB_CUDA(cudaEventElapsedTime(&m->last_ms, m->ev[0], m->ev[1]));
+    for (int p = 0; p < n; ++p) {
+        adb_proj_search& s = probs[p];
+        const SearchDev& D = dev[p];
+        auto host = [&](const void* dptr) { return m->h_scratch + ((const uint8_t*)dptr - m->d_scratch); };
+        if (s.n_kp) memcpy(s.kp_match, host(D.kp_match), (size_t)s.n_kp * 4);
+        if (s.q_best_idx && s.n_q) memcpy(s.q_best_idx, host(D.q_best_idx), (size_t)s.n_q * 4);
+        if (s.q_best_dist && s.n_q) memcpy(s.q_best_dist, host(D.q_best_dist), (size_t)s.n_q * 4);
+        memcpy(&s.n_matches, host(D.n_matches), 4);
+    }
+    return ADB_OK;
+}
+
+}  // extern "C"

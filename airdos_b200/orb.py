@@ -217,6 +217,68 @@ class ORBmatcher:
         return bi, bd, sd
 
 
+    # -- guided window searches (candidate generation on the device) ---------------------------------
+    def search_by_projection(self, problems: list[dict]):
+        """Batch of independent searches.  Each problem is a dict with the current frame (`kps`, `u_right`, `desc`,
+        optional `taken`, `bounds` = (mnMinX, mnMinY, mnMaxX, mnMaxY)) and either projected queries (`q_u`, `q_v`, `q_ur`,
+        `q_radius`, `q_min_level`, `q_max_level`, `q_flags`, `q_desc`; SearchByProjection(F, vpMapPoints, th),
+        src/ORBmatcher.cc:45-129) or the last frame (`last_xw`, `last_octave`, `q_flags`, `q_desc`, `q_angle`, `tcw_cur`,
+        `tcw_last`, `cam` = (fx, fy, cx, cy, mbf, mb), `scale_factors`, `th`, `mono`; SearchByProjection(Current, Last, th,
+        bMono), src/ORBmatcher.cc:1328-1470).  Returns a list of (nmatches, kp_match, q_best_idx, q_best_dist)."""
+        from .capi import ProjSearch
+        n = len(problems)
+        arr = (ProjSearch * n)()
+        keep = []   # numpy arrays referenced by the structs
+
+        def a(x, dt):
+            x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+
+        outs = []
+        for i, pr in enumerate(problems):
+            S = arr[i]
+            kps = np.ascontiguousarray(pr["kps"], KP_DTYPE); keep.append(kps)
+            S.n_kp = len(kps); S.kps = kps.ctypes.data
+            S.u_right = a(pr["u_right"], np.float32); S.desc = a(pr["desc"], np.uint8)
+            S.taken = a(pr["taken"], np.uint8) if pr.get("taken") is not None else None
+            mnx, mny, mxx, mxy = [np.float32(v) for v in pr["bounds"]]
+            S.min_x, S.min_y, S.max_x, S.max_y = mnx, mny, mxx, mxy
+            S.grid_inv_w = np.float32(64) / np.float32(mxx - mnx)      # src/Frame.cc:107-108
+            S.grid_inv_h = np.float32(48) / np.float32(mxy - mny)
+            S.n_q = len(pr["q_flags"])
+            S.q_flags = a(pr["q_flags"], np.uint8); S.q_desc = a(pr["q_desc"], np.uint8)
+            if "last_xw" in pr:
+                S.last_xw = a(pr["last_xw"], np.float32); S.last_octave = a(pr["last_octave"], np.int32)
+                S.tcw_cur = a(pr["tcw_cur"], np.float32); S.tcw_last = a(pr["tcw_last"], np.float32)
+                S.fx, S.fy, S.cx, S.cy, S.mbf, S.mb = [float(v) for v in pr["cam"]]
+                sf = np.ascontiguousarray(pr["scale_factors"], np.float32); keep.append(sf)
+                S.scale_factors = sf.ctypes.data; S.n_levels = len(sf)
+                S.th = float(pr["th"]); S.mono = int(pr.get("mono", 0))
+                S.q_angle = a(pr["q_angle"], np.float32)
+                S.check_orientation = int(pr.get("check_orientation", self.mbCheckOrientation)); S.use_ratio = 0
+            else:
+                for k in ("q_u", "q_v", "q_ur", "q_radius"):
+                    setattr(S, k, a(pr[k], np.float32))
+                S.q_min_level = a(pr["q_min_level"], np.int32); S.q_max_level = a(pr["q_max_level"], np.int32)
+                S.use_ratio = int(pr.get("use_ratio", 1)); S.nn_ratio = float(pr.get("nn_ratio", self.mfNNratio))
+                S.check_orientation = int(pr.get("check_orientation", 0))
+                if S.check_orientation:
+                    S.q_angle = a(pr["q_angle"], np.float32)
+            km = np.full(S.n_kp, -1, np.int32); bi = np.full(S.n_q, -1, np.int32); bd = np.full(S.n_q, 256, np.int32)
+            S.kp_match, S.q_best_idx, S.q_best_dist = km.ctypes.data, bi.ctypes.data, bd.ctypes.data
+            outs.append((km, bi, bd))
+        check(lib().adb_search_by_projection(self._m, C.byref(arr), n))
+        return [(int(arr[i].n_matches),) + outs[i] for i in range(n)]
+
+    def SearchByProjection(self, problem: dict):
+        """One frame: returns (nmatches, kp_match, q_best_idx, q_best_dist)."""
+        return self.search_by_projection([problem])[0]
+
+    def search_last_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().adb_search_last_ms(self._m, C.byref(ms)))
+        return float(ms.value)
+
+
 def compute_distinctive_descriptors(matcher: ORBmatcher, desc: np.ndarray, point_ptr: np.ndarray):
     """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (CSR over observation descriptors) ->
     (best_idx [P], best_desc [P, 32])."""

@@ -303,3 +303,71 @@ def make_pose_frames(n_frames: int = 4, n_points: int = 600, seed: int = 7, outl
                            inv_sigma2=(np.float32(1) / (np.float32(1.2) ** lvl.astype(np.float32)) ** 2).astype(np.float32)))
         gts.append(t)
     return cam, frames, np.array(gts)
+
+
+# ------------------------------------------------------------------------------------------
+# Tracking search problems: a current Frame and the map points of the last frame
+def make_tracking_problem(seed: int = 0, n_kp: int = 2000, n_q: int = 1500, width: int = 640, height: int = 480,
+                          th: float = 7.0, dup_frac: float = 0.1, n_levels: int = 8, scale: float = 1.2, last_dz: float = 0.02):
+    """Problem dict for ORBmatcher.search_by_projection, last-frame variant (src/ORBmatcher.cc:1328-1470): key-points of the
+    current frame (positions uniform in the image, octaves by the ORB quota, ~70 % with a stereo match), and n_q map
+    points of the last frame: most are a current key-point back-projected through its stereo depth (descriptor with a few
+    flipped bits, octave +-1), `dup_frac` of them duplicates that compete for the same key-point (the reference's
+    sequential closure rule decides), the rest random.  The last pose is the current one moved by a few centimetres."""
+    from .capi import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    sf = (np.float32(scale) ** np.arange(n_levels)).astype(np.float32)
+    for i in range(1, n_levels):   # mvScaleFactor[i] = mvScaleFactor[i-1] * scaleFactor (src/ORBextractor.cc:418-424)
+        sf[i] = np.float32(sf[i - 1] * np.float32(scale))
+    kps = np.zeros(n_kp, KP_DTYPE)
+    kps["x"] = rng.uniform(20, width - 20, n_kp).astype(np.float32)
+    kps["y"] = rng.uniform(20, height - 20, n_kp).astype(np.float32)
+    quota = ORB_QUOTA_2000[:n_levels] / ORB_QUOTA_2000[:n_levels].sum()
+    kps["octave"] = rng.choice(n_levels, n_kp, p=quota)
+    kps["angle"] = rng.uniform(0, 360, n_kp).astype(np.float32)
+    kps["size"] = 31 * sf[kps["octave"]]
+    desc = rng.integers(0, 256, (n_kp, 32), dtype=np.uint8)
+    depth = rng.uniform(3.0, 40.0, n_kp)
+    has_stereo = rng.random(n_kp) < 0.7
+    u_right = np.where(has_stereo, kps["x"] - BF / depth, -1.0).astype(np.float32)
+    taken = (rng.random(n_kp) < 0.03).astype(np.uint8)
+    # poses: current = small motion from identity; last = current moved a little further back
+    Tc = np.eye(4); Tc[:3, :3] = _small_rot(rng.normal(0, 0.01, 3)); Tc[:3, 3] = rng.normal(0, 0.05, 3)
+    Tl = np.eye(4); Tl[:3, :3] = _small_rot(rng.normal(0, 0.01, 3)) @ Tc[:3, :3]; Tl[:3, 3] = Tc[:3, 3] + np.array([0.0, 0.0, last_dz])   # |dz| > mb switches the forward / backward level rule
+    Rcw, tcw = Tc[:3, :3], Tc[:3, 3]
+    src = rng.integers(0, n_kp, n_q)
+    n_dup = int(dup_frac * n_q)
+    src[n_q - n_dup:] = src[rng.integers(0, n_q - n_dup, n_dup)]          # duplicates of earlier queries
+    perm = rng.permutation(n_q); src = src[perm]
+    is_random = rng.random(n_q) < 0.15
+    # back-project the source key-point (with a little pixel noise) into the world through the current pose
+    u = kps["x"][src] + rng.normal(0, 1.5, n_q); v = kps["y"][src] + rng.normal(0, 1.5, n_q)
+    z = depth[src]
+    xc = np.stack([(u - CX) * z / FX, (v - CY) * z / FY, z], 1)
+    xw = (xc - tcw) @ Rcw          # Rcw^T (xc - tcw)
+    xw[is_random] = rng.uniform([-10, -5, 2], [10, 5, 40], (int(is_random.sum()), 3))
+    xw[rng.random(n_q) < 0.02, 2] = -5.0   # behind the camera
+    q_desc = desc[src].copy()
+    flips = rng.integers(0, 60, n_q)
+    for i in range(n_q):
+        bits = rng.choice(256, flips[i], replace=False)
+        np.bitwise_xor.at(q_desc[i], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    q_desc[is_random] = rng.integers(0, 256, (int(is_random.sum()), 32), dtype=np.uint8)
+    octave = np.clip(kps["octave"][src] + rng.integers(-1, 2, n_q), 0, n_levels - 1).astype(np.int32)
+    rot = np.where(rng.random(n_q) < 0.8, rng.normal(4.0, 3.0, n_q), rng.uniform(0, 360, n_q))
+    q_angle = np.mod(kps["angle"][src] + rot, 360.0).astype(np.float32)
+    q_flags = ((rng.random(n_q) < 0.93).astype(np.uint8) | ((rng.random(n_q) < 0.5).astype(np.uint8) << 1)).astype(np.uint8)
+    return dict(kps=kps, u_right=u_right, desc=desc, taken=taken, bounds=(0.0, 0.0, float(width), float(height)),
+                q_flags=q_flags, q_desc=q_desc, q_angle=q_angle, last_xw=xw.astype(np.float32), last_octave=octave,
+                tcw_cur=Tc.astype(np.float32), tcw_last=Tl.astype(np.float32), cam=(FX, FY, CX, CY, BF, BF / FX),
+                scale_factors=sf, th=th, mono=0)
+
+
+def tracking_problem_as_map_points(pr: dict, proj: dict, nn_ratio: float = 0.8) -> dict:
+    """The same scene as a SearchByProjection(Frame, vpMapPoints, th) problem (src/ORBmatcher.cc:45-129): `proj` are the
+    projected query arrays (from the oracle's projection); level window = (nPredictedLevel - 1, nPredictedLevel)."""
+    out = {k: pr[k] for k in ("kps", "u_right", "desc", "taken", "bounds", "q_desc", "q_angle")}
+    lvl = np.asarray(pr["last_octave"], np.int32)
+    out.update(q_u=proj["q_u"], q_v=proj["q_v"], q_ur=proj["q_ur"], q_radius=proj["q_radius"], q_min_level=(lvl - 1).astype(np.int32),
+               q_max_level=lvl.copy(), q_flags=proj["q_flags"], use_ratio=1, nn_ratio=nn_ratio, check_orientation=0)
+    return out

@@ -184,6 +184,65 @@ adb_status adb_match_best2_device(adb_matcher_t m, const uint8_t* q_desc, int32_
 adb_status adb_distinctive_descriptors(adb_matcher_t m, const uint8_t* desc, const int32_t* point_ptr, int32_t n_points,
                                        int32_t* best_idx, uint8_t* best_desc);
 
+/* ---------------------------------------------------------------------------------------
+ * Guided window searches on the Frame grid, candidate generation included:
+ *   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)          src/ORBmatcher.cc:45-129
+ *   ORBmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono)  src/ORBmatcher.cc:1328-1470
+ * with Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:534-549, 700-712, 645-698) and
+ * ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1601-1642) behind them.  Both searches are one loop over queries
+ * (map points with a predicted pixel): the key-points of the 64 x 48 grid cells under the query's window, in the
+ * reference's order (cell column, cell row, insertion order), minus the ones already held by an observed map point,
+ * minus the ones whose right coordinate is off; best / second-best Hamming; accept; assign.  The loop is sequential in
+ * the reference (an earlier query closes a key-point to later ones); the kernel iterates to the same fixed point.
+ * One problem = one frame; all pointers are host memory. */
+typedef struct adb_proj_search {
+    /* the current Frame */
+    int32_t n_kp;                  /* Frame::N (<= ADB_SEARCH_MAX) */
+    const adb_keypoint* kps;       /* mvKeysUn: pt, octave, angle */
+    const float* u_right;          /* mvuRight */
+    const uint8_t* desc;           /* mDescriptors, n_kp x 32 */
+    const uint8_t* taken;          /* NULL, or [n_kp]: mvpMapPoints[i] != NULL && Observations() > 0 on entry */
+    float min_x, min_y, max_x, max_y;   /* mnMinX .. mnMaxY */
+    float grid_inv_w, grid_inv_h;       /* mfGridElementWidthInv / mfGridElementHeightInv */
+    /* queries, variant 1 (map points, src/ORBmatcher.cc:45-129): filled by the caller from MapPoint::mTrackProj* */
+    int32_t n_q;                   /* <= ADB_SEARCH_MAX */
+    const float* q_u;              /* mTrackProjX */
+    const float* q_v;              /* mTrackProjY */
+    const float* q_ur;             /* mTrackProjXR */
+    const float* q_radius;         /* r * mvScaleFactors[nPredictedLevel] (r = RadiusByViewingCos(...) [* th]) */
+    const int32_t* q_min_level;    /* nPredictedLevel - 1 */
+    const int32_t* q_max_level;    /* nPredictedLevel */
+    const uint8_t* q_flags;        /* bit 0: takes part (mbTrackInView && !isBad); bit 1: Observations() > 0 */
+    const uint8_t* q_desc;         /* pMP->GetDescriptor(), n_q x 32 */
+    const float* q_angle;          /* LastFrame.mvKeysUn[i].angle; only read when check_orientation != 0 */
+    int32_t use_ratio;             /* 1: second-best + same-level ratio rule (variant 1) */
+    float nn_ratio;                /* mfNNratio */
+    int32_t check_orientation;     /* mbCheckOrientation (variant 2) */
+    /* queries, variant 2 (last frame, src/ORBmatcher.cc:1328-1393): when last_xw != NULL the library projects the last
+     * frame's map points itself and q_u .. q_max_level are ignored.  q_flags bit 0 then means "mvpMapPoints[i] != NULL
+     * && !mvbOutlier[i]"; q_desc / q_angle / n_q are the last frame's. */
+    const float* last_xw;          /* [n_q][3] pMP->GetWorldPos() */
+    const int32_t* last_octave;    /* [n_q] LastFrame.mvKeys[i].octave */
+    const float* tcw_cur;          /* row-major 4x4 CurrentFrame.mTcw */
+    const float* tcw_last;         /* row-major 4x4 LastFrame.mTcw */
+    float fx, fy, cx, cy, mbf, mb;
+    const float* scale_factors;    /* CurrentFrame.mvScaleFactors */
+    int32_t n_levels;
+    float th;
+    int32_t mono;                  /* bMono */
+    /* results */
+    int32_t* kp_match;             /* [n_kp] CurrentFrame.mvpMapPoints after the call: -1 untouched, -2 set to NULL by the rotation
+                                      check, >= 0 index of the query (map point) now held */
+    int32_t* q_best_idx;           /* [n_q] optional: bestIdx of every query (-1: no candidate) */
+    int32_t* q_best_dist;          /* [n_q] optional: bestDist (256: no candidate) */
+    int32_t n_matches;             /* return value of the reference function */
+} adb_proj_search;
+#define ADB_SEARCH_MAX 8192
+/* Runs n_problems independent searches (one thread block each). */
+adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* problems, int32_t n_problems);
+/* Device time in ms of the kernels of the last adb_search_by_projection call. */
+adb_status adb_search_last_ms(adb_matcher_t m, float* ms);
+
 /* Frame::ComputeStereoMatches()  (src/Frame.cc:829-1003) for the n_frames frames resident in
  * the two extractor handles (frame i of `left` against frame i of `right`): row-band Hamming
  * match, 11x11 SAD sub-pixel refinement on the pyramids, median-distance cut.

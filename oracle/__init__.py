@@ -213,6 +213,48 @@ def distinctive(desc: np.ndarray, point_ptr: np.ndarray) -> np.ndarray:
     return out
 
 
+def search_by_projection(pr: dict, nn_ratio: float = 0.6, check_orientation: bool = True):
+    """SearchByProjection restatement on the problem dicts of airdos_b200.ORBmatcher.search_by_projection.
+    Returns (nmatches, kp_match, q_best_idx, q_best_dist)."""
+    lib = _match_lib()
+    kps = np.ascontiguousarray(pr["kps"], KP_DTYPE)
+    ur = np.ascontiguousarray(pr["u_right"], np.float32); desc = np.ascontiguousarray(pr["desc"], np.uint8)
+    taken = np.ascontiguousarray(pr["taken"], np.uint8) if pr.get("taken") is not None else None
+    mnx, mny, mxx, mxy = [np.float32(v) for v in pr["bounds"]]
+    inv_w = np.float32(64) / np.float32(mxx - mnx); inv_h = np.float32(48) / np.float32(mxy - mny)
+    qf = np.ascontiguousarray(pr["q_flags"], np.uint8); qd = np.ascontiguousarray(pr["q_desc"], np.uint8)
+    nq, nk = len(qf), len(kps)
+    if "last_xw" in pr:
+        qu = np.zeros(nq, np.float32); qv = np.zeros(nq, np.float32); qur = np.zeros(nq, np.float32); qr = np.zeros(nq, np.float32)
+        qmin = np.zeros(nq, np.int32); qmax = np.zeros(nq, np.int32); qfl = np.zeros(nq, np.uint8)
+        fx, fy, cx, cy, mbf, mb = [float(v) for v in pr["cam"]]
+        sf = np.ascontiguousarray(pr["scale_factors"], np.float32)
+        xw = np.ascontiguousarray(pr["last_xw"], np.float32); lo = np.ascontiguousarray(pr["last_octave"], np.int32)
+        tc = np.ascontiguousarray(pr["tcw_cur"], np.float32); tl = np.ascontiguousarray(pr["tcw_last"], np.float32)
+        lib.match_oracle_project_last.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] +
+                                                  [C.c_float] * 10 + [C.c_void_p, C.c_float, C.c_int] + [C.c_void_p] * 7)
+        lib.match_oracle_project_last(_p(tc), _p(tl), nq, _p(xw), _p(lo), _p(qf), fx, fy, cx, cy, mbf, mb, mnx, mxx, mny, mxy,
+                                      _p(sf), float(pr["th"]), int(pr.get("mono", 0)), _p(qu), _p(qv), _p(qur), _p(qr),
+                                      _p(qmin), _p(qmax), _p(qfl))
+        use_ratio, chk = 0, int(pr.get("check_orientation", check_orientation))
+        qa = np.ascontiguousarray(pr["q_angle"], np.float32)
+    else:
+        qu, qv, qur, qr = [np.ascontiguousarray(pr[k], np.float32) for k in ("q_u", "q_v", "q_ur", "q_radius")]
+        qmin = np.ascontiguousarray(pr["q_min_level"], np.int32); qmax = np.ascontiguousarray(pr["q_max_level"], np.int32)
+        qfl = qf
+        use_ratio, chk = int(pr.get("use_ratio", 1)), int(pr.get("check_orientation", 0))
+        nn_ratio = float(pr.get("nn_ratio", nn_ratio))
+        qa = np.ascontiguousarray(pr["q_angle"], np.float32) if chk else np.zeros(nq, np.float32)
+    km = np.zeros(nk, np.int32); bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32)
+    lib.match_oracle_search_projection.restype = C.c_int
+    lib.match_oracle_search_projection.argtypes = ([C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_int] + [C.c_void_p] * 9 +
+                                                   [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 3)
+    n = lib.match_oracle_search_projection(_p(kps), _p(ur), _p(desc), _p(taken) if taken is not None else None, nk, mnx, mny,
+                                           inv_w, inv_h, nq, _p(qu), _p(qv), _p(qur), _p(qr), _p(qmin), _p(qmax), _p(qd), _p(qfl),
+                                           _p(qa), use_ratio, nn_ratio, chk, _p(km), _p(bi), _p(bd))
+    return int(n), km, bi, bd, dict(q_u=qu, q_v=qv, q_ur=qur, q_radius=qr, q_min_level=qmin, q_max_level=qmax, q_flags=qfl)
+
+
 def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, scale, mb: float, mbf: float, stage: int = 0):
     """Frame::ComputeStereoMatches restatement.  pyr_l / pyr_r: lists of level ROIs (u8 2-D).
     Returns (uRight, depth, ham_idx, ham_dist)."""

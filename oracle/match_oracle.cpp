@@ -190,3 +190,185 @@ extern "C" void match_oracle_distinctive(const uint8_t* desc, const int32_t* poi
         best_idx[p] = bestIdx;
     }
 }
+
+// =========================================================================================
+// Guided window searches: ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+// (src/ORBmatcher.cc:45-129) and ORBmatcher::SearchByProjection(Frame& Current, const Frame& Last,
+// th, bMono) (src/ORBmatcher.cc:1328-1470), on the Frame grid of src/Frame.cc:534-549, 645-712.
+// Both are the same loop: for every query (a map point with a predicted pixel, a window radius and a
+// level range) take the key-points of the 64 x 48 grid cells under the window in the reference's order
+// (cell column, cell row, insertion order), skip the ones already held by an observed map point, check
+// the right coordinate, keep best / second-best Hamming, accept, assign -- sequentially, so an earlier
+// query can take a key-point away from a later one.  The restatement keeps that sequential structure
+// (std::vector grid, one query after the other); the CUDA kernel reaches the same fixed point in parallel.
+namespace {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48, HISTO_LENGTH = 30;   // include/Frame.h:38-39, src/ORBmatcher.cc:39
+
+struct Grid {
+    std::vector<int> cell[GRID_COLS][GRID_ROWS];
+};
+
+// Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:534-549, 700-712)
+void assign_to_grid(const KeyPoint* kps, int n, float minX, float minY, float invW, float invH, Grid& g) {
+    for (int i = 0; i < n; ++i) {
+        const int px = (int)std::round((kps[i].x - minX) * invW);
+        const int py = (int)std::round((kps[i].y - minY) * invH);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+        g.cell[px][py].push_back(i);
+    }
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:645-698)
+void features_in_area(const Grid& g, const KeyPoint* kps, float minX, float minY, float invW, float invH, float x, float y,
+                      float r, int minLevel, int maxLevel, std::vector<int>& out) {
+    out.clear();
+    const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * invW));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * invH));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+            for (int idx : g.cell[ix][iy]) {
+                const KeyPoint& kp = kps[idx];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float distx = kp.x - x, disty = kp.y - y;
+                if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+            }
+}
+
+}  // namespace
+
+extern "C" {
+
+// q_flags: bit 0 = the query takes part (mbTrackInView && !isBad / has a map point && !outlier && in front && inside the
+// image), bit 1 = its map point has Observations() > 0 (a key-point it takes is closed to later queries).
+// taken[i] != 0: CurrentFrame.mvpMapPoints[i] is set on entry and has Observations() > 0.
+// use_ratio != 0: the map-point variant (second-best + same-level ratio rule, nn_ratio = mfNNratio);
+// check_ori != 0: the last-frame variant's rotation histogram (ComputeThreeMaxima, src/ORBmatcher.cc:1601-1642).
+// kp_match[i]: -1 untouched, -2 cleared by the rotation check, >= 0 the query that holds key-point i at the end.
+// Returns nmatches.
+int match_oracle_search_projection(const void* kps_, const float* u_right, const uint8_t* desc, const uint8_t* taken, int n_kp,
+                                   float minX, float minY, float invW, float invH, int n_q, const float* q_u, const float* q_v,
+                                   const float* q_ur, const float* q_radius, const int32_t* q_minl, const int32_t* q_maxl,
+                                   const uint8_t* q_desc, const uint8_t* q_flags, const float* q_angle, int use_ratio,
+                                   float nn_ratio, int check_ori, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist) {
+    const KeyPoint* kps = (const KeyPoint*)kps_;
+    Grid* g = new Grid();
+    assign_to_grid(kps, n_kp, minX, minY, invW, invH, *g);
+    std::vector<int> holder(n_kp, -1);          // query index written into mvpMapPoints[i] (-1: not written here)
+    std::vector<uint8_t> closed(n_kp, 0);       // mvpMapPoints[i] && Observations() > 0 right now
+    for (int i = 0; i < n_kp; ++i) closed[i] = taken ? (taken[i] != 0) : 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int q = 0; q < n_q; ++q) {
+        q_best_idx[q] = -1; q_best_dist[q] = 256;
+        if (!(q_flags[q] & 1)) continue;
+        features_in_area(*g, kps, minX, minY, invW, invH, q_u[q], q_v[q], q_radius[q], q_minl[q], q_maxl[q], cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (closed[idx]) continue;
+            if (u_right[idx] > 0) {
+                const float er = std::fabs(q_ur[q] - u_right[idx]);
+                if (er > q_radius[q]) continue;
+            }
+            const int dist = hamming256(q_desc + (size_t)q * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps[idx].octave; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = kps[idx].octave; bestDist2 = dist; }
+        }
+        q_best_idx[q] = bestIdx; q_best_dist[q] = bestDist;
+        if (bestDist <= TH_HIGH) {
+            if (use_ratio && bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) continue;
+            holder[bestIdx] = q;
+            closed[bestIdx] = (q_flags[q] & 2) != 0;
+            ++nmatches;
+            if (check_ori) {
+                float rot = q_angle[q] - kps[bestIdx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx);
+            }
+        }
+    }
+    for (int i = 0; i < n_kp; ++i) kp_match[i] = holder[i];
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { kp_match[idx] = -2; --nmatches; }
+    }
+    delete g;
+    return nmatches;
+}
+
+// The projection at the head of SearchByProjection(CurrentFrame, LastFrame) (src/ORBmatcher.cc:1338-1393): queries from
+// the last frame's map points.  cv::Mat arithmetic convention: Rcw * x + tcw is one cv::gemm, which accumulates float
+// products in double and rounds once (OpenCV GEMMSingleMul<float, double>); everything after it is float without
+// contraction.  tcw_cur / tcw_last: row-major 4x4 float Tcw.  last_flags bit 0: map point present and not an outlier,
+// bit 1: Observations() > 0.  Outputs the query arrays of match_oracle_search_projection.
+void match_oracle_project_last(const float* tcw_cur, const float* tcw_last, int n, const float* xw, const int32_t* octave,
+                               const uint8_t* last_flags, float fx, float fy, float cx, float cy, float mbf, float mb,
+                               float minX, float maxX, float minY, float maxY, const float* scale_factors, float th, int mono,
+                               float* q_u, float* q_v, float* q_ur, float* q_radius, int32_t* q_minl, int32_t* q_maxl,
+                               uint8_t* q_flags) {
+    auto R = [](const float* T, int r, int c) { return (double)T[4 * r + c]; };
+    // twc = -Rcw^T * tcw ; tlc = Rlw * twc + tlw
+    float twc[3], tlc[3];
+    for (int i = 0; i < 3; ++i) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += (-R(tcw_cur, k, i)) * R(tcw_cur, k, 3);   // (-Rcw.t()) is exact, then one gemm
+        twc[i] = (float)s;
+    }
+    for (int i = 0; i < 3; ++i) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += R(tcw_last, i, k) * (double)twc[k];
+        tlc[i] = (float)(s + R(tcw_last, i, 3));
+    }
+    const bool bForward = tlc[2] > mb && !mono, bBackward = -tlc[2] > mb && !mono;
+    for (int i = 0; i < n; ++i) {
+        q_u[i] = q_v[i] = q_ur[i] = q_radius[i] = 0.f; q_minl[i] = 0; q_maxl[i] = -1; q_flags[i] = 0;
+        if (!(last_flags[i] & 1)) continue;
+        float xc3[3];
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += R(tcw_cur, r, k) * (double)xw[3 * i + k];
+            xc3[r] = (float)(s + R(tcw_cur, r, 3));
+        }
+        const float xc = xc3[0], yc = xc3[1];
+        const float invzc = (float)(1.0 / (double)xc3[2]);
+        if (invzc < 0) continue;
+        const float u = fx * xc * invzc + cx, v = fy * yc * invzc + cy;
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        const int lo = octave[i];
+        q_u[i] = u; q_v[i] = v;
+        q_ur[i] = u - mbf * invzc;
+        q_radius[i] = th * scale_factors[lo];
+        if (bForward) { q_minl[i] = lo; q_maxl[i] = -1; }
+        else if (bBackward) { q_minl[i] = 0; q_maxl[i] = lo; }
+        else { q_minl[i] = lo - 1; q_maxl[i] = lo + 1; }
+        q_flags[i] = (uint8_t)(1 | (last_flags[i] & 2));
+    }
+}
+
+}  // extern "C"

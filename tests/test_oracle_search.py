@@ -1,0 +1,128 @@
+"""CPU pinning of the guided-search oracle (oracle/match_oracle.cpp: match_oracle_search_projection / _project_last,
+restating src/ORBmatcher.cc:45-129, 1328-1470 and src/Frame.cc:534-549, 645-712).  The reference ships no tests for these,
+so the restatement is checked against an independently written formulation: a flat candidate table sorted by
+(cell column, cell row, index) instead of the per-cell vectors, numpy float64 projection instead of the gemm emulation."""
+import numpy as np
+import pytest
+
+import oracle
+from airdos_b200 import synth
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    oracle.build()
+
+
+def _popcount(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def brute_force(pr, q, use_ratio, nn_ratio, check_ori):
+    kps = pr["kps"]; n_kp = len(kps)
+    mnx, mny, mxx, mxy = [np.float32(v) for v in pr["bounds"]]
+    iw = np.float32(64) / np.float32(mxx - mnx); ih = np.float32(48) / np.float32(mxy - mny)
+    px = np.floor((kps["x"] - mnx) * iw + np.float32(0.5)).astype(int)   # round half up == half away from zero for x >= 0
+    py = np.floor((kps["y"] - mny) * ih + np.float32(0.5)).astype(int)
+    ok = (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+    order = [i for i in np.lexsort((np.arange(n_kp), py, px)) if ok[i]]
+    closed = np.zeros(n_kp, bool) if pr.get("taken") is None else pr["taken"].astype(bool).copy()
+    holder = np.full(n_kp, -1); bins = {}
+    nm = 0
+    for j in range(len(q["q_flags"])):
+        if not q["q_flags"][j] & 1:
+            continue
+        x, y, r = q["q_u"][j], q["q_v"][j], q["q_radius"][j]
+        c0 = max(0, int(np.floor((x - mnx - r) * iw))); c1 = min(63, int(np.ceil((x - mnx + r) * iw)))
+        r0 = max(0, int(np.floor((y - mny - r) * ih))); r1 = min(47, int(np.ceil((y - mny + r) * ih)))
+        if c0 >= 64 or c1 < 0 or r0 >= 48 or r1 < 0:
+            continue
+        mn, mx = q["q_min_level"][j], q["q_max_level"][j]
+        cands = []
+        for i in order:
+            if not (c0 <= px[i] <= c1 and r0 <= py[i] <= r1):
+                continue
+            if (mn > 0 or mx >= 0) and (kps["octave"][i] < mn or (mx >= 0 and kps["octave"][i] > mx)):
+                continue
+            if abs(np.float32(kps["x"][i] - x)) < r and abs(np.float32(kps["y"][i] - y)) < r:
+                cands.append(i)
+        scored = []
+        for i in cands:
+            if closed[i]:
+                continue
+            if pr["u_right"][i] > 0 and abs(np.float32(q["q_ur"][j] - pr["u_right"][i])) > r:
+                continue
+            scored.append((_popcount(pr["q_desc"][j], pr["desc"][i]), len(scored), i))
+        if not scored:
+            continue
+        scored.sort()
+        d, _, i = scored[0]
+        if d > 100:
+            continue
+        if use_ratio and len(scored) > 1:
+            d2, _, i2 = scored[1]
+            if kps["octave"][i] == kps["octave"][i2] and np.float32(d) > np.float32(nn_ratio) * np.float32(d2):
+                continue
+        holder[i] = j; closed[i] = bool(q["q_flags"][j] & 2); nm += 1
+        if check_ori:
+            rot = np.float32(pr["q_angle"][j] - kps["angle"][i])
+            if rot < 0:
+                rot = np.float32(rot + np.float32(360))
+            b = int(np.floor(np.float32(rot * np.float32(1.0 / 30)) + np.float32(0.5)))
+            bins.setdefault(0 if b == 30 else b, []).append(i)
+    if check_ori:
+        sizes = sorted(((len(v), -k) for k, v in bins.items()), reverse=True)   # ties: lower bin first, as the scan does
+        keep = []
+        if sizes:
+            m1 = sizes[0][0]; keep.append(-sizes[0][1])
+            if len(sizes) > 1 and not sizes[1][0] < 0.1 * m1:
+                keep.append(-sizes[1][1])
+                if len(sizes) > 2 and not sizes[2][0] < 0.1 * m1:
+                    keep.append(-sizes[2][1])
+        for k, v in bins.items():
+            if k not in keep:
+                for i in v:
+                    holder[i] = -2; nm -= 1
+    return nm, holder
+
+
+@pytest.mark.parametrize("seed,dz", [(1, 0.02), (2, 0.6), (3, -0.6)])
+def test_last_frame_search_matches_brute_force(seed, dz):
+    pr = synth.make_tracking_problem(seed, n_kp=500, n_q=400, last_dz=dz)
+    n, km, bi, bd, proj = oracle.search_by_projection(pr)
+    nb, hb = brute_force(pr, proj, 0, 0.0, True)
+    assert n == nb and (km == hb).all()
+    assert n > 50 and (km == -2).sum() > 0
+
+
+def test_map_point_search_matches_brute_force():
+    pr = synth.make_tracking_problem(5, n_kp=600, n_q=500)
+    _, _, _, _, proj = oracle.search_by_projection(pr)
+    pm = synth.tracking_problem_as_map_points(pr, proj, nn_ratio=0.8)
+    n, km, bi, bd, _ = oracle.search_by_projection(pm)
+    nb, hb = brute_force(pm, pm, 1, 0.8, False)
+    assert n == nb and (km == hb).all() and n > 50
+
+
+def test_projection_matches_float64():
+    pr = synth.make_tracking_problem(7, n_kp=300, n_q=300)
+    _, _, _, _, q = oracle.search_by_projection(pr)
+    T = pr["tcw_cur"].astype(np.float64); fx, fy, cx, cy, mbf, mb = pr["cam"]
+    xc = pr["last_xw"].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    u = fx * xc[:, 0] / xc[:, 2] + cx; v = fy * xc[:, 1] / xc[:, 2] + cy
+    inside = (xc[:, 2] > 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480) & ((pr["q_flags"] & 1) != 0)
+    valid = (q["q_flags"] & 1) != 0
+    edge = (np.abs(u) < 1e-2) | (np.abs(u - 640) < 1e-2) | (np.abs(v) < 1e-2) | (np.abs(v - 480) < 1e-2)
+    assert (valid == inside)[~edge].all()
+    assert np.abs(q["q_u"][valid] - u[valid]).max() < 2e-3 and np.abs(q["q_v"][valid] - v[valid]).max() < 2e-3
+    assert np.abs(q["q_ur"][valid] - (u - mbf / xc[:, 2])[valid]).max() < 2e-3
+    assert (q["q_radius"][valid] == (np.float32(pr["th"]) * pr["scale_factors"][pr["last_octave"]])[valid]).all()
+
+
+def test_closure_order_matters():
+    """Two queries compete for one key-point: the first one (observed map point) closes it, the second takes its next best."""
+    pr = synth.make_tracking_problem(9, n_kp=400, n_q=300, dup_frac=0.4)
+    n, km, bi, bd, _ = oracle.search_by_projection(pr)
+    free = dict(pr); free["q_flags"] = (pr["q_flags"] & 1).astype(np.uint8)
+    n2, km2, bi2, _, _ = oracle.search_by_projection(free)
+    assert (bi != bi2).sum() > 5

@@ -1,0 +1,67 @@
+"""GPU parity tests of the guided window searches (airdos_b200/csrc/search.cu) against the oracle: final
+CurrentFrame.mvpMapPoints, nmatches, bestIdx / bestDist of every query -- all bit-exact, through the C-ABI."""
+import numpy as np
+import pytest
+
+from airdos_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def adb():
+    import airdos_b200
+    return airdos_b200
+
+
+def _same(got, ref):
+    n, km, bi, bd = got
+    rn, rkm, rbi, rbd = ref[:4]
+    assert n == rn, (n, rn)
+    assert (km == rkm).all(), np.nonzero(km != rkm)[0][:10]
+    assert (bi == rbi).all() and (bd == rbd).all()
+
+
+@pytest.mark.parametrize("seed,n_kp,n_q,dz", [(0, 2000, 1500, 0.02), (1, 2000, 2000, 0.6), (2, 1200, 1800, -0.6), (3, 4000, 3000, 0.02),
+                                               (4, 300, 50, 0.02)])
+def test_last_frame_search_matches_oracle(adb, oracle_mod, seed, n_kp, n_q, dz):
+    pr = synth.make_tracking_problem(seed, n_kp=n_kp, n_q=n_q, last_dz=dz, dup_frac=0.2)
+    m = adb.ORBmatcher(0.9, True)
+    ref = oracle_mod.search_by_projection(pr)
+    _same(m.SearchByProjection(pr), ref)
+    assert ref[0] > 20
+    # mono flag (no forward / backward rule) and the wider second pass of TrackWithMotionModel (2 * th)
+    pr2 = dict(pr); pr2["mono"] = 1; pr2["th"] = 2 * pr["th"]
+    _same(m.SearchByProjection(pr2), oracle_mod.search_by_projection(pr2))
+    m.close()
+
+
+def test_map_point_search_matches_oracle(adb, oracle_mod):
+    m = adb.ORBmatcher(0.8, True)
+    for seed in (10, 11):
+        pr = synth.make_tracking_problem(seed, n_kp=2000, n_q=2500, dup_frac=0.3)
+        proj = oracle_mod.search_by_projection(pr)[4]
+        pm = synth.tracking_problem_as_map_points(pr, proj, nn_ratio=0.8)
+        ref = oracle_mod.search_by_projection(pm)
+        _same(m.SearchByProjection(pm), ref)
+        assert ref[0] > 100
+    m.close()
+
+
+def test_search_batch_and_edge_cases(adb, oracle_mod):
+    m = adb.ORBmatcher(0.9, True)
+    probs = [synth.make_tracking_problem(20 + i, n_kp=500 + 300 * i, n_q=400 + 200 * i) for i in range(5)]
+    # everything closed on entry; no valid query; no orientation check
+    p_closed = dict(probs[0]); p_closed["taken"] = np.ones(len(p_closed["kps"]), np.uint8)
+    p_none = dict(probs[1]); p_none["q_flags"] = np.zeros_like(p_none["q_flags"])
+    p_noori = dict(probs[2]); p_noori["check_orientation"] = 0
+    p_notaken = dict(probs[3]); p_notaken["taken"] = None
+    probs += [p_closed, p_none, p_noori, p_notaken]
+    got = m.search_by_projection(probs)
+    for g, pr in zip(got, probs):
+        _same(g, oracle_mod.search_by_projection(pr))
+    assert got[5][0] == 0 and got[6][0] == 0
+    assert m.search_last_ms() > 0
+    # single calls give the same as the batch
+    _same(m.SearchByProjection(probs[4]), got[4])
+    m.close()
