@@ -17,6 +17,13 @@ def default_options() -> T.BAOptions:
     return o
 
 
+def global_options(n_iterations: int = 5, robust: bool = True) -> T.BAOptions:
+    """Constants of Optimizer::BundleAdjustment / GlobalBundleAdjustemnt (src/Optimizer.cc:52-230)."""
+    o = T.BAOptions()
+    lib().adb_ba_global_options(C.byref(o), n_iterations, int(robust))
+    return o
+
+
 def pose_from_tcw(tcw: np.ndarray):
     """Converter::toSE3Quat on a 4x4 float32 Tcw -> (q[x,y,z,w], t) float64."""
     tcw = np.ascontiguousarray(tcw, np.float32).reshape(16)
@@ -61,6 +68,13 @@ class Optimizer:
         if st not in (0, ERR_STOPPED):
             raise AdbError(st, lib().adb_last_error().decode(errors="replace"))
         return p, r, st
+
+    def GlobalBundleAdjustemnt(self, problem: dict, nIterations: int = 5, pbStopFlag: np.ndarray | None = None, bRobust: bool = True):
+        """Optimizer::GlobalBundleAdjustemnt / BundleAdjustment (src/Optimizer.cc:52-230; the reference's spelling): every
+        key-frame a pose (id 0 fixed), every map point marginalised, one round of nIterations."""
+        return self.LocalBundleAdjustment(problem, pbStopFlag, global_options(nIterations, bRobust))
+
+    BundleAdjustment = GlobalBundleAdjustemnt
 
     # the dynamic window is the same call: the human arrays of the problem dict switch it on
     LocalBundleAdjustmentHumanTrajactory = LocalBundleAdjustment

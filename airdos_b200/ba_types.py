@@ -25,7 +25,8 @@ class BAProblem(C.Structure):
 class BAOptions(C.Structure):
     _fields_ = [("iterations", C.c_int32 * 2), ("max_trials", C.c_int32), ("tau", C.c_double),
                 ("chi2_mono", C.c_double), ("chi2_stereo", C.c_double), ("chi2_rigid", C.c_double), ("chi2_motion", C.c_double),
-                ("huber_mono", C.c_double), ("huber_stereo", C.c_double), ("huber_rigid", C.c_double), ("huber_motion", C.c_double)]
+                ("huber_mono", C.c_double), ("huber_stereo", C.c_double), ("huber_rigid", C.c_double), ("huber_motion", C.c_double),
+                ("robust", C.c_int32 * 2)]
 
 
 class BAResult(C.Structure):

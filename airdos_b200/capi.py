@@ -89,6 +89,7 @@ SYMBOLS = {
     "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),
     "adb_stereo_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "adb_ba_default_options": (None, [_vp]),
+    "adb_ba_global_options": (None, [_vp, _i32, _i32]),
     "adb_ba_pose_from_tcw": (None, [_vp, _vp, _vp]),
     "adb_ba_pose_to_tcw": (None, [_vp, _vp, _vp]),
     "adb_ba_create": (C.c_int, [_i32, C.POINTER(_vp)]),

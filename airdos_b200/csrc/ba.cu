@@ -1506,6 +1506,14 @@ void adb_ba_default_options(adb_ba_options* o) {
     o->chi2_mono = 5.991; o->chi2_stereo = 7.815; o->chi2_rigid = 1.0; o->chi2_motion = 4.0;
     o->huber_mono = (double)(float)std::sqrt(5.991); o->huber_stereo = (double)(float)std::sqrt(7.815);
     o->huber_rigid = 1.0; o->huber_motion = (double)(float)std::sqrt(4.0);
+    o->robust[0] = 1; o->robust[1] = 0;
+}
+
+void adb_ba_global_options(adb_ba_options* o, int32_t n_iterations, int32_t robust) {
+    adb_ba_default_options(o);
+    o->iterations[0] = n_iterations; o->iterations[1] = 0;
+    o->huber_mono = (double)(float)std::sqrt(5.99);   // thHuber2D of BundleAdjustment (src/Optimizer.cc:84): 5.99, not 5.991
+    o->robust[0] = robust ? 1 : 0;
 }
 
 void adb_ba_pose_from_tcw(const float* T, double* q, double* t) {
@@ -1573,7 +1581,7 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
     if ((r = c.build_layout()) != ADB_OK) return r;
     auto t2 = now();
     double chi = 0;
-    if ((r = c.optimize(O->iterations[0], true, 0, &chi)) != ADB_OK) return r;
+    if ((r = c.optimize(O->iterations[0], O->robust[0] != 0, 0, &chi)) != ADB_OK) return r;
     auto t3 = now();
     if (timing) fprintf(stderr, "[adb_ba] upload %.2f ms, layout %.2f ms, round-1 optimise %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
     R->chi2_round[0] = chi;
@@ -1588,7 +1596,7 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
         for (size_t k = 0; k < fm.size(); ++k) if (fm[k]) c.lvl_m[k] = 1;
         // the dense layout may shrink: H offsets change, but the state buffers and chi2 arrays stay
         if ((r = c.build_layout()) != ADB_OK) return r;
-        if ((r = c.optimize(O->iterations[1], false, 1, &chi)) != ADB_OK) return r;
+        if ((r = c.optimize(O->iterations[1], O->robust[1] != 0, 1, &chi)) != ADB_OK) return r;
         R->chi2_round[1] = chi;
         if (c.stopped()) R->stopped = 1;
     }

@@ -164,6 +164,14 @@ public:
         airdos::check(st, "Optimizer::LocalBundleAdjustment");
         return true;
     }
+    // Optimizer::GlobalBundleAdjustemnt(pMap, nIterations, pbStopFlag, nLoopKF, bRobust) / BundleAdjustment
+    // (src/Optimizer.cc:52-230): all key-frames and map points, one round, no gating.
+    static bool GlobalBundleAdjustemnt(adb_ba_problem& problem, int nIterations, bool* pbStopFlag, bool bRobust, adb_ba_result& result,
+                                       int device = 0) {
+        adb_ba_options o;
+        adb_ba_global_options(&o, nIterations, bRobust ? 1 : 0);
+        return LocalBundleAdjustment(problem, pbStopFlag, result, &o, device);
+    }
     // LocalBundleAdjustmentHumanTrajactory(pKF, pbStopFlag, pMap, SigmaStatic, SigmaHuman, SigmaRigidity, SigmaMotion,
     // thRanSacMotion, thRanSacRigidity): the sigmas are the *_info arrays of the problem, the thresholds the options.
     static bool LocalBundleAdjustmentHumanTrajactory(adb_ba_problem& problem, bool* pbStopFlag, adb_ba_result& result, float thRanSacMotion,

@@ -356,6 +356,12 @@ def main():
             pass
         except Exception as e:   # the headline metric must still print
             out["ba"] = {"error": repr(e)}
+    if not args.no_ba and rank == 0:
+        try:
+            import bench_search
+            out["search"] = bench_search.run(local, steps=max(3, K // 2))
+        except Exception as e:
+            out["search"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out))
     exL.close(); exR.close()

@@ -323,6 +323,9 @@ typedef struct adb_ba_options {
     double chi2_rigid, chi2_motion;  /* thRanSacRigidity / thRanSacMotion gates (src/Optimizer.cc:2002,2011) */
     double huber_mono, huber_stereo; /* (float)sqrt(5.991), (float)sqrt(7.815) (src/Optimizer.cc:538-539) */
     double huber_rigid, huber_motion;/* thRanSacRigidity (not rooted, D.11), (float)sqrt(thRanSacMotion) */
+    int32_t robust[2];               /* Huber kernel on in round 1 / round 2: {1, 0} for the two local-BA functions
+                                        (src/Optimizer.cc:605-609, 660-665); Optimizer::BundleAdjustment(..., bRobust)
+                                        (src/Optimizer.cc:52-230) is one round with robust[0] = bRobust */
 } adb_ba_options;
 
 #define ADB_BA_TRACE_COLS 5          /* lambda, chi2 before, chi2 after, rho, accepted (0/1) per LM trial */
@@ -344,6 +347,11 @@ typedef struct adb_ba_result {
 } adb_ba_result;
 
 void adb_ba_default_options(adb_ba_options* opt);   /* the constants of Optimizer::LocalBundleAdjustment */
+/* The constants of Optimizer::BundleAdjustment / GlobalBundleAdjustemnt(pMap, nIterations, pbStopFlag, nLoopKF, bRobust)
+ * (src/Optimizer.cc:52-230): one round of nIterations, Huber deltas sqrt(5.99) / sqrt(7.815), no chi2 gating between
+ * rounds (outlier flags are still reported against 5.991 / 7.815 for the caller to ignore).  The problem is the same flat
+ * adb_ba_problem: every key-frame a pose (id 0 fixed), every map point a marginalised point. */
+void adb_ba_global_options(adb_ba_options* opt, int32_t n_iterations, int32_t robust);
 
 /* Converter::toSE3Quat (src/Converter.cc:37-47) / Converter::toCvMat(SE3Quat) (src/Converter.cc:74-82):
  * row-major 4x4 float Tcw <-> quaternion (x,y,z,w) + translation in double. */

@@ -316,6 +316,15 @@ def ba_default_options():
     return o
 
 
+def ba_global_options(n_iterations: int = 5, robust: bool = True):
+    from airdos_b200 import ba_types as T
+    o = T.BAOptions()
+    lib = ba_lib()
+    lib.ba_oracle_global_options.argtypes = [C.POINTER(T.BAOptions), C.c_int32, C.c_int32]
+    lib.ba_oracle_global_options(C.byref(o), n_iterations, int(robust))
+    return o
+
+
 def ba_solve(problem_dict: dict, options=None, stop: np.ndarray | None = None, trace_cap: int = 256):
     """Two-round LM on a copy of `problem_dict` -> (Problem with updated state, Result, status)."""
     from airdos_b200 import ba_types as T

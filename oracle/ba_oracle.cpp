@@ -599,6 +599,15 @@ void ba_oracle_default_options(adb_ba_options* o) {
     o->chi2_mono = 5.991; o->chi2_stereo = 7.815; o->chi2_rigid = 1.0; o->chi2_motion = 4.0;
     o->huber_mono = (double)(float)std::sqrt(5.991); o->huber_stereo = (double)(float)std::sqrt(7.815);
     o->huber_rigid = 1.0; o->huber_motion = (double)(float)std::sqrt(4.0);
+    o->robust[0] = 1; o->robust[1] = 0;
+}
+
+// Optimizer::BundleAdjustment (src/Optimizer.cc:52-230): one round, thHuber2D = sqrt(5.99), robust kernel by bRobust.
+void ba_oracle_global_options(adb_ba_options* o, int32_t n_iterations, int32_t robust) {
+    ba_oracle_default_options(o);
+    o->iterations[0] = n_iterations; o->iterations[1] = 0;
+    o->huber_mono = (double)(float)std::sqrt(5.99);
+    o->robust[0] = robust ? 1 : 0;
 }
 
 // Same contract as adb_ba_solve (include/airdos_b200.h).
@@ -607,7 +616,7 @@ int ba_oracle_solve(adb_ba_problem* prob, const adb_ba_options* opt, volatile co
     Solver S(*prob, *opt);
     res->iterations_run[0] = res->iterations_run[1] = 0; res->trials_run = 0; res->stopped = 0; res->trace_len = 0;
     res->chi2_initial = 0; res->chi2_round[0] = res->chi2_round[1] = 0;
-    S.robust = true;
+    S.robust = opt->robust[0] != 0;
     S.build_layout();
     double chi = 0;
     res->iterations_run[0] = S.optimize(opt->iterations[0], stop, res, &chi);
@@ -628,7 +637,7 @@ int ba_oracle_solve(adb_ba_problem* prob, const adb_ba_options* opt, volatile co
         }
         for (int e = 0; e < prob->n_rigid_edges; ++e) if (S.chi_r[e] > opt->chi2_rigid) S.lvl_r[e] = 1;
         for (int e = 0; e < prob->n_motion_edges; ++e) if (S.chi_m[e] > opt->chi2_motion) S.lvl_m[e] = 1;
-        S.robust = false;
+        S.robust = opt->robust[1] != 0;
         S.build_layout();
         res->iterations_run[1] = S.optimize(opt->iterations[1], stop, res, &chi);
         res->chi2_round[1] = chi;

@@ -110,3 +110,24 @@ def test_pose_optimization_matches_oracle(opt, oracle_mod):
     tiny = dict(frames[0]); tiny["xw"] = tiny["xw"][:2]; tiny["obs"] = tiny["obs"][:2]; tiny["inv_sigma2"] = tiny["inv_sigma2"][:2]
     g = opt.PoseOptimization(cam, [tiny, frames[1]])
     assert g.n_inliers[0] == 0 and (g.pose_t[0] == frames[0]["pose_t"]).all() and g.n_inliers[1] > 0
+
+
+@pytest.mark.parametrize("robust,its", [(True, 5), (False, 10)], ids=["robust5", "plain10"])
+def test_global_bundle_adjustment_matches_oracle(opt, oracle_mod, robust, its, tmp_path):
+    """Optimizer::GlobalBundleAdjustemnt / BundleAdjustment (src/Optimizer.cc:52-230): one round, bRobust on / off (loop
+    closing calls it with bRobust = false), on a window read back from the reference's own dump format."""
+    from airdos_b200 import ba, dump, synth
+    d = synth.make_ba_problem(12, 1500, 5, seed=77)
+    table, _ = dump.inv_sigma2_table()
+    d["edge_info"] = table[np.random.default_rng(1).integers(0, 8, len(d["edge_info"]))].astype(np.float64)
+    dump.save_map_dump(str(tmp_path), d)
+    g = dump.load_map_dump(str(tmp_path), {k: d[k] for k in ("fx", "fy", "cx", "cy", "bf")})
+    prob = {k: v for k, v in g.items() if k not in ("kf_ids", "mp_ids")}
+    pg, rg, sg = opt.GlobalBundleAdjustemnt(prob, its, bRobust=robust)
+    po, ro, so = oracle_mod.ba_solve(prob, oracle_mod.ba_global_options(its, robust))
+    assert sg == so == 0
+    assert rg.c.iterations_run[1] == 0 and list(rg.c.iterations_run) == list(ro.c.iterations_run)
+    assert np.abs(pg["pose_t"] - po["pose_t"]).max() < TOL_T and np.abs(pg["points"] - po["points"]).max() < 1e-3
+    assert rg.c.chi2_round[0] < rg.c.chi2_initial
+    o = ba.global_options(its, robust)
+    assert o.robust[0] == int(robust) and o.iterations[1] == 0 and abs(o.huber_mono - np.float32(np.sqrt(5.99))) < 1e-9
