@@ -35,11 +35,11 @@ namespace adb {
 __global__ void __launch_bounds__(128) pyr_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                          size_t sfstride, uint8_t* __restrict__ dst, int dw, int dh,
                                                          int dpitch, size_t dfstride, const int2* __restrict__ xtab,
-                                                         const int2* __restrict__ ytab) {
+                                                         const int2* __restrict__ ytab, int f0) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     if (x4 >= dw) return;
-    const int f = blockIdx.z;
+    const int f = blockIdx.z + f0;
     const int2 cy = __ldg(&ytab[y]);
     const int sy0 = cy.x, sy1 = min(sy0 + 1, sh - 1);
     const int b0 = cy.y & 0xFFFF, b1 = cy.y >> 16;
@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const uint8_t* __restri
 __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                                size_t sfstride, uint8_t* __restrict__ dst, int dw, int dh,
                                                                int dpitch, size_t dfstride, const int2* __restrict__ xtab,
-                                                               const int2* __restrict__ ytab, int nq, int rows, int nchunks) {
+                                                               const int2* __restrict__ ytab, int nq, int rows, int nchunks, int f0) {
     const int t = blockIdx.x * 128 + threadIdx.x;
     if (t >= nq * nchunks) return;
-    const int chunk = t / nq, q = t - chunk * nq, f = blockIdx.y;
+    const int chunk = t / nq, q = t - chunk * nq, f = blockIdx.y + f0;
     uint32_t sel[4], a0[4], a1[4];
     const int base = __ldg(&xtab[4 * q]).x;
 #pragma unroll
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
                                                                  const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
                                                                  int ini_th, int min_th, uint32_t* __restrict__ cand,
                                                                  int cand_total, uint16_t* __restrict__ cellcnt,
-                                                                 int ncells_total) {
+                                                                 int ncells_total, int f0) {
     __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kBW];
     __shared__ __align__(16) uint8_t score[kCellBoxHMax * kBW];
     __shared__ uint16_t clist[kDirect ? 1 : kMaxCorners];
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     __shared__ uint32_t klist[kMaxKeep];
     __shared__ int n_corner, n_keep, n_sel;
 
-    const int tid = threadIdx.x, f = blockIdx.y;
+    const int tid = threadIdx.x, f = blockIdx.y + f0;
     const uint32_t ce = __ldg(&cell_table[blockIdx.x]);
     const int level = ce >> 24, ci = (ce >> 12) & 0xFFF, cj = ce & 0xFFF;
     const LevelDev& L = levels[level];
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
                                                              uint32_t* __restrict__ qkeys, uint32_t* __restrict__ qstate,
                                                              int32_t* __restrict__ qcount, uint32_t* __restrict__ list,
                                                              int list_total, int32_t* __restrict__ listcnt, int maxa,
-                                                             int32_t* __restrict__ status) {
+                                                             int32_t* __restrict__ status, int f0) {
     extern __shared__ __align__(16) uint8_t qt_smem[];
     // carve dynamic shared memory
     short4* bnd0 = reinterpret_cast<short4*>(qt_smem);            // [2][maxa] node bounds ulx,uly,brx,bry
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
     __shared__ uint16_t suf[kQtSeqWords];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int level = blockIdx.x, f = blockIdx.y;
+    const int level = blockIdx.x, f = blockIdx.y + f0;
     const LevelDev& L = levels[level];
     const uint32_t* cslots = cand + (size_t)f * cand_total + L.cand_base;
     const uint16_t* ccnt = cellcnt + (size_t)f * ncells_total + L.cell_base;
@@ -747,12 +747,12 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
                                                                          adb_keypoint* __restrict__ kps,
                                                                          uint8_t* __restrict__ desc,
                                                                          int32_t* __restrict__ counts, int cap,
-                                                                         const __grid_constant__ adb_gather_targets gather) {
+                                                                         const __grid_constant__ adb_gather_targets gather, int f0) {
     extern __shared__ __align__(128) uint8_t desc_smem_raw[];
     // 128-B alignment for the TMA destinations; the offset is added to the shared array itself (not to a uintptr_t) so the
     // compiler keeps the shared address space: LDS / STS with 32-bit addresses instead of generic LD / ST
     DescSmem& sm = *reinterpret_cast<DescSmem*>(desc_smem_raw + ((128u - (smem_u32(desc_smem_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y + f0;
     for (int i = tid; i < 512; i += kDescWarps * 32) sm.pat[i] = make_char2(pattern[2 * i], pattern[2 * i + 1]);
     if (lane == 0) mbar_init(&sm.bar[warp], 1);
     if (tid == 0) mbar_fence_init();
@@ -960,6 +960,10 @@ static void free_handle(adb_orb* h) {
     for (auto& l : h->lv) {
         cudaFree(l.img); cudaFree(l.mask); cudaFree(l.xtab); cudaFree(l.ytab);
     }
+    if (h->copy_stream) {
+        cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->d2h_stream);
+        for (auto& e : h->cev) if (e) cudaEventDestroy(e);
+    }
     cudaFree(h->d_levels); cudaFree(h->d_cell_table); cudaFree(h->d_pattern); cudaFree(h->d_cand); cudaFree(h->d_cellcnt);
     cudaFree(h->d_qkeys); cudaFree(h->d_qstate); cudaFree(h->d_qcount); cudaFree(h->d_list); cudaFree(h->d_listcnt);
     cudaFree(h->d_status); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts);
@@ -1141,13 +1145,15 @@ static bool debug_sync() {
         }                                                                                    \
     } while (0)
 
-static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitch, size_t l0_fstride, bool masked) {
+// Per call: level-0 view and TMA maps over all `n_total` frames.  Then run_range launches the kernels for frames
+// [f0, f0 + n) -- the whole batch at once, or chunk by chunk behind the chunk's host-to-device copy.
+static adb_status run_range(adb_orb* h, int f0, int n, bool masked);
+static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitch, size_t l0_fstride, bool masked, bool launch = true) {
     cudaStream_t st = h->stream;
     const int nl = h->nlevels;
     h->l0_base = l0; h->l0_pitch = l0_pitch; h->l0_fstride = l0_fstride; h->have_mask = masked; h->last_frames = n;
     h->pev_n = 0;
     if (h->profiling) ADB_CUDA(cudaEventRecord(h->pev[h->pev_n++], st));
-    h->launches += (masked ? 2 : 1) * (nl - 1) + (h->ncells_total > 0 ? 1 : 0) + 2;
     {
         const LevelDev& d = h->lv[0].d;
         adb_status s = encode_tma_u8_3d(&h->cell_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, h->cell_box_w, d.box_h);
@@ -1162,6 +1168,14 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         ADB_CUDA(cudaMemcpyAsync(h->d_levels, &d0, sizeof(LevelDev), cudaMemcpyHostToDevice, st));
         h->lv[0].d = d0;
     }
+    return launch ? run_range(h, 0, n, masked) : ADB_OK;
+}
+
+static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
+    cudaStream_t st = h->stream;
+    const int nl = h->nlevels;
+    const uint8_t* l0 = h->l0_base;
+    h->launches += (masked ? 2 : 1) * (nl - 1) + (h->ncells_total > 0 ? 1 : 0) + 2;
     // ---- pyramid
     for (int l = 1; l < nl; ++l) {
         const LevelDev& s = h->lv[l - 1].d;
@@ -1174,18 +1188,18 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
             const int nchunks = (d.h + rows - 1) / rows;
             dim3 grid((nq * nchunks + 127) / 128, n);
             pyr_resize_strip_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
-                                                         d.frame_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks);
+                                                         d.frame_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0);
             if (masked)
                 pyr_resize_strip_kernel<<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w,
-                                                             d.h, d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks);
+                                                             d.h, d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0);
             continue;
         }
         dim3 grid((d.pitch / 4 + 127) / 128, d.h, n);
         pyr_resize_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
-                                               d.frame_stride, h->lv[l].xtab, h->lv[l].ytab);
+                                               d.frame_stride, h->lv[l].xtab, h->lv[l].ytab, f0);
         if (masked)
             pyr_resize_kernel<<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w, d.h,
-                                                   d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab);
+                                                   d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, f0);
     }
     ADB_STAGE("pyramid");
     // ---- FAST per cell
@@ -1200,7 +1214,7 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         auto kern = h->cell_box_w == 64 ? (two_phase ? fast_cells_kernel<false, 64> : fast_cells_kernel<true, 64>)
                                         : (two_phase ? fast_cells_kernel<false, kCellBoxWMax> : fast_cells_kernel<true, kCellBoxWMax>);
         kern<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
-                                            h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total);
+                                            h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, f0);
         ADB_STAGE("fast_cells");
     }
     // ---- quad-tree
@@ -1208,7 +1222,7 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         dim3 grid(nl, n);
         quadtree_kernel<<<grid, kQtThreads, h->qt_smem, st>>>(h->d_levels, nl, h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total,
                                                              h->d_qkeys, h->d_qstate, h->d_qcount, h->d_list, h->list_total,
-                                                             h->d_listcnt, h->qt_maxa, h->d_status);
+                                                             h->d_listcnt, h->qt_maxa, h->d_status, f0);
         ADB_STAGE("quadtree");
     }
     // ---- orientation + descriptors
@@ -1216,7 +1230,7 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         dim3 grid((h->capacity + kDescWarps - 1) / kDescWarps, n);
         orient_describe_kernel<<<grid, kDescWarps * 32, sizeof(DescSmem) + 128, st>>>(h->patch_maps, h->d_levels, nl, h->d_list, h->list_total,
                                                                                      h->d_listcnt, h->d_pattern, h->d_kps, h->d_desc,
-                                                                                     h->d_counts, h->capacity, h->gather);
+                                                                                     h->d_counts, h->capacity, h->gather, f0);
         ADB_STAGE("orient_describe");
     }
     return ADB_OK;
@@ -1359,23 +1373,75 @@ adb_status adb_orb_results_device(adb_orb_t h, const adb_keypoint** d_kps, const
     return ADB_OK;
 }
 
+// device -> host copies of the results of frames [first, first + n) on stream `st` (asynchronous)
+static adb_status download_async(adb_orb* h, int first, int n, adb_keypoint* kps, uint8_t* desc, int cap, int32_t* h_counts, cudaStream_t st) {
+    ADB_CUDA(cudaMemcpyAsync(h_counts, h->d_counts + first, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    const int rows = std::min(cap, h->capacity);
+    if (kps && rows > 0)
+        ADB_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(adb_keypoint), h->d_kps + (size_t)first * h->capacity,
+                                   (size_t)h->capacity * sizeof(adb_keypoint), (size_t)rows * sizeof(adb_keypoint), n, cudaMemcpyDeviceToHost, st));
+    if (desc && rows > 0)
+        ADB_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc + (size_t)first * h->capacity * 32, (size_t)h->capacity * 32,
+                                   (size_t)rows * 32, n, cudaMemcpyDeviceToHost, st));
+    return ADB_OK;
+}
+
 adb_status adb_orb_download(adb_orb_t h, int32_t first, int32_t n, adb_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* counts) {
     ADB_CHECK(h && counts, ADB_ERR_INVALID, "null argument");
     ADB_CHECK(first >= 0 && n >= 0 && first + n <= h->cfg.max_batch, ADB_ERR_INVALID, "bad frame range");
     ADB_CUDA(cudaSetDevice(h->cfg.device));
-    ADB_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts + first, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-    const int rows = std::min(cap, h->capacity);
-    if (kps && rows > 0)
-        ADB_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(adb_keypoint), h->d_kps + (size_t)first * h->capacity,
-                                   (size_t)h->capacity * sizeof(adb_keypoint), (size_t)rows * sizeof(adb_keypoint), n, cudaMemcpyDeviceToHost, h->stream));
-    if (desc && rows > 0)
-        ADB_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc + (size_t)first * h->capacity * 32, (size_t)h->capacity * 32,
-                                   (size_t)rows * 32, n, cudaMemcpyDeviceToHost, h->stream));
-    adb_status s = check_device_status(h);
+    adb_status s = download_async(h, first, n, kps, desc, cap, h->h_counts, h->stream);
+    if (s != ADB_OK) return s;
+    s = check_device_status(h);
     if (s != ADB_OK) return s;
     for (int i = 0; i < n; ++i) {
         counts[i] = h->h_counts[i];
         ADB_CHECK(counts[i] <= cap, ADB_ERR_CAPACITY, "frame %d holds %d key-points, caller capacity %d", first + i, counts[i], cap);
+    }
+    return ADB_OK;
+}
+
+// Large host batches run as a pipeline of chunks: the host-to-device copy of chunk c + 1 (copy stream), the kernels of chunk c
+// (handle stream) and the device-to-host copy of chunk c - 1's results (download stream) overlap, so the call costs about
+// max(upload, compute, download) instead of their sum.  Results are identical: chunking only changes the launch ranges.
+constexpr int kChunks = 4, kMinChunkedFrames = 32;
+
+static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images, size_t fstride, int w, int hh, int pitch,
+                                        adb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+    const int p0 = (w + 15) & ~15;
+    const size_t dfs = (size_t)p0 * hh;
+    if (!h->copy_stream) {
+        ADB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        ADB_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * kChunks + 1; ++i) ADB_CUDA(cudaEventCreateWithFlags(&h->cev[i], cudaEventDisableTiming));
+    }
+    // the upload must not overtake kernels of an earlier asynchronous call that still read the staging buffer
+    ADB_CUDA(cudaEventRecord(h->cev[2 * kChunks], h->stream));
+    ADB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->cev[2 * kChunks], 0));
+    adb_status s = run_pipeline(h, n, h->lv[0].img, p0, dfs, false, /*launch=*/false);
+    if (s != ADB_OK) return s;
+    const int per = (n + kChunks - 1) / kChunks;
+    int c = 0;
+    for (int f0 = 0; f0 < n; f0 += per, ++c) {
+        const int nc = std::min(per, n - f0);
+        s = copy_frames(h->lv[0].img + f0 * dfs, p0, dfs, images + f0 * fstride, pitch, fstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
+        if (s != ADB_OK) return s;
+        ADB_CUDA(cudaEventRecord(h->cev[c], h->copy_stream));
+        ADB_CUDA(cudaStreamWaitEvent(h->stream, h->cev[c], 0));
+        s = run_range(h, f0, nc, false);
+        if (s != ADB_OK) return s;
+        ADB_CUDA(cudaEventRecord(h->cev[kChunks + c], h->stream));
+        ADB_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->cev[kChunks + c], 0));
+        s = download_async(h, f0, nc, kps ? kps + (size_t)f0 * cap : nullptr, desc ? desc + (size_t)f0 * cap * 32 : nullptr, cap,
+                           h->h_counts + f0, h->d2h_stream);
+        if (s != ADB_OK) return s;
+    }
+    ADB_CUDA(cudaStreamSynchronize(h->d2h_stream));
+    s = check_device_status(h);
+    if (s != ADB_OK) return s;
+    for (int i = 0; i < n; ++i) {
+        counts[i] = h->h_counts[i];
+        ADB_CHECK(counts[i] <= cap, ADB_ERR_CAPACITY, "frame %d holds %d key-points, caller capacity %d", i, counts[i], cap);
     }
     return ADB_OK;
 }
@@ -1391,6 +1457,9 @@ adb_status adb_orb_extract_batch(adb_orb_t h, int32_t n, const uint8_t* images, 
     ADB_CHECK(n >= 1 && n <= h->cfg.max_batch, ADB_ERR_INVALID, "n_frames %d exceeds max_batch %d", n, h->cfg.max_batch);
     ADB_CHECK(w == h->cfg.width && hh == h->cfg.height && pitch >= w, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
     ADB_CUDA(cudaSetDevice(h->cfg.device));
+    static const bool no_chunks = getenv("ADB_NO_CHUNKS") != nullptr;   // measurement switch
+    if (n >= kMinChunkedFrames && !masks && !h->profiling && !no_chunks)
+        return extract_batch_chunked(h, n, images, fstride, w, hh, pitch, kps, desc, cap, counts);
     const int p0 = (w + 15) & ~15;
     adb_status s = copy_frames(h->lv[0].img, p0, (size_t)p0 * hh, images, pitch, fstride, w, hh, n, cudaMemcpyHostToDevice, h->stream);
     if (s != ADB_OK) return s;

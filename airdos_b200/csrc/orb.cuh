@@ -60,6 +60,8 @@ struct adb_orb {
     std::vector<float> sigma2, inv_sigma2;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // chunked host-buffer calls: upload / download streams
+    cudaEvent_t cev[9] = {};                                   // [0..3] chunk uploaded, [4..7] chunk computed, [8] entry fence
     adb::LevelDev* d_levels = nullptr;
     uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col
     int8_t* d_pattern = nullptr;        // [16][32][2] rBRIEF points, lane-major

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, int iters) {
@@ -26,6 +27,19 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, int iter
                 if (OP == 7) a[i] = __dp2a_lo(a[i], b, c);
                 if (OP == 8) a[i] = __dp4a(a[i], b, c);
                 if (OP == 9) a[i] = (uint32_t)max(min((int)a[i], (int)b), (int)c);  // VIMNMX3 scalar
+                if (OP == 11) { __half2 h = __hmin2(__hmin2(*(__half2*)&a[i], *(__half2*)&b), *(__half2*)&c); a[i] = *(uint32_t*)&h; }   // VHMNMX
+                if (OP == 12) { __half2 h = __hmin2(*(__half2*)&a[i], *(__half2*)&b); a[i] = *(uint32_t*)&h; }                             // HMNMX2
+                if (OP == 13) {   // VIMNMX3.U16x2 + VHMNMX alternating on independent chains
+                    if (i & 1) a[i] = __vimin3_u16x2(a[i], b, c);
+                    else { __half2 h = __hmin2(__hmin2(*(__half2*)&a[i], *(__half2*)&b), *(__half2*)&c); a[i] = *(uint32_t*)&h; }
+                }
+                if (OP == 14) {   // VIMNMX3.U16x2 + HMNMX2
+                    if (i & 1) a[i] = __vimin3_u16x2(a[i], b, c);
+                    else { __half2 h = __hmin2(*(__half2*)&a[i], *(__half2*)&b); a[i] = *(uint32_t*)&h; }
+                }
+                if (OP == 15) { if (i & 1) a[i] = __vimin3_u16x2(a[i], b, c); else a[i] = a[i] * b + c; }   // VIMNMX3 + IMAD
+                if (OP == 16) { float f = fminf(fminf(__uint_as_float(a[i]), __uint_as_float(b)), __uint_as_float(c)); a[i] = __float_as_uint(f); }   // FMNMX3
+                if (OP == 17) { if (i & 1) a[i] = __vimin3_u16x2(a[i], b, c); else a[i] = __vminu2(a[i], b); }   // VIMNMX3 + VIMNMX
                 if (OP == 10) { a[i] = a[i] * b + c; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[(i + 4) & 7]) : "r"(b), "r"(c)); }
             }
             b += c;
@@ -57,5 +71,7 @@ int main() {
     run<0>("VIMNMX3.U16x2", 1); run<1>("VIMNMX.U16x2", 1); run<2>("LOP3", 1); run<3>("IMAD", 1); run<4>("PRMT", 1);
     run<5>("SHF", 1); run<6>("VIMNMX.S32", 1); run<7>("IDP2A", 1); run<8>("IDP4A", 1); run<9>("VIMNMX3.S32(min,max)", 1);
     run<10>("IMAD+LOP3 mix", 2);
+    run<11>("VHMNMX (half2, 3 in)", 1); run<12>("HMNMX2", 1); run<13>("VIMNMX3+VHMNMX mix", 1); run<14>("VIMNMX3+HMNMX2 mix", 1);
+    run<15>("VIMNMX3+IMAD mix", 1); run<16>("FMNMX3", 1); run<17>("VIMNMX3+VIMNMX mix", 1);
     return 0;
 }
