@@ -171,23 +171,6 @@ __device__ __forceinline__ void load_ring_packed(const uint8_t* c, int bw, uint3
 #undef ADB_Q
 }
 
-// Corner test at threshold t for both polarities at once.  a = (0x8000 + v - t - 1) | (0x8000 - v - t - 1) << 16 puts
-// "v - q > t" into bit 15 and "q - v > t" into bit 31 of x_i; a run of 9 set flags = AND over 9 consecutive words,
-// built from 3-input ANDs (40 LOP3 for all 16 arcs).
-__device__ __forceinline__ uint32_t fast_corner_a(int v, int t) {
-    return (uint32_t)(0x8000 + v - t - 1) | ((uint32_t)(0x8000 - v - t - 1) << 16);
-}
-__device__ __forceinline__ bool fast_is_corner(const uint32_t (&x)[16]) {
-    uint32_t a3[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a3[i] = x[i] & x[(i + 1) & 15] & x[(i + 2) & 15];
-    uint32_t any = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i += 2)
-        any |= (a3[i] & a3[(i + 3) & 15] & a3[(i + 6) & 15]) | (a3[i + 1] & a3[(i + 4) & 15] & a3[(i + 7) & 15]);
-    return (any & 0x80008000u) != 0;
-}
-
 // Exact score: max over the 16 arcs of 9 of min(v - q) and of min(q - v) (cv::cornerScore<16>), again both
 // polarities at once: a = (256 + v) | (256 - v) << 16 makes the lanes 256 + d and 256 - d, and the arc minima / the
 // final maximum are packed 3-input min / max (VIMNMX3.U16x2): 40 of them per pixel.
@@ -209,17 +192,16 @@ __device__ __forceinline__ int fast_best(const uint32_t (&x)[16]) {
 
 constexpr int kFastThreads = 256;
 constexpr int kMaxKeep = 1152;      // >= ceil(75 / 2) * ceil(60 / 2): strict 3x3 NMS keeps at most one pixel per 2x2 block
-constexpr int kMaxCorners = 4608;   // >= inner pixels of the largest supported cell (75 x 60)
 
 // Phases per (cell, frame) CTA, each a dense loop (no divergent heavy branch):
 //   1 exact FAST score of every pixel of the cell (packed, branch free); a corner at min(iniTh, minTh) keeps
-//     score - 1 in the score tile, everything else 0
-//     [kDirect == false, measurement variant: packed corner test -> corner list -> exact score of the listed corners]
+//     score - 1 in the score tile, everything else 0.  (A packed LOP3 corner test costs the same 40 alu-pipe slots as the
+//     score itself, so "test first, score the corners" was measured slower: 0.80 vs 0.75 ms per 128 frames.)
 //   3 strict 3x3 NMS + mask post-filter of the corners -> unordered kept list
 //   4 ini / min rule, then each kept corner's rank in row-major order places it in the cell's slot
 // kBW = pitch of the TMA box in shared memory (one value per handle), a compile-time constant so that the 16 ring
 // loads are immediate offsets from one address register.
-template <bool kDirect, int kBW>
+template <int kBW>
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                  const LevelDev* __restrict__ levels,
                                                                  const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
@@ -228,10 +210,9 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
                                                                  int ncells_total, int f0) {
     __shared__ __align__(128) uint8_t tile[kCellBoxHMax * kBW];
     __shared__ __align__(16) uint8_t score[kCellBoxHMax * kBW];
-    __shared__ uint16_t clist[kDirect ? 1 : kMaxCorners];
     __shared__ uint64_t bar;
     __shared__ uint32_t klist[kMaxKeep];
-    __shared__ int n_corner, n_keep, n_sel;
+    __shared__ int n_keep, n_sel;
 
     const int tid = threadIdx.x, f = blockIdx.y + f0;
     const uint32_t ce = __ldg(&cell_table[blockIdx.x]);
@@ -249,7 +230,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     constexpr int bw = kBW;
     const int bh = L.box_h;
     if (tid == 0) {
-        n_corner = 0; n_keep = 0; n_sel = 0;
+        n_keep = 0; n_sel = 0;
         mbar_init(&bar, 1);
         mbar_fence_init();
         fence_proxy_async();
@@ -266,55 +247,28 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)iw + 1u;   // p / iw == umulhi(p, rcp) for p < 65536
     const int t_low = min(ini_th, min_th);
 
-    // ---- phase 1 (+ 2)
-    if (kDirect) {
-        for (int p = tid; p < npx; p += kFastThreads) {
-            const int y0 = (int)__umulhi((uint32_t)p, rcp);
-            const int o = (y0 + 3) * bw + (p - y0 * iw + 3);
-            const uint8_t* c = tile + o + dx;
-            uint32_t ring[16];
-            load_ring_packed(c, bw, fast_score_a(c[0]), ring);
-            const int best = fast_best(ring);
-            score[o] = (uint8_t)(best > t_low ? best - 1 : 0);   // response = best - 1 (>= 1 for every corner)
-        }
-        __syncthreads();
-    } else {
-        for (int p = tid; p < npx; p += kFastThreads) {
-            const int y0 = (int)__umulhi((uint32_t)p, rcp);
-            const uint8_t* c = tile + (y0 + 3) * bw + (p - y0 * iw + 3) + dx;
-            uint32_t ring[16];
-            load_ring_packed(c, bw, fast_corner_a(c[0], t_low), ring);
-            if (fast_is_corner(ring)) {
-                const int slot = atomicAdd(&n_corner, 1);
-                if (slot < kMaxCorners) clist[slot] = (uint16_t)p;
-            }
-        }
-        __syncthreads();
-        const int nc = min(n_corner, kMaxCorners);
-        for (int i = tid; i < nc; i += kFastThreads) {
-            const int p = clist[i];
-            const int y0 = (int)__umulhi((uint32_t)p, rcp);
-            const int o = (y0 + 3) * bw + (p - y0 * iw + 3);
-            const uint8_t* c = tile + o + dx;
-            uint32_t ring[16];
-            load_ring_packed(c, bw, fast_score_a(c[0]), ring);
-            score[o] = (uint8_t)(fast_best(ring) - 1);
-        }
-        __syncthreads();
+    // ---- phase 1
+    for (int p = tid; p < npx; p += kFastThreads) {
+        const int y0 = (int)__umulhi((uint32_t)p, rcp);
+        const int o = (y0 + 3) * bw + (p - y0 * iw + 3);
+        const uint8_t* c = tile + o + dx;
+        uint32_t ring[16];
+        load_ring_packed(c, bw, fast_score_a(c[0]), ring);
+        const int best = fast_best(ring);
+        score[o] = (uint8_t)(best > t_low ? best - 1 : 0);   // response = best - 1 (>= 1 for every corner)
     }
+    __syncthreads();
 
     // ---- phase 3: NMS + mask for the corners -> unordered kept list (p | score << 16 | flags << 24;
     //      flag bit 0: kept at minTh, bit 1: kept at iniTh)
     const uint8_t* ml = masks.p[level];
     int mineB = 0;
-    const int n3 = kDirect ? npx : min(n_corner, kMaxCorners);
-    for (int i = tid; i < n3; i += kFastThreads) {
-        const int p = kDirect ? i : (int)clist[i];
+    for (int p = tid; p < npx; p += kFastThreads) {
         const int y0 = (int)__umulhi((uint32_t)p, rcp);
         const int y = y0 + 3, x = p - y0 * iw + 3;
         const uint8_t* s = score + y * bw + x;
         const int v = s[0];
-        if (kDirect && v == 0) continue;
+        if (v == 0) continue;
         bool keep = v > s[-1] && v > s[1] && v > s[-bw - 1] && v > s[-bw] && v > s[-bw + 1] && v > s[bw - 1] && v > s[bw] && v > s[bw + 1];
         if (keep && ml) keep = ml[(size_t)f * L.mframe_stride + (size_t)(iniY + y) * L.mpitch + iniX + x] != 0;
         const int fl = keep ? ((v >= min_th ? 1 : 0) | (v >= ini_th ? 2 : 0)) : 0;
@@ -735,9 +689,16 @@ constexpr int kVPitchW = 26;            // 32-bit words per row of the column-pa
 struct DescSmem {
     uint8_t raw[kDescWarps][kRawBytes];               // 43 x 64 B patch; reused for the blurred 37 x 37 core (pitch kBPitch)
     uint32_t vert[kDescWarps][37 * kVPitchW];         // column pass: 37 rows x 48 u16
-    char2 pat[16 * 32];
+    uint32_t ic_wu[16][8];                            // IC_Angle row tables by |v|: signed weights u of word k (0 outside the disc)
+    uint32_t ic_m[16][8];                             // ... and the disc mask as 0 / 1 bytes
     uint64_t bar[kDescWarps];
 };
+
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c) {   // sum of unsigned bytes of a times signed bytes of b
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                          const LevelDev* __restrict__ levels, int nlevels,
@@ -753,7 +714,17 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     // compiler keeps the shared address space: LDS / STS with 32-bit addresses instead of generic LD / ST
     DescSmem& sm = *reinterpret_cast<DescSmem*>(desc_smem_raw + ((128u - (smem_u32(desc_smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y + f0;
-    for (int i = tid; i < 512; i += kDescWarps * 32) sm.pat[i] = make_char2(pattern[2 * i], pattern[2 * i + 1]);
+    if (tid < 128) {   // one table entry per thread: word k of rows +-av covers u = -15 + 4k .. -12 + 4k
+        const int av = tid >> 3, k = tid & 7;
+        const int lim = c_umax[av];
+        uint32_t wu = 0, m = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int u = -15 + 4 * k + b;
+            if (u <= 15 && abs(u) <= lim) { wu |= (uint32_t)(u & 0xFF) << (8 * b); m |= 1u << (8 * b); }
+        }
+        sm.ic_wu[av][k] = wu; sm.ic_m[av][k] = m;
+    }
     if (lane == 0) mbar_init(&sm.bar[warp], 1);
     if (tid == 0) mbar_fence_init();
     __syncthreads();
@@ -806,16 +777,22 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     }
 
     // ---- IC_Angle (src/ORBextractor.cc:78-105): m10 = sum u*I, m01 = sum v*I over the r=15 disc
+    // a lane owns word k of four rows at a time (8 lanes per row: the 64-B row pitch would put all rows of a lane-per-row
+    // mapping on two banks); the funnel shift lines the word up with u = -15 + 4k, and two DP4A give its share of
+    // sum(u * I) (signed weights, zero outside the disc) and of sum(I) (0 / 1 mask); m01 = sum over rows of v * sum(I).
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - 15, au = abs(u);
-        const uint8_t* col = raw + kPatchR * kPatchBoxW + kPatchR + u;
+    {
+        const int k = lane & 7, rsub = lane >> 3;
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw0 + (kPatchR - 15) * kPatchBoxW) + ((dxp + 6) >> 2) + k;
+        const uint32_t s8 = (uint32_t)((dxp + 6) & 3) * 8u;
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) {
-            if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = col[v * kPatchBoxW];
-                m10 += u * val;
-                m01 += v * val;
+        for (int it = 0; it < 8; ++it) {
+            const int row = 4 * it + rsub;          // v + 15
+            if (row < 31) {
+                const uint32_t d = __funnelshift_r(rw[row * (kPatchBoxW / 4)], rw[row * (kPatchBoxW / 4) + 1], s8);
+                const int av = abs(row - 15);
+                m10 = dp4a_u8_s8(d, sm.ic_wu[av][k], m10);
+                m01 += (row - 15) * (int)__dp4a(d, sm.ic_m[av][k], 0u);
             }
         }
     }
@@ -896,10 +873,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
     const uint8_t* ctr = bl + 18 * kBPitch + 18;
+    const char2* pat2 = reinterpret_cast<const char2*>(pattern);
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const char2 p0 = sm.pat[(2 * k) * 32 + lane], p1 = sm.pat[(2 * k + 1) * 32 + lane];
+        const char2 p0 = __ldg(pat2 + (2 * k) * 32 + lane), p1 = __ldg(pat2 + (2 * k + 1) * 32 + lane);   // 1 KB, L1 resident
         const float x0f = (float)p0.x, y0f = (float)p0.y, x1f = (float)p1.x, y1f = (float)p1.y;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0f, b), __fmul_rn(y0f, a)));
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0f, a), __fmul_rn(y0f, b)));
@@ -1210,9 +1188,7 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
 #endif
     if (h->ncells_total > 0) {
         dim3 grid(h->ncells_total, n);
-        static const bool two_phase = getenv("ADB_FAST_TWO_PHASE") != nullptr;   // measurement switch: test first, score the corners
-        auto kern = h->cell_box_w == 64 ? (two_phase ? fast_cells_kernel<false, 64> : fast_cells_kernel<true, 64>)
-                                        : (two_phase ? fast_cells_kernel<false, kCellBoxWMax> : fast_cells_kernel<true, kCellBoxWMax>);
+        auto kern = h->cell_box_w == 64 ? fast_cells_kernel<64> : fast_cells_kernel<kCellBoxWMax>;
         kern<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
                                             h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, f0);
         ADB_STAGE("fast_cells");
