@@ -48,6 +48,9 @@ class ProjSearch(C.Structure):
                 ("last_xw", C.c_void_p), ("last_octave", C.c_void_p), ("tcw_cur", C.c_void_p), ("tcw_last", C.c_void_p),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float), ("mb", C.c_float),
                 ("scale_factors", C.c_void_p), ("n_levels", C.c_int32), ("th", C.c_float), ("mono", C.c_int32),
+                ("mp_xw", C.c_void_p), ("mp_normal", C.c_void_p), ("mp_min_distance", C.c_void_p), ("mp_max_distance", C.c_void_p),
+                ("ow", C.c_void_p), ("view_cos_limit", C.c_float), ("log_scale_factor", C.c_float),
+                ("q_track", C.c_void_p), ("q_level", C.c_void_p),
                 ("kp_match", C.c_void_p), ("q_best_idx", C.c_void_p), ("q_best_dist", C.c_void_p), ("n_matches", C.c_int32)]
 
 

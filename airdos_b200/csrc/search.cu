@@ -49,6 +49,12 @@ struct SearchDev {
     float fx, fy, cx, cy, mbf, th;
     const float* scale_factors;
     int forward, backward;
+    // visibility test (variant 1 with Frame::isInFrustum on the device)
+    const float* mp_xw; const float* mp_normal; const float* mp_min_distance; const float* mp_max_distance; const uint8_t* mp_flags;
+    float ow[3], Tcw[12];
+    float view_cos_limit, log_scale_factor;
+    int n_levels;
+    float* q_track; int32_t* q_level;
     // results
     int32_t* kp_match; int32_t* q_best_idx; int32_t* q_best_dist; int32_t* q_choice; int32_t* n_matches;
 };
@@ -89,6 +95,57 @@ __global__ void project_last_kernel(const SearchDev* __restrict__ probs) {
         }
     }
     P.q_u[i] = u; P.q_v[i] = v; P.q_ur[i] = ur; P.q_radius[i] = rad; P.q_minl[i] = minl; P.q_maxl[i] = maxl; P.q_flags[i] = fl;
+}
+
+// Frame::isInFrustum + MapPoint::PredictScale + the window radius of SearchByProjection(F, vpMapPoints, th); conventions as in
+// oracle/match_oracle.cpp (match_oracle_frustum): gemm / norm / dot in double with one rounding, log in double rounded once.
+__global__ void frustum_kernel(const SearchDev* __restrict__ probs) {
+    const SearchDev& P = probs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!P.mp_xw || i >= P.n_q) return;
+    float u = 0.f, v = 0.f, ur = 0.f, rad = 0.f, vc = 0.f;
+    int minl = 0, maxl = -1, level = -1;
+    uint8_t fl = 0;
+    const uint8_t inf = P.mp_flags[i];
+    if (inf & 1) {
+        const float px = P.mp_xw[3 * i], py = P.mp_xw[3 * i + 1], pz = P.mp_xw[3 * i + 2];
+        float c[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double s = __dmul_rn((double)P.Tcw[4 * r], (double)px);
+            s = __dadd_rn(s, __dmul_rn((double)P.Tcw[4 * r + 1], (double)py));
+            s = __dadd_rn(s, __dmul_rn((double)P.Tcw[4 * r + 2], (double)pz));
+            c[r] = (float)__dadd_rn(s, (double)P.Tcw[4 * r + 3]);
+        }
+        bool ok = !(c[2] < 0.0f);
+        const float invz = __fdiv_rn(1.0f, c[2]);
+        const float uu = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c[0]), invz), P.cx);
+        const float vv = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c[1]), invz), P.cy);
+        ok = ok && !(uu < P.min_x || uu > P.max_x) && !(vv < P.min_y || vv > P.max_y);
+        const float maxD = __fmul_rn(1.2f, P.mp_max_distance[i]), minD = __fmul_rn(0.8f, P.mp_min_distance[i]);
+        const float ox = __fsub_rn(px, P.ow[0]), oy = __fsub_rn(py, P.ow[1]), oz = __fsub_rn(pz, P.ow[2]);
+        const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)ox), __dmul_rn((double)oy, (double)oy)), __dmul_rn((double)oz, (double)oz));
+        const float dist = (float)__dsqrt_rn(n2);
+        ok = ok && !(dist < minD || dist > maxD);
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)P.mp_normal[3 * i]), __dmul_rn((double)oy, (double)P.mp_normal[3 * i + 1])),
+                                     __dmul_rn((double)oz, (double)P.mp_normal[3 * i + 2]));
+        const float viewCos = (float)__ddiv_rn(dot, (double)dist);
+        ok = ok && !(viewCos < P.view_cos_limit);
+        if (ok) {
+            const float ratio = __fdiv_rn(P.mp_max_distance[i], dist);
+            int ns = (int)ceilf(__fdiv_rn((float)log((double)ratio), P.log_scale_factor));
+            if (ns < 0) ns = 0; else if (ns >= P.n_levels) ns = P.n_levels - 1;
+            float r = (double)viewCos > 0.998 ? 2.5f : 4.0f;
+            if (P.th != 1.0f) r = __fmul_rn(r, P.th);
+            u = uu; v = vv; ur = __fsub_rn(uu, __fmul_rn(P.mbf, invz)); vc = viewCos;
+            rad = __fmul_rn(r, P.scale_factors[ns]);
+            minl = ns - 1; maxl = ns; level = ns;
+            fl = (uint8_t)(1 | (inf & 2));
+        }
+    }
+    P.q_u[i] = u; P.q_v[i] = v; P.q_ur[i] = ur; P.q_radius[i] = rad; P.q_minl[i] = minl; P.q_maxl[i] = maxl; P.q_flags[i] = fl;
+    P.q_track[4 * i] = u; P.q_track[4 * i + 1] = v; P.q_track[4 * i + 2] = ur; P.q_track[4 * i + 3] = vc;
+    P.q_level[i] = level;
 }
 
 // 64-bit search key: distance << 43 | cell sequence << 31 | position in cell << 18 | key-point index << 5 | octave.
@@ -353,8 +410,11 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
         ADB_CHECK(s.kp_match || s.n_kp == 0, ADB_ERR_INVALID, "problem %d: kp_match is NULL", p);
         ADB_CHECK(s.n_kp == 0 || (s.kps && s.u_right && s.desc), ADB_ERR_INVALID, "problem %d: frame arrays missing", p);
         ADB_CHECK(s.n_q == 0 || (s.q_flags && s.q_desc), ADB_ERR_INVALID, "problem %d: query arrays missing", p);
-        ADB_CHECK(s.n_q == 0 || s.last_xw || (s.q_u && s.q_v && s.q_ur && s.q_radius && s.q_min_level && s.q_max_level),
-                  ADB_ERR_INVALID, "problem %d: neither projected queries nor last-frame points given", p);
+        ADB_CHECK(s.n_q == 0 || s.last_xw || s.mp_xw || (s.q_u && s.q_v && s.q_ur && s.q_radius && s.q_min_level && s.q_max_level),
+                  ADB_ERR_INVALID, "problem %d: neither projected queries nor last-frame / map points given", p);
+        ADB_CHECK(!(s.last_xw && s.mp_xw), ADB_ERR_INVALID, "problem %d: last-frame and map-point projection are exclusive", p);
+        ADB_CHECK(!s.mp_xw || (s.mp_normal && s.mp_min_distance && s.mp_max_distance && s.ow && s.tcw_cur && s.scale_factors && s.n_levels > 0),
+                  ADB_ERR_INVALID, "problem %d: map-point visibility inputs missing", p);
         ADB_CHECK(!s.last_xw || (s.last_octave && s.tcw_cur && s.tcw_last && s.scale_factors && s.n_levels > 0), ADB_ERR_INVALID,
                   "problem %d: last-frame projection inputs missing", p);
         ADB_CHECK(!s.check_orientation || s.q_angle, ADB_ERR_INVALID, "problem %d: q_angle missing", p);
@@ -375,7 +435,7 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
             D.kps = pk.put(s.kps, s.n_kp); D.u_right = pk.put(s.u_right, s.n_kp); D.desc = pk.put(s.desc, (size_t)s.n_kp * 32);
             D.taken = s.taken ? pk.put(s.taken, s.n_kp) : nullptr;
             D.min_x = s.min_x; D.min_y = s.min_y; D.max_x = s.max_x; D.max_y = s.max_y; D.inv_w = s.grid_inv_w; D.inv_h = s.grid_inv_h;
-            const bool proj = s.last_xw != nullptr;
+            const bool proj = s.last_xw != nullptr || s.mp_xw != nullptr;
             D.q_u = pk.put(proj ? nullptr : s.q_u, s.n_q); D.q_v = pk.put(proj ? nullptr : s.q_v, s.n_q);
             D.q_ur = pk.put(proj ? nullptr : s.q_ur, s.n_q); D.q_radius = pk.put(proj ? nullptr : s.q_radius, s.n_q);
             D.q_minl = pk.put(proj ? nullptr : s.q_min_level, s.n_q); D.q_maxl = pk.put(proj ? nullptr : s.q_max_level, s.n_q);
@@ -383,7 +443,16 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
             D.q_desc = pk.put(s.q_desc, (size_t)s.n_q * 32);
             D.q_angle = s.check_orientation ? pk.put(s.q_angle, s.n_q) : nullptr;
             D.use_ratio = s.use_ratio; D.nn_ratio = s.nn_ratio; D.check_ori = s.check_orientation;
-            if (proj) {
+            if (s.mp_xw) {
+                D.mp_xw = pk.put(s.mp_xw, (size_t)s.n_q * 3); D.mp_normal = pk.put(s.mp_normal, (size_t)s.n_q * 3);
+                D.mp_min_distance = pk.put(s.mp_min_distance, s.n_q); D.mp_max_distance = pk.put(s.mp_max_distance, s.n_q);
+                D.mp_flags = pk.put(s.q_flags, s.n_q);
+                D.scale_factors = pk.put(s.scale_factors, s.n_levels);
+                for (int k = 0; k < 12; ++k) D.Tcw[k] = s.tcw_cur[k];
+                for (int k = 0; k < 3; ++k) D.ow[k] = s.ow[k];
+                D.fx = s.fx; D.fy = s.fy; D.cx = s.cx; D.cy = s.cy; D.mbf = s.mbf; D.th = s.th;
+                D.view_cos_limit = s.view_cos_limit; D.log_scale_factor = s.log_scale_factor; D.n_levels = s.n_levels;
+            } else if (proj) {
                 D.last_xw = pk.put(s.last_xw, (size_t)s.n_q * 3); D.last_octave = pk.put(s.last_octave, s.n_q);
                 D.last_flags = pk.put(s.q_flags, s.n_q);
                 D.scale_factors = pk.put(s.scale_factors, s.n_levels);
@@ -417,6 +486,8 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
             D.q_best_dist = pk.put((const int32_t*)nullptr, s.n_q);
             D.q_choice = pk.put((const int32_t*)nullptr, s.n_q);
             D.n_matches = pk.put((const int32_t*)nullptr, 1);
+            D.q_track = pk.put((const float*)nullptr, (size_t)s.n_q * 4);
+            D.q_level = pk.put((const int32_t*)nullptr, s.n_q);
         }
         total = pk.reserve(0);
         if (pass == 0 && total > m->scratch_bytes) {
@@ -446,6 +517,12 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
         dim3 grid((max_nq + 255) / 256, n);
         project_last_kernel<<<grid, 256, 0, m->stream>>>(dprobs);
     }
+    bool any_mp = false;
+    for (int p = 0; p < n; ++p) any_mp |= probs[p].mp_xw != nullptr;
+    if (any_mp && max_nq > 0) {
+        dim3 grid((max_nq + 255) / 256, n);
+        frustum_kernel<<<grid, 256, 0, m->stream>>>(dprobs);
+    }
     proj_search_kernel<<<n, kSearchThreads, smem, m->stream>>>(dprobs);
     ADB_CUDA(cudaGetLastError());
     ADB_CUDA(cudaEventRecord(m->ev[1], m->stream));
@@ -460,6 +537,8 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
         if (s.q_best_idx && s.n_q) memcpy(s.q_best_idx, host(D.q_best_idx), (size_t)s.n_q * 4);
         if (s.q_best_dist && s.n_q) memcpy(s.q_best_dist, host(D.q_best_dist), (size_t)s.n_q * 4);
         memcpy(&s.n_matches, host(D.n_matches), 4);
+        if (s.mp_xw && s.q_track && s.n_q) memcpy(s.q_track, host(D.q_track), (size_t)s.n_q * 16);
+        if (s.mp_xw && s.q_level && s.n_q) memcpy(s.q_level, host(D.q_level), (size_t)s.n_q * 4);
     }
     return ADB_OK;
 }

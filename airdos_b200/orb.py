@@ -224,7 +224,11 @@ class ORBmatcher:
         `q_radius`, `q_min_level`, `q_max_level`, `q_flags`, `q_desc`; SearchByProjection(F, vpMapPoints, th),
         src/ORBmatcher.cc:45-129) or the last frame (`last_xw`, `last_octave`, `q_flags`, `q_desc`, `q_angle`, `tcw_cur`,
         `tcw_last`, `cam` = (fx, fy, cx, cy, mbf, mb), `scale_factors`, `th`, `mono`; SearchByProjection(Current, Last, th,
-        bMono), src/ORBmatcher.cc:1328-1470).  Returns a list of (nmatches, kp_match, q_best_idx, q_best_dist)."""
+        bMono), src/ORBmatcher.cc:1328-1470) or the local map points before the visibility test (`mp_xw`, `mp_normal`,
+        `mp_min_distance`, `mp_max_distance`, `ow`, `tcw_cur`, `cam`, `scale_factors`, `log_scale_factor`, `th`; Frame::isInFrustum
+        + SearchByProjection as Tracking::SearchLocalPoints runs them, src/Tracking.cc:1319-1343; two more outputs: q_track
+        [n_q, 4] = mTrackProjX / Y / XR / ViewCos and q_level = mnTrackScaleLevel or -1).
+        Returns a list of (nmatches, kp_match, q_best_idx, q_best_dist[, q_track, q_level])."""
         from .capi import ProjSearch
         n = len(problems)
         arr = (ProjSearch * n)()
@@ -246,7 +250,20 @@ class ORBmatcher:
             S.grid_inv_h = np.float32(48) / np.float32(mxy - mny)
             S.n_q = len(pr["q_flags"])
             S.q_flags = a(pr["q_flags"], np.uint8); S.q_desc = a(pr["q_desc"], np.uint8)
-            if "last_xw" in pr:
+            track = level = None
+            if "mp_xw" in pr:      # variant 1 with Frame::isInFrustum on the device
+                S.mp_xw = a(pr["mp_xw"], np.float32); S.mp_normal = a(pr["mp_normal"], np.float32)
+                S.mp_min_distance = a(pr["mp_min_distance"], np.float32); S.mp_max_distance = a(pr["mp_max_distance"], np.float32)
+                S.ow = a(pr["ow"], np.float32); S.tcw_cur = a(pr["tcw_cur"], np.float32)
+                S.fx, S.fy, S.cx, S.cy, S.mbf, S.mb = [float(v) for v in pr["cam"]]
+                sf = np.ascontiguousarray(pr["scale_factors"], np.float32); keep.append(sf)
+                S.scale_factors = sf.ctypes.data; S.n_levels = len(sf)
+                S.th = float(pr.get("th", 1.0)); S.view_cos_limit = float(pr.get("view_cos_limit", 0.5))
+                S.log_scale_factor = float(pr["log_scale_factor"])
+                S.use_ratio = int(pr.get("use_ratio", 1)); S.nn_ratio = float(pr.get("nn_ratio", self.mfNNratio)); S.check_orientation = 0
+                track = np.zeros((S.n_q, 4), np.float32); level = np.full(S.n_q, -1, np.int32); keep += [track, level]
+                S.q_track, S.q_level = track.ctypes.data, level.ctypes.data
+            elif "last_xw" in pr:
                 S.last_xw = a(pr["last_xw"], np.float32); S.last_octave = a(pr["last_octave"], np.int32)
                 S.tcw_cur = a(pr["tcw_cur"], np.float32); S.tcw_last = a(pr["tcw_last"], np.float32)
                 S.fx, S.fy, S.cx, S.cy, S.mbf, S.mb = [float(v) for v in pr["cam"]]
@@ -265,7 +282,7 @@ class ORBmatcher:
                     S.q_angle = a(pr["q_angle"], np.float32)
             km = np.full(S.n_kp, -1, np.int32); bi = np.full(S.n_q, -1, np.int32); bd = np.full(S.n_q, 256, np.int32)
             S.kp_match, S.q_best_idx, S.q_best_dist = km.ctypes.data, bi.ctypes.data, bd.ctypes.data
-            outs.append((km, bi, bd))
+            outs.append((km, bi, bd) if track is None else (km, bi, bd, track, level))
         check(lib().adb_search_by_projection(self._m, C.byref(arr), n))
         return [(int(arr[i].n_matches),) + outs[i] for i in range(n)]
 

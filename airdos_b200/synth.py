@@ -371,3 +371,30 @@ def tracking_problem_as_map_points(pr: dict, proj: dict, nn_ratio: float = 0.8) 
     out.update(q_u=proj["q_u"], q_v=proj["q_v"], q_ur=proj["q_ur"], q_radius=proj["q_radius"], q_min_level=(lvl - 1).astype(np.int32),
                q_max_level=lvl.copy(), q_flags=proj["q_flags"], use_ratio=1, nn_ratio=nn_ratio, check_orientation=0)
     return out
+
+
+def tracking_problem_as_local_map(pr: dict, seed: int = 0, nn_ratio: float = 0.8, th: float = 1.0) -> dict:
+    """The same scene as Tracking::SearchLocalPoints sees it (src/Tracking.cc:1319-1343): local map points BEFORE the
+    visibility test -- world position, mean viewing direction, scale-invariance distances -- so Frame::isInFrustum,
+    MapPoint::PredictScale and SearchByProjection(F, vpMapPoints, th) all run behind the C-ABI.  A fifth of the points
+    fails one of the tests (wrong side, out of the distance range, oblique view)."""
+    rng = np.random.default_rng(seed + 77)
+    out = {k: pr[k] for k in ("kps", "u_right", "desc", "taken", "bounds", "q_desc", "tcw_cur", "cam", "scale_factors")}
+    T = pr["tcw_cur"].astype(np.float64)
+    ow = -T[:3, :3].T @ T[:3, 3]
+    xw = pr["last_xw"].astype(np.float64)
+    po = xw - ow
+    dist = np.linalg.norm(po, axis=1)
+    normal = po / dist[:, None] + rng.normal(0, 0.15, po.shape)
+    oblique = rng.random(len(xw)) < 0.07
+    normal[oblique] = rng.normal(0, 1, (int(oblique.sum()), 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    lvl = np.asarray(pr["last_octave"], np.float64)
+    max_d = dist * 1.2 ** lvl * rng.uniform(0.9, 1.1, len(xw))           # PredictScale then lands near the source octave
+    min_d = max_d / 1.2 ** 7
+    far = rng.random(len(xw)) < 0.07
+    max_d[far] = dist[far] * 0.5
+    out.update(mp_xw=xw.astype(np.float32), mp_normal=normal.astype(np.float32), mp_min_distance=min_d.astype(np.float32),
+               mp_max_distance=max_d.astype(np.float32), ow=ow.astype(np.float32), q_flags=pr["q_flags"].copy(),
+               log_scale_factor=float(np.log(np.float32(1.2))), th=th, nn_ratio=nn_ratio, use_ratio=1, view_cos_limit=0.5)
+    return out

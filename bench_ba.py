@@ -81,3 +81,7 @@ def run(device: int = 0, steps: int = 5, with_cpu: bool = True, n_kf: int = 50, 
                                "sample": f"the same window, 10 LM iterations, oracle port on 1 host thread ({t10 * 1e3:.0f} ms; 5+10 schedule {t_full * 1e3:.0f} ms)"}
     opt.close()
     return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(run()))

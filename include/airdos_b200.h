@@ -230,6 +230,20 @@ typedef struct adb_proj_search {
     int32_t n_levels;
     float th;
     int32_t mono;                  /* bMono */
+    /* queries, variant 1 with the visibility test on the device: when mp_xw != NULL the library runs Frame::isInFrustum
+     * (src/Frame.cc:587-643) + MapPoint::PredictScale (src/MapPoint.cc:405-420) on every map point whose q_flags bit 0 is
+     * set (= the point reached the test in Tracking::SearchLocalPoints, src/Tracking.cc:1319-1331) and builds the queries
+     * from the result: q_u .. q_max_level are ignored, radius = RadiusByViewingCos(viewCos) [* th if th != 1] *
+     * mvScaleFactors[level] (src/ORBmatcher.cc:55-69).  Uses tcw_cur, fx .. mbf, scale_factors, n_levels, th from above. */
+    const float* mp_xw;            /* [n_q][3] GetWorldPos() */
+    const float* mp_normal;        /* [n_q][3] GetNormal() */
+    const float* mp_min_distance;  /* [n_q] mfMinDistance (the test uses 0.8f * it) */
+    const float* mp_max_distance;  /* [n_q] mfMaxDistance (the test uses 1.2f * it, PredictScale the raw value) */
+    const float* ow;               /* [3] Frame::mOw */
+    float view_cos_limit;          /* 0.5 */
+    float log_scale_factor;        /* Frame::mfLogScaleFactor */
+    float* q_track;                /* optional out [n_q][4]: mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos (0 when not in view) */
+    int32_t* q_level;              /* optional out [n_q]: mnTrackScaleLevel, -1 = mbTrackInView false */
     /* results */
     int32_t* kp_match;             /* [n_kp] CurrentFrame.mvpMapPoints after the call: -1 untouched, -2 set to NULL by the rotation
                                       check, >= 0 index of the query (map point) now held */

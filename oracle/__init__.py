@@ -224,7 +224,25 @@ def search_by_projection(pr: dict, nn_ratio: float = 0.6, check_orientation: boo
     inv_w = np.float32(64) / np.float32(mxx - mnx); inv_h = np.float32(48) / np.float32(mxy - mny)
     qf = np.ascontiguousarray(pr["q_flags"], np.uint8); qd = np.ascontiguousarray(pr["q_desc"], np.uint8)
     nq, nk = len(qf), len(kps)
-    if "last_xw" in pr:
+    extra = {}
+    if "mp_xw" in pr:
+        qu = np.zeros(nq, np.float32); qv = np.zeros(nq, np.float32); qur = np.zeros(nq, np.float32); qr = np.zeros(nq, np.float32)
+        qmin = np.zeros(nq, np.int32); qmax = np.zeros(nq, np.int32); qfl = np.zeros(nq, np.uint8)
+        track = np.zeros((nq, 4), np.float32); level = np.zeros(nq, np.int32)
+        fx, fy, cx, cy, mbf, mb = [float(v) for v in pr["cam"]]
+        sf = np.ascontiguousarray(pr["scale_factors"], np.float32)
+        arrs = [np.ascontiguousarray(pr[k], np.float32) for k in ("tcw_cur", "ow", "mp_xw", "mp_normal", "mp_min_distance", "mp_max_distance")]
+        lib.match_oracle_frustum.argtypes = ([C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_float] * 11 +
+                                             [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 9)
+        lib.match_oracle_frustum(_p(arrs[0]), _p(arrs[1]), nq, _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), _p(qf), fx, fy, cx, cy,
+                                 mbf, mnx, mxx, mny, mxy, float(pr.get("view_cos_limit", 0.5)), float(pr["log_scale_factor"]), _p(sf),
+                                 len(sf), float(pr.get("th", 1.0)), _p(qu), _p(qv), _p(qur), _p(qr), _p(qmin), _p(qmax), _p(qfl),
+                                 _p(track), _p(level))
+        use_ratio, chk = int(pr.get("use_ratio", 1)), 0
+        nn_ratio = float(pr.get("nn_ratio", nn_ratio))
+        qa = np.zeros(nq, np.float32)
+        extra = dict(q_track=track, q_level=level)
+    elif "last_xw" in pr:
         qu = np.zeros(nq, np.float32); qv = np.zeros(nq, np.float32); qur = np.zeros(nq, np.float32); qr = np.zeros(nq, np.float32)
         qmin = np.zeros(nq, np.int32); qmax = np.zeros(nq, np.int32); qfl = np.zeros(nq, np.uint8)
         fx, fy, cx, cy, mbf, mb = [float(v) for v in pr["cam"]]
@@ -252,7 +270,7 @@ def search_by_projection(pr: dict, nn_ratio: float = 0.6, check_orientation: boo
     n = lib.match_oracle_search_projection(_p(kps), _p(ur), _p(desc), _p(taken) if taken is not None else None, nk, mnx, mny,
                                            inv_w, inv_h, nq, _p(qu), _p(qv), _p(qur), _p(qr), _p(qmin), _p(qmax), _p(qd), _p(qfl),
                                            _p(qa), use_ratio, nn_ratio, chk, _p(km), _p(bi), _p(bd))
-    return int(n), km, bi, bd, dict(q_u=qu, q_v=qv, q_ur=qur, q_radius=qr, q_min_level=qmin, q_max_level=qmax, q_flags=qfl)
+    return int(n), km, bi, bd, dict(q_u=qu, q_v=qv, q_ur=qur, q_radius=qr, q_min_level=qmin, q_max_level=qmax, q_flags=qfl, **extra)
 
 
 def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, scale, mb: float, mbf: float, stage: int = 0):

@@ -371,4 +371,52 @@ void match_oracle_project_last(const float* tcw_cur, const float* tcw_last, int 
     }
 }
 
+// Frame::isInFrustum (src/Frame.cc:587-643) + MapPoint::PredictScale (src/MapPoint.cc:405-420) + the window radius of
+// SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:55-69) -> the query arrays.  cv::Mat conventions: Rcw * P + tcw is
+// one gemm (double accumulation, one rounding); P - Ow is float; cv::norm and Mat::dot accumulate in double.  The log of
+// PredictScale is evaluated in double on the float ratio and rounded once (the reference's unqualified log() may bind to
+// either overload, and libm / CUDA logf differ in the last bit).  in_flags bit 0: the point reaches the test.
+void match_oracle_frustum(const float* tcw, const float* ow, int n, const float* xw, const float* normal, const float* min_distance,
+                          const float* max_distance, const uint8_t* in_flags, float fx, float fy, float cx, float cy, float mbf,
+                          float minX, float maxX, float minY, float maxY, float view_cos_limit, float log_scale_factor,
+                          const float* scale_factors, int n_levels, float th, float* q_u, float* q_v, float* q_ur, float* q_radius,
+                          int32_t* q_minl, int32_t* q_maxl, uint8_t* q_flags, float* q_track, int32_t* q_level) {
+    for (int i = 0; i < n; ++i) {
+        q_u[i] = q_v[i] = q_ur[i] = q_radius[i] = 0.f; q_minl[i] = 0; q_maxl[i] = -1; q_flags[i] = 0;
+        q_level[i] = -1; for (int k = 0; k < 4; ++k) q_track[4 * i + k] = 0.f;
+        if (!(in_flags[i] & 1)) continue;
+        const float* P = xw + 3 * i;
+        float Pc[3];
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += (double)tcw[4 * r + k] * (double)P[k];
+            Pc[r] = (float)(s + (double)tcw[4 * r + 3]);
+        }
+        if (Pc[2] < 0.0f) continue;
+        const float invz = 1.0f / Pc[2];
+        const float u = fx * Pc[0] * invz + cx, v = fy * Pc[1] * invz + cy;
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        const float maxD = 1.2f * max_distance[i], minD = 0.8f * min_distance[i];
+        const float PO[3] = {P[0] - ow[0], P[1] - ow[1], P[2] - ow[2]};
+        const float dist = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        if (dist < minD || dist > maxD) continue;
+        const float* Pn = normal + 3 * i;
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
+        const float viewCos = (float)(dot / (double)dist);
+        if (viewCos < view_cos_limit) continue;
+        const float ratio = max_distance[i] / dist;
+        int nScale = (int)std::ceil((float)std::log((double)ratio) / log_scale_factor);
+        if (nScale < 0) nScale = 0; else if (nScale >= n_levels) nScale = n_levels - 1;
+        float r = (double)viewCos > 0.998 ? 2.5f : 4.0f;   // RadiusByViewingCos compares against a double literal
+        if (th != 1.0f) r *= th;
+        q_u[i] = u; q_v[i] = v; q_ur[i] = u - mbf * invz;
+        q_radius[i] = r * scale_factors[nScale];
+        q_minl[i] = nScale - 1; q_maxl[i] = nScale;
+        q_flags[i] = (uint8_t)(1 | (in_flags[i] & 2));
+        q_track[4 * i] = u; q_track[4 * i + 1] = v; q_track[4 * i + 2] = q_ur[i]; q_track[4 * i + 3] = viewCos;
+        q_level[i] = nScale;
+    }
+}
+
 }  // extern "C"

@@ -126,3 +126,33 @@ def test_closure_order_matters():
     free = dict(pr); free["q_flags"] = (pr["q_flags"] & 1).astype(np.uint8)
     n2, km2, bi2, _, _ = oracle.search_by_projection(free)
     assert (bi != bi2).sum() > 5
+
+
+def test_frustum_matches_float64_and_feeds_the_search():
+    """Frame::isInFrustum + PredictScale restatement vs plain float64 numpy; the search then equals the brute force."""
+    pr = synth.make_tracking_problem(11, n_kp=400, n_q=400)
+    pm = synth.tracking_problem_as_local_map(pr, seed=3)
+    n, km, bi, bd, q = oracle.search_by_projection(pm)
+    T = pm["tcw_cur"].astype(np.float64); fx, fy, cx, cy, mbf, mb = pm["cam"]
+    X = pm["mp_xw"].astype(np.float64)
+    pc = X @ T[:3, :3].T + T[:3, 3]
+    u = fx * pc[:, 0] / pc[:, 2] + cx; v = fy * pc[:, 1] / pc[:, 2] + cy
+    po = X - pm["ow"].astype(np.float64); dist = np.linalg.norm(po, axis=1)
+    vc = (po * pm["mp_normal"]).sum(1) / dist
+    ok = ((pm["q_flags"] & 1) != 0) & (pc[:, 2] >= 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480)
+    ok &= (dist >= 0.8 * pm["mp_min_distance"]) & (dist <= 1.2 * pm["mp_max_distance"]) & (vc >= 0.5)
+    lvl = np.clip(np.ceil(np.log(pm["mp_max_distance"] / dist) / pm["log_scale_factor"]), 0, 7).astype(int)
+    got = q["q_level"] >= 0
+    # float32 vs float64 only differ right at a threshold: allow a handful of border cases, none elsewhere
+    margin = (np.minimum.reduce([np.abs(u), np.abs(u - 640), np.abs(v), np.abs(v - 480)]) < 1e-2) | (np.abs(vc - 0.5) < 1e-5) | \
+             (np.abs(dist / (1.2 * pm["mp_max_distance"]) - 1) < 1e-5) | (np.abs(dist / (0.8 * pm["mp_min_distance"]) - 1) < 1e-5)
+    assert (got == ok)[~margin].all() and got.sum() > 200
+    frac = np.log(pm["mp_max_distance"] / dist) / pm["log_scale_factor"]
+    near_int = np.abs(frac - np.rint(frac)) < 1e-4
+    sel = got & ~near_int
+    assert (q["q_level"][sel] == lvl[sel]).all()
+    assert np.abs(q["q_track"][got, 0] - u[got]).max() < 2e-3 and np.abs(q["q_track"][got, 3] - vc[got]).max() < 1e-5
+    r = np.where(q["q_track"][got, 3].astype(np.float64) > 0.998, 2.5, 4.0).astype(np.float32)
+    assert (q["q_radius"][got] == r * pm["scale_factors"][q["q_level"][got]]).all()
+    nb, hb = brute_force(pm, q, 1, 0.8, False)
+    assert n == nb and (km == hb).all() and n > 50

@@ -65,3 +65,18 @@ def test_search_batch_and_edge_cases(adb, oracle_mod):
     # single calls give the same as the batch
     _same(m.SearchByProjection(probs[4]), got[4])
     m.close()
+
+
+@pytest.mark.parametrize("seed,th", [(30, 1.0), (31, 5.0)])
+def test_local_map_search_with_frustum_on_device(adb, oracle_mod, seed, th):
+    """Tracking::SearchLocalPoints: isInFrustum + PredictScale + SearchByProjection(F, vpMapPoints, th) behind one call."""
+    pr = synth.make_tracking_problem(seed, n_kp=2000, n_q=3000, dup_frac=0.25)
+    pm = synth.tracking_problem_as_local_map(pr, seed=seed, th=th)
+    m = adb.ORBmatcher(0.8, True)
+    ref = oracle_mod.search_by_projection(pm)
+    got = m.SearchByProjection(pm)
+    _same(got[:4], ref)
+    assert (got[5] == ref[4]["q_level"]).all()
+    assert (got[4].view(np.uint32) == ref[4]["q_track"].view(np.uint32)).all()     # float outputs by bit pattern
+    assert ref[0] > 100 and (ref[4]["q_level"] >= 0).sum() > 1000
+    m.close()
