@@ -880,12 +880,12 @@ constexpr int kCholNB = 32;
 // n = matrix order (columns), n_rows >= n: rows n..n_rows-1 are extra right-hand-side rows carried through the factorisation
 // (row n = b^T turns into y^T = (L^-1 b)^T, i.e. the forward substitution comes for free).  pitch = n.
 constexpr int kCholThreads = 512;   // 16 warps: thread (r, c) owns elements (r, c) and (r + 16, c) of the 32 x 32 tiles
-__global__ void __launch_bounds__(kCholThreads) chol_left_kernel(double* __restrict__ A, int n, int n_rows, int kb, double* __restrict__ Ldiag,
-                                                                int* __restrict__ info) {
+__device__ __forceinline__ void chol_panel(double* A, int n, int n_rows, int kb, int ib, double* Ldiag, int* info) {
     __shared__ double Ta[kCholNB][kCholNB + 1], Tb[kCholNB][kCholNB + 1];   // operand tiles, then U and D / L
     __shared__ double col[kCholNB];                                          // 1 / L[j][j]
     const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;                 // r in 0..15
-    const int k = kb * kCholNB, ib = kb + blockIdx.x, i0 = ib * kCholNB;
+    const int k = kb * kCholNB, i0 = ib * kCholNB;
+    const bool diag_cta = ib == kb;
     const int nbk = min(kCholNB, n - k);
     double accU[2] = {0.0, 0.0}, accD[2] = {0.0, 0.0};
     // software-pipelined tile loads: the next tiles are fetched while the current ones are multiplied
@@ -935,7 +935,8 @@ __global__ void __launch_bounds__(kCholThreads) chol_left_kernel(double* __restr
         for (int j = 0; j < kCholNB; ++j) {
             double d = __shfl_sync(0xFFFFFFFFu, row[j], j);
             if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-            const double sd = sqrt(d), isd = 1.0 / sd;
+            // the 32 pivots are the serial spine of the whole solve: one rsqrt (MUFU.RSQ64H + Newton) instead of sqrt + divide
+            const double isd = rsqrt(d), sd = d * isd;
             double v = 0.0;
             if (lane == j) { row[j] = sd; col[j] = isd; }
             else if (lane > j) { v = row[j] * isd; row[j] = v; }
@@ -945,32 +946,39 @@ __global__ void __launch_bounds__(kCholThreads) chol_left_kernel(double* __restr
                 if (lane >= q) row[q] -= v * vq;
             }
         }
-        if (bad && lane == 0 && blockIdx.x == 0 && *info == 0) *info = k + 1;
+        if (bad && lane == 0 && diag_cta && *info == 0) *info = k + 1;
 #pragma unroll
         for (int q = 0; q < kCholNB; ++q) Tb[lane][q] = q <= lane ? row[q] : 0.0;
     }
     __syncthreads();
     // the diagonal block's CTA publishes the factor (A keeps the unfactored block: nobody reads it again); of its rows only
     // the extra right-hand-side rows (>= n) that share the row block still need the triangular solve
-    if (blockIdx.x == 0) { Ldiag[(size_t)kb * kCholNB * kCholNB + tid] = Tb[r][c]; Ldiag[(size_t)kb * kCholNB * kCholNB + tid + 512] = Tb[r + 16][c]; }
-    // ---- x L_kk^T = u: a warp owns rows r and r + 16, lane c holds x[c]; right-looking, no block barriers
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        double x = u[h];
+    if (diag_cta) { Ldiag[(size_t)kb * kCholNB * kCholNB + tid] = Tb[r][c]; Ldiag[(size_t)kb * kCholNB * kCholNB + tid + 512] = Tb[r + 16][c]; }
+    // ---- x L_kk^T = u: a warp owns rows r and r + 16 (solved together: two independent dependency chains), lane c holds
+    //      x[c]; right-looking, no block barriers
+    {
+        double x0 = u[0], x1 = u[1];
 #pragma unroll
         for (int j = 0; j < kCholNB; ++j) {
-            const double xj = __shfl_sync(0xFFFFFFFFu, x, j) * col[j];
-            if (c == j) x = xj;
-            if (c > j) x -= xj * Tb[c][j];
+            const double cj = col[j], l = Tb[c][j];
+            const double a0 = __shfl_sync(0xFFFFFFFFu, x0, j) * cj, a1 = __shfl_sync(0xFFFFFFFFu, x1, j) * cj;
+            if (c == j) { x0 = a0; x1 = a1; }
+            if (c > j) { x0 -= a0 * l; x1 -= a1 * l; }
         }
-        const int rr = r + 16 * h;
-        if (i0 + rr < n_rows && c < nbk && (blockIdx.x > 0 || i0 + rr >= n)) A[(size_t)(i0 + rr) * n + k + c] = x;
+        if (i0 + r < n_rows && c < nbk && (!diag_cta || i0 + r >= n)) A[(size_t)(i0 + r) * n + k + c] = x0;
+        if (i0 + r + 16 < n_rows && c < nbk && (!diag_cta || i0 + r + 16 >= n)) A[(size_t)(i0 + r + 16) * n + k + c] = x1;
     }
+}
+
+__global__ void __launch_bounds__(kCholThreads) chol_left_kernel(double* __restrict__ A, int n, int n_rows, int kb, double* __restrict__ Ldiag,
+                                                                int* __restrict__ info) {
+    chol_panel(A, n, n_rows, kb, kb + blockIdx.x, Ldiag, info);
 }
 
 // backward substitution L^T x = y, y = row n of the factored array; x -> out.  One CTA, 32-wide blocks.  Every block step
 // first stages its diagonal factor in shared memory (one coalesced load) so that the 32 serial pivots never wait on L2.
-__global__ void __launch_bounds__(1024) chol_back_kernel(const double* __restrict__ A, const double* __restrict__ Ldiag, int n, double* __restrict__ out) {
+// (no __restrict__ / read-only path on A and Ldiag: in the fused kernel other CTAs wrote them earlier in the same launch)
+__device__ __forceinline__ void chol_back(const double* A, const double* Ldiag, int n, double* out) {
     extern __shared__ double yb[];       // [n] working copy of y
     __shared__ double Ld[kCholNB][kCholNB + 1];
     __shared__ double xb[kCholNB];
@@ -981,13 +989,15 @@ __global__ void __launch_bounds__(1024) chol_back_kernel(const double* __restric
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int k = kb * kCholNB, nbk = min(kCholNB, n - k);
         Ld[tid >> 5][tid & 31] = Ldiag[(size_t)kb * kCholNB * kCholNB + tid];
+        Ld[(tid >> 5) + 16][tid & 31] = Ldiag[(size_t)kb * kCholNB * kCholNB + 512 + tid];
         __syncthreads();
         if (tid < 32) {
             const int lane = tid;
             double part = (lane < nbk) ? yb[k + lane] : 0.0;
+            const double rinv = (lane < nbk) ? 1.0 / Ld[lane][lane] : 0.0;   // one parallel divide instead of 32 serial ones
             for (int j = nbk - 1; j >= 0; --j) {
                 double xj = 0.0;
-                if (lane == j) xj = part / Ld[j][j];
+                if (lane == j) xj = part * rinv;
                 xj = __shfl_sync(0xFFFFFFFFu, xj, j);
                 if (lane == j) xb[j] = xj;
                 if (lane < j) part -= Ld[j][lane] * xj;
@@ -1008,6 +1018,13 @@ __global__ void __launch_bounds__(1024) chol_back_kernel(const double* __restric
         __syncthreads();
     }
 }
+
+__global__ void __launch_bounds__(512) chol_back_kernel(const double* __restrict__ A, const double* __restrict__ Ldiag, int n, double* __restrict__ out) {
+    chol_back(A, Ldiag, n, out);
+}
+
+// (A single cooperative launch with a grid-wide barrier between panels was measured SLOWER than one launch per panel:
+// 0.42 vs 0.30 ms per solve at n = 294 -- cg::grid_group::sync costs more than a kernel boundary on an 11-CTA grid.)
 
 // ----------------------------------------------------------------------------------------
 struct DevBuf {
@@ -1335,12 +1352,14 @@ struct Ctx {
         if (nd > 0) {
             {
                 const int nblk = (nd + kCholNB - 1) / kCholNB, nrb = (nd + 1 + kCholNB - 1) / kCholNB;   // row blocks incl. the rhs row
-                for (int kb = 0; kb < nblk; ++kb) {
-                    chol_left_kernel<<<nrb - kb, kCholThreads, 0, st>>>(s->Sm.as<double>(), nd, nd + 1, kb, s->work.as<double>(), &sc->info);
+                {
+                    for (int kb = 0; kb < nblk; ++kb) {
+                        chol_left_kernel<<<nrb - kb, kCholThreads, 0, st>>>(s->Sm.as<double>(), nd, nd + 1, kb, s->work.as<double>(), &sc->info);
+                        ++s->launches;
+                    }
+                    chol_back_kernel<<<1, 512, (size_t)nd * 8, st>>>(s->Sm.as<double>(), s->work.as<double>(), nd, s->bs.as<double>());
                     ++s->launches;
                 }
-                chol_back_kernel<<<1, 1024, (size_t)nd * 8, st>>>(s->Sm.as<double>(), s->work.as<double>(), nd, s->bs.as<double>());
-                ++s->launches;
                 ADB_CUDA(cudaGetLastError());
             }
         }
