@@ -33,7 +33,7 @@ def full_summary(reps, out_csv, out_json, note):
     lines = [f"# {note}", "# ncu --set full --clock-control none --import-source on; one row per profiled launch", "kernel," + ",".join(WANT)]
     traffic = {}
     for rep in reps:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         h = rows[0]; ki = h.index('Kernel Name')
         idx = [h.index(w) if w in h else None for w in WANT]
