@@ -50,7 +50,7 @@ class ProjSearch(C.Structure):
                 ("scale_factors", C.c_void_p), ("n_levels", C.c_int32), ("th", C.c_float), ("mono", C.c_int32),
                 ("mp_xw", C.c_void_p), ("mp_normal", C.c_void_p), ("mp_min_distance", C.c_void_p), ("mp_max_distance", C.c_void_p),
                 ("ow", C.c_void_p), ("view_cos_limit", C.c_float), ("log_scale_factor", C.c_float),
-                ("q_track", C.c_void_p), ("q_level", C.c_void_p),
+                ("q_track", C.c_void_p), ("q_level", C.c_void_p), ("fuse", C.c_int32), ("inv_level_sigma2", C.c_void_p),
                 ("kp_match", C.c_void_p), ("q_best_idx", C.c_void_p), ("q_best_dist", C.c_void_p), ("n_matches", C.c_int32)]
 
 

@@ -25,7 +25,7 @@ namespace adb {
 
 constexpr int kGridCols = 64, kGridRows = 48, kGridCells = kGridCols * kGridRows;   // include/Frame.h:38-39
 constexpr int kHisto = 30;                                                          // HISTO_LENGTH src/ORBmatcher.cc:39
-constexpr int kThHigh = 100;                                                        // TH_HIGH src/ORBmatcher.cc:37
+constexpr int kThHigh = 100, kThLow = 50;                                           // TH_HIGH / TH_LOW src/ORBmatcher.cc:37-38
 constexpr int kSearchThreads = 1024;
 constexpr uint32_t kNoBlock = 0x7FFFFFFFu;
 
@@ -55,6 +55,7 @@ struct SearchDev {
     float view_cos_limit, log_scale_factor;
     int n_levels;
     float* q_track; int32_t* q_level;
+    int fuse; const float* inv_sigma2;     // ORBmatcher::Fuse candidate search (src/ORBmatcher.cc:825-975)
     // results
     int32_t* kp_match; int32_t* q_best_idx; int32_t* q_best_dist; int32_t* q_choice; int32_t* n_matches;
 };
@@ -119,9 +120,16 @@ __global__ void frustum_kernel(const SearchDev* __restrict__ probs) {
         }
         bool ok = !(c[2] < 0.0f);
         const float invz = __fdiv_rn(1.0f, c[2]);
-        const float uu = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c[0]), invz), P.cx);
-        const float vv = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c[1]), invz), P.cy);
-        ok = ok && !(uu < P.min_x || uu > P.max_x) && !(vv < P.min_y || vv > P.max_y);
+        float uu, vv;
+        if (P.fuse) {   // Fuse: x = Xc * invz first, IsInImage is half open (src/ORBmatcher.cc:859-868, src/KeyFrame.cc:630-633)
+            uu = __fadd_rn(__fmul_rn(P.fx, __fmul_rn(c[0], invz)), P.cx);
+            vv = __fadd_rn(__fmul_rn(P.fy, __fmul_rn(c[1], invz)), P.cy);
+            ok = ok && (uu >= P.min_x && uu < P.max_x && vv >= P.min_y && vv < P.max_y);
+        } else {
+            uu = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c[0]), invz), P.cx);
+            vv = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c[1]), invz), P.cy);
+            ok = ok && !(uu < P.min_x || uu > P.max_x) && !(vv < P.min_y || vv > P.max_y);
+        }
         const float maxD = __fmul_rn(1.2f, P.mp_max_distance[i]), minD = __fmul_rn(0.8f, P.mp_min_distance[i]);
         const float ox = __fsub_rn(px, P.ow[0]), oy = __fsub_rn(py, P.ow[1]), oz = __fsub_rn(pz, P.ow[2]);
         const double n2 = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)ox), __dmul_rn((double)oy, (double)oy)), __dmul_rn((double)oz, (double)oz));
@@ -130,17 +138,19 @@ __global__ void frustum_kernel(const SearchDev* __restrict__ probs) {
         const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)P.mp_normal[3 * i]), __dmul_rn((double)oy, (double)P.mp_normal[3 * i + 1])),
                                      __dmul_rn((double)oz, (double)P.mp_normal[3 * i + 2]));
         const float viewCos = (float)__ddiv_rn(dot, (double)dist);
-        ok = ok && !(viewCos < P.view_cos_limit);
+        if (P.fuse) ok = ok && !(dot < __dmul_rn(0.5, (double)dist));   // PO.dot(Pn) < 0.5 * dist3D (src/ORBmatcher.cc:883)
+        else ok = ok && !(viewCos < P.view_cos_limit);
         if (ok) {
             const float ratio = __fdiv_rn(P.mp_max_distance[i], dist);
             int ns = (int)ceilf(__fdiv_rn((float)log((double)ratio), P.log_scale_factor));
             if (ns < 0) ns = 0; else if (ns >= P.n_levels) ns = P.n_levels - 1;
             float r = (double)viewCos > 0.998 ? 2.5f : 4.0f;
             if (P.th != 1.0f) r = __fmul_rn(r, P.th);
+            if (P.fuse) r = P.th;                                       // radius = th * mvScaleFactors[level] (src/ORBmatcher.cc:889)
             u = uu; v = vv; ur = __fsub_rn(uu, __fmul_rn(P.mbf, invz)); vc = viewCos;
             rad = __fmul_rn(r, P.scale_factors[ns]);
             minl = ns - 1; maxl = ns; level = ns;
-            fl = (uint8_t)(1 | (inf & 2));
+            fl = (uint8_t)(P.fuse ? 1 : (1 | (inf & 2)));
         }
     }
     P.q_u[i] = u; P.q_v[i] = v; P.q_ur[i] = ur; P.q_radius[i] = rad; P.q_minl[i] = minl; P.q_maxl[i] = maxl; P.q_flags[i] = fl;
@@ -263,9 +273,17 @@ __global__ void __launch_bounds__(kSearchThreads) proj_search_kernel(const Searc
                                 if (maxl >= 0 && kp.octave > maxl) continue;
                             }
                             if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
-                            if (prev[idx] <= (uint32_t)q) continue;                  // held by an observed map point
                             const float ur = P.u_right[idx];
-                            if (ur > 0 && fabsf(__fsub_rn(urq, ur)) > r) continue;
+                            if (P.fuse) {   // chi2 gate on the reprojection error (src/ORBmatcher.cc:913-936)
+                                const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                                double lim = 5.99;
+                                if (ur >= 0) { const float er = __fsub_rn(urq, ur); e2 = __fadd_rn(e2, __fmul_rn(er, er)); lim = 7.8; }
+                                if ((double)__fmul_rn(e2, P.inv_sigma2[kp.octave]) > lim) continue;
+                            } else {
+                                if (prev[idx] <= (uint32_t)q) continue;              // held by an observed map point
+                                if (ur > 0 && fabsf(__fsub_rn(urq, ur)) > r) continue;
+                            }
                             const uint4* tp = reinterpret_cast<const uint4*>(P.desc + (size_t)idx * 32);
                             const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
                             const int d = __popc(qd[0] ^ ta.x) + __popc(qd[1] ^ ta.y) + __popc(qd[2] ^ ta.z) + __popc(qd[3] ^ ta.w) +
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(kSearchThreads) proj_search_kernel(const Searc
                 int choice = -1, bidx = -1, bdist = 256;
                 if (best != ~0ull) {
                     bdist = (int)(best >> 43); bidx = (int)((best >> 5) & 0x1FFF);
-                    if (bdist <= kThHigh) {
+                    if (bdist <= (P.fuse ? kThLow : kThHigh)) {
                         bool ok = true;
                         if (P.use_ratio) {
                             const int lvl = (int)(best & 31), lvl2 = second != ~0ull ? (int)(second & 31) : -1;
@@ -297,7 +315,7 @@ __global__ void __launch_bounds__(kSearchThreads) proj_search_kernel(const Searc
                         }
                         if (ok) {
                             choice = bidx;
-                            if (fl & 2) atomicMin(&cur[bidx], (uint32_t)q + 1u);
+                            if ((fl & 2) && !P.fuse) atomicMin(&cur[bidx], (uint32_t)q + 1u);
                         }
                     }
                 }
@@ -417,7 +435,8 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
                   ADB_ERR_INVALID, "problem %d: map-point visibility inputs missing", p);
         ADB_CHECK(!s.last_xw || (s.last_octave && s.tcw_cur && s.tcw_last && s.scale_factors && s.n_levels > 0), ADB_ERR_INVALID,
                   "problem %d: last-frame projection inputs missing", p);
-        ADB_CHECK(!s.check_orientation || s.q_angle, ADB_ERR_INVALID, "problem %d: q_angle missing", p);
+        ADB_CHECK(!s.check_orientation || s.q_angle || s.fuse, ADB_ERR_INVALID, "problem %d: q_angle missing", p);
+        ADB_CHECK(!s.fuse || (s.mp_xw && s.inv_level_sigma2), ADB_ERR_INVALID, "problem %d: fuse needs the map-point inputs and inv_level_sigma2", p);
         max_nk = std::max(max_nk, s.n_kp); max_nq = std::max(max_nq, s.n_q);
     }
     // two passes over the same layout code: size, then copy
@@ -452,6 +471,8 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
                 for (int k = 0; k < 3; ++k) D.ow[k] = s.ow[k];
                 D.fx = s.fx; D.fy = s.fy; D.cx = s.cx; D.cy = s.cy; D.mbf = s.mbf; D.th = s.th;
                 D.view_cos_limit = s.view_cos_limit; D.log_scale_factor = s.log_scale_factor; D.n_levels = s.n_levels;
+                D.fuse = s.fuse ? 1 : 0;
+                if (s.fuse) { D.inv_sigma2 = pk.put(s.inv_level_sigma2, s.n_levels); D.use_ratio = 0; D.check_ori = 0; }
             } else if (proj) {
                 D.last_xw = pk.put(s.last_xw, (size_t)s.n_q * 3); D.last_octave = pk.put(s.last_octave, s.n_q);
                 D.last_flags = pk.put(s.q_flags, s.n_q);

@@ -140,6 +140,17 @@ public:
         mvuRight.resize(nLeft); mvDepth.resize(nLeft);
     }
 
+    // SearchByProjection(Frame& F, const vector<MapPoint*>&, th) / SearchByProjection(Frame& Current, const Frame& Last, th,
+    // bMono) (src/ORBmatcher.cc:45-129, 1328-1470) after the shim has copied the Frame / MapPoint members into an
+    // adb_proj_search.  mfNNratio / mbCheckOrientation come from this matcher like in the
+    // reference; returns nmatches, the new CurrentFrame.mvpMapPoints are in problem.kp_match.
+    int SearchByProjection(adb_proj_search& problem) {
+        if (problem.last_xw) { problem.use_ratio = 0; problem.check_orientation = mbCheckOrientation ? 1 : 0; }
+        else { problem.use_ratio = 1; problem.nn_ratio = mfNNratio; problem.check_orientation = 0; }
+        airdos::check(adb_search_by_projection(m_, &problem, 1), "ORBmatcher::SearchByProjection");
+        return problem.n_matches;
+    }
+
 protected:
     float mfNNratio;
     bool mbCheckOrientation;

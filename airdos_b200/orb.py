@@ -227,7 +227,8 @@ class ORBmatcher:
         bMono), src/ORBmatcher.cc:1328-1470) or the local map points before the visibility test (`mp_xw`, `mp_normal`,
         `mp_min_distance`, `mp_max_distance`, `ow`, `tcw_cur`, `cam`, `scale_factors`, `log_scale_factor`, `th`; Frame::isInFrustum
         + SearchByProjection as Tracking::SearchLocalPoints runs them, src/Tracking.cc:1319-1343; two more outputs: q_track
-        [n_q, 4] = mTrackProjX / Y / XR / ViewCos and q_level = mnTrackScaleLevel or -1).
+        [n_q, 4] = mTrackProjX / Y / XR / ViewCos and q_level = mnTrackScaleLevel or -1).  With `fuse` = 1 (+ `inv_level_sigma2`)
+        the same inputs run the candidate search of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:825-975).
         Returns a list of (nmatches, kp_match, q_best_idx, q_best_dist[, q_track, q_level])."""
         from .capi import ProjSearch
         n = len(problems)
@@ -261,6 +262,8 @@ class ORBmatcher:
                 S.th = float(pr.get("th", 1.0)); S.view_cos_limit = float(pr.get("view_cos_limit", 0.5))
                 S.log_scale_factor = float(pr["log_scale_factor"])
                 S.use_ratio = int(pr.get("use_ratio", 1)); S.nn_ratio = float(pr.get("nn_ratio", self.mfNNratio)); S.check_orientation = 0
+                if pr.get("fuse"):     # ORBmatcher::Fuse candidate search (src/ORBmatcher.cc:825-975)
+                    S.fuse = 1; S.inv_level_sigma2 = a(pr["inv_level_sigma2"], np.float32)
                 track = np.zeros((S.n_q, 4), np.float32); level = np.full(S.n_q, -1, np.int32); keep += [track, level]
                 S.q_track, S.q_level = track.ctypes.data, level.ctypes.data
             elif "last_xw" in pr:

@@ -398,3 +398,12 @@ def tracking_problem_as_local_map(pr: dict, seed: int = 0, nn_ratio: float = 0.8
                mp_max_distance=max_d.astype(np.float32), ow=ow.astype(np.float32), q_flags=pr["q_flags"].copy(),
                log_scale_factor=float(np.log(np.float32(1.2))), th=th, nn_ratio=nn_ratio, use_ratio=1, view_cos_limit=0.5)
     return out
+
+
+def tracking_problem_as_fuse(pr: dict, seed: int = 0, th: float = 3.0) -> dict:
+    """The same scene as ORBmatcher::Fuse(pKF, vpMapPoints, th) sees it (src/ORBmatcher.cc:825-975; LocalMapping::SearchInNeighbors
+    calls it with the default th = 3.0): the key-frame's key-points and the neighbours' map points."""
+    out = tracking_problem_as_local_map(pr, seed=seed, th=th)
+    sf = np.asarray(pr["scale_factors"], np.float32)
+    out.update(fuse=1, inv_level_sigma2=(np.float32(1.0) / (sf * sf)).astype(np.float32), taken=None)
+    return out

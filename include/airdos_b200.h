@@ -244,6 +244,16 @@ typedef struct adb_proj_search {
     float log_scale_factor;        /* Frame::mfLogScaleFactor */
     float* q_track;                /* optional out [n_q][4]: mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos (0 when not in view) */
     int32_t* q_level;              /* optional out [n_q]: mnTrackScaleLevel, -1 = mbTrackInView false */
+    /* fuse != 0: the candidate search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:825-975) on the
+     * mp_* inputs: the "frame" arrays are the KeyFrame's (mvKeysUn, mvuRight, mDescriptors, grid), q_flags bit 0 =
+     * pMP && !isBad() && !IsInKeyFrame(pKF).  Projection and tests as at :845-885 (x = Xc * invz first, IsInImage with a
+     * half-open range, PO.dot(Pn) < 0.5 * dist3D), window radius th * mvScaleFactors[level], candidates of levels
+     * [level - 1, level] that pass the chi2 gate on the reprojection error (:913-936, needs inv_level_sigma2), best
+     * Hamming only, accepted when <= TH_LOW.  No key-point is closed to later queries: the Replace / AddObservation
+     * bookkeeping of :948-968 stays on the host, driven by q_best_idx (>= 0 and q_best_dist <= 50 = "fuse this one").
+     * kp_match / n_matches: the last accepted query per key-point / the number of accepted queries (= nFused). */
+    int32_t fuse;
+    const float* inv_level_sigma2; /* [n_levels] KeyFrame::mvInvLevelSigma2 */
     /* results */
     int32_t* kp_match;             /* [n_kp] CurrentFrame.mvpMapPoints after the call: -1 untouched, -2 set to NULL by the rotation
                                       check, >= 0 index of the query (map point) now held */

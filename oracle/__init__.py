@@ -225,6 +225,18 @@ def search_by_projection(pr: dict, nn_ratio: float = 0.6, check_orientation: boo
     qf = np.ascontiguousarray(pr["q_flags"], np.uint8); qd = np.ascontiguousarray(pr["q_desc"], np.uint8)
     nq, nk = len(qf), len(kps)
     extra = {}
+    if pr.get("fuse"):
+        fx, fy, cx, cy, mbf, mb = [float(v) for v in pr["cam"]]
+        sf = np.ascontiguousarray(pr["scale_factors"], np.float32); isg = np.ascontiguousarray(pr["inv_level_sigma2"], np.float32)
+        arrs = [np.ascontiguousarray(pr[k], np.float32) for k in ("tcw_cur", "ow", "mp_xw", "mp_normal", "mp_min_distance", "mp_max_distance")]
+        km = np.zeros(nk, np.int32); bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32)
+        lib.match_oracle_fuse_search.restype = C.c_int
+        lib.match_oracle_fuse_search.argtypes = ([C.c_void_p] * 3 + [C.c_int] + [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_int] +
+                                                 [C.c_void_p] * 6 + [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 3)
+        n = lib.match_oracle_fuse_search(_p(kps), _p(ur), _p(desc), nk, mnx, mny, mxx, mxy, inv_w, inv_h, _p(arrs[0]), _p(arrs[1]), nq,
+                                         _p(arrs[2]), _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), _p(qf), _p(qd), fx, fy, cx, cy, mbf,
+                                         float(pr["log_scale_factor"]), _p(sf), _p(isg), len(sf), float(pr["th"]), _p(km), _p(bi), _p(bd))
+        return int(n), km, bi, bd, {}
     if "mp_xw" in pr:
         qu = np.zeros(nq, np.float32); qv = np.zeros(nq, np.float32); qur = np.zeros(nq, np.float32); qr = np.zeros(nq, np.float32)
         qmin = np.zeros(nq, np.int32); qmax = np.zeros(nq, np.int32); qfl = np.zeros(nq, np.uint8)

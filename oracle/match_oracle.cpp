@@ -419,4 +419,72 @@ void match_oracle_frustum(const float* tcw, const float* ow, int n, const float*
     }
 }
 
+// The search half of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:825-975) with
+// KeyFrame::GetFeaturesInArea / IsInImage (src/KeyFrame.cc:589-633): per map point the key-point it would be fused with.
+// Same cv::Mat conventions as match_oracle_frustum.  Returns nFused (queries with bestDist <= TH_LOW).
+int match_oracle_fuse_search(const void* kps_, const float* u_right, const uint8_t* desc, int n_kp, float minX, float minY, float maxX,
+                             float maxY, float invW, float invH, const float* tcw, const float* ow, int n, const float* xw,
+                             const float* normal, const float* min_distance, const float* max_distance, const uint8_t* in_flags,
+                             const uint8_t* q_desc, float fx, float fy, float cx, float cy, float mbf, float log_scale_factor,
+                             const float* scale_factors, const float* inv_level_sigma2, int n_levels, float th, int32_t* kp_match,
+                             int32_t* q_best_idx, int32_t* q_best_dist) {
+    const KeyPoint* kps = (const KeyPoint*)kps_;
+    Grid* g = new Grid();
+    assign_to_grid(kps, n_kp, minX, minY, invW, invH, *g);
+    for (int i = 0; i < n_kp; ++i) kp_match[i] = -1;
+    int nFused = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < n; ++i) {
+        q_best_idx[i] = -1; q_best_dist[i] = 256;
+        if (!(in_flags[i] & 1)) continue;
+        const float* P = xw + 3 * i;
+        float Pc[3];
+        for (int r = 0; r < 3; ++r) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += (double)tcw[4 * r + k] * (double)P[k];
+            Pc[r] = (float)(s + (double)tcw[4 * r + 3]);
+        }
+        if (Pc[2] < 0.0f) continue;
+        const float invz = 1 / Pc[2];
+        const float x = Pc[0] * invz, y = Pc[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!(u >= minX && u < maxX && v >= minY && v < maxY)) continue;
+        const float ur = u - mbf * invz;
+        const float maxD = 1.2f * max_distance[i], minD = 0.8f * min_distance[i];
+        const float PO[3] = {P[0] - ow[0], P[1] - ow[1], P[2] - ow[2]};
+        const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+        if (dist3D < minD || dist3D > maxD) continue;
+        const float* Pn = normal + 3 * i;
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
+        if (dot < 0.5 * (double)dist3D) continue;
+        const float ratio = max_distance[i] / dist3D;
+        int lvl = (int)std::ceil((float)std::log((double)ratio) / log_scale_factor);
+        if (lvl < 0) lvl = 0; else if (lvl >= n_levels) lvl = n_levels - 1;
+        const float radius = th * scale_factors[lvl];
+        features_in_area(*g, kps, minX, minY, invW, invH, u, v, radius, -1, -1, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const KeyPoint& kp = kps[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            if (u_right[idx] >= 0) {
+                const float ex = u - kp.x, ey = v - kp.y, er = ur - u_right[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if ((double)(e2 * inv_level_sigma2[kpLevel]) > 7.8) continue;
+            } else {
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if ((double)(e2 * inv_level_sigma2[kpLevel]) > 5.99) continue;
+            }
+            const int dist = hamming256(q_desc + (size_t)i * 32, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        q_best_idx[i] = bestIdx; q_best_dist[i] = bestDist;
+        if (bestDist <= TH_LOW) { kp_match[bestIdx] = i; ++nFused; }
+    }
+    delete g;
+    return nFused;
+}
+
 }  // extern "C"

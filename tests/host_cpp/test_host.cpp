@@ -66,6 +66,40 @@ int main(int argc, char** argv) {
     stop = true;
     if (ORB_SLAM2::Optimizer::LocalBundleAdjustment(P, &stop, R)) return 9;   // stop flag set: early return
 
+    // global BA entry: one round, robust off (LoopClosing's call), same toy window
+    stop = false;
+    t[3] += 0.02;
+    if (!ORB_SLAM2::Optimizer::GlobalBundleAdjustemnt(P, 10, &stop, false, R)) return 10;
+    if (R.iterations_run[1] != 0 || std::fabs(t[3] + 0.5) > 1e-3) return 11;
+
+    // SearchByProjection(Current, Last): the extracted frame against itself (identity poses, every key-point a map point at
+    // 5 m): each valid query must come back holding its own key-point
+    {
+        const int nk = (int)kps.size();
+        std::vector<float> ur(nk, -1.f), xw(3 * (size_t)nk), ang(nk), sf(8);
+        std::vector<int32_t> oct(nk), match(nk, -1);
+        std::vector<uint8_t> flags(nk, 3);
+        sf[0] = 1.f; for (int l = 1; l < 8; ++l) sf[l] = sf[l - 1] * 1.2f;
+        for (int i = 0; i < nk; ++i) {
+            xw[3 * i] = (kps[i].x - 320.f) * 5.f / 500.f; xw[3 * i + 1] = (kps[i].y - 240.f) * 5.f / 500.f; xw[3 * i + 2] = 5.f;
+            oct[i] = kps[i].octave; ang[i] = kps[i].angle;
+        }
+        const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        adb_proj_search S;
+        std::memset(&S, 0, sizeof(S));
+        S.n_kp = nk; S.kps = kps.data(); S.u_right = ur.data(); S.desc = desc.data();
+        S.min_x = 0; S.min_y = 0; S.max_x = 640; S.max_y = 480; S.grid_inv_w = 64.f / 640.f; S.grid_inv_h = 48.f / 480.f;
+        S.n_q = nk; S.q_flags = flags.data(); S.q_desc = desc.data(); S.q_angle = ang.data();
+        S.last_xw = xw.data(); S.last_octave = oct.data(); S.tcw_cur = I4; S.tcw_last = I4;
+        S.fx = 500; S.fy = 500; S.cx = 320; S.cy = 240; S.mbf = 100; S.mb = 0.2f; S.scale_factors = sf.data(); S.n_levels = 8; S.th = 7; S.mono = 0;
+        S.kp_match = match.data();
+        ORB_SLAM2::ORBmatcher matcher(0.9f, true);
+        const int nm = matcher.SearchByProjection(S);
+        int self = 0;
+        for (int i = 0; i < nk; ++i) self += match[i] == i;
+        if (nm < nk * 9 / 10 || self < nk * 9 / 10) { std::printf("self search: %d matches, %d on themselves of %d\n", nm, self, nk); return 12; }
+    }
+
     f = std::fopen(argv[2], "wb");
     const int32_t n = (int32_t)kps.size();
     std::fwrite(&n, 4, 1, f);

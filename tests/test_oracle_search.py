@@ -156,3 +156,46 @@ def test_frustum_matches_float64_and_feeds_the_search():
     assert (q["q_radius"][got] == r * pm["scale_factors"][q["q_level"][got]]).all()
     nb, hb = brute_force(pm, q, 1, 0.8, False)
     assert n == nb and (km == hb).all() and n > 50
+
+
+def test_fuse_search_matches_brute_force():
+    """ORBmatcher::Fuse candidate search restatement vs a flat numpy formulation (no grid at all: the window test
+    |dx| < r, |dy| < r already implies the cell range, and Fuse has no first-come rule, so order only breaks ties)."""
+    pr = synth.make_tracking_problem(13, n_kp=500, n_q=500)
+    pf = synth.tracking_problem_as_fuse(pr, seed=1)
+    n, km, bi, bd, _ = oracle.search_by_projection(pf)
+    # reuse the frustum restatement for the projected quantities (pinned above), then brute-force the candidate scan
+    pm = dict(pf); pm.pop("fuse")
+    q = oracle.search_by_projection(pm)[4]
+    kps = pf["kps"]; T = pf["tcw_cur"].astype(np.float64); fx, fy, cx, cy, mbf, mb = pf["cam"]
+    X = pf["mp_xw"].astype(np.float64); pc = X @ T[:3, :3].T + T[:3, 3]
+    u = (fx * (pc[:, 0] / pc[:, 2]) + cx).astype(np.float32); v = (fy * (pc[:, 1] / pc[:, 2]) + cy).astype(np.float32)
+    px = np.floor(kps["x"] * np.float32(0.1) + np.float32(0.5)).astype(int); py = np.floor(kps["y"] * np.float32(0.1) + np.float32(0.5)).astype(int)
+    order = np.lexsort((np.arange(len(kps)), py, px))
+    nf = 0; agree = 0; checked = 0
+    for j in range(len(u)):
+        lvl = q["q_level"][j]
+        if lvl < 0:
+            continue            # (the two visibility tests differ only in open / closed borders; covered by the GPU parity test)
+        r = np.float32(pf["th"]) * pf["scale_factors"][lvl]
+        ur = np.float32(u[j] - np.float32(mbf) / np.float32(pc[j, 2]))
+        best, bidx = 256, -1
+        for i in order:
+            if not (abs(np.float32(kps["x"][i] - u[j])) < r and abs(np.float32(kps["y"][i] - v[j])) < r):
+                continue
+            if kps["octave"][i] < lvl - 1 or kps["octave"][i] > lvl:
+                continue
+            ex, ey = np.float32(u[j] - kps["x"][i]), np.float32(v[j] - kps["y"][i])
+            e2 = np.float32(ex * ex + ey * ey); lim = 5.99
+            if pf["u_right"][i] >= 0:
+                er = np.float32(ur - pf["u_right"][i]); e2 = np.float32(e2 + er * er); lim = 7.8
+            if float(np.float32(e2 * pf["inv_level_sigma2"][kps["octave"][i]])) > lim:
+                continue
+            d = _popcount(pf["q_desc"][j], pf["desc"][i])
+            if d < best:
+                best, bidx = d, i
+        checked += 1
+        agree += (bidx == bi[j] and best == bd[j])
+        nf += best <= 50
+    # u, v come from float64 here: a candidate right at the chi2 gate or the window edge may flip
+    assert checked > 200 and agree >= checked - 3 and abs(nf - n) <= 3 and n > 100

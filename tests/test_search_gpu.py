@@ -80,3 +80,16 @@ def test_local_map_search_with_frustum_on_device(adb, oracle_mod, seed, th):
     assert (got[4].view(np.uint32) == ref[4]["q_track"].view(np.uint32)).all()     # float outputs by bit pattern
     assert ref[0] > 100 and (ref[4]["q_level"] >= 0).sum() > 1000
     m.close()
+
+
+def test_fuse_candidate_search_on_device(adb, oracle_mod):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th): projection, visibility tests, window search with the chi2 gate, TH_LOW."""
+    m = adb.ORBmatcher(0.6, True)
+    for seed, th in ((40, 3.0), (41, 4.0)):
+        pr = synth.make_tracking_problem(seed, n_kp=2000, n_q=3000, dup_frac=0.3)
+        pf = synth.tracking_problem_as_fuse(pr, seed=seed, th=th)
+        ref = oracle_mod.search_by_projection(pf)
+        got = m.SearchByProjection(pf)
+        _same(got[:4], ref)
+        assert ref[0] > 200
+    m.close()
