@@ -54,6 +54,16 @@ class ProjSearch(C.Structure):
                 ("kp_match", C.c_void_p), ("q_best_idx", C.c_void_p), ("q_best_dist", C.c_void_p), ("n_matches", C.c_int32)]
 
 
+class BowSearch(C.Structure):
+    """adb_bow_search (include/airdos_b200.h)."""
+    _fields_ = [("mode", C.c_int32), ("n1", C.c_int32), ("kps1", C.c_void_p), ("u_right1", C.c_void_p), ("desc1", C.c_void_p), ("flags1", C.c_void_p),
+                ("n2", C.c_int32), ("kps2", C.c_void_p), ("u_right2", C.c_void_p), ("desc2", C.c_void_p), ("flags2", C.c_void_p),
+                ("n_buckets", C.c_int32), ("b_ptr1", C.c_void_p), ("b_idx1", C.c_void_p), ("b_ptr2", C.c_void_p), ("b_idx2", C.c_void_p),
+                ("nn_ratio", C.c_float), ("check_orientation", C.c_int32), ("f12", C.c_void_p), ("ex", C.c_float), ("ey", C.c_float),
+                ("scale_factors2", C.c_void_p), ("level_sigma2_2", C.c_void_p), ("n_levels", C.c_int32),
+                ("match21", C.c_void_p), ("match12", C.c_void_p), ("n_matches", C.c_int32)]
+
+
 # every symbol include/airdos_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _f32, _sz = C.c_void_p, C.c_int32, C.c_float, C.c_size_t
 _ip = C.POINTER(C.c_int32)
@@ -87,6 +97,7 @@ SYMBOLS = {
     "adb_match_best2_device": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "adb_search_by_projection": (C.c_int, [_vp, _vp, _i32]),
     "adb_search_last_ms": (C.c_int, [_vp, _fp]),
+    "adb_search_by_bow": (C.c_int, [_vp, _vp, _i32]),
     "adb_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "adb_stereo_match": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
     "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),

@@ -383,6 +383,168 @@ __global__ void __launch_bounds__(kSearchThreads) proj_search_kernel(const Searc
     if (tid == 0) *P.n_matches = s_acc - s_removed;
 }
 
+// =========================================================================================
+// Vocabulary-bucket searches (SearchByBoW, SearchForTriangulation).  One CTA per problem, one warp per query (a side-1
+// feature in FeatureVector order), lanes stride the side-2 features of the same vocabulary node.
+struct BowDev {
+    int mode, n1, n2, n_buckets, nq;
+    const adb_keypoint* kps1; const float* ur1; const uint8_t* d1; const uint8_t* fl1;
+    const adb_keypoint* kps2; const float* ur2; const uint8_t* d2; const uint8_t* fl2;
+    const int32_t* p2; const int32_t* i1; const int32_t* i2; const int32_t* q_bucket;
+    float nn_ratio; int check_ori;
+    float F12[9], ex, ey;
+    const float* scale2; const float* sigma2_2;
+    int32_t* choice;      // [nq] accepted partner of every query position (-1: none)
+    int32_t* match21; int32_t* match12; int32_t* n_matches;
+};
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {   // src/ORBmatcher.cc:228-234
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
+    return bin == kHisto ? 0 : bin;
+}
+
+__device__ __forceinline__ void three_maxima(const int* hist, int* keep) {   // ORBmatcher::ComputeThreeMaxima
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < kHisto; ++i) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+    keep[0] = ind1; keep[1] = ind2; keep[2] = ind3;
+}
+
+__global__ void __launch_bounds__(kSearchThreads) bow_search_kernel(const BowDev* __restrict__ probs) {
+    extern __shared__ __align__(16) uint8_t search_smem[];
+    const BowDev& P = probs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kSearchThreads / 32;
+    uint32_t* blk0 = reinterpret_cast<uint32_t*>(search_smem);
+    uint32_t* blk1 = blk0 + P.n2;
+    __shared__ int s_hist[kHisto];
+    __shared__ int s_keep[3];
+    __shared__ int s_acc, s_removed;
+    if (tid < kHisto) s_hist[tid] = 0;
+    if (tid == 0) { s_acc = 0; s_removed = 0; }
+    for (int i = tid; i < P.n2; i += kSearchThreads) blk0[i] = kNoBlock;
+    __syncthreads();
+    uint32_t* prev = blk0;
+    uint32_t* cur = blk1;
+    const int max_rounds = P.mode == 0 ? P.nq + 1 : 1;
+    for (int round = 0; round < max_rounds; ++round) {
+        for (int i = tid; i < P.n2; i += kSearchThreads) cur[i] = kNoBlock;
+        __syncthreads();
+        for (int a = warp; a < P.nq; a += nwarps) {
+            const int idx1 = P.i1[a];
+            uint64_t best = ~0ull, second = ~0ull;
+            if (P.fl1[idx1] & 1) {
+                const int b = P.q_bucket[a];
+                const int c0 = P.p2[b], c1 = P.p2[b + 1];
+                uint32_t qd[8];
+                {
+                    const uint4* qp = reinterpret_cast<const uint4*>(P.d1 + (size_t)idx1 * 32);
+                    const uint4 u = __ldg(qp), w = __ldg(qp + 1);
+                    qd[0] = u.x; qd[1] = u.y; qd[2] = u.z; qd[3] = u.w; qd[4] = w.x; qd[5] = w.y; qd[6] = w.z; qd[7] = w.w;
+                }
+                float la = 0.f, lb = 0.f, lc = 0.f, den = 0.f;
+                bool stereo1 = false;
+                if (P.mode == 1) {   // epipolar line of key-point 1 in image 2 (CheckDistEpipolarLine, src/ORBmatcher.cc:131-157)
+                    const adb_keypoint k1 = P.kps1[idx1];
+                    la = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, P.F12[0]), __fmul_rn(k1.y, P.F12[3])), P.F12[6]);
+                    lb = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, P.F12[1]), __fmul_rn(k1.y, P.F12[4])), P.F12[7]);
+                    lc = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, P.F12[2]), __fmul_rn(k1.y, P.F12[5])), P.F12[8]);
+                    den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+                    stereo1 = P.ur1[idx1] >= 0;
+                }
+                for (int c = c0 + lane; c < c1; c += 32) {
+                    const int idx2 = P.i2[c];
+                    if (P.mode == 0) { if (prev[idx2] <= (uint32_t)a) continue; }           // matched by an earlier query
+                    else if (!(P.fl2[idx2] & 1)) continue;
+                    const uint4* tp = reinterpret_cast<const uint4*>(P.d2 + (size_t)idx2 * 32);
+                    const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+                    const int d = __popc(qd[0] ^ ta.x) + __popc(qd[1] ^ ta.y) + __popc(qd[2] ^ ta.z) + __popc(qd[3] ^ ta.w) +
+                                  __popc(qd[4] ^ tb.x) + __popc(qd[5] ^ tb.y) + __popc(qd[6] ^ tb.z) + __popc(qd[7] ^ tb.w);
+                    uint32_t pos = (uint32_t)(c - c0);
+                    if (P.mode == 1) {
+                        if (d > kThLow) continue;
+                        const adb_keypoint k2 = P.kps2[idx2];
+                        if (!stereo1 && !(P.ur2[idx2] >= 0)) {   // both monocular: not too close to the epipole (:744-750)
+                            const float dx = __fsub_rn(P.ex, k2.x), dy = __fsub_rn(P.ey, k2.y);
+                            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, P.scale2[k2.octave])) continue;
+                        }
+                        const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, k2.x), __fmul_rn(lb, k2.y)), lc);
+                        if (den == 0.f) continue;
+                        const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                        if (!((double)dsqr < __dmul_rn(3.84, (double)P.sigma2_2[k2.octave]))) continue;
+                        pos = 8191u - pos;                                                  // equal distance: the later one wins
+                    }
+                    key_insert(((uint64_t)d << 26) | ((uint64_t)pos << 13) | (uint64_t)idx2, best, second);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, o), os = __shfl_xor_sync(0xFFFFFFFFu, second, o);
+                const uint64_t lo = min(best, ob), hi = max(best, ob);
+                second = min(hi, min(second, os));
+                best = lo;
+            }
+            if (lane == 0) {
+                int choice = -1;
+                if (best != ~0ull) {
+                    const int bd = (int)(best >> 26), bi = (int)(best & 0x1FFF);
+                    if (P.mode == 1) choice = bi;                                           // gates already applied
+                    else if (bd <= kThLow) {
+                        const int d2 = second != ~0ull ? (int)(second >> 26) : 256;
+                        if ((float)bd < __fmul_rn(P.nn_ratio, (float)d2)) { choice = bi; atomicMin(&cur[bi], (uint32_t)a + 1u); }
+                    }
+                }
+                P.choice[a] = choice;
+            }
+        }
+        __syncthreads();
+        int changed = 0;
+        for (int i = tid; i < P.n2; i += kSearchThreads) changed |= (cur[i] != prev[i]);
+        uint32_t* t = prev; prev = cur; cur = t;
+        if (!__syncthreads_or(changed)) break;
+    }
+    // ---- write-back + rotation consistency
+    if (P.mode == 0) for (int i = tid; i < P.n2; i += kSearchThreads) P.match21[i] = -1;
+    else for (int i = tid; i < P.n1; i += kSearchThreads) P.match12[i] = -1;
+    __syncthreads();
+    int my_acc = 0;
+    for (int a = tid; a < P.nq; a += kSearchThreads) {
+        const int c = P.choice[a];
+        if (c < 0) continue;
+        const int idx1 = P.i1[a];
+        ++my_acc;
+        if (P.mode == 0) P.match21[c] = idx1; else P.match12[idx1] = c;   // mode 0: one accepted query per key-point (closure)
+        if (P.check_ori) atomicAdd(&s_hist[rot_bin(P.kps1[idx1].angle, P.kps2[c].angle)], 1);
+    }
+    if (my_acc) atomicAdd(&s_acc, my_acc);
+    __syncthreads();
+    if (P.check_ori) {
+        if (tid == 0) three_maxima(s_hist, s_keep);
+        __syncthreads();
+        int my_rm = 0;
+        for (int a = tid; a < P.nq; a += kSearchThreads) {
+            const int c = P.choice[a];
+            if (c < 0) continue;
+            const int idx1 = P.i1[a];
+            const int bin = rot_bin(P.kps1[idx1].angle, P.kps2[c].angle);
+            if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) {
+                if (P.mode == 0) P.match21[c] = -1; else P.match12[idx1] = -1;
+                ++my_rm;
+            }
+        }
+        if (my_rm) atomicAdd(&s_removed, my_rm);
+        __syncthreads();
+    }
+    if (tid == 0) *P.n_matches = s_acc - s_removed;
+}
+
 static size_t search_smem_bytes(int nk) {
     return (size_t)(2 * kGridCells + 1) * 4 + (size_t)2 * nk * 4 + (size_t)((nk + 1) & ~1) * 2 + (size_t)nk * 2 + 16;
 }
@@ -560,6 +722,100 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
         memcpy(&s.n_matches, host(D.n_matches), 4);
         if (s.mp_xw && s.q_track && s.n_q) memcpy(s.q_track, host(D.q_track), (size_t)s.n_q * 16);
         if (s.mp_xw && s.q_level && s.n_q) memcpy(s.q_level, host(D.q_level), (size_t)s.n_q * 4);
+    }
+    return ADB_OK;
+}
+
+adb_status adb_search_by_bow(adb_matcher_t m, adb_bow_search* probs, int32_t n) {
+    ADB_CHECK(m && (probs || n == 0) && n >= 0, ADB_ERR_INVALID, "null argument");
+    if (n == 0) return ADB_OK;
+    ADB_CUDA(cudaSetDevice(m->device));
+    int max_n2 = 0;
+    std::vector<std::vector<int32_t>> qb(n);
+    for (int p = 0; p < n; ++p) {
+        const adb_bow_search& s = probs[p];
+        ADB_CHECK((s.mode == 0 || s.mode == 1) && s.n1 >= 0 && s.n1 <= ADB_SEARCH_MAX && s.n2 >= 0 && s.n2 <= ADB_SEARCH_MAX && s.n_buckets >= 0,
+                  ADB_ERR_INVALID, "problem %d: bad mode or sizes (max %d key-points)", p, ADB_SEARCH_MAX);
+        ADB_CHECK(s.n1 == 0 || (s.kps1 && s.desc1 && s.flags1), ADB_ERR_INVALID, "problem %d: side-1 arrays missing", p);
+        ADB_CHECK(s.n2 == 0 || (s.kps2 && s.desc2), ADB_ERR_INVALID, "problem %d: side-2 arrays missing", p);
+        ADB_CHECK(s.n_buckets == 0 || (s.b_ptr1 && s.b_idx1 && s.b_ptr2 && s.b_idx2), ADB_ERR_INVALID, "problem %d: bucket lists missing", p);
+        ADB_CHECK(s.mode == 0 ? s.match21 != nullptr || s.n2 == 0 : s.match12 != nullptr || s.n1 == 0, ADB_ERR_INVALID, "problem %d: result array missing", p);
+        ADB_CHECK(s.mode == 0 || (s.f12 && s.scale_factors2 && s.level_sigma2_2 && s.n_levels > 0 && (s.n1 == 0 || s.u_right1) &&
+                                  (s.n2 == 0 || (s.u_right2 && s.flags2))), ADB_ERR_INVALID, "problem %d: triangulation inputs missing", p);
+        const int nq = s.n_buckets ? s.b_ptr1[s.n_buckets] : 0, nt = s.n_buckets ? s.b_ptr2[s.n_buckets] : 0;
+        ADB_CHECK(nq <= ADB_SEARCH_MAX && nt <= ADB_SEARCH_MAX, ADB_ERR_INVALID, "problem %d: bucket lists longer than the frames", p);
+        for (int b = 0; b < s.n_buckets; ++b) {
+            ADB_CHECK(s.b_ptr2[b + 1] - s.b_ptr2[b] <= 8191, ADB_ERR_INVALID, "problem %d: vocabulary node with more than 8191 features", p);
+            for (int a = s.b_ptr1[b]; a < s.b_ptr1[b + 1]; ++a) qb[p].push_back(b);
+        }
+        max_n2 = std::max(max_n2, s.n2);
+    }
+    std::vector<BowDev> dev(n);
+    size_t out_begin = 0, total = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        Packer pk;
+        if (pass == 1) { pk.h = m->h_scratch; pk.d = m->d_scratch; }
+        pk.reserve((size_t)n * sizeof(BowDev));
+        for (int p = 0; p < n; ++p) {
+            const adb_bow_search& s = probs[p];
+            BowDev& D = dev[p];
+            memset(&D, 0, sizeof(D));
+            const int nq = (int)qb[p].size(), nt = s.n_buckets ? s.b_ptr2[s.n_buckets] : 0;
+            D.mode = s.mode; D.n1 = s.n1; D.n2 = s.n2; D.n_buckets = s.n_buckets; D.nq = nq;
+            D.kps1 = pk.put(s.kps1, s.n1); D.d1 = pk.put(s.desc1, (size_t)s.n1 * 32); D.fl1 = pk.put(s.flags1, s.n1);
+            D.kps2 = pk.put(s.kps2, s.n2); D.d2 = pk.put(s.desc2, (size_t)s.n2 * 32);
+            D.p2 = pk.put(s.b_ptr2, s.n_buckets + 1); D.i1 = pk.put(s.b_idx1, nq); D.i2 = pk.put(s.b_idx2, nt);
+            D.q_bucket = pk.put(qb[p].data(), nq);
+            D.nn_ratio = s.nn_ratio; D.check_ori = s.check_orientation;
+            if (s.mode == 1) {
+                D.ur1 = pk.put(s.u_right1, s.n1); D.ur2 = pk.put(s.u_right2, s.n2); D.fl2 = pk.put(s.flags2, s.n2);
+                D.scale2 = pk.put(s.scale_factors2, s.n_levels); D.sigma2_2 = pk.put(s.level_sigma2_2, s.n_levels);
+                for (int k = 0; k < 9; ++k) D.F12[k] = s.f12[k];
+                D.ex = s.ex; D.ey = s.ey;
+            }
+        }
+        out_begin = pk.reserve(0);
+        for (int p = 0; p < n; ++p) {
+            const adb_bow_search& s = probs[p];
+            BowDev& D = dev[p];
+            D.match21 = pk.put((const int32_t*)nullptr, s.n2);
+            D.match12 = pk.put((const int32_t*)nullptr, s.n1);
+            D.choice = pk.put((const int32_t*)nullptr, qb[p].size());
+            D.n_matches = pk.put((const int32_t*)nullptr, 1);
+        }
+        total = pk.reserve(0);
+        if (pass == 0 && total > m->scratch_bytes) {
+            cudaFree(m->d_scratch); m->d_scratch = nullptr;
+            if (m->h_scratch) { cudaFreeHost(m->h_scratch); m->h_scratch = nullptr; }
+            m->scratch_bytes = 0;
+            const size_t want = total + total / 4;
+            ADB_CUDA(cudaMalloc(&m->d_scratch, want));
+            ADB_CUDA(cudaMallocHost(&m->h_scratch, want));
+            m->scratch_bytes = want;
+        }
+    }
+    memcpy(m->h_scratch, dev.data(), (size_t)n * sizeof(BowDev));
+    if (!m->ev[0]) { ADB_CUDA(cudaEventCreate(&m->ev[0])); ADB_CUDA(cudaEventCreate(&m->ev[1])); }
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADB_CUDA(cudaFuncSetAttribute(bow_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ADB_SEARCH_MAX * 4 + 16));
+        attr_set = true;
+    }
+    ADB_CUDA(cudaMemcpyAsync(m->d_scratch, m->h_scratch, out_begin, cudaMemcpyHostToDevice, m->stream));
+    ADB_CUDA(cudaEventRecord(m->ev[0], m->stream));
+    bow_search_kernel<<<n, kSearchThreads, (size_t)2 * max_n2 * 4 + 16, m->stream>>>(reinterpret_cast<const BowDev*>(m->d_scratch));
+    ADB_CUDA(cudaGetLastError());
+    ADB_CUDA(cudaEventRecord(m->ev[1], m->stream));
+    ADB_CUDA(cudaMemcpyAsync(m->h_scratch + out_begin, m->d_scratch + out_begin, total - out_begin, cudaMemcpyDeviceToHost, m->stream));
+    ADB_CUDA(cudaStreamSynchronize(m->stream));
+    ADB_CUDA(cudaEventElapsedTime(&m->last_ms, m->ev[0], m->ev[1]));
+    for (int p = 0; p < n; ++p) {
+        adb_bow_search& s = probs[p];
+        const BowDev& D = dev[p];
+        auto host = [&](const void* dptr) { return m->h_scratch + ((const uint8_t*)dptr - m->d_scratch); };
+        if (s.mode == 0 && s.n2) memcpy(s.match21, host(D.match21), (size_t)s.n2 * 4);
+        if (s.mode == 1 && s.n1) memcpy(s.match12, host(D.match12), (size_t)s.n1 * 4);
+        memcpy(&s.n_matches, host(D.n_matches), 4);
     }
     return ADB_OK;
 }

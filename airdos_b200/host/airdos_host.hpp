@@ -151,6 +151,14 @@ public:
         return problem.n_matches;
     }
 
+    // SearchByBoW(pKF, F, vpMapPointMatches) (mode 0) / SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)
+    // (mode 1) (src/ORBmatcher.cc:159-288, 657-823) after the shim's FeatureVector walk has filled the per-node lists.
+    int SearchByBoW(adb_bow_search& problem) {
+        problem.nn_ratio = mfNNratio; problem.check_orientation = mbCheckOrientation ? 1 : 0;
+        airdos::check(adb_search_by_bow(m_, &problem, 1), "ORBmatcher::SearchByBoW");
+        return problem.n_matches;
+    }
+
 protected:
     float mfNNratio;
     bool mbCheckOrientation;

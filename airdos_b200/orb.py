@@ -293,6 +293,44 @@ class ORBmatcher:
         """One frame: returns (nmatches, kp_match, q_best_idx, q_best_dist)."""
         return self.search_by_projection([problem])[0]
 
+    def search_by_bow(self, problems: list[dict]):
+        """ORBmatcher::SearchByBoW(pKF, F, ...) (mode 0, src/ORBmatcher.cc:159-288) / SearchForTriangulation(pKF1, pKF2, F12, ...)
+        (mode 1, src/ORBmatcher.cc:657-823) on the per-node feature lists of the two FeatureVectors.  Problem dict: `mode`,
+        `kps1`, `desc1`, `flags1`, `kps2`, `desc2`, `b_ptr1`, `b_idx1`, `b_ptr2`, `b_idx2`; mode 0: `nn_ratio`; mode 1:
+        `u_right1`, `u_right2`, `flags2`, `f12`, `epipole`, `scale_factors2`, `level_sigma2_2`.
+        Returns a list of (nmatches, match): match21 [n2] for mode 0 (index on side 1 or -1), match12 [n1] for mode 1."""
+        from .capi import BowSearch
+        n = len(problems)
+        arr = (BowSearch * n)()
+        keep, outs = [], []
+
+        def a(x, dt):
+            x = np.ascontiguousarray(x, dt); keep.append(x); return x.ctypes.data
+
+        for i, pr in enumerate(problems):
+            S = arr[i]
+            S.mode = int(pr["mode"])
+            k1 = np.ascontiguousarray(pr["kps1"], KP_DTYPE); k2 = np.ascontiguousarray(pr["kps2"], KP_DTYPE); keep += [k1, k2]
+            S.n1, S.n2 = len(k1), len(k2)
+            S.kps1, S.kps2 = k1.ctypes.data, k2.ctypes.data
+            S.desc1 = a(pr["desc1"], np.uint8); S.desc2 = a(pr["desc2"], np.uint8); S.flags1 = a(pr["flags1"], np.uint8)
+            S.n_buckets = len(pr["b_ptr1"]) - 1
+            S.b_ptr1 = a(pr["b_ptr1"], np.int32); S.b_idx1 = a(pr["b_idx1"], np.int32)
+            S.b_ptr2 = a(pr["b_ptr2"], np.int32); S.b_idx2 = a(pr["b_idx2"], np.int32)
+            S.nn_ratio = float(pr.get("nn_ratio", self.mfNNratio))
+            S.check_orientation = int(pr.get("check_orientation", self.mbCheckOrientation))
+            if S.mode == 1:
+                S.u_right1 = a(pr["u_right1"], np.float32); S.u_right2 = a(pr["u_right2"], np.float32); S.flags2 = a(pr["flags2"], np.uint8)
+                S.f12 = a(pr["f12"], np.float32); S.ex, S.ey = [float(v) for v in pr["epipole"]]
+                sf = np.ascontiguousarray(pr["scale_factors2"], np.float32); keep.append(sf)
+                S.scale_factors2 = sf.ctypes.data; S.n_levels = len(sf); S.level_sigma2_2 = a(pr["level_sigma2_2"], np.float32)
+                out = np.full(S.n1, -1, np.int32); S.match12 = out.ctypes.data
+            else:
+                out = np.full(S.n2, -1, np.int32); S.match21 = out.ctypes.data
+            outs.append(out)
+        check(lib().adb_search_by_bow(self._m, C.byref(arr), n))
+        return [(int(arr[i].n_matches), outs[i]) for i in range(n)]
+
     def search_last_ms(self) -> float:
         ms = C.c_float()
         check(lib().adb_search_last_ms(self._m, C.byref(ms)))

@@ -407,3 +407,56 @@ def tracking_problem_as_fuse(pr: dict, seed: int = 0, th: float = 3.0) -> dict:
     sf = np.asarray(pr["scale_factors"], np.float32)
     out.update(fuse=1, inv_level_sigma2=(np.float32(1.0) / (sf * sf)).astype(np.float32), taken=None)
     return out
+
+
+def make_bow_problem(seed: int = 0, mode: int = 0, n1: int = 1800, n2: int = 2000, n_nodes: int = 400, n_levels: int = 8, scale: float = 1.2):
+    """Problem dict for ORBmatcher.search_by_bow.  Side 2 = a frame / key-frame with random key-points; side 1 = n1 features that
+    mostly re-observe a side-2 feature (descriptor with a few flipped bits, same vocabulary node, small rotation), shifted
+    along x like a second key-frame translated sideways (F12 of a pure x translation: horizontal epipolar lines, epipole at
+    infinity).  Vocabulary nodes are synthetic (DBoW2 is out of scope): node = source feature mod n_nodes, 10 % of the
+    side-1 features land in a random node; duplicates compete for the same partner (the first-come rule of SearchByBoW)."""
+    from .capi import KP_DTYPE
+    rng = np.random.default_rng(seed + 9000)
+    sf = np.ones(n_levels, np.float32)
+    for i in range(1, n_levels):
+        sf[i] = np.float32(sf[i - 1] * np.float32(scale))
+    quota = ORB_QUOTA_2000[:n_levels] / ORB_QUOTA_2000[:n_levels].sum()
+    k2 = np.zeros(n2, KP_DTYPE)
+    k2["x"] = rng.uniform(20, 620, n2).astype(np.float32); k2["y"] = rng.uniform(20, 460, n2).astype(np.float32)
+    k2["octave"] = rng.choice(n_levels, n2, p=quota); k2["angle"] = rng.uniform(0, 360, n2).astype(np.float32)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    ur2 = np.where(rng.random(n2) < 0.7, k2["x"] - rng.uniform(5, 60, n2), -1.0).astype(np.float32)
+    node2 = np.arange(n2) % n_nodes
+    src = rng.integers(0, n2, n1)
+    src[n1 - n1 // 5:] = src[rng.integers(0, n1 - n1 // 5, n1 // 5)]      # duplicates
+    src = src[rng.permutation(n1)]
+    k1 = np.zeros(n1, KP_DTYPE)
+    k1["x"] = (k2["x"][src] + rng.uniform(5, 40, n1)).astype(np.float32)
+    k1["y"] = (k2["y"][src] + rng.normal(0, 1.0, n1) * sf[k2["octave"][src]]).astype(np.float32)
+    k1["octave"] = k2["octave"][src]
+    rot = np.where(rng.random(n1) < 0.8, rng.normal(3.0, 3.0, n1), rng.uniform(0, 360, n1))
+    k1["angle"] = np.mod(k2["angle"][src] + rot, 360.0).astype(np.float32)
+    d1 = d2[src].copy()
+    flips = rng.integers(0, 70, n1)
+    for i in range(n1):
+        bits = rng.choice(256, flips[i], replace=False)
+        np.bitwise_xor.at(d1[i], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    ur1 = np.where(rng.random(n1) < 0.7, k1["x"] - rng.uniform(5, 60, n1), -1.0).astype(np.float32)
+    node1 = node2[src].copy()
+    stray = rng.random(n1) < 0.1
+    node1[stray] = rng.integers(0, n_nodes + 40, int(stray.sum()))       # some nodes exist on one side only
+    common = sorted(set(node1.tolist()) & set(node2.tolist()))
+    p1, i1, p2, i2 = [0], [], [0], []
+    for nd in common:                                                    # the FeatureVector walk keeps ascending node ids
+        a = np.nonzero(node1 == nd)[0]; b = np.nonzero(node2 == nd)[0]
+        i1 += a.tolist(); i2 += b.tolist(); p1.append(len(i1)); p2.append(len(i2))
+    pr = dict(mode=mode, kps1=k1, desc1=d1, kps2=k2, desc2=d2, b_ptr1=np.array(p1, np.int32), b_idx1=np.array(i1, np.int32),
+              b_ptr2=np.array(p2, np.int32), b_idx2=np.array(i2, np.int32), nn_ratio=0.7, check_orientation=1)
+    if mode == 0:
+        pr["flags1"] = (rng.random(n1) < 0.85).astype(np.uint8)         # key-points of the key-frame that hold a good map point
+    else:
+        pr["flags1"] = (rng.random(n1) < 0.6).astype(np.uint8)          # not triangulated yet
+        pr.update(flags2=(rng.random(n2) < 0.6).astype(np.uint8), u_right1=ur1, u_right2=ur2,
+                  f12=np.array([0, 0, 0, 0, 0, -1, 0, 1, 0], np.float32), epipole=(1.0e6, 240.0), scale_factors2=sf,
+                  level_sigma2_2=(sf * sf).astype(np.float32))
+    return pr

@@ -267,6 +267,50 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* problems, 
 /* Device time in ms of the kernels of the last adb_search_by_projection call. */
 adb_status adb_search_last_ms(adb_matcher_t m, float* ms);
 
+/* ---------------------------------------------------------------------------------------
+ * Vocabulary-bucket searches: ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)  (src/ORBmatcher.cc:159-288)
+ * and ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  (src/ORBmatcher.cc:657-823, with
+ * CheckDistEpipolarLine, :131-157).  DBoW2 stays on the host (out of scope): the shim walks the two FeatureVectors as the
+ * reference does (:183-245 / :692-775) and hands over, per common vocabulary node, the feature indices of both sides
+ * in the reference's order (CSR).  Everything else -- Hamming scans, the first-come rule of SearchByBoW (a matched
+ * key-point is closed to later queries), ratio test, epipole / epipolar-line gates, rotation histogram -- runs on the device.
+ * One problem = one (key-frame, frame) or (key-frame, key-frame) pair; all pointers are host memory. */
+typedef struct adb_bow_search {
+    int32_t mode;                  /* 0 = SearchByBoW, 1 = SearchForTriangulation */
+    /* side 1 (queries): pKF / pKF1 */
+    int32_t n1;
+    const adb_keypoint* kps1;      /* mvKeysUn */
+    const float* u_right1;         /* mvuRight (mode 1) */
+    const uint8_t* desc1;          /* mDescriptors */
+    const uint8_t* flags1;         /* [n1] bit 0: takes part.  mode 0: map point present and not bad (:196-202);
+                                      mode 1: no map point yet and (stereo || !bOnlyStereo) (:703-712) */
+    /* side 2 (targets): F / pKF2 */
+    int32_t n2;
+    const adb_keypoint* kps2;      /* mode 0: F.mvKeys (angle, :228); mode 1: pKF2->mvKeysUn */
+    const float* u_right2;
+    const uint8_t* desc2;
+    const uint8_t* flags2;         /* [n2] bit 0: may be taken.  mode 0: all 1; mode 1: no map point and (stereo || !bOnlyStereo) (:726-735) */
+    /* common vocabulary nodes, ascending node id */
+    int32_t n_buckets;
+    const int32_t* b_ptr1;         /* [n_buckets + 1] into b_idx1 */
+    const int32_t* b_idx1;         /* feature indices of side 1 per node, in FeatureVector order */
+    const int32_t* b_ptr2;
+    const int32_t* b_idx2;
+    float nn_ratio;                /* mfNNratio (mode 0) */
+    int32_t check_orientation;     /* mbCheckOrientation */
+    /* mode 1 only */
+    const float* f12;              /* row-major 3x3 */
+    float ex, ey;                  /* epipole of camera 1 in image 2 (:663-670) */
+    const float* scale_factors2;   /* pKF2->mvScaleFactors */
+    const float* level_sigma2_2;   /* pKF2->mvLevelSigma2 */
+    int32_t n_levels;
+    /* results */
+    int32_t* match21;              /* mode 0, [n2]: vpMapPointMatches as the index (side 1) of the key-point whose map point it holds, -1 none */
+    int32_t* match12;              /* mode 1, [n1]: vMatches12 (index in side 2 or -1) */
+    int32_t n_matches;
+} adb_bow_search;
+adb_status adb_search_by_bow(adb_matcher_t m, adb_bow_search* problems, int32_t n_problems);
+
 /* Frame::ComputeStereoMatches()  (src/Frame.cc:829-1003) for the n_frames frames resident in
  * the two extractor handles (frame i of `left` against frame i of `right`): row-band Hamming
  * match, 11x11 SAD sub-pixel refinement on the pyramids, median-distance cut.

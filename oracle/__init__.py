@@ -285,6 +285,32 @@ def search_by_projection(pr: dict, nn_ratio: float = 0.6, check_orientation: boo
     return int(n), km, bi, bd, dict(q_u=qu, q_v=qv, q_ur=qur, q_radius=qr, q_min_level=qmin, q_max_level=qmax, q_flags=qfl, **extra)
 
 
+def search_by_bow(pr: dict, nn_ratio: float = 0.6, check_orientation: bool = True):
+    """SearchByBoW / SearchForTriangulation restatement on the problem dicts of ORBmatcher.search_by_bow -> (nmatches, match)."""
+    lib = _match_lib()
+    mode = int(pr["mode"])
+    k1 = np.ascontiguousarray(pr["kps1"], KP_DTYPE); k2 = np.ascontiguousarray(pr["kps2"], KP_DTYPE)
+    d1 = np.ascontiguousarray(pr["desc1"], np.uint8); d2 = np.ascontiguousarray(pr["desc2"], np.uint8)
+    f1 = np.ascontiguousarray(pr["flags1"], np.uint8)
+    n1, n2 = len(k1), len(k2)
+    z = np.zeros(max(n1, n2, 1), np.float32); zf = np.ones(max(n2, 1), np.uint8)
+    ur1 = np.ascontiguousarray(pr.get("u_right1", z[:n1]), np.float32); ur2 = np.ascontiguousarray(pr.get("u_right2", z[:n2]), np.float32)
+    f2 = np.ascontiguousarray(pr.get("flags2", zf[:n2]), np.uint8)
+    p1, i1, p2, i2 = [np.ascontiguousarray(pr[k], np.int32) for k in ("b_ptr1", "b_idx1", "b_ptr2", "b_idx2")]
+    F = np.ascontiguousarray(pr.get("f12", np.zeros(9)), np.float32)
+    ex, ey = [float(v) for v in pr.get("epipole", (0.0, 0.0))]
+    sf = np.ascontiguousarray(pr.get("scale_factors2", np.ones(8)), np.float32)
+    sg = np.ascontiguousarray(pr.get("level_sigma2_2", np.ones(8)), np.float32)
+    m21 = np.zeros(max(n2, 1), np.int32); m12 = np.zeros(max(n1, 1), np.int32)
+    lib.match_oracle_bow_search.restype = C.c_int
+    lib.match_oracle_bow_search.argtypes = ([C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 4 +
+                                            [C.c_float, C.c_int, C.c_void_p, C.c_float, C.c_float] + [C.c_void_p] * 4)
+    n = lib.match_oracle_bow_search(mode, _p(k1), _p(ur1), _p(d1), _p(f1), n1, _p(k2), _p(ur2), _p(d2), _p(f2), n2, len(p1) - 1,
+                                    _p(p1), _p(i1), _p(p2), _p(i2), float(pr.get("nn_ratio", nn_ratio)),
+                                    int(pr.get("check_orientation", check_orientation)), _p(F), ex, ey, _p(sf), _p(sg), _p(m21), _p(m12))
+    return int(n), (m21[:n2] if mode == 0 else m12[:n1])
+
+
 def stereo_match(kl, dl, kr, dr, pyr_l, pyr_r, scale, mb: float, mbf: float, stage: int = 0):
     """Frame::ComputeStereoMatches restatement.  pyr_l / pyr_r: lists of level ROIs (u8 2-D).
     Returns (uRight, depth, ham_idx, ham_dist)."""

@@ -487,4 +487,101 @@ int match_oracle_fuse_search(const void* kps_, const float* u_right, const uint8
     return nFused;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:159-288) and ORBmatcher::SearchForTriangulation
+// (src/ORBmatcher.cc:657-823, CheckDistEpipolarLine :131-157) on the bucket lists the FeatureVector walk produces.  Sequential
+// like the reference.  Note SearchForTriangulation never sets vbMatched2 (:680, :729): two key-points of frame 1 may end up
+// with the same partner, exactly as in the reference.  Its update rule "dist > bestDist -> skip" lets a LATER candidate
+// with an equal distance replace the best one.
+int match_oracle_bow_search(int mode, const void* kps1_, const float* ur1, const uint8_t* d1, const uint8_t* fl1, int n1,
+                            const void* kps2_, const float* ur2, const uint8_t* d2, const uint8_t* fl2, int n2, int n_buckets,
+                            const int32_t* p1, const int32_t* i1, const int32_t* p2, const int32_t* i2, float nn_ratio, int check_ori,
+                            const float* F12, float ex, float ey, const float* scale_factors2, const float* level_sigma2_2,
+                            int32_t* match21, int32_t* match12) {
+    const KeyPoint* k1 = (const KeyPoint*)kps1_;
+    const KeyPoint* k2 = (const KeyPoint*)kps2_;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    if (mode == 0) for (int i = 0; i < n2; ++i) match21[i] = -1;
+    else for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (int b = 0; b < n_buckets; ++b) {
+        for (int a = p1[b]; a < p1[b + 1]; ++a) {
+            const int idx1 = i1[a];
+            if (!(fl1[idx1] & 1)) continue;
+            if (mode == 0) {
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int c = p2[b]; c < p2[b + 1]; ++c) {
+                    const int idxF = i2[c];
+                    if (match21[idxF] >= 0) continue;
+                    const int dist = hamming256(d1 + (size_t)idx1 * 32, d2 + (size_t)idxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = idxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW && (float)bestDist1 < nn_ratio * (float)bestDist2) {
+                    match21[bestIdxF] = idx1;
+                    if (check_ori) {
+                        float rot = k1[idx1].angle - k2[bestIdxF].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(bestIdxF);
+                    }
+                    ++nmatches;
+                }
+            } else {
+                const bool bStereo1 = ur1[idx1] >= 0;
+                const KeyPoint& kp1 = k1[idx1];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int c = p2[b]; c < p2[b + 1]; ++c) {
+                    const int idx2 = i2[c];
+                    if (!(fl2[idx2] & 1)) continue;
+                    const bool bStereo2 = ur2[idx2] >= 0;
+                    const int dist = hamming256(d1 + (size_t)idx1 * 32, d2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const KeyPoint& kp2 = k2[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scale_factors2[kp2.octave]) continue;
+                    }
+                    // CheckDistEpipolarLine
+                    const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                    const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                    const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                    const float num = la * kp2.x + lb * kp2.y + lc;
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if ((double)dsqr < 3.84 * (double)level_sigma2_2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    ++nmatches;
+                    if (check_ori) {
+                        float rot = kp1.angle - k2[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)std::round(rot * factor);
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int idx : rotHist[i]) { if (mode == 0) match21[idx] = -1; else match12[idx] = -1; --nmatches; }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

@@ -199,3 +199,80 @@ def test_fuse_search_matches_brute_force():
         nf += best <= 50
     # u, v come from float64 here: a candidate right at the chi2 gate or the window edge may flip
     assert checked > 200 and agree >= checked - 3 and abs(nf - n) <= 3 and n > 100
+
+
+def _bow_brute_force(pr):
+    """Independent formulation: per query a numpy distance vector over its bucket; closures as a set."""
+    k1, k2, d1, d2 = pr["kps1"], pr["kps2"], pr["desc1"], pr["desc2"]
+    mode = pr["mode"]
+    taken = set(); pairs = []          # (idx1, idx2) in acceptance order
+    bits1 = np.unpackbits(d1, axis=1).astype(np.int16); bits2 = np.unpackbits(d2, axis=1).astype(np.int16)
+    for b in range(len(pr["b_ptr1"]) - 1):
+        q = pr["b_idx1"][pr["b_ptr1"][b]:pr["b_ptr1"][b + 1]]; t = pr["b_idx2"][pr["b_ptr2"][b]:pr["b_ptr2"][b + 1]]
+        for i in q:
+            if not pr["flags1"][i] & 1:
+                continue
+            if mode == 0:
+                cand = [j for j in t if j not in taken]
+                if not cand:
+                    continue
+                dist = np.abs(bits1[i] - bits2[cand]).sum(1)
+                o = np.argsort(dist, kind="stable")
+                best = int(dist[o[0]]); second = int(dist[o[1]]) if len(o) > 1 else 256
+                if best <= 50 and np.float32(best) < np.float32(pr["nn_ratio"]) * np.float32(second):
+                    taken.add(cand[o[0]]); pairs.append((i, cand[o[0]]))
+            else:
+                F = pr["f12"].reshape(3, 3); x1, y1 = k1["x"][i], k1["y"][i]
+                la = np.float32(np.float32(x1 * F[0, 0] + y1 * F[1, 0]) + F[2, 0]); lb = np.float32(np.float32(x1 * F[0, 1] + y1 * F[1, 1]) + F[2, 1])
+                lc = np.float32(np.float32(x1 * F[0, 2] + y1 * F[1, 2]) + F[2, 2])
+                best, bj = 51, -1
+                for j in t:
+                    if not pr["flags2"][j] & 1:
+                        continue
+                    d = int(np.abs(bits1[i] - bits2[j]).sum())
+                    if d > 50 or d > best:
+                        continue
+                    if pr["u_right1"][i] < 0 and pr["u_right2"][j] < 0:
+                        ex, ey = pr["epipole"]
+                        if (np.float32(ex) - k2["x"][j]) ** 2 + (np.float32(ey) - k2["y"][j]) ** 2 < 100 * pr["scale_factors2"][k2["octave"][j]]:
+                            continue
+                    num = np.float32(np.float32(la * k2["x"][j] + lb * k2["y"][j]) + lc); den = np.float32(la * la + lb * lb)
+                    if den == 0 or not float(np.float32(num * num / den)) < 3.84 * float(pr["level_sigma2_2"][k2["octave"][j]]):
+                        continue
+                    best, bj = d, j
+                if bj >= 0:
+                    pairs.append((i, bj))
+    bins = {}
+    for i, j in pairs:
+        rot = np.float32(k1["angle"][i] - k2["angle"][j])
+        if rot < 0:
+            rot = np.float32(rot + np.float32(360))
+        b = int(np.floor(np.float32(rot * np.float32(1.0 / 30)) + np.float32(0.5)))
+        bins.setdefault(0 if b == 30 else b, []).append((i, j))
+    sizes = sorted(((len(v), -k) for k, v in bins.items()), reverse=True)
+    keep = []
+    if sizes:
+        m1 = sizes[0][0]; keep.append(-sizes[0][1])
+        if len(sizes) > 1 and not sizes[1][0] < 0.1 * m1:
+            keep.append(-sizes[1][1])
+            if len(sizes) > 2 and not sizes[2][0] < 0.1 * m1:
+                keep.append(-sizes[2][1])
+    out = np.full(len(k2) if mode == 0 else len(k1), -1)
+    n = 0
+    for k, v in bins.items():
+        if k in keep:
+            for i, j in v:
+                if mode == 0:
+                    out[j] = i
+                else:
+                    out[i] = j
+                n += 1
+    return n, out
+
+
+@pytest.mark.parametrize("mode,seed", [(0, 1), (0, 2), (1, 3), (1, 4)])
+def test_bow_searches_match_brute_force(mode, seed):
+    pr = synth.make_bow_problem(seed, mode, n1=500, n2=600, n_nodes=80)
+    n, m = oracle.search_by_bow(pr)
+    nb, mb = _bow_brute_force(pr)
+    assert n == nb and (m == mb).all() and n > 30

@@ -93,3 +93,21 @@ def test_fuse_candidate_search_on_device(adb, oracle_mod):
         _same(got[:4], ref)
         assert ref[0] > 200
     m.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["SearchByBoW", "SearchForTriangulation"])
+def test_bow_searches_on_device(adb, oracle_mod, mode):
+    m = adb.ORBmatcher(0.7, True)
+    probs = [synth.make_bow_problem(50 + s, mode, n1=1500 + 300 * s, n2=2000, n_nodes=nn) for s, nn in ((0, 400), (1, 60), (2, 1500))]
+    p_noori = dict(probs[0]); p_noori["check_orientation"] = 0
+    p_none = dict(probs[1]); p_none["flags1"] = np.zeros_like(p_none["flags1"])
+    probs += [p_noori, p_none]
+    got = m.search_by_bow(probs)
+    for g, pr in zip(got, probs):
+        n, match = oracle_mod.search_by_bow(pr)
+        assert g[0] == n and (g[1] == match).all(), (g[0], n)
+    assert got[0][0] > 100 and got[4][0] == 0
+    # one problem per call gives the same
+    one = m.search_by_bow([probs[2]])[0]
+    assert one[0] == got[2][0] and (one[1] == got[2][1]).all()
+    m.close()
