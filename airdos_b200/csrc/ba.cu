@@ -894,7 +894,7 @@ __device__ __forceinline__ void chol_panel(double* A, int n, int n_rows, int kb,
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             na[h] = (i0 + r + 16 * h < n_rows) ? A[(size_t)(i0 + r + 16 * h) * n + c] : 0.0;
-            nb[h] = A[(size_t)(k + r + 16 * h) * n + c];
+            nb[h] = (k + r + 16 * h < n_rows) ? A[(size_t)(k + r + 16 * h) * n + c] : 0.0;   // last panel: rows past the array
         }
     }
     for (int p0 = 0; p0 < k; p0 += kCholNB) {
@@ -905,7 +905,7 @@ __device__ __forceinline__ void chol_panel(double* A, int n, int n_rows, int kb,
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 na[h] = (i0 + r + 16 * h < n_rows) ? A[(size_t)(i0 + r + 16 * h) * n + p0 + kCholNB + c] : 0.0;
-                nb[h] = A[(size_t)(k + r + 16 * h) * n + p0 + kCholNB + c];
+                nb[h] = (k + r + 16 * h < n_rows) ? A[(size_t)(k + r + 16 * h) * n + p0 + kCholNB + c] : 0.0;
             }
         }
 #pragma unroll

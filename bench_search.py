@@ -47,6 +47,24 @@ def run(device: int = 0, steps: int = 5, frames: int = 128, with_cpu: bool = Tru
         out["cpu_baseline"] = {"value": sum(len(p["q_flags"]) for p in base) / t, "unit": "queries/s", "cores": 1, "kind": "port",
                                "sample": f"{len(base)} of the frames, oracle port on 1 host thread (the reference searches on the tracking thread)"}
         out["parity"] = {"kp_match_equal": bool((g[1] == ref[1]).all()), "nmatches_equal": g[0] == ref[0]}
+    # vocabulary-bucket searches (SearchByBoW / SearchForTriangulation), 64 key-frame pairs per call
+    bow = {}
+    for mode, name in ((0, "SearchByBoW"), (1, "SearchForTriangulation")):
+        bprobs = [synth.make_bow_problem(700 + i, mode) for i in range(4)] * 16
+        nqb = sum(len(p["b_idx1"]) for p in bprobs)
+        for _ in range(2):
+            m.search_by_bow(bprobs)
+        ms = []
+        for _ in range(steps):
+            m.search_by_bow(bprobs)
+            ms.append(m.search_last_ms())
+        bow[name] = {"queries_per_s": nqb / (float(np.median(ms)) * 1e-3), "ms_per_64_pairs": float(np.median(ms))}
+        if with_cpu:
+            t0 = time.perf_counter()
+            for p in bprobs[:4]:
+                oracle.search_by_bow(p)
+            bow[name]["cpu_port_queries_per_s"] = sum(len(p["b_idx1"]) for p in bprobs[:4]) / (time.perf_counter() - t0)
+    out["bow"] = bow
     m.close()
     return out
 
