@@ -11,13 +11,15 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --steps 2 --warmup 3 --pairs 128 --no-cpu-baseline > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fast_cells|pyr_resize|orient_describe|quadtree|stereo_' -s 22 -c 15 \
   -f -o gpurun_out/${TAG}_orb python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba > gpurun_out/${TAG}_ncu_orb.log 2>&1; echo "orb rc=$?"
-timeout 900 ncu --set full --clock-control none -k regex:'ba_|chol_|pose_opt' -s 200 -c 24 \
+timeout 900 ncu --set full --clock-control none -k regex:'ba_|chol_|pose_opt' -s 200 -c 20 \
   -f -o gpurun_out/${TAG}_ba python bench_ba.py > gpurun_out/${TAG}_ncu_ba.log 2>&1; echo "ba rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'proj_search|project_last' -s 4 -c 2 \
+timeout 900 ncu --set full --clock-control none -k regex:'proj_search|project_last' -s 6 -c 2 \
   -f -o gpurun_out/${TAG}_search python bench_search.py > gpurun_out/${TAG}_ncu_search.log 2>&1; echo "search rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:'bow_search' -s 2 -c 1 \
+  -f -o gpurun_out/${TAG}_bow python bench_search.py > gpurun_out/${TAG}_ncu_bow.log 2>&1; echo "bow rc=$?"
 # gpurun copies back at most 64 MiB: keep the raw-metric CSV of every report, the .ncu-rep (source view) only for the extractor
-for r in orb ba search; do
+for r in orb ba search bow; do
   ncu -i gpurun_out/${TAG}_$r.ncu-rep --page raw --csv > gpurun_out/${TAG}_${r}_raw.csv 2>/dev/null
 done
-rm -f gpurun_out/${TAG}_ba.ncu-rep gpurun_out/${TAG}_search.ncu-rep
+rm -f gpurun_out/${TAG}_ba.ncu-rep gpurun_out/${TAG}_search.ncu-rep gpurun_out/${TAG}_bow.ncu-rep
 ls -la gpurun_out/ | tail -20
