@@ -53,3 +53,32 @@ def test_product_package_never_imports_the_oracle():
                 for bad in ("import oracle", "from oracle", "liborb_oracle", "libba_oracle", "oracle/_build", "oracle/_ref"):
                     assert bad not in src, (f, bad)
                 assert not re.search(r'#include\s*"[^"]*oracle', src), f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Every ctypes mirror has the size and field offsets the C compiler gives the header's struct (a drifted mirror would
+    corrupt memory silently: the library reads the caller's struct)."""
+    import ctypes as C
+    import subprocess
+    from airdos_b200 import ba_types as T, capi
+    pairs = {"adb_orb_config": capi.OrbConfig, "adb_gather_targets": capi.GatherTargets, "adb_proj_search": capi.ProjSearch,
+             "adb_bow_search": capi.BowSearch, "adb_ba_options": T.BAOptions, "adb_ba_problem": T.BAProblem,
+             "adb_ba_result": T.BAResult, "adb_pose_problem": T.PoseProblem}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "airdos_b200.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, *_ in ct._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"; exe = tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line in out:
+        f = line.split()
+        ct = pairs[f[0]]
+        assert int(f[1]) == C.sizeof(ct), (f[0], f[1], C.sizeof(ct))
+        for (fname, *_), off in zip(ct._fields_, f[2:]):
+            assert getattr(ct, fname).offset == int(off), (f[0], fname)
