@@ -350,7 +350,7 @@ def main():
         v, ms, _ = cpu_reference_run(sample, threads, 2, 1)
         out["cpu_baseline"] = {"value": v, "unit": "keypoints/s", "cores": threads, "kind": "port",
                                "sample": f"2 passes over {n_s} stereo pairs ({2 * n_s} frames) of the same workload, oracle port, {threads} host threads"}
-    if not args.no_ba and rank == 0:
+    if not args.no_ba and rank == 0 and world == 1:   # single-GPU sections (BA stays single-GPU; replicas only)
         try:
             import bench_ba
             out["ba"] = bench_ba.run(local, steps=max(3, K // 2))
@@ -358,7 +358,7 @@ def main():
             pass
         except Exception as e:   # the headline metric must still print
             out["ba"] = {"error": repr(e)}
-    if not args.no_ba and rank == 0:
+    if not args.no_ba and rank == 0 and world == 1:
         try:
             import bench_search
             out["search"] = bench_search.run(local, steps=max(3, K // 2))
