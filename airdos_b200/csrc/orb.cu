@@ -2,7 +2,7 @@
 //
 // Replaces ORB_SLAM2::ORBextractor (src/ORBextractor.cc) for a batch of F frames:
 //
-//   pyr_resize_kernel        ComputePyramid                src/ORBextractor.cc:1121-1156
+//   pyr_resize_strip_kernel  ComputePyramid                src/ORBextractor.cc:1121-1156
 //   fast_cells_kernel        per-cell FAST + ini/min rule  src/ORBextractor.cc:791-840
 //   quadtree_kernel          DistributeOctTree             src/ORBextractor.cc:541-765
 //   orient_describe_kernel   IC_Angle + GaussianBlur + computeOrbDescriptor

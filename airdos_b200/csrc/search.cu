@@ -1,6 +1,10 @@
-// search.cu -- guided window searches on the Frame grid (candidate generation on the device).
+// search.cu -- guided searches of ORBmatcher with the candidate generation on the device.
 //
 //   project_last_kernel    head of SearchByProjection(Current, Last)     src/ORBmatcher.cc:1338-1393
+//   frustum_kernel         Frame::isInFrustum + MapPoint::PredictScale   src/Frame.cc:587-643, src/MapPoint.cc:405-420
+//                          (and the projection head of ORBmatcher::Fuse  src/ORBmatcher.cc:845-889)
+//   bow_search_kernel      SearchByBoW(KF, Frame) / SearchForTriangulation + CheckDistEpipolarLine
+//                                                                        src/ORBmatcher.cc:159-288, 657-823, 131-157
 //   proj_search_kernel     Frame::AssignFeaturesToGrid / PosInGrid       src/Frame.cc:534-549, 700-712
 //                          Frame::GetFeaturesInArea                      src/Frame.cc:645-698
 //                          SearchByProjection(Frame, vpMapPoints, th)    src/ORBmatcher.cc:45-129
