@@ -173,3 +173,98 @@ def test_pose_optimization_oracle(oracle_mod):
     tiny = dict(frames[0]); tiny["xw"] = tiny["xw"][:2]; tiny["obs"] = tiny["obs"][:2]; tiny["inv_sigma2"] = tiny["inv_sigma2"][:2]
     pb2 = oracle_mod.pose_optimize(cam, [tiny])
     assert pb2.n_inliers[0] == 0 and (pb2.pose_t[0] == frames[0]["pose_t"]).all()
+
+
+def _residuals_g2o(d, pose_q, pose_t, points):
+    """Residual with the reference's arithmetic quirk: EdgeStereoSE3ProjectXYZ::cam_project keeps 1 / z in a float
+    (Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:152-161); the monocular edge divides in double."""
+    R = np.array([_q2R(q) for q in pose_q])
+    Xc = np.einsum("eij,ej->ei", R[d["edge_pose"]], points[d["edge_point"]]) + pose_t[d["edge_pose"]]
+    mono = d["edge_obs"][:, 2] < 0
+    invz = np.where(mono, 1.0 / Xc[:, 2], (1.0 / Xc[:, 2]).astype(np.float32).astype(np.float64))
+    u = Xc[:, 0] * invz * d["fx"] + d["cx"]
+    v = Xc[:, 1] * invz * d["fy"] + d["cy"]
+    ur = u - d["bf"] * invz
+    e = d["edge_obs"] - np.stack([u, v, ur], 1)
+    e[mono, 2] = 0
+    return e
+
+
+@pytest.mark.parametrize("seed,mono_frac,point_noise,pose_noise,tau,its", [(23, 0.0, 0.05, 0.02, 1e-5, 5), (26, 0.7, 8.0, 0.5, 1e-10, 6)],
+                         ids=["all_accepted", "with_rejections"])
+def test_lm_trajectory_matches_an_independent_numpy_levenberg(oracle_mod, seed, mono_frac, point_noise, pose_noise, tau, its):
+    """The whole LM control loop of g2o (optimization_algorithm_levenberg.cpp:61-189: lambda_0 = tau * max diag, trial loop with
+    push / pop, rho = (chi2 - chi2_trial) / (x.(lambda x + b) + 1e-3), lambda *= max(1/3, min(2/3, 1 - (2 rho - 1)^3)) or
+    *= ni, ni *= 2) restated independently: dense normal equations over ALL unknowns (no Schur complement), Jacobian by central
+    differences of the smooth projection model, Huber IRLS weights, numpy solve.  The oracle's trace (lambda, chi2 before /
+    after, accept flag per trial) must follow it."""
+    d = synth.make_ba_problem(4, 40, 4, seed=seed, mono_frac=mono_frac)
+    rng = np.random.default_rng(seed - 20)
+    d["pose_t"][1:] += rng.normal(0, pose_noise, d["pose_t"][1:].shape)      # far enough from the optimum for several steps
+    d["points"] = d["points"] + rng.normal(0, point_noise, d["points"].shape)
+    K, P, E = len(d["pose_t"]), len(d["points"]), len(d["edge_pose"])
+    free = [k for k in range(K) if not d["pose_fixed"][k]]
+    off = {k: 6 * i for i, k in enumerate(free)}
+    nd = 6 * len(free); n = nd + 3 * P
+    delta = np.where(d["edge_obs"][:, 2] >= 0, np.float32(np.sqrt(7.815)), np.float32(np.sqrt(5.991))).astype(np.float64)
+
+    def apply(st, x):
+        pq, pt, X = st[0].copy(), st[1].copy(), st[2].copy()
+        for k in free:
+            Tm = np.eye(4); Tm[:3, :3] = _q2R(pq[k]); Tm[:3, 3] = pt[k]
+            Tn = _se3_exp(x[off[k]:off[k] + 6]) @ Tm
+            m = Tn[:3, :3]
+            w = np.sqrt(max(0, 1 + m[0, 0] + m[1, 1] + m[2, 2])) / 2
+            pq[k] = np.array([(m[2, 1] - m[1, 2]) / (4 * w), (m[0, 2] - m[2, 0]) / (4 * w), (m[1, 0] - m[0, 1]) / (4 * w), w])
+            pt[k] = Tn[:3, 3]
+        return pq, pt, X + x[nd:].reshape(P, 3)
+
+    def robust_chi2(st):
+        e = _residuals_g2o(d, *st)
+        chi = (e ** 2 * d["edge_info"][:, None]).sum(1)
+        rho = np.where(chi <= delta ** 2, chi, 2 * delta * np.sqrt(chi) - delta ** 2)
+        return float(rho.sum()), e, chi
+
+    st = (d["pose_q"].copy(), d["pose_t"].copy(), d["points"].copy())
+    lam, ni, trace = None, 2.0, []
+    for it in range(its):
+        cur, e0, chi = robust_chi2(st)
+        Jm = np.zeros((3 * E, n)); h = 1e-6
+        for j in range(n):
+            dx = np.zeros(n); dx[j] = h
+            Jm[:, j] = ((_residuals(d, *apply(st, dx)) - _residuals(d, *apply(st, -dx))) / (2 * h)).ravel()
+        rho1 = np.where(chi <= delta ** 2, 1.0, delta / np.sqrt(np.maximum(chi, 1e-300)))
+        Wd = np.repeat(d["edge_info"] * rho1, 3)
+        Hm = Jm.T @ (Wd[:, None] * Jm); bm = -Jm.T @ (Wd * e0.ravel())
+        if it == 0:
+            lam = tau * np.abs(np.diag(Hm)).max()
+        q = 0
+        while True:
+            x = np.linalg.solve(Hm + lam * np.eye(n), bm)
+            trial = apply(st, x)
+            tmp = robust_chi2(trial)[0]
+            rho = (cur - tmp) / (float(x @ (lam * x + bm)) + 1e-3)
+            ok = rho > 0 and np.isfinite(tmp)
+            trace.append((lam, cur, tmp, ok))
+            if ok:
+                lam *= max(1.0 / 3.0, min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0)); ni = 2.0
+                st, cur = trial, tmp
+            else:
+                lam *= ni; ni *= 2
+            q += 1
+            if not (rho < 0 and q < 10):
+                break
+    o = oracle_mod.ba_default_options()
+    o.iterations[0] = its; o.iterations[1] = 0; o.tau = tau
+    p, r, status = oracle_mod.ba_solve(d, o)
+    tr = r.trace_rows
+    assert status == 0 and len(tr) == len(trace) >= 5
+    if mono_frac > 0:
+        assert not all(t[3] for t in trace), "this case is meant to exercise rejected trials"
+    ref = np.array([(t[0], t[1], t[2]) for t in trace])
+    assert np.allclose(tr[:, 0], ref[:, 0], rtol=1e-5), (tr[:, 0], ref[:, 0])       # lambda of every trial
+    # chi2 before / after; the far-from-optimum case (chi2 ~ 1e6, rejected overshoots) amplifies the finite-difference Jacobian
+    assert np.allclose(tr[:, 1:3], ref[:, 1:3], rtol=1e-6 if mono_frac == 0 else 1e-5)
+    assert [bool(a) for a in tr[:, 4]] == [t[3] for t in trace]
+    assert np.abs(p["pose_t"] - st[1]).max() < (1e-6 if mono_frac == 0 else 1e-4)
+    assert np.abs(p["points"] - st[2]).max() < (1e-5 if mono_frac == 0 else 1e-3)
