@@ -268,3 +268,102 @@ def test_lm_trajectory_matches_an_independent_numpy_levenberg(oracle_mod, seed, 
     assert [bool(a) for a in tr[:, 4]] == [t[3] for t in trace]
     assert np.abs(p["pose_t"] - st[1]).max() < (1e-6 if mono_frac == 0 else 1e-4)
     assert np.abs(p["points"] - st[2]).max() < (1e-5 if mono_frac == 0 else 1e-3)
+
+
+def test_dynamic_lm_trajectory_with_rigidity_edges_matches_numpy(oracle_mod):
+    """The articulated part of LocalBundleAdjustmentHumanTrajactory that is a true least-squares model -- non-marginalised
+    joint vertices with stereo observations (src/Optimizer.cc:1775-1843), VertexDistanceDouble bone lengths and
+    EdgeRigidBodyDouble e = |Ji - Jj| - d (include/g2o_edge_rigidbody.h:67-149) -- against the same independent numpy LM:
+    dense normal equations over [poses | bone lengths | joints | points], finite-difference Jacobian.  (The motion edges are
+    left out here: by convention D.6 their Jacobian is deliberately not the derivative of the residual.)"""
+    d = synth.make_ba_problem(8, 60, 4, seed=31, humans=1, human_poses=2)
+    for k in ("medge_p1", "medge_p2", "medge_motion"):
+        d[k] = np.zeros(0, np.int32)
+    d["medge_dt"] = np.zeros(0); d["medge_info"] = np.zeros(0)
+    d["motion_q"] = np.zeros((0, 4)); d["motion_t"] = np.zeros((0, 3))
+    rng = np.random.default_rng(5)
+    d["joints"] = d["joints"] + rng.normal(0, 0.05, d["joints"].shape)
+    d["dists"] = d["dists"] + rng.normal(0, 0.05, d["dists"].shape)
+    K, P, E = len(d["pose_t"]), len(d["points"]), len(d["edge_pose"])
+    NJ, ND = len(d["joints"]), len(d["dists"])
+    free = [k for k in range(K) if not d["pose_fixed"][k]]
+    off = {k: 6 * i for i, k in enumerate(free)}
+    nd = 6 * len(free)
+    o_d, o_j, o_p = nd, nd + ND, nd + ND + 3 * NJ
+    n = o_p + 3 * P
+    opt = oracle_mod.ba_default_options()
+    opt.iterations[0] = 5; opt.iterations[1] = 0
+    hs, hr = opt.huber_stereo, opt.huber_rigid
+
+    def apply(st, x):
+        pq, pt, X, J, D = [a.copy() for a in st]
+        for k in free:
+            Tm = np.eye(4); Tm[:3, :3] = _q2R(pq[k]); Tm[:3, 3] = pt[k]
+            Tn = _se3_exp(x[off[k]:off[k] + 6]) @ Tm
+            m = Tn[:3, :3]
+            w = np.sqrt(max(0, 1 + m[0, 0] + m[1, 1] + m[2, 2])) / 2
+            pq[k] = np.array([(m[2, 1] - m[1, 2]) / (4 * w), (m[0, 2] - m[2, 0]) / (4 * w), (m[1, 0] - m[0, 1]) / (4 * w), w])
+            pt[k] = Tn[:3, 3]
+        return pq, pt, X + x[o_p:].reshape(P, 3), J + x[o_j:o_p].reshape(NJ, 3), D + x[o_d:o_j]
+
+    def residuals(st, smooth):
+        pq, pt, X, J, D = st
+        f = _residuals if smooth else _residuals_g2o
+        e_s = f(d, pq, pt, X)
+        dj = dict(d, edge_pose=d["jedge_pose"], edge_point=d["jedge_joint"], edge_obs=d["jedge_obs"])
+        e_j = f(dj, pq, pt, J)
+        e_r = np.linalg.norm(J[d["redge_i"]] - J[d["redge_j"]], axis=1) - D[d["redge_dist"]]
+        return e_s, e_j, e_r
+
+    def parts(st, smooth=False):
+        e_s, e_j, e_r = residuals(st, smooth)
+        e = np.concatenate([e_s.ravel(), e_j.ravel(), e_r])
+        info = np.concatenate([np.repeat(d["edge_info"], 3), np.repeat(d["jedge_info"], 3), d["redge_info"]])
+        chi = np.concatenate([(e_s ** 2 * d["edge_info"][:, None]).sum(1), (e_j ** 2 * d["jedge_info"][:, None]).sum(1), e_r ** 2 * d["redge_info"]])
+        dl = np.concatenate([np.where(d["edge_obs"][:, 2] >= 0, hs, opt.huber_mono), np.full(len(e_j), hs), np.full(len(e_r), hr)])
+        reps = np.concatenate([np.full(len(e_s), 3), np.full(len(e_j), 3), np.full(len(e_r), 1)])
+        return e, info, chi, dl, reps
+
+    def robust_chi2(st):
+        e, info, chi, dl, reps = parts(st)
+        return float(np.where(chi <= dl ** 2, chi, 2 * dl * np.sqrt(chi) - dl ** 2).sum())
+
+    st = (d["pose_q"].copy(), d["pose_t"].copy(), d["points"].copy(), d["joints"].copy(), d["dists"].copy())
+    lam, ni, trace = None, 2.0, []
+    for it in range(5):
+        cur = robust_chi2(st)
+        e0, info, chi, dl, reps = parts(st)
+        h = 1e-6
+        Jm = np.zeros((len(e0), n))
+        for j in range(n):
+            dx = np.zeros(n); dx[j] = h
+            Jm[:, j] = (parts(apply(st, dx), True)[0] - parts(apply(st, -dx), True)[0]) / (2 * h)
+        rho1 = np.where(chi <= dl ** 2, 1.0, dl / np.sqrt(np.maximum(chi, 1e-300)))
+        Wd = info * np.repeat(rho1, reps)
+        Hm = Jm.T @ (Wd[:, None] * Jm); bm = -Jm.T @ (Wd * e0)
+        if it == 0:
+            lam = opt.tau * np.abs(np.diag(Hm)).max()
+        q = 0
+        while True:
+            x = np.linalg.solve(Hm + lam * np.eye(n), bm)
+            trial = apply(st, x)
+            tmp = robust_chi2(trial)
+            rho = (cur - tmp) / (float(x @ (lam * x + bm)) + 1e-3)
+            ok = rho > 0 and np.isfinite(tmp)
+            trace.append((lam, cur, tmp, ok))
+            if ok:
+                lam *= max(1.0 / 3.0, min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0)); ni = 2.0
+                st, cur = trial, tmp
+            else:
+                lam *= ni; ni *= 2
+            q += 1
+            if not (rho < 0 and q < 10):
+                break
+    p, r, status = oracle_mod.ba_solve(d, opt)
+    tr = r.trace_rows
+    assert status == 0 and len(tr) == len(trace) >= 5
+    ref = np.array([(t[0], t[1], t[2]) for t in trace])
+    assert np.allclose(tr[:, 0], ref[:, 0], rtol=1e-5) and np.allclose(tr[:, 1:3], ref[:, 1:3], rtol=1e-6)
+    assert [bool(a) for a in tr[:, 4]] == [t[3] for t in trace]
+    assert np.abs(p["joints"] - st[3]).max() < 1e-5 and np.abs(p["dists"] - st[4]).max() < 1e-5
+    assert np.abs(p["pose_t"] - st[1]).max() < 1e-6
