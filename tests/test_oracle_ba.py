@@ -367,3 +367,48 @@ def test_dynamic_lm_trajectory_with_rigidity_edges_matches_numpy(oracle_mod):
     assert [bool(a) for a in tr[:, 4]] == [t[3] for t in trace]
     assert np.abs(p["joints"] - st[3]).max() < 1e-5 and np.abs(p["dists"] - st[4]).max() < 1e-5
     assert np.abs(p["pose_t"] - st[1]).max() < 1e-6
+
+
+def test_full_dynamic_window_initial_chi2_matches_numpy(oracle_mod):
+    """All four edge families of LocalBundleAdjustmentHumanTrajactory at once, incl. LandmarkMotionTernaryEdge
+    (include/g2o_dyn_slam3d.h:65-76: e = p1 - M^-1 p2 with M = [R | t * delta_t]): the robust chi2 the LM starts from, for
+    non-trivial motion estimates and delta_t != 1, against a plain numpy evaluation."""
+    d = synth.make_ba_problem(10, 80, 4, seed=41, humans=2, human_poses=3)
+    rng = np.random.default_rng(8)
+    nm = len(d["motion_t"])
+    d["motion_t"] = rng.normal(0, 0.3, (nm, 3))
+    q = np.concatenate([rng.normal(0, 0.05, (nm, 3)), np.ones((nm, 1))], 1)
+    d["motion_q"] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    d["medge_dt"] = rng.uniform(0.5, 1.5, len(d["medge_dt"]))
+    opt = oracle_mod.ba_default_options()
+    opt.iterations[0] = 1; opt.iterations[1] = 0
+    _, r, status = oracle_mod.ba_solve(d, opt)
+    assert status == 0
+    # the same window without its motion edges: the difference of the two initial chi2 isolates the motion family exactly
+    d0 = dict(d, medge_p1=np.zeros(0, np.int32), medge_p2=np.zeros(0, np.int32), medge_motion=np.zeros(0, np.int32),
+              medge_dt=np.zeros(0), medge_info=np.zeros(0), motion_q=np.zeros((0, 4)), motion_t=np.zeros((0, 3)))
+    _, r0, status0 = oracle_mod.ba_solve(d0, opt)
+    assert status0 == 0
+
+    def rho(chi, dl):
+        return np.where(chi <= dl ** 2, chi, 2 * dl * np.sqrt(chi) - dl ** 2).sum()
+
+    e_s = _residuals_g2o(d, d["pose_q"], d["pose_t"], d["points"])
+    chi_s = (e_s ** 2 * d["edge_info"][:, None]).sum(1)
+    dl_s = np.where(d["edge_obs"][:, 2] >= 0, opt.huber_stereo, opt.huber_mono)
+    dj = dict(d, edge_pose=d["jedge_pose"], edge_point=d["jedge_joint"], edge_obs=d["jedge_obs"])
+    e_j = _residuals_g2o(dj, d["pose_q"], d["pose_t"], d["joints"])
+    chi_j = (e_j ** 2 * d["jedge_info"][:, None]).sum(1)
+    J = d["joints"]
+    e_r = np.linalg.norm(J[d["redge_i"]] - J[d["redge_j"]], axis=1) - d["dists"][d["redge_dist"]]
+    chi_r = e_r ** 2 * d["redge_info"]
+    Rm = np.array([_q2R(qq) for qq in d["motion_q"]])[d["medge_motion"]]
+    tm = d["motion_t"][d["medge_motion"]] * d["medge_dt"][:, None]
+    e_m = J[d["medge_p1"]] - np.einsum("eji,ej->ei", Rm, J[d["medge_p2"]] - tm)      # p1 - R^T (p2 - t * dt)
+    chi_m = (e_m ** 2).sum(1) * d["medge_info"]
+    total = rho(chi_s, dl_s) + rho(chi_j, opt.huber_stereo) + rho(chi_r, opt.huber_rigid) + rho(chi_m, opt.huber_motion)
+    assert len(chi_m) > 0 and (chi_m > opt.huber_motion ** 2).any()              # the Huber branch of the motion edges is exercised
+    # the float 1 / z of the stereo projection makes the static part sensitive to the last bit of z (~1e-8 relative) ...
+    assert abs(r.c.chi2_initial - total) < 1e-7 * total
+    # ... the motion family alone is exact
+    assert abs((r.c.chi2_initial - r0.c.chi2_initial) - rho(chi_m, opt.huber_motion)) < 1e-9 * rho(chi_m, opt.huber_motion)
