@@ -412,3 +412,98 @@ def test_full_dynamic_window_initial_chi2_matches_numpy(oracle_mod):
     assert abs(r.c.chi2_initial - total) < 1e-7 * total
     # ... the motion family alone is exact
     assert abs((r.c.chi2_initial - r0.c.chi2_initial) - rho(chi_m, opt.huber_motion)) < 1e-9 * rho(chi_m, opt.huber_motion)
+
+
+def test_pose_optimization_matches_an_independent_numpy_schedule(oracle_mod):
+    """Optimizer::PoseOptimization (src/Optimizer.cc:232-429) restated independently in numpy: four rounds, each restarted
+    from the initial pose, ten g2o LM iterations per round on the edges still at level 0 (6 x 6 normal equations, Jacobian by
+    central differences), re-classification of EVERY edge after each round (outliers re-evaluated at the new pose, inliers
+    judged by the error of the last evaluated trial, float chi2 against 5.991f / 7.815f), robust kernel off in the last round."""
+    cam, frames, _ = synth.make_pose_frames(3, 300, seed=17)
+    pb = oracle_mod.pose_optimize(cam, frames)
+    th_m, th_s = np.float32(5.991), np.float32(7.815)
+    d_m, d_s = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815)))
+    for f, fr in enumerate(frames):
+        n = len(fr["xw"])
+        if n < 10:
+            continue                                   # the < 10 edges early exit has its own test above
+        X = fr["xw"].astype(np.float64); obs = fr["obs"].astype(np.float64); w = fr["inv_sigma2"].astype(np.float64)
+        stereo = ~(fr["obs"][:, 2] < 0)
+        dl = np.where(stereo, d_s, d_m)
+
+        def err(q, t, smooth=False):
+            Xc = X @ _q2R(q).T + t
+            invz = 1.0 / Xc[:, 2]
+            if not smooth:
+                invz = np.where(stereo, invz.astype(np.float32).astype(np.float64), invz)
+            u = Xc[:, 0] * invz * cam["fx"] + cam["cx"]; v = Xc[:, 1] * invz * cam["fy"] + cam["cy"]
+            e = obs - np.stack([u, v, u - cam["bf"] * invz], 1)
+            e[~stereo, 2] = 0
+            return e
+
+        def oplus(q, t, x):
+            Tm = np.eye(4); Tm[:3, :3] = _q2R(q); Tm[:3, 3] = t
+            Tn = _se3_exp(x) @ Tm
+            m = Tn[:3, :3]
+            ww = np.sqrt(max(0, 1 + m[0, 0] + m[1, 1] + m[2, 2])) / 2
+            return np.array([(m[2, 1] - m[1, 2]) / (4 * ww), (m[0, 2] - m[2, 0]) / (4 * ww), (m[1, 0] - m[0, 1]) / (4 * ww), ww]), Tn[:3, 3]
+
+        q0, t0 = np.asarray(fr["pose_q"], np.float64), np.asarray(fr["pose_t"], np.float64)
+        level = np.zeros(n, bool)          # True = level 1 (left out of the optimisation)
+        outlier = np.zeros(n, bool)
+        robust = True
+        for rnd in range(4):
+            q, t = q0.copy(), t0.copy()
+            act = ~level
+
+            def rchi(e):
+                chi = (e ** 2).sum(1) * w
+                r = np.where(chi <= dl ** 2, chi, 2 * dl * np.sqrt(chi) - dl ** 2) if robust else chi
+                return float(r[act].sum()), chi
+
+            last_e = err(q, t)
+            lam, ni, n_bad = None, 2.0, 0
+            for it in range(10):
+                e0 = err(q, t); last_e = e0
+                cur, chi = rchi(e0); ini = cur
+                Jm = np.zeros((3 * n, 6)); h = 1e-6
+                for j in range(6):
+                    dx = np.zeros(6); dx[j] = h
+                    Jm[:, j] = ((err(*oplus(q, t, dx), True) - err(*oplus(q, t, -dx), True)) / (2 * h)).ravel()
+                rho1 = np.where(chi <= dl ** 2, 1.0, dl / np.sqrt(np.maximum(chi, 1e-300))) if robust else np.ones(n)
+                Wd = np.repeat(w * rho1 * act, 3)
+                Hm = Jm.T @ (Wd[:, None] * Jm); bm = -Jm.T @ (Wd * e0.ravel())
+                if it == 0:
+                    lam = 1e-5 * np.abs(np.diag(Hm)).max()
+                qn, rho = 0, 0.0
+                while True:
+                    x = np.linalg.solve(Hm + lam * np.eye(6), bm)
+                    q2, t2 = oplus(q, t, x)
+                    last_e = err(q2, t2)
+                    tmp = rchi(last_e)[0]
+                    rho = (cur - tmp) / (float(x @ (lam * x + bm)) + 1e-3)
+                    if rho > 0 and np.isfinite(tmp):
+                        lam *= max(1.0 / 3.0, min(1.0 - (2 * rho - 1) ** 3, 2.0 / 3.0)); ni = 2.0
+                        q, t, cur = q2, t2, tmp
+                    else:
+                        lam *= ni; ni *= 2
+                    qn += 1
+                    if not (rho < 0 and qn < 10):
+                        break
+                if qn == 10 or rho == 0:
+                    break
+                n_bad = n_bad + 1 if (ini - cur) * 1e3 < ini else 0
+                if n_bad >= 3:
+                    break
+            # classification: former outliers are re-evaluated at the current estimate, the rest keep the last evaluated error
+            e_now = err(q, t)
+            e_cls = np.where(outlier[:, None], e_now, last_e)
+            chi_f = ((e_cls ** 2).sum(1) * w).astype(np.float32)
+            outlier = chi_f > np.where(stereo, th_s, th_m)
+            level = outlier.copy()
+            if rnd == 2:
+                robust = False
+        a, b = pb.frame_ptr[f], pb.frame_ptr[f + 1]
+        assert (pb.outlier[a:b].astype(bool) == outlier).all(), f
+        assert pb.n_inliers[f] == n - outlier.sum()
+        assert np.abs(pb.pose_t[f] - t).max() < 1e-6 and np.abs(np.abs(pb.pose_q[f] @ q) - 1) < 1e-10
