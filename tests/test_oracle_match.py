@@ -80,3 +80,101 @@ def test_distinctive_descriptor_rule(oracle_mod):
         m = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
         med = np.sort(m, 1)[:, int(0.5 * (len(d) - 1))]
         assert got[p] == int(np.argmin(med))                  # least median, first on ties
+
+
+def _stereo_numpy(kl, dl, kr, dr, pyr_l, pyr_r, scale, mb, mbf):
+    """Frame::ComputeStereoMatches (src/Frame.cc:829-1003) written again from the reference in plain Python / numpy float32
+    (bit counting by unpackbits, SAD windows as array slices): an independent check of oracle/match_oracle.cpp."""
+    f32 = np.float32
+    n_l = len(kl)
+    u_right = np.full(n_l, -1, f32); depth = np.full(n_l, -1, f32)
+    inv_scale = (f32(1.0) / scale).astype(f32)
+    n_rows = pyr_l[0].shape[0]
+    rows = [[] for _ in range(n_rows)]
+    for i_r in range(len(kr)):
+        y = kr["y"][i_r]; r = f32(2.0) * scale[kr["octave"][i_r]]
+        hi = min(int(np.ceil(f32(y + r))), n_rows - 1); lo = max(int(np.floor(f32(y - r))), 0)
+        for yi in range(lo, hi + 1):
+            rows[yi].append(i_r)
+    bits_l = np.unpackbits(dl, axis=1).astype(np.int16); bits_r = np.unpackbits(dr, axis=1).astype(np.int16)
+    min_d = f32(0); max_d = f32(f32(mbf) / f32(mb))
+    dist_idx = []
+    for i_l in range(n_l):
+        lvl = int(kl["octave"][i_l]); v_l = kl["y"][i_l]; u_l = kl["x"][i_l]
+        cands = rows[int(v_l)]
+        if not cands:
+            continue
+        min_u = f32(u_l - max_d); max_u = f32(u_l - min_d)
+        if max_u < 0:
+            continue
+        best, best_r = 100, 0
+        for i_r in cands:
+            o = int(kr["octave"][i_r])
+            if o < lvl - 1 or o > lvl + 1:
+                continue
+            u_r = kr["x"][i_r]
+            if min_u <= u_r <= max_u:
+                d = int(np.abs(bits_l[i_l] - bits_r[i_r]).sum())
+                if d < best:
+                    best, best_r = d, i_r
+        if best >= 75:
+            continue
+        sf = inv_scale[lvl]
+
+        def rnd(x):     # C round(): half away from zero
+            return float(np.floor(abs(float(x)) + 0.5) * (1 if x >= 0 else -1))
+        su_l = rnd(f32(u_l * sf)); sv_l = rnd(f32(v_l * sf)); su_r0 = rnd(f32(kr["x"][best_r] * sf))
+        img_l, img_r = pyr_l[lvl], pyr_r[lvl]
+        w, big_l = 5, 5
+        cy, cx = int(sv_l), int(su_l)
+        ini_u = su_r0 + big_l - w; end_u = su_r0 + big_l + w + 1
+        if ini_u < 0 or end_u >= img_r.shape[1]:
+            continue
+        win_l = img_l[cy - w:cy + w + 1, cx - w:cx + w + 1].astype(f32)
+        win_l = win_l - win_l[w, w]
+        best_sad, best_inc, dists = 2 ** 31 - 1, 0, np.zeros(2 * big_l + 1, f32)
+        for inc in range(-big_l, big_l + 1):
+            cxr = int(su_r0) + inc
+            win_r = img_r[cy - w:cy + w + 1, cxr - w:cxr + w + 1].astype(f32)
+            win_r = win_r - win_r[w, w]
+            dist = f32(np.abs((win_l - win_r).astype(np.float64)).sum())     # cv::norm(NORM_L1): double accumulation
+            if dist < f32(best_sad):
+                best_sad, best_inc = int(dist), inc
+            dists[big_l + inc] = dist
+        if best_inc in (-big_l, big_l):
+            continue
+        d1, d2, d3 = dists[big_l + best_inc - 1], dists[big_l + best_inc], dists[big_l + best_inc + 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+        if delta < -1 or delta > 1 or np.isnan(delta):
+            continue
+        best_u = f32(scale[lvl] * f32(f32(f32(su_r0) + f32(best_inc)) + delta))
+        disp = f32(u_l - best_u)
+        if min_d <= disp < max_d:
+            if disp <= 0:
+                disp = f32(0.01); best_u = f32(np.float64(u_l) - 0.01)
+            depth[i_l] = f32(f32(mbf) / disp); u_right[i_l] = best_u
+            dist_idx.append((best_sad, i_l))
+    if dist_idx:
+        dist_idx.sort()
+        median = f32(dist_idx[len(dist_idx) // 2][0])
+        th = f32(f32(f32(1.5) * f32(1.4)) * median)
+        for sad, i_l in reversed(dist_idx):
+            if f32(sad) < th:
+                break
+            u_right[i_l] = -1; depth[i_l] = -1
+    return u_right, depth
+
+
+def test_stereo_oracle_matches_an_independent_numpy_restatement(oracle_mod):
+    from airdos_b200 import synth
+    for frame in (1, 2):
+        L, R = synth.make_stereo_pair(frame)
+        a = oracle_mod.orb_extract(L, None, 1000, 1.2, 8, 12, 7, want_pyramid=True)
+        b = oracle_mod.orb_extract(R, None, 1000, 1.2, 8, 12, 7, want_pyramid=True)
+        sc = np.asarray(oracle_mod.orb_params(1000, 1.2, 8, 640, 480)["scale"], np.float32)
+        mbf = synth.BF; mb = mbf / synth.FX
+        ur, dp, _, _ = oracle_mod.stereo_match(a["kps"], a["desc"], b["kps"], b["desc"], a["pyramid"], b["pyramid"], sc, mb, mbf)
+        ur2, dp2 = _stereo_numpy(a["kps"], a["desc"], b["kps"], b["desc"], a["pyramid"], b["pyramid"], sc, mb, mbf)
+        assert (dp > 0).sum() > 200
+        assert (ur.view(np.uint32) == ur2.view(np.uint32)).all() and (dp.view(np.uint32) == dp2.view(np.uint32)).all()
