@@ -255,14 +255,19 @@ void fast_detect_cell(const uint8_t* img, int w, int h, int pitch, int threshold
                       std::vector<int>& score /*scratch w*h*/) {
     out.clear();
     if (w < 7 || h < 7) return;
-    int off[16];
-    for (int i = 0; i < 16; ++i) off[i] = kCircleDy[i] * pitch + kCircleDx[i];
-    score.assign((size_t)w * h, 0);
+    // padded private copy of the sub-image: rows of a whole number of 16-pixel vectors plus slack, so the row loops below
+    // have no scalar remainder and never read outside the copy (the extra columns are computed and thrown away)
+    const int n = w - 6, n_pad = (n + 15) & ~15, lp = n_pad + 6 + 2;
+    static thread_local std::vector<uint8_t> local;
     static thread_local std::vector<int16_t> scratch, best;
-    const int n = w - 6;
-    best.resize(n);
+    local.assign((size_t)lp * h, 0);
+    for (int y = 0; y < h; ++y) std::memcpy(&local[(size_t)y * lp], img + (size_t)y * pitch, (size_t)w);
+    int off[16];
+    for (int i = 0; i < 16; ++i) off[i] = kCircleDy[i] * lp + kCircleDx[i];
+    score.assign((size_t)w * h, 0);
+    best.resize(n_pad);
     for (int y = 3; y < h - 3; ++y) {
-        fast_best_row(img + (size_t)y * pitch + 3, off, n, best.data(), scratch);
+        fast_best_row(&local[(size_t)y * lp + 3], off, n_pad, best.data(), scratch);
         int* srow = &score[(size_t)y * w + 3];
         for (int x = 0; x < n; ++x)
             if (best[x] > threshold) srow[x] = best[x] - 1;
