@@ -1133,9 +1133,40 @@ struct Ctx {
     Opt opt(bool robust) const { return Opt{O->huber_mono, O->huber_stereo, O->huber_rigid, O->huber_motion, robust ? 1 : 0}; }
     int n_dyn() const { return P->n_joint_edges + P->n_rigid_edges + P->n_motion_edges; }
 
+    // every index array of the articulated-human part against its vertex count, NULL arrays with a non-zero count
+    adb_status validate_dynamic() const {
+        ADB_CHECK(P->n_joints >= 0 && P->n_dists >= 0 && P->n_motions >= 0 && P->n_joint_edges >= 0 && P->n_rigid_edges >= 0 && P->n_motion_edges >= 0,
+                  ADB_ERR_INVALID, "negative count in the articulated part");
+        ADB_CHECK(P->pose_q && P->pose_t && P->pose_fixed, ADB_ERR_INVALID, "null pose arrays");
+        ADB_CHECK(P->n_points == 0 || P->points, ADB_ERR_INVALID, "null point array");
+        ADB_CHECK(P->n_edges == 0 || (P->edge_pose && P->edge_point && P->edge_obs && P->edge_info), ADB_ERR_INVALID, "null edge arrays");
+        ADB_CHECK(P->n_joints == 0 || P->joints, ADB_ERR_INVALID, "null joint array");
+        ADB_CHECK(P->n_dists == 0 || P->dists, ADB_ERR_INVALID, "null bone-length array");
+        ADB_CHECK(P->n_motions == 0 || (P->motion_q && P->motion_t), ADB_ERR_INVALID, "null motion arrays");
+        ADB_CHECK(P->n_joint_edges == 0 || (P->jedge_pose && P->jedge_joint && P->jedge_obs && P->jedge_info), ADB_ERR_INVALID, "null joint-edge arrays");
+        ADB_CHECK(P->n_rigid_edges == 0 || (P->redge_i && P->redge_j && P->redge_dist && P->redge_info), ADB_ERR_INVALID, "null rigidity-edge arrays");
+        ADB_CHECK(P->n_motion_edges == 0 || (P->medge_p1 && P->medge_p2 && P->medge_motion && P->medge_dt && P->medge_info), ADB_ERR_INVALID,
+                  "null motion-edge arrays");
+        auto in = [](int v, int n) { return v >= 0 && v < n; };
+        for (int e = 0; e < P->n_joint_edges; ++e)
+            ADB_CHECK(in(P->jedge_pose[e], P->n_poses) && in(P->jedge_joint[e], P->n_joints), ADB_ERR_INVALID,
+                      "joint edge %d references pose %d / joint %d out of range", e, P->jedge_pose[e], P->jedge_joint[e]);
+        for (int e = 0; e < P->n_rigid_edges; ++e)
+            ADB_CHECK(in(P->redge_i[e], P->n_joints) && in(P->redge_j[e], P->n_joints) && in(P->redge_dist[e], P->n_dists), ADB_ERR_INVALID,
+                      "rigidity edge %d references joints %d, %d / bone length %d out of range", e, P->redge_i[e], P->redge_j[e], P->redge_dist[e]);
+        for (int e = 0; e < P->n_motion_edges; ++e)
+            ADB_CHECK(in(P->medge_p1[e], P->n_joints) && in(P->medge_p2[e], P->n_joints) && in(P->medge_motion[e], P->n_motions), ADB_ERR_INVALID,
+                      "motion edge %d references joints %d, %d / motion %d out of range", e, P->medge_p1[e], P->medge_p2[e], P->medge_motion[e]);
+        return ADB_OK;
+    }
+
     // ---- one-time upload: edges sorted by point (stable), state
     adb_status upload_problem() {
         const int E = P->n_edges, NP = P->n_points;
+        {
+            const adb_status v = validate_dynamic();
+            if (v != ADB_OK) return v;
+        }
         ptr.assign(NP + 1, 0);
         for (int e = 0; e < E; ++e) {
             ADB_CHECK(P->edge_point[e] >= 0 && P->edge_point[e] < NP && P->edge_pose[e] >= 0 && P->edge_pose[e] < P->n_poses, ADB_ERR_INVALID,

@@ -613,6 +613,15 @@ void ba_oracle_global_options(adb_ba_options* o, int32_t n_iterations, int32_t r
 // Same contract as adb_ba_solve (include/airdos_b200.h).
 int ba_oracle_solve(adb_ba_problem* prob, const adb_ba_options* opt, volatile const uint8_t* stop, adb_ba_result* res) {
     if (stop && *stop) return ADB_ERR_STOPPED;
+    {   // same range checks as adb_ba_solve: a bad index is ADB_ERR_INVALID, never a wild write
+        auto in = [](int v, int n) { return v >= 0 && v < n; };
+        for (int e = 0; e < prob->n_edges; ++e) if (!in(prob->edge_pose[e], prob->n_poses) || !in(prob->edge_point[e], prob->n_points)) return ADB_ERR_INVALID;
+        for (int e = 0; e < prob->n_joint_edges; ++e) if (!in(prob->jedge_pose[e], prob->n_poses) || !in(prob->jedge_joint[e], prob->n_joints)) return ADB_ERR_INVALID;
+        for (int e = 0; e < prob->n_rigid_edges; ++e)
+            if (!in(prob->redge_i[e], prob->n_joints) || !in(prob->redge_j[e], prob->n_joints) || !in(prob->redge_dist[e], prob->n_dists)) return ADB_ERR_INVALID;
+        for (int e = 0; e < prob->n_motion_edges; ++e)
+            if (!in(prob->medge_p1[e], prob->n_joints) || !in(prob->medge_p2[e], prob->n_joints) || !in(prob->medge_motion[e], prob->n_motions)) return ADB_ERR_INVALID;
+    }
     Solver S(*prob, *opt);
     res->iterations_run[0] = res->iterations_run[1] = 0; res->trials_run = 0; res->stopped = 0; res->trace_len = 0;
     res->chi2_initial = 0; res->chi2_round[0] = res->chi2_round[1] = 0;

@@ -56,16 +56,48 @@ def test_config4_local_ba(opt, oracle_mod):
     assert np.abs(pg["pose_t"].reshape(-1, 3) - d["gt_pose_t"]).mean() < np.abs(d["pose_t"] - d["gt_pose_t"]).mean()
 
 
+def _check_dynamic(pg, rg, po, ro):
+    assert np.abs(pg["joints"] - po["joints"]).max() < 1e-4
+    assert np.abs(pg["dists"] - po["dists"]).max() < 1e-4
+    assert np.abs(pg["motion_t"] - po["motion_t"]).max() < 1e-4 and np.abs(pg["motion_q"] - po["motion_q"]).max() < 1e-6
+    assert (rg.jedge_outlier == ro.jedge_outlier).all() and (rg.redge_outlier == ro.redge_outlier).all()
+    assert (rg.medge_outlier == ro.medge_outlier).all()
+
+
 def test_dynamic_ba_matches_oracle(opt, oracle_mod):
     from airdos_b200 import synth
     for kw in (dict(n_kf=12, n_points=600, seed=9, humans=2), dict(n_kf=20, n_points=1500, seed=10, humans=4, human_poses=4)):
         d = synth.make_ba_problem(**kw)
-        pg, rg, po, ro = _compare(opt, oracle_mod, d)
-        assert np.abs(pg["joints"] - po["joints"]).max() < 1e-4
-        assert np.abs(pg["dists"] - po["dists"]).max() < 1e-4
-        assert np.abs(pg["motion_t"] - po["motion_t"]).max() < 1e-4 and np.abs(pg["motion_q"] - po["motion_q"]).max() < 1e-6
-        assert (rg.jedge_outlier == ro.jedge_outlier).all() and (rg.redge_outlier == ro.redge_outlier).all()
-        assert (rg.medge_outlier == ro.medge_outlier).all()
+        _check_dynamic(*_compare(opt, oracle_mod, d))
+
+
+def test_config5_dynamic_ba(opt, oracle_mod):
+    """BASELINE.json configs[4] (Optimizer::LocalBundleAdjustmentHumanTrajactory, src/Optimizer.cc:1496-2222): 80 KF, 30k points,
+    180k stereo edges, 16 MapHumanPose skeletons = 4 trajectories x 4 consecutive poses: 224 joint vertices, 56 bone lengths,
+    4 motions; 224 joint + 224 rigidity + 60 motion edges; dense reduced system of order 79*6 + 56 + 4*6 + 224*3 = 1226."""
+    from airdos_b200 import synth
+    d = synth.make_ba_problem(n_kf=80, n_points=30000, seed=5000, humans=4, human_poses=4)
+    assert len(d["edge_pose"]) == 180000 and d["joints"].shape == (224, 3) and len(d["dists"]) == 56 and len(d["motion_t"]) == 4
+    assert len(d["jedge_pose"]) == 224 and len(d["redge_i"]) == 224 and len(d["medge_p1"]) == 60
+    pg, rg, po, ro = _compare(opt, oracle_mod, d)
+    _check_dynamic(pg, rg, po, ro)
+    assert (pg["pose_t"].reshape(-1, 3)[0] == d["pose_t"][0]).all()
+    assert rg.c.chi2_round[0] < rg.c.chi2_initial
+    assert np.abs(pg["pose_t"].reshape(-1, 3) - d["gt_pose_t"]).mean() < np.abs(d["pose_t"] - d["gt_pose_t"]).mean()
+
+
+def test_out_of_range_indices_are_rejected(opt):
+    """every index array (static and articulated) is range-checked before anything is uploaded."""
+    from airdos_b200 import synth
+    from airdos_b200.capi import AdbError
+    d = synth.make_ba_problem(n_kf=6, n_points=120, seed=31, humans=2, human_poses=4)
+    for key, bad in (("edge_pose", 6), ("edge_point", -1), ("jedge_pose", 99), ("jedge_joint", 10 ** 6), ("redge_i", -3), ("redge_j", 10 ** 5),
+                     ("redge_dist", 28), ("medge_p1", 112), ("medge_p2", -1), ("medge_motion", 2)):
+        b = dict(d); b[key] = d[key].copy(); b[key][len(b[key]) // 2] = bad
+        with pytest.raises(AdbError) as ei:
+            opt.LocalBundleAdjustment(b)
+        assert ei.value.status == 1, key
+    assert opt.LocalBundleAdjustment(d)[2] == 0
 
 
 def test_stop_flag_semantics(opt, oracle_mod):

@@ -507,3 +507,15 @@ def test_pose_optimization_matches_an_independent_numpy_schedule(oracle_mod):
         assert (pb.outlier[a:b].astype(bool) == outlier).all(), f
         assert pb.n_inliers[f] == n - outlier.sum()
         assert np.abs(pb.pose_t[f] - t).max() < 1e-6 and np.abs(np.abs(pb.pose_q[f] @ q) - 1) < 1e-10
+
+
+def test_out_of_range_indices_are_rejected(oracle_mod):
+    """A bad vertex index in any edge family is ADB_ERR_INVALID (1), never a wild access (same contract as adb_ba_solve)."""
+    from airdos_b200 import synth
+    d = synth.make_ba_problem(n_kf=6, n_points=120, seed=31, humans=2, human_poses=4)
+    for key, bad in (("edge_pose", 6), ("edge_point", -1), ("jedge_pose", 99), ("jedge_joint", 10 ** 6), ("redge_i", -3), ("redge_j", 10 ** 5),
+                     ("redge_dist", 28), ("medge_p1", 112), ("medge_p2", -1), ("medge_motion", 2)):
+        b = dict(d); b[key] = d[key].copy(); b[key][len(b[key]) // 2] = bad
+        _, _, st = oracle_mod.ba_solve(b)
+        assert st == 1, key
+    assert oracle_mod.ba_solve(d)[2] == 0
