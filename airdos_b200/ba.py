@@ -39,6 +39,17 @@ def pose_to_tcw(q: np.ndarray, t: np.ndarray) -> np.ndarray:
     return out.reshape(4, 4)
 
 
+def dense_solve(a: np.ndarray, b: np.ndarray, device: int = 0, cluster: int = 0, reps: int = 1):
+    """g2o::LinearSolverDense::solve (linear_solver_dense.h:64-113) on the device: x with A x = b for SPD A (lower triangle read).
+    Returns (x, info, ms_per_solve): info != 0 = not positive definite (g2o returns false and LM rejects the step)."""
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    n = a.shape[0]
+    assert a.shape == (n, n) and b.shape == (n,)
+    x = np.zeros(n); info = C.c_int32(0); ms = C.c_float(0)
+    check(lib().adb_dense_solve(device, n, ptr(a), ptr(b), ptr(x), C.byref(info), cluster, reps, C.byref(ms)))
+    return x, int(info.value), float(ms.value)
+
+
 class Optimizer:
     """Optimizer::LocalBundleAdjustment / LocalBundleAdjustmentHumanTrajactory on one GPU."""
 

@@ -442,6 +442,16 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* prob, const adb_ba_options* 
 adb_status adb_ba_stage_ms(adb_ba_t s, float* ms6);
 int64_t adb_ba_launch_count(adb_ba_t s);
 
+/* g2o::LinearSolverDense<MatrixType>::solve (Thirdparty/g2o/g2o/solvers/linear_solver_dense.h:64-113: dense Eigen LDLT of the
+ * whole non-marginalised block, `!ldlt.isPositive()` -> false) and LinearSolverEigen::solve (linear_solver_eigen.h:92-115), as
+ * adb_ba_solve uses them internally: solves A x = b for a symmetric positive definite A (row-major n x n, only the lower
+ * triangle is read) by the in-cluster FP64 tensor-core Cholesky (chol.cu).  Host pointers.  *info = 0, or the 1-based index
+ * of the 32-column panel start whose pivot was not positive (x is then meaningless, like g2o's rejected step).
+ * cluster = CTAs in the thread-block cluster (8 or 16; 0 = chosen by order).  reps >= 1 repeats the device solve and
+ * ms_per_solve (may be NULL) returns the mean device time of one solve (CUDA events around the kernel). */
+adb_status adb_dense_solve(int32_t device, int32_t n, const double* a, const double* b, double* x, int32_t* info,
+                           int32_t cluster, int32_t reps, float* ms_per_solve);
+
 /* Optimizer::PoseOptimization(Frame*)  (src/Optimizer.cc:232-429): pose-only robust LM over the frame's
  * MapPoint correspondences (g2o::Edge(Stereo)SE3ProjectXYZOnlyPose), 4 rounds x 10 iterations with
  * chi2 re-classification between rounds, batched over frames (the reference calls it once per frame:
