@@ -11,8 +11,8 @@
 //                           which live in the dense (non-marginalised) block
 //   ba_dinv_kernel          (Hll + lambda I)^-1 per point, bschur -= Hpl Dinv bl
 //   ba_schur_kernel         Hschur -= Hpl_i Dinv Hpl_j^T over the per-point edge pairs
-//   chol_left_kernel,       dense FP64 Cholesky of the reduced system: left-looking, one launch per 32-wide panel,
-//   chol_solve_kernel       then forward / backward substitution (cuSOLVER potrf/potrs was the bring-up baseline)
+//   chol_cluster_kernel     (chol.cu) dense FP64 Cholesky solve of the reduced system in ONE launch of one thread-block
+//                           cluster: DMMA trailing update / panel solve, look-ahead factorisation, substitutions
 //   ba_pose_update_kernel   exp(dx) * T, additive / right-multiplicative updates of the rest
 //   ba_backsub_kernel       xl = Dinv (bl - Hpl^T xp), trial points, landmark part of the gain ratio
 //   ba_eval_kernel          residuals + robust chi2 of the trial state
@@ -31,7 +31,7 @@
 #include <limits>
 #include <vector>
 
-#include "common.cuh"
+#include "chol.cuh"
 
 namespace adb {
 
@@ -461,15 +461,17 @@ __global__ void ba_maxdiag_kernel(const double* __restrict__ H, int nd, const do
         atomicMax(reinterpret_cast<unsigned long long*>(&sc->maxdiag), (unsigned long long)__double_as_longlong(m));   // m >= 0: order preserved
 }
 
-// S = H (lower) + lambda I, bs = b
-__global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __restrict__ b, int nd, double lambda, double* __restrict__ Sm,
+// S = H (lower) + lambda I in the padded layout of the cluster Cholesky (chol.cuh: pitch ld = 32 ceil(nd / 32), identity pad,
+// right-hand side in row ld), bs = b
+__global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __restrict__ b, int nd, int ld, double lambda, double* __restrict__ Sm,
                                   double* __restrict__ bs) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (size_t)nd * nd) {
-        const int r = (int)(i / nd), c = (int)(i - (size_t)r * nd);
-        Sm[i] = H[i] + (r == c ? lambda : 0.0);
+    if (i < (size_t)ld * ld) {
+        const int r = (int)(i / ld), c = (int)(i - (size_t)r * ld);
+        Sm[i] = (r < nd && c < nd) ? H[(size_t)r * nd + c] + (r == c ? lambda : 0.0) : (r == c ? 1.0 : 0.0);
     }
-    if (i < (size_t)nd) { bs[i] = b[i]; Sm[(size_t)nd * nd + i] = b[i]; }   // row nd of Sm carries the right-hand side through the factorisation
+    if (i < (size_t)ld) { const double v = i < (size_t)nd ? b[i] : 0.0; bs[i] = v; Sm[(size_t)ld * ld + i] = v; }   // row ld carries the right-hand side through the factorisation
+    if (i < (size_t)(kCholNB - 1) * ld) Sm[(size_t)(ld + 1) * ld + i] = 0.0;                                          // spare rows of the right-hand-side row block
 }
 
 // per point: Dinv = (Hll + lambda I)^-1 by cofactors (Eigen fixed-size inverse), db = Dinv bl
@@ -868,165 +870,6 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
 
 
 // ----------------------------------------------------------------------------------------
-// Dense FP64 Cholesky of the reduced system (row-major lower triangle), left-looking with 32-wide panels and ONE
-// launch per panel: CTA `ib` owns row block ib >= kb.  It forms its 32 x 32 block of the panel,
-//     U = A[ib, kb] - L[ib, 0:kb] L[kb, 0:kb]^T,
-// and (redundantly, to avoid any grid-wide synchronisation) the diagonal block D = A[kb, kb] - L[kb, 0:kb] L[kb, 0:kb]^T,
-// factors D in registers (one warp, column broadcast by shuffles) and solves U L_kk^-T for its rows.  Factored diagonal
-// blocks go to a side buffer (Ldiag) so no CTA ever reads a block another CTA is writing.  chol_solve_kernel then does the
-// forward / backward substitution.  Replaces cuSOLVER potrf + potrs (LinearSolverEigen / LinearSolverDense of g2o).
-constexpr int kCholNB = 32;
-
-// n = matrix order (columns), n_rows >= n: rows n..n_rows-1 are extra right-hand-side rows carried through the factorisation
-// (row n = b^T turns into y^T = (L^-1 b)^T, i.e. the forward substitution comes for free).  pitch = n.
-constexpr int kCholThreads = 512;   // 16 warps: thread (r, c) owns elements (r, c) and (r + 16, c) of the 32 x 32 tiles
-__device__ __forceinline__ void chol_panel(double* A, int n, int n_rows, int kb, int ib, double* Ldiag, int* info) {
-    __shared__ double Ta[kCholNB][kCholNB + 1], Tb[kCholNB][kCholNB + 1];   // operand tiles, then U and D / L
-    __shared__ double col[kCholNB];                                          // 1 / L[j][j]
-    const int tid = threadIdx.x, r = tid >> 5, c = tid & 31;                 // r in 0..15
-    const int k = kb * kCholNB, i0 = ib * kCholNB;
-    const bool diag_cta = ib == kb;
-    const int nbk = min(kCholNB, n - k);
-    double accU[2] = {0.0, 0.0}, accD[2] = {0.0, 0.0};
-    // software-pipelined tile loads: the next tiles are fetched while the current ones are multiplied
-    double na[2] = {0.0, 0.0}, nb[2] = {0.0, 0.0};
-    if (k > 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            na[h] = (i0 + r + 16 * h < n_rows) ? A[(size_t)(i0 + r + 16 * h) * n + c] : 0.0;
-            nb[h] = (k + r + 16 * h < n_rows) ? A[(size_t)(k + r + 16 * h) * n + c] : 0.0;   // last panel: rows past the array
-        }
-    }
-    for (int p0 = 0; p0 < k; p0 += kCholNB) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) { Ta[r + 16 * h][c] = na[h]; Tb[r + 16 * h][c] = nb[h]; }
-        __syncthreads();
-        if (p0 + kCholNB < k) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                na[h] = (i0 + r + 16 * h < n_rows) ? A[(size_t)(i0 + r + 16 * h) * n + p0 + kCholNB + c] : 0.0;
-                nb[h] = (k + r + 16 * h < n_rows) ? A[(size_t)(k + r + 16 * h) * n + p0 + kCholNB + c] : 0.0;
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < kCholNB; ++p) {
-            const double b = Tb[c][p];
-            accU[0] += Ta[r][p] * b; accU[1] += Ta[r + 16][p] * b;
-            accD[0] += Tb[r][p] * b; accD[1] += Tb[r + 16][p] * b;
-        }
-        __syncthreads();
-    }
-    double u[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int rr = r + 16 * h;
-        u[h] = (i0 + rr < n_rows && c < nbk) ? A[(size_t)(i0 + rr) * n + k + c] - accU[h] : 0.0;
-        Tb[rr][c] = (rr < nbk && c < nbk) ? ((c <= rr) ? A[(size_t)(k + rr) * n + k + c] - accD[h] : 0.0) : (rr == c ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    // ---- factor D with one warp and no block barriers: lane = row held in registers, column j broadcast by shuffles
-    if (tid < 32) {
-        const int lane = tid;
-        double row[kCholNB];
-#pragma unroll
-        for (int q = 0; q < kCholNB; ++q) row[q] = Tb[lane][q];
-        bool bad = false;
-#pragma unroll
-        for (int j = 0; j < kCholNB; ++j) {
-            double d = __shfl_sync(0xFFFFFFFFu, row[j], j);
-            if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
-            // the 32 pivots are the serial spine of the whole solve: one rsqrt (MUFU.RSQ64H + Newton) instead of sqrt + divide
-            const double isd = rsqrt(d), sd = d * isd;
-            double v = 0.0;
-            if (lane == j) { row[j] = sd; col[j] = isd; }
-            else if (lane > j) { v = row[j] * isd; row[j] = v; }
-#pragma unroll
-            for (int q = j + 1; q < kCholNB; ++q) {
-                const double vq = __shfl_sync(0xFFFFFFFFu, v, q);
-                if (lane >= q) row[q] -= v * vq;
-            }
-        }
-        if (bad && lane == 0 && diag_cta && *info == 0) *info = k + 1;
-#pragma unroll
-        for (int q = 0; q < kCholNB; ++q) Tb[lane][q] = q <= lane ? row[q] : 0.0;
-    }
-    __syncthreads();
-    // the diagonal block's CTA publishes the factor (A keeps the unfactored block: nobody reads it again); of its rows only
-    // the extra right-hand-side rows (>= n) that share the row block still need the triangular solve
-    if (diag_cta) { Ldiag[(size_t)kb * kCholNB * kCholNB + tid] = Tb[r][c]; Ldiag[(size_t)kb * kCholNB * kCholNB + tid + 512] = Tb[r + 16][c]; }
-    // ---- x L_kk^T = u: a warp owns rows r and r + 16 (solved together: two independent dependency chains), lane c holds
-    //      x[c]; right-looking, no block barriers
-    {
-        double x0 = u[0], x1 = u[1];
-#pragma unroll
-        for (int j = 0; j < kCholNB; ++j) {
-            const double cj = col[j], l = Tb[c][j];
-            const double a0 = __shfl_sync(0xFFFFFFFFu, x0, j) * cj, a1 = __shfl_sync(0xFFFFFFFFu, x1, j) * cj;
-            if (c == j) { x0 = a0; x1 = a1; }
-            if (c > j) { x0 -= a0 * l; x1 -= a1 * l; }
-        }
-        if (i0 + r < n_rows && c < nbk && (!diag_cta || i0 + r >= n)) A[(size_t)(i0 + r) * n + k + c] = x0;
-        if (i0 + r + 16 < n_rows && c < nbk && (!diag_cta || i0 + r + 16 >= n)) A[(size_t)(i0 + r + 16) * n + k + c] = x1;
-    }
-}
-
-__global__ void __launch_bounds__(kCholThreads) chol_left_kernel(double* __restrict__ A, int n, int n_rows, int kb, double* __restrict__ Ldiag,
-                                                                int* __restrict__ info) {
-    chol_panel(A, n, n_rows, kb, kb + blockIdx.x, Ldiag, info);
-}
-
-// backward substitution L^T x = y, y = row n of the factored array; x -> out.  One CTA, 32-wide blocks.  Every block step
-// first stages its diagonal factor in shared memory (one coalesced load) so that the 32 serial pivots never wait on L2.
-// (no __restrict__ / read-only path on A and Ldiag: in the fused kernel other CTAs wrote them earlier in the same launch)
-__device__ __forceinline__ void chol_back(const double* A, const double* Ldiag, int n, double* out) {
-    extern __shared__ double yb[];       // [n] working copy of y
-    __shared__ double Ld[kCholNB][kCholNB + 1];
-    __shared__ double xb[kCholNB];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += blockDim.x) yb[i] = A[(size_t)n * n + i];
-    if (tid < kCholNB) xb[tid] = 0.0;
-    const int nblk = (n + kCholNB - 1) / kCholNB;
-    for (int kb = nblk - 1; kb >= 0; --kb) {
-        const int k = kb * kCholNB, nbk = min(kCholNB, n - k);
-        Ld[tid >> 5][tid & 31] = Ldiag[(size_t)kb * kCholNB * kCholNB + tid];
-        Ld[(tid >> 5) + 16][tid & 31] = Ldiag[(size_t)kb * kCholNB * kCholNB + 512 + tid];
-        __syncthreads();
-        if (tid < 32) {
-            const int lane = tid;
-            double part = (lane < nbk) ? yb[k + lane] : 0.0;
-            const double rinv = (lane < nbk) ? 1.0 / Ld[lane][lane] : 0.0;   // one parallel divide instead of 32 serial ones
-            for (int j = nbk - 1; j >= 0; --j) {
-                double xj = 0.0;
-                if (lane == j) xj = part * rinv;
-                xj = __shfl_sync(0xFFFFFFFFu, xj, j);
-                if (lane == j) xb[j] = xj;
-                if (lane < j) part -= Ld[j][lane] * xj;
-            }
-        }
-        __syncthreads();
-        if (tid < nbk) out[k + tid] = xb[tid];
-        for (int i = tid; i < k; i += blockDim.x) {   // y[i] -= sum_j L[k+j][i] x[j]: 32 independent coalesced loads per thread
-            const double* col = A + (size_t)k * n + i;
-            double a[kCholNB];
-#pragma unroll
-            for (int j = 0; j < kCholNB; ++j) a[j] = j < nbk ? col[(size_t)j * n] : 0.0;
-            double sacc = yb[i];
-#pragma unroll
-            for (int j = 0; j < kCholNB; ++j) sacc -= a[j] * xb[j];
-            yb[i] = sacc;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(512) chol_back_kernel(const double* __restrict__ A, const double* __restrict__ Ldiag, int n, double* __restrict__ out) {
-    chol_back(A, Ldiag, n, out);
-}
-
-// (A single cooperative launch with a grid-wide barrier between panels was measured SLOWER than one launch per panel:
-// 0.42 vs 0.30 ms per solve at n = 294 -- cg::grid_group::sync costs more than a kernel boundary on an 11-CTA grid.)
-
-// ----------------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -1108,7 +951,7 @@ struct Ctx {
     std::vector<int> off_pose, off_dist, off_motion, off_joint;
     std::vector<int2> pairs, chunks;
     std::vector<int> pose_ptr, pose_edges, free_pose;
-    int nd = 0, cur = 0, chi_last = 0;
+    int nd = 0, ld = 32, cur = 0, chi_last = 0;
     double lambda = 0, ni = 2;
     int trace_len = 0;
     Ctx(adb_ba* s_, adb_ba_problem* p, const adb_ba_options* o, adb_ba_result* r, volatile const uint8_t* st) : s(s_), P(p), O(o), R(r), stop(st), tm(s_) {}
@@ -1300,13 +1143,13 @@ struct Ctx {
         UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs); UP(s->chunks, chunks); UP(s->free_pose, free_pose);
 #undef UP
         const size_t n2 = std::max<size_t>((size_t)nd * nd, 1);
+        ld = chol_nblk(std::max(nd, 1)) * kCholNB;
         if ((r = s->H.ensure(n2 * 8)) != ADB_OK) return r;
-        if ((r = s->Sm.ensure((n2 + (size_t)std::max(nd, 1)) * 8)) != ADB_OK) return r;
         if ((r = s->b.ensure(std::max(nd, 1) * 8)) != ADB_OK) return r;
-        if ((r = s->bs.ensure(std::max(nd, 1) * 8)) != ADB_OK) return r;
+        if ((r = s->bs.ensure((size_t)ld * 8)) != ADB_OK) return r;
         if (nd > 0) {
-            const size_t ldiag = (size_t)((nd + kCholNB - 1) / kCholNB) * kCholNB * kCholNB;   // factored diagonal blocks
-            if ((r = s->work.ensure(ldiag * 8)) != ADB_OK) return r;
+            if ((r = s->Sm.ensure(chol_elems(nd) * 8)) != ADB_OK) return r;
+            if ((r = s->work.ensure(chol_scratch_elems(nd) * 8)) != ADB_OK) return r;
         }
         return ADB_OK;
     }
@@ -1360,7 +1203,7 @@ struct Ctx {
         ADB_CUDA(cudaMemsetAsync(&sc->chi_trial, 0, 2 * sizeof(double), st));
         ADB_CUDA(cudaMemsetAsync(&sc->info, 0, sizeof(int), st));
         if (nd > 0) {
-            ba_prepare_kernel<<<grid_for((size_t)nd * nd, 256), 256, 0, st>>>(s->H.as<double>(), s->b.as<double>(), nd, lambda, s->Sm.as<double>(),
+            ba_prepare_kernel<<<grid_for((size_t)ld * ld, 256), 256, 0, st>>>(s->H.as<double>(), s->b.as<double>(), nd, ld, lambda, s->Sm.as<double>(),
                                                                              s->bs.as<double>());
             ++s->launches;
         }
@@ -1373,26 +1216,18 @@ struct Ctx {
             const int nch = (int)chunks.size();
             ba_schur_block_kernel<<<grid_for(nch, kBaThreads / 32), kBaThreads, 0, st>>>(s->pairs.as<int2>(), s->chunks.as<int2>(), nch,
                                                                                         s->e_pose.as<int>(), s->e_point.as<int>(), s->off_pose.as<int>(),
-                                                                                        s->W.as<double>(), s->Dinv.as<double>(), s->db.as<double>(), nd,
-                                                                                        s->Sm.as<double>(), s->Sm.as<double>() + (size_t)nd * nd);   // rhs row
+                                                                                        s->W.as<double>(), s->Dinv.as<double>(), s->db.as<double>(), ld,
+                                                                                        s->Sm.as<double>(), s->Sm.as<double>() + (size_t)ld * ld);   // rhs row
             ++s->launches;
         }
         ADB_CUDA(cudaGetLastError());
         tm.end();
         tm.begin(2);
         if (nd > 0) {
-            {
-                const int nblk = (nd + kCholNB - 1) / kCholNB, nrb = (nd + 1 + kCholNB - 1) / kCholNB;   // row blocks incl. the rhs row
-                {
-                    for (int kb = 0; kb < nblk; ++kb) {
-                        chol_left_kernel<<<nrb - kb, kCholThreads, 0, st>>>(s->Sm.as<double>(), nd, nd + 1, kb, s->work.as<double>(), &sc->info);
-                        ++s->launches;
-                    }
-                    chol_back_kernel<<<1, 512, (size_t)nd * 8, st>>>(s->Sm.as<double>(), s->work.as<double>(), nd, s->bs.as<double>());
-                    ++s->launches;
-                }
-                ADB_CUDA(cudaGetLastError());
-            }
+            // LinearSolverDense / LinearSolverEigen::solve: one cluster launch factors, substitutes and writes x to bs
+            const adb_status cs = chol_solve_launch(st, s->Sm.as<double>(), ld, ld / kCholNB, s->work.as<double>(), s->bs.as<double>(), &sc->info, 0);
+            if (cs != ADB_OK) return cs;
+            ++s->launches;
         }
         tm.end();
         tm.begin(3);

@@ -78,28 +78,30 @@ __device__ __forceinline__ bool factor_chain(TileSmem& T, int jb, int lane) {
 #pragma unroll
         for (int q = 0; q <= p; ++q) L[p][q] = T.Tb[j0 + p][j0 + q];   // broadcast reads
     }
+    // right-looking inside the sub-block: after pivot p every remaining entry gets ONE independent fma, and the two operations
+    // the next pivot waits for (its sub-diagonal entry and its diagonal) are issued first -- the rest fills the rsqrt latency
 #pragma unroll
     for (int p = 0; p < kCholSB; ++p) {
         double d = L[p][p];
-#pragma unroll
-        for (int q = 0; q < p; ++q) d = fma(-L[p][q], L[p][q], d);
         if (!(d > 0.0) || !isfinite(d)) { bad = true; d = 1.0; }
         const double isd = rsqrt(d);
         L[p][p] = d * isd;
-#pragma unroll
-        for (int q = p + 1; q < kCholSB; ++q) {
-            double t = L[q][p];
-#pragma unroll
-            for (int u = 0; u < p; ++u) t = fma(-L[q][u], L[p][u], t);
-            L[q][p] = t * isd;
+        if (p + 1 < kCholSB) {
+            L[p + 1][p] *= isd;
+            L[p + 1][p + 1] = fma(-L[p + 1][p], L[p + 1][p], L[p + 1][p + 1]);
         }
-        double t = r[p];
 #pragma unroll
-        for (int u = 0; u < p; ++u) t = fma(-r[u], L[p][u], t);
-        t *= isd;
+        for (int q = p + 2; q < kCholSB; ++q) L[q][p] *= isd;
+#pragma unroll
+        for (int q = p + 2; q < kCholSB; ++q)
+#pragma unroll
+            for (int u = p + 1; u <= q; ++u) L[q][u] = fma(-L[q][p], L[u][p], L[q][u]);
+        double t = r[p] * isd;
         if (lane == j0 + p) t = L[p][p];     // the pivot row: exactly sqrt(d) (also when the pivot was replaced)
         if (lane < j0 + p) t = 0.0;          // above the diagonal
         r[p] = t;
+#pragma unroll
+        for (int u = p + 1; u < kCholSB; ++u) r[u] = fma(-t, L[u][p], r[u]);
         if (lane == 0) T.isd[j0 + p] = isd;
     }
 #pragma unroll
@@ -125,19 +127,27 @@ __device__ __forceinline__ void factor_update(TileSmem& T, int jb, int c0, int c
 // Factor the 32 x 32 tile in T.Tb (lower triangle) in place and invert its four diagonal sub-blocks; all threads of the CTA call
 // it.  Look-ahead inside the tile: after sub-block jb only the 8 columns of sub-block jb + 1 are updated by everybody (one
 // element per thread); then warp 0 runs the next chain of pivots while warps 1-7 update the columns further right.
-__device__ __forceinline__ bool factor_tile(TileSmem& T, int tid) {
+__device__ __forceinline__ bool factor_tile(TileSmem& T, int tid, long long* fp = nullptr) {
     const int warp = tid >> 5, lane = tid & 31;
     bool bad = false;
+    long long tl = fp ? clock64() : 0;
+#define FMARK(slot) do { if (fp) { const long long n_ = clock64(); fp[slot] += n_ - tl; tl = n_; } } while (0)
     if (warp == 0) bad = factor_chain(T, 0, lane);
+    FMARK(0);
     __syncthreads();
+    FMARK(1);
 #pragma unroll 1
     for (int jb = 0; jb + 1 < kCholNSB; ++jb) {
         const int next0 = (jb + 1) * kCholSB;
         factor_update(T, jb, next0, next0 + kCholSB, tid, kCholThreads);
+        FMARK(2);
         __syncthreads();
+        FMARK(1);
         if (warp == 0) bad |= factor_chain(T, jb + 1, lane);
         else factor_update(T, jb, next0 + kCholSB, kCholNB, tid - 32, kCholThreads - 32);
+        FMARK(0);
         __syncthreads();
+        FMARK(1);
     }
     // inverses of the 8 x 8 diagonal sub-blocks (the panel solve multiplies by them on the tensor pipe): warp w < 4 takes
     // sub-block w, lane p < 8 the column p of M = L_sub^-1:  M[p][p] = 1 / L[p][p],  M[q][p] = -(sum_{u=p}^{q-1} L[q][u] M[u][p]) / L[q][q]
@@ -154,7 +164,10 @@ __device__ __forceinline__ bool factor_tile(TileSmem& T, int tid) {
 #pragma unroll
         for (int q = 0; q < kCholSB; ++q) T.Dinv[warp][q][p] = M[q];
     }
+    FMARK(3);
     __syncthreads();
+    FMARK(1);
+#undef FMARK
     return bad;
 }
 
@@ -265,13 +278,14 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
     double* Ld = scratch + (size_t)nblk * kCholNB * kCholNB;         // [nblk][kCholLd] diagonal factors, published by CTA 0
     // optional phase profile (thread 0 of every CTA, SM clock): load, factor, panel, inverse, barrier 1, update, barrier 2, back-substitution
     __shared__ long long pacc[9];   // [8] = last time stamp
+    __shared__ long long facc[4];   // inside the tile factorisation: pivot chains, barriers, look-ahead column update, inverses
     const bool profiling = prof != nullptr && tid == 0;
 #define CHOL_MARK(slot) do { if (profiling) { const long long now_ = clock64(); pacc[slot] += now_ - pacc[8]; pacc[8] = now_; } } while (0)
-    if (profiling) { for (int i = 0; i < 8; ++i) pacc[i] = 0; pacc[8] = clock64(); }
+    if (profiling) { for (int i = 0; i < 8; ++i) pacc[i] = 0; for (int i = 0; i < 4; ++i) facc[i] = 0; pacc[8] = clock64(); }
 
     // factor the tile in T.Tb and publish it as diagonal factor k (CTA 0 only)
     auto factor_and_publish = [&](int k) {
-        const bool bad = factor_tile(T, tid);
+        const bool bad = factor_tile(T, tid, profiling ? facc : nullptr);
         if (bad && tid == 0 && *info == 0) *info = k * kCholNB + 1;
         double* dst = Ld + (size_t)k * kCholLd;
 #pragma unroll
@@ -336,15 +350,30 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
             //      other CTAs update the rest of the trailing matrix; then it takes a (reduced) share of the tiles itself.
             const int nt = m * (m + 1) / 2 + m;
             const double* panel = S + kc + 2 * q;
+            // contiguous ranges of equal COST per CTA: a full tile = 16 sub-tile products, a diagonal tile 10, a right-hand-side
+            // tile 4 (one row group).  cost_before(t) = cost of tiles [0, t) in closed form; boundaries by bisection.
+            const int ntri = m * (m + 1) / 2;
+            // cost model (bytes moved rather than products: the update runs at about half the tensor-pipe rate, bound by L1 / L2
+            // traffic): full tile 16, diagonal tile 14, right-hand-side tile (one row group) 8
+            const int ctri = 8 * m * (m - 1) + 14 * m;             // cost of the triangle; all costs fit 32 bits (m <= 160)
+            auto tile_at_cost = [&](int c) -> int {                 // smallest t with cost of tiles [0, t) >= c: closed form + fix-up
+                if (c >= ctri) return min(nt, ntri + ((c - ctri + 7) >> 3));
+                if (c <= 0) return 0;
+                int a = (int)((sqrtf(36.0f + 32.0f * (float)c) - 6.0f) * 0.0625f);   // largest a with 8 a (a - 1) + 14 a <= c
+                while (8 * (a + 1) * a + 14 * (a + 1) <= c) ++a;
+                while (a > 0 && 8 * a * (a - 1) + 14 * a > c) --a;
+                const int bq = (c - (8 * a * (a - 1) + 14 * a) + 15) >> 4;           // full tiles of row a before the boundary
+                return bq > a ? (a + 1) * (a + 2) / 2 : a * (a + 1) / 2 + bq;
+            };
             int t0, t1;
             {
-                const int rest = nt - 1;
-                const int n0 = max(0, rest / C - kCholFactorTiles);
-                if (rank == 0) { t0 = 1; t1 = 1 + n0; }
+                const int total = ctri + 8 * m - 14;   // without tile 0 (the next diagonal tile, CTA 0's look-ahead)
+                const int share0 = max(0, total / C - 16 * kCholFactorTiles);
+                const int others = total - share0, per = others / (C - 1);
+                if (rank == 0) { t0 = 1; t1 = max(1, tile_at_cost(14 + share0)); }
                 else {
-                    const long long others = rest - n0;
-                    t0 = 1 + n0 + (int)(others * (rank - 1) / (C - 1));
-                    t1 = 1 + n0 + (int)(others * rank / (C - 1));
+                    t0 = max(1, tile_at_cost(14 + share0 + per * (rank - 1)));
+                    t1 = rank == C - 1 ? nt : max(1, tile_at_cost(14 + share0 + per * rank));
                 }
             }
             if (rank == 0) {
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
         __syncthreads();
     }
     CHOL_MARK(7);
-    if (profiling) for (int i = 0; i < 8; ++i) prof[i] = pacc[i];
+    if (profiling) { for (int i = 0; i < 8; ++i) prof[i] = pacc[i]; for (int i = 0; i < 4; ++i) prof[15 * 8 + 8 + i] = facc[i]; }
 #undef CHOL_MARK
 }
 
@@ -517,7 +546,7 @@ extern "C" adb_status adb_dense_solve(int32_t device, int32_t n, const double* A
     TRY(cudaEventCreate(&e0)); TRY(cudaEventCreate(&e1));
     TRY(cudaMalloc(&d0, elems * 8)); TRY(cudaMalloc(&d1, elems * 8)); TRY(cudaMalloc(&dinv, chol_scratch_elems(n) * 8));
     TRY(cudaMalloc(&dx, (size_t)ld * 8)); TRY(cudaMalloc(&dinfo, 4));
-    if (want_prof) { TRY(cudaMalloc(&dprof, 16 * 8 * sizeof(long long))); TRY(cudaMemset(dprof, 0, 16 * 8 * sizeof(long long))); }
+    if (want_prof) { TRY(cudaMalloc(&dprof, (16 * 8 + 4) * sizeof(long long))); TRY(cudaMemset(dprof, 0, (16 * 8 + 4) * sizeof(long long))); }
     TRY(cudaMemcpyAsync(d0, h.data(), elems * 8, cudaMemcpyHostToDevice, s));
     float total = 0.f;
     const int R = std::max(1, (int)reps);
@@ -538,7 +567,7 @@ extern "C" adb_status adb_dense_solve(int32_t device, int32_t n, const double* A
     TRY(cudaMemcpy(hx.data(), dx, (size_t)ld * 8, cudaMemcpyDeviceToHost));
     TRY(cudaMemcpy(&hinfo, dinfo, 4, cudaMemcpyDeviceToHost));
     if (want_prof) {   // developer aid: per-CTA phase cycles of the last repetition on stderr
-        long long hp[16 * 8];
+        long long hp[16 * 8 + 4];
         TRY(cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost));
         static const char* names[8] = {"load", "factor", "panel", "inverse", "barrier1", "update", "barrier2", "backsub"};
         for (int r : {0, 1, 7, 15}) {
@@ -546,6 +575,8 @@ extern "C" adb_status adb_dense_solve(int32_t device, int32_t n, const double* A
             for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %.1f", names[i], hp[r * 8 + i] / 1000.0);
             fprintf(stderr, " kcycles\n");
         }
+        fprintf(stderr, "[chol n=%d] inside factor_tile (cta 0): chains %.1f barriers %.1f column-update %.1f inverses %.1f kcycles\n", n, hp[128] / 1000.0,
+                hp[129] / 1000.0, hp[130] / 1000.0, hp[131] / 1000.0);
     }
     for (int c = 0; c < n; ++c) x[c] = hx[c];
     *info = hinfo;
