@@ -160,10 +160,25 @@ __device__ inline void huber(double delta, bool robust, double e2, double* rho0,
     else { const double s = sqrt(e2); *rho0 = 2 * s * delta - dsqr; *rho1 = delta / s; }
 }
 
-// scalars shared between the kernels and the host LM loop
+// sums the kernels of one LM step produce for the device-side LM controller
 struct Scalars {
     double chi_cur, chi_trial, scale, maxdiag;
     int info, pad;
+};
+
+// OptimizationAlgorithmLevenberg::solve + SparseOptimizer::optimize as a device-resident state machine
+// (optimization_algorithm_levenberg.cpp:61-189, sparse_optimizer.cpp:optimize): every kernel of a step reads its lambda, its
+// state buffers (cur = accepted state, cur ^ 1 = trial) and whether it has anything to do from here, so the host can enqueue
+// whole rounds without waiting for a single accept / reject decision.
+struct Lm {
+    double lambda, ni, current, ini, tau, chi2_initial;
+    int cur;              // state buffers holding the accepted state
+    int chi_last;         // chi2 buffers written by the last evaluation (the gates read these: stale-error semantics)
+    int need_lin;         // 1: the next step opens an outer iteration (buildSystem first)
+    int done;             // 1: the round is over, every later kernel of the batch returns at once
+    int first;            // 1: first iteration of the round (computeLambdaInit)
+    int it, it_max, q, max_trials, nbad;
+    int iterations_run, trials_run, trace_len, trace_cap, round, pad;
 };
 
 struct Opt {
@@ -196,6 +211,8 @@ struct StaticEdges {
 struct State {
     const double* pq; const double* pt; const double* X; const double* J; const double* D; const double* mq; const double* mt;
 };
+struct StatePair { State s[2]; };
+struct ChiPair { double* e[2]; double* j[2]; double* r[2]; double* m[2]; };   // chi2 per edge family, double buffered like the state
 
 // sums `nv` doubles per thread over the block in a fixed order; result in out[0..nv) (shared), valid after the call
 template <int NV>
@@ -221,10 +238,13 @@ constexpr int kBaThreads = 128;
 
 // buildSystem, landmark side: one thread per map point walks the point's (contiguous) edges: residual, Jacobians, Huber
 // weight; Hll / bl accumulate in registers and are stored once (no atomics, fixed order); one 6x3 Hpl block per edge.
-__global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, Opt O, StaticEdges E, State S, const int* __restrict__ point_ptr,
-                                                                       int np, const int* __restrict__ off_pose, double* __restrict__ Hll,
-                                                                       double* __restrict__ bl, double* __restrict__ W,
-                                                                       double* __restrict__ chi_e, Scalars* sc) {
+__global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, Opt O, StaticEdges E, StatePair SP, const Lm* __restrict__ lm,
+                                                                       const int* __restrict__ point_ptr, int np, const int* __restrict__ off_pose,
+                                                                       double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ W,
+                                                                       ChiPair chi, Scalars* sc) {
+    if (lm->done || !lm->need_lin) return;
+    const State S = SP.s[lm->cur];
+    double* __restrict__ chi_e = chi.e[lm->cur];
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     double rho_sum = 0;
     if (l < np) {
@@ -279,11 +299,14 @@ __global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, O
 // buildSystem, pose side: one CTA per free pose sums J_pose^T (w Omega) J_pose and -J_pose^T w Omega e over the pose's edges
 // (index list built once per solve) with a fixed-order block reduction and stores its 6x6 block: no atomics.
 // Runs after ba_point_linearize_kernel (reads the chi2 it stored) and before the dense-edge kernel adds to H atomically.
-__global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, StaticEdges E, State S, const int* __restrict__ pose_ptr,
-                                                               const int* __restrict__ pose_edges, const int* __restrict__ free_pose,
-                                                               const int* __restrict__ off_pose, int nd, const double* __restrict__ chi_e,
+__global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, StaticEdges E, StatePair SP, const Lm* __restrict__ lm,
+                                                               const int* __restrict__ pose_ptr, const int* __restrict__ pose_edges,
+                                                               const int* __restrict__ free_pose, const int* __restrict__ off_pose, int nd, ChiPair chi,
                                                                double* __restrict__ H, double* __restrict__ b) {
     __shared__ double scratch[8 * 27], red[27];
+    if (lm->done || !lm->need_lin) return;
+    const State S = SP.s[lm->cur];
+    const double* __restrict__ chi_e = chi.e[lm->cur];
     const int ip = free_pose[blockIdx.x], op = off_pose[ip];
     double v[27];
 #pragma unroll
@@ -360,11 +383,19 @@ __device__ inline void motion_error(const State& S, int m, double dt, const doub
 }
 
 // mode 0: linearise into H / b and accumulate chi_cur; mode 1: evaluate only, accumulate chi_trial
-__global__ void __launch_bounds__(kBaThreads) ba_dyn_kernel(Cam C, Opt O, DynEdges E, State S, DynOff off, int nd, double* __restrict__ H,
-                                                           double* __restrict__ b, double* __restrict__ chi_j, double* __restrict__ chi_r,
-                                                           double* __restrict__ chi_m, Scalars* sc, int mode) {
+__global__ void __launch_bounds__(kBaThreads) ba_dyn_kernel(Cam C, Opt O, DynEdges E, StatePair SP, const Lm* __restrict__ lm, DynOff off, int nd,
+                                                           double* __restrict__ H, double* __restrict__ b, ChiPair chi, Scalars* sc, int mode) {
+    if (lm->done || (mode == 0 && !lm->need_lin)) return;
+    const int which = mode == 0 ? lm->cur : lm->cur ^ 1;
+    const State S = SP.s[which];
+    double* __restrict__ chi_j = chi.j[which]; double* __restrict__ chi_r = chi.r[which]; double* __restrict__ chi_m = chi.m[which];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     double rho0 = 0, rho1 = 1;
+    if (mode == 1) {   // level-1 edges keep their last chi2 (the trial buffers inherit it)
+        if (t < E.nj) { if (E.j_level[t]) chi_j[t] = chi.j[which ^ 1][t]; }
+        else if (t < E.nj + E.nr) { if (E.r_level[t - E.nj]) chi_r[t - E.nj] = chi.r[which ^ 1][t - E.nj]; }
+        else if (t < E.nj + E.nr + E.nm) { if (E.m_level[t - E.nj - E.nr]) chi_m[t - E.nj - E.nr] = chi.m[which ^ 1][t - E.nj - E.nr]; }
+    }
     if (t < E.nj) {
         const int e = t;
         if (!E.j_level[e]) {
@@ -447,7 +478,8 @@ __global__ void __launch_bounds__(kBaThreads) ba_dyn_kernel(Cam C, Opt O, DynEdg
 
 // max |diag| over the dense block and the landmark blocks (computeLambdaInit, levenberg.cpp:166-180)
 __global__ void ba_maxdiag_kernel(const double* __restrict__ H, int nd, const double* __restrict__ Hll, const uint8_t* __restrict__ act_point,
-                                  int np, Scalars* sc) {
+                                  int np, const Lm* __restrict__ lm, Scalars* sc) {
+    if (lm->done || !lm->need_lin || !lm->first) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0;
     if (i < nd) m = fabs(H[(size_t)i * nd + i]);
@@ -463,8 +495,10 @@ __global__ void ba_maxdiag_kernel(const double* __restrict__ H, int nd, const do
 
 // S = H (lower) + lambda I in the padded layout of the cluster Cholesky (chol.cuh: pitch ld = 32 ceil(nd / 32), identity pad,
 // right-hand side in row ld), bs = b
-__global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __restrict__ b, int nd, int ld, double lambda, double* __restrict__ Sm,
-                                  double* __restrict__ bs) {
+__global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __restrict__ b, int nd, int ld, const Lm* __restrict__ lm,
+                                  double* __restrict__ Sm, double* __restrict__ bs) {
+    if (lm->done) return;
+    const double lambda = lm->lambda;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (size_t)ld * ld) {
         const int r = (int)(i / ld), c = (int)(i - (size_t)r * ld);
@@ -476,7 +510,9 @@ __global__ void ba_prepare_kernel(const double* __restrict__ H, const double* __
 
 // per point: Dinv = (Hll + lambda I)^-1 by cofactors (Eigen fixed-size inverse), db = Dinv bl
 __global__ void ba_dinv_kernel(const double* __restrict__ Hll, const double* __restrict__ bl, const uint8_t* __restrict__ act_point, int np,
-                               double lambda, double* __restrict__ Dinv, double* __restrict__ db) {
+                               const Lm* __restrict__ lm, double* __restrict__ Dinv, double* __restrict__ db) {
+    if (lm->done) return;
+    const double lambda = lm->lambda;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= np || !act_point[l]) return;
     const double* h = Hll + 6 * (size_t)l;
@@ -500,7 +536,8 @@ __global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* 
                                                                    const int* __restrict__ e_pose, const int* __restrict__ e_point,
                                                                    const int* __restrict__ off_pose, const double* __restrict__ W,
                                                                    const double* __restrict__ Dinv, const double* __restrict__ db, int nd,
-                                                                   double* __restrict__ Sm, double* __restrict__ bs) {
+                                                                   const Lm* __restrict__ lm, double* __restrict__ Sm, double* __restrict__ bs) {
+    if (lm->done) return;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (kBaThreads / 32) + (threadIdx.x >> 5);
     if (c >= nchunks) return;
@@ -569,9 +606,13 @@ __global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* 
 // dense updates: poses (exp), bone lengths (+), motions (right multiply), joints (+); also the dense
 // part of the gain-ratio denominator sum x (lambda x + b)
 struct DenseSizes { int n_poses, n_dists, n_motions, n_joints; };
-__global__ void ba_dense_update_kernel(DenseSizes N, DynOff off, const double* __restrict__ x, const double* __restrict__ b, double lambda,
-                                       int nd, State cur, double* __restrict__ pq, double* __restrict__ pt, double* __restrict__ D,
-                                       double* __restrict__ mq, double* __restrict__ mt, double* __restrict__ J, Scalars* sc) {
+__global__ void ba_dense_update_kernel(DenseSizes N, DynOff off, const double* __restrict__ x, const double* __restrict__ b, const Lm* __restrict__ lm,
+                                       int nd, StatePair SP, Scalars* sc) {
+    if (lm->done) return;
+    const double lambda = lm->lambda;
+    const State cur = SP.s[lm->cur], trs = SP.s[lm->cur ^ 1];
+    double* pq = const_cast<double*>(trs.pq); double* pt = const_cast<double*>(trs.pt); double* D = const_cast<double*>(trs.D);
+    double* mq = const_cast<double*>(trs.mq); double* mt = const_cast<double*>(trs.mt); double* J = const_cast<double*>(trs.J);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N.n_poses) {
         const int o = off.pose[i];
@@ -598,8 +639,11 @@ __global__ void __launch_bounds__(kBaThreads) ba_backsub_kernel(const int* __res
                                                                const uint8_t* __restrict__ e_level, const int* __restrict__ off_pose,
                                                                const uint8_t* __restrict__ act_point, int np, const double* __restrict__ W,
                                                                const double* __restrict__ Dinv, const double* __restrict__ bl,
-                                                               const double* __restrict__ x, double lambda, const double* __restrict__ Xcur,
-                                                               double* __restrict__ Xtrial, Scalars* sc) {
+                                                               const double* __restrict__ x, const Lm* __restrict__ lm, StatePair SP, Scalars* sc) {
+    if (lm->done) return;
+    const double lambda = lm->lambda;
+    const double* __restrict__ Xcur = SP.s[lm->cur].X;
+    double* __restrict__ Xtrial = const_cast<double*>(SP.s[lm->cur ^ 1].X);
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0;
     if (l < np) {
@@ -630,9 +674,13 @@ __global__ void __launch_bounds__(kBaThreads) ba_backsub_kernel(const int* __res
 }
 
 // computeActiveErrors + activeRobustChi2 on the trial state (static edges)
-__global__ void __launch_bounds__(kBaThreads) ba_eval_kernel(Cam C, Opt O, StaticEdges E, State S, double* __restrict__ chi_e, Scalars* sc) {
+__global__ void __launch_bounds__(kBaThreads) ba_eval_kernel(Cam C, Opt O, StaticEdges E, StatePair SP, const Lm* __restrict__ lm, ChiPair chi, Scalars* sc) {
+    if (lm->done) return;
+    const State S = SP.s[lm->cur ^ 1];
+    double* __restrict__ chi_e = chi.e[lm->cur ^ 1];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     double rho0 = 0, rho1;
+    if (e < E.n && E.level[e]) chi_e[e] = chi.e[lm->cur][e];   // level-1 edges keep their last chi2
     if (e < E.n && !E.level[e]) {
         const int ip = E.pose[e];
         double R[9], er[3], Xc[3];
@@ -647,10 +695,12 @@ __global__ void __launch_bounds__(kBaThreads) ba_eval_kernel(Cam C, Opt O, Stati
 }
 
 // chi2 gates + live depth test (src/Optimizer.cc:633-662, 671-699): flag = chi2 > gate || z <= 0
-__global__ void ba_gate_kernel(StaticEdges E, State S, const double* __restrict__ chi_e, double gate_mono, double gate_stereo,
+__global__ void ba_gate_kernel(StaticEdges E, StatePair SP, const Lm* __restrict__ lm, ChiPair chi, double gate_mono, double gate_stereo,
                                uint8_t* __restrict__ flag) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E.n) return;
+    const State S = SP.s[lm->cur];
+    const double* __restrict__ chi_e = chi.e[lm->chi_last];
     const int ip = E.pose[e];
     double R[9];
     quat_to_rot(S.pq + 4 * ip, R);
@@ -660,6 +710,71 @@ __global__ void ba_gate_kernel(StaticEdges E, State S, const double* __restrict_
     flag[e] = (chi_e[e] > (stereo ? gate_stereo : gate_mono)) || !(z > 0);
 }
 
+// H = 0, b = 0 and the buildSystem sums, only when the step opens an outer iteration
+__global__ void ba_clear_kernel(double* __restrict__ H, size_t n2, double* __restrict__ b, int nd, const Lm* __restrict__ lm, Scalars* sc) {
+    if (lm->done || !lm->need_lin) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) H[i] = 0.0;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (size_t)nd) b[t] = 0.0;
+    if (t == 0) { sc->chi_cur = 0.0; sc->maxdiag = 0.0; }
+}
+
+// between buildSystem and the first trial of an outer iteration: computeLambdaInit on the first one (lambda = tau max diag),
+// chi2 bookkeeping (levenberg.cpp:77-92); always: reset the sums of the coming trial
+__global__ void lm_iter_kernel(Lm* lm, Scalars* sc) {
+    if (lm->done) return;
+    if (lm->need_lin) {
+        lm->current = sc->chi_cur;
+        if (lm->first) {
+            lm->lambda = lm->tau * sc->maxdiag; lm->ni = 2; lm->nbad = 0; lm->first = 0;
+            if (lm->round == 0) lm->chi2_initial = lm->current;
+        }
+        lm->ini = lm->current;
+        lm->q = 0;
+        lm->need_lin = 0;
+        lm->chi_last = lm->cur;
+    }
+    sc->chi_trial = 0.0; sc->scale = 0.0; sc->info = 0;
+}
+
+// after the trial state has been evaluated: the accept / reject decision and the loop control of
+// OptimizationAlgorithmLevenberg::solve (levenberg.cpp:95-147) and SparseOptimizer::optimize (the nbad early exit of
+// src/Optimizer.cc's g2o copy); appends one row to the trace
+__global__ void lm_decide_kernel(Lm* lm, const Scalars* sc, double* __restrict__ trace) {
+    if (lm->done) return;
+    const bool ok = sc->info == 0;
+    const double temp = ok ? sc->chi_trial : DBL_MAX;
+    double rho = lm->current - temp;
+    const double scale = (ok ? sc->scale : 0.0) + 1e-3;
+    rho /= scale;
+    const bool good = rho > 0 && isfinite(temp);
+    if (trace && lm->trace_len < lm->trace_cap) {
+        double* t = trace + (size_t)ADB_BA_TRACE_COLS * lm->trace_len++;
+        t[0] = lm->lambda; t[1] = lm->current; t[2] = temp; t[3] = rho; t[4] = good ? 1 : 0;
+    }
+    lm->trials_run++;
+    lm->chi_last = lm->cur ^ 1;            // the trial buffers hold the errors of the last evaluation, accepted or not
+    if (good) {
+        double alpha = 1. - pow(2 * rho - 1, 3.0);
+        alpha = fmin(alpha, 2. / 3.);
+        lm->lambda *= fmax(1. / 3., alpha);
+        lm->ni = 2;
+        lm->current = temp;
+        lm->cur ^= 1;                      // accept: the trial buffers become the state (g2o: discardTop)
+    } else {
+        lm->lambda *= lm->ni;
+        lm->ni *= 2;                       // reject: nothing to restore (g2o: pop)
+    }
+    ++lm->q;
+    if (rho < 0 && lm->q < lm->max_trials) return;          // another trial on the same linearisation
+    ++lm->iterations_run;
+    if (lm->q == lm->max_trials || rho == 0) { lm->done = 1; return; }
+    if ((lm->ini - lm->current) * 1e3 < lm->ini) ++lm->nbad; else lm->nbad = 0;
+    if (lm->nbad >= 3) { lm->done = 1; return; }
+    if (++lm->it >= lm->it_max) { lm->done = 1; return; }
+    lm->need_lin = 1;
+}
 
 // ----------------------------------------------------------------------------------------
 // Optimizer::PoseOptimization (src/Optimizer.cc:232-429), one CTA per frame: the whole 4 x 10 LM
@@ -899,8 +1014,8 @@ struct adb_ba {
     DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, off_pose, act_point, pose_ptr, pose_edges, free_pose;
     DevBuf j_pose, j_joint, j_obs, j_info, j_level, r_i, r_j, r_d, r_info, r_level, m_p1, m_p2, m_m, m_dt, m_info, m_level;
     DevBuf off_joint, off_dist, off_motion;
-    DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work;
-    Scalars* h_scal = nullptr;   // pinned
+    DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work, lm, trace;
+    Lm* h_lm = nullptr;          // pinned mirror of the device LM controller
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
     std::vector<cudaEvent_t> tev;   // per-stage timing events
@@ -951,9 +1066,8 @@ struct Ctx {
     std::vector<int> off_pose, off_dist, off_motion, off_joint;
     std::vector<int2> pairs, chunks;
     std::vector<int> pose_ptr, pose_edges, free_pose;
-    int nd = 0, ld = 32, cur = 0, chi_last = 0;
-    double lambda = 0, ni = 2;
-    int trace_len = 0;
+    int nd = 0, ld = 32;
+    Lm hl = {};            // host copy of the controller as of the last read-back
     Ctx(adb_ba* s_, adb_ba_problem* p, const adb_ba_options* o, adb_ba_result* r, volatile const uint8_t* st) : s(s_), P(p), O(o), R(r), stop(st), tm(s_) {}
 
     bool stopped() const { return stop && *stop; }
@@ -962,6 +1076,12 @@ struct Ctx {
         return State{s->pq[i].as<double>(), s->pt[i].as<double>(), s->X[i].as<double>(), s->Jt[i].as<double>(), s->Dd[i].as<double>(),
                      s->mq[i].as<double>(), s->mt[i].as<double>()};
     }
+    StatePair states() const { return StatePair{{state(0), state(1)}}; }
+    ChiPair chis() const {
+        return ChiPair{{s->chi_e[0].as<double>(), s->chi_e[1].as<double>()}, {s->chi_j[0].as<double>(), s->chi_j[1].as<double>()},
+                       {s->chi_r[0].as<double>(), s->chi_r[1].as<double>()}, {s->chi_m[0].as<double>(), s->chi_m[1].as<double>()}};
+    }
+    Lm* dlm() const { return s->lm.as<Lm>(); }
     StaticEdges sedges() const {
         return StaticEdges{P->n_edges, s->e_pose.as<int>(), s->e_point.as<int>(), s->e_obs.as<double>(), s->e_info.as<double>(), s->e_level.as<uint8_t>()};
     }
@@ -1075,6 +1195,9 @@ struct Ctx {
         }
         if ((r = s->flag.ensure(std::max<size_t>(std::max(E, n_dyn()), 1))) != ADB_OK) return r;
         if ((r = s->scal.ensure(sizeof(Scalars))) != ADB_OK) return r;
+        if ((r = s->lm.ensure(sizeof(Lm))) != ADB_OK) return r;
+        if ((r = s->trace.ensure(std::max<size_t>(R->trace ? R->trace_cap : 0, 1) * ADB_BA_TRACE_COLS * sizeof(double))) != ADB_OK) return r;
+        ADB_CUDA(cudaMemsetAsync(s->scal.p, 0, sizeof(Scalars), st));
         lvl_e.assign(E, 0); lvl_j.assign(P->n_joint_edges, 0); lvl_r.assign(P->n_rigid_edges, 0); lvl_m.assign(P->n_motion_edges, 0);
         return ADB_OK;
     }
@@ -1154,70 +1277,65 @@ struct Ctx {
         return ADB_OK;
     }
 
-    adb_status read_scalars() {
-        ADB_CUDA(cudaMemcpyAsync(s->h_scal, s->scal.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    adb_status read_lm() {
+        ADB_CUDA(cudaMemcpyAsync(s->h_lm, s->lm.p, sizeof(Lm), cudaMemcpyDeviceToHost, s->stream));
         ADB_CUDA(cudaStreamSynchronize(s->stream));
+        hl = *s->h_lm;
         return ADB_OK;
     }
 
-    // buildSystem at the current state (+ chi2 of the current state into chi_*[chi_last])
-    adb_status linearize(bool robust) {
+    // One LM step, enqueued without knowing what the previous one decided: buildSystem at the accepted state (skipped on the
+    // device unless the step opens an outer iteration), one trial with the controller's lambda into the other state buffers,
+    // evaluation, decision.  Every kernel returns at once when the round is already over.
+    adb_status enqueue_step(bool robust) {
         cudaStream_t st = s->stream;
         const int E = P->n_edges, NP = P->n_points;
+        Scalars* sc = s->scal.as<Scalars>();
+        Lm* lm = dlm();
+        const StatePair SP = states();
+        const ChiPair CH = chis();
+        const size_t n2 = (size_t)nd * nd;
         tm.begin(0);
-        ADB_CUDA(cudaMemsetAsync(s->H.p, 0, std::max<size_t>((size_t)nd * nd, 1) * 8, st));
-        ADB_CUDA(cudaMemsetAsync(s->b.p, 0, std::max(nd, 1) * 8, st));
-        ADB_CUDA(cudaMemsetAsync(s->scal.p, 0, sizeof(Scalars), st));
-        chi_last = cur;
+        ba_clear_kernel<<<std::min(grid_for(std::max<size_t>(n2, 1), 256), 592), 256, 0, st>>>(s->H.as<double>(), n2, s->b.as<double>(), nd, lm, sc);
+        ++s->launches;
         if (NP > 0) {
-            ba_point_linearize_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), state(cur), s->point_ptr.as<int>(), NP,
+            ba_point_linearize_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->point_ptr.as<int>(), NP,
                                                                                       s->off_pose.as<int>(), s->Hll.as<double>(), s->bl.as<double>(),
-                                                                                      s->W.as<double>(), s->chi_e[chi_last].as<double>(), s->scal.as<Scalars>());
+                                                                                      s->W.as<double>(), CH, sc);
             ++s->launches;
         }
         if (E > 0 && !free_pose.empty()) {
-            ba_pose_linearize_kernel<<<(int)free_pose.size(), 256, 0, st>>>(cam(), opt(robust), sedges(), state(cur), s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
-                                                                           s->free_pose.as<int>(), s->off_pose.as<int>(), nd, s->chi_e[chi_last].as<double>(),
-                                                                           s->H.as<double>(), s->b.as<double>());
+            ba_pose_linearize_kernel<<<(int)free_pose.size(), 256, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
+                                                                           s->free_pose.as<int>(), s->off_pose.as<int>(), nd, CH, s->H.as<double>(), s->b.as<double>());
             ++s->launches;
         }
         if (n_dyn() > 0) {
-            ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), state(cur), doff(), nd, s->H.as<double>(),
-                                                                               s->b.as<double>(), s->chi_j[chi_last].as<double>(),
-                                                                               s->chi_r[chi_last].as<double>(), s->chi_m[chi_last].as<double>(),
-                                                                               s->scal.as<Scalars>(), 0);
+            ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), SP, lm, doff(), nd, s->H.as<double>(),
+                                                                               s->b.as<double>(), CH, sc, 0);
             ++s->launches;
         }
-        ADB_CUDA(cudaGetLastError());
         tm.end();
-        return ADB_OK;
-    }
-
-    // one LM trial: solve with the current lambda, form the trial state in buffer cur^1, evaluate it
-    adb_status trial(bool robust) {
-        cudaStream_t st = s->stream;
-        const int E = P->n_edges, NP = P->n_points, tr = cur ^ 1;
-        Scalars* sc = s->scal.as<Scalars>();
+        tm.begin(4);
+        ba_maxdiag_kernel<<<grid_for(nd + NP, 256), 256, 0, st>>>(s->H.as<double>(), nd, s->Hll.as<double>(), s->act_point.as<uint8_t>(), NP, lm, sc);
+        lm_iter_kernel<<<1, 1, 0, st>>>(lm, sc);
+        s->launches += 2;
+        tm.end();
         tm.begin(1);
-        // keep chi_cur / maxdiag, reset the rest
-        ADB_CUDA(cudaMemsetAsync(&sc->chi_trial, 0, 2 * sizeof(double), st));
-        ADB_CUDA(cudaMemsetAsync(&sc->info, 0, sizeof(int), st));
         if (nd > 0) {
-            ba_prepare_kernel<<<grid_for((size_t)ld * ld, 256), 256, 0, st>>>(s->H.as<double>(), s->b.as<double>(), nd, ld, lambda, s->Sm.as<double>(),
-                                                                             s->bs.as<double>());
+            ba_prepare_kernel<<<grid_for((size_t)ld * ld, 256), 256, 0, st>>>(s->H.as<double>(), s->b.as<double>(), nd, ld, lm, s->Sm.as<double>(), s->bs.as<double>());
             ++s->launches;
         }
         if (NP > 0) {
-            ba_dinv_kernel<<<grid_for(NP, 128), 128, 0, st>>>(s->Hll.as<double>(), s->bl.as<double>(), s->act_point.as<uint8_t>(), NP, lambda,
-                                                              s->Dinv.as<double>(), s->db.as<double>());
+            ba_dinv_kernel<<<grid_for(NP, 128), 128, 0, st>>>(s->Hll.as<double>(), s->bl.as<double>(), s->act_point.as<uint8_t>(), NP, lm, s->Dinv.as<double>(),
+                                                              s->db.as<double>());
             ++s->launches;
         }
         if (!chunks.empty()) {
             const int nch = (int)chunks.size();
-            ba_schur_block_kernel<<<grid_for(nch, kBaThreads / 32), kBaThreads, 0, st>>>(s->pairs.as<int2>(), s->chunks.as<int2>(), nch,
-                                                                                        s->e_pose.as<int>(), s->e_point.as<int>(), s->off_pose.as<int>(),
-                                                                                        s->W.as<double>(), s->Dinv.as<double>(), s->db.as<double>(), ld,
-                                                                                        s->Sm.as<double>(), s->Sm.as<double>() + (size_t)ld * ld);   // rhs row
+            ba_schur_block_kernel<<<grid_for(nch, kBaThreads / 32), kBaThreads, 0, st>>>(s->pairs.as<int2>(), s->chunks.as<int2>(), nch, s->e_pose.as<int>(),
+                                                                                        s->e_point.as<int>(), s->off_pose.as<int>(), s->W.as<double>(),
+                                                                                        s->Dinv.as<double>(), s->db.as<double>(), ld, lm, s->Sm.as<double>(),
+                                                                                        s->Sm.as<double>() + (size_t)ld * ld);   // rhs row
             ++s->launches;
         }
         ADB_CUDA(cudaGetLastError());
@@ -1225,7 +1343,7 @@ struct Ctx {
         tm.begin(2);
         if (nd > 0) {
             // LinearSolverDense / LinearSolverEigen::solve: one cluster launch factors, substitutes and writes x to bs
-            const adb_status cs = chol_solve_launch(st, s->Sm.as<double>(), ld, ld / kCholNB, s->work.as<double>(), s->bs.as<double>(), &sc->info, 0);
+            const adb_status cs = chol_solve_launch(st, s->Sm.as<double>(), ld, ld / kCholNB, s->work.as<double>(), s->bs.as<double>(), &sc->info, 0, &lm->done);
             if (cs != ADB_OK) return cs;
             ++s->launches;
         }
@@ -1234,99 +1352,52 @@ struct Ctx {
         {
             const DenseSizes N{P->n_poses, P->n_dists, P->n_motions, P->n_joints};
             const int nthreads = std::max(nd, P->n_poses + P->n_dists + P->n_motions + P->n_joints);
-            ba_dense_update_kernel<<<grid_for(nthreads, 128), 128, 0, st>>>(N, doff(), s->bs.as<double>(), s->b.as<double>(), lambda, nd, state(cur),
-                                                                           s->pq[tr].as<double>(), s->pt[tr].as<double>(), s->Dd[tr].as<double>(),
-                                                                           s->mq[tr].as<double>(), s->mt[tr].as<double>(), s->Jt[tr].as<double>(), sc);
+            ba_dense_update_kernel<<<grid_for(nthreads, 128), 128, 0, st>>>(N, doff(), s->bs.as<double>(), s->b.as<double>(), lm, nd, SP, sc);
             ++s->launches;
         }
         if (NP > 0) {
             ba_backsub_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(s->point_ptr.as<int>(), s->e_pose.as<int>(), s->e_level.as<uint8_t>(),
                                                                               s->off_pose.as<int>(), s->act_point.as<uint8_t>(), NP, s->W.as<double>(),
-                                                                              s->Dinv.as<double>(), s->bl.as<double>(), s->bs.as<double>(), lambda,
-                                                                              s->X[cur].as<double>(), s->X[tr].as<double>(), sc);
+                                                                              s->Dinv.as<double>(), s->bl.as<double>(), s->bs.as<double>(), lm, SP, sc);
             ++s->launches;
         }
-        chi_last = tr;
         if (E > 0) {
-            // level-1 edges keep their last chi2: copy-forward is not needed because both chi buffers are only
-            // ever written for active edges and gates read the buffer of the last evaluation; seed it first
-            ADB_CUDA(cudaMemcpyAsync(s->chi_e[tr].p, s->chi_e[cur].p, (size_t)E * 8, cudaMemcpyDeviceToDevice, st));
-            ba_eval_kernel<<<grid_for(E, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), state(tr), s->chi_e[tr].as<double>(), sc);
+            ba_eval_kernel<<<grid_for(E, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, CH, sc);
             ++s->launches;
         }
         if (n_dyn() > 0) {
-            if (P->n_joint_edges) ADB_CUDA(cudaMemcpyAsync(s->chi_j[tr].p, s->chi_j[cur].p, (size_t)P->n_joint_edges * 8, cudaMemcpyDeviceToDevice, st));
-            if (P->n_rigid_edges) ADB_CUDA(cudaMemcpyAsync(s->chi_r[tr].p, s->chi_r[cur].p, (size_t)P->n_rigid_edges * 8, cudaMemcpyDeviceToDevice, st));
-            if (P->n_motion_edges) ADB_CUDA(cudaMemcpyAsync(s->chi_m[tr].p, s->chi_m[cur].p, (size_t)P->n_motion_edges * 8, cudaMemcpyDeviceToDevice, st));
-            ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), state(tr), doff(), nd, nullptr, nullptr,
-                                                                               s->chi_j[tr].as<double>(), s->chi_r[tr].as<double>(),
-                                                                               s->chi_m[tr].as<double>(), sc, 1);
+            ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), SP, lm, doff(), nd, nullptr, nullptr, CH, sc, 1);
             ++s->launches;
         }
+        tm.end();
+        tm.begin(4);
+        lm_decide_kernel<<<1, 1, 0, st>>>(lm, sc, R->trace ? s->trace.as<double>() : nullptr);
+        ++s->launches;
         ADB_CUDA(cudaGetLastError());
         tm.end();
         return ADB_OK;
     }
 
-    // SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve
+    // SparseOptimizer::optimize(iterations) + OptimizationAlgorithmLevenberg::solve, controlled on the device (struct Lm).  The host
+    // enqueues `iterations` steps -- enough when every trial is accepted, the common case -- reads the controller back once, and
+    // tops up while rejected trials have used up steps.  The stop flag is polled between those batches (the reference polls it
+    // per iteration and per trial; a flag raised mid-batch takes effect at the next read-back).
     adb_status optimize(int iterations, bool robust, int round, double* chi_out) {
-        int nbad = 0, it_run = 0;
-        double current = 0;
         adb_status r;
-        for (int it = 0; it < iterations && !stopped(); ++it) {
-            if ((r = linearize(robust)) != ADB_OK) return r;
-            if (it == 0) {
-                tm.begin(4);
-                ba_maxdiag_kernel<<<grid_for(nd + P->n_points, 256), 256, 0, s->stream>>>(s->H.as<double>(), nd, s->Hll.as<double>(),
-                                                                                         s->act_point.as<uint8_t>(), P->n_points, s->scal.as<Scalars>());
-                ++s->launches;
-                tm.end();
-            }
-            if ((r = read_scalars()) != ADB_OK) return r;
-            current = s->h_scal->chi_cur;
-            if (it == 0) {
-                lambda = O->tau * s->h_scal->maxdiag; ni = 2; nbad = 0;
-                if (round == 0) R->chi2_initial = current;
-            }
-            const double ini = current;
-            double rho = 0;
-            int q = 0;
-            do {
-                if ((r = trial(robust)) != ADB_OK) return r;
-                if ((r = read_scalars()) != ADB_OK) return r;
-                const bool ok = s->h_scal->info == 0;
-                double temp = s->h_scal->chi_trial;
-                if (!ok) temp = std::numeric_limits<double>::max();
-                rho = current - temp;
-                double scale = ok ? s->h_scal->scale : 0.0;
-                scale += 1e-3;
-                rho /= scale;
-                const bool good = rho > 0 && std::isfinite(temp);
-                if (R->trace && trace_len < R->trace_cap) {
-                    double* t = R->trace + (size_t)ADB_BA_TRACE_COLS * trace_len++;
-                    t[0] = lambda; t[1] = current; t[2] = temp; t[3] = rho; t[4] = good ? 1 : 0;
-                }
-                R->trials_run++;
-                if (good) {
-                    double alpha = 1. - std::pow((2 * rho - 1), 3);
-                    alpha = std::min(alpha, 2. / 3.);
-                    lambda *= std::max(1. / 3., alpha);
-                    ni = 2;
-                    current = temp;
-                    cur ^= 1;          // accept: the trial buffers become the state (g2o: discardTop)
-                } else {
-                    lambda *= ni;
-                    ni *= 2;           // reject: nothing to restore (g2o: pop)
-                }
-                ++q;
-            } while (rho < 0 && q < O->max_trials && !stopped());
-            ++it_run;
-            if (q == O->max_trials || rho == 0) break;
-            if ((ini - current) * 1e3 < ini) ++nbad; else nbad = 0;
-            if (nbad >= 3) break;
+        hl.need_lin = 1; hl.done = iterations <= 0 ? 1 : 0; hl.first = 1; hl.it = 0; hl.it_max = iterations; hl.q = 0; hl.max_trials = O->max_trials;
+        hl.nbad = 0; hl.iterations_run = 0; hl.round = round; hl.tau = O->tau; hl.trace_cap = R->trace ? R->trace_cap : 0;
+        if (round == 0) { hl.cur = 0; hl.chi_last = 0; hl.trials_run = 0; hl.trace_len = 0; hl.lambda = 0; hl.ni = 2; hl.current = 0; hl.ini = 0; hl.chi2_initial = 0; }
+        *s->h_lm = hl;
+        ADB_CUDA(cudaMemcpyAsync(s->lm.p, s->h_lm, sizeof(Lm), cudaMemcpyHostToDevice, s->stream));
+        int batch = iterations;
+        while (!hl.done && !stopped()) {
+            for (int k = 0; k < batch; ++k) if ((r = enqueue_step(robust)) != ADB_OK) return r;
+            if ((r = read_lm()) != ADB_OK) return r;
+            batch = 2;
         }
-        R->iterations_run[round] = it_run;
-        *chi_out = current;
+        R->iterations_run[round] = hl.iterations_run;
+        R->trials_run = hl.trials_run;
+        *chi_out = hl.current;
         return ADB_OK;
     }
 
@@ -1336,14 +1407,14 @@ struct Ctx {
         const int E = P->n_edges;
         fe.assign(E, 0);
         if (E > 0) {
-            ba_gate_kernel<<<grid_for(E, 256), 256, 0, st>>>(sedges(), state(cur), s->chi_e[chi_last].as<double>(), O->chi2_mono, O->chi2_stereo,
-                                                             s->flag.as<uint8_t>());
+            ba_gate_kernel<<<grid_for(E, 256), 256, 0, st>>>(sedges(), states(), dlm(), chis(), O->chi2_mono, O->chi2_stereo, s->flag.as<uint8_t>());
             ++s->launches;
             ADB_CUDA(cudaGetLastError());
             ADB_CUDA(cudaMemcpyAsync(fe.data(), s->flag.p, E, cudaMemcpyDeviceToHost, st));
-            if (chi_out) { chi_out->assign(E, 0); ADB_CUDA(cudaMemcpyAsync(chi_out->data(), s->chi_e[chi_last].p, (size_t)E * 8, cudaMemcpyDeviceToHost, st)); }
+            if (chi_out) { chi_out->assign(E, 0); ADB_CUDA(cudaMemcpyAsync(chi_out->data(), s->chi_e[hl.chi_last].p, (size_t)E * 8, cudaMemcpyDeviceToHost, st)); }
         }
         // the few hundred dense-block edges are gated on the host from their chi2 and the current state
+        const int cur = hl.cur, chi_last = hl.chi_last;   // as of the read-back that ended the round
         std::vector<double> cj(P->n_joint_edges), cr(P->n_rigid_edges), cm(P->n_motion_edges), hq, ht, hj;
         if (P->n_joint_edges) {
             ADB_CUDA(cudaMemcpyAsync(cj.data(), s->chi_j[chi_last].p, cj.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -1371,6 +1442,7 @@ struct Ctx {
 
     adb_status download_state() {
         cudaStream_t st = s->stream;
+        const int cur = hl.cur;
 #define DN(dst, buf, n) if ((n) > 0) ADB_CUDA(cudaMemcpyAsync(dst, buf.p, (size_t)(n) * 8, cudaMemcpyDeviceToHost, st))
         DN(P->pose_q, s->pq[cur], 4 * (size_t)P->n_poses); DN(P->pose_t, s->pt[cur], 3 * (size_t)P->n_poses); DN(P->points, s->X[cur], 3 * (size_t)P->n_points);
         DN(P->joints, s->Jt[cur], 3 * (size_t)P->n_joints); DN(P->dists, s->Dd[cur], P->n_dists);
@@ -1423,7 +1495,7 @@ adb_status adb_ba_create(int32_t device, adb_ba_t* out) {
     adb_ba* s = new adb_ba();
     s->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMallocHost(&s->h_scal, sizeof(Scalars));
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_lm, sizeof(Lm));
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "ba create", __FILE__, __LINE__); }
     *out = s;
     return ADB_OK;
@@ -1438,10 +1510,10 @@ adb_status adb_ba_destroy(adb_ba_t s) {
                      &s->act_point, &s->j_pose, &s->j_joint, &s->j_obs, &s->j_info, &s->j_level, &s->r_i, &s->r_j, &s->r_d, &s->r_info, &s->r_level,
                      &s->m_p1, &s->m_p2, &s->m_m, &s->m_dt, &s->m_info, &s->m_level, &s->off_joint, &s->off_dist, &s->off_motion, &s->H, &s->b,
                      &s->Sm, &s->bs, &s->Hll, &s->bl, &s->W, &s->Dinv, &s->db, &s->chi_e[0], &s->chi_e[1], &s->chi_j[0], &s->chi_j[1], &s->chi_r[0],
-                     &s->chi_r[1], &s->chi_m[0], &s->chi_m[1], &s->flag, &s->scal, &s->work};
+                     &s->chi_r[1], &s->chi_m[0], &s->chi_m[1], &s->flag, &s->scal, &s->work, &s->lm, &s->trace};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
-    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->h_lm) cudaFreeHost(s->h_lm);
     cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -1485,8 +1557,11 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
         R->chi2_round[1] = chi;
         if (c.stopped()) R->stopped = 1;
     }
-    R->lambda_final = c.lambda;
-    R->trace_len = c.trace_len;
+    R->lambda_final = c.hl.lambda;
+    R->chi2_initial = c.hl.chi2_initial;
+    R->trace_len = c.hl.trace_len;
+    if (R->trace && c.hl.trace_len > 0)
+        ADB_CUDA(cudaMemcpyAsync(R->trace, s->trace.p, (size_t)c.hl.trace_len * ADB_BA_TRACE_COLS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     std::vector<double> chi_sorted;
     if ((r = c.gates(fe, fj, fr, fm, R->edge_chi2 ? &chi_sorted : nullptr)) != ADB_OK) return r;
     for (int k = 0; k < P->n_edges; ++k) {

@@ -267,7 +267,8 @@ constexpr int kCholFactorTiles = 12;   // the look-ahead factorisation costs CTA
 
 size_t chol_scratch_elems(int n) { const size_t nb = (size_t)chol_nblk(n); return nb * kCholNB * kCholNB + nb * kCholLd; }
 
-__global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S, int ld, int nblk, double* scratch, double* xout, int* info, long long* prof) {
+__global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S, int ld, int nblk, double* scratch, double* xout, int* info, const int* skip, long long* prof) {
+    if (skip != nullptr && *skip != 0) return;   // device-side LM control: the round is already over (uniform over the cluster)
     __shared__ TileSmem T;
     __shared__ double xb[kCholNB];
     extern __shared__ double yb[];   // [ld] (back-substitution, CTA 0)
@@ -492,7 +493,7 @@ int chol_max_cluster() {
     return cached;
 }
 
-adb_status chol_solve_launch(cudaStream_t st, double* S, int ld, int nblk, double* scratch, double* x, int* info, int cluster, long long* prof) {
+adb_status chol_solve_launch(cudaStream_t st, double* S, int ld, int nblk, double* scratch, double* x, int* info, int cluster, const int* skip, long long* prof) {
     ADB_CHECK(nblk >= 1 && ld == nblk * kCholNB, ADB_ERR_INVALID, "chol: bad padded order");
     if (cluster <= 0) cluster = nblk >= 16 ? chol_max_cluster() : 8;   // small systems: fewer CTAs, cheaper barriers
     ADB_CHECK(cluster == 2 || cluster == 4 || cluster == 8 || cluster == 16, ADB_ERR_INVALID, "chol: cluster size %d", cluster);
@@ -509,7 +510,7 @@ adb_status chol_solve_launch(cudaStream_t st, double* S, int ld, int nblk, doubl
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    ADB_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, S, ld, nblk, scratch, x, info, prof));
+    ADB_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, S, ld, nblk, scratch, x, info, skip, prof));
     return ADB_OK;
 }
 
@@ -554,7 +555,7 @@ extern "C" adb_status adb_dense_solve(int32_t device, int32_t n, const double* A
         TRY(cudaMemcpyAsync(d1, d0, elems * 8, cudaMemcpyDeviceToDevice, s));
         TRY(cudaMemsetAsync(dinfo, 0, 4, s));
         TRY(cudaEventRecord(e0, s));
-        st = chol_solve_launch(s, d1, ld, nblk, dinv, dx, dinfo, cluster, dprof);
+        st = chol_solve_launch(s, d1, ld, nblk, dinv, dx, dinfo, cluster, nullptr, dprof);
         if (st != ADB_OK) { cleanup(); return st; }
         TRY(cudaEventRecord(e1, s));
         TRY(cudaStreamSynchronize(s));

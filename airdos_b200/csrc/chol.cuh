@@ -14,7 +14,8 @@ inline size_t chol_elems(int n) { const size_t ld = (size_t)chol_nblk(n) * kChol
 // Factors S in place (lower triangle, right-hand side in row ld) and writes the solution (ld entries, pad = 0) to x.
 // scratch: chol_scratch_elems(n) doubles (inverted / published diagonal factors).  cluster: 8 / 16, or 0 = choose by order.  *info must be zero on entry.
 size_t chol_scratch_elems(int n);
-adb_status chol_solve_launch(cudaStream_t st, double* S, int ld, int nblk, double* scratch, double* x, int* info, int cluster, long long* prof = nullptr);
+adb_status chol_solve_launch(cudaStream_t st, double* S, int ld, int nblk, double* scratch, double* x, int* info, int cluster, const int* skip = nullptr,
+                             long long* prof = nullptr);   // *skip != 0 (device memory) turns the launch into a no-op
 int chol_max_cluster();
 
 }  // namespace adb
