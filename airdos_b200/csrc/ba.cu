@@ -139,17 +139,21 @@ __device__ inline int reproj_error(const Cam& C, const double* R, const double* 
     e[2] = 0;
     return 2;
 }
+// linearizeOplus of Edge(Stereo)SE3ProjectXYZ (types_six_dof_expmap.cpp:188-234, 159-185).  The reference divides by z / z^2 in
+// every term (28 FP64 divisions per edge); here 1/z and 1/z^2 are formed once and multiplied in: each term differs from the
+// quotient form by at most one rounding (1e-16 relative), far below the 1e-4 parity bar, and the kernels lose a third of
+// their instructions.
 __device__ inline void reproj_jacobians(const Cam& C, const double* R, const double* Xc, int dim, double* Ji, double* Jj) {
-    const double x = Xc[0], y = Xc[1], z = Xc[2], z2 = z * z, fx = C.fx, fy = C.fy, bf = C.bf;
+    const double x = Xc[0], y = Xc[1], z = Xc[2], iz = 1.0 / z, iz2 = iz * iz, fx = C.fx, fy = C.fy, bf = C.bf;
     for (int c = 0; c < 3; ++c) {
-        Ji[c] = -fx * R[c] / z + fx * x * R[6 + c] / z2;
-        Ji[3 + c] = -fy * R[3 + c] / z + fy * y * R[6 + c] / z2;
-        Ji[6 + c] = dim == 3 ? Ji[c] - bf * R[6 + c] / z2 : 0.0;
+        Ji[c] = -fx * R[c] * iz + fx * x * R[6 + c] * iz2;
+        Ji[3 + c] = -fy * R[3 + c] * iz + fy * y * R[6 + c] * iz2;
+        Ji[6 + c] = dim == 3 ? Ji[c] - bf * R[6 + c] * iz2 : 0.0;
     }
-    Jj[0] = x * y / z2 * fx; Jj[1] = -(1 + (x * x / z2)) * fx; Jj[2] = y / z * fx; Jj[3] = -1. / z * fx; Jj[4] = 0; Jj[5] = x / z2 * fx;
-    Jj[6] = (1 + y * y / z2) * fy; Jj[7] = -x * y / z2 * fy; Jj[8] = -x / z * fy; Jj[9] = 0; Jj[10] = -1. / z * fy; Jj[11] = y / z2 * fy;
+    Jj[0] = x * y * iz2 * fx; Jj[1] = -(1 + (x * x * iz2)) * fx; Jj[2] = y * iz * fx; Jj[3] = -iz * fx; Jj[4] = 0; Jj[5] = x * iz2 * fx;
+    Jj[6] = (1 + y * y * iz2) * fy; Jj[7] = -x * y * iz2 * fy; Jj[8] = -x * iz * fy; Jj[9] = 0; Jj[10] = -iz * fy; Jj[11] = y * iz2 * fy;
     if (dim == 3) {
-        Jj[12] = Jj[0] - bf * y / z2; Jj[13] = Jj[1] + bf * x / z2; Jj[14] = Jj[2]; Jj[15] = Jj[3]; Jj[16] = 0; Jj[17] = Jj[5] - bf / z2;
+        Jj[12] = Jj[0] - bf * y * iz2; Jj[13] = Jj[1] + bf * x * iz2; Jj[14] = Jj[2]; Jj[15] = Jj[3]; Jj[16] = 0; Jj[17] = Jj[5] - bf * iz2;
     } else {
         for (int i = 12; i < 18; ++i) Jj[i] = 0;
     }
@@ -236,8 +240,10 @@ __device__ inline void block_reduce_fixed(double (&v)[NV], double* scratch /*[8]
 
 constexpr int kBaThreads = 128;
 
-// buildSystem, landmark side: one thread per map point walks the point's (contiguous) edges: residual, Jacobians, Huber
-// weight; Hll / bl accumulate in registers and are stored once (no atomics, fixed order); one 6x3 Hpl block per edge.
+// buildSystem, landmark side: kPtLanes lanes per map point, one edge per lane (a point's edges are contiguous): residual,
+// Jacobians, Huber weight, one 6x3 Hpl block stored per edge; Hll / bl are summed over the lane group by shuffles in a fixed
+// order and stored once (no atomics).  Thread-per-point left 93 % of the warp slots idle (157 CTAs, 0.27 waves).
+constexpr int kPtLanes = 8;
 __global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, Opt O, StaticEdges E, StatePair SP, const Lm* __restrict__ lm,
                                                                        const int* __restrict__ point_ptr, int np, const int* __restrict__ off_pose,
                                                                        double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ W,
@@ -245,12 +251,12 @@ __global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, O
     if (lm->done || !lm->need_lin) return;
     const State S = SP.s[lm->cur];
     double* __restrict__ chi_e = chi.e[lm->cur];
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) / kPtLanes, sub = threadIdx.x % kPtLanes;
     double rho_sum = 0;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // Hll (6 unique) | bl (3)
     if (l < np) {
-        double hl[6] = {0, 0, 0, 0, 0, 0}, bv[3] = {0, 0, 0};
         const double X[3] = {S.X[3 * (size_t)l], S.X[3 * (size_t)l + 1], S.X[3 * (size_t)l + 2]};
-        for (int e = point_ptr[l]; e < point_ptr[l + 1]; ++e) {
+        for (int e = point_ptr[l] + sub; e < point_ptr[l + 1]; e += kPtLanes) {
             if (E.level[e]) continue;
             const int ip = E.pose[e];
             double R[9], er[3], Xc[3], Ji[9], Jj[18], rho0, rho1;
@@ -270,11 +276,11 @@ __global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, O
                 for (int j = i; j < 3; ++j, ++u) {
                     double s = 0;
                     for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * w * Ji[k * 3 + j];
-                    hl[u] += s;
+                    acc[u] += s;
                 }
                 double s = 0;
                 for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * (-w0 * er[k] * rho1);
-                bv[i] += s;
+                acc[6 + i] += s;
             }
             if (off_pose[ip] >= 0) {
                 double* We = W + 18 * (size_t)e;
@@ -288,33 +294,45 @@ __global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, O
                     }
             }
         }
+    }
+    // fixed-order tree over the lane group (all 32 lanes take part: groups are aligned)
 #pragma unroll
-        for (int u = 0; u < 6; ++u) Hll[6 * (size_t)l + u] = hl[u];
+    for (int k = 0; k < 9; ++k)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) bl[3 * (size_t)l + i] = bv[i];
+        for (int o = 1; o < kPtLanes; o <<= 1) acc[k] += __shfl_xor_sync(0xFFFFFFFFu, acc[k], o);
+    if (l < np && sub == 0) {
+#pragma unroll
+        for (int u = 0; u < 6; ++u) Hll[6 * (size_t)l + u] = acc[u];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) bl[3 * (size_t)l + i] = acc[6 + i];
     }
     block_sum_to(rho_sum, &sc->chi_cur);
 }
 
-// buildSystem, pose side: one CTA per free pose sums J_pose^T (w Omega) J_pose and -J_pose^T w Omega e over the pose's edges
-// (index list built once per solve) with a fixed-order block reduction and stores its 6x6 block: no atomics.
+// buildSystem, pose side: kPoseChunks CTAs per free pose, each over a contiguous slice of the pose's edge list (built once per solve):
+// J_pose^T (w Omega) J_pose and -J_pose^T w Omega e summed with a fixed-order block reduction into a partial record; the reduce
+// kernel adds the partials in a fixed order and stores the 6x6 block: no atomics, deterministic.  (One CTA per pose was 49 CTAs
+// on 148 SMs with ~10 edges per thread in sequence.)
 // Runs after ba_point_linearize_kernel (reads the chi2 it stored) and before the dense-edge kernel adds to H atomically.
+constexpr int kPoseChunks = 8;
 __global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, StaticEdges E, StatePair SP, const Lm* __restrict__ lm,
                                                                const int* __restrict__ pose_ptr, const int* __restrict__ pose_edges,
-                                                               const int* __restrict__ free_pose, const int* __restrict__ off_pose, int nd, ChiPair chi,
-                                                               double* __restrict__ H, double* __restrict__ b) {
+                                                               const int* __restrict__ free_pose, ChiPair chi, double* __restrict__ partial) {
     __shared__ double scratch[8 * 27], red[27];
     if (lm->done || !lm->need_lin) return;
     const State S = SP.s[lm->cur];
     const double* __restrict__ chi_e = chi.e[lm->cur];
-    const int ip = free_pose[blockIdx.x], op = off_pose[ip];
+    const int fp = blockIdx.x / kPoseChunks, ch = blockIdx.x % kPoseChunks;
+    const int ip = free_pose[fp];
     double v[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) v[k] = 0;
     double R[9];
     quat_to_rot(S.pq + 4 * ip, R);
     const double t[3] = {S.pt[3 * ip], S.pt[3 * ip + 1], S.pt[3 * ip + 2]};
-    for (int q = pose_ptr[ip] + threadIdx.x; q < pose_ptr[ip + 1]; q += 256) {
+    const int lo = pose_ptr[ip], n = pose_ptr[ip + 1] - lo, per = (n + kPoseChunks - 1) / kPoseChunks;
+    const int q0 = lo + ch * per, q1 = min(lo + n, q0 + per);
+    for (int q = q0 + threadIdx.x; q < q1; q += 256) {
         const int e = pose_edges[q];
         if (E.level[e]) continue;
         double er[3], Xc[3], Ji[9], Jj[18], rho0, rho1;
@@ -338,13 +356,22 @@ __global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, St
         }
     }
     block_reduce_fixed<27>(v, scratch, red);
-    if (threadIdx.x < 21) {
+    if (threadIdx.x < 27) partial[(size_t)blockIdx.x * 27 + threadIdx.x] = red[threadIdx.x];
+}
+__global__ void ba_pose_reduce_kernel(const double* __restrict__ partial, const int* __restrict__ free_pose, const int* __restrict__ off_pose, int nd,
+                                      const Lm* __restrict__ lm, double* __restrict__ H, double* __restrict__ b) {
+    if (lm->done || !lm->need_lin) return;
+    const int fp = blockIdx.x, k = threadIdx.x;   // 32 threads, 27 active
+    if (k >= 27) return;
+    double sum = 0;
+    for (int c = 0; c < kPoseChunks; ++c) sum += partial[((size_t)fp * kPoseChunks + c) * 27 + k];
+    const int op = off_pose[free_pose[fp]];
+    if (k < 21) {
         int r = 0, acc = 0;
-        while (acc + r + 1 <= (int)threadIdx.x) { acc += r + 1; ++r; }
-        const int c = threadIdx.x - acc;
-        H[(size_t)(op + r) * nd + op + c] = red[threadIdx.x];
-    } else if (threadIdx.x < 27) {
-        b[op + threadIdx.x - 21] = red[threadIdx.x];
+        while (acc + r + 1 <= k) { acc += r + 1; ++r; }
+        H[(size_t)(op + r) * nd + op + (k - acc)] = sum;
+    } else {
+        b[op + k - 21] = sum;
     }
 }
 
@@ -606,14 +633,10 @@ __global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* 
 // dense updates: poses (exp), bone lengths (+), motions (right multiply), joints (+); also the dense
 // part of the gain-ratio denominator sum x (lambda x + b)
 struct DenseSizes { int n_poses, n_dists, n_motions, n_joints; };
-__global__ void ba_dense_update_kernel(DenseSizes N, DynOff off, const double* __restrict__ x, const double* __restrict__ b, const Lm* __restrict__ lm,
-                                       int nd, StatePair SP, Scalars* sc) {
-    if (lm->done) return;
-    const double lambda = lm->lambda;
-    const State cur = SP.s[lm->cur], trs = SP.s[lm->cur ^ 1];
+__device__ __forceinline__ void dense_update_block(DenseSizes N, DynOff off, const double* __restrict__ x, const double* __restrict__ b, double lambda, int nd,
+                                                   const State& cur, const State& trs, int i, Scalars* sc) {
     double* pq = const_cast<double*>(trs.pq); double* pt = const_cast<double*>(trs.pt); double* D = const_cast<double*>(trs.D);
     double* mq = const_cast<double*>(trs.mq); double* mt = const_cast<double*>(trs.mt); double* J = const_cast<double*>(trs.J);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N.n_poses) {
         const int o = off.pose[i];
         if (o >= 0) pose_oplus(cur.pq + 4 * i, cur.pt + 3 * i, x + o, pq + 4 * i, pt + 3 * i);
@@ -634,34 +657,48 @@ __global__ void ba_dense_update_kernel(DenseSizes N, DynOff off, const double* _
     block_sum_to(s, &sc->scale);
 }
 
-// xl = Dinv (bl - W^T xp) per point (edges of a point are contiguous), trial point, landmark part of the scale
+// xl = Dinv (bl - W^T xp) per point (edges of a point are contiguous), trial point, landmark part of the scale; kPtLanes lanes per
+// point share its edges, the three partial sums meet by shuffles
 __global__ void __launch_bounds__(kBaThreads) ba_backsub_kernel(const int* __restrict__ point_ptr, const int* __restrict__ e_pose,
                                                                const uint8_t* __restrict__ e_level, const int* __restrict__ off_pose,
                                                                const uint8_t* __restrict__ act_point, int np, const double* __restrict__ W,
                                                                const double* __restrict__ Dinv, const double* __restrict__ bl,
-                                                               const double* __restrict__ x, const Lm* __restrict__ lm, StatePair SP, Scalars* sc) {
+                                                               const double* __restrict__ x, const Lm* __restrict__ lm, StatePair SP, Scalars* sc,
+                                                               DenseSizes N, DynOff off, const double* __restrict__ b, int nd, int dense_blocks) {
     if (lm->done) return;
     const double lambda = lm->lambda;
+    if ((int)blockIdx.x < dense_blocks) {   // SparseOptimizer::update for the dense vertices rides in the first blocks of the same launch
+        dense_update_block(N, off, x, b, lambda, nd, SP.s[lm->cur], SP.s[lm->cur ^ 1], blockIdx.x * blockDim.x + threadIdx.x, sc);
+        return;
+    }
     const double* __restrict__ Xcur = SP.s[lm->cur].X;
     double* __restrict__ Xtrial = const_cast<double*>(SP.s[lm->cur ^ 1].X);
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = ((blockIdx.x - dense_blocks) * blockDim.x + threadIdx.x) / kPtLanes, sub = threadIdx.x % kPtLanes;
     double s = 0;
-    if (l < np) {
-        if (!act_point[l]) {
+    const bool active = l < np && act_point[l];
+    double c[3] = {0, 0, 0};
+    if (active) {
+        for (int e = point_ptr[l] + sub; e < point_ptr[l + 1]; e += kPtLanes) {
+            if (e_level[e]) continue;
+            const int o = off_pose[e_pose[e]];
+            if (o < 0) continue;
+            const double* We = W + 18 * (size_t)e;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double xi = x[o + i];
+                c[0] -= We[i * 3] * xi; c[1] -= We[i * 3 + 1] * xi; c[2] -= We[i * 3 + 2] * xi;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 1; o < kPtLanes; o <<= 1) c[k] += __shfl_xor_sync(0xFFFFFFFFu, c[k], o);
+    if (l < np && sub == 0) {
+        if (!active) {
             for (int k = 0; k < 3; ++k) Xtrial[3 * (size_t)l + k] = Xcur[3 * (size_t)l + k];
         } else {
-            double c[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
-            for (int e = point_ptr[l]; e < point_ptr[l + 1]; ++e) {
-                if (e_level[e]) continue;
-                const int o = off_pose[e_pose[e]];
-                if (o < 0) continue;
-                const double* We = W + 18 * (size_t)e;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const double xi = x[o + i];
-                    c[0] -= We[i * 3] * xi; c[1] -= We[i * 3 + 1] * xi; c[2] -= We[i * 3 + 2] * xi;
-                }
-            }
+            for (int k = 0; k < 3; ++k) c[k] += bl[3 * (size_t)l + k];
             const double* Di = Dinv + 9 * (size_t)l;
             for (int i = 0; i < 3; ++i) {
                 const double xl = Di[i * 3] * c[0] + Di[i * 3 + 1] * c[1] + Di[i * 3 + 2] * c[2];
@@ -1014,7 +1051,7 @@ struct adb_ba {
     DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, off_pose, act_point, pose_ptr, pose_edges, free_pose;
     DevBuf j_pose, j_joint, j_obs, j_info, j_level, r_i, r_j, r_d, r_info, r_level, m_p1, m_p2, m_m, m_dt, m_info, m_level;
     DevBuf off_joint, off_dist, off_motion;
-    DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work, lm, trace;
+    DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work, lm, trace, pose_partial;
     Lm* h_lm = nullptr;          // pinned mirror of the device LM controller
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
@@ -1196,6 +1233,7 @@ struct Ctx {
         if ((r = s->flag.ensure(std::max<size_t>(std::max(E, n_dyn()), 1))) != ADB_OK) return r;
         if ((r = s->scal.ensure(sizeof(Scalars))) != ADB_OK) return r;
         if ((r = s->lm.ensure(sizeof(Lm))) != ADB_OK) return r;
+        if ((r = s->pose_partial.ensure(std::max<size_t>(P->n_poses, 1) * kPoseChunks * 27 * sizeof(double))) != ADB_OK) return r;
         if ((r = s->trace.ensure(std::max<size_t>(R->trace ? R->trace_cap : 0, 1) * ADB_BA_TRACE_COLS * sizeof(double))) != ADB_OK) return r;
         ADB_CUDA(cudaMemsetAsync(s->scal.p, 0, sizeof(Scalars), st));
         lvl_e.assign(E, 0); lvl_j.assign(P->n_joint_edges, 0); lvl_r.assign(P->n_rigid_edges, 0); lvl_m.assign(P->n_motion_edges, 0);
@@ -1287,7 +1325,7 @@ struct Ctx {
     // One LM step, enqueued without knowing what the previous one decided: buildSystem at the accepted state (skipped on the
     // device unless the step opens an outer iteration), one trial with the controller's lambda into the other state buffers,
     // evaluation, decision.  Every kernel returns at once when the round is already over.
-    adb_status enqueue_step(bool robust) {
+    adb_status enqueue_step(bool robust, bool first_step) {
         cudaStream_t st = s->stream;
         const int E = P->n_edges, NP = P->n_points;
         Scalars* sc = s->scal.as<Scalars>();
@@ -1299,15 +1337,18 @@ struct Ctx {
         ba_clear_kernel<<<std::min(grid_for(std::max<size_t>(n2, 1), 256), 592), 256, 0, st>>>(s->H.as<double>(), n2, s->b.as<double>(), nd, lm, sc);
         ++s->launches;
         if (NP > 0) {
-            ba_point_linearize_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->point_ptr.as<int>(), NP,
+            ba_point_linearize_kernel<<<grid_for((size_t)NP * kPtLanes, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->point_ptr.as<int>(), NP,
                                                                                       s->off_pose.as<int>(), s->Hll.as<double>(), s->bl.as<double>(),
                                                                                       s->W.as<double>(), CH, sc);
             ++s->launches;
         }
         if (E > 0 && !free_pose.empty()) {
-            ba_pose_linearize_kernel<<<(int)free_pose.size(), 256, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
-                                                                           s->free_pose.as<int>(), s->off_pose.as<int>(), nd, CH, s->H.as<double>(), s->b.as<double>());
-            ++s->launches;
+            const int nfp = (int)free_pose.size();
+            ba_pose_linearize_kernel<<<nfp * kPoseChunks, 256, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
+                                                                       s->free_pose.as<int>(), CH, s->pose_partial.as<double>());
+            ba_pose_reduce_kernel<<<nfp, 32, 0, st>>>(s->pose_partial.as<double>(), s->free_pose.as<int>(), s->off_pose.as<int>(), nd, lm, s->H.as<double>(),
+                                                      s->b.as<double>());
+            s->launches += 2;
         }
         if (n_dyn() > 0) {
             ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), SP, lm, doff(), nd, s->H.as<double>(),
@@ -1316,9 +1357,12 @@ struct Ctx {
         }
         tm.end();
         tm.begin(4);
-        ba_maxdiag_kernel<<<grid_for(nd + NP, 256), 256, 0, st>>>(s->H.as<double>(), nd, s->Hll.as<double>(), s->act_point.as<uint8_t>(), NP, lm, sc);
+        if (first_step) {   // computeLambdaInit: only the first iteration of a round reads it
+            ba_maxdiag_kernel<<<grid_for(nd + NP, 256), 256, 0, st>>>(s->H.as<double>(), nd, s->Hll.as<double>(), s->act_point.as<uint8_t>(), NP, lm, sc);
+            ++s->launches;
+        }
         lm_iter_kernel<<<1, 1, 0, st>>>(lm, sc);
-        s->launches += 2;
+        ++s->launches;
         tm.end();
         tm.begin(1);
         if (nd > 0) {
@@ -1352,13 +1396,11 @@ struct Ctx {
         {
             const DenseSizes N{P->n_poses, P->n_dists, P->n_motions, P->n_joints};
             const int nthreads = std::max(nd, P->n_poses + P->n_dists + P->n_motions + P->n_joints);
-            ba_dense_update_kernel<<<grid_for(nthreads, 128), 128, 0, st>>>(N, doff(), s->bs.as<double>(), s->b.as<double>(), lm, nd, SP, sc);
-            ++s->launches;
-        }
-        if (NP > 0) {
-            ba_backsub_kernel<<<grid_for(NP, kBaThreads), kBaThreads, 0, st>>>(s->point_ptr.as<int>(), s->e_pose.as<int>(), s->e_level.as<uint8_t>(),
-                                                                              s->off_pose.as<int>(), s->act_point.as<uint8_t>(), NP, s->W.as<double>(),
-                                                                              s->Dinv.as<double>(), s->bl.as<double>(), s->bs.as<double>(), lm, SP, sc);
+            const int dense_blocks = grid_for(nthreads, kBaThreads), point_blocks = NP > 0 ? grid_for((size_t)NP * kPtLanes, kBaThreads) : 0;
+            ba_backsub_kernel<<<dense_blocks + point_blocks, kBaThreads, 0, st>>>(s->point_ptr.as<int>(), s->e_pose.as<int>(), s->e_level.as<uint8_t>(),
+                                                                                 s->off_pose.as<int>(), s->act_point.as<uint8_t>(), NP, s->W.as<double>(),
+                                                                                 s->Dinv.as<double>(), s->bl.as<double>(), s->bs.as<double>(), lm, SP, sc, N, doff(),
+                                                                                 s->b.as<double>(), nd, dense_blocks);
             ++s->launches;
         }
         if (E > 0) {
@@ -1390,8 +1432,9 @@ struct Ctx {
         *s->h_lm = hl;
         ADB_CUDA(cudaMemcpyAsync(s->lm.p, s->h_lm, sizeof(Lm), cudaMemcpyHostToDevice, s->stream));
         int batch = iterations;
+        bool first_step = true;
         while (!hl.done && !stopped()) {
-            for (int k = 0; k < batch; ++k) if ((r = enqueue_step(robust)) != ADB_OK) return r;
+            for (int k = 0; k < batch; ++k) { if ((r = enqueue_step(robust, first_step)) != ADB_OK) return r; first_step = false; }
             if ((r = read_lm()) != ADB_OK) return r;
             batch = 2;
         }
@@ -1510,7 +1553,7 @@ adb_status adb_ba_destroy(adb_ba_t s) {
                      &s->act_point, &s->j_pose, &s->j_joint, &s->j_obs, &s->j_info, &s->j_level, &s->r_i, &s->r_j, &s->r_d, &s->r_info, &s->r_level,
                      &s->m_p1, &s->m_p2, &s->m_m, &s->m_dt, &s->m_info, &s->m_level, &s->off_joint, &s->off_dist, &s->off_motion, &s->H, &s->b,
                      &s->Sm, &s->bs, &s->Hll, &s->bl, &s->W, &s->Dinv, &s->db, &s->chi_e[0], &s->chi_e[1], &s->chi_j[0], &s->chi_j[1], &s->chi_r[0],
-                     &s->chi_r[1], &s->chi_m[0], &s->chi_m[1], &s->flag, &s->scal, &s->work, &s->lm, &s->trace};
+                     &s->chi_r[1], &s->chi_m[0], &s->chi_m[1], &s->flag, &s->scal, &s->work, &s->lm, &s->trace, &s->pose_partial};
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     if (s->h_lm) cudaFreeHost(s->h_lm);
