@@ -559,7 +559,7 @@ __global__ void ba_dinv_kernel(const double* __restrict__ Hll, const double* __r
 // chunks of <= 128 pairs; one warp sums a chunk in registers, reduces with shuffles and issues 36 (+6) atomics per chunk
 // instead of 36 per pair.
 constexpr int kSchurChunk = 128;
-__global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* __restrict__ pairs, const int2* __restrict__ chunks, int nchunks,
+__global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* __restrict__ pairs, const int2* __restrict__ chunks, const int* __restrict__ totals,
                                                                    const int* __restrict__ e_pose, const int* __restrict__ e_point,
                                                                    const int* __restrict__ off_pose, const double* __restrict__ W,
                                                                    const double* __restrict__ Dinv, const double* __restrict__ db, int nd,
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kBaThreads) ba_schur_block_kernel(const int2* 
     if (lm->done) return;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (kBaThreads / 32) + (threadIdx.x >> 5);
-    if (c >= nchunks) return;
+    if (c >= totals[1]) return;   // the grid is sized for the host's upper bound of the chunk count
     const int2 ch = chunks[c];
     double acc[36], rhs[6];
 #pragma unroll
@@ -745,6 +745,75 @@ __global__ void ba_gate_kernel(StaticEdges E, StatePair SP, const Lm* __restrict
     const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + S.pt[3 * ip + 2];
     const bool stereo = E.obs[3 * e + 2] >= 0;
     flag[e] = (chi_e[e] > (stereo ? gate_stereo : gate_mono)) || !(z > 0);
+}
+
+// ---- Schur pair list on the device (was a host counting sort: 1.9 ms per layout at config 4, twice per solve).
+// Pairs (e1, e2) of one point with block(e1) >= block(e2), grouped by destination block key = b1 (b1 + 1) / 2 + b2 and cut into
+// chunks of <= kSchurChunk pairs.  Order inside a key is the order of the atomic cursors; the chunk sums meet in L2 atomics anyway.
+__device__ __forceinline__ int pose_block_of(int e, const int* __restrict__ e_pose, const uint8_t* __restrict__ e_level, const int* __restrict__ off_pose) {
+    if (e_level[e]) return -1;
+    const int o = off_pose[e_pose[e]];
+    return o < 0 ? -1 : o / 6;
+}
+// pass 0: count per key; pass 1: place (cursor starts at the key's first slot)
+__global__ void __launch_bounds__(128) schur_pairs_kernel(const int* __restrict__ point_ptr, int np, const int* __restrict__ e_pose,
+                                                         const uint8_t* __restrict__ e_level, const int* __restrict__ off_pose, int* __restrict__ counter,
+                                                         int2* __restrict__ pairs, int pass) {
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) / kPtLanes, sub = threadIdx.x % kPtLanes;
+    if (l >= np) return;
+    const int lo = point_ptr[l], hi = point_ptr[l + 1];
+    for (int a = lo + sub; a < hi; a += kPtLanes) {
+        const int b1 = pose_block_of(a, e_pose, e_level, off_pose);
+        if (b1 < 0) continue;
+        const int base = b1 * (b1 + 1) / 2;
+        for (int c = lo; c < hi; ++c) {
+            const int b2 = pose_block_of(c, e_pose, e_level, off_pose);
+            if (b2 < 0 || b2 > b1) continue;
+            const int pos = atomicAdd(counter + base + b2, 1);
+            if (pass == 1) pairs[pos] = make_int2(a, c);
+        }
+    }
+}
+// one block: exclusive scans of the counts (-> cursor = first slot of every key) and of the chunk counts; writes the chunk list
+__global__ void __launch_bounds__(1024) schur_scan_kernel(const int* __restrict__ count, int nkeys, int* __restrict__ cursor, int2* __restrict__ chunks,
+                                                         int* __restrict__ totals /* [0] pairs, [1] chunks */) {
+    __shared__ int warp_p[32], warp_c[32];
+    __shared__ int carry_p, carry_c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry_p = 0; carry_c = 0; }
+    __syncthreads();
+    for (int base = 0; base < nkeys; base += 1024) {
+        const int k = base + tid;
+        const int cnt = k < nkeys ? count[k] : 0, nch = (cnt + kSchurChunk - 1) / kSchurChunk;
+        int ip = cnt, ic = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tp = __shfl_up_sync(0xFFFFFFFFu, ip, o), tc = __shfl_up_sync(0xFFFFFFFFu, ic, o);
+            if (lane >= o) { ip += tp; ic += tc; }
+        }
+        if (lane == 31) { warp_p[warp] = ip; warp_c[warp] = ic; }
+        __syncthreads();
+        if (warp == 0) {
+            int wp = warp_p[lane], wc = warp_c[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tp = __shfl_up_sync(0xFFFFFFFFu, wp, o), tc = __shfl_up_sync(0xFFFFFFFFu, wc, o);
+                if (lane >= o) { wp += tp; wc += tc; }
+            }
+            warp_p[lane] = wp; warp_c[lane] = wc;
+        }
+        __syncthreads();
+        const int start_p = carry_p + (warp ? warp_p[warp - 1] : 0) + ip - cnt;
+        const int start_c = carry_c + (warp ? warp_c[warp - 1] : 0) + ic - nch;
+        if (k < nkeys) {
+            cursor[k] = start_p;
+            for (int i = 0; i < nch; ++i) chunks[start_c + i] = make_int2(start_p + i * kSchurChunk, min(kSchurChunk, cnt - i * kSchurChunk));
+        }
+        __syncthreads();
+        if (tid == 1023) { carry_p += warp_p[31]; carry_c += warp_c[31]; }
+        __syncthreads();
+    }
+    if (tid == 0) { totals[0] = carry_p; totals[1] = carry_c; }
 }
 
 // H = 0, b = 0 and the buildSystem sums, only when the step opens an outer iteration
@@ -1048,11 +1117,13 @@ struct adb_ba {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // device buffers
     DevBuf pq[2], pt[2], X[2], Jt[2], Dd[2], mq[2], mt[2];                         // double-buffered state
-    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, off_pose, act_point, pose_ptr, pose_edges, free_pose;
+    DevBuf e_pose, e_point, e_obs, e_info, e_level, point_ptr, pairs, chunks, pair_count, pair_cursor, pair_totals, off_pose, act_point, pose_ptr, pose_edges, free_pose;
     DevBuf j_pose, j_joint, j_obs, j_info, j_level, r_i, r_j, r_d, r_info, r_level, m_p1, m_p2, m_m, m_dt, m_info, m_level;
     DevBuf off_joint, off_dist, off_motion;
     DevBuf H, b, Sm, bs, Hll, bl, W, Dinv, db, chi_e[2], chi_j[2], chi_r[2], chi_m[2], flag, scal, work, lm, trace, pose_partial;
     Lm* h_lm = nullptr;          // pinned mirror of the device LM controller
+    char* h_stage = nullptr;     // pinned staging arena for the sorted edge arrays (true asynchronous H2D at PCIe rate)
+    size_t h_stage_cap = 0;
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
     std::vector<cudaEvent_t> tev;   // per-stage timing events
@@ -1097,12 +1168,13 @@ struct Ctx {
     Timer tm;
     // host-side derived structure
     std::vector<int> perm;            // sorted position -> original edge index
-    std::vector<int> se_pose, se_point, ptr;
-    std::vector<double> se_obs, se_info;
+    int *se_pose = nullptr, *se_point = nullptr, *ptr = nullptr;   // in the pinned arena of the handle
+    double *se_obs = nullptr, *se_info = nullptr;
     std::vector<uint8_t> lvl_e, lvl_j, lvl_r, lvl_m, act_point;
     std::vector<int> off_pose, off_dist, off_motion, off_joint;
-    std::vector<int2> pairs, chunks;
-    std::vector<int> pose_ptr, pose_edges, free_pose;
+    int chunks_ub = 0;     // upper bound of the Schur chunk count (the exact one lives on the device)
+    int *pose_ptr = nullptr, *pose_edges = nullptr;
+    std::vector<int> free_pose;
     int nd = 0, ld = 32;
     Lm hl = {};            // host copy of the controller as of the last read-back
     Ctx(adb_ba* s_, adb_ba_problem* p, const adb_ba_options* o, adb_ba_result* r, volatile const uint8_t* st) : s(s_), P(p), O(o), R(r), stop(st), tm(s_) {}
@@ -1167,7 +1239,23 @@ struct Ctx {
             const adb_status v = validate_dynamic();
             if (v != ADB_OK) return v;
         }
-        ptr.assign(NP + 1, 0);
+        {   // carve the sorted arrays out of the pinned arena (grown on demand, kept across solves)
+            const size_t need = ((size_t)E * (4 + 4 + 24 + 8 + 4) + (size_t)(NP + 1 + P->n_poses + 1) * 4 + 256 + 7 * 16);
+            if (need > s->h_stage_cap) {
+                ADB_CUDA(cudaStreamSynchronize(s->stream));
+                if (s->h_stage) cudaFreeHost(s->h_stage);
+                s->h_stage = nullptr; s->h_stage_cap = 0;
+                ADB_CUDA(cudaMallocHost(&s->h_stage, need + need / 4));
+                s->h_stage_cap = need + need / 4;
+            }
+            char* cursor = s->h_stage;
+            auto take = [&](size_t bytes) { char* r0 = cursor; cursor += (bytes + 15) & ~(size_t)15; return r0; };
+            se_obs = reinterpret_cast<double*>(take((size_t)E * 24)); se_info = reinterpret_cast<double*>(take((size_t)E * 8));
+            se_pose = reinterpret_cast<int*>(take((size_t)E * 4)); se_point = reinterpret_cast<int*>(take((size_t)E * 4));
+            pose_edges = reinterpret_cast<int*>(take((size_t)E * 4));
+            ptr = reinterpret_cast<int*>(take((size_t)(NP + 1) * 4)); pose_ptr = reinterpret_cast<int*>(take((size_t)(P->n_poses + 1) * 4));
+        }
+        std::fill(ptr, ptr + NP + 1, 0);
         for (int e = 0; e < E; ++e) {
             ADB_CHECK(P->edge_point[e] >= 0 && P->edge_point[e] < NP && P->edge_pose[e] >= 0 && P->edge_pose[e] < P->n_poses, ADB_ERR_INVALID,
                       "edge %d references pose %d / point %d out of range", e, P->edge_pose[e], P->edge_point[e]);
@@ -1176,30 +1264,28 @@ struct Ctx {
         for (int l = 0; l < NP; ++l) ptr[l + 1] += ptr[l];
         perm.assign(E, 0);
         {
-            std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+            std::vector<int> fill(ptr, ptr + NP);
             for (int e = 0; e < E; ++e) perm[fill[P->edge_point[e]]++] = e;
         }
-        se_pose.resize(E); se_point.resize(E); se_obs.resize((size_t)3 * E); se_info.resize(E);
         for (int k = 0; k < E; ++k) {
             const int e = perm[k];
             se_pose[k] = P->edge_pose[e]; se_point[k] = P->edge_point[e]; se_info[k] = P->edge_info[e];
             for (int c = 0; c < 3; ++c) se_obs[(size_t)3 * k + c] = P->edge_obs[(size_t)3 * e + c];
         }
         // CSR of the (sorted) edges by pose, for the atomic-free pose-block accumulation
-        pose_ptr.assign(P->n_poses + 1, 0);
+        std::fill(pose_ptr, pose_ptr + P->n_poses + 1, 0);
         for (int k = 0; k < E; ++k) pose_ptr[se_pose[k] + 1]++;
         for (int i = 0; i < P->n_poses; ++i) pose_ptr[i + 1] += pose_ptr[i];
-        pose_edges.assign(E, 0);
         {
-            std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
+            std::vector<int> fill(pose_ptr, pose_ptr + P->n_poses);
             for (int k = 0; k < E; ++k) pose_edges[fill[se_pose[k]]++] = k;
         }
         cudaStream_t st = s->stream;
         adb_status r;
 #define UP(buf, ptr_, n) if ((r = upload(buf, ptr_, (size_t)(n), st)) != ADB_OK) return r
-        UP(s->e_pose, se_pose.data(), E); UP(s->e_point, se_point.data(), E); UP(s->e_obs, se_obs.data(), 3 * (size_t)E);
-        UP(s->e_info, se_info.data(), E); UP(s->point_ptr, ptr.data(), NP + 1);
-        UP(s->pose_ptr, pose_ptr.data(), P->n_poses + 1); UP(s->pose_edges, pose_edges.data(), E);
+        UP(s->e_pose, se_pose, E); UP(s->e_point, se_point, E); UP(s->e_obs, se_obs, 3 * (size_t)E);
+        UP(s->e_info, se_info, E); UP(s->point_ptr, ptr, NP + 1);
+        UP(s->pose_ptr, pose_ptr, P->n_poses + 1); UP(s->pose_edges, pose_edges, E);
         UP(s->pq[0], P->pose_q, 4 * (size_t)P->n_poses); UP(s->pt[0], P->pose_t, 3 * (size_t)P->n_poses); UP(s->X[0], P->points, 3 * (size_t)NP);
         UP(s->Jt[0], P->joints, 3 * (size_t)P->n_joints); UP(s->Dd[0], P->dists, P->n_dists);
         UP(s->mq[0], P->motion_q, 4 * (size_t)P->n_motions); UP(s->mt[0], P->motion_t, 3 * (size_t)P->n_motions);
@@ -1258,51 +1344,38 @@ struct Ctx {
         nd = o;
         free_pose.clear();
         for (int i = 0; i < P->n_poses; ++i) if (off_pose[i] >= 0) free_pose.push_back(i);
-        // Schur pair list: (e1, e2) of one point with block(e1) >= block(e2), counting-sorted by destination block
-        // (pose offsets are multiples of 6 and come first in the dense layout), then cut into chunks
-        {
-            int nblk = 0;
-            for (int i = 0; i < P->n_poses; ++i) if (off_pose[i] >= 0) nblk = std::max(nblk, off_pose[i] / 6 + 1);
-            const size_t nkeys = (size_t)nblk * (nblk + 1) / 2;
-            std::vector<int> cnt(nkeys + 1, 0);
-            std::vector<int> blk(E);   // pose block of every (sorted) edge, -1 = inactive or fixed pose
-            for (int e = 0; e < E; ++e) blk[e] = (lvl_e[e] || off_pose[se_pose[e]] < 0) ? -1 : off_pose[se_pose[e]] / 6;
-            for (int pass = 0; pass < 2; ++pass) {
-                if (pass == 1) {
-                    size_t run = 0;
-                    for (size_t k = 0; k <= nkeys; ++k) { const size_t c = cnt[k]; cnt[k] = (int)run; run += c; }
-                    pairs.resize(run);
-                }
-                for (int l = 0; l < NP; ++l) {
-                    const int lo = ptr[l], hi = ptr[l + 1];
-                    for (int a = lo; a < hi; ++a) {
-                        const int b1 = blk[a];
-                        if (b1 < 0) continue;
-                        const size_t base = (size_t)b1 * (b1 + 1) / 2;
-                        for (int c = lo; c < hi; ++c) {
-                            const int b2 = blk[c];
-                            if (b2 < 0 || b2 > b1) continue;
-                            if (pass == 0) cnt[base + b2]++;
-                            else pairs[cnt[base + b2]++] = make_int2(a, c);
-                        }
-                    }
-                }
-            }
-            // after the fill pass cnt[k] = end of block k
-            chunks.clear();
-            size_t begin = 0;
-            for (size_t k = 0; k < nkeys; ++k) {
-                const size_t end = cnt[k];
-                for (size_t b = begin; b < end; b += kSchurChunk) chunks.push_back(make_int2((int)b, (int)std::min<size_t>(kSchurChunk, end - b)));
-                begin = end;
-            }
-        }
         cudaStream_t st = s->stream;
         adb_status r;
 #define UP(buf, v) if ((r = upload(buf, (v).data(), (v).size(), st)) != ADB_OK) return r
         UP(s->e_level, lvl_e); UP(s->j_level, lvl_j); UP(s->r_level, lvl_r); UP(s->m_level, lvl_m); UP(s->act_point, act_point);
-        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->pairs, pairs); UP(s->chunks, chunks); UP(s->free_pose, free_pose);
+        UP(s->off_pose, off_pose); UP(s->off_dist, off_dist); UP(s->off_motion, off_motion); UP(s->off_joint, off_joint); UP(s->free_pose, free_pose);
 #undef UP
+        // Schur pair list on the device (schur_pairs_kernel / schur_scan_kernel); the host only needs upper bounds for the buffers and the grid
+        {
+            int nblk = 0;
+            for (int i = 0; i < P->n_poses; ++i) if (off_pose[i] >= 0) nblk = std::max(nblk, off_pose[i] / 6 + 1);
+            const int nkeys = nblk * (nblk + 1) / 2;
+            size_t pairs_ub = 0;
+            for (int l = 0; l < NP; ++l) { const size_t n = (size_t)(ptr[l + 1] - ptr[l]); pairs_ub += n * (n + 1) / 2; }
+            chunks_ub = nkeys > 0 && E > 0 ? (int)(pairs_ub / kSchurChunk) + nkeys : 0;
+            if ((r = s->pair_totals.ensure(2 * sizeof(int))) != ADB_OK) return r;
+            ADB_CUDA(cudaMemsetAsync(s->pair_totals.p, 0, 2 * sizeof(int), st));
+            if (chunks_ub > 0) {
+                if ((r = s->pairs.ensure(std::max<size_t>(pairs_ub, 1) * sizeof(int2))) != ADB_OK) return r;
+                if ((r = s->chunks.ensure((size_t)chunks_ub * sizeof(int2))) != ADB_OK) return r;
+                if ((r = s->pair_count.ensure((size_t)nkeys * sizeof(int))) != ADB_OK) return r;
+                if ((r = s->pair_cursor.ensure((size_t)nkeys * sizeof(int))) != ADB_OK) return r;
+                ADB_CUDA(cudaMemsetAsync(s->pair_count.p, 0, (size_t)nkeys * sizeof(int), st));
+                const int grid = grid_for((size_t)NP * kPtLanes, 128);
+                schur_pairs_kernel<<<grid, 128, 0, st>>>(s->point_ptr.as<int>(), NP, s->e_pose.as<int>(), s->e_level.as<uint8_t>(), s->off_pose.as<int>(),
+                                                         s->pair_count.as<int>(), nullptr, 0);
+                schur_scan_kernel<<<1, 1024, 0, st>>>(s->pair_count.as<int>(), nkeys, s->pair_cursor.as<int>(), s->chunks.as<int2>(), s->pair_totals.as<int>());
+                schur_pairs_kernel<<<grid, 128, 0, st>>>(s->point_ptr.as<int>(), NP, s->e_pose.as<int>(), s->e_level.as<uint8_t>(), s->off_pose.as<int>(),
+                                                         s->pair_cursor.as<int>(), s->pairs.as<int2>(), 1);
+                s->launches += 3;
+                ADB_CUDA(cudaGetLastError());
+            }
+        }
         const size_t n2 = std::max<size_t>((size_t)nd * nd, 1);
         ld = chol_nblk(std::max(nd, 1)) * kCholNB;
         if ((r = s->H.ensure(n2 * 8)) != ADB_OK) return r;
@@ -1374,9 +1447,8 @@ struct Ctx {
                                                               s->db.as<double>());
             ++s->launches;
         }
-        if (!chunks.empty()) {
-            const int nch = (int)chunks.size();
-            ba_schur_block_kernel<<<grid_for(nch, kBaThreads / 32), kBaThreads, 0, st>>>(s->pairs.as<int2>(), s->chunks.as<int2>(), nch, s->e_pose.as<int>(),
+        if (chunks_ub > 0) {
+            ba_schur_block_kernel<<<grid_for(chunks_ub, kBaThreads / 32), kBaThreads, 0, st>>>(s->pairs.as<int2>(), s->chunks.as<int2>(), s->pair_totals.as<int>(), s->e_pose.as<int>(),
                                                                                         s->e_point.as<int>(), s->off_pose.as<int>(), s->W.as<double>(),
                                                                                         s->Dinv.as<double>(), s->db.as<double>(), ld, lm, s->Sm.as<double>(),
                                                                                         s->Sm.as<double>() + (size_t)ld * ld);   // rhs row
@@ -1549,7 +1621,7 @@ adb_status adb_ba_destroy(adb_ba_t s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     DevBuf* all[] = {&s->pq[0], &s->pq[1], &s->pt[0], &s->pt[1], &s->X[0], &s->X[1], &s->Jt[0], &s->Jt[1], &s->Dd[0], &s->Dd[1], &s->mq[0], &s->mq[1],
-                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->chunks, &s->pose_ptr, &s->pose_edges, &s->free_pose, &s->off_pose,
+                     &s->mt[0], &s->mt[1], &s->e_pose, &s->e_point, &s->e_obs, &s->e_info, &s->e_level, &s->point_ptr, &s->pairs, &s->chunks, &s->pair_count, &s->pair_cursor, &s->pair_totals, &s->pose_ptr, &s->pose_edges, &s->free_pose, &s->off_pose,
                      &s->act_point, &s->j_pose, &s->j_joint, &s->j_obs, &s->j_info, &s->j_level, &s->r_i, &s->r_j, &s->r_d, &s->r_info, &s->r_level,
                      &s->m_p1, &s->m_p2, &s->m_m, &s->m_dt, &s->m_info, &s->m_level, &s->off_joint, &s->off_dist, &s->off_motion, &s->H, &s->b,
                      &s->Sm, &s->bs, &s->Hll, &s->bl, &s->W, &s->Dinv, &s->db, &s->chi_e[0], &s->chi_e[1], &s->chi_j[0], &s->chi_j[1], &s->chi_r[0],
@@ -1557,6 +1629,7 @@ adb_status adb_ba_destroy(adb_ba_t s) {
     for (DevBuf* b : all) b->release();
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     if (s->h_lm) cudaFreeHost(s->h_lm);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
     cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -1600,6 +1673,7 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
         R->chi2_round[1] = chi;
         if (c.stopped()) R->stopped = 1;
     }
+    auto t4 = now();
     R->lambda_final = c.hl.lambda;
     R->chi2_initial = c.hl.chi2_initial;
     R->trace_len = c.hl.trace_len;
@@ -1616,6 +1690,7 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* P, const adb_ba_options* O, 
     if (R->medge_outlier) for (int e = 0; e < P->n_motion_edges; ++e) R->medge_outlier[e] = fm[e];
     if ((r = c.download_state()) != ADB_OK) return r;
     c.tm.collect();
+    if (timing) fprintf(stderr, "[adb_ba] gates + round 2 %.2f ms, final gates + write-back %.2f ms\n", ms(t3, t4), ms(t4, now()));
     return ADB_OK;
 }
 
