@@ -116,3 +116,11 @@ class PoseBatch:
         s.xw = self.xw.ctypes.data_as(fp); s.obs = self.obs.ctypes.data_as(fp); s.inv_sigma2 = self.inv_sigma2.ctypes.data_as(fp)
         s.outlier = self.outlier.ctypes.data_as(_bp); s.n_inliers = self.n_inliers.ctypes.data_as(_ip)
         self.c = s
+
+
+class LeafIO(C.Structure):
+    """adb_ba_leaf_io (include/airdos_b200.h): inputs / outputs of the leaf-arithmetic pinning hook."""
+    _fields_ = [("n", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
+                ("pose_q", C.c_void_p), ("pose_t", C.c_void_p), ("x", C.c_void_p), ("obs", C.c_void_p), ("pose_update", C.c_void_p),
+                ("joint_a", C.c_void_p), ("joint_b", C.c_void_p), ("bone", C.c_void_p),
+                ("motion_q", C.c_void_p), ("motion_t", C.c_void_p), ("motion_dt", C.c_void_p), ("motion_update", C.c_void_p), ("out", C.c_void_p)]

@@ -112,6 +112,7 @@ SYMBOLS = {
     "adb_ba_stage_ms": (C.c_int, [_vp, _fp]),
     "adb_ba_launch_count": (C.c_int64, [_vp]),
     "adb_pose_optimize": (C.c_int, [_vp, _vp]),
+    "adb_ba_leaf_eval": (C.c_int, [_vp, _vp]),
     "adb_dense_solve": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _ip, _i32, _i32, _fp]),
 }
 

@@ -403,10 +403,20 @@ __device__ inline void add_rhs(double* b, int oa, int da, const double* A, int d
         if (s != 0.0) atomicAdd(b + oa + i, s);
     }
 }
-__device__ inline void motion_error(const State& S, int m, double dt, const double* p1, const double* p2, double* er, double* Rm) {
-    quat_to_rot(S.mq + 4 * m, Rm);
-    const double d[3] = {p2[0] - dt * S.mt[3 * m], p2[1] - dt * S.mt[3 * m + 1], p2[2] - dt * S.mt[3 * m + 2]};
+// LandmarkMotionTernaryEdge::computeError, zero measurement (include/g2o_dyn_slam3d.h:65-76): e = p1 - M^-1 p2, M = (R, dt t)
+__device__ inline void motion_error_qt(const double* mq, const double* mt, double dt, const double* p1, const double* p2, double* er, double* Rm) {
+    quat_to_rot(mq, Rm);
+    const double d[3] = {p2[0] - dt * mt[0], p2[1] - dt * mt[1], p2[2] - dt * mt[2]};
     for (int i = 0; i < 3; ++i) er[i] = p1[i] - (Rm[i] * d[0] + Rm[3 + i] * d[1] + Rm[6 + i] * d[2]);
+}
+__device__ inline void motion_error(const State& S, int m, double dt, const double* p1, const double* p2, double* er, double* Rm) {
+    motion_error_qt(S.mq + 4 * m, S.mt + 3 * m, dt, p1, p2, er, Rm);
+}
+// EdgeRigidBodyDouble::computeError (include/g2o_edge_rigidbody.h:139-149): |a - b| - d; d3 / n return the difference and its norm
+__device__ inline double rigid_error(const double* a, const double* b, double dist, double* d3, double* n) {
+    d3[0] = a[0] - b[0]; d3[1] = a[1] - b[1]; d3[2] = a[2] - b[2];
+    *n = sqrt(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
+    return *n - dist;
 }
 
 // mode 0: linearise into H / b and accumulate chi_cur; mode 1: evaluate only, accumulate chi_trial
@@ -449,10 +459,8 @@ __global__ void __launch_bounds__(kBaThreads) ba_dyn_kernel(Cam C, Opt O, DynEdg
         const int e = t - E.nj;
         if (!E.r_level[e]) {
             const int i1 = E.r_i[e], i2 = E.r_j[e], id = E.r_d[e];
-            const double* a = S.J + 3 * i1; const double* c2 = S.J + 3 * i2;
-            const double d[3] = {a[0] - c2[0], a[1] - c2[1], a[2] - c2[2]};
-            const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            const double er = n - S.D[id];
+            double d[3], n;
+            const double er = rigid_error(S.J + 3 * i1, S.J + 3 * i2, S.D[id], d, &n);
             const double w0 = E.r_info[e];
             const double c = er * (w0 * er);
             chi_r[e] = c;
@@ -906,6 +914,15 @@ __device__ inline void pose_edge_error(const Cam& C, const double* R, const doub
     }
 }
 
+// linearizeOplus of Edge(Stereo)SE3ProjectXYZOnlyPose (types_six_dof_expmap.cpp:300-364): the reference's own reciprocal form
+__device__ inline void pose_edge_jacobian(const Cam& C, const double* Xc, bool stereo, double* J) {
+    const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = C.fx, fy = C.fy, bf = C.bf;
+    J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
+    J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
+    if (stereo) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
+    else { for (int k = 12; k < 18; ++k) J[k] = 0; }
+}
+
 __device__ inline bool chol6_solve(const double* H, double lambda, const double* b, double* x) {
     double L[36];
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) L[i * 6 + j] = H[i * 6 + j] + (i == j ? lambda : 0.0);
@@ -985,11 +1002,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
                     const bool stereo = !(A.obs[3 * (size_t)(a + i) + 2] < 0);
                     double er[3], Xc[3], J[18];
                     pose_edge_error(A.C, R, t, A.xw + 3 * (size_t)(a + i), A.obs + 3 * (size_t)(a + i), stereo, er, Xc);
-                    const double x = Xc[0], y = Xc[1], invz = 1.0 / Xc[2], invz_2 = invz * invz, fx = A.C.fx, fy = A.C.fy, bf = A.C.bf;
-                    J[0] = x * y * invz_2 * fx; J[1] = -(1 + (x * x * invz_2)) * fx; J[2] = y * invz * fx; J[3] = -invz * fx; J[4] = 0; J[5] = x * invz_2 * fx;
-                    J[6] = (1 + y * y * invz_2) * fy; J[7] = -x * y * invz_2 * fy; J[8] = -x * invz * fy; J[9] = 0; J[10] = -invz * fy; J[11] = y * invz_2 * fy;
-                    if (stereo) { J[12] = J[0] - bf * y * invz_2; J[13] = J[1] + bf * x * invz_2; J[14] = J[2]; J[15] = J[3]; J[16] = 0; J[17] = J[5] - bf * invz_2; }
-                    else { for (int k = 12; k < 18; ++k) J[k] = 0; }
+                    pose_edge_jacobian(A.C, Xc, stereo, J);
                     const int dim = stereo ? 3 : 2;
                     const double w0 = (double)A.inv_sigma2[a + i];
                     huber(stereo ? ds : dm, robust, chi[i], &r0, &r1);
@@ -1089,6 +1102,52 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Pinning hook (adb_ba_leaf_eval): the device functions above on arrays of inputs, one thread per item, so that the tests can hold
+// them against values computed by the reference's own sources (tests/golden/ba_leaf_ref.npz).  Output record per item, doubles:
+//   [0,3) stereo error  [3,12) d e / d point  [12,30) d e / d pose      (Edge(Stereo)SE3ProjectXYZ; mono: rows 0-1 of the same at +30)
+//   [30,33) [33,42) [42,60) the same for the monocular edge            [60,63) [63,81) stereo OnlyPose error / Jacobian
+//   [81,84) [84,102) mono OnlyPose   [102,106) [106,109) pose oplus q, t   [109] rigidity error   [110,113) motion error
+//   [113,117) [117,120) motion oplus q, t
+constexpr int kLeafRecord = 120;
+__global__ void ba_leaf_kernel(int n, Cam C, const double* __restrict__ pose_q, const double* __restrict__ pose_t, const double* __restrict__ X,
+                               const double* __restrict__ obs, const double* __restrict__ pose_update, const double* __restrict__ joint_a,
+                               const double* __restrict__ joint_b, const double* __restrict__ bone, const double* __restrict__ motion_q,
+                               const double* __restrict__ motion_t, const double* __restrict__ motion_dt, const double* __restrict__ motion_update,
+                               double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* o = out + (size_t)kLeafRecord * i;
+    double R[9], Xc[3], er[3], Ji[9], Jj[18];
+    quat_to_rot(pose_q + 4 * i, R);
+    const double ob[3] = {obs[3 * i], obs[3 * i + 1], obs[3 * i + 2]};
+    int dim = reproj_error(C, R, pose_t + 3 * i, X + 3 * i, ob, er, Xc);
+    reproj_jacobians(C, R, Xc, dim, Ji, Jj);
+    for (int k = 0; k < 3; ++k) o[k] = er[k];
+    for (int k = 0; k < 9; ++k) o[3 + k] = Ji[k];
+    for (int k = 0; k < 18; ++k) o[12 + k] = Jj[k];
+    const double obm[3] = {ob[0], ob[1], -1.0};
+    dim = reproj_error(C, R, pose_t + 3 * i, X + 3 * i, obm, er, Xc);
+    reproj_jacobians(C, R, Xc, dim, Ji, Jj);
+    for (int k = 0; k < 3; ++k) o[30 + k] = er[k];
+    for (int k = 0; k < 9; ++k) o[33 + k] = Ji[k];
+    for (int k = 0; k < 18; ++k) o[42 + k] = Jj[k];
+    const float xw[3] = {(float)X[3 * i], (float)X[3 * i + 1], (float)X[3 * i + 2]}, of[3] = {(float)ob[0], (float)ob[1], (float)ob[2]};
+    for (int stereo = 1; stereo >= 0; --stereo) {
+        pose_edge_error(C, R, pose_t + 3 * i, xw, of, stereo != 0, er, Xc);
+        pose_edge_jacobian(C, Xc, stereo != 0, Jj);
+        double* p = o + (stereo ? 60 : 81);
+        for (int k = 0; k < 3; ++k) p[k] = er[k];
+        for (int k = 0; k < 18; ++k) p[3 + k] = Jj[k];
+    }
+    pose_oplus(pose_q + 4 * i, pose_t + 3 * i, pose_update + 6 * i, o + 102, o + 106);
+    double d3[3], nrm;
+    o[109] = rigid_error(joint_a + 3 * i, joint_b + 3 * i, bone[i], d3, &nrm);
+    double Rm[9];
+    motion_error_qt(motion_q + 4 * i, motion_t + 3 * i, motion_dt[i], joint_a + 3 * i, joint_b + 3 * i, o + 110, Rm);
+    motion_oplus(motion_q + 4 * i, motion_t + 3 * i, motion_update + 6 * i, o + 113, o + 117);
+}
 
 // ----------------------------------------------------------------------------------------
 struct DevBuf {
@@ -1731,6 +1790,32 @@ adb_status adb_pose_optimize(adb_ba_t s, adb_pose_problem* P) {
     if (n > 0) ADB_CUDA(cudaMemcpyAsync(P->outlier, s->flag.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     ADB_CUDA(cudaMemcpyAsync(P->n_inliers, s->off_pose.p, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
     ADB_CUDA(cudaStreamSynchronize(st));
+    return ADB_OK;
+}
+
+adb_status adb_ba_leaf_eval(adb_ba_t s, const adb_ba_leaf_io* io) {
+    ADB_CHECK(s && io && io->n >= 1 && io->out, ADB_ERR_INVALID, "null argument");
+    ADB_CUDA(cudaSetDevice(s->device));
+    const int n = io->n;
+    const double* src[12] = {io->pose_q, io->pose_t, io->x, io->obs, io->pose_update, io->joint_a, io->joint_b, io->bone, io->motion_q, io->motion_t, io->motion_dt,
+                             io->motion_update};
+    const int width[12] = {4, 3, 3, 3, 6, 3, 3, 1, 4, 3, 1, 6};
+    size_t total = 0;
+    for (int k = 0; k < 12; ++k) { ADB_CHECK(src[k], ADB_ERR_INVALID, "null input array %d", k); total += (size_t)width[k] * n; }
+    adb_status r;
+    if ((r = s->work.ensure((total + (size_t)kLeafRecord * n) * sizeof(double))) != ADB_OK) return r;
+    double* d = s->work.as<double>();
+    const double* dev[12];
+    for (int k = 0; k < 12; ++k) {
+        ADB_CUDA(cudaMemcpyAsync(d, src[k], (size_t)width[k] * n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        dev[k] = d; d += (size_t)width[k] * n;
+    }
+    ba_leaf_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, Cam{io->fx, io->fy, io->cx, io->cy, io->bf}, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7],
+                                                          dev[8], dev[9], dev[10], dev[11], d);
+    ++s->launches;
+    ADB_CUDA(cudaGetLastError());
+    ADB_CUDA(cudaMemcpyAsync(io->out, d, (size_t)kLeafRecord * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    ADB_CUDA(cudaStreamSynchronize(s->stream));
     return ADB_OK;
 }
 

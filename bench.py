@@ -353,11 +353,18 @@ def main():
     if not args.no_ba and rank == 0 and world == 1:   # single-GPU sections (BA stays single-GPU; replicas only)
         try:
             import bench_ba
-            out["ba"] = bench_ba.run(local, steps=max(3, K // 2))
+            out["ba"] = bench_ba.run(local, steps=max(3, K // 2), with_cpu=not args.no_cpu_baseline)
         except ImportError:
             pass
         except Exception as e:   # the headline metric must still print
             out["ba"] = {"error": repr(e)}
+        try:
+            import bench_ba
+            out["ba_dynamic"] = bench_ba.run_dynamic(local, steps=3, with_cpu=not args.no_cpu_baseline)
+        except ImportError:
+            pass
+        except Exception as e:
+            out["ba_dynamic"] = {"error": repr(e)}
     if not args.no_ba and rank == 0 and world == 1:
         try:
             import bench_search

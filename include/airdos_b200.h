@@ -442,6 +442,23 @@ adb_status adb_ba_solve(adb_ba_t s, adb_ba_problem* prob, const adb_ba_options* 
 adb_status adb_ba_stage_ms(adb_ba_t s, float* ms6);
 int64_t adb_ba_launch_count(adb_ba_t s);
 
+/* Pinning hook for the tests: evaluates the device implementations of the reference's LEAF arithmetic on arrays of n inputs --
+ * Edge(Stereo)SE3ProjectXYZ[OnlyPose]::computeError / linearizeOplus (types_six_dof_expmap.cpp:103-364), VertexSE3Expmap::oplusImpl
+ * (types_six_dof_expmap.h:73-76), EdgeRigidBodyDouble::computeError (include/g2o_edge_rigidbody.h:139-149),
+ * LandmarkMotionTernaryEdge::computeError (include/g2o_dyn_slam3d.h:65-76), VertexSE3::oplusImpl (include/g2o_vertex_se3.h:113-122) --
+ * so that they can be compared with tests/golden/ba_leaf_ref.npz (values produced by those reference sources themselves).
+ * All arrays are host memory, doubles; out = n records of ADB_BA_LEAF_RECORD doubles (layout: airdos_b200/csrc/ba.cu, ba_leaf_kernel). */
+#define ADB_BA_LEAF_RECORD 120
+typedef struct adb_ba_leaf_io {
+    int32_t n;
+    double fx, fy, cx, cy, bf;
+    const double* pose_q; const double* pose_t; const double* x; const double* obs; const double* pose_update;   /* [n][4|3|3|3|6] */
+    const double* joint_a; const double* joint_b; const double* bone;                                             /* [n][3|3|1] */
+    const double* motion_q; const double* motion_t; const double* motion_dt; const double* motion_update;         /* [n][4|3|1|6] */
+    double* out;
+} adb_ba_leaf_io;
+adb_status adb_ba_leaf_eval(adb_ba_t s, const adb_ba_leaf_io* io);
+
 /* g2o::LinearSolverDense<MatrixType>::solve (Thirdparty/g2o/g2o/solvers/linear_solver_dense.h:64-113: dense Eigen LDLT of the
  * whole non-marginalised block, `!ldlt.isPositive()` -> false) and LinearSolverEigen::solve (linear_solver_eigen.h:92-115), as
  * adb_ba_solve uses them internally: solves A x = b for a symmetric positive definite A (row-major n x n, only the lower

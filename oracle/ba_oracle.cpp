@@ -139,6 +139,26 @@ void motion_oplus(double* q, double* t, const double* d) {
     for (int i = 0; i < 4; ++i) q[i] /= n;
 }
 
+// EdgeRigidBodyDouble::computeError (include/g2o_edge_rigidbody.h:139-149): |p_from - p_to| - d; `n` returns the norm
+inline double rigid_error(const double* a, const double* c2, double dist, double* d3, double* n) {
+    d3[0] = a[0] - c2[0]; d3[1] = a[1] - c2[1]; d3[2] = a[2] - c2[2];
+    *n = std::sqrt(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
+    return *n - dist;
+}
+// LandmarkMotionTernaryEdge::computeError with zero measurement (include/g2o_dyn_slam3d.h:65-76): e = p1 - M^-1 p2, M = (R, dt * t)
+inline void motion_edge_error(const double* mq, const double* mt, double dt, const double* p1, const double* p2, double* er, double* Rm) {
+    quat_to_rot(mq, Rm);
+    const double d[3] = {p2[0] - dt * mt[0], p2[1] - dt * mt[1], p2[2] - dt * mt[2]};
+    for (int i = 0; i < 3; ++i) er[i] = p1[i] - (Rm[i] * d[0] + Rm[3 + i] * d[1] + Rm[6 + i] * d[2]);   // R^T d
+}
+// its linearizeOplus (g2o_dyn_slam3d.h:78-101), first call on a fresh edge: I, -R^T, (dt I | 0)   (D.6)
+inline void motion_edge_jacobians(const double* Rm, double dt, double* J1, double* J2, double* Jm) {
+    for (int i = 0; i < 9; ++i) J1[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J2[i * 3 + j] = -Rm[j * 3 + i];
+    std::memset(Jm, 0, 18 * sizeof(double));
+    Jm[0] = dt; Jm[7] = dt; Jm[14] = dt;
+}
+
 struct Huber { double delta, dsqr; };
 inline void robustify(const Huber& h, bool robust, double e2, double* rho0, double* rho1) {
     if (!robust || e2 <= h.dsqr) { *rho0 = e2; *rho1 = 1.0; }
@@ -316,9 +336,8 @@ struct Solver {
         }
         for (int e = 0; e < P.n_rigid_edges; ++e) {
             if (lvl_r[e]) continue;
-            const double* a = &J[3 * P.redge_i[e]]; const double* c2 = &J[3 * P.redge_j[e]];
-            const double dx = a[0] - c2[0], dy = a[1] - c2[1], dz = a[2] - c2[2];
-            const double er = std::sqrt(dx * dx + dy * dy + dz * dz) - D[P.redge_dist[e]];
+            double d3[3], nrm;
+            const double er = rigid_error(&J[3 * P.redge_i[e]], &J[3 * P.redge_j[e]], D[P.redge_dist[e]], d3, &nrm);
             const double c = er * (P.redge_info[e] * er);
             chi_r[e] = c;
             robustify(huber(O.huber_rigid), robust, c, &r0, &r1);
@@ -340,11 +359,7 @@ struct Solver {
     // e = p1 - M^-1 p2, M = (R, dt * t)   (include/g2o_dyn_slam3d.h:65-76)
     void motion_error(int e, double* er, double* Rm) const {
         const int m = P.medge_motion[e];
-        quat_to_rot(&mq[4 * m], Rm);
-        const double dt = P.medge_dt[e];
-        const double* p1 = &J[3 * P.medge_p1[e]]; const double* p2 = &J[3 * P.medge_p2[e]];
-        const double d[3] = {p2[0] - dt * mt[3 * m], p2[1] - dt * mt[3 * m + 1], p2[2] - dt * mt[3 * m + 2]};
-        for (int i = 0; i < 3; ++i) er[i] = p1[i] - (Rm[i] * d[0] + Rm[3 + i] * d[1] + Rm[6 + i] * d[2]);   // R^T d
+        motion_edge_error(&mq[4 * m], &mt[3 * m], P.medge_dt[e], &J[3 * P.medge_p1[e]], &J[3 * P.medge_p2[e]], er, Rm);
     }
 
     // BlockSolver::buildSystem at the current state (errors of the current state are recomputed inside)
@@ -408,10 +423,8 @@ struct Solver {
         for (int e = 0; e < P.n_rigid_edges; ++e) {
             if (lvl_r[e]) continue;
             const int i1 = P.redge_i[e], i2 = P.redge_j[e], id = P.redge_dist[e];
-            const double* a = &J[3 * i1]; const double* c2 = &J[3 * i2];
-            const double d[3] = {a[0] - c2[0], a[1] - c2[1], a[2] - c2[2]};
-            const double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            const double er = n - D[id];
+            double d[3], n;
+            const double er = rigid_error(&J[3 * i1], &J[3 * i2], D[id], d, &n);
             const double w0 = P.redge_info[e];
             const double c = er * (w0 * er);
             robustify(huber(O.huber_rigid), robust, c, &r0, &r1);
@@ -436,13 +449,8 @@ struct Solver {
             robustify(huber(O.huber_motion), robust, c, &r0, &r1);
             const double w = r1 * w0;
             const double wr[3] = {-w0 * er[0] * r1, -w0 * er[1] * r1, -w0 * er[2] * r1};
-            const double J1[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            double J2[9];
-            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) J2[i * 3 + j] = -Rm[j * 3 + i];   // -R^T
-            double Jm[18];
-            std::memset(Jm, 0, sizeof(Jm));
-            const double dt = P.medge_dt[e];
-            Jm[0] = dt; Jm[7] = dt; Jm[14] = dt;                                                  // D.6
+            double J1[9], J2[9], Jm[18];
+            motion_edge_jacobians(Rm, P.medge_dt[e], J1, J2, Jm);                                  // I, -R^T, (dt I | 0): D.6
             const int offs[3] = {off_joint[P.medge_p1[e]], off_joint[P.medge_p2[e]], off_motion[P.medge_motion[e]]};
             const int dims[3] = {3, 3, 6}; const double* Js[3] = {J1, J2, Jm};
             for (int u = 0; u < 3; ++u) {
@@ -685,6 +693,12 @@ int ba_oracle_reproj(const adb_ba_problem* P, const double* q, const double* t, 
     reproj_jacobians(*P, R, Xc, dim, Ji, Jj);
     return dim;
 }
+double ba_oracle_rigid_error(const double* a, const double* c2, double dist) { double d3[3], n; return rigid_error(a, c2, dist, d3, &n); }
+void ba_oracle_motion_edge(const double* p1, const double* p2, const double* mq, const double* mt, double dt, double* er, double* J1, double* J2, double* Jm) {
+    double Rm[9];
+    motion_edge_error(mq, mt, dt, p1, p2, er, Rm);
+    motion_edge_jacobians(Rm, dt, J1, J2, Jm);
+}
 void ba_oracle_pose_oplus(double* q, double* t, const double* d) { pose_oplus(q, t, d); }
 void ba_oracle_motion_oplus(double* q, double* t, const double* d) { motion_oplus(q, t, d); }
 
@@ -856,4 +870,18 @@ int pose_optimize_one(const adb_pose_problem& P, int f) {
 extern "C" int ba_oracle_pose_optimize(adb_pose_problem* P) {
     for (int f = 0; f < P->n_frames; ++f) P->n_inliers[f] = pose_optimize_one(*P, f);
     return ADB_OK;
+}
+
+// Edge(Stereo)SE3ProjectXYZOnlyPose: error and d e / d pose of one correspondence (pinning tests); cam5 = fx fy cx cy bf
+extern "C" void ba_oracle_pose_edge(const double* q, const double* t, const double* Xw, const double* obs, int stereo, const double* cam5, double* er,
+                                    double* J18) {
+    adb_pose_problem P{};
+    P.fx = cam5[0]; P.fy = cam5[1]; P.cx = cam5[2]; P.cy = cam5[3]; P.bf = cam5[4];
+    PoseEdge e{};
+    for (int i = 0; i < 3; ++i) { e.X[i] = Xw[i]; e.obs[i] = obs[i]; }
+    e.stereo = stereo != 0;
+    double R[9], Xc[3];
+    quat_to_rot(q, R);
+    pose_edge_error(P, R, t, e, er, Xc);
+    pose_edge_jac(P, Xc, e.stereo, J18);
 }
