@@ -132,22 +132,85 @@ __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __
     }
 }
 
-// cv::erode(mask, ones(10,10)), anchor (5,5), outside = 255.  oracle/orb_oracle.cpp:70-92.  Parity-only path.
-__global__ void erode10_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, size_t sfstride,
-                               uint8_t* __restrict__ dst, int dpitch, size_t dfstride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= w) return;
-    const uint8_t* s = src + (size_t)f * sfstride;
-    int m = 255;
-    for (int dy = -5; dy <= 4; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= h) continue;
-        for (int dx = -5; dx <= 4; ++dx) {
-            const int xx = x + dx;
-            if (xx >= 0 && xx < w) m = min(m, (int)s[(size_t)yy * spitch + xx]);
+// cv::erode(mask, ones(10,10)), anchor (5,5), outside = 255 (src/ORBextractor.cc:1130-1131; oracle/orb_oracle.cpp:70-92): the
+// reference passes a mask with EVERY frame (src/Frame.cc:551-571, System.IsMask), so this is on the measured path.  Separable:
+// one CTA stages a (16 + 9) x (128 + 9) tile in shared memory, takes the 10-wide row minimum in place, then the 10-high column
+// minimum -- each mask byte is read from HBM once instead of 100 times.
+constexpr int kErTW = 128, kErTH = 32, kErR0 = 5, kErSpan = 10, kErRun = 16;
+// running minimum over 10 of a run of kErRun + 9 values held in registers, by doubling: 2, 4, 8, then 8 + 2 = 10 -> 5 min per output
+__device__ __forceinline__ void min10_run(const int (&a)[kErRun + kErSpan - 1], int (&o)[kErRun]) {
+    int m2[kErRun + 8], m4[kErRun + 6], m8[kErRun + 2];
+#pragma unroll
+    for (int i = 0; i < kErRun + 8; ++i) m2[i] = min(a[i], a[i + 1]);
+#pragma unroll
+    for (int i = 0; i < kErRun + 6; ++i) m4[i] = min(m2[i], m2[i + 2]);
+#pragma unroll
+    for (int i = 0; i < kErRun + 2; ++i) m8[i] = min(m4[i], m4[i + 4]);
+#pragma unroll
+    for (int i = 0; i < kErRun; ++i) o[i] = min(m8[i], m2[i + 8]);
+}
+__global__ void __launch_bounds__(256) erode10_tile_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, size_t sfstride,
+                                                           uint8_t* __restrict__ dst, int dpitch, size_t dfstride, int f0) {
+    // input tile: rows y0 - 5 .. y0 + 36, columns x0 - 8 .. x0 + 135 (word aligned: x0 is a multiple of 128), 36 words per row
+    constexpr int IH = kErTH + kErSpan - 1, IWW = (kErTW + 16) / 4, OFF = 8 - kErR0;
+    __shared__ uint32_t tile[IH][IWW + 1];
+    __shared__ uint32_t rmin[IH][kErTW / 4 + 1];
+    __shared__ uint32_t outt[kErTH][kErTW / 4 + 1];
+    const int x0 = blockIdx.x * kErTW, y0 = blockIdx.y * kErTH, f = blockIdx.z;
+    const uint8_t* sp = src + (size_t)f * sfstride;
+    const bool aligned = (((uintptr_t)sp | (uintptr_t)spitch) & 3) == 0;
+    for (int i = threadIdx.x; i < IWW * IH; i += 256) {
+        const int r = i / IWW, cw = i - r * IWW, yy = y0 - kErR0 + r, xx = x0 - 8 + 4 * cw;
+        uint32_t v = 0xFFFFFFFFu;                                   // outside the image = 255 (cv::erode's border value)
+        if (yy >= 0 && yy < h) {
+            const uint8_t* rowp = sp + (size_t)yy * spitch;
+            if (aligned && xx >= 0 && xx + 3 < w) v = *reinterpret_cast<const uint32_t*>(rowp + xx);
+            else {
+                v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v |= (uint32_t)((xx + k >= 0 && xx + k < w) ? rowp[xx + k] : (uint8_t)255) << (8 * k);
+            }
         }
+        tile[r][cw] = v;
     }
-    dst[(size_t)f * dfstride + (size_t)y * dpitch + x] = (uint8_t)m;
+    __syncthreads();
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(&tile[0][0]);
+    uint8_t* rb = reinterpret_cast<uint8_t*>(&rmin[0][0]);
+    // rows: a thread owns a run of 16 outputs of one row (8 runs per row, 41 rows = 328 runs)
+    for (int i = threadIdx.x; i < IH * (kErTW / kErRun); i += 256) {
+        const int r = i / (kErTW / kErRun), c0 = (i - r * (kErTW / kErRun)) * kErRun;
+        int a[kErRun + kErSpan - 1], o[kErRun];
+        const uint8_t* tr = tb + (size_t)r * (IWW + 1) * 4 + OFF + c0;
+#pragma unroll
+        for (int k = 0; k < kErRun + kErSpan - 1; ++k) a[k] = tr[k];
+        min10_run(a, o);
+#pragma unroll
+        for (int k = 0; k < kErRun; k += 4)
+            rmin[r][(c0 + k) >> 2] = (uint32_t)o[k] | ((uint32_t)o[k + 1] << 8) | ((uint32_t)o[k + 2] << 16) | ((uint32_t)o[k + 3] << 24);
+    }
+    __syncthreads();
+    // columns: a thread owns a run of 16 outputs of one column (2 runs per column, 128 columns = 256 runs = one per thread)
+    {
+        const int c = threadIdx.x % kErTW, r0 = (threadIdx.x / kErTW) * kErRun;
+        int a[kErRun + kErSpan - 1], o[kErRun];
+#pragma unroll
+        for (int k = 0; k < kErRun + kErSpan - 1; ++k) a[k] = rb[(size_t)(r0 + k) * (kErTW / 4 + 1) * 4 + c];
+        min10_run(a, o);
+        uint8_t* ob = reinterpret_cast<uint8_t*>(&outt[0][0]);
+#pragma unroll
+        for (int k = 0; k < kErRun; ++k) ob[(size_t)(r0 + k) * (kErTW / 4 + 1) * 4 + c] = (uint8_t)o[k];
+    }
+    __syncthreads();
+    // store: 32 x 32 words per tile, coalesced; byte-wise only at a ragged right edge or an unaligned destination
+    uint8_t* dp = dst + (size_t)(f0 + f) * dfstride;
+    const bool daligned = (((uintptr_t)dp | (uintptr_t)dpitch) & 3) == 0;
+    for (int i = threadIdx.x; i < kErTH * (kErTW / 4); i += 256) {
+        const int r = i / (kErTW / 4), cw = i - r * (kErTW / 4), y = y0 + r, x = x0 + 4 * cw;
+        if (y >= h || x >= w) continue;
+        const uint32_t v = outt[r][cw];
+        if (daligned && x + 3 < w) *reinterpret_cast<uint32_t*>(dp + (size_t)y * dpitch + x) = v;
+        else for (int k = 0; k < 4 && x + k < w; ++k) dp[(size_t)y * dpitch + x + k] = (uint8_t)(v >> (8 * k));
+    }
 }
 
 // =========================================================================================
@@ -940,6 +1003,7 @@ static void free_handle(adb_orb* h) {
     for (auto& l : h->lv) {
         cudaFree(l.img); cudaFree(l.mask); cudaFree(l.xtab); cudaFree(l.ytab);
     }
+    cudaFree(h->mask_stage);
     if (h->copy_stream) {
         cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->d2h_stream);
         for (auto& e : h->cev) if (e) cudaEventDestroy(e);
@@ -1092,6 +1156,10 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
 static adb_status ensure_mask_buffers(adb_orb* h) {
     for (auto& l : h->lv)
         if (!l.mask) ADB_CUDA(cudaMalloc(&l.mask, (size_t)h->cfg.max_batch * l.d.mframe_stride));
+    if (!h->mask_stage) {   // host-buffer calls: the caller's masks land here before the erosion (kept for the life of the handle)
+        const size_t p0 = (size_t)((h->cfg.width + 15) & ~15);
+        ADB_CUDA(cudaMalloc(&h->mask_stage, (size_t)h->cfg.max_batch * p0 * h->cfg.height));
+    }
     return ADB_OK;
 }
 
@@ -1309,12 +1377,14 @@ adb_status adb_orb_sync(adb_orb_t h) {
     return check_device_status(h);
 }
 
-static adb_status prepare_masks(adb_orb* h, int n, const uint8_t* d_masks, size_t mfstride, int mpitch) {
+// level-0 mask of frames [f0, f0 + n) = erode(caller's mask); d_masks points at the first of the n masks
+static adb_status prepare_masks(adb_orb* h, int f0, int n, const uint8_t* d_masks, size_t mfstride, int mpitch) {
     adb_status s = ensure_mask_buffers(h);
     if (s != ADB_OK) return s;
     const LevelDev& d = h->lv[0].d;
-    dim3 grid((d.w + 127) / 128, d.h, n);
-    erode10_kernel<<<grid, 128, 0, h->stream>>>(d_masks, d.w, d.h, mpitch, mfstride, h->lv[0].mask, d.mpitch, d.mframe_stride);
+    dim3 grid((d.w + kErTW - 1) / kErTW, (d.h + kErTH - 1) / kErTH, n);
+    erode10_tile_kernel<<<grid, 256, 0, h->stream>>>(d_masks, d.w, d.h, mpitch, mfstride, h->lv[0].mask, d.mpitch, d.mframe_stride, f0);
+    ++h->launches;
     ADB_CUDA(cudaGetLastError());
     return ADB_OK;
 }
@@ -1333,7 +1403,7 @@ adb_status adb_orb_extract_batch_device(adb_orb_t h, int32_t n, const uint8_t* d
         l0 = h->lv[0].img; l0p = p0; l0s = (size_t)p0 * hh;
     }
     if (d_masks) {
-        adb_status s = prepare_masks(h, n, d_masks, mfstride, mpitch);
+        adb_status s = prepare_masks(h, 0, n, d_masks, mfstride, mpitch);
         if (s != ADB_OK) return s;
     }
     return run_pipeline(h, n, l0, l0p, l0s, d_masks != nullptr);
@@ -1379,10 +1449,10 @@ adb_status adb_orb_download(adb_orb_t h, int32_t first, int32_t n, adb_keypoint*
 // Large host batches run as a pipeline of chunks: the host-to-device copy of chunk c + 1 (copy stream), the kernels of chunk c
 // (handle stream) and the device-to-host copy of chunk c - 1's results (download stream) overlap, so the call costs about
 // max(upload, compute, download) instead of their sum.  Results are identical: chunking only changes the launch ranges.
-constexpr int kChunks = 4, kMinChunkedFrames = 32;
+constexpr int kChunks = 8, kMinChunkedFrames = 32;
 
-static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images, size_t fstride, int w, int hh, int pitch,
-                                        adb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images, size_t fstride, int w, int hh, int pitch, const uint8_t* masks,
+                                        size_t mfstride, int mpitch, adb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
     const int p0 = (w + 15) & ~15;
     const size_t dfs = (size_t)p0 * hh;
     if (!h->copy_stream) {
@@ -1390,10 +1460,12 @@ static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images
         ADB_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2 * kChunks + 1; ++i) ADB_CUDA(cudaEventCreateWithFlags(&h->cev[i], cudaEventDisableTiming));
     }
+    adb_status s = ADB_OK;
+    if (masks && (s = ensure_mask_buffers(h)) != ADB_OK) return s;
     // the upload must not overtake kernels of an earlier asynchronous call that still read the staging buffer
     ADB_CUDA(cudaEventRecord(h->cev[2 * kChunks], h->stream));
     ADB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->cev[2 * kChunks], 0));
-    adb_status s = run_pipeline(h, n, h->lv[0].img, p0, dfs, false, /*launch=*/false);
+    s = run_pipeline(h, n, h->lv[0].img, p0, dfs, masks != nullptr, /*launch=*/false);
     if (s != ADB_OK) return s;
     const int per = (n + kChunks - 1) / kChunks;
     int c = 0;
@@ -1401,9 +1473,14 @@ static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images
         const int nc = std::min(per, n - f0);
         s = copy_frames(h->lv[0].img + f0 * dfs, p0, dfs, images + f0 * fstride, pitch, fstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
         if (s != ADB_OK) return s;
+        if (masks) {   // the chunk's masks ride on the same copy stream; erosion + mask pyramid run with the chunk's kernels
+            s = copy_frames(h->mask_stage + f0 * dfs, p0, dfs, masks + f0 * mfstride, mpitch, mfstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
+            if (s != ADB_OK) return s;
+        }
         ADB_CUDA(cudaEventRecord(h->cev[c], h->copy_stream));
         ADB_CUDA(cudaStreamWaitEvent(h->stream, h->cev[c], 0));
-        s = run_range(h, f0, nc, false);
+        if (masks && (s = prepare_masks(h, f0, nc, h->mask_stage + f0 * dfs, dfs, p0)) != ADB_OK) return s;
+        s = run_range(h, f0, nc, masks != nullptr);
         if (s != ADB_OK) return s;
         ADB_CUDA(cudaEventRecord(h->cev[kChunks + c], h->stream));
         ADB_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->cev[kChunks + c], 0));
@@ -1433,19 +1510,16 @@ adb_status adb_orb_extract_batch(adb_orb_t h, int32_t n, const uint8_t* images, 
     ADB_CHECK(w == h->cfg.width && hh == h->cfg.height && pitch >= w, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
     ADB_CUDA(cudaSetDevice(h->cfg.device));
     static const bool no_chunks = getenv("ADB_NO_CHUNKS") != nullptr;   // measurement switch
-    if (n >= kMinChunkedFrames && !masks && !h->profiling && !no_chunks)
-        return extract_batch_chunked(h, n, images, fstride, w, hh, pitch, kps, desc, cap, counts);
+    if (n >= kMinChunkedFrames && !h->profiling && !no_chunks)
+        return extract_batch_chunked(h, n, images, fstride, w, hh, pitch, masks, mfstride, mpitch, kps, desc, cap, counts);
     const int p0 = (w + 15) & ~15;
     adb_status s = copy_frames(h->lv[0].img, p0, (size_t)p0 * hh, images, pitch, fstride, w, hh, n, cudaMemcpyHostToDevice, h->stream);
     if (s != ADB_OK) return s;
     if (masks) {
         s = ensure_mask_buffers(h);
         if (s != ADB_OK) return s;
-        uint8_t* stage = nullptr;
-        ADB_CUDA(cudaMallocAsync((void**)&stage, (size_t)n * p0 * hh, h->stream));
-        s = copy_frames(stage, p0, (size_t)p0 * hh, masks, mpitch, mfstride, w, hh, n, cudaMemcpyHostToDevice, h->stream);
-        if (s == ADB_OK) s = prepare_masks(h, n, stage, (size_t)p0 * hh, p0);
-        cudaFreeAsync(stage, h->stream);
+        s = copy_frames(h->mask_stage, p0, (size_t)p0 * hh, masks, mpitch, mfstride, w, hh, n, cudaMemcpyHostToDevice, h->stream);
+        if (s == ADB_OK) s = prepare_masks(h, 0, n, h->mask_stage, (size_t)p0 * hh, p0);
         if (s != ADB_OK) return s;
     }
     s = run_pipeline(h, n, h->lv[0].img, p0, (size_t)p0 * hh, masks != nullptr);

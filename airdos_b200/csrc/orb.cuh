@@ -57,11 +57,12 @@ struct adb_orb {
     int qt_maxa = 0;                // quad-tree node capacity
     size_t qt_smem = 0;
     std::vector<adb::LevelHost> lv;
+    uint8_t* mask_stage = nullptr;  // [max_batch][h][pitch0] caller's masks of a host-buffer call, before the erosion
     std::vector<float> sigma2, inv_sigma2;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // chunked host-buffer calls: upload / download streams
-    cudaEvent_t cev[9] = {};                                   // [0..3] chunk uploaded, [4..7] chunk computed, [8] entry fence
+    cudaEvent_t cev[17] = {};                                  // [0..7] chunk uploaded, [8..15] chunk computed, [16] entry fence
     adb::LevelDev* d_levels = nullptr;
     uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col
     int8_t* d_pattern = nullptr;        // [16][32][2] rBRIEF points, lane-major

@@ -98,6 +98,25 @@ def make_mask(seed: int, width: int = 640, height: int = 480, n_rect: int = 3) -
     return m
 
 
+def make_human_mask(seed: int, width: int = 640, height: int = 480, n_people: int = 2) -> np.ndarray:
+    """Segmentation-shaped extractor mask as AirDOS feeds it (src/Frame.cc:551-571, System.IsMask: 1 in the shipped
+    Examples/Stereo/config/tartanair.yaml): 255 = static scene, 0 = pixels of a detected person.  A person is a head disc, a
+    torso ellipse and two leg strips, 80-220 px tall, anywhere in the lower two thirds of the image (TartanAir-Shibuya street
+    scenes); 2-10 % of the image ends up masked."""
+    rng = np.random.default_rng(seed)
+    m = np.full((height, width), 255, np.uint8)
+    yy, xx = np.mgrid[0:height, 0:width]
+    for _ in range(n_people):
+        hgt = float(rng.uniform(80, 220)); cx = float(rng.uniform(40, width - 40)); top = float(rng.uniform(height * 0.15, height - hgt * 0.6))
+        head_r = 0.08 * hgt
+        m[(xx - cx) ** 2 + (yy - (top + head_r)) ** 2 <= head_r ** 2] = 0
+        m[((xx - cx) / (0.17 * hgt)) ** 2 + ((yy - (top + 0.38 * hgt)) / (0.25 * hgt)) ** 2 <= 1.0] = 0
+        for side in (-1, 1):
+            lx = cx + side * 0.08 * hgt
+            m[(np.abs(xx - lx) <= 0.055 * hgt) & (yy >= top + 0.55 * hgt) & (yy <= top + hgt)] = 0
+    return m
+
+
 # ------------------------------------------------------------------------------------------
 # Bundle-adjustment windows (SURVEY.md appendix E; BASELINE.json configs[3] / configs[4])
 ORB_QUOTA_2000 = np.array([434, 362, 302, 251, 209, 175, 145, 122], np.float64)

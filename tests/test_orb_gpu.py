@@ -62,6 +62,33 @@ def test_cuda_matches_oracle_batch(adb, oracle_mod, w, h, nf, ini, mn, masked):
     ex.close()
 
 
+def test_chunked_masked_host_batch_equals_single_calls(adb, oracle_mod):
+    """A host batch of >= 32 frames runs as a chunk pipeline (upload / kernels / download overlapped), with the masks
+    (the reference passes one with every frame: src/Frame.cc:551-571) uploaded, eroded and resized chunk by chunk.  The result
+    must equal one call per frame, and the oracle on a sample."""
+    from airdos_b200 import synth
+    F, w, h = 40, 640, 480
+    base = [synth.make_stereo_pair(50 + f, w, h)[f % 2] for f in range(5)]
+    bmask = [synth.make_mask(60 + f, w, h, 3) for f in range(5)]
+    imgs = np.stack([base[f % 5] for f in range(F)]); masks = np.stack([bmask[(f * 3) % 5] for f in range(F)])
+    ex = adb.ORBextractor(2000, 1.2, 8, 12, 7, w, h, max_batch=F)
+    kps, desc, cnt = ex.extract_batch(imgs, masks)
+    one = adb.ORBextractor(2000, 1.2, 8, 12, 7, w, h, max_batch=1)
+    for f in (0, 9, 10, 19, 20, 31, 39):       # both sides of every chunk boundary (40 frames / 8 chunks = 5 per chunk)
+        k1, d1 = one(imgs[f], masks[f])
+        assert k1.tobytes() == kps[f, :cnt[f]].tobytes() and (d1 == desc[f, :cnt[f]]).all(), f
+    for f in (7, 23):
+        o = oracle_mod.orb_extract(imgs[f], masks[f], 2000, 1.2, 8, 12, 7)
+        assert _same(kps[f, :cnt[f]], desc[f, :cnt[f]], o), f
+    # and the unmasked chunk pipeline still agrees with the masked one where the mask keeps everything
+    full = np.full_like(masks, 255)
+    ka, da, ca = ex.extract_batch(imgs, full)
+    ka, da, ca = ka.copy(), da.copy(), ca.copy()
+    kb, db, cb = ex.extract_batch(imgs, None)
+    assert (ca == cb).all() and all(ka[f, :ca[f]].tobytes() == kb[f, :cb[f]].tobytes() for f in range(F))
+    ex.close(); one.close()
+
+
 def test_device_resident_path_and_unaligned_input(adb, oracle_mod):
     import torch
     from airdos_b200 import synth
