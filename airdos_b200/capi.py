@@ -28,7 +28,7 @@ class AdbError(RuntimeError):
 
 
 class GatherTargets(C.Structure):
-    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p * 8), ("desc", C.c_void_p * 8), ("counts", C.c_void_p * 8)]
+    _fields_ = [("n", C.c_int32), ("multicast", C.c_int32), ("kps", C.c_void_p * 8), ("desc", C.c_void_p * 8), ("counts", C.c_void_p * 8)]
 
 
 class OrbConfig(C.Structure):

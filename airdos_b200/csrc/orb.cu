@@ -765,6 +765,12 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c) {   // 
     return d;
 }
 
+// one 32-bit store of the fused all-gather: a plain store to a peer-mapped address, or multimem.st to an NVLS multicast address
+__device__ __forceinline__ void gather_store_u32(uint32_t* p, uint32_t v, int multicast) {
+    if (multicast) asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else *p = v;
+}
+
 __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                          const LevelDev* __restrict__ levels, int nlevels,
                                                                          const uint32_t* __restrict__ list, int list_total,
@@ -803,7 +809,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     }
     if (i == 0 && lane == 0) {
         counts[f] = total;
-        for (int g = 0; g < gather.n; ++g) gather.counts[g][f] = total;   // peer-mapped over NVLink
+        for (int g = 0; g < gather.n; ++g) gather_store_u32(reinterpret_cast<uint32_t*>(gather.counts[g] + f), (uint32_t)total, gather.multicast);   // over NVLink
     }
     if (lvl < 0 || i >= cap) return;
     const LevelDev& L = levels[lvl];
@@ -952,18 +958,28 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         byte |= (uint32_t)(t0 < t1) << k;
     }
     desc[((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
-    // fused all-gather: the same 32 B go to every peer's buffer (one NVLink write transaction per peer)
-    for (int g = 0; g < gather.n; ++g) gather.desc[g][((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
-    if (lane == 0) {
-        adb_keypoint kp;
-        kp.x = lvl ? __fmul_rn((float)cx, L.scale) : (float)cx;
-        kp.y = lvl ? __fmul_rn((float)cy, L.scale) : (float)cy;
-        kp.size = (float)L.patch_size;
-        kp.angle = angle;
-        kp.response = (float)resp;
-        kp.octave = lvl;
-        kps[(size_t)f * cap + i] = kp;
-        for (int g = 0; g < gather.n; ++g) gather.kps[g][(size_t)f * cap + i] = kp;
+    adb_keypoint kp;
+    kp.x = lvl ? __fmul_rn((float)cx, L.scale) : (float)cx;
+    kp.y = lvl ? __fmul_rn((float)cy, L.scale) : (float)cy;
+    kp.size = (float)L.patch_size;
+    kp.angle = angle;
+    kp.response = (float)resp;
+    kp.octave = lvl;
+    if (lane == 0) kps[(size_t)f * cap + i] = kp;
+    // fused all-gather: the record also goes to every peer's buffer (or once to the NVLS multicast mapping, which the switch
+    // replicates) as 32-bit words -- lanes 0..7 one word of the descriptor each, lanes 0..5 one word of the key-point: one store
+    // instruction and one NVLink write per destination for each half of the record (multimem.st has no byte form)
+    if (gather.n > 0) {
+        uint32_t w = byte | (__shfl_down_sync(0xFFFFFFFFu, byte, 1) << 8) | (__shfl_down_sync(0xFFFFFFFFu, byte, 2) << 16) |
+                     (__shfl_down_sync(0xFFFFFFFFu, byte, 3) << 24);                // valid in lanes 0, 4, 8, ...
+        w = __shfl_sync(0xFFFFFFFFu, w, (lane & 7) * 4);                           // lanes 0..7: word `lane` of the descriptor
+        const uint32_t kw = lane == 0 ? __float_as_uint(kp.x) : lane == 1 ? __float_as_uint(kp.y) : lane == 2 ? __float_as_uint(kp.size)
+                          : lane == 3 ? __float_as_uint(kp.angle) : lane == 4 ? __float_as_uint(kp.response) : (uint32_t)kp.octave;
+        const size_t rec = (size_t)f * cap + i;
+        for (int g = 0; g < gather.n; ++g) {
+            if (lane < 8) gather_store_u32(reinterpret_cast<uint32_t*>(gather.desc[g]) + rec * 8 + lane, w, gather.multicast);
+            if (lane < 6) gather_store_u32(reinterpret_cast<uint32_t*>(gather.kps[g]) + rec * 6 + lane, kw, gather.multicast);
+        }
     }
 }
 

@@ -68,13 +68,25 @@ class SymmetricGather:
         self.peers = [self.hdl.get_buffer(r, (total,), torch.uint8) for r in range(world)]
         dist.barrier()
 
-    def targets(self):
-        """Pointer triples (one per peer, offset to this rank's slot) for ORBextractor.set_gather."""
+    def multicast_ptr(self) -> int:
+        """NVLS multicast address of the symmetric buffer (0 when the fabric / driver has no multicast support)."""
+        try:
+            return int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        except Exception:   # noqa: BLE001
+            return 0
+
+    def targets(self, prefer_multicast: bool = True):
+        """Pointer triples for ORBextractor.set_gather, offset to this rank's slot: ONE triple on the NVLS multicast mapping when the
+        NVSwitch can replicate stores (a record leaves the GPU once), else one triple per peer.  Returns (kps, desc, counts, multicast)."""
         slot_kp, slot_desc, slot_cnt = self.P * self.cap * 24, self.P * self.cap * 32, self.P * 4
+        mc = self.multicast_ptr() if prefer_multicast else 0
+        if mc:
+            return ([mc + self.rank * slot_kp], [mc + self.kp_bytes + self.rank * slot_desc],
+                    [mc + self.kp_bytes + self.desc_bytes + self.rank * slot_cnt], True)
         kps = [p.data_ptr() + self.rank * slot_kp for p in self.peers]
         desc = [p.data_ptr() + self.kp_bytes + self.rank * slot_desc for p in self.peers]
         cnts = [p.data_ptr() + self.kp_bytes + self.desc_bytes + self.rank * slot_cnt for p in self.peers]
-        return kps, desc, cnts
+        return kps, desc, cnts, False
 
     def kps_view(self):
         return self.buf[:self.kp_bytes].view(self.world, self.P, self.cap, 24)

@@ -125,11 +125,12 @@ class ORBextractor:
     def stream(self) -> int:
         return int(lib().adb_orb_stream(self._h) or 0)
 
-    def set_gather(self, kps_ptrs=(), desc_ptrs=(), counts_ptrs=()):
+    def set_gather(self, kps_ptrs=(), desc_ptrs=(), counts_ptrs=(), multicast: bool = False):
         """Peer-mapped device pointers (one triple per rank, already offset to this rank's slot) that the descriptor
-        kernel writes every record to as well; empty = off."""
+        kernel writes every record to as well; empty = off.  multicast: the single triple is an NVLS multicast mapping."""
         t = capi.GatherTargets()
         t.n = len(kps_ptrs)
+        t.multicast = int(bool(multicast))
         for g, (a, b, c) in enumerate(zip(kps_ptrs, desc_ptrs, counts_ptrs)):
             t.kps[g], t.desc[g], t.counts[g] = int(a), int(b), int(c)
         check(lib().adb_orb_set_gather(self._h, C.byref(t)))

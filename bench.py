@@ -216,8 +216,9 @@ def main():
                     help="stereo pairs per step per GPU (2048 pairs = 4096 frames = 53 ms per step: 20 steps give a timed region above one second)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: 'fused' = descriptor kernel stores records into every peer's buffer over NVLink (symmetric memory); "
+    ap.add_argument("--gather", default="fused", choices=["fused", "fused_p2p", "nccl"],
+                    help="N > 1: 'fused' = descriptor kernel stores records over NVLink into the symmetric buffers of all ranks: once, to the NVLS "
+                         "multicast mapping, when the NVSwitch can replicate (else per peer); 'fused_p2p' = per-peer stores always; "
                          "'nccl' = separate ncclAllGather per step")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -266,11 +267,16 @@ def main():
     gather_bufs = None
     gather_mode = "none"
     symm = None
-    if world > 1 and args.gather == "fused":
+    nvlink_bytes = None
+    if world > 1 and args.gather in ("fused", "fused_p2p"):
         try:
             symm = adist.SymmetricGather(world, rank, P, cap, dev)      # rendezvous + peer-mapped buffers
-            exL.set_gather(*symm.targets())
-            gather_mode = "fused: orient_describe_kernel stores every record to all peers over NVLink (symmetric memory)"
+            tk, td, tc, mc = symm.targets(prefer_multicast=args.gather == "fused")
+            exL.set_gather(tk, td, tc, mc)
+            gather_mode = ("fused: orient_describe_kernel stores every record ONCE to the NVLS multicast mapping of the symmetric buffers (multimem.st; the "
+                           "NVSwitch replicates to all ranks)" if mc else
+                           "fused: orient_describe_kernel stores every record to all peers over NVLink (symmetric memory, one 32-bit-word store per destination)")
+            nvlink_copies = 1 if mc else world - 1
         except Exception as e:   # symmetric memory unavailable: separate collective
             symm = None
             gather_mode = "nccl all_gather_into_tensor (symmetric memory unavailable: %r)" % (e,)
@@ -301,7 +307,17 @@ def main():
         got = symm.counts_view()
         for r in range(world):
             assert torch.equal(got[r], allc[r]), "fused gather: counts of rank %d differ" % r
-        assert torch.equal(symm.desc_view()[rank], descL_t), "fused gather: own descriptors differ"
+        # ... and the PAYLOAD of every rank: key-point records and descriptors as the owner holds them (valid rows), fetched by NCCL
+        alld = [torch.empty_like(descL_t) for _ in range(world)]
+        allk = [torch.empty_like(kpsL_t) for _ in range(world)]
+        dist.all_gather(alld, descL_t.contiguous()); dist.all_gather(allk, kpsL_t.contiguous())
+        rows = torch.arange(cap, device=dev)[None, :]
+        for r in range(world):
+            valid = rows < allc[r][:, None]                               # [P, cap]
+            assert torch.equal(symm.desc_view()[r][valid], alld[r][valid]), "fused gather: descriptors of rank %d differ" % r
+            assert torch.equal(symm.kps_view()[r][valid], allk[r][valid]), "fused gather: key-points of rank %d differ" % r
+        del alld, allk
+        nvlink_bytes = int(cntL_t.sum().item()) * 56 * nvlink_copies
     n_kp_step = int(cntL_t.sum().item() + cntR_t.sum().item())
     launches0 = exL.launch_count() + exR.launch_count()
     sampler = ClockSampler(local)
@@ -473,7 +489,8 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "640x480 stereo stream, 8-level pyramid, 2000 feat/frame, ORB extract L+R + stereo match"
                                + (" + all-gather of descriptor records" if world > 1 else ""),
-                   "pairs_per_step_per_gpu": P, "gather": gather_mode, "frames_per_step": 2 * P * world, "keypoints_per_step": int(nkp.item()),
+                   "pairs_per_step_per_gpu": P, "gather": gather_mode, "gather_payload_checked": symm is not None,
+                   "nvlink_bytes_sent_per_step_per_gpu": nvlink_bytes, "gathered_record_bytes_per_step_per_gpu": (int(cntL_t.sum().item()) * 56 if world > 1 else None), "frames_per_step": 2 * P * world, "keypoints_per_step": int(nkp.item()),
                    "frames_per_s": 2 * P * world / (ms_step * 1e-3), "single_pair_latency_ms_host_api": lat_ms, "cpu_affinity": numa,
                    "l2_policy": "inputs larger than L2: %.0f MB of images + %.0f MB of pyramid per step vs 126 MB L2"
                                 % (2 * P * W * H / 1e6, 2 * P * (PYR_PX - W * H) / 1e6)},

@@ -128,6 +128,8 @@ int64_t adb_orb_launch_count(adb_orb_t h);
 #define ADB_MAX_GATHER 8
 typedef struct adb_gather_targets {
     int32_t n;
+    int32_t multicast;   /* 1: the (single) target is an NVLS multicast mapping of the symmetric buffers (NVSwitch replicates every
+                            store to all ranks, own copy included): written with multimem.st, one copy leaves the GPU instead of n */
     adb_keypoint* kps[ADB_MAX_GATHER];
     uint8_t* desc[ADB_MAX_GATHER];
     int32_t* counts[ADB_MAX_GATHER];
