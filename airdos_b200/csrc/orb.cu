@@ -1014,8 +1014,7 @@ static size_t qt_smem_bytes(int maxa) {
     return (size_t)maxa * (2 * sizeof(short4) + 2 * 4 + 2 * 4 + 4 * 4 + 4 + 4 + 4 + 4 + 4 + 2 + 2 + 1 + 1) + 64;
 }
 
-static void free_handle(adb_orb* h) {
-    if (!h) return;
+static void release_resources(adb_orb* h) {
     for (auto& l : h->lv) {
         cudaFree(l.img); cudaFree(l.mask); cudaFree(l.xtab); cudaFree(l.ytab);
     }
@@ -1035,6 +1034,10 @@ static void free_handle(adb_orb* h) {
     for (auto& e : h->pev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
+}
+static void free_handle(adb_orb* h) {
+    if (!h) return;
+    release_resources(h);
     delete h;
 }
 
@@ -1317,15 +1320,47 @@ adb_status adb_orb_create(const adb_orb_config* cfg, adb_orb_t* out) {
     ADB_CHECK(cfg && out, ADB_ERR_INVALID, "null argument");
     *out = nullptr;
     ADB_CHECK(cfg->nlevels >= 1 && cfg->nlevels <= kMaxLevels, ADB_ERR_INVALID, "nlevels %d out of range 1..%d", cfg->nlevels, kMaxLevels);
-    ADB_CHECK(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && cfg->width >= 1 && cfg->height >= 1 && cfg->max_batch >= 1 &&
+    const bool lazy = cfg->width == 0 && cfg->height == 0;   // ORBextractor's own 5-argument constructor: the image size comes with the first frame
+    ADB_CHECK(cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f && (lazy || (cfg->width >= 1 && cfg->height >= 1)) && cfg->max_batch >= 1 &&
                   cfg->ini_th_fast >= 0 && cfg->min_th_fast >= 0 && cfg->ini_th_fast < 255 && cfg->min_th_fast < 255,
               ADB_ERR_INVALID, "bad extractor configuration");
     adb_status s = select_device(cfg->device);
     if (s != ADB_OK) return s;
     adb_orb* h = new adb_orb();
+    if (lazy) {
+        // scale tables for the getters (GetScaleFactors ... src/ORBextractor.cc:411-430) are size independent; everything else is
+        // provisioned by the first operator() from the size of its image (ensure_size)
+        h->cfg = *cfg; h->nlevels = cfg->nlevels; h->lazy = true;
+        h->capacity = cfg->nfeatures + 16 * cfg->nlevels;   // upper bound of any provisioned capacity (sum of quotas + per-level slack)
+        h->sigma2.resize(cfg->nlevels); h->inv_sigma2.resize(cfg->nlevels); h->lazy_scale.resize(cfg->nlevels);
+        h->lazy_scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+        for (int i = 1; i < cfg->nlevels; ++i) { h->lazy_scale[i] = h->lazy_scale[i - 1] * cfg->scale_factor; h->sigma2[i] = h->lazy_scale[i] * h->lazy_scale[i]; }
+        for (int i = 0; i < cfg->nlevels; ++i) h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+        *out = h;
+        return ADB_OK;
+    }
     s = create_impl(cfg, h);
     if (s != ADB_OK) { free_handle(h); return s; }
     *out = h;
+    return ADB_OK;
+}
+
+// lazy handles: (re)provision for a w x hh image, keeping the handle's identity, gather targets and profiling switch
+static adb_status ensure_size(adb_orb* h, int w, int hh) {
+    if (!h->lazy || (h->provisioned && w == h->cfg.width && hh == h->cfg.height)) return ADB_OK;
+    ADB_CHECK(w >= 1 && hh >= 1, ADB_ERR_INVALID, "bad image size %dx%d", w, hh);
+    ADB_CUDA(cudaSetDevice(h->cfg.device));
+    adb_orb_config cfg = h->cfg;
+    cfg.width = w; cfg.height = hh;
+    adb_orb* fresh = new adb_orb();
+    adb_status s = create_impl(&cfg, fresh);
+    if (s != ADB_OK) { free_handle(fresh); return s; }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    const adb_gather_targets g = h->gather; const bool prof = h->profiling; const long long launches = h->launches;
+    release_resources(h);
+    *h = std::move(*fresh);
+    delete fresh;                 // its resources now belong to *h (no user destructor: only the moved-from vectors are destroyed)
+    h->lazy = true; h->provisioned = true; h->gather = g; h->profiling = prof; h->launches = launches;
     return ADB_OK;
 }
 
@@ -1343,6 +1378,25 @@ int32_t adb_orb_capacity(adb_orb_t h) { return h ? h->capacity : 0; }
 adb_status adb_orb_level_info(adb_orb_t h, int32_t level, int32_t* w, int32_t* h_, int32_t* pitch, float* scale,
                               float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* quota) {
     ADB_CHECK(h && level >= 0 && level < h->nlevels, ADB_ERR_INVALID, "bad level");
+    if (h->lazy && !h->provisioned) {   // before the first frame only the size-independent tables exist
+        if (w) *w = 0;
+        if (h_) *h_ = 0;
+        if (pitch) *pitch = 0;
+        if (scale) *scale = h->lazy_scale[level];
+        if (inv_scale) *inv_scale = 1.0f / h->lazy_scale[level];
+        if (sigma2) *sigma2 = h->sigma2[level];
+        if (inv_sigma2) *inv_sigma2 = h->inv_sigma2[level];
+        if (quota) {   // mnFeaturesPerLevel is size independent (src/ORBextractor.cc:432-445)
+            const int nl = h->nlevels;
+            const float factor = 1.0f / h->cfg.scale_factor;
+            float per = h->cfg.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+            int sum = 0, ql = 0;
+            for (int l = 0; l < nl - 1; ++l) { const int v = round_even_f(per); if (l == level) ql = v; sum += v; per *= factor; }
+            if (level == nl - 1) ql = std::max(h->cfg.nfeatures - sum, 0);
+            *quota = ql;
+        }
+        return ADB_OK;
+    }
     const LevelDev& d = h->lv[level].d;
     if (w) *w = d.w;
     if (h_) *h_ = d.h;
@@ -1409,6 +1463,7 @@ adb_status adb_orb_extract_batch_device(adb_orb_t h, int32_t n, const uint8_t* d
                                         int32_t pitch, const uint8_t* d_masks, size_t mfstride, int32_t mpitch) {
     ADB_CHECK(h && d_images, ADB_ERR_INVALID, "null argument");
     ADB_CHECK(n >= 1 && n <= h->cfg.max_batch, ADB_ERR_INVALID, "n_frames %d exceeds max_batch %d", n, h->cfg.max_batch);
+    { const adb_status es = ensure_size(h, w, hh); if (es != ADB_OK) return es; }
     ADB_CHECK(w == h->cfg.width && hh == h->cfg.height && pitch >= w, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
     ADB_CUDA(cudaSetDevice(h->cfg.device));
     const uint8_t* l0 = d_images; int l0p = pitch; size_t l0s = fstride;
@@ -1523,6 +1578,7 @@ adb_status adb_orb_extract_batch(adb_orb_t h, int32_t n, const uint8_t* images, 
         return ADB_OK;
     }
     ADB_CHECK(n >= 1 && n <= h->cfg.max_batch, ADB_ERR_INVALID, "n_frames %d exceeds max_batch %d", n, h->cfg.max_batch);
+    { const adb_status es = ensure_size(h, w, hh); if (es != ADB_OK) return es; }
     ADB_CHECK(w == h->cfg.width && hh == h->cfg.height && pitch >= w, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
     ADB_CUDA(cudaSetDevice(h->cfg.device));
     static const bool no_chunks = getenv("ADB_NO_CHUNKS") != nullptr;   // measurement switch

@@ -59,6 +59,8 @@ struct adb_orb {
     std::vector<adb::LevelHost> lv;
     uint8_t* mask_stage = nullptr;  // [max_batch][h][pitch0] caller's masks of a host-buffer call, before the erosion
     std::vector<float> sigma2, inv_sigma2;
+    bool lazy = false, provisioned = false;   // created with width = height = 0: provisioned (and re-provisioned) from the image of each call
+    std::vector<float> lazy_scale;            // mvScaleFactor before the first frame
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // chunked host-buffer calls: upload / download streams

@@ -39,7 +39,11 @@ class ORBextractor {
 public:
     enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
 
-    // include/ORBextractor.h:51-52 (+ the image size the device buffers are provisioned for)
+    // include/ORBextractor.h:51-52, the reference's own signature: source compatible with src/Tracking.cc:160-163.  The device
+    // buffers are provisioned by the first operator() from the size of its image (and again if the size ever changes).
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+        : ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, 0, 0, 0) {}
+    // the same with the image size known up front (nothing is allocated inside operator()) and a device ordinal
     ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int width, int height, int device = 0)
         : nfeatures_(nfeatures), scaleFactor_(scaleFactor) {
         adb_orb_config cfg{nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width, height, 1, device};
@@ -47,12 +51,8 @@ public:
         const int nl = adb_orb_levels(h_);
         mvScaleFactor.resize(nl); mvInvScaleFactor.resize(nl); mvLevelSigma2.resize(nl); mvInvLevelSigma2.resize(nl);
         mnFeaturesPerLevel.resize(nl); levelW_.resize(nl); levelH_.resize(nl);
-        for (int l = 0; l < nl; ++l) {
-            int32_t w, h, p, q;
-            adb_orb_level_info(h_, l, &w, &h, &p, &mvScaleFactor[l], &mvInvScaleFactor[l], &mvLevelSigma2[l], &mvInvLevelSigma2[l], &q);
-            mnFeaturesPerLevel[l] = q; levelW_[l] = w; levelH_[l] = h;
-        }
         mvImagePyramid.resize(nl);
+        refresh_levels();
     }
     ~ORBextractor() { adb_orb_destroy(h_); }
     ORBextractor(const ORBextractor&) = delete;
@@ -70,6 +70,7 @@ public:
                                       keypoints.data(), descriptors.data(), cap, &n), "ORBextractor::operator()");
         keypoints.resize(n); descriptors.resize((size_t)n * 32);
         pyramid_valid_ = false;
+        if (levelW_[0] != image.cols || levelH_[0] != image.rows) refresh_levels();   // lazily provisioned handle: level sizes are known now
     }
 
     int GetLevels() const { return (int)mvScaleFactor.size(); }
@@ -99,6 +100,13 @@ public:
     std::vector<int> mnFeaturesPerLevel;
 
 protected:
+    void refresh_levels() {
+        for (int l = 0; l < (int)mvScaleFactor.size(); ++l) {
+            int32_t w, h, p, q;
+            adb_orb_level_info(h_, l, &w, &h, &p, &mvScaleFactor[l], &mvInvScaleFactor[l], &mvLevelSigma2[l], &mvInvLevelSigma2[l], &q);
+            mnFeaturesPerLevel[l] = q; levelW_[l] = w; levelH_[l] = h;
+        }
+    }
     int nfeatures_;
     float scaleFactor_;
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;

@@ -48,11 +48,12 @@ class HostStereo:
 
 
 class ORBextractor:
-    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) bound to one image
-    size and a maximum batch (the device buffers are provisioned once per handle)."""
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) -- the reference's own five arguments
+    (include/ORBextractor.h:51-52): the device buffers are then provisioned by the first call from the size of its image.
+    width / height given up front provision at construction (nothing is allocated inside a call); max_batch frames per call."""
 
     def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int,
-                 width: int = 640, height: int = 480, max_batch: int = 1, device: int = 0):
+                 width: int = 0, height: int = 0, max_batch: int = 1, device: int = 0):
         cfg = capi.OrbConfig(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width, height, max_batch, device)
         self._h = C.c_void_p()
         check(lib().adb_orb_create(C.byref(cfg), C.byref(self._h)))
@@ -109,15 +110,29 @@ class ORBextractor:
             assert masks.shape == images.shape
         check(lib().adb_orb_extract_batch(self._h, f, ptr(images), h * w, w, h, w, ptr(masks), h * w, w,
                                           ptr(kps), ptr(desc), self.capacity, ptr(counts)))
+        self._after_call(w, h)
         return kps, desc, counts
 
+    def _after_call(self, w: int, h: int):
+        """A lazily provisioned handle learns its level sizes with the first image (and again when the size changes)."""
+        if (self.width, self.height) != (w, h):
+            self.width, self.height = w, h
+            self._info = [self._level_info(l) for l in range(self.nlevels)]
+
     def extract_batch_device(self, d_images: int, n_frames: int, frame_stride: int | None = None, pitch: int | None = None,
-                             d_masks: int | None = None):
+                             d_masks: int | None = None, width: int | None = None, height: int | None = None):
         """Device-resident inputs (raw device pointer); asynchronous, results stay in HBM."""
-        pitch = pitch or self.width
-        frame_stride = frame_stride or pitch * self.height
-        check(lib().adb_orb_extract_batch_device(self._h, n_frames, ptr(d_images), frame_stride, self.width, self.height,
+        if width is not None and height is not None:
+            w, h = width, height
+        else:
+            w, h = self.width, self.height
+            if not w or not h:
+                raise ValueError("a lazily provisioned extractor needs width / height with its first device-resident call")
+        pitch = pitch or w
+        frame_stride = frame_stride or pitch * h
+        check(lib().adb_orb_extract_batch_device(self._h, n_frames, ptr(d_images), frame_stride, w, h,
                                                  pitch, ptr(d_masks), frame_stride, pitch))
+        self._after_call(w, h)
 
     def sync(self):
         check(lib().adb_orb_sync(self._h))
@@ -231,6 +246,12 @@ class ORBmatcher:
         [n_q, 4] = mTrackProjX / Y / XR / ViewCos and q_level = mnTrackScaleLevel or -1).  With `fuse` = 1 (+ `inv_level_sigma2`)
         the same inputs run the candidate search of ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:825-975).
         Returns a list of (nmatches, kp_match, q_best_idx, q_best_dist[, q_track, q_level])."""
+        prep = self.prepare_projection(problems)
+        return self.run_prepared_projection(prep)
+
+    def prepare_projection(self, problems: list[dict]):
+        """Fills the adb_proj_search array of a batch once (what the C++ shim does with plain pointer assignments); the batch can then
+        be run any number of times with run_prepared_projection -- the C-ABI call proper, host buffers in and out."""
         from .capi import ProjSearch
         n = len(problems)
         arr = (ProjSearch * n)()
@@ -287,6 +308,10 @@ class ORBmatcher:
             km = np.full(S.n_kp, -1, np.int32); bi = np.full(S.n_q, -1, np.int32); bd = np.full(S.n_q, 256, np.int32)
             S.kp_match, S.q_best_idx, S.q_best_dist = km.ctypes.data, bi.ctypes.data, bd.ctypes.data
             outs.append((km, bi, bd) if track is None else (km, bi, bd, track, level))
+        return arr, n, outs, keep
+
+    def run_prepared_projection(self, prep):
+        arr, n, outs, _keep = prep
         check(lib().adb_search_by_projection(self._m, C.byref(arr), n))
         return [(int(arr[i].n_matches),) + outs[i] for i in range(n)]
 

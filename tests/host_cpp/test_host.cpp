@@ -4,6 +4,7 @@
 // Without a GPU it prints NO_DEVICE and exits 0 (the CPU test only checks that it compiles, links and loads).
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "../../airdos_b200/host/airdos_host.hpp"
@@ -23,11 +24,19 @@ int main(int argc, char** argv) {
     FILE* f = std::fopen(argv[1], "rb");
     if (!f || std::fread(img.data(), 1, img.size(), f) != img.size()) return 3;
     std::fclose(f);
-    ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 12, 7, 640, 480);
+    // the reference's own five-argument constructor (include/ORBextractor.h:51-52, src/Tracking.cc:160-163): provisioned by the first frame
+    ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 12, 7);
+    if (ex.GetLevels() != 8 || ex.GetScaleFactors()[1] != 1.2f || ex.mnFeaturesPerLevel[0] != 217) return 7;   // getters work before the first frame
     std::vector<adb_keypoint> kps;
     std::vector<uint8_t> desc;
     airdos::ImageView im; im.data = img.data(); im.cols = 640; im.rows = 480; im.step = 640;
     ex(im, airdos::ImageView(), kps, desc);
+    {   // the sized constructor gives the same answer
+        ORB_SLAM2::ORBextractor sized(1000, 1.2f, 8, 12, 7, 640, 480);
+        std::vector<adb_keypoint> ks; std::vector<uint8_t> ds;
+        sized(im, airdos::ImageView(), ks, ds);
+        if (ks.size() != kps.size() || ds != desc || std::memcmp(ks.data(), kps.data(), ks.size() * sizeof(adb_keypoint)) != 0) return 8;
+    }
     // empty image: silent return
     std::vector<adb_keypoint> k2; std::vector<uint8_t> d2;
     ex(airdos::ImageView(), airdos::ImageView(), k2, d2);

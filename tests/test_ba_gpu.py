@@ -163,3 +163,21 @@ def test_global_bundle_adjustment_matches_oracle(opt, oracle_mod, robust, its, t
     assert rg.c.chi2_round[0] < rg.c.chi2_initial
     o = ba.global_options(its, robust)
     assert o.robust[0] == int(robust) and o.iterations[1] == 0 and abs(o.huber_mono - np.float32(np.sqrt(5.99))) < 1e-9
+
+
+def test_dumped_dynamic_window_replays(opt, oracle_mod, tmp_path):
+    """SURVEY.md 8(f)-3: a window written in the reference's own dump format (Tracking::SaveMap, src/Tracking.cc:1745-1838: KF / MP /
+    Match / HMTraj / Motion .txt, Match.txt with the missing record separator) is read back and optimised; the articulated part is
+    what the dump determines (joints, motions, rigidity + motion edges; the joints' image observations are not dumped)."""
+    from airdos_b200 import dump, synth
+    d = synth.make_ba_problem(n_kf=14, n_points=900, seed=41, humans=3, human_poses=4)
+    table, _ = dump.inv_sigma2_table()
+    d["edge_info"] = table[np.random.default_rng(3).integers(0, 8, len(d["edge_info"]))].astype(np.float64)
+    dump.save_map_dump(str(tmp_path), d, human_poses=4)
+    g = dump.load_map_dump(str(tmp_path), {k: d[k] for k in ("fx", "fy", "cx", "cy", "bf")}, humans=True)
+    prob = {k: v for k, v in g.items() if k not in ("kf_ids", "mp_ids", "joint_key_ids", "joint_bad", "joint_lost", "joint_pose_ids", "joint_track_ids", "track_ids")}
+    assert len(prob["redge_i"]) == 3 * 4 * 14 and len(prob["medge_p1"]) == 3 * 3 * 5 and len(prob["jedge_pose"]) == 0
+    pg, rg, po, ro = _compare(opt, oracle_mod, prob)
+    assert np.abs(pg["joints"] - po["joints"]).max() < 1e-4 and np.abs(pg["dists"] - po["dists"]).max() < 1e-4
+    assert (rg.redge_outlier == ro.redge_outlier).all() and (rg.medge_outlier == ro.medge_outlier).all()
+    assert rg.c.chi2_round[0] < rg.c.chi2_initial

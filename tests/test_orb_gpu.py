@@ -62,6 +62,26 @@ def test_cuda_matches_oracle_batch(adb, oracle_mod, w, h, nf, ini, mn, masked):
     ex.close()
 
 
+def test_five_argument_constructor_provisions_lazily(adb, oracle_mod):
+    """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) as the reference declares it (include/ORBextractor.h:51-52):
+    getters work before the first frame, the first operator() provisions for its image size, a different size re-provisions."""
+    from airdos_b200 import synth
+    ex = adb.ORBextractor(1000, 1.2, 8, 12, 7)
+    assert ex.GetLevels() == 8 and abs(ex.GetScaleFactors()[3] - np.float32(1.2) ** 3) < 1e-6 and sum(ex.quotas()) == 1000
+    for w, h in ((640, 480), (320, 240), (640, 480)):
+        img = synth.make_stereo_pair(70, w, h)[0]
+        msk = synth.make_mask(71, w, h, 2)
+        k, d = ex(img, msk)
+        o = oracle_mod.orb_extract(img, msk, 1000, 1.2, 8, 12, 7)
+        assert _same(k, d, o), (w, h)
+        assert ex.level_sizes()[0] == (w, h)
+        sized = adb.ORBextractor(1000, 1.2, 8, 12, 7, w, h)
+        k2, d2 = sized(img, msk)
+        assert k2.tobytes() == k.tobytes() and (d2 == d).all()
+        sized.close()
+    ex.close()
+
+
 def test_chunked_masked_host_batch_equals_single_calls(adb, oracle_mod):
     """A host batch of >= 32 frames runs as a chunk pipeline (upload / kernels / download overlapped), with the masks
     (the reference passes one with every frame: src/Frame.cc:551-571) uploaded, eroded and resized chunk by chunk.  The result
