@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "matcher.cuh"
@@ -563,12 +564,32 @@ struct Packer {   // lays host arrays out in one staging block; device pointers 
     uint8_t* h = nullptr;
     uint8_t* d = nullptr;
     size_t off = 0;
+    struct Job { uint8_t* dst; const void* src; size_t bytes; };
+    std::vector<Job> jobs;
+    size_t job_bytes = 0;
     size_t reserve(size_t bytes) { off = (off + 15) & ~(size_t)15; const size_t o = off; off += bytes; return o; }
     template <typename T>
-    T* put(const T* src, size_t n) {   // copies when h is set (second pass), returns the device address
+    T* put(const T* src, size_t n) {   // second pass (h set): queues the copy into the pinned block; returns the device address
         const size_t o = reserve(n * sizeof(T));
-        if (h && src) memcpy(h + o, src, n * sizeof(T));
+        if (h && src && n) { jobs.push_back(Job{h + o, src, n * sizeof(T)}); job_bytes += n * sizeof(T); }
         return reinterpret_cast<T*>(d + o);
+    }
+    // The staging copy from the caller's (pageable) arrays is what a batched call costs on the host: 25 MB per 128 tracking frames.
+    // Above 2 MB it is spread over a few threads (the copies are independent ranges of one pinned block).
+    void run() {
+        const int nt = job_bytes < (2u << 20) ? 1 : (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+        if (nt <= 1) { for (const Job& j : jobs) memcpy(j.dst, j.src, j.bytes); jobs.clear(); job_bytes = 0; return; }
+        std::vector<std::thread> th;
+        const size_t per = (job_bytes + nt - 1) / nt;
+        size_t first = 0;
+        for (int t = 0; t < nt && first < jobs.size(); ++t) {
+            size_t last = first, acc = 0;
+            while (last < jobs.size() && (acc < per || t == nt - 1)) acc += jobs[last++].bytes;
+            th.emplace_back([this, first, last] { for (size_t k = first; k < last; ++k) memcpy(jobs[k].dst, jobs[k].src, jobs[k].bytes); });
+            first = last;
+        }
+        for (auto& x : th) x.join();
+        jobs.clear(); job_bytes = 0;
     }
 };
 
@@ -676,6 +697,7 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
             D.q_track = pk.put((const float*)nullptr, (size_t)s.n_q * 4);
             D.q_level = pk.put((const int32_t*)nullptr, s.n_q);
         }
+        if (pass == 1) pk.run();
         total = pk.reserve(0);
         if (pass == 0 && total > m->scratch_bytes) {
             cudaFree(m->d_scratch); m->d_scratch = nullptr;
@@ -787,6 +809,7 @@ adb_status adb_search_by_bow(adb_matcher_t m, adb_bow_search* probs, int32_t n) 
             D.choice = pk.put((const int32_t*)nullptr, qb[p].size());
             D.n_matches = pk.put((const int32_t*)nullptr, 1);
         }
+        if (pass == 1) pk.run();
         total = pk.reserve(0);
         if (pass == 0 && total > m->scratch_bytes) {
             cudaFree(m->d_scratch); m->d_scratch = nullptr;

@@ -118,6 +118,7 @@ class ORBextractor:
         if (self.width, self.height) != (w, h):
             self.width, self.height = w, h
             self._info = [self._level_info(l) for l in range(self.nlevels)]
+            self.capacity = lib().adb_orb_capacity(self._h)      # the creation-time upper bound becomes the provisioned row count
 
     def extract_batch_device(self, d_images: int, n_frames: int, frame_stride: int | None = None, pitch: int | None = None,
                              d_masks: int | None = None, width: int | None = None, height: int | None = None):

@@ -91,7 +91,8 @@ def run_best2(m, device: int = 0, steps: int = 5, nq: int = 65536, nt: int = 204
     t = torch.randint(0, 256, (nt, 32), dtype=torch.uint8, device=dev, generator=g)
     t[::97] = q[:len(t[::97])]                                   # some exact matches
     o = torch.empty((3, nq), dtype=torch.int32, device=dev)
-    st = torch.cuda.current_stream(dev)
+    st = torch.cuda.Stream(dev)          # a real stream handle: a NULL stream argument means "the matcher's own stream" to the C-ABI
+    st.wait_stream(torch.cuda.current_stream(dev))
 
     def call():
         check(lib().adb_match_best2_device(m._m, q.data_ptr(), nq, t.data_ptr(), nt, None, None, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
@@ -105,6 +106,7 @@ def run_best2(m, device: int = 0, steps: int = 5, nq: int = 65536, nt: int = 204
     e1.record(st)
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
+    torch.cuda.current_stream(dev).wait_stream(st)
     # parity on a sample against a brute force in torch (bit counting by table)
     pop = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int16, device=dev)
     sample = torch.arange(0, nq, 509, device=dev)
