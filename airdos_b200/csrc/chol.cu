@@ -467,15 +467,6 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
 #undef CHOL_MARK
 }
 
-// S += pad: identity on the padded diagonal, zero right-hand-side padding rows (the caller fills the n x n part and row ld)
-__global__ void chol_pad_kernel(double* S, int n, int ld) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n && i < ld) {
-        for (int c = 0; c < ld; ++c) S[(size_t)i * ld + c] = c == i ? 1.0 : 0.0;
-        S[(size_t)ld * ld + i] = 0.0;
-    }
-}
-
 int chol_max_cluster() {
     static int cached = -1;
     if (cached >= 0) return cached;
