@@ -1089,6 +1089,9 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         d.cand_base = cand_base; d.cand_cap = d.ncells * d.slotcap;
         // quad-tree roots: src/ORBextractor.cc:545-549
         d.n_ini = d.ncells ? (int)roundf(width / height) : 0;
+        // the reference divides by nIni and indexes an empty root vector when it is 0 (src/ORBextractor.cc:545-549): refuse the shape
+        ADB_CHECK(d.ncells == 0 || d.n_ini >= 1, ADB_ERR_INVALID, "level %d (%dx%d): region taller than twice its width, nIni = round(w / h) = 0 is undefined in the reference",
+                  l, d.w, d.h);
         d.hx = d.n_ini > 0 ? width / d.n_ini : 1.f;
         d.list_base = list_base;
         d.list_cap = std::max(d.quota + 3, 4 * std::max(d.n_ini, 1));

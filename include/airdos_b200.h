@@ -359,7 +359,11 @@ typedef struct adb_ba_problem {
     const int32_t* edge_point;       /* [n_edges] */
     const double* edge_obs;          /* [n_edges][3] u, v, u_right */
     const double* edge_info;         /* [n_edges] invSigma2 (information = invSigma2 * I) */
-    /* ---- articulated-human part (all counts may be 0), src/Optimizer.cc:1732-1957 ---- */
+    /* ---- articulated-human part (all counts may be 0), src/Optimizer.cc:1732-1957 ----
+     * Residuals of the rigidity and motion edges are the reference's; their JACOBIANS deviate on purpose:
+     * the reference's EdgeRigidBodyDouble::linearizeOplus reads never-assigned members (undefined behaviour) and
+     * LandmarkMotionTernaryEdge::linearizeOplus rescales its Jacobian on every call; this library uses the analytic rigidity
+     * Jacobian and the first-call motion Jacobian. */
     int32_t n_joints;                /* MapHumanKey vertices: VertexSBAPointXYZ, NOT marginalised */
     double* joints;                  /* [n_joints][3] in/out */
     int32_t n_joint_edges;           /* EdgeStereoSE3ProjectXYZ pose <-> joint, information SigmaHuman * I */

@@ -144,6 +144,8 @@ def orb_extract(img: np.ndarray, mask: np.ndarray | None = None, nfeatures: int 
     n = orb_lib().orb_oracle_extract(_p(img), w, h, w, _p(mask) if mask is not None else None, w,
                                      nfeatures, scale, nlevels, ini_th, min_th, _p(kps), _p(desc), cap,
                                      _p(pyr) if pyr is not None else None, _p(cand))
+    if n == -2:
+        raise ValueError("image shape unsupported: a pyramid level is taller than twice its width (nIni = round(w / h) = 0, undefined in the reference)")
     if n < 0:
         raise RuntimeError("oracle key-point capacity exceeded")
     out = {"kps": kps[:n].copy(), "desc": desc[:n].copy(), "cand_counts": cand}

@@ -310,10 +310,15 @@ void divide(const QNode& n, QNode c[4]) {
     for (int i = 0; i < 4; ++i) c[i].leaf = (c[i].keys.size() == 1);
 }
 
+// set when a level's region is so tall that nIni = round(width / height) = 0: the reference then divides by zero and indexes an
+// empty root vector (src/ORBextractor.cc:545-549, undefined behaviour); oracle and library refuse such image shapes instead
+static thread_local bool g_bad_aspect = false;
+
 void distribute_quadtree(const std::vector<KeyPoint>& cand, int minX, int maxX, int minY, int maxY,
                          int N, std::vector<KeyPoint>& out) {
     out.clear();
     const int nIni = (int)std::round((float)(maxX - minX) / (float)(maxY - minY));
+    if (nIni < 1) { g_bad_aspect = true; return; }
     const float hX = (float)(maxX - minX) / nIni;
     std::list<QNode> nodes;
     std::vector<QNode*> roots(nIni);
@@ -645,7 +650,9 @@ int orb_oracle_extract(const uint8_t* img, int w, int h, int pitch, const uint8_
                        void* kps, uint8_t* desc, int cap, uint8_t* pyr_out, int32_t* cand_counts) {
     Extractor ex(nfeatures, sf, nlevels, iniTh, minTh);
     std::vector<Level> pyr;
+    g_bad_aspect = false;
     const int n = extract(ex, img, w, h, pitch, mask, mpitch, (KeyPoint*)kps, desc, cap, &pyr, cand_counts);
+    if (g_bad_aspect) return -2;   // same contract as adb_orb_create: ADB_ERR_INVALID for portrait shapes with nIni = 0
     if (pyr_out) {
         size_t o = 0;
         for (int l = 0; l < nlevels; ++l)

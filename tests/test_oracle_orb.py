@@ -147,3 +147,15 @@ def test_extract_edge_cases(oracle_mod):
         if len(k):
             x, y = k["x"] / p["scale"][l], k["y"] / p["scale"][l]
             assert x.min() >= 18.99 and y.min() >= 18.99 and x.max() <= p["w"][l] - 19.99 and y.max() <= p["h"][l] - 19.99
+
+
+def test_portrait_shapes_with_zero_roots_are_refused(oracle_mod):
+    """DistributeOctTree takes nIni = round(width / height) root nodes (src/ORBextractor.cc:545-549); for a region taller than
+    twice its width that is 0 and the reference divides by it -- undefined.  Oracle and library refuse the shape (ADB_ERR_INVALID)."""
+    import numpy as np
+    import pytest
+    img = np.random.default_rng(0).integers(0, 256, (640, 200), dtype=np.uint8)
+    with pytest.raises(ValueError):
+        oracle_mod.orb_extract(img, None, 500, 1.2, 8, 20, 7)
+    ok = np.random.default_rng(0).integers(0, 256, (400, 300), dtype=np.uint8)     # 268 / 368 rounds to 1: fine
+    assert len(oracle_mod.orb_extract(ok, None, 500, 1.2, 8, 20, 7)["kps"]) > 0

@@ -62,6 +62,14 @@ def test_cuda_matches_oracle_batch(adb, oracle_mod, w, h, nf, ini, mn, masked):
     ex.close()
 
 
+def test_portrait_shapes_with_zero_roots_are_refused(adb):
+    """nIni = round(w / h) = 0 (src/ORBextractor.cc:545-549) is undefined in the reference: adb_orb_create refuses the shape."""
+    with pytest.raises(adb.AdbError) as e:
+        adb.ORBextractor(500, 1.2, 8, 20, 7, 200, 640)
+    assert e.value.status == 1
+    adb.ORBextractor(500, 1.2, 8, 20, 7, 300, 400).close()
+
+
 def test_five_argument_constructor_provisions_lazily(adb, oracle_mod):
     """ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) as the reference declares it (include/ORBextractor.h:51-52):
     getters work before the first frame, the first operator() provisions for its image size, a different size re-provisions."""
