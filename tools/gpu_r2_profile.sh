@@ -4,7 +4,7 @@
 # tools/summarize_ncu.py turns it into profiles/.
 mkdir -p gpurun_out
 TAG=${TAG:-r2}
-EXTRA="sm__inst_executed_pipe_fp64.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,sm__inst_executed_pipe_tensor_op_dmma.sum,sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active,lts__t_bytes.sum,launch__cluster_size"
+EXTRA="sm__inst_executed_pipe_fp64.sum,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum"
 ncu --query-metrics 2>/dev/null | grep -i -E "dmma|pipe_tensor|pipe_fp64" | cut -c1-110 > gpurun_out/${TAG}_metric_names.txt
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_line.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; echo "ref rc=$?"

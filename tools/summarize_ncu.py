@@ -21,10 +21,11 @@ WANT = [('gpu__time_duration.sum', 'duration_us', 'time'), ('dram__bytes_read.su
         ('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'pipe_fma_pct', 'pct'),
         ('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'pipe_fp64_pct', 'pct'),
         ('sm__inst_executed_pipe_fp64.sum', 'inst_pipe_fp64', 'count'),
-        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'pipe_tensor_pct', 'pct'),
+        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'pipe_tensor_pct_of_active', 'pct'),
+        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'pipe_tensor_pct_of_elapsed_all_sms', 'pct'),
+        ('sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active', 'pipe_tensor_dmma_inst_pct_of_active', 'pct'),
         ('sm__inst_executed_pipe_tensor.sum', 'inst_pipe_tensor', 'count'),
-        ('sm__inst_executed_pipe_tensor_op_dmma.sum', 'inst_pipe_tensor_dmma', 'count'),
-        ('sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active', 'pipe_tensor_dmma_pct', 'pct'),
+        ('sm__cycles_active.avg', 'sm_cycles_active_avg', 'count'), ('sm__cycles_elapsed.avg', 'sm_cycles_elapsed_avg', 'count'),
         ('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'pipe_lsu_pct', 'pct'),
         ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem_bank_conflicts', 'count'),
         ('launch__registers_per_thread', 'registers', 'count'), ('launch__grid_size', 'grid', 'count'), ('launch__block_size', 'block', 'count'),
