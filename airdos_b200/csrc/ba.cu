@@ -313,15 +313,15 @@ __global__ void __launch_bounds__(kBaThreads) ba_point_linearize_kernel(Cam C, O
 // J_pose^T (w Omega) J_pose and -J_pose^T w Omega e summed with a fixed-order block reduction into a partial record; the reduce
 // kernel adds the partials in a fixed order and stores the 6x6 block: no atomics, deterministic.  (One CTA per pose was 49 CTAs
 // on 148 SMs with ~10 edges per thread in sequence.)
-// Runs after ba_point_linearize_kernel (reads the chi2 it stored) and before the dense-edge kernel adds to H atomically.
+// Independent of ba_point_linearize_kernel (it re-evaluates the edge's chi2 itself): the two run concurrently on two streams and
+// join before the dense-edge kernel adds to H atomically.
 constexpr int kPoseChunks = 8;
 __global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, StaticEdges E, StatePair SP, const Lm* __restrict__ lm,
                                                                const int* __restrict__ pose_ptr, const int* __restrict__ pose_edges,
-                                                               const int* __restrict__ free_pose, ChiPair chi, double* __restrict__ partial) {
+                                                               const int* __restrict__ free_pose, double* __restrict__ partial) {
     __shared__ double scratch[8 * 27], red[27];
     if (lm->done || !lm->need_lin) return;
     const State S = SP.s[lm->cur];
-    const double* __restrict__ chi_e = chi.e[lm->cur];
     const int fp = blockIdx.x / kPoseChunks, ch = blockIdx.x % kPoseChunks;
     const int ip = free_pose[fp];
     double v[27];
@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(256) ba_pose_linearize_kernel(Cam C, Opt O, St
         const int dim = reproj_error(C, R, t, S.X + 3 * (size_t)E.point[e], E.obs + 3 * (size_t)e, er, Xc);
         reproj_jacobians(C, R, Xc, dim, Ji, Jj);
         const double w0 = E.info[e];
-        huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, chi_e[e], &rho0, &rho1);
+        // the same expression as the landmark-side kernel evaluates (bit for bit): the two kernels run concurrently on two streams
+        const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+        huber(dim == 3 ? O.huber_stereo : O.huber_mono, O.robust, c, &rho0, &rho1);
         const double w = rho1 * w0;
         int u = 0;
 #pragma unroll
@@ -1172,7 +1174,8 @@ using namespace adb;
 
 struct adb_ba {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: the pose side of buildSystem, forked / joined by events
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     // device buffers
     DevBuf pq[2], pt[2], X[2], Jt[2], Dd[2], mq[2], mt[2];                         // double-buffered state
@@ -1468,20 +1471,25 @@ struct Ctx {
         tm.begin(0);
         ba_clear_kernel<<<std::min(grid_for(std::max<size_t>(n2, 1), 256), 592), 256, 0, st>>>(s->H.as<double>(), n2, s->b.as<double>(), nd, lm, sc);
         ++s->launches;
+        const bool pose_side = E > 0 && !free_pose.empty();
+        if (pose_side) {   // fork: the pose side (J_pose^T W J_pose per free pose) runs on the second stream next to the landmark side
+            ADB_CUDA(cudaEventRecord(s->fork_ev, st));
+            ADB_CUDA(cudaStreamWaitEvent(s->stream2, s->fork_ev, 0));
+            const int nfp = (int)free_pose.size();
+            ba_pose_linearize_kernel<<<nfp * kPoseChunks, 256, 0, s->stream2>>>(cam(), opt(robust), sedges(), SP, lm, s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
+                                                                               s->free_pose.as<int>(), s->pose_partial.as<double>());
+            ba_pose_reduce_kernel<<<nfp, 32, 0, s->stream2>>>(s->pose_partial.as<double>(), s->free_pose.as<int>(), s->off_pose.as<int>(), nd, lm, s->H.as<double>(),
+                                                              s->b.as<double>());
+            ADB_CUDA(cudaEventRecord(s->join_ev, s->stream2));
+            s->launches += 2;
+        }
         if (NP > 0) {
             ba_point_linearize_kernel<<<grid_for((size_t)NP * kPtLanes, kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->point_ptr.as<int>(), NP,
                                                                                       s->off_pose.as<int>(), s->Hll.as<double>(), s->bl.as<double>(),
                                                                                       s->W.as<double>(), CH, sc);
             ++s->launches;
         }
-        if (E > 0 && !free_pose.empty()) {
-            const int nfp = (int)free_pose.size();
-            ba_pose_linearize_kernel<<<nfp * kPoseChunks, 256, 0, st>>>(cam(), opt(robust), sedges(), SP, lm, s->pose_ptr.as<int>(), s->pose_edges.as<int>(),
-                                                                       s->free_pose.as<int>(), CH, s->pose_partial.as<double>());
-            ba_pose_reduce_kernel<<<nfp, 32, 0, st>>>(s->pose_partial.as<double>(), s->free_pose.as<int>(), s->off_pose.as<int>(), nd, lm, s->H.as<double>(),
-                                                      s->b.as<double>());
-            s->launches += 2;
-        }
+        if (pose_side) ADB_CUDA(cudaStreamWaitEvent(st, s->join_ev, 0));   // join
         if (n_dyn() > 0) {
             ba_dyn_kernel<<<grid_for(n_dyn(), kBaThreads), kBaThreads, 0, st>>>(cam(), opt(robust), dedges(), SP, lm, doff(), nd, s->H.as<double>(),
                                                                                s->b.as<double>(), CH, sc, 0);
@@ -1669,6 +1677,9 @@ adb_status adb_ba_create(int32_t device, adb_ba_t* out) {
     adb_ba* s = new adb_ba();
     s->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_lm, sizeof(Lm));
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "ba create", __FILE__, __LINE__); }
     *out = s;
@@ -1690,6 +1701,9 @@ adb_status adb_ba_destroy(adb_ba_t s) {
     if (s->h_lm) cudaFreeHost(s->h_lm);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     cudaStreamDestroy(s->stream);
+    if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
+    if (s->fork_ev) cudaEventDestroy(s->fork_ev);
+    if (s->join_ev) cudaEventDestroy(s->join_ev);
     cudaGetLastError();
     delete s;
     return ADB_OK;

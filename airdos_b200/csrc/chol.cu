@@ -36,6 +36,10 @@ namespace {
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// the two halves of the barrier: CTA 0 arrives as soon as its panel rows are stored and waits only after it has factored the next
+// diagonal tile, so that nobody waits for that factorisation at the panel barrier
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -270,6 +274,7 @@ size_t chol_scratch_elems(int n) { const size_t nb = (size_t)chol_nblk(n); retur
 __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S, int ld, int nblk, double* scratch, double* xout, int* info, const int* skip, long long* prof) {
     if (skip != nullptr && *skip != 0) return;   // device-side LM control: the round is already over (uniform over the cluster)
     __shared__ TileSmem T;
+    __shared__ double Pn[kCholNB][kTbPitch];   // CTA 0: its freshly solved panel tile L(k + 1, k), operand of the next diagonal tile's update
     __shared__ double xb[kCholNB];
     extern __shared__ double yb[];   // [ld] (back-substitution, CTA 0)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -318,6 +323,18 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
             __syncthreads();
         }
         CHOL_MARK(0);
+        const int m = nblk - (k + 1);   // trailing column blocks
+        // CTA 0, look-ahead: the next diagonal tile C(k + 1, k + 1) has been final since the previous step's barrier -- fetch this warp's
+        // part now (warp w: row group w / 2, column groups 2 (w % 2), + 1), its latency hides behind the panel solve
+        const int drg = warp >> 1, dcg0 = 2 * (warp & 1);
+        const bool don0 = dcg0 <= drg, don1 = dcg0 + 1 <= drg;
+        double2 dacc[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+        if (rank == 0 && m > 0) {
+            const size_t r0 = (size_t)(k + 1) * kCholNB;
+            const double* pc = S + (r0 + 8 * drg + g) * ld + r0 + 2 * q;
+            if (don0) dacc[0] = *reinterpret_cast<const double2*>(pc + 8 * dcg0);
+            if (don1) dacc[1] = *reinterpret_cast<const double2*>(pc + 8 * dcg0 + 8);
+        }
         // row blocks i = k + 1 + rank, + C, ... (the right-hand side is row block nblk); a pass takes two of them: warp w solves
         // the 8 rows of group w % 4 of row block (w / 4)
         for (int i = k + 1 + rank + C * (warp >> 2); i < nrb; i += 2 * C) {
@@ -328,6 +345,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
             trsm_group(T, g, q, x);
 #pragma unroll
             for (int j = 0; j < kCholNSB; ++j) *reinterpret_cast<double2*>(rowp + 8 * j) = x[j];
+            if (rank == 0 && i == k + 1 && m > 0) {   // keep L(k + 1, k) on chip for the diagonal update
+#pragma unroll
+                for (int j = 0; j < kCholNSB; ++j) { Pn[8 * (warp & 3) + g][8 * j + 2 * q] = x[j].x; Pn[8 * (warp & 3) + g][8 * j + 2 * q + 1] = x[j].y; }
+            }
         }
         CHOL_MARK(2);
         // the last CTA (fewest row blocks) also inverts the diagonal tile for the back-substitution: X L^T = I -> X = L^-T
@@ -342,20 +363,45 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
             for (int j = 0; j < kCholNSB; ++j) *reinterpret_cast<double2*>(rowp + 8 * j) = x[j];
         }
         CHOL_MARK(3);
-        cluster_barrier();   // panel k complete and visible to the whole cluster
+        if (rank == 0 && m > 0) {
+            // ---- CTA 0: arrive at the panel barrier (its rows are stored), then -- without waiting for the others' panel rows -- update
+            //      the next diagonal tile from the on-chip panel tile, factor it and publish the factor; only then wait.
+            cluster_arrive();
+            __syncthreads();   // Pn complete; everybody is done reading T (the current factor)
+            if (don0) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const double ax = -Pn[8 * drg + g][8 * s + 2 * q], ay = -Pn[8 * drg + g][8 * s + 2 * q + 1];
+                    dmma884(dacc[0].x, dacc[0].y, ax, Pn[8 * dcg0 + g][8 * s + 2 * q]);
+                    dmma884(dacc[0].x, dacc[0].y, ay, Pn[8 * dcg0 + g][8 * s + 2 * q + 1]);
+                    if (don1) {
+                        dmma884(dacc[1].x, dacc[1].y, ax, Pn[8 * dcg0 + 8 + g][8 * s + 2 * q]);
+                        dmma884(dacc[1].x, dacc[1].y, ay, Pn[8 * dcg0 + 8 + g][8 * s + 2 * q + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 8 * drg + g, c = 8 * (dcg0 + h) + 2 * q;
+                T.Tb[r][c] = c <= r ? dacc[h].x : 0.0;
+                T.Tb[r][c + 1] = c + 1 <= r ? dacc[h].y : 0.0;
+            }
+            __syncthreads();
+            factor_and_publish(k + 1);
+            CHOL_MARK(1);
+            cluster_wait();    // now the whole panel k is visible
+        } else {
+            cluster_barrier();   // panel k complete and visible to the whole cluster
+        }
         CHOL_MARK(4);
-        const int m = nblk - (k + 1);   // trailing column blocks
         if (m > 0) {
-            // ---- phase B: trailing update on the FP64 tensor cores + look-ahead.  Tile 0 of the row-major order is the next
-            //      diagonal tile: CTA 0 updates it straight into shared memory, factors it and publishes the factor while the
-            //      other CTAs update the rest of the trailing matrix; then it takes a (reduced) share of the tiles itself.
+            // ---- phase B: trailing update on the FP64 tensor cores.  Tile 0 of the row-major order is the next diagonal tile, which
+            //      CTA 0 has already taken care of (look-ahead above); CTA 0 takes a reduced share of the rest.
             const int nt = m * (m + 1) / 2 + m;
             const double* panel = S + kc + 2 * q;
-            // contiguous ranges of equal COST per CTA: a full tile = 16 sub-tile products, a diagonal tile 10, a right-hand-side
-            // tile 4 (one row group).  cost_before(t) = cost of tiles [0, t) in closed form; boundaries by bisection.
+            // contiguous ranges of equal COST per CTA (bytes moved rather than products: the update runs at about half the tensor-pipe
+            // rate, bound by L1 / L2 traffic): full tile 16, diagonal tile 14, right-hand-side tile (one row group) 8
             const int ntri = m * (m + 1) / 2;
-            // cost model (bytes moved rather than products: the update runs at about half the tensor-pipe rate, bound by L1 / L2
-            // traffic): full tile 16, diagonal tile 14, right-hand-side tile (one row group) 8
             const int ctri = 8 * m * (m - 1) + 14 * m;             // cost of the triangle; all costs fit 32 bits (m <= 160)
             auto tile_at_cost = [&](int c) -> int {                 // smallest t with cost of tiles [0, t) >= c: closed form + fix-up
                 if (c >= ctri) return min(nt, ntri + ((c - ctri + 7) >> 3));
@@ -376,40 +422,6 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(double* S
                     t0 = max(1, tile_at_cost(14 + share0 + per * (rank - 1)));
                     t1 = rank == C - 1 ? nt : max(1, tile_at_cost(14 + share0 + per * rank));
                 }
-            }
-            if (rank == 0) {
-                // next diagonal tile: 8 warps share it (warp w: row group w / 2, column groups 2 (w % 2), + 1) -- it is on the critical path
-                const int rg = warp >> 1, cg0 = 2 * (warp & 1);
-                const size_t r0 = (size_t)(k + 1) * kCholNB;
-                double2 acc[2];
-                const bool on0 = cg0 <= rg, on1 = cg0 + 1 <= rg;
-                const double* pa = panel + (r0 + 8 * rg + g) * ld;
-                const double* pc = S + (r0 + 8 * rg + g) * ld + r0 + 2 * q;
-                acc[0] = on0 ? *reinterpret_cast<const double2*>(pc + 8 * cg0) : make_double2(0.0, 0.0);
-                acc[1] = on1 ? *reinterpret_cast<const double2*>(pc + 8 * cg0 + 8) : make_double2(0.0, 0.0);
-                if (on0) {
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const double2 av = *reinterpret_cast<const double2*>(pa + 8 * s);
-                        const double2 b0 = *reinterpret_cast<const double2*>(panel + (r0 + 8 * cg0 + g) * ld + 8 * s);
-                        dmma884(acc[0].x, acc[0].y, -av.x, b0.x);
-                        dmma884(acc[0].x, acc[0].y, -av.y, b0.y);
-                        if (on1) {
-                            const double2 b1 = *reinterpret_cast<const double2*>(panel + (r0 + 8 * cg0 + 8 + g) * ld + 8 * s);
-                            dmma884(acc[1].x, acc[1].y, -av.x, b1.x);
-                            dmma884(acc[1].x, acc[1].y, -av.y, b1.y);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = 8 * rg + g, c = 8 * (cg0 + h) + 2 * q;
-                    T.Tb[r][c] = c <= r ? acc[h].x : 0.0;
-                    T.Tb[r][c + 1] = c + 1 <= r ? acc[h].y : 0.0;
-                }
-                __syncthreads();
-                factor_and_publish(k + 1);
-                CHOL_MARK(1);
             }
             // one warp per tile: 16 independent accumulator chains keep the tensor pipe busy without any block-level barrier
             for (int t = t0 + warp; t < t1; t += kCholThreads / 32) {
