@@ -370,6 +370,109 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     if (tid == 0) *cnt_out = (uint16_t)min(n_sel, L.slotcap);
 }
 
+// The hot variant: ONE WARP per (cell, frame), eight independent warps per CTA, no block barrier and no score tile.
+//   * lane = column of the cell (cells are 30 .. 33 pixels wide at the usual settings); wider cells are walked as column tiles of
+//     30 + 2 halo lanes inside the same row step (kFwTiles of them: up to 92 columns, above that the CTA-per-cell kernel runs);
+//   * the warp walks down the rows: address += pitch, no index arithmetic; the scores of rows y - 2, y - 1, y stay in registers, so
+//     the strict 3 x 3 NMS of row y - 1 is one packed 3-input maximum per column plus two shuffles -- and the reference's blindness
+//     across cell seams is free: whatever lies outside the cell is simply a lane that holds 0;
+//   * kept corners leave in row-major order as they are found (ballot + popc): corners at iniTh grow from the front of the cell's
+//     slot, corners that only reach minTh from its back; the ini / min rule is then just WHICH end the consumer reads (bit 15 of the
+//     cell count = "no corner at iniTh: read the back, reversed").  No rank loop, no atomics.
+// Per 32 pixels: 17 LDS + 17 IMAD + 41 packed min / max for the score, ~25 instructions for everything else (the CTA-per-cell
+// kernel: ~170 on top of the score).
+constexpr int kFwWarps = 8, kFwTiles = 3, kFwStep = 30;   // column tiles advance by 30: 32 lanes minus the two halo lanes
+template <int kBW>
+__global__ void __launch_bounds__(kFwWarps * 32) fast_cells_warp_kernel(const __grid_constant__ TmaMaps16 maps,
+                                                                        const LevelDev* __restrict__ levels,
+                                                                        const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
+                                                                        int ini_th, int min_th, uint32_t* __restrict__ cand,
+                                                                        int cand_total, uint16_t* __restrict__ cellcnt,
+                                                                        int ncells_total, int tile_bytes, int f0) {
+    extern __shared__ __align__(128) uint8_t fw_smem[];
+    __shared__ uint64_t bars[kFwWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y + f0;
+    const int cell = blockIdx.x * kFwWarps + warp;
+    if (cell >= ncells_total) return;
+    uint8_t* tile = fw_smem + ((128u - (smem_u32(fw_smem) & 127u)) & 127u) + (size_t)warp * tile_bytes;
+    uint64_t* bar = &bars[warp];
+    const uint32_t ce = __ldg(&cell_table[cell]);
+    const int level = ce >> 24, ci = (ce >> 12) & 0xFFF, cj = ce & 0xFFF;
+    const LevelDev& L = levels[level];
+    const int maxBX = L.w - kMinBorder, maxBY = L.h - kMinBorder;
+    const int iniY = kMinBorder + ci * L.hcell, iniX = kMinBorder + cj * L.wcell;
+    const int maxY = min(iniY + L.hcell + 6, maxBY), maxX = min(iniX + L.wcell + 6, maxBX);
+    const int cw = maxX - iniX, ch = maxY - iniY;
+    uint16_t* cnt_out = cellcnt + (size_t)f * ncells_total + cell;
+    if (iniY >= maxBY - 3 || iniX >= maxBX - 6 || cw < 7 || ch < 7) {   // the reference's `continue`s
+        if (lane == 0) *cnt_out = 0;
+        return;
+    }
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)(kBW * L.box_h));
+        tma_load_3d(tile, &maps.m[level], bar, iniX & ~15, iniY, f);   // box origin must be 16-B aligned in x
+    }
+    __syncwarp();
+    const int iw = cw - 6, ih = ch - 6;
+    const int nt = max(1, (iw + 27) / kFwStep);                              // tiles start at columns 0, 30, 60; a tile decides lanes 1 .. 30
+    const int t_low = min(ini_th, min_th);                                     // (+ lane 0 of the first, lane 31 when it is the last column)
+    const uint8_t* ml = masks.p[level];
+    if (ml) ml += (size_t)f * L.mframe_stride + (size_t)(iniY + 3) * L.mpitch + iniX + 3;
+    uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(cell - L.cell_base) * L.slotcap;
+    const int slotcap = L.slotcap, mpitch = L.mpitch;
+    const uint32_t rec0 = (uint32_t)(3 + cj * L.wcell) | ((uint32_t)(3 + ci * L.hcell) << 12);   // record of the cell's first inner pixel
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t sA[kFwTiles], sB[kFwTiles];      // scores of rows y - 2, y - 1 of this lane's column, per tile
+    bool decide[kFwTiles];
+    const uint8_t* cp[kFwTiles];
+#pragma unroll
+    for (int t = 0; t < kFwTiles; ++t) {
+        sA[t] = 0; sB[t] = 0;
+        const int col = t * kFwStep + lane;
+        decide[t] = t < nt && col < iw && (lane > 0 || t == 0) && (lane < 31 || col == iw - 1);
+        cp[t] = tile + 3 * kBW + (iniX & 15) + 3 + min(col, iw - 1);
+    }
+    int cntA = 0, cntB = 0;
+    mbar_wait(bar, 0);
+    for (int y = 0; y <= ih; ++y) {
+#pragma unroll
+        for (int t = 0; t < kFwTiles; ++t) {
+            if (t > 0 && t >= nt) break;
+            uint32_t s = 0;
+            if (y < ih) {
+                const uint8_t* c = cp[t];
+                uint32_t ring[16];
+                load_ring_packed(c, kBW, (uint32_t)c[0] * 0xFFFF0001u + 0x01000100u, ring);   // (256 + v) | (256 - v) << 16
+                const int best = fast_best(ring);
+                s = (t * kFwStep + lane < iw && best > t_low) ? (uint32_t)(best - 1) : 0u;   // response = best - 1 (>= 1 for every corner)
+                cp[t] = c + kBW;
+            }
+            // strict 3 x 3 NMS of row y - 1
+            const uint32_t v = sB[t];
+            const uint32_t c3 = max(max(sA[t], v), s);
+            uint32_t cl = __shfl_up_sync(0xFFFFFFFFu, c3, 1), cr = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
+            if (lane == 0) cl = 0;
+            if (lane == 31) cr = 0;
+            bool keep = decide[t] && v > max(max(cl, cr), max(sA[t], s));
+            sA[t] = v; sB[t] = s;
+            if (__any_sync(0xFFFFFFFFu, keep)) {
+                const int col = t * kFwStep + lane;
+                if (keep && ml) keep = ml[(size_t)(y - 1) * mpitch + col] != 0;
+                const bool isA = keep && (int)v >= ini_th, isB = keep && !isA && (int)v >= min_th;
+                const uint32_t balA = __ballot_sync(0xFFFFFFFFu, isA), balB = __ballot_sync(0xFFFFFFFFu, isB);
+                const uint32_t rec = (rec0 + (uint32_t)col + ((uint32_t)(y - 1) << 12)) | (v << 24);
+                if (isA) slot[cntA + __popc(balA & lt)] = rec;
+                if (isB) slot[slotcap - 1 - cntB - __popc(balB & lt)] = rec;
+                cntA += __popc(balA); cntB += __popc(balB);
+            }
+        }
+    }
+    if (lane == 0) *cnt_out = (uint16_t)(cntA ? cntA : (cntB ? (cntB | 0x8000) : 0));
+}
+
 // =========================================================================================
 // Quad-tree distribution, one CTA per (level, frame).
 //
@@ -444,7 +547,7 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
         int run = 0;
         for (int c0 = 0; c0 < L.ncells; c0 += 32) {
             const int c = c0 + lane;
-            const int v = c < L.ncells ? (int)ccnt[c] : 0;
+            const int v = c < L.ncells ? (int)(ccnt[c] & 0x7FFF) : 0;
             const int inc = warp_incl_scan(v, lane);
             if (c < L.ncells) state[c] = (uint32_t)(run + inc - v);   // cell offsets live in state[0..ncells)
             run += __shfl_sync(0xFFFFFFFFu, inc, 31);
@@ -460,10 +563,11 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
     }
     // cell offsets live in state[0..ncells) (ncells <= cand_cap); the gather writes keys[] only
     for (int c = warp; c < L.ncells; c += kQtThreads / 32) {
-        const int n = ccnt[c];
+        const int cc = ccnt[c], n = cc & 0x7FFF;          // bit 15: no corner at iniTh, the minTh corners sit at the back of the slot, reversed
         const uint32_t o = state[c];
         const uint32_t* src = cslots + (size_t)c * L.slotcap;
-        for (int s = lane; s < n; s += 32) keys[o + s] = src[s];
+        if (cc & 0x8000) for (int s = lane; s < n; s += 32) keys[o + s] = src[L.slotcap - 1 - s];
+        else for (int s = lane; s < n; s += 32) keys[o + s] = src[s];
     }
     __syncthreads();
 
@@ -712,9 +816,90 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
 // arrives by TMA (out-of-image bytes zero-filled, then mirrored per BORDER_REFLECT_101 at the
 // ROI edge); IC-angle on the raw patch; 7x7 fixed-point Gaussian on the 37 x 37 core; the 256
 // rotated tests read the blurred core.
+// =========================================================================================
+// GaussianBlur(7 x 7, sigma 2, BORDER_REFLECT_101) of a whole pyramid level (src/ORBextractor.cc:1099-1100: the reference blurs a clone
+// of the level ROI once per level).  Fixed point {18,34,48,56,48,34,18} / 256 on both axes, (v + 2^15) >> 16: integer and exact, so
+// the pass order is free.  Round 1 blurred a 37 x 37 core per key-point inside the descriptor kernel: 1200 of its 2065
+// warp-instructions per key-point, 2.4 M per frame; the whole level costs 0.4 M per frame and the descriptor kernel fetches the
+// blurred patch with a second TMA box load.
+// One WARP per (120-pixel column group, 32-row strip), no shared memory and no block barrier: lane = one aligned word (4 pixels) of the
+// row, lanes 0 and 31 are the halo words of the group.  A lane walks down its column: one coalesced word load per row slides through
+// a 7-row register window (even / odd pixels as two 16-bit lanes each: two pixels per multiply, 7 x 255 x 56 < 2^16; the kernel is
+// symmetric: 3 adds + 4 multiply-adds per lane pair), the four 16-bit column sums of the word go to the neighbours by shuffles, the
+// row pass is DP2A on the packed sums, one word store per lane and row.  BORDER_REFLECT_101: rows by the row index; the left edge on
+// the column SUMS (the column pass is per column, so S(-k) = S(k)); words that reach over the right edge are assembled byte-wise.
+constexpr int kBlRows = 32, kBlGroupW = 30, kBlAhead = 8;
+__device__ __forceinline__ int reflect101_any(int p, int len) {   // halo lanes may hang far over the right edge of a small level
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+__global__ void __launch_bounds__(128) blur7_level_kernel(const __grid_constant__ BlurLevels B, int f0) {
+    const int lane = threadIdx.x & 31;
+    int task = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (task >= B.ntasks) return;
+    int l = 0;
+    while (task >= B.task_end[l]) ++l;
+    if (l) task -= B.task_end[l - 1];
+    const int w = B.w[l], h = B.h[l], spitch = B.spitch[l], dpitch = B.dpitch[l], ncg = B.ncg[l];
+    const int strip = task / ncg, g = task - strip * ncg, f = blockIdx.y + f0;
+    const int wi = g * kBlGroupW - 1 + lane;               // this lane's word: pixels 4 wi .. 4 wi + 3
+    const int y0 = strip * kBlRows, nrows = min(kBlRows, h - y0);
+    const uint8_t* sp = B.src[l] + (size_t)f * B.sfstride[l];
+    const int fullwords = w >> 2;
+    const bool aligned = (((uintptr_t)sp | (uintptr_t)spitch) & 3) == 0;
+    const bool bytewise = wi >= fullwords || !aligned;     // right edge (reflected bytes) or a caller buffer without word alignment
+    const int lw = max(wi, 0);
+    const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
+    int bx[4];                                             // byte-wise path: the four (reflected) columns of this lane's word
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bx[k] = reflect101_any(min(4 * lw + k, w + 6), w);
+    uint8_t* dp = B.dst[l] + (size_t)f * B.dfstride[l] + 4 * lw;     // destination: the handle's own buffer, word aligned
+    const bool store = lane >= 1 && lane <= kBlGroupW && 4 * wi < w;
+    auto load_row = [&](int i) -> uint32_t {               // input row i of the strip (row y0 - 3 + i of the level, reflected)
+        int yy = y0 - 3 + i;
+        yy = yy < 0 ? -yy : (yy >= h ? 2 * (h - 1) - yy : yy);
+        yy = min(max(yy, 0), h - 1);                       // (levels of fewer than 4 rows cannot occur; keeps the load in bounds)
+        const uint8_t* rowp = sp + (size_t)yy * spitch;
+        if (!bytewise) return __ldg(reinterpret_cast<const uint32_t*>(rowp) + lw);
+        return (uint32_t)__ldg(rowp + bx[0]) | ((uint32_t)__ldg(rowp + bx[1]) << 8) | ((uint32_t)__ldg(rowp + bx[2]) << 16) | ((uint32_t)__ldg(rowp + bx[3]) << 24);
+    };
+    uint32_t we[7], wo[7], pre[kBlAhead];                  // kBlAhead rows are in flight ahead of the one being consumed
+#pragma unroll
+    for (int k = 0; k < kBlAhead; ++k) pre[k] = load_row(min(k, nrows + 5));
+#pragma unroll
+    for (int i = 0; i < kBlRows + 6; ++i) {
+        if (i >= nrows + 6) break;
+        const uint32_t wv = pre[i % kBlAhead];
+        if (i + kBlAhead < kBlRows + 6) pre[i % kBlAhead] = load_row(min(i + kBlAhead, nrows + 5));
+#pragma unroll
+        for (int t = 0; t < 6; ++t) { we[t] = we[t + 1]; wo[t] = wo[t + 1]; }
+        we[6] = wv & 0x00FF00FFu; wo[6] = (wv >> 8) & 0x00FF00FFu;
+        if (i >= 6) {
+            const uint32_t lo = 18u * (we[0] + we[6]) + 34u * (we[1] + we[5]) + 48u * (we[2] + we[4]) + 56u * we[3];   // sums of pixels 0, 2
+            const uint32_t hi = 18u * (wo[0] + wo[6]) + 34u * (wo[1] + wo[5]) + 48u * (wo[2] + wo[4]) + 56u * wo[3];   // pixels 1, 3
+            const uint32_t w2 = __byte_perm(lo, hi, 0x5410), w3 = __byte_perm(lo, hi, 0x7632);   // [S0, S1], [S2, S3]
+            uint32_t w0 = __shfl_up_sync(0xFFFFFFFFu, w2, 1), w1 = __shfl_up_sync(0xFFFFFFFFu, w3, 1);
+            const uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w2, 1), w5 = __shfl_down_sync(0xFFFFFFFFu, w3, 1);
+            if (wi == 0) { w0 = w3; w1 = __byte_perm(w2, w3, 0x3254); }      // S(-3) = S3 (upper half), [S(-2), S(-1)] = [S2, S1]
+            const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16), s2 = __funnelshift_r(w2, w3, 16),
+                           s3 = __funnelshift_r(w3, w4, 16), s4 = __funnelshift_r(w4, w5, 16);
+            const uint32_t v0 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 32768u))));
+            const uint32_t v1 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 32768u))));
+            const uint32_t v2 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 32768u))));
+            const uint32_t v3 = __dp2a_hi(w5, kw1, __dp2a_lo(w4, kw1, __dp2a_hi(w3, kw0, __dp2a_lo(w2, kw0, 32768u))));
+            // bytes 2 of v0 .. v3 (sums < 2^24): two PRMTs pick them
+            const uint32_t packed = __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410);
+            if (store) *reinterpret_cast<uint32_t*>(dp + (size_t)(y0 + i - 6) * dpitch) = packed;   // the pitch is padded to 16 B: a ragged last word fits
+        }
+    }
+}
+
 constexpr int kDescWarps = 8;
-constexpr int kRawBytes = 2816;          // 43 rows x 64 B, padded to a multiple of 128 B
-constexpr int kBPitch = 40;              // blurred core: 37 rows x 40
+constexpr int kIcBoxH = 31, kIcR = 15;   // level box for IC_Angle: the r = 15 disc, 31 rows x 64 B
+constexpr int kBlBoxH = 37, kBlR = 18;   // blurred box for rBRIEF: samples reach +-18 px, 37 rows x 64 B
+constexpr int kRawBytes = 2048;          // 31 x 64 B padded to a multiple of 128 B
+constexpr int kBlrBytes = 2432;          // 37 x 64 B padded to a multiple of 128 B
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 // cv::fastAtan2 in degrees, every operation rounded to float32, no contraction (oracle/orb_oracle.cpp:153-177)
@@ -750,10 +935,9 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-constexpr int kVPitchW = 26;            // 32-bit words per row of the column-pass buffer (48 u16 columns + slack for the last quad)
 struct DescSmem {
-    uint8_t raw[kDescWarps][kRawBytes];               // 43 x 64 B patch; reused for the blurred 37 x 37 core (pitch kBPitch)
-    uint32_t vert[kDescWarps][37 * kVPitchW];         // column pass: 37 rows x 48 u16
+    uint8_t raw[kDescWarps][kRawBytes];               // 31 x 64 B box of the level around the key-point: the r = 15 disc of IC_Angle
+    uint8_t blr[kDescWarps][kBlrBytes];               // 37 x 64 B box of the BLURRED level (blur7_level_kernel): rBRIEF samples +-18 px
     uint32_t ic_wu[16][8];                            // IC_Angle row tables by |v|: signed weights u of word k (0 outside the disc)
     uint32_t ic_m[16][8];                             // ... and the disc mask as 0 / 1 bytes
     uint64_t bar[kDescWarps];
@@ -771,7 +955,7 @@ __device__ __forceinline__ void gather_store_u32(uint32_t* p, uint32_t v, int mu
     else *p = v;
 }
 
-__global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const __grid_constant__ TmaMaps16 maps,
+__global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const __grid_constant__ TmaMaps16 maps, const __grid_constant__ TmaMaps16 bmaps,
                                                                          const LevelDev* __restrict__ levels, int nlevels,
                                                                          const uint32_t* __restrict__ list, int list_total,
                                                                          const int32_t* __restrict__ listcnt,
@@ -817,35 +1001,17 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;
 
     uint8_t* raw0 = sm.raw[warp];
+    uint8_t* blr0 = sm.blr[warp];
     uint64_t* bar = &sm.bar[warp];
     const int x0 = cx - kPatchR, y0 = cy - kPatchR;
     if (lane == 0) {
         fence_proxy_async();
-        mbar_expect_tx(bar, kPatchBoxW * kPatchBoxH);
-        tma_load_3d(raw0, &maps.m[lvl], bar, x0 & ~15, y0, f);   // 16-B aligned box origin
+        mbar_expect_tx(bar, kPatchBoxW * (kIcBoxH + kBlBoxH));
+        tma_load_3d(raw0, &maps.m[lvl], bar, x0 & ~15, cy - kIcR, f);    // 16-B aligned box origin; both boxes lie inside the level:
+        tma_load_3d(blr0, &bmaps.m[lvl], bar, x0 & ~15, cy - kBlR, f);   // key-points sit >= 19 px from its edges
     }
     mbar_wait(bar, 0);
     const int dxp = x0 & 15;
-    uint8_t* raw = raw0 + dxp;   // column 0 of the 43 x 43 patch
-    // BORDER_REFLECT_101 at the ROI edge (only key-points within 21 px of it; at most 2 rows / columns)
-    if (y0 < 0 || y0 + 42 >= L.h) {
-        for (int r = 0; r < kPatchBoxH; ++r) {
-            const int gy = y0 + r;
-            if (gy >= 0 && gy < L.h) continue;
-            const int sr = reflect101(gy, L.h) - y0;
-            for (int c = lane; c < 43; c += 32) raw[r * kPatchBoxW + c] = raw[sr * kPatchBoxW + c];
-        }
-        __syncwarp();
-    }
-    if (x0 < 0 || x0 + 42 >= L.w) {
-        for (int c = 0; c < 43; ++c) {
-            const int gx = x0 + c;
-            if (gx >= 0 && gx < L.w) continue;
-            const int sc = reflect101(gx, L.w) - x0;
-            for (int r = lane; r < kPatchBoxH; r += 32) raw[r * kPatchBoxW + c] = raw[r * kPatchBoxW + sc];
-        }
-        __syncwarp();
-    }
 
     // ---- IC_Angle (src/ORBextractor.cc:78-105): m10 = sum u*I, m01 = sum v*I over the r=15 disc
     // a lane owns word k of four rows at a time (8 lanes per row: the 64-B row pitch would put all rows of a lane-per-row
@@ -854,7 +1020,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     int m10 = 0, m01 = 0;
     {
         const int k = lane & 7, rsub = lane >> 3;
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw0 + (kPatchR - 15) * kPatchBoxW) + ((dxp + 6) >> 2) + k;
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw0) + ((dxp + 6) >> 2) + k;   // row 0 of the box is v = -15
         const uint32_t s8 = (uint32_t)((dxp + 6) & 3) * 8u;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -874,76 +1040,12 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- GaussianBlur 7x7 sigma 2 = fixed-point {18,34,48,56,48,34,18}/256 on both axes, (v + 2^15) >> 16.
-    // Integer and exact, so the pass order is free: columns first, two pixels per 32-bit multiply
-    // (7 x 255 x 56 < 2^16 per 16-bit lane), then rows with DP2A on the 16-bit sums.
-    uint32_t* vert = sm.vert[warp];
-    const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw0) + (dxp >> 2);   // aligned words covering the patch columns
-    const int sh = dxp & 3;                                                         // patch column c sits at u16 column c + sh
-    // column pass as a sliding window: a lane owns one 4-pixel word column and half of the rows; every input row is
-    // loaded once and scattered into the seven running sums it contributes to.
-    if (lane < 24) {
-        const int wd = lane < 12 ? lane : lane - 12;
-        const int r_begin = lane < 12 ? 0 : 19, r_end = lane < 12 ? 19 : 37;        // output rows [r_begin, r_end)
-        // sliding window of the last 7 input rows (even / odd pixels as two 16-bit lanes each); the kernel is symmetric, so an
-        // output row costs 3 adds (alu pipe) + 4 multiply-adds (fma pipe) per register instead of 7 multiply-adds.
-        // Fully unrolled (25 rows) so the window rotation is pure register renaming.
-        uint32_t we[7], wo[7];
-#pragma unroll
-        for (int i = 0; i < 25; ++i) {
-            const int ri = min(r_begin + i, kPatchBoxH - 1);
-            const uint32_t w = raw32[ri * (kPatchBoxW / 4) + wd];
-#pragma unroll
-            for (int t = 0; t < 6; ++t) { we[t] = we[t + 1]; wo[t] = wo[t + 1]; }
-            we[6] = w & 0x00FF00FFu; wo[6] = (w >> 8) & 0x00FF00FFu;
-            if (i >= 6 && r_begin + i - 6 < r_end) {
-                const uint32_t lo = 18u * (we[0] + we[6]) + 34u * (we[1] + we[5]) + 48u * (we[2] + we[4]) + 56u * we[3];
-                const uint32_t hi = 18u * (wo[0] + wo[6]) + 34u * (wo[1] + wo[5]) + 48u * (wo[2] + wo[4]) + 56u * wo[3];
-                uint2 out;
-                out.x = __byte_perm(lo, hi, 0x5410);
-                out.y = __byte_perm(lo, hi, 0x7632);
-                *reinterpret_cast<uint2*>(vert + (r_begin + i - 6) * kVPitchW + 2 * wd) = out;
-            }
-        }
-    }
-    __syncwarp();
-    uint8_t* bl = raw0;   // the raw patch is dead from here on: blurred core, 37 rows x kBPitch
-    {
-        // row pass: a lane makes 4 adjacent outputs from 6 words of 16-bit column sums; DP2A does two taps per instruction
-        const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
-        const bool odd = sh & 1;
-        const int wsh = sh >> 1;
-        // 30 lanes = 3 rows x 10 quads per step (no index arithmetic inside the loop)
-        const int r3 = lane / 10, qd = lane - r3 * 10;      // outputs c = 4 qd .. 4 qd + 3
-        for (int r = r3; r < 37 && lane < 30; r += 3) {
-            const uint32_t* p = vert + r * kVPitchW + 2 * qd + wsh;
-            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4], w5 = p[5];
-            const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16), s2 = __funnelshift_r(w2, w3, 16),
-                           s3 = __funnelshift_r(w3, w4, 16), s4 = __funnelshift_r(w4, w5, 16);
-            uint32_t v0, v1, v2, v3;
-            if (!odd) {   // windows start at u16 columns 4qd+sh (even), +1, +2, +3
-                v0 = __dp2a_hi(w3, kw1, __dp2a_lo(w2, kw1, __dp2a_hi(w1, kw0, __dp2a_lo(w0, kw0, 0u))));
-                v1 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 0u))));
-                v2 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 0u))));
-                v3 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 0u))));
-            } else {      // first window starts in the upper half of w0
-                v0 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 0u))));
-                v1 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 0u))));
-                v2 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 0u))));
-                v3 = __dp2a_hi(w5, kw1, __dp2a_lo(w4, kw1, __dp2a_hi(w3, kw0, __dp2a_lo(w2, kw0, 0u))));
-            }
-            const uint32_t packed = ((v0 + 32768u) >> 16) | (((v1 + 32768u) >> 16) << 8) | (((v2 + 32768u) >> 16) << 16) | (((v3 + 32768u) >> 16) << 24);
-            *reinterpret_cast<uint32_t*>(bl + r * kBPitch + 4 * qd) = packed;   // columns 37..39 of the last quad are padding
-        }
-    }
-    __syncwarp();
-
     // ---- steered rBRIEF (src/ORBextractor.cc:109-148); lane = descriptor byte
     const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     double sd, cd;
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    const uint8_t* ctr = bl + 18 * kBPitch + 18;
+    const uint8_t* ctr = blr0 + dxp + kBlR * kPatchBoxW + kPatchR;   // the key-point inside the blurred box (row 18, patch column 21)
     const char2* pat2 = reinterpret_cast<const char2*>(pattern);
     uint32_t byte = 0;
 #pragma unroll
@@ -954,7 +1056,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0f, a), __fmul_rn(y0f, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1f, b), __fmul_rn(y1f, a)));
         const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1f, a), __fmul_rn(y1f, b)));
-        const int t0 = ctr[r0 * kBPitch + q0], t1 = ctr[r1 * kBPitch + q1];
+        const int t0 = ctr[r0 * kPatchBoxW + q0], t1 = ctr[r1 * kPatchBoxW + q1];
         byte |= (uint32_t)(t0 < t1) << k;
     }
     desc[((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
@@ -1016,7 +1118,7 @@ static size_t qt_smem_bytes(int maxa) {
 
 static void release_resources(adb_orb* h) {
     for (auto& l : h->lv) {
-        cudaFree(l.img); cudaFree(l.mask); cudaFree(l.xtab); cudaFree(l.ytab);
+        cudaFree(l.img); cudaFree(l.mask); cudaFree(l.blur); cudaFree(l.xtab); cudaFree(l.ytab);
     }
     cudaFree(h->mask_stage);
     if (h->copy_stream) {
@@ -1062,6 +1164,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     }
     int cell_base = 0, cand_base = 0, list_base = 0, maxq = 0;
     std::vector<uint32_t> cell_table;
+    int max_box_h = 1, max_wcell = 1;
     for (int l = 0; l < nl; ++l) {
         LevelDev& d = h->lv[l].d;
         d.w = round_even_f((float)W * inv[l]);
@@ -1084,6 +1187,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         d.box_w = (15 + d.wcell + 6 + 15) & ~15; d.box_h = d.hcell + 6;
         ADB_CHECK(d.box_w <= kCellBoxWMax && d.box_h <= kCellBoxHMax, ADB_ERR_INVALID, "level %d: cell box %dx%d too large", l, d.box_w, d.box_h);
         h->cell_box_w = std::max(h->cell_box_w, d.box_w <= 64 ? 64 : kCellBoxWMax);
+        max_box_h = std::max(max_box_h, d.box_h); max_wcell = std::max(max_wcell, d.wcell);
         ADB_CHECK(d.nrows < 4096 && d.ncols < 4096 && d.w < 4096 && d.h < 4096, ADB_ERR_INVALID, "image too large (max 4095 px per side)");
         d.slotcap = ((d.wcell + 1) / 2) * ((d.hcell + 1) / 2);
         d.cand_base = cand_base; d.cand_cap = d.ncells * d.slotcap;
@@ -1162,15 +1266,38 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     ADB_CUDA(cudaMemset(h->d_counts, 0, (size_t)B * 4));
     ADB_CUDA(cudaMallocHost(&h->h_counts, (size_t)B * 4));
     ADB_CUDA(cudaMallocHost(&h->h_status, 4));
+    // blurred pyramid (always the handle's own buffers, level 0 included) and its descriptor-patch boxes
+    for (int l = 0; l < nl; ++l) {
+        const LevelDev& d = h->lv[l].d;
+        const size_t bp = (size_t)((d.w + 15) & ~15);
+        ADB_CUDA(cudaMalloc(&h->lv[l].blur, (size_t)B * bp * d.h));
+        adb_status s = encode_tma_u8_3d(&h->blur_maps.m[l], h->lv[l].blur, d.w, d.h, B, bp, bp * d.h, kPatchBoxW, kBlBoxH);
+        if (s != ADB_OK) return s;
+        BlurLevels& bl = h->blur_levels;
+        bl.src[l] = h->lv[l].img; bl.dst[l] = h->lv[l].blur; bl.w[l] = d.w; bl.h[l] = d.h; bl.spitch[l] = d.pitch; bl.dpitch[l] = (int)bp;
+        bl.sfstride[l] = d.frame_stride; bl.dfstride[l] = (unsigned)(bp * d.h);
+        bl.ncg[l] = ((d.w + 3) / 4 + kBlGroupW - 1) / kBlGroupW;
+        bl.task_end[l] = (l ? bl.task_end[l - 1] : 0) + bl.ncg[l] * ((d.h + kBlRows - 1) / kBlRows);
+        bl.nlevels = nl; bl.ntasks = bl.task_end[l];
+    }
     // TMA descriptors for levels >= 1 (level 0 is encoded per call: it may alias the caller's buffer)
     for (int l = 1; l < nl; ++l) {
         const LevelDev& d = h->lv[l].d;
         adb_status s = encode_tma_u8_3d(&h->cell_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, h->cell_box_w, d.box_h);
         if (s != ADB_OK) return s;
-        s = encode_tma_u8_3d(&h->patch_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, kPatchBoxW, kPatchBoxH);
+        s = encode_tma_u8_3d(&h->patch_maps.m[l], h->lv[l].img, d.w, d.h, B, d.pitch, d.frame_stride, kPatchBoxW, kIcBoxH);
         if (s != ADB_OK) return s;
     }
     ADB_CUDA(cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qt_smem));
+    // warp-per-cell FAST: one TMA box per warp (the CTA-per-cell kernel stays for cells wider than kFwTiles column tiles, or ADB_FAST_CTA=1)
+    h->fast_tile_bytes = (max_box_h * h->cell_box_w + 127) & ~127;
+    {
+        const char* e = getenv("ADB_FAST_CTA");
+        h->fast_warp_ok = max_wcell <= kFwTiles * kFwStep + 2 && !(e && *e == '1');
+        const int bytes = h->fast_tile_bytes * kFwWarps + 128;
+        if (h->cell_box_w == 64) ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        else ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<kCellBoxWMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
     ADB_CUDA(cudaFuncSetAttribute(orient_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem) + 128));
     return ADB_OK;
 }
@@ -1228,7 +1355,7 @@ static adb_status run_pipeline(adb_orb* h, int n, const uint8_t* l0, int l0_pitc
         const LevelDev& d = h->lv[0].d;
         adb_status s = encode_tma_u8_3d(&h->cell_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, h->cell_box_w, d.box_h);
         if (s != ADB_OK) return s;
-        s = encode_tma_u8_3d(&h->patch_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, kPatchBoxW, kPatchBoxH);
+        s = encode_tma_u8_3d(&h->patch_maps.m[0], l0, d.w, d.h, n, l0_pitch, l0_fstride, kPatchBoxW, kIcBoxH);
         if (s != ADB_OK) return s;
     }
     // level table with the per-call level-0 geometry
@@ -1277,9 +1404,17 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
     for (int l = 0; l < kMaxLevels; ++l) mp.p[l] = (masked && l < nl) ? h->lv[l].mask : nullptr;
     if (h->ncells_total > 0) {
         dim3 grid(h->ncells_total, n);
-        auto kern = h->cell_box_w == 64 ? fast_cells_kernel<64> : fast_cells_kernel<kCellBoxWMax>;
-        kern<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
-                                            h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, f0);
+        if (h->fast_warp_ok) {
+            dim3 wgrid((h->ncells_total + kFwWarps - 1) / kFwWarps, n);
+            auto kern = h->cell_box_w == 64 ? fast_cells_warp_kernel<64> : fast_cells_warp_kernel<kCellBoxWMax>;
+            kern<<<wgrid, kFwWarps * 32, h->fast_tile_bytes * kFwWarps + 128, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast,
+                                                                                   h->cfg.min_th_fast, h->d_cand, h->cand_total, h->d_cellcnt,
+                                                                                   h->ncells_total, h->fast_tile_bytes, f0);
+        } else {
+            auto kern = h->cell_box_w == 64 ? fast_cells_kernel<64> : fast_cells_kernel<kCellBoxWMax>;
+            kern<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
+                                                h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, f0);
+        }
         ADB_STAGE("fast_cells");
     }
     // ---- quad-tree
@@ -1290,10 +1425,18 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
                                                              h->d_listcnt, h->qt_maxa, h->d_status, f0);
         ADB_STAGE("quadtree");
     }
+    // ---- GaussianBlur of every level (the reference: once per level before the descriptors, src/ORBextractor.cc:1099-1100), one launch
+    {
+        BlurLevels bl = h->blur_levels;
+        bl.src[0] = l0; bl.spitch[0] = h->lv[0].d.pitch; bl.sfstride[0] = h->lv[0].d.frame_stride;
+        dim3 grid((bl.ntasks + 3) / 4, n);
+        blur7_level_kernel<<<grid, 128, 0, st>>>(bl, f0);
+    }
+    h->launches += 1;
     // ---- orientation + descriptors
     {
         dim3 grid((h->capacity + kDescWarps - 1) / kDescWarps, n);
-        orient_describe_kernel<<<grid, kDescWarps * 32, sizeof(DescSmem) + 128, st>>>(h->patch_maps, h->d_levels, nl, h->d_list, h->list_total,
+        orient_describe_kernel<<<grid, kDescWarps * 32, sizeof(DescSmem) + 128, st>>>(h->patch_maps, h->blur_maps, h->d_levels, nl, h->d_list, h->list_total,
                                                                                      h->d_listcnt, h->d_pattern, h->d_kps, h->d_desc,
                                                                                      h->d_counts, h->capacity, h->gather, f0);
         ADB_STAGE("orient_describe");

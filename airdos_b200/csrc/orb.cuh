@@ -35,10 +35,19 @@ struct LevelDev {
     int box_w, box_h;        // FAST cell TMA box
 };
 
+struct BlurLevels {                       // all levels in ONE launch: warp tasks are numbered level by level
+    const uint8_t* src[kMaxLevels];
+    uint8_t* dst[kMaxLevels];
+    int w[kMaxLevels], h[kMaxLevels], spitch[kMaxLevels], dpitch[kMaxLevels], ncg[kMaxLevels], task_end[kMaxLevels];
+    unsigned sfstride[kMaxLevels], dfstride[kMaxLevels];
+    int nlevels, ntasks;
+};
+
 struct LevelHost {
     LevelDev d;
     uint8_t* img = nullptr;    // [max_batch][h][pitch]   (level 0: internal staging copy)
     uint8_t* mask = nullptr;   // same layout, allocated on first masked call
+    uint8_t* blur = nullptr;   // GaussianBlur 7x7 of the level, [max_batch][h][(w + 15) & ~15] (always the handle's own buffer)
     int2* xtab = nullptr;      // resize tables for producing this level from level-1: {src index, a0 | a1 << 16}
     int2* ytab = nullptr;
     bool strip_ok = false;     // pyr_resize_strip_kernel applies (scale factor <= 2)
@@ -52,6 +61,8 @@ struct adb_orb {
     int capacity = 0;               // key-points per frame
     int ncells_total = 0;
     int cell_box_w = 64;                // shared-memory pitch of the FAST cell box (64 or kCellBoxWMax), one per handle
+    int fast_tile_bytes = 0;            // warp-per-cell FAST: bytes of one warp's TMA box (largest level), a multiple of 128
+    bool fast_warp_ok = false;
     int cand_total = 0;             // u32 entries per frame
     int list_total = 0;             // entries per frame
     int qt_maxa = 0;                // quad-tree node capacity
@@ -96,6 +107,8 @@ struct adb_orb {
     int last_frames = 0;
     adb::TmaMaps16 cell_maps;    // FAST cell boxes
     adb::TmaMaps16 patch_maps;   // descriptor patches
+    adb::TmaMaps16 blur_maps;    // the same boxes of the blurred levels
+    adb::BlurLevels blur_levels = {};   // geometry of the one-launch level blur
     // profiling: CUDA events on the handle's stream around each stage of the last call
     adb_gather_targets gather = {};   // peer buffers the descriptor kernel also writes to (n = 0: off)
     bool profiling = false;
