@@ -236,6 +236,24 @@ __device__ __forceinline__ void load_ring_packed(const uint8_t* c, int bw, uint3
 #undef ADB_Q
 }
 
+// The same from a 32-bit shared-memory address (warp-per-cell kernel: one register per pointer); a = (256 + v) | (256 - v) << 16 by one IMAD.
+template <int kOff>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
+    return v;
+}
+template <int bw>
+__device__ __forceinline__ void load_ring_packed_s(uint32_t c, uint32_t (&x)[16]) {
+    const uint32_t a = lds_u8<0>(c) * 0xFFFF0001u + 0x01000100u;
+#define ADB_Q(off) (lds_u8<(off)>(c) * 0xFFFFu + a)
+    x[0] = ADB_Q(3 * bw);      x[1] = ADB_Q(3 * bw + 1);  x[2] = ADB_Q(2 * bw + 2);   x[3] = ADB_Q(bw + 3);
+    x[4] = ADB_Q(3);           x[5] = ADB_Q(-bw + 3);     x[6] = ADB_Q(-2 * bw + 2);  x[7] = ADB_Q(-3 * bw + 1);
+    x[8] = ADB_Q(-3 * bw);     x[9] = ADB_Q(-3 * bw - 1); x[10] = ADB_Q(-2 * bw - 2); x[11] = ADB_Q(-bw - 3);
+    x[12] = ADB_Q(-3);         x[13] = ADB_Q(bw - 3);     x[14] = ADB_Q(2 * bw - 2);  x[15] = ADB_Q(3 * bw - 1);
+#undef ADB_Q
+}
+
 // Exact score: max over the 16 arcs of 9 of min(v - q) and of min(q - v) (cv::cornerScore<16>), again both
 // polarities at once: a = (256 + v) | (256 - v) << 16 makes the lanes 256 + d and 256 - d, and the arc minima / the
 // final maximum are packed 3-input min / max (VIMNMX3.U16x2): 40 of them per pixel.
@@ -382,18 +400,22 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
 // Per 32 pixels: 17 LDS + 17 IMAD + 41 packed min / max for the score, ~25 instructions for everything else (the CTA-per-cell
 // kernel: ~170 on top of the score).
 constexpr int kFwWarps = 8, kFwTiles = 3, kFwStep = 30;   // column tiles advance by 30: 32 lanes minus the two halo lanes
-template <int kBW>
-__global__ void __launch_bounds__(kFwWarps * 32) fast_cells_warp_kernel(const __grid_constant__ TmaMaps16 maps,
+// NT = column tiles per row step: the cells of levels whose cells fit one tile (<= 32 columns) run the NT = 1 instance, the others the
+// NT = kFwTiles one (two launches over the two halves of the cell order list).
+template <int kBW, int NT>
+__global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_warp_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                         const LevelDev* __restrict__ levels,
-                                                                        const uint32_t* __restrict__ cell_table, const __grid_constant__ MaskPtrs masks,
+                                                                        const uint32_t* __restrict__ cell_table, const uint32_t* __restrict__ cell_order,
+                                                                        int order_count, const __grid_constant__ MaskPtrs masks,
                                                                         int ini_th, int min_th, uint32_t* __restrict__ cand,
                                                                         int cand_total, uint16_t* __restrict__ cellcnt,
                                                                         int ncells_total, int tile_bytes, int f0) {
     extern __shared__ __align__(128) uint8_t fw_smem[];
     __shared__ uint64_t bars[kFwWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y + f0;
-    const int cell = blockIdx.x * kFwWarps + warp;
-    if (cell >= ncells_total) return;
+    const int oi = blockIdx.x * kFwWarps + warp;
+    if (oi >= order_count) return;
+    const int cell = (int)__ldg(&cell_order[oi]);
     uint8_t* tile = fw_smem + ((128u - (smem_u32(fw_smem) & 127u)) & 127u) + (size_t)warp * tile_bytes;
     uint64_t* bar = &bars[warp];
     const uint32_t ce = __ldg(&cell_table[cell]);
@@ -417,58 +439,63 @@ __global__ void __launch_bounds__(kFwWarps * 32) fast_cells_warp_kernel(const __
     }
     __syncwarp();
     const int iw = cw - 6, ih = ch - 6;
-    const int nt = max(1, (iw + 27) / kFwStep);                              // tiles start at columns 0, 30, 60; a tile decides lanes 1 .. 30
-    const int t_low = min(ini_th, min_th);                                     // (+ lane 0 of the first, lane 31 when it is the last column)
+    const int nt = NT == 1 ? 1 : max(1, (iw + 27) / kFwStep);   // tiles start at columns 0, 30, 60; a tile decides lanes 1 .. 30
+    const int t_low = min(ini_th, min_th);                       // (+ lane 0 of the first, lane 31 when it is the last column)
     const uint8_t* ml = masks.p[level];
     if (ml) ml += (size_t)f * L.mframe_stride + (size_t)(iniY + 3) * L.mpitch + iniX + 3;
     uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(cell - L.cell_base) * L.slotcap;
-    const int slotcap = L.slotcap, mpitch = L.mpitch;
-    const uint32_t rec0 = (uint32_t)(3 + cj * L.wcell) | ((uint32_t)(3 + ci * L.hcell) << 12);   // record of the cell's first inner pixel
+    uint32_t* slot_back = slot + L.slotcap - 1;
+    const int mpitch = L.mpitch;
+    uint32_t rec = ((uint32_t)(3 + cj * L.wcell + lane) | ((uint32_t)(3 + ci * L.hcell) << 12)) - (1u << 12);   // record of (row -1, this lane's column of tile 0)
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t sA[kFwTiles], sB[kFwTiles];      // scores of rows y - 2, y - 1 of this lane's column, per tile
-    bool decide[kFwTiles];
-    const uint8_t* cp[kFwTiles];
+    uint32_t sA[NT], sB[NT];                  // scores of rows y - 2, y - 1 of this lane's column, per tile
+    bool decide[NT];
+    uint32_t cp[NT];                          // shared-memory address of the centre pixel
 #pragma unroll
-    for (int t = 0; t < kFwTiles; ++t) {
+    for (int t = 0; t < NT; ++t) {
         sA[t] = 0; sB[t] = 0;
         const int col = t * kFwStep + lane;
         decide[t] = t < nt && col < iw && (lane > 0 || t == 0) && (lane < 31 || col == iw - 1);
-        cp[t] = tile + 3 * kBW + (iniX & 15) + 3 + min(col, iw - 1);
+        cp[t] = smem_u32(tile) + 3 * kBW + (iniX & 15) + 3 + min(col, iw - 1);
     }
     int cntA = 0, cntB = 0;
-    mbar_wait(bar, 0);
-    for (int y = 0; y <= ih; ++y) {
-#pragma unroll
-        for (int t = 0; t < kFwTiles; ++t) {
-            if (t > 0 && t >= nt) break;
-            uint32_t s = 0;
-            if (y < ih) {
-                const uint8_t* c = cp[t];
-                uint32_t ring[16];
-                load_ring_packed(c, kBW, (uint32_t)c[0] * 0xFFFF0001u + 0x01000100u, ring);   // (256 + v) | (256 - v) << 16
-                const int best = fast_best(ring);
-                s = (t * kFwStep + lane < iw && best > t_low) ? (uint32_t)(best - 1) : 0u;   // response = best - 1 (>= 1 for every corner)
-                cp[t] = c + kBW;
-            }
-            // strict 3 x 3 NMS of row y - 1
-            const uint32_t v = sB[t];
-            const uint32_t c3 = max(max(sA[t], v), s);
-            uint32_t cl = __shfl_up_sync(0xFFFFFFFFu, c3, 1), cr = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
-            if (lane == 0) cl = 0;
-            if (lane == 31) cr = 0;
-            bool keep = decide[t] && v > max(max(cl, cr), max(sA[t], s));
-            sA[t] = v; sB[t] = s;
-            if (__any_sync(0xFFFFFFFFu, keep)) {
-                const int col = t * kFwStep + lane;
-                if (keep && ml) keep = ml[(size_t)(y - 1) * mpitch + col] != 0;
-                const bool isA = keep && (int)v >= ini_th, isB = keep && !isA && (int)v >= min_th;
-                const uint32_t balA = __ballot_sync(0xFFFFFFFFu, isA), balB = __ballot_sync(0xFFFFFFFFu, isB);
-                const uint32_t rec = (rec0 + (uint32_t)col + ((uint32_t)(y - 1) << 12)) | (v << 24);
-                if (isA) slot[cntA + __popc(balA & lt)] = rec;
-                if (isB) slot[slotcap - 1 - cntB - __popc(balB & lt)] = rec;
-                cntA += __popc(balA); cntB += __popc(balB);
-            }
+    // NMS of the row above the one just scored (s = its scores; all zero for the flush step) and ordered emission of the kept corners
+    auto nms_emit = [&](const int t, const uint32_t s, const int yr) {
+        const uint32_t v = sB[t];
+        const uint32_t c3 = max(max(sA[t], v), s);
+        uint32_t cl = __shfl_up_sync(0xFFFFFFFFu, c3, 1), cr = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
+        if (lane == 0) cl = 0;
+        if (lane == 31) cr = 0;
+        bool keep = decide[t] && v > max(max(cl, cr), max(sA[t], s));
+        sA[t] = v; sB[t] = s;
+        if (__any_sync(0xFFFFFFFFu, keep)) {
+            if (ml) { if (keep) keep = ml[(size_t)yr * mpitch + t * kFwStep + lane] != 0; }
+            const bool isA = keep && (int)v >= ini_th, isB = keep && !isA && (int)v >= min_th;
+            const uint32_t balA = __ballot_sync(0xFFFFFFFFu, isA), balB = __ballot_sync(0xFFFFFFFFu, isB);
+            const uint32_t r = (rec + (uint32_t)(t * kFwStep)) | (v << 24);
+            if (isA) slot[cntA + __popc(balA & lt)] = r;
+            if (isB) slot_back[-(cntB + __popc(balB & lt))] = r;
+            cntA += __popc(balA); cntB += __popc(balB);
         }
+    };
+    mbar_wait(bar, 0);
+    for (int y = 0; y < ih; ++y) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (t > 0 && t >= nt) break;
+            uint32_t ring[16];
+            load_ring_packed_s<kBW>(cp[t], ring);
+            const int best = fast_best(ring);
+            const uint32_t s = (t * kFwStep + lane < iw && best > t_low) ? (uint32_t)(best - 1) : 0u;   // response = best - 1 (>= 1 for every corner)
+            cp[t] += kBW;
+            nms_emit(t, s, y - 1);
+        }
+        rec += 1u << 12;
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        if (t > 0 && t >= nt) break;
+        nms_emit(t, 0u, ih - 1);
     }
     if (lane == 0) *cnt_out = (uint16_t)(cntA ? cntA : (cntB ? (cntB | 0x8000) : 0));
 }
@@ -1236,6 +1263,14 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     for (int l = 0; l < nl; ++l) ld[l] = h->lv[l].d;
     ADB_CUDA(cudaMalloc(&h->d_levels, nl * sizeof(LevelDev)));
     ADB_CUDA(cudaMemcpy(h->d_levels, ld.data(), nl * sizeof(LevelDev), cudaMemcpyHostToDevice));
+    // cell order of the warp-per-cell FAST kernel: the cells of single-tile levels (<= 32 columns) first, then the wide ones
+    {
+        std::vector<uint32_t> narrow, wide;
+        for (size_t c = 0; c < cell_table.size(); ++c) (h->lv[cell_table[c] >> 24].d.wcell <= 32 ? narrow : wide).push_back((uint32_t)c);
+        h->n_narrow_cells = (int)narrow.size();
+        cell_table.insert(cell_table.end(), narrow.begin(), narrow.end());
+        cell_table.insert(cell_table.end(), wide.begin(), wide.end());
+    }
     ADB_CUDA(cudaMalloc(&h->d_cell_table, std::max<size_t>(cell_table.size(), 1) * 4));
     if (!cell_table.empty()) ADB_CUDA(cudaMemcpy(h->d_cell_table, cell_table.data(), cell_table.size() * 4, cudaMemcpyHostToDevice));
     {
@@ -1295,8 +1330,13 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         const char* e = getenv("ADB_FAST_CTA");
         h->fast_warp_ok = max_wcell <= kFwTiles * kFwStep + 2 && !(e && *e == '1');
         const int bytes = h->fast_tile_bytes * kFwWarps + 128;
-        if (h->cell_box_w == 64) ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        else ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<kCellBoxWMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (h->cell_box_w == 64) {
+            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<64, kFwTiles>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        } else {
+            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<kCellBoxWMax, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<kCellBoxWMax, kFwTiles>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
     }
     ADB_CUDA(cudaFuncSetAttribute(orient_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem) + 128));
     return ADB_OK;
@@ -1405,11 +1445,22 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
     if (h->ncells_total > 0) {
         dim3 grid(h->ncells_total, n);
         if (h->fast_warp_ok) {
-            dim3 wgrid((h->ncells_total + kFwWarps - 1) / kFwWarps, n);
-            auto kern = h->cell_box_w == 64 ? fast_cells_warp_kernel<64> : fast_cells_warp_kernel<kCellBoxWMax>;
-            kern<<<wgrid, kFwWarps * 32, h->fast_tile_bytes * kFwWarps + 128, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast,
-                                                                                   h->cfg.min_th_fast, h->d_cand, h->cand_total, h->d_cellcnt,
-                                                                                   h->ncells_total, h->fast_tile_bytes, f0);
+            const int nn = h->n_narrow_cells, nw = h->ncells_total - nn;
+            const uint32_t* order = h->d_cell_table + h->ncells_total;
+            const size_t smem = (size_t)h->fast_tile_bytes * kFwWarps + 128;
+            if (nn) {
+                dim3 wgrid((nn + kFwWarps - 1) / kFwWarps, n);
+                auto kern = h->cell_box_w == 64 ? fast_cells_warp_kernel<64, 1> : fast_cells_warp_kernel<kCellBoxWMax, 1>;
+                kern<<<wgrid, kFwWarps * 32, smem, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, order, nn, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
+                                                        h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, h->fast_tile_bytes, f0);
+            }
+            if (nw) {
+                dim3 wgrid((nw + kFwWarps - 1) / kFwWarps, n);
+                auto kern = h->cell_box_w == 64 ? fast_cells_warp_kernel<64, kFwTiles> : fast_cells_warp_kernel<kCellBoxWMax, kFwTiles>;
+                kern<<<wgrid, kFwWarps * 32, smem, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, order + nn, nw, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
+                                                        h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, h->fast_tile_bytes, f0);
+                h->launches += nn ? 1 : 0;
+            }
         } else {
             auto kern = h->cell_box_w == 64 ? fast_cells_kernel<64> : fast_cells_kernel<kCellBoxWMax>;
             kern<<<grid, kFastThreads, 0, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,

@@ -63,6 +63,7 @@ struct adb_orb {
     int cell_box_w = 64;                // shared-memory pitch of the FAST cell box (64 or kCellBoxWMax), one per handle
     int fast_tile_bytes = 0;            // warp-per-cell FAST: bytes of one warp's TMA box (largest level), a multiple of 128
     bool fast_warp_ok = false;
+    int n_narrow_cells = 0;             // d_cell_table[ncells_total ..]: cell order of the warp kernel, this many single-tile cells first
     int cand_total = 0;             // u32 entries per frame
     int list_total = 0;             // entries per frame
     int qt_maxa = 0;                // quad-tree node capacity
@@ -77,7 +78,7 @@ struct adb_orb {
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // chunked host-buffer calls: upload / download streams
     cudaEvent_t cev[17] = {};                                  // [0..7] chunk uploaded, [8..15] chunk computed, [16] entry fence
     adb::LevelDev* d_levels = nullptr;
-    uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col
+    uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col, then [ncells_total] the warp kernel's cell order
     int8_t* d_pattern = nullptr;        // [16][32][2] rBRIEF points, lane-major
     uint32_t* d_cand = nullptr;         // [max_batch][cand_total] per-cell slots
     uint16_t* d_cellcnt = nullptr;      // [max_batch][ncells_total]
