@@ -258,7 +258,13 @@ __device__ __forceinline__ void load_ring_packed_s(uint32_t c, uint32_t (&x)[16]
 // polarities at once: a = (256 + v) | (256 - v) << 16 makes the lanes 256 + d and 256 - d, and the arc minima / the
 // final maximum are packed 3-input min / max (VIMNMX3.U16x2): 40 of them per pixel.
 __device__ __forceinline__ uint32_t fast_score_a(int v) { return (uint32_t)(256 + v) | ((uint32_t)(256 - v) << 16); }
+__device__ __forceinline__ uint32_t fast_best_packed(const uint32_t (&x)[16]);
 __device__ __forceinline__ int fast_best(const uint32_t (&x)[16]) {
+    const uint32_t r0 = fast_best_packed(x);
+    return (int)max(r0 & 0xFFFFu, r0 >> 16) - 256;
+}
+// both polarities, still packed: max over the 16 arcs of the arc minimum, + 256 in each 16-bit lane
+__device__ __forceinline__ uint32_t fast_best_packed(const uint32_t (&x)[16]) {
     uint32_t m3[16], m9[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) m3[i] = __vimin3_u16x2(x[i], x[(i + 1) & 15], x[(i + 2) & 15]);
@@ -269,8 +275,7 @@ __device__ __forceinline__ int fast_best(const uint32_t (&x)[16]) {
     uint32_t r4 = __vimax3_u16x2(m9[12], m9[13], m9[14]);
     r0 = __vimax3_u16x2(r0, r1, r2);
     r3 = __vimax3_u16x2(r3, r4, m9[15]);
-    r0 = __vmaxu2(r0, r3);
-    return (int)max(r0 & 0xFFFFu, r0 >> 16) - 256;
+    return __vmaxu2(r0, r3);
 }
 
 constexpr int kFastThreads = 256;
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
 constexpr int kFwWarps = 8, kFwTiles = 3, kFwStep = 30;   // column tiles advance by 30: 32 lanes minus the two halo lanes
 // NT = column tiles per row step: the cells of levels whose cells fit one tile (<= 32 columns) run the NT = 1 instance, the others the
 // NT = kFwTiles one (two launches over the two halves of the cell order list).
-template <int kBW, int NT>
+template <int kBW, int NT, bool kMasked>
 __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_warp_kernel(const __grid_constant__ TmaMaps16 maps,
                                                                         const LevelDev* __restrict__ levels,
                                                                         const uint32_t* __restrict__ cell_table, const uint32_t* __restrict__ cell_order,
@@ -440,42 +445,47 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
     __syncwarp();
     const int iw = cw - 6, ih = ch - 6;
     const int nt = NT == 1 ? 1 : max(1, (iw + 27) / kFwStep);   // tiles start at columns 0, 30, 60; a tile decides lanes 1 .. 30
-    const int t_low = min(ini_th, min_th);                       // (+ lane 0 of the first, lane 31 when it is the last column)
+                                                                 // (+ lane 0 of the first, lane 31 when it is the last column)
+    // Scores live in the "z domain": z = 256 + best, clamped from below to zlow = 256 + min(iniTh, minTh) -- every non-corner, every
+    // pixel outside the cell and the rows above / below it hold exactly zlow, so a corner (z > zlow) that beats its 8 neighbours is
+    // what the reference keeps, and the response is z - 257.
+    const uint32_t zlow = 256u + (uint32_t)min(ini_th, min_th), zini = 257u + (uint32_t)ini_th;
+    const bool has_b = min_th < ini_th;                          // else every corner already passes iniTh
     const uint8_t* ml = masks.p[level];
-    if (ml) ml += (size_t)f * L.mframe_stride + (size_t)(iniY + 3) * L.mpitch + iniX + 3;
-    uint32_t* slot = cand + (size_t)f * cand_total + L.cand_base + (size_t)(cell - L.cell_base) * L.slotcap;
-    uint32_t* slot_back = slot + L.slotcap - 1;
+    if (kMasked) ml += (size_t)f * L.mframe_stride + (size_t)(iniY + 3) * L.mpitch + iniX + 3 + lane;
     const int mpitch = L.mpitch;
-    uint32_t rec = ((uint32_t)(3 + cj * L.wcell + lane) | ((uint32_t)(3 + ci * L.hcell) << 12)) - (1u << 12);   // record of (row -1, this lane's column of tile 0)
+    const uint32_t slot0 = (uint32_t)((size_t)f * cand_total) + (uint32_t)L.cand_base + (uint32_t)(cell - L.cell_base) * (uint32_t)L.slotcap;   // < 2^32: checked at creation
+    uint32_t idxA = slot0, idxB = slot0 + (uint32_t)L.slotcap - 1u;   // next free entry of the front (iniTh) / back (minTh only) list
+    const uint32_t rec0 = ((uint32_t)(3 + cj * L.wcell + lane) | ((uint32_t)(3 + ci * L.hcell) << 12)) - (257u << 24);   // + (row << 12) + (z << 24)
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t sA[NT], sB[NT];                  // scores of rows y - 2, y - 1 of this lane's column, per tile
+    uint32_t zA[NT], zB[NT], zcap[NT];        // scores of rows y - 2, y - 1 of this lane's column, per tile
     bool decide[NT];
     uint32_t cp[NT];                          // shared-memory address of the centre pixel
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-        sA[t] = 0; sB[t] = 0;
+        zA[t] = zlow; zB[t] = zlow;
         const int col = t * kFwStep + lane;
         decide[t] = t < nt && col < iw && (lane > 0 || t == 0) && (lane < 31 || col == iw - 1);
+        zcap[t] = col < iw ? 0xFFFFu : zlow;
         cp[t] = smem_u32(tile) + 3 * kBW + (iniX & 15) + 3 + min(col, iw - 1);
     }
-    int cntA = 0, cntB = 0;
-    // NMS of the row above the one just scored (s = its scores; all zero for the flush step) and ordered emission of the kept corners
-    auto nms_emit = [&](const int t, const uint32_t s, const int yr) {
-        const uint32_t v = sB[t];
-        const uint32_t c3 = max(max(sA[t], v), s);
+    // NMS of the row above the one just scored (z = its scores; zlow for the flush step) and ordered emission of the kept corners
+    auto nms_emit = [&](const int t, const uint32_t z, const int yr) {
+        const uint32_t v = zB[t], vert = max(zA[t], z);
+        const uint32_t c3 = max(vert, v);
         uint32_t cl = __shfl_up_sync(0xFFFFFFFFu, c3, 1), cr = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
         if (lane == 0) cl = 0;
         if (lane == 31) cr = 0;
-        bool keep = decide[t] && v > max(max(cl, cr), max(sA[t], s));
-        sA[t] = v; sB[t] = s;
-        if (__any_sync(0xFFFFFFFFu, keep)) {
-            if (ml) { if (keep) keep = ml[(size_t)yr * mpitch + t * kFwStep + lane] != 0; }
-            const bool isA = keep && (int)v >= ini_th, isB = keep && !isA && (int)v >= min_th;
-            const uint32_t balA = __ballot_sync(0xFFFFFFFFu, isA), balB = __ballot_sync(0xFFFFFFFFu, isB);
-            const uint32_t r = (rec + (uint32_t)(t * kFwStep)) | (v << 24);
-            if (isA) slot[cntA + __popc(balA & lt)] = r;
-            if (isB) slot_back[-(cntB + __popc(balB & lt))] = r;
-            cntA += __popc(balA); cntB += __popc(balB);
+        bool keep = decide[t] && v > max(max(cl, cr), vert);
+        zA[t] = v; zB[t] = z;
+        if (kMasked) { if (keep) keep = ml[(size_t)yr * mpitch + t * kFwStep] != 0; }
+        const uint32_t balK = __ballot_sync(0xFFFFFFFFu, keep);
+        if (balK) {
+            const bool isA = keep && v >= zini;
+            const uint32_t balA = __ballot_sync(0xFFFFFFFFu, isA), balB = has_b ? balK & ~balA : 0u;
+            const uint32_t idx = isA ? idxA + __popc(balA & lt) : idxB - __popc(balB & lt);
+            if (keep && (isA || has_b)) cand[idx] = rec0 + (uint32_t)(t * kFwStep) + ((uint32_t)yr << 12) + (v << 24);
+            idxA += __popc(balA); idxB -= __popc(balB);
         }
     };
     mbar_wait(bar, 0);
@@ -485,19 +495,29 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
             if (t > 0 && t >= nt) break;
             uint32_t ring[16];
             load_ring_packed_s<kBW>(cp[t], ring);
-            const int best = fast_best(ring);
-            const uint32_t s = (t * kFwStep + lane < iw && best > t_low) ? (uint32_t)(best - 1) : 0u;   // response = best - 1 (>= 1 for every corner)
+            const uint32_t r = fast_best_packed(ring);
+            const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[t]);
             cp[t] += kBW;
-            nms_emit(t, s, y - 1);
+            nms_emit(t, z, y - 1);
         }
-        rec += 1u << 12;
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         if (t > 0 && t >= nt) break;
-        nms_emit(t, 0u, ih - 1);
+        nms_emit(t, zlow, ih - 1);
     }
+    const int cntA = (int)(idxA - slot0), cntB = (int)(slot0 + (uint32_t)L.slotcap - 1u - idxB);
     if (lane == 0) *cnt_out = (uint16_t)(cntA ? cntA : (cntB ? (cntB | 0x8000) : 0));
+}
+
+using FwKernel = void (*)(const TmaMaps16, const LevelDev*, const uint32_t*, const uint32_t*, int, const MaskPtrs, int, int, uint32_t*, int, uint16_t*, int, int, int);
+static FwKernel fw_kernel(int box_w, int nt, bool masked) {
+    if (box_w == 64) {
+        if (nt == 1) return masked ? fast_cells_warp_kernel<64, 1, true> : fast_cells_warp_kernel<64, 1, false>;
+        return masked ? fast_cells_warp_kernel<64, kFwTiles, true> : fast_cells_warp_kernel<64, kFwTiles, false>;
+    }
+    if (nt == 1) return masked ? fast_cells_warp_kernel<kCellBoxWMax, 1, true> : fast_cells_warp_kernel<kCellBoxWMax, 1, false>;
+    return masked ? fast_cells_warp_kernel<kCellBoxWMax, kFwTiles, true> : fast_cells_warp_kernel<kCellBoxWMax, kFwTiles, false>;
 }
 
 // =========================================================================================
@@ -1285,6 +1305,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         ADB_CUDA(cudaMalloc(&h->d_pattern, 1024));
         ADB_CUDA(cudaMemcpy(h->d_pattern, pat.data(), 1024, cudaMemcpyHostToDevice));
     }
+    ADB_CHECK((unsigned long long)B * h->cand_total < (1ull << 32), ADB_ERR_INVALID, "max_batch x candidate slots exceeds 2^32 entries (%d x %d)", B, h->cand_total);
     const size_t cb = (size_t)B * h->cand_total * 4;
     ADB_CUDA(cudaMalloc(&h->d_cand, cb));
     ADB_CUDA(cudaMalloc(&h->d_qkeys, cb));
@@ -1330,13 +1351,9 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         const char* e = getenv("ADB_FAST_CTA");
         h->fast_warp_ok = max_wcell <= kFwTiles * kFwStep + 2 && !(e && *e == '1');
         const int bytes = h->fast_tile_bytes * kFwWarps + 128;
-        if (h->cell_box_w == 64) {
-            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<64, kFwTiles>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        } else {
-            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<kCellBoxWMax, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            ADB_CUDA(cudaFuncSetAttribute(fast_cells_warp_kernel<kCellBoxWMax, kFwTiles>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        }
+        for (auto k : {fw_kernel(h->cell_box_w, 1, false), fw_kernel(h->cell_box_w, 1, true), fw_kernel(h->cell_box_w, kFwTiles, false),
+                       fw_kernel(h->cell_box_w, kFwTiles, true)})
+            ADB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
     ADB_CUDA(cudaFuncSetAttribute(orient_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem) + 128));
     return ADB_OK;
@@ -1450,13 +1467,13 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
             const size_t smem = (size_t)h->fast_tile_bytes * kFwWarps + 128;
             if (nn) {
                 dim3 wgrid((nn + kFwWarps - 1) / kFwWarps, n);
-                auto kern = h->cell_box_w == 64 ? fast_cells_warp_kernel<64, 1> : fast_cells_warp_kernel<kCellBoxWMax, 1>;
+                auto kern = fw_kernel(h->cell_box_w, 1, masked);
                 kern<<<wgrid, kFwWarps * 32, smem, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, order, nn, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
                                                         h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, h->fast_tile_bytes, f0);
             }
             if (nw) {
                 dim3 wgrid((nw + kFwWarps - 1) / kFwWarps, n);
-                auto kern = h->cell_box_w == 64 ? fast_cells_warp_kernel<64, kFwTiles> : fast_cells_warp_kernel<kCellBoxWMax, kFwTiles>;
+                auto kern = fw_kernel(h->cell_box_w, kFwTiles, masked);
                 kern<<<wgrid, kFwWarps * 32, smem, st>>>(h->cell_maps, h->d_levels, h->d_cell_table, order + nn, nw, mp, h->cfg.ini_th_fast, h->cfg.min_th_fast,
                                                         h->d_cand, h->cand_total, h->d_cellcnt, h->ncells_total, h->fast_tile_bytes, f0);
                 h->launches += nn ? 1 : 0;
