@@ -875,13 +875,74 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
 // symmetric: 3 adds + 4 multiply-adds per lane pair), the four 16-bit column sums of the word go to the neighbours by shuffles, the
 // row pass is DP2A on the packed sums, one word store per lane and row.  BORDER_REFLECT_101: rows by the row index; the left edge on
 // the column SUMS (the column pass is per column, so S(-k) = S(k)); words that reach over the right edge are assembled byte-wise.
-constexpr int kBlRows = 32, kBlGroupW = 30, kBlAhead = 8;
+constexpr int kBlRows = 42, kBlGroupW = 30;   // 42 output rows = 6 groups of 7 (the window rotates through 7 register slots)
 __device__ __forceinline__ int reflect101_any(int p, int len) {   // halo lanes may hang far over the right edge of a small level
     if (len == 1) return 0;
     while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
     return p;
 }
-__global__ void __launch_bounds__(128) blur7_level_kernel(const __grid_constant__ BlurLevels B, int f0) {
+// kInterior: every input row of the strip lies inside the level and the lane's word is a full aligned word -> rows are pitch steps.
+// The row loop runs in groups of 7 (the window rotates through 7 register slots, so inside a group every slot index is static);
+// the 7 loads of the next group are in flight while a group is computed.
+template <bool kInterior>
+__device__ __forceinline__ void blur7_strip(const uint8_t* __restrict__ sp, int spitch, int w, int h, int y0, int nrows, int wi, int lw,
+                                            bool bytewise, uint8_t* __restrict__ dp, int dpitch, bool store) {
+    const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
+    int bx[4];                                             // byte-wise path: the four (reflected) columns of this lane's word
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bx[k] = kInterior ? 0 : reflect101_any(min(4 * lw + k, w + 6), w);
+    const int last_in = nrows + 5;                         // last input row the strip needs
+    auto load_row = [&](int i) -> uint32_t {               // input row i of the strip (row y0 - 3 + i of the level, reflected)
+        int yy = y0 - 3 + min(i, last_in);
+        if (!kInterior) {
+            yy = yy < 0 ? -yy : (yy >= h ? 2 * (h - 1) - yy : yy);
+            yy = min(max(yy, 0), h - 1);                   // (levels of fewer than 4 rows cannot occur; keeps the load in bounds)
+        }
+        const uint8_t* rowp = sp + (size_t)yy * spitch;
+        if (kInterior || !bytewise) return __ldg(reinterpret_cast<const uint32_t*>(rowp) + lw);
+        return (uint32_t)__ldg(rowp + bx[0]) | ((uint32_t)__ldg(rowp + bx[1]) << 8) | ((uint32_t)__ldg(rowp + bx[2]) << 16) | ((uint32_t)__ldg(rowp + bx[3]) << 24);
+    };
+    uint32_t we[7], wo[7], pre[7];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {                          // rows 0 .. 5 fill slots 0 .. 5
+        const uint32_t wv = load_row(j);
+        we[j] = wv & 0x00FF00FFu; wo[j] = (wv >> 8) & 0x00FF00FFu;
+    }
+    we[6] = 0; wo[6] = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pre[j] = load_row(6 + j);
+#pragma unroll 1
+    for (int g0 = 0; g0 < nrows; g0 += 7) {                // output rows g0 .. g0 + 6 from input rows g0 + 6 .. g0 + 12
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            constexpr int kNone = 0;
+            const int sl = (6 + j) % 7 + kNone;            // slot of the newest row; slot (sl - k) mod 7 = the row k above it
+            const uint32_t wv = pre[j];
+            pre[j] = load_row(g0 + 13 + j);
+            we[sl] = wv & 0x00FF00FFu; wo[sl] = (wv >> 8) & 0x00FF00FFu;
+            const uint32_t lo = 18u * (we[(sl + 1) % 7] + we[sl]) + 34u * (we[(sl + 2) % 7] + we[(sl + 6) % 7]) + 48u * (we[(sl + 3) % 7] + we[(sl + 5) % 7]) +
+                                56u * we[(sl + 4) % 7];   // column sums of pixels 0, 2
+            const uint32_t hi = 18u * (wo[(sl + 1) % 7] + wo[sl]) + 34u * (wo[(sl + 2) % 7] + wo[(sl + 6) % 7]) + 48u * (wo[(sl + 3) % 7] + wo[(sl + 5) % 7]) +
+                                56u * wo[(sl + 4) % 7];   // pixels 1, 3
+            const uint32_t w2 = __byte_perm(lo, hi, 0x5410), w3 = __byte_perm(lo, hi, 0x7632);   // [S0, S1], [S2, S3]
+            uint32_t w0 = __shfl_up_sync(0xFFFFFFFFu, w2, 1), w1 = __shfl_up_sync(0xFFFFFFFFu, w3, 1);
+            const uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w2, 1), w5 = __shfl_down_sync(0xFFFFFFFFu, w3, 1);
+            if (wi == 0) { w0 = w3; w1 = __byte_perm(w2, w3, 0x3254); }      // S(-3) = S3 (upper half), [S(-2), S(-1)] = [S2, S1]
+            const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16), s2 = __funnelshift_r(w2, w3, 16),
+                           s3 = __funnelshift_r(w3, w4, 16), s4 = __funnelshift_r(w4, w5, 16);
+            const uint32_t v0 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 32768u))));
+            const uint32_t v1 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 32768u))));
+            const uint32_t v2 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 32768u))));
+            const uint32_t v3 = __dp2a_hi(w5, kw1, __dp2a_lo(w4, kw1, __dp2a_hi(w3, kw0, __dp2a_lo(w2, kw0, 32768u))));
+            // (v + 2^15) >> 16 = byte 2 of each sum (< 2^24): two PRMTs pick them
+            const uint32_t packed = __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410);
+            const int yo = g0 + j;
+            if (store && yo < nrows) *reinterpret_cast<uint32_t*>(dp + (size_t)yo * dpitch) = packed;   // the pitch is padded to 16 B: a ragged last word fits
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 8) blur7_level_kernel(const __grid_constant__ BlurLevels B, int f0) {
     const int lane = threadIdx.x & 31;
     int task = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (task >= B.ntasks) return;
@@ -893,53 +954,14 @@ __global__ void __launch_bounds__(128) blur7_level_kernel(const __grid_constant_
     const int wi = g * kBlGroupW - 1 + lane;               // this lane's word: pixels 4 wi .. 4 wi + 3
     const int y0 = strip * kBlRows, nrows = min(kBlRows, h - y0);
     const uint8_t* sp = B.src[l] + (size_t)f * B.sfstride[l];
-    const int fullwords = w >> 2;
     const bool aligned = (((uintptr_t)sp | (uintptr_t)spitch) & 3) == 0;
-    const bool bytewise = wi >= fullwords || !aligned;     // right edge (reflected bytes) or a caller buffer without word alignment
+    const bool bytewise = wi >= (w >> 2) || !aligned;      // right edge (reflected bytes) or a caller buffer without word alignment
     const int lw = max(wi, 0);
-    const uint32_t kw0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), kw1 = 48u | (34u << 8) | (18u << 16);
-    int bx[4];                                             // byte-wise path: the four (reflected) columns of this lane's word
-#pragma unroll
-    for (int k = 0; k < 4; ++k) bx[k] = reflect101_any(min(4 * lw + k, w + 6), w);
-    uint8_t* dp = B.dst[l] + (size_t)f * B.dfstride[l] + 4 * lw;     // destination: the handle's own buffer, word aligned
+    uint8_t* dp = B.dst[l] + (size_t)f * B.dfstride[l] + (size_t)y0 * dpitch + 4 * lw;   // destination: the handle's own buffer, word aligned
     const bool store = lane >= 1 && lane <= kBlGroupW && 4 * wi < w;
-    auto load_row = [&](int i) -> uint32_t {               // input row i of the strip (row y0 - 3 + i of the level, reflected)
-        int yy = y0 - 3 + i;
-        yy = yy < 0 ? -yy : (yy >= h ? 2 * (h - 1) - yy : yy);
-        yy = min(max(yy, 0), h - 1);                       // (levels of fewer than 4 rows cannot occur; keeps the load in bounds)
-        const uint8_t* rowp = sp + (size_t)yy * spitch;
-        if (!bytewise) return __ldg(reinterpret_cast<const uint32_t*>(rowp) + lw);
-        return (uint32_t)__ldg(rowp + bx[0]) | ((uint32_t)__ldg(rowp + bx[1]) << 8) | ((uint32_t)__ldg(rowp + bx[2]) << 16) | ((uint32_t)__ldg(rowp + bx[3]) << 24);
-    };
-    uint32_t we[7], wo[7], pre[kBlAhead];                  // kBlAhead rows are in flight ahead of the one being consumed
-#pragma unroll
-    for (int k = 0; k < kBlAhead; ++k) pre[k] = load_row(min(k, nrows + 5));
-#pragma unroll
-    for (int i = 0; i < kBlRows + 6; ++i) {
-        if (i >= nrows + 6) break;
-        const uint32_t wv = pre[i % kBlAhead];
-        if (i + kBlAhead < kBlRows + 6) pre[i % kBlAhead] = load_row(min(i + kBlAhead, nrows + 5));
-#pragma unroll
-        for (int t = 0; t < 6; ++t) { we[t] = we[t + 1]; wo[t] = wo[t + 1]; }
-        we[6] = wv & 0x00FF00FFu; wo[6] = (wv >> 8) & 0x00FF00FFu;
-        if (i >= 6) {
-            const uint32_t lo = 18u * (we[0] + we[6]) + 34u * (we[1] + we[5]) + 48u * (we[2] + we[4]) + 56u * we[3];   // sums of pixels 0, 2
-            const uint32_t hi = 18u * (wo[0] + wo[6]) + 34u * (wo[1] + wo[5]) + 48u * (wo[2] + wo[4]) + 56u * wo[3];   // pixels 1, 3
-            const uint32_t w2 = __byte_perm(lo, hi, 0x5410), w3 = __byte_perm(lo, hi, 0x7632);   // [S0, S1], [S2, S3]
-            uint32_t w0 = __shfl_up_sync(0xFFFFFFFFu, w2, 1), w1 = __shfl_up_sync(0xFFFFFFFFu, w3, 1);
-            const uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w2, 1), w5 = __shfl_down_sync(0xFFFFFFFFu, w3, 1);
-            if (wi == 0) { w0 = w3; w1 = __byte_perm(w2, w3, 0x3254); }      // S(-3) = S3 (upper half), [S(-2), S(-1)] = [S2, S1]
-            const uint32_t s0 = __funnelshift_r(w0, w1, 16), s1 = __funnelshift_r(w1, w2, 16), s2 = __funnelshift_r(w2, w3, 16),
-                           s3 = __funnelshift_r(w3, w4, 16), s4 = __funnelshift_r(w4, w5, 16);
-            const uint32_t v0 = __dp2a_hi(s3, kw1, __dp2a_lo(s2, kw1, __dp2a_hi(s1, kw0, __dp2a_lo(s0, kw0, 32768u))));
-            const uint32_t v1 = __dp2a_hi(w4, kw1, __dp2a_lo(w3, kw1, __dp2a_hi(w2, kw0, __dp2a_lo(w1, kw0, 32768u))));
-            const uint32_t v2 = __dp2a_hi(s4, kw1, __dp2a_lo(s3, kw1, __dp2a_hi(s2, kw0, __dp2a_lo(s1, kw0, 32768u))));
-            const uint32_t v3 = __dp2a_hi(w5, kw1, __dp2a_lo(w4, kw1, __dp2a_hi(w3, kw0, __dp2a_lo(w2, kw0, 32768u))));
-            // bytes 2 of v0 .. v3 (sums < 2^24): two PRMTs pick them
-            const uint32_t packed = __byte_perm(__byte_perm(v0, v1, 0x0062), __byte_perm(v2, v3, 0x0062), 0x5410);
-            if (store) *reinterpret_cast<uint32_t*>(dp + (size_t)(y0 + i - 6) * dpitch) = packed;   // the pitch is padded to 16 B: a ragged last word fits
-        }
-    }
+    const bool interior = y0 >= 3 && y0 + kBlRows + 3 <= h && aligned && (g + 1) * kBlGroupW + 1 <= (w >> 2);   // warp-uniform
+    if (interior) blur7_strip<true>(sp, spitch, w, h, y0, nrows, wi, lw, false, dp, dpitch, store);
+    else blur7_strip<false>(sp, spitch, w, h, y0, nrows, wi, lw, bytewise, dp, dpitch, store);
 }
 
 constexpr int kDescWarps = 8;
@@ -1006,7 +1028,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
                                                                          const LevelDev* __restrict__ levels, int nlevels,
                                                                          const uint32_t* __restrict__ list, int list_total,
                                                                          const int32_t* __restrict__ listcnt,
-                                                                         const int8_t* __restrict__ pattern,
+                                                                         const float4* __restrict__ pattern,
                                                                          adb_keypoint* __restrict__ kps,
                                                                          uint8_t* __restrict__ desc,
                                                                          int32_t* __restrict__ counts, int cap,
@@ -1032,11 +1054,16 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     __syncthreads();
 
     const int i = blockIdx.x * kDescWarps + warp;
-    int base = 0, lvl = -1, total = 0;
-    for (int l = 0; l < nlevels; ++l) {
-        const int c = listcnt[f * nlevels + l];
-        if (lvl < 0 && i < total + c) { lvl = l; base = total; }
-        total += c;
+    // level of key-point i: the per-level counts of the frame, one per lane, prefix-summed by shuffles
+    int base, lvl, total;
+    {
+        const int c = lane < nlevels ? listcnt[f * nlevels + lane] : 0;
+        const int incl = warp_incl_scan(c, lane);
+        const uint32_t below = __ballot_sync(0xFFFFFFFFu, lane < nlevels && i >= incl);   // levels that end at or before i (a prefix of the lanes)
+        lvl = __popc(below);
+        base = lvl ? __shfl_sync(0xFFFFFFFFu, incl, (lvl - 1) & 31) : 0;
+        total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (lvl >= nlevels) lvl = -1;
     }
     if (i == 0 && lane == 0) {
         counts[f] = total;
@@ -1093,12 +1120,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
     const uint8_t* ctr = blr0 + dxp + kBlR * kPatchBoxW + kPatchR;   // the key-point inside the blurred box (row 18, patch column 21)
-    const char2* pat2 = reinterpret_cast<const char2*>(pattern);
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const char2 p0 = __ldg(pat2 + (2 * k) * 32 + lane), p1 = __ldg(pat2 + (2 * k + 1) * 32 + lane);   // 1 KB, L1 resident
-        const float x0f = (float)p0.x, y0f = (float)p0.y, x1f = (float)p1.x, y1f = (float)p1.y;
+        const float4 pt = __ldg(pattern + k * 32 + lane);   // 4 KB, L1 resident
+        const float x0f = pt.x, y0f = pt.y, x1f = pt.z, y1f = pt.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0f, b), __fmul_rn(y0f, a)));
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0f, a), __fmul_rn(y0f, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1f, b), __fmul_rn(y1f, a)));
@@ -1296,14 +1322,15 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     {
         static const signed char px[512] = AIRDOS_ORB_PATTERN_X;
         static const signed char py[512] = AIRDOS_ORB_PATTERN_Y;
-        std::vector<int8_t> pat(1024);
-        for (int s = 0; s < 16; ++s)
-            for (int lane = 0; lane < 32; ++lane) {
-                pat[2 * (s * 32 + lane)] = px[16 * lane + s];
-                pat[2 * (s * 32 + lane) + 1] = py[16 * lane + s];
-            }
-        ADB_CUDA(cudaMalloc(&h->d_pattern, 1024));
-        ADB_CUDA(cudaMemcpy(h->d_pattern, pat.data(), 1024, cudaMemcpyHostToDevice));
+        std::vector<float> pat(8 * 32 * 4);     // test k of descriptor byte `lane`: {x0, y0, x1, y1} as floats (one 16-byte load per test)
+        for (int k = 0; k < 8; ++k)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int e = 0; e < 2; ++e) {
+                    pat[4 * (k * 32 + lane) + 2 * e] = (float)px[16 * lane + 2 * k + e];
+                    pat[4 * (k * 32 + lane) + 2 * e + 1] = (float)py[16 * lane + 2 * k + e];
+                }
+        ADB_CUDA(cudaMalloc(&h->d_pattern, pat.size() * 4));
+        ADB_CUDA(cudaMemcpy(h->d_pattern, pat.data(), pat.size() * 4, cudaMemcpyHostToDevice));
     }
     ADB_CHECK((unsigned long long)B * h->cand_total < (1ull << 32), ADB_ERR_INVALID, "max_batch x candidate slots exceeds 2^32 entries (%d x %d)", B, h->cand_total);
     const size_t cb = (size_t)B * h->cand_total * 4;

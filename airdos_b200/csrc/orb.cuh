@@ -79,7 +79,7 @@ struct adb_orb {
     cudaEvent_t cev[17] = {};                                  // [0..7] chunk uploaded, [8..15] chunk computed, [16] entry fence
     adb::LevelDev* d_levels = nullptr;
     uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col, then [ncells_total] the warp kernel's cell order
-    int8_t* d_pattern = nullptr;        // [16][32][2] rBRIEF points, lane-major
+    float4* d_pattern = nullptr;        // [8][32] rBRIEF tests as floats {x0, y0, x1, y1}, lane-major
     uint32_t* d_cand = nullptr;         // [max_batch][cand_total] per-cell slots
     uint16_t* d_cellcnt = nullptr;      // [max_batch][ncells_total]
     uint32_t* d_qkeys = nullptr;        // [max_batch][cand_total] gathered candidates (reference order)
