@@ -29,11 +29,13 @@ assert len(ins) == len(lines_of), (len(ins), len(lines_of))
 per = collections.Counter(); tot = 0; perop = collections.Counter()
 for r, ln in zip(ins, lines_of):
     n = int(r[ie]); per[ln] += n; tot += n; perop[r[isrc].split()[0] if not r[isrc].strip().startswith('@') else r[isrc].split()[1]] += n
-src = open("/root/repo/airdos_b200/csrc/orb.cu").read().splitlines()
+import os
+srcname = os.environ.get("SRC", "orb.cu")
+src = open("/root/repo/airdos_b200/csrc/" + srcname).read().splitlines()
 print("total warp-instructions", tot)
 for ln, n in per.most_common(top):
     fn, k = ln if ln else ("?", 0)
-    print(f"{n:>12} {100*n/tot:5.1f}%  {fn}:{k:5d}: {src[k-1].strip()[:120] if fn == 'orb.cu' and 0 < k <= len(src) else ''}")
+    print(f"{n:>12} {100*n/tot:5.1f}%  {fn}:{k:5d}: {src[k-1].strip()[:120] if fn == srcname and 0 < k <= len(src) else ''}")
 print("by opcode:")
 for op, n in perop.most_common(25):
     print(f"{n:>12} {100*n/tot:5.1f}%  {op}")
