@@ -77,28 +77,25 @@ __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __
     const int t = blockIdx.x * 128 + threadIdx.x;
     if (t >= nq * nchunks) return;
     const int chunk = t / nq, q = t - chunk * nq, f = blockIdx.y + f0;
-    uint32_t sel[4], a0[4], a1[4];
+    uint32_t sel[4], ac[4];
     const int base = __ldg(&xtab[4 * q]).x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int2 cx = __ldg(&xtab[min(4 * q + k, dw - 1)]);
         const int o0 = cx.x - base, o1 = min(cx.x + 1, sw - 1) - base;   // <= 7 (checked on the host)
         sel[k] = (uint32_t)(o0 | (o1 << 4));
-        a0[k] = (uint32_t)cx.y & 0xFFFFu; a1[k] = (uint32_t)cx.y >> 16;
+        ac[k] = (uint32_t)cx.y;                                          // a0 | a1 << 16: the two 16-bit operands of one DP2A
     }
     const int maxw = (spitch >> 2) - 1;
     const int w0i = base >> 2, w1i = min(w0i + 1, maxw), w2i = min(w0i + 2, maxw);
     const uint32_t sft = (uint32_t)(base & 3) * 8u;
     const uint8_t* sf = src + (size_t)f * sfstride;
-    auto hrow = [&](int sy, uint32_t (&H)[4]) {   // (S[sx0] * a0 + S[sx1] * a1) >> 4 for the 4 columns
+    auto hrow = [&](int sy, uint32_t (&H)[4]) {   // (S[sx0] * a0 + S[sx1] * a1) >> 4 for the 4 columns: PRMT puts the two neighbours in bytes 0, 1
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(sf + (size_t)sy * spitch);
         const uint32_t w0 = __ldg(sp + w0i), w1 = __ldg(sp + w1i), w2 = __ldg(sp + w2i);
         const uint32_t W0 = __funnelshift_r(w0, w1, sft), W1 = __funnelshift_r(w1, w2, sft);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t T = __byte_perm(W0, W1, sel[k]);
-            H[k] = ((T & 0xFFu) * a0[k] + ((T >> 8) & 0xFFu) * a1[k]) >> 4;
-        }
+        for (int k = 0; k < 4; ++k) H[k] = __dp2a_lo(ac[k], __byte_perm(W0, W1, sel[k]), 0u) >> 4;
     };
     uint32_t A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0};
     int ia = -1, ib = -1;
@@ -107,7 +104,7 @@ __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __
     for (int y = chunk * rows; y < y_end; ++y) {
         const int2 cy = __ldg(&ytab[y]);
         const int sy0 = cy.x, sy1 = min(sy0 + 1, sh - 1);
-        const uint32_t b0 = (uint32_t)cy.y & 0xFFFFu, b1 = (uint32_t)cy.y >> 16;
+        const uint32_t b0s = (uint32_t)cy.y << 16, b1s = (uint32_t)cy.y & 0xFFFF0000u;   // (b * r) >> 16 = umulhi(b << 16, r)
         if (sy0 != ia) {
             if (sy0 == ib) {
 #pragma unroll
@@ -122,13 +119,10 @@ __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __
             } else hrow(sy1, B);
             ib = sy1;
         }
-        uint32_t out = 0;
+        uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t v = (((b0 * A[k]) >> 16) + ((b1 * B[k]) >> 16) + 2u) >> 2;
-            out |= (v & 0xFFu) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(dp + (size_t)y * dpitch) = out;
+        for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b1s, B[k]) + (__umulhi(b0s, A[k]) + 2u)) >> 2;   // <= 255
+        *reinterpret_cast<uint32_t*>(dp + (size_t)y * dpitch) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
     }
 }
 
@@ -1528,6 +1522,7 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
         bl.src[0] = l0; bl.spitch[0] = h->lv[0].d.pitch; bl.sfstride[0] = h->lv[0].d.frame_stride;
         dim3 grid((bl.ntasks + 3) / 4, n);
         blur7_level_kernel<<<grid, 128, 0, st>>>(bl, f0);
+        ADB_STAGE("blur7_level");
     }
     h->launches += 1;
     // ---- orientation + descriptors
@@ -1673,12 +1668,12 @@ adb_status adb_orb_profile(adb_orb_t h, int32_t enable) {
     return ADB_OK;
 }
 
-adb_status adb_orb_stage_ms(adb_orb_t h, float* ms4) {
-    ADB_CHECK(h && ms4, ADB_ERR_INVALID, "null argument");
-    ADB_CHECK(h->profiling && h->pev_n == 5, ADB_ERR_INVALID, "no profiled call recorded (enable adb_orb_profile, then extract)");
+adb_status adb_orb_stage_ms(adb_orb_t h, float* ms5) {
+    ADB_CHECK(h && ms5, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK(h->profiling && h->pev_n == 6, ADB_ERR_INVALID, "no profiled call recorded (enable adb_orb_profile, then extract)");
     ADB_CUDA(cudaSetDevice(h->cfg.device));
-    ADB_CUDA(cudaEventSynchronize(h->pev[4]));
-    for (int i = 0; i < 4; ++i) ADB_CUDA(cudaEventElapsedTime(&ms4[i], h->pev[i], h->pev[i + 1]));
+    ADB_CUDA(cudaEventSynchronize(h->pev[5]));
+    for (int i = 0; i < 5; ++i) ADB_CUDA(cudaEventElapsedTime(&ms5[i], h->pev[i], h->pev[i + 1]));
     return ADB_OK;
 }
 

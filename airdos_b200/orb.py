@@ -155,8 +155,8 @@ class ORBextractor:
         check(lib().adb_orb_profile(self._h, int(enable)))
 
     def stage_ms(self):
-        """Device ms of the last profiled call: (pyramid, fast_cells, quadtree, orient_describe)."""
-        ms = (C.c_float * 4)()
+        """Device ms of the last profiled call: (pyramid, fast_cells, quadtree, blur7_level, orient_describe)."""
+        ms = (C.c_float * 5)()
         check(lib().adb_orb_stage_ms(self._h, ms))
         return tuple(ms)
 

@@ -111,11 +111,11 @@ adb_status adb_orb_sync(adb_orb_t h);
 void* adb_orb_stream(adb_orb_t h); /* cudaStream_t of the handle */
 
 /* Measurement hooks.  adb_orb_profile(h, 1) makes every following extract call record CUDA events
- * on the handle's stream around its four stages; adb_orb_stage_ms then returns the device time
- * of the last call's stages {pyramid, FAST cells, quad-tree, orientation + descriptors} in ms.
+ * on the handle's stream around its five stages; adb_orb_stage_ms then returns the device time
+ * of the last call's stages {pyramid, FAST cells, quad-tree, level blur, orientation + descriptors} in ms.
  * adb_orb_launch_count = kernels this handle has launched since it was created. */
 adb_status adb_orb_profile(adb_orb_t h, int32_t enable);
-adb_status adb_orb_stage_ms(adb_orb_t h, float* ms4);
+adb_status adb_orb_stage_ms(adb_orb_t h, float* ms5);
 int64_t adb_orb_launch_count(adb_orb_t h);
 
 /* Multi-GPU fusion of the descriptor all-gather (BASELINE configs[2]) into the extraction: besides its own result

@@ -11,7 +11,7 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/$
 timeout 300 python tools/chol_bench.py > gpurun_out/${TAG}_chol_vs_cusolver.jsonl 2>> gpurun_out/${TAG}_bench.err; echo "chol rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "list rc=$?"
-timeout 900 ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:'fast_cells|pyr_resize|orient_describe|quadtree|stereo_|erode' -s 60 -c 24 \
+timeout 900 ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:'fast_cells|pyr_resize|orient_describe|quadtree|stereo_|erode|blur7' -s 66 -c 28 \
   -f -o gpurun_out/${TAG}_orb python bench.py --steps 1 --warmup 3 --pairs 128 --no-cpu-baseline --no-ba > gpurun_out/${TAG}_ncu_orb.log 2>&1; echo "orb rc=$?"
 timeout 900 ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:'ba_|chol_|lm_|schur_' -s 120 -c 36 \
   -f -o gpurun_out/${TAG}_ba python bench_ba.py > gpurun_out/${TAG}_ncu_ba.log 2>&1; echo "ba rc=$?"
