@@ -200,37 +200,43 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
             const uint8_t* IL = S.L + (size_t)f * S.fstrideL;
             const uint8_t* IR = S.R + (size_t)f * S.fstrideR;
             const int cL = IL[(size_t)cy * S.pitchL + cxL];
-            int pl[4], py[4], px[4];
+            // lane owns window pixels p = lane + 32 k (121 = 11 x 11): its left value once, and ONE pointer per pixel into the right image
+            // at shift 0 -- the 11 shifts are then immediate byte offsets of the same pointer
+            int pl[4];
+            const uint8_t* pr[4];
+            const uint8_t* rc = IR + (size_t)cy * S.pitchR + cxR0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int p = lane + 32 * k;
-                py[k] = p / 11 - w; px[k] = p % 11 - w;
-                pl[k] = p < 121 ? (int)IL[(size_t)(cy + py[k]) * S.pitchL + cxL + px[k]] - cL : 0;
+                const int py = p / 11 - w, px = p % 11 - w;
+                const bool in = p < 121;
+                pl[k] = in ? (int)IL[(ptrdiff_t)(cy + py) * S.pitchL + cxL + px] - cL : 0;
+                pr[k] = in ? rc + (ptrdiff_t)py * S.pitchR + px : rc;   // outside the window: the centre itself, |0 - (cR - cR)| = 0
             }
-            int bestSad = INT_MAX, bestinc = 0;
-            float dists[11];
+            // per-lane partial SADs of the 11 shifts, two per register (a lane's share is <= 4 x 510, the total <= 121 x 510 < 2^16)
+            uint32_t pk[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int inc = -5; inc <= 5; ++inc) {
-                const int cxR = cxR0 + inc;
-                const int cR = IR[(size_t)cy * S.pitchR + cxR];
+                const int cR = rc[inc];
                 int acc = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (lane + 32 * k < 121) {
-                        const int b = (int)IR[(size_t)(cy + py[k]) * S.pitchR + cxR + px[k]] - cR;
-                        acc += abs(pl[k] - b);
-                    }
-                }
+                for (int k = 0; k < 4; ++k) acc += abs(pl[k] - ((int)pr[k][inc] - cR));
+                pk[(inc + 5) >> 1] += (uint32_t)acc << (((inc + 5) & 1) * 16);
+            }
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
+            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) pk[j] += __shfl_xor_sync(0xFFFFFFFFu, pk[j], s);
+            int bestSad = INT_MAX, bestinc = 0, mine = 0;        // lane l < 11 also keeps the SAD of shift l - 5 for the parabola
+#pragma unroll
+            for (int inc = -5; inc <= 5; ++inc) {
+                const int acc = (int)((pk[(inc + 5) >> 1] >> (((inc + 5) & 1) * 16)) & 0xFFFFu);
                 if (acc < bestSad) { bestSad = acc; bestinc = inc; }
-                dists[inc + 5] = (float)acc;
+                if (lane == inc + 5) mine = acc;
             }
             if (bestinc != -Ls && bestinc != Ls) {
-                float d1 = 0, d2 = 0, d3 = 0;
-#pragma unroll
-                for (int k = 1; k < 10; ++k)
-                    if (k == bestinc + 5) { d1 = dists[k - 1]; d2 = dists[k]; d3 = dists[k + 1]; }
+                const float d1 = (float)__shfl_sync(0xFFFFFFFFu, mine, bestinc + 4), d2 = (float)bestSad,
+                            d3 = (float)__shfl_sync(0xFFFFFFFFu, mine, bestinc + 6);
                 const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
                 if (!(deltaR < -1 || deltaR > 1)) {
                     float bestuR = __fmul_rn(S.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));

@@ -70,10 +70,15 @@ __global__ void __launch_bounds__(128) pyr_resize_kernel(const uint8_t* __restri
 // interpolated ~1.2 times per output row instead of 2 and no byte-wide loads are issued.
 // (Measured dead ends: 8 columns per thread and prefetching the next source row one output row ahead both left the stage at
 // 0.17 ms per 128 frames -- the seven dependent launches, not the per-pixel work, set the time of the small levels.)
+// kMask: the mask pyramid (src/ORBextractor.cc:1146-1147: the same resize of the eroded mask) rides along in the same threads: tables,
+// selectors, row bookkeeping and the loop are shared, only the loads and the interpolation are done twice.
+template <bool kMask>
 __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                                size_t sfstride, uint8_t* __restrict__ dst, int dw, int dh,
                                                                int dpitch, size_t dfstride, const int2* __restrict__ xtab,
-                                                               const int2* __restrict__ ytab, int nq, int rows, int nchunks, int f0) {
+                                                               const int2* __restrict__ ytab, int nq, int rows, int nchunks, int f0,
+                                                               const uint8_t* __restrict__ msrc, int mspitch, size_t msfstride,
+                                                               uint8_t* __restrict__ mdst, int mdpitch, size_t mdfstride) {
     const int t = blockIdx.x * 128 + threadIdx.x;
     if (t >= nq * nchunks) return;
     const int chunk = t / nq, q = t - chunk * nq, f = blockIdx.y + f0;
@@ -86,21 +91,23 @@ __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __
         sel[k] = (uint32_t)(o0 | (o1 << 4));
         ac[k] = (uint32_t)cx.y;                                          // a0 | a1 << 16: the two 16-bit operands of one DP2A
     }
-    const int maxw = (spitch >> 2) - 1;
+    const int maxw = (spitch >> 2) - 1;                                  // (the mask levels have the pitch of the image levels' own buffers or more)
     const int w0i = base >> 2, w1i = min(w0i + 1, maxw), w2i = min(w0i + 2, maxw);
     const uint32_t sft = (uint32_t)(base & 3) * 8u;
     const uint8_t* sf = src + (size_t)f * sfstride;
-    auto hrow = [&](int sy, uint32_t (&H)[4]) {   // (S[sx0] * a0 + S[sx1] * a1) >> 4 for the 4 columns: PRMT puts the two neighbours in bytes 0, 1
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(sf + (size_t)sy * spitch);
+    const uint8_t* mf = kMask ? msrc + (size_t)f * msfstride : nullptr;
+    auto hrow = [&](const uint8_t* rowp, uint32_t (&H)[4]) {   // (S[sx0] * a0 + S[sx1] * a1) >> 4 for the 4 columns: PRMT puts the two neighbours in bytes 0, 1
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(rowp);
         const uint32_t w0 = __ldg(sp + w0i), w1 = __ldg(sp + w1i), w2 = __ldg(sp + w2i);
         const uint32_t W0 = __funnelshift_r(w0, w1, sft), W1 = __funnelshift_r(w1, w2, sft);
 #pragma unroll
         for (int k = 0; k < 4; ++k) H[k] = __dp2a_lo(ac[k], __byte_perm(W0, W1, sel[k]), 0u) >> 4;
     };
-    uint32_t A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0};
+    uint32_t A[4] = {0, 0, 0, 0}, B[4] = {0, 0, 0, 0}, MA[4] = {0, 0, 0, 0}, MB[4] = {0, 0, 0, 0};
     int ia = -1, ib = -1;
     const int y_end = min(dh, (chunk + 1) * rows);
     uint8_t* dp = dst + (size_t)f * dfstride + 4 * q;
+    uint8_t* mp = kMask ? mdst + (size_t)f * mdfstride + 4 * q : nullptr;
     for (int y = chunk * rows; y < y_end; ++y) {
         const int2 cy = __ldg(&ytab[y]);
         const int sy0 = cy.x, sy1 = min(sy0 + 1, sh - 1);
@@ -108,21 +115,32 @@ __global__ void __launch_bounds__(128) pyr_resize_strip_kernel(const uint8_t* __
         if (sy0 != ia) {
             if (sy0 == ib) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) A[k] = B[k];
-            } else hrow(sy0, A);
+                for (int k = 0; k < 4; ++k) { A[k] = B[k]; if (kMask) MA[k] = MB[k]; }
+            } else {
+                hrow(sf + (size_t)sy0 * spitch, A);
+                if (kMask) hrow(mf + (size_t)sy0 * mspitch, MA);
+            }
             ia = sy0;
         }
         if (sy1 != ib) {
             if (sy1 == ia) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) B[k] = A[k];
-            } else hrow(sy1, B);
+                for (int k = 0; k < 4; ++k) { B[k] = A[k]; if (kMask) MB[k] = MA[k]; }
+            } else {
+                hrow(sf + (size_t)sy1 * spitch, B);
+                if (kMask) hrow(mf + (size_t)sy1 * mspitch, MB);
+            }
             ib = sy1;
         }
         uint32_t v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b1s, B[k]) + (__umulhi(b0s, A[k]) + 2u)) >> 2;   // <= 255
         *reinterpret_cast<uint32_t*>(dp + (size_t)y * dpitch) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        if (kMask) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (__umulhi(b1s, MB[k]) + (__umulhi(b0s, MA[k]) + 2u)) >> 2;
+            *reinterpret_cast<uint32_t*>(mp + (size_t)y * mdpitch) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        }
     }
 }
 
@@ -1452,7 +1470,7 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
     cudaStream_t st = h->stream;
     const int nl = h->nlevels;
     const uint8_t* l0 = h->l0_base;
-    h->launches += (masked ? 2 : 1) * (nl - 1) + (h->ncells_total > 0 ? 1 : 0) + 2;
+    h->launches += (nl - 1) + (h->ncells_total > 0 ? 1 : 0) + 2;   // + the mask levels that need their own launch (counted below)
     // ---- pyramid
     for (int l = 1; l < nl; ++l) {
         const LevelDev& s = h->lv[l - 1].d;
@@ -1464,16 +1482,25 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
             const int rows = std::max(4, std::min(16, (int)((long long)nq * d.h * n / 300000)));
             const int nchunks = (d.h + rows - 1) / rows;
             dim3 grid((nq * nchunks + 127) / 128, n);
-            pyr_resize_strip_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
-                                                         d.frame_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0);
-            if (masked)
-                pyr_resize_strip_kernel<<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w,
-                                                             d.h, d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0);
+            // the mask level shares the launch when its source rows are word-addressable like the image's (the handle's own buffers are)
+            const bool fuse = masked && s.mpitch >= s.pitch && (s.mpitch & 3) == 0;
+            if (fuse)
+                pyr_resize_strip_kernel<true><<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch, d.frame_stride,
+                                                                   h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0, h->lv[l - 1].mask, s.mpitch,
+                                                                   s.mframe_stride, h->lv[l].mask, d.mpitch, d.mframe_stride);
+            else
+                pyr_resize_strip_kernel<false><<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch, d.frame_stride,
+                                                                    h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0, nullptr, 0, 0, nullptr, 0, 0);
+            if (masked && !fuse) ++h->launches;
+            if (masked && !fuse)
+                pyr_resize_strip_kernel<false><<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w, d.h, d.mpitch,
+                                                                    d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, nq, rows, nchunks, f0, nullptr, 0, 0, nullptr, 0, 0);
             continue;
         }
         dim3 grid((d.pitch / 4 + 127) / 128, d.h, n);
         pyr_resize_kernel<<<grid, 128, 0, st>>>(src, s.w, s.h, s.pitch, s.frame_stride, h->lv[l].img, d.w, d.h, d.pitch,
                                                d.frame_stride, h->lv[l].xtab, h->lv[l].ytab, f0);
+        if (masked) ++h->launches;
         if (masked)
             pyr_resize_kernel<<<grid, 128, 0, st>>>(h->lv[l - 1].mask, s.w, s.h, s.mpitch, s.mframe_stride, h->lv[l].mask, d.w, d.h,
                                                    d.mpitch, d.mframe_stride, h->lv[l].xtab, h->lv[l].ytab, f0);
