@@ -23,6 +23,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "orb.cuh"
 #include "../../include/airdos_orb_pattern.h"
@@ -255,6 +256,29 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
     return v;
 }
+template <int kOff>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Ring rows of the single-tile FAST kernel: every pixel of the cell box is converted ONCE to X = q | (255 - q) << 16 (one IMAD) when
+// its row enters an 8-row ring of 32-bit words, instead of once per (centre, ring position) pair = 16 times.  The packed minimum of an
+// arc is then (min q, 255 - max q) and the centre enters only at the very end: with A = max over arcs of the low half and H of the
+// high half, 256 + score = max(A + 256 - v, H + v + 1).
+constexpr int kRingPitch = 40, kRingRows = 8;          // words per ring row (cell + 6 <= 40 columns: single-tile cells are <= 32 wide)
+template <int J>                                        // J = (inner row) mod 8: the slot of a box row is (row & 7), so all offsets are immediates
+__device__ __forceinline__ void load_ring_words(uint32_t rb, uint32_t (&x)[16]) {   // rb: ring address of this lane's centre COLUMN, slot 0
+#define ADB_R(ox, oy) lds_u32<(((J + 3 + (oy)) & 7) * kRingPitch + (ox)) * 4>(rb)
+    x[0] = ADB_R(0, 3);    x[1] = ADB_R(1, 3);    x[2] = ADB_R(2, 2);    x[3] = ADB_R(3, 1);
+    x[4] = ADB_R(3, 0);    x[5] = ADB_R(3, -1);   x[6] = ADB_R(2, -2);   x[7] = ADB_R(1, -3);
+    x[8] = ADB_R(0, -3);   x[9] = ADB_R(-1, -3);  x[10] = ADB_R(-2, -2); x[11] = ADB_R(-3, -1);
+    x[12] = ADB_R(-3, 0);  x[13] = ADB_R(-3, 1);  x[14] = ADB_R(-2, 2);  x[15] = ADB_R(-1, 3);
+#undef ADB_R
+}
+
 template <int bw>
 __device__ __forceinline__ void load_ring_packed_s(uint32_t c, uint32_t (&x)[16]) {
     const uint32_t a = lds_u8<0>(c) * 0xFFFF0001u + 0x01000100u;
@@ -418,6 +442,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
 //     cell count = "no corner at iniTh: read the back, reversed").  No rank loop, no atomics.
 // Per 32 pixels: 17 LDS + 17 IMAD + 41 packed min / max for the score, ~25 instructions for everything else (the CTA-per-cell
 // kernel: ~170 on top of the score).
+constexpr int kFwRingBytes = 8 * 40 * 4;   // = kRingRows * kRingPitch words: the ring of converted rows behind every warp's TMA box
 constexpr int kFwWarps = 8, kFwTiles = 3, kFwStep = 30;   // column tiles advance by 30: 32 lanes minus the two halo lanes
 // NT = column tiles per row step: the cells of levels whose cells fit one tile (<= 32 columns) run the NT = 1 instance, the others the
 // NT = kFwTiles one (two launches over the two halves of the cell order list).
@@ -435,7 +460,7 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
     const int oi = blockIdx.x * kFwWarps + warp;
     if (oi >= order_count) return;
     const int cell = (int)__ldg(&cell_order[oi]);
-    uint8_t* tile = fw_smem + ((128u - (smem_u32(fw_smem) & 127u)) & 127u) + (size_t)warp * tile_bytes;
+    uint8_t* tile = fw_smem + ((128u - (smem_u32(fw_smem) & 127u)) & 127u) + (size_t)warp * (tile_bytes + kFwRingBytes);
     uint64_t* bar = &bars[warp];
     const uint32_t ce = __ldg(&cell_table[cell]);
     const int level = ce >> 24, ci = (ce >> 12) & 0xFFF, cj = ce & 0xFFF;
@@ -503,16 +528,46 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
         }
     };
     mbar_wait(bar, 0);
-    for (int y = 0; y < ih; ++y) {
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            if (t > 0 && t >= nt) break;
+    if constexpr (NT == 1) {
+        // single-tile cells: rows pass through the ring of converted words (see load_ring_words)
+        const uint32_t ring0 = smem_u32(tile) + (uint32_t)tile_bytes;                       // this warp's ring, behind its TMA box
+        const uint32_t rb = ring0 + 4u * (3u + lane);                                         // centre column of this lane, slot 0
+        uint32_t rawp = smem_u32(tile) + (iniX & 15) + lane;                                  // box row 0, sub-image column `lane`
+        const bool second = lane + 32 < cw;                                                   // columns 32 .. cw - 1 (cw <= 38)
+        auto convert_row = [&](uint32_t slot_addr) {                                          // box row at rawp -> ring row at slot_addr
+            sts_u32(slot_addr + 4u * lane, lds_u8<0>(rawp) * 0xFFFF0001u + 0x00FF0000u);
+            if (second) sts_u32(slot_addr + 4u * (lane + 32), lds_u8<32>(rawp) * 0xFFFF0001u + 0x00FF0000u);
+            rawp += kBW;
+        };
+        for (int r = 0; r < 6; ++r) convert_row(ring0 + (uint32_t)r * (kRingPitch * 4));
+        auto step = [&](auto jc, const int y) {
+            constexpr int J = decltype(jc)::value;
+            convert_row(ring0 + ((J + 6) & 7) * (kRingPitch * 4));                             // box row y + 6, the last one row y needs
+            __syncwarp();
             uint32_t ring[16];
-            load_ring_packed_s<kBW>(cp[t], ring);
-            const uint32_t r = fast_best_packed(ring);
-            const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[t]);
-            cp[t] += kBW;
-            nms_emit(t, z, y - 1);
+            load_ring_words<J>(rb, ring);
+            const uint32_t v = lds_u8<((J + 3) & 7) * kRingPitch * 4>(rb);                    // low byte of the centre word
+            const uint32_t r = fast_best_packed(ring) + (v * 0xFFFFu + 0x00010100u);           // + (256 - v) | (v + 1) << 16
+            const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[0]);
+            nms_emit(0, z, y - 1);
+        };
+        for (int y0 = 0; y0 < ih; y0 += 8) {
+#define ADB_STEP(J) if (y0 + J >= ih) break; step(std::integral_constant<int, J>{}, y0 + J);
+            ADB_STEP(0) ADB_STEP(1) ADB_STEP(2) ADB_STEP(3) ADB_STEP(4) ADB_STEP(5) ADB_STEP(6) ADB_STEP(7)
+#undef ADB_STEP
+        }
+    } else {
+        for (int y = 0; y < ih; ++y) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if (t > 0 && t >= nt) break;
+                uint32_t ring[16];
+                load_ring_packed_s<kBW>(cp[t], ring);
+                const uint32_t r = fast_best_packed(ring);
+                const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[t]);
+                cp[t] += kBW;
+                nms_emit(t, z, y - 1);
+            }
         }
     }
 #pragma unroll
@@ -1391,7 +1446,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     {
         const char* e = getenv("ADB_FAST_CTA");
         h->fast_warp_ok = max_wcell <= kFwTiles * kFwStep + 2 && !(e && *e == '1');
-        const int bytes = h->fast_tile_bytes * kFwWarps + 128;
+        const int bytes = (h->fast_tile_bytes + kFwRingBytes) * kFwWarps + 128;
         for (auto k : {fw_kernel(h->cell_box_w, 1, false), fw_kernel(h->cell_box_w, 1, true), fw_kernel(h->cell_box_w, kFwTiles, false),
                        fw_kernel(h->cell_box_w, kFwTiles, true)})
             ADB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1514,7 +1569,7 @@ static adb_status run_range(adb_orb* h, int f0, int n, bool masked) {
         if (h->fast_warp_ok) {
             const int nn = h->n_narrow_cells, nw = h->ncells_total - nn;
             const uint32_t* order = h->d_cell_table + h->ncells_total;
-            const size_t smem = (size_t)h->fast_tile_bytes * kFwWarps + 128;
+            const size_t smem = (size_t)(h->fast_tile_bytes + kFwRingBytes) * kFwWarps + 128;
             if (nn) {
                 dim3 wgrid((nn + kFwWarps - 1) / kFwWarps, n);
                 auto kern = fw_kernel(h->cell_box_w, 1, masked);
