@@ -301,8 +301,10 @@ __device__ __forceinline__ int fast_best(const uint32_t (&x)[16]) {
 }
 // both polarities, still packed: max over the 16 arcs of the arc minimum, + 256 in each 16-bit lane
 __device__ __forceinline__ uint32_t fast_best_packed(const uint32_t (&x)[16]) {
-    // (Measured dead end: the arc minima by prefix / suffix minima of the two half rings -- 44 two-input minima = 44 pipe passes where
-    // these 32 three-input ones take 64 -- ran slower, 8.2 vs 7.8 ms per 2048 frames: 12 more issue slots and 16 more live registers.)
+    // (Measured dead end, twice: the arc minima by prefix / suffix minima of the two half rings (van Herk) -- 59 two-input packed
+    // min / max instead of these 39 three-input ones -- ran slower in both FAST kernels (8.2 vs 7.8 and 8.3 vs 7.5 ms per 2048 frames),
+    // also in a register-lean interleaving without spills: inside this instruction mix a two-input packed min / max costs the alu pipe
+    // what a three-input one does, whatever the isolated stream of tools/probe/pipe_probe.cu suggests.)
     uint32_t m3[16], m9[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) m3[i] = __vimin3_u16x2(x[i], x[(i + 1) & 15], x[(i + 2) & 15]);
@@ -544,9 +546,9 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
             constexpr int J = decltype(jc)::value;
             convert_row(ring0 + ((J + 6) & 7) * (kRingPitch * 4));                             // box row y + 6, the last one row y needs
             __syncwarp();
+            const uint32_t v = lds_u8<((J + 3) & 7) * kRingPitch * 4>(rb);                    // low byte of the centre word
             uint32_t ring[16];
             load_ring_words<J>(rb, ring);
-            const uint32_t v = lds_u8<((J + 3) & 7) * kRingPitch * 4>(rb);                    // low byte of the centre word
             const uint32_t r = fast_best_packed(ring) + (v * 0xFFFFu + 0x00010100u);           // + (256 - v) | (v + 1) << 16
             const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[0]);
             nms_emit(0, z, y - 1);
