@@ -264,10 +264,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-// Ring rows of the single-tile FAST kernel: every pixel of the cell box is converted ONCE to X = q | (255 - q) << 16 (one IMAD) when
-// its row enters an 8-row ring of 32-bit words, instead of once per (centre, ring position) pair = 16 times.  The packed minimum of an
-// arc is then (min q, 255 - max q) and the centre enters only at the very end: with A = max over arcs of the low half and H of the
-// high half, 256 + score = max(A + 256 - v, H + v + 1).
+// Ring rows of the single-tile FAST kernel: every pixel of the cell box is converted ONCE to X = (q + 256) | (256 - q) << 16 (one IMAD)
+// when its row enters an 8-row ring of 32-bit words, instead of once per (centre, ring position) pair = 16 times.  The packed minimum
+// of an arc is then (256 + min q, 256 - max q) and the centre enters only at the very end: with A = max over arcs of the low half and
+// H of the high half, 256 + score = max(A - v, H + v) = the halves of the packed sum (A | H << 16) + v * 0xFFFF.
 constexpr int kRingPitch = 40, kRingRows = 8;          // words per ring row (cell + 6 <= 40 columns: single-tile cells are <= 32 wide)
 template <int J>                                        // J = (inner row) mod 8: the slot of a box row is (row & 7), so all offsets are immediates
 __device__ __forceinline__ void load_ring_words(uint32_t rb, uint32_t (&x)[16]) {   // rb: ring address of this lane's centre COLUMN, slot 0
@@ -537,8 +537,8 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
         uint32_t rawp = smem_u32(tile) + (iniX & 15) + lane;                                  // box row 0, sub-image column `lane`
         const bool second = lane + 32 < cw;                                                   // columns 32 .. cw - 1 (cw <= 38)
         auto convert_row = [&](uint32_t slot_addr) {                                          // box row at rawp -> ring row at slot_addr
-            sts_u32(slot_addr + 4u * lane, lds_u8<0>(rawp) * 0xFFFF0001u + 0x00FF0000u);
-            if (second) sts_u32(slot_addr + 4u * (lane + 32), lds_u8<32>(rawp) * 0xFFFF0001u + 0x00FF0000u);
+            sts_u32(slot_addr + 4u * lane, lds_u8<0>(rawp) * 0xFFFF0001u + 0x01000100u);       // (q + 256) | (256 - q) << 16
+            if (second) sts_u32(slot_addr + 4u * (lane + 32), lds_u8<32>(rawp) * 0xFFFF0001u + 0x01000100u);
             rawp += kBW;
         };
         for (int r = 0; r < 6; ++r) convert_row(ring0 + (uint32_t)r * (kRingPitch * 4));
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
             const uint32_t v = lds_u8<((J + 3) & 7) * kRingPitch * 4>(rb);                    // low byte of the centre word
             uint32_t ring[16];
             load_ring_words<J>(rb, ring);
-            const uint32_t r = fast_best_packed(ring) + (v * 0xFFFFu + 0x00010100u);           // + (256 - v) | (v + 1) << 16
+            const uint32_t r = fast_best_packed(ring) + v * 0xFFFFu;                           // halves: A + 256 - v, (255 - B) + 1 + v
             const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[0]);
             nms_emit(0, z, y - 1);
         };
