@@ -62,6 +62,39 @@ def test_cuda_matches_oracle_batch(adb, oracle_mod, w, h, nf, ini, mn, masked):
     ex.close()
 
 
+@pytest.mark.parametrize("ini,mn", [(90, 7), (40, 7), (7, 7), (5, 9), (250, 200)])
+def test_ini_min_rule_both_ends_of_the_slot(adb, oracle_mod, ini, mn):
+    """The warp-per-cell FAST kernel writes iniTh corners from the front of a cell's slot and minTh-only corners from its back; the
+    cell count says which end holds the answer (src/ORBextractor.cc:812-824).  High iniTh: most cells fall back to minTh; iniTh ==
+    minTh and iniTh < minTh: one list only; thresholds nothing passes: empty cells."""
+    from airdos_b200 import synth
+    w, h = 640, 480
+    img = synth.make_stereo_pair(31, w, h)[0]
+    img[:, : w // 3] = (img[:, : w // 3] // 8 + 100).astype(np.uint8)          # a low-contrast third: no corner at a high iniTh
+    msk = synth.make_mask(32, w, h, 2)
+    ex = adb.ORBextractor(1500, 1.2, 8, ini, mn, w, h)
+    for m in (None, msk):
+        k, d = ex(img, m)
+        o = oracle_mod.orb_extract(img, m, 1500, 1.2, 8, ini, mn)
+        assert [len(ex.debug_candidates(0, l)) for l in range(8)] == list(o["cand_counts"])
+        assert _same(k, d, o), (ini, mn, m is not None)
+    ex.close()
+
+
+def test_cta_per_cell_fallback_kernel_agrees(adb, oracle_mod, monkeypatch):
+    """ADB_FAST_CTA=1 selects the CTA-per-cell FAST kernel (the path for cells wider than the warp kernel's three column tiles)."""
+    from airdos_b200 import synth
+    monkeypatch.setenv("ADB_FAST_CTA", "1")
+    w, h = 640, 480
+    img = synth.make_stereo_pair(33, w, h)[1]
+    msk = synth.make_mask(34, w, h, 3)
+    ex = adb.ORBextractor(1200, 1.2, 8, 20, 7, w, h)
+    for m in (None, msk):
+        k, d = ex(img, m)
+        assert _same(k, d, oracle_mod.orb_extract(img, m, 1200, 1.2, 8, 20, 7))
+    ex.close()
+
+
 def test_portrait_shapes_with_zero_roots_are_refused(adb):
     """nIni = round(w / h) = 0 (src/ORBextractor.cc:545-549) is undefined in the reference: adb_orb_create refuses the shape."""
     with pytest.raises(adb.AdbError) as e:
