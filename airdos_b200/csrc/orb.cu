@@ -1190,17 +1190,21 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     double sd, cd;
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    const uint8_t* ctr = blr0 + dxp + kBlR * kPatchBoxW + kPatchR;   // the key-point inside the blurred box (row 18, patch column 21)
+    // Rounding without the conversion unit: x + 1.5 * 2^23 has ulp 1, so the float addition IS cvRound (nearest, ties to even) and the
+    // integer sits in the low mantissa bits: bits = 0x4B400000 + round(x), negative x included.  Row * 64 + column is then formed on the
+    // raw bit patterns and the two biases are folded into the base address (F2I runs at a quarter of the FADD rate).
+    constexpr float kMagic = 12582912.f;
+    const uint32_t cbase = smem_u32(blr0) + (uint32_t)(dxp + kBlR * kPatchBoxW + kPatchR) - 65u * 0x4B400000u;   // the key-point inside the blurred box
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float4 pt = __ldg(pattern + k * 32 + lane);   // 4 KB, L1 resident
         const float x0f = pt.x, y0f = pt.y, x1f = pt.z, y1f = pt.w;
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0f, b), __fmul_rn(y0f, a)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0f, a), __fmul_rn(y0f, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1f, b), __fmul_rn(y1f, a)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1f, a), __fmul_rn(y1f, b)));
-        const int t0 = ctr[r0 * kPatchBoxW + q0], t1 = ctr[r1 * kPatchBoxW + q1];
+        const uint32_t r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(x0f, b), __fmul_rn(y0f, a)), kMagic));
+        const uint32_t q0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(x0f, a), __fmul_rn(y0f, b)), kMagic));
+        const uint32_t r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(x1f, b), __fmul_rn(y1f, a)), kMagic));
+        const uint32_t q1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(x1f, a), __fmul_rn(y1f, b)), kMagic));
+        const uint32_t t0 = lds_u8<0>(cbase + r0 * (uint32_t)kPatchBoxW + q0), t1 = lds_u8<0>(cbase + r1 * (uint32_t)kPatchBoxW + q1);
         byte |= (uint32_t)(t0 < t1) << k;
     }
     desc[((size_t)f * cap + i) * 32 + lane] = (uint8_t)byte;
