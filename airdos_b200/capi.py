@@ -100,6 +100,8 @@ SYMBOLS = {
     "adb_search_by_bow": (C.c_int, [_vp, _vp, _i32]),
     "adb_distinctive_descriptors": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "adb_stereo_match": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
+    "adb_stereo_frames_batch": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _sz, _i32, _i32, _i32, _vp, _vp, _sz, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                          _f32, _f32, _vp, _vp, _vp, _vp]),
     "adb_stereo_match_device": (C.c_int, [_vp, _vp, _i32, _f32, _f32]),
     "adb_stereo_results_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "adb_ba_default_options": (None, [_vp]),

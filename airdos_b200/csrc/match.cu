@@ -88,10 +88,10 @@ constexpr int kBucketThreads = 512;
 __global__ void __launch_bounds__(kBucketThreads) stereo_bucket_kernel(const __grid_constant__ StereoLevels lv, int n_rows,
                                                                       const adb_keypoint* __restrict__ kpsR, const int32_t* __restrict__ cntR,
                                                                       int cap, int maxband, int32_t* __restrict__ row_ptr,
-                                                                      uint16_t* __restrict__ row_items, float2* __restrict__ rinfo) {
+                                                                      uint16_t* __restrict__ row_items, float2* __restrict__ rinfo, int f0) {
     extern __shared__ int bk_smem[];     // [n_rows + 1] counts -> offsets -> cursors
     __shared__ int s_run;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int f = blockIdx.x + f0, tid = threadIdx.x, lane = tid & 31;
     const int nR = min(cntR[f], cap);
     const adb_keypoint* kR = kpsR + (size_t)f * cap;
     for (int i = tid; i <= n_rows; i += kBucketThreads) bk_smem[i] = 0;
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
     const uint8_t* __restrict__ descL, const int32_t* __restrict__ cntL, const uint8_t* __restrict__ descR, int cap, int maxband,
     const int32_t* __restrict__ row_ptr, const uint16_t* __restrict__ row_items, const float2* __restrict__ rinfo, float mbf, float maxD,
     float* __restrict__ uRight, float* __restrict__ depth, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist,
-    int32_t* __restrict__ sad_out) {
-    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t* __restrict__ sad_out, int f0) {
+    const int f = blockIdx.y + f0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nL = min(cntL[f], cap);
     const int32_t* rp = row_ptr + (size_t)f * (n_rows + 1);
     const uint16_t* items = row_items + (size_t)f * cap * maxband;
@@ -263,10 +263,10 @@ __global__ void __launch_bounds__(kStereoWarps * 32) stereo_match_kernel(
 // One CTA per frame; k-th smallest by a two-pass 256-bin radix select (SAD <= 121 * 510 < 2^16).
 __global__ void __launch_bounds__(256) stereo_median_kernel(const int32_t* __restrict__ cntL, int cap,
                                                             const int32_t* __restrict__ sad, float* __restrict__ uRight,
-                                                            float* __restrict__ depth) {
+                                                            float* __restrict__ depth, int f0) {
     __shared__ int hist[256];
     __shared__ int s_n, s_bin, s_rank;
-    const int f = blockIdx.x, tid = threadIdx.x;
+    const int f = blockIdx.x + f0, tid = threadIdx.x;
     const int nL = min(cntL[f], cap);
     const int32_t* s = sad + (size_t)f * cap;
     hist[tid] = 0;
@@ -486,14 +486,15 @@ adb_status adb_distinctive_descriptors(adb_matcher_t m, const uint8_t* desc, con
     return st;
 }
 
-adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb, float mbf) {
-    ADB_CHECK(L && R, ADB_ERR_INVALID, "null handle");
+}  // extern "C"
+
+// Stereo matching of frames [f0, f0 + n) of two handles whose results are resident, on stream `st` (the caller has ordered `st`
+// behind both extractions).  Shared by adb_stereo_match_device and the chunk pipeline of adb_stereo_frames_batch (orb.cu).
+adb_status adb_stereo_match_range(adb_orb* L, adb_orb* R, int f0, int n, float mb, float mbf, cudaStream_t st) {
     ADB_CHECK(L->cfg.device == R->cfg.device && L->nlevels == R->nlevels && L->capacity == R->capacity &&
                   L->cfg.width == R->cfg.width && L->cfg.height == R->cfg.height,
               ADB_ERR_INVALID, "left / right extractors differ in configuration");
-    ADB_CHECK(n >= 1 && n <= L->last_frames && n <= R->last_frames, ADB_ERR_INVALID, "n_frames %d exceeds the resident frames", n);
     ADB_CHECK(mb > 0.f, ADB_ERR_INVALID, "baseline must be positive");
-    ADB_CUDA(cudaSetDevice(L->cfg.device));
     const size_t per = (size_t)L->cfg.max_batch * L->capacity;
     if (!L->d_uright) {
         ADB_CUDA(cudaMalloc(&L->d_uright, per * 4));
@@ -502,9 +503,6 @@ adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb
         ADB_CUDA(cudaMalloc(&L->d_best_dist, per * 4));
         ADB_CUDA(cudaMalloc(&L->d_sad, per * 4));
     }
-    // the right extractor's stream must have finished before the left stream reads its results
-    ADB_CUDA(cudaEventRecord(R->ev, R->stream));
-    ADB_CUDA(cudaStreamWaitEvent(L->stream, R->ev, 0));
     StereoLevels sl;
     memset(&sl, 0, sizeof(sl));
     for (int l = 0; l < L->nlevels; ++l) {
@@ -530,18 +528,41 @@ adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb
         ADB_CUDA(cudaMalloc(&L->d_row_items, B * cap * maxband * 2));
         ADB_CUDA(cudaMalloc(&L->d_rinfo, B * cap * 8));
     }
-    stereo_bucket_kernel<<<n, kBucketThreads, (size_t)(n_rows + 1) * 4, L->stream>>>(sl, n_rows, R->d_kps, R->d_counts, cap, maxband, L->d_row_ptr,
-                                                                                    L->d_row_items, (float2*)L->d_rinfo);
+    stereo_bucket_kernel<<<n, kBucketThreads, (size_t)(n_rows + 1) * 4, st>>>(sl, n_rows, R->d_kps, R->d_counts, cap, maxband, L->d_row_ptr,
+                                                                             L->d_row_items, (float2*)L->d_rinfo, f0);
     ADB_CUDA(cudaGetLastError());
     dim3 grid((cap + kStereoWarps * kStereoPerWarp - 1) / (kStereoWarps * kStereoPerWarp), n);
-    stereo_match_kernel<<<grid, kStereoWarps * 32, 0, L->stream>>>(sl, n_rows, L->d_kps, L->d_desc, L->d_counts, R->d_desc, cap, maxband,
-                                                                  L->d_row_ptr, L->d_row_items, (const float2*)L->d_rinfo, mbf, maxD, L->d_uright,
-                                                                  L->d_depth, L->d_best_idx, L->d_best_dist, L->d_sad);
+    stereo_match_kernel<<<grid, kStereoWarps * 32, 0, st>>>(sl, n_rows, L->d_kps, L->d_desc, L->d_counts, R->d_desc, cap, maxband,
+                                                           L->d_row_ptr, L->d_row_items, (const float2*)L->d_rinfo, mbf, maxD, L->d_uright,
+                                                           L->d_depth, L->d_best_idx, L->d_best_dist, L->d_sad, f0);
     ADB_CUDA(cudaGetLastError());
-    stereo_median_kernel<<<n, 256, 0, L->stream>>>(L->d_counts, cap, L->d_sad, L->d_uright, L->d_depth);
+    stereo_median_kernel<<<n, 256, 0, st>>>(L->d_counts, cap, L->d_sad, L->d_uright, L->d_depth, f0);
     ADB_CUDA(cudaGetLastError());
     L->launches += 3;
     return ADB_OK;
+}
+
+// Asynchronous copy of the stereo outputs of frames [f0, f0 + n) to host arrays laid out [frame][cap] (pointers at frame 0).
+adb_status adb_stereo_download_range(adb_orb* L, int f0, int n, float* ur, float* dp, int32_t* bi, int32_t* bd, int cap, cudaStream_t st) {
+    const int rows = std::min(cap, L->capacity);
+    const size_t sp = (size_t)L->capacity * 4, dpitch = (size_t)cap * 4, so = (size_t)f0 * L->capacity, ho = (size_t)f0 * cap;
+    if (ur) ADB_CUDA(cudaMemcpy2DAsync(ur + ho, dpitch, L->d_uright + so, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, st));
+    if (dp) ADB_CUDA(cudaMemcpy2DAsync(dp + ho, dpitch, L->d_depth + so, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, st));
+    if (bi) ADB_CUDA(cudaMemcpy2DAsync(bi + ho, dpitch, L->d_best_idx + so, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, st));
+    if (bd) ADB_CUDA(cudaMemcpy2DAsync(bd + ho, dpitch, L->d_best_dist + so, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, st));
+    return ADB_OK;
+}
+
+extern "C" {
+
+adb_status adb_stereo_match_device(adb_orb_t L, adb_orb_t R, int32_t n, float mb, float mbf) {
+    ADB_CHECK(L && R, ADB_ERR_INVALID, "null handle");
+    ADB_CHECK(n >= 1 && n <= L->last_frames && n <= R->last_frames, ADB_ERR_INVALID, "n_frames %d exceeds the resident frames", n);
+    ADB_CUDA(cudaSetDevice(L->cfg.device));
+    // the right extractor's stream must have finished before the left stream reads its results
+    ADB_CUDA(cudaEventRecord(R->ev, R->stream));
+    ADB_CUDA(cudaStreamWaitEvent(L->stream, R->ev, 0));
+    return adb_stereo_match_range(L, R, 0, n, mb, mbf, L->stream);
 }
 
 adb_status adb_stereo_results_device(adb_orb_t L, const float** ur, const float** dp, const int32_t** bi, const int32_t** bd) {
@@ -558,12 +579,8 @@ adb_status adb_stereo_match(adb_orb_t L, adb_orb_t R, int32_t n, float mb, float
     ADB_CHECK(ur && dp, ADB_ERR_INVALID, "null output");
     adb_status s = adb_stereo_match_device(L, R, n, mb, mbf);
     if (s != ADB_OK) return s;
-    const int rows = std::min(cap, L->capacity);
-    const size_t sp = (size_t)L->capacity * 4, dpitch = (size_t)cap * 4;
-    ADB_CUDA(cudaMemcpy2DAsync(ur, dpitch, L->d_uright, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, L->stream));
-    ADB_CUDA(cudaMemcpy2DAsync(dp, dpitch, L->d_depth, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, L->stream));
-    if (bi) ADB_CUDA(cudaMemcpy2DAsync(bi, dpitch, L->d_best_idx, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, L->stream));
-    if (bd) ADB_CUDA(cudaMemcpy2DAsync(bd, dpitch, L->d_best_dist, sp, (size_t)rows * 4, n, cudaMemcpyDeviceToHost, L->stream));
+    s = adb_stereo_download_range(L, 0, n, ur, dp, bi, bd, cap, L->stream);
+    if (s != ADB_OK) return s;
     ADB_CUDA(cudaMemcpyAsync(L->h_counts, L->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, L->stream));
     ADB_CUDA(cudaStreamSynchronize(L->stream));
     for (int i = 0; i < n; ++i)

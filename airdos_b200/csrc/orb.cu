@@ -1272,6 +1272,8 @@ static void release_resources(adb_orb* h) {
     if (h->copy_stream) {
         cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->d2h_stream);
         for (auto& e : h->cev) if (e) cudaEventDestroy(e);
+        for (auto& e : h->sev) if (e) cudaEventDestroy(e);
+        if (h->stereo_stream) cudaStreamDestroy(h->stereo_stream);
     }
     cudaFree(h->d_levels); cudaFree(h->d_cell_table); cudaFree(h->d_pattern); cudaFree(h->d_cand); cudaFree(h->d_cellcnt);
     cudaFree(h->d_qkeys); cudaFree(h->d_qstate); cudaFree(h->d_qcount); cudaFree(h->d_list); cudaFree(h->d_listcnt);
@@ -1846,53 +1848,73 @@ adb_status adb_orb_download(adb_orb_t h, int32_t first, int32_t n, adb_keypoint*
 // Large host batches run as a pipeline of chunks: the host-to-device copy of chunk c + 1 (copy stream), the kernels of chunk c
 // (handle stream) and the device-to-host copy of chunk c - 1's results (download stream) overlap, so the call costs about
 // max(upload, compute, download) instead of their sum.  Results are identical: chunking only changes the launch ranges.
-constexpr int kChunks = 8, kMinChunkedFrames = 32;
+constexpr int kChunks = 32, kMinChunkedFrames = 32;   // 8 chunks once the batch is chunked at all, more (of >= 256 frames, at most kChunks) for very large batches
 
-static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images, size_t fstride, int w, int hh, int pitch, const uint8_t* masks,
-                                        size_t mfstride, int mpitch, adb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+static int chunk_count(int n) { return std::min(kChunks, std::max(8, n / 256)); }   // fill / drain = one chunk of upload + one of download
+
+// streams / events of the pipeline, entry fence, per-call level-0 view (no launch yet)
+static adb_status chunk_begin(adb_orb* h, int n, int w, int hh, bool masked) {
     const int p0 = (w + 15) & ~15;
-    const size_t dfs = (size_t)p0 * hh;
     if (!h->copy_stream) {
         ADB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         ADB_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2 * kChunks + 1; ++i) ADB_CUDA(cudaEventCreateWithFlags(&h->cev[i], cudaEventDisableTiming));
     }
     adb_status s = ADB_OK;
-    if (masks && (s = ensure_mask_buffers(h)) != ADB_OK) return s;
+    if (masked && (s = ensure_mask_buffers(h)) != ADB_OK) return s;
     // the upload must not overtake kernels of an earlier asynchronous call that still read the staging buffer
     ADB_CUDA(cudaEventRecord(h->cev[2 * kChunks], h->stream));
     ADB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->cev[2 * kChunks], 0));
-    s = run_pipeline(h, n, h->lv[0].img, p0, dfs, masks != nullptr, /*launch=*/false);
+    return run_pipeline(h, n, h->lv[0].img, p0, (size_t)p0 * hh, masked, /*launch=*/false);
+}
+
+// chunk c = frames [f0, f0 + nc): upload on the copy stream, kernels on the handle's stream behind it; cev[kChunks + c] = chunk computed
+static adb_status chunk_issue(adb_orb* h, int c, int f0, int nc, const uint8_t* images, size_t fstride, int w, int hh, int pitch,
+                              const uint8_t* masks, size_t mfstride, int mpitch) {
+    const int p0 = (w + 15) & ~15;
+    const size_t dfs = (size_t)p0 * hh;
+    adb_status s = copy_frames(h->lv[0].img + f0 * dfs, p0, dfs, images + f0 * fstride, pitch, fstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
     if (s != ADB_OK) return s;
-    const int per = (n + kChunks - 1) / kChunks;
-    int c = 0;
-    for (int f0 = 0; f0 < n; f0 += per, ++c) {
-        const int nc = std::min(per, n - f0);
-        s = copy_frames(h->lv[0].img + f0 * dfs, p0, dfs, images + f0 * fstride, pitch, fstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
-        if (s != ADB_OK) return s;
-        if (masks) {   // the chunk's masks ride on the same copy stream; erosion + mask pyramid run with the chunk's kernels
-            s = copy_frames(h->mask_stage + f0 * dfs, p0, dfs, masks + f0 * mfstride, mpitch, mfstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
-            if (s != ADB_OK) return s;
-        }
-        ADB_CUDA(cudaEventRecord(h->cev[c], h->copy_stream));
-        ADB_CUDA(cudaStreamWaitEvent(h->stream, h->cev[c], 0));
-        if (masks && (s = prepare_masks(h, f0, nc, h->mask_stage + f0 * dfs, dfs, p0)) != ADB_OK) return s;
-        s = run_range(h, f0, nc, masks != nullptr);
-        if (s != ADB_OK) return s;
-        ADB_CUDA(cudaEventRecord(h->cev[kChunks + c], h->stream));
-        ADB_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->cev[kChunks + c], 0));
-        s = download_async(h, f0, nc, kps ? kps + (size_t)f0 * cap : nullptr, desc ? desc + (size_t)f0 * cap * 32 : nullptr, cap,
-                           h->h_counts + f0, h->d2h_stream);
+    if (masks) {   // the chunk's masks ride on the same copy stream; erosion + mask pyramid run with the chunk's kernels
+        s = copy_frames(h->mask_stage + f0 * dfs, p0, dfs, masks + f0 * mfstride, mpitch, mfstride, w, hh, nc, cudaMemcpyHostToDevice, h->copy_stream);
         if (s != ADB_OK) return s;
     }
+    ADB_CUDA(cudaEventRecord(h->cev[c], h->copy_stream));
+    ADB_CUDA(cudaStreamWaitEvent(h->stream, h->cev[c], 0));
+    if (masks && (s = prepare_masks(h, f0, nc, h->mask_stage + f0 * dfs, dfs, p0)) != ADB_OK) return s;
+    s = run_range(h, f0, nc, masks != nullptr);
+    if (s != ADB_OK) return s;
+    ADB_CUDA(cudaEventRecord(h->cev[kChunks + c], h->stream));
+    return ADB_OK;
+}
+
+static adb_status chunk_finish(adb_orb* h, int n, int cap, int32_t* counts) {
     ADB_CUDA(cudaStreamSynchronize(h->d2h_stream));
-    s = check_device_status(h);
+    adb_status s = check_device_status(h);
     if (s != ADB_OK) return s;
     for (int i = 0; i < n; ++i) {
         counts[i] = h->h_counts[i];
         ADB_CHECK(counts[i] <= cap, ADB_ERR_CAPACITY, "frame %d holds %d key-points, caller capacity %d", i, counts[i], cap);
     }
     return ADB_OK;
+}
+
+static adb_status extract_batch_chunked(adb_orb* h, int n, const uint8_t* images, size_t fstride, int w, int hh, int pitch, const uint8_t* masks,
+                                        size_t mfstride, int mpitch, adb_keypoint* kps, uint8_t* desc, int cap, int32_t* counts) {
+    adb_status s = chunk_begin(h, n, w, hh, masks != nullptr);
+    if (s != ADB_OK) return s;
+    const int per = (n + chunk_count(n) - 1) / chunk_count(n);
+    int c = 0;
+    for (int f0 = 0; f0 < n; f0 += per, ++c) {
+        const int nc = std::min(per, n - f0);
+        s = chunk_issue(h, c, f0, nc, images, fstride, w, hh, pitch, masks, mfstride, mpitch);
+        if (s != ADB_OK) return s;
+        ADB_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->cev[kChunks + c], 0));
+        s = download_async(h, f0, nc, kps ? kps + (size_t)f0 * cap : nullptr, desc ? desc + (size_t)f0 * cap * 32 : nullptr, cap,
+                           h->h_counts + f0, h->d2h_stream);
+        if (s != ADB_OK) return s;
+    }
+    return chunk_finish(h, n, cap, counts);
 }
 
 adb_status adb_orb_extract_batch(adb_orb_t h, int32_t n, const uint8_t* images, size_t fstride, int32_t w, int32_t hh, int32_t pitch,
@@ -1929,6 +1951,75 @@ adb_status adb_orb_extract(adb_orb_t h, const uint8_t* image, int32_t w, int32_t
                            int32_t mpitch, adb_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* n_out) {
     ADB_CHECK(n_out, ADB_ERR_INVALID, "null argument");
     return adb_orb_extract_batch(h, 1, image, (size_t)pitch * hh, w, hh, pitch, mask, (size_t)mpitch * hh, mpitch, kps, desc, cap, n_out);
+}
+
+// The hot part of the stereo Frame constructor (src/Frame.cc:80-100: ExtractORB left / right on two threads, then ComputeStereoMatches) for
+// n stereo pairs in host memory, as ONE pipeline: per chunk of frames the two uploads, the two extractions (one stream per handle), the
+// stereo matcher of the chunk behind both, and the downloads of everything the chunk produced -- so the matcher and its results overlap
+// the next chunks' copies instead of running after the last one.  Results are identical to adb_orb_extract_batch x 2 + adb_stereo_match.
+adb_status adb_stereo_frames_batch(adb_orb_t L, adb_orb_t R, int32_t n, const uint8_t* imagesL, const uint8_t* imagesR, size_t fstride, int32_t w,
+                                   int32_t hh, int32_t pitch, const uint8_t* masksL, const uint8_t* masksR, size_t mfstride, int32_t mpitch,
+                                   adb_keypoint* kpsL, uint8_t* descL, int32_t* countsL, adb_keypoint* kpsR, uint8_t* descR, int32_t* countsR,
+                                   int32_t cap, float mb, float mbf, float* ur, float* dp, int32_t* bi, int32_t* bd) {
+    ADB_CHECK(L && R && L != R && imagesL && imagesR && countsL && countsR && ur && dp, ADB_ERR_INVALID, "null argument");
+    ADB_CHECK((masksL == nullptr) == (masksR == nullptr), ADB_ERR_INVALID, "masks must be given for both images or for neither");
+    ADB_CHECK(n >= 1 && n <= L->cfg.max_batch && n <= R->cfg.max_batch, ADB_ERR_INVALID, "n_frames %d exceeds max_batch", n);
+    ADB_CHECK(w > 0 && hh > 0 && pitch >= w, ADB_ERR_INVALID, "bad image geometry");
+    static const bool no_chunks = getenv("ADB_NO_CHUNKS") != nullptr;   // measurement switch
+    if (n < kMinChunkedFrames || L->profiling || R->profiling || no_chunks) {   // small batches: the three calls it stands for
+        adb_status s = adb_orb_extract_batch(L, n, imagesL, fstride, w, hh, pitch, masksL, mfstride, mpitch, kpsL, descL, cap, countsL);
+        if (s == ADB_OK) s = adb_orb_extract_batch(R, n, imagesR, fstride, w, hh, pitch, masksR, mfstride, mpitch, kpsR, descR, cap, countsR);
+        if (s == ADB_OK) s = adb_stereo_match(L, R, n, mb, mbf, ur, dp, bi, bd, cap);
+        return s;
+    }
+    for (adb_orb* h : {L, R}) {
+        const adb_status es = ensure_size(h, w, hh);
+        if (es != ADB_OK) return es;
+        ADB_CHECK(w == h->cfg.width && hh == h->cfg.height, ADB_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", w, hh, h->cfg.width, h->cfg.height);
+    }
+    ADB_CHECK(L->cfg.device == R->cfg.device, ADB_ERR_INVALID, "left / right extractors live on different devices");
+    ADB_CUDA(cudaSetDevice(L->cfg.device));
+    adb_status s = chunk_begin(L, n, w, hh, masksL != nullptr);
+    if (s == ADB_OK) s = chunk_begin(R, n, w, hh, masksR != nullptr);
+    if (s != ADB_OK) return s;
+    if (!L->sev[0]) {
+        for (auto& e : L->sev) ADB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ADB_CUDA(cudaStreamCreateWithFlags(&L->stereo_stream, cudaStreamNonBlocking));
+    }
+    const int per = (n + chunk_count(n) - 1) / chunk_count(n);
+    int c = 0;
+    for (int f0 = 0; f0 < n; f0 += per, ++c) {
+        const int nc = std::min(per, n - f0);
+        s = chunk_issue(L, c, f0, nc, imagesL, fstride, w, hh, pitch, masksL, mfstride, mpitch);
+        if (s == ADB_OK) s = chunk_issue(R, c, f0, nc, imagesR, fstride, w, hh, pitch, masksR, mfstride, mpitch);
+        if (s != ADB_OK) return s;
+        // the right handle's results leave as soon as its chunk is done
+        ADB_CUDA(cudaStreamWaitEvent(R->d2h_stream, R->cev[kChunks + c], 0));
+        s = download_async(R, f0, nc, kpsR ? kpsR + (size_t)f0 * cap : nullptr, descR ? descR + (size_t)f0 * cap * 32 : nullptr, cap, R->h_counts + f0,
+                           R->d2h_stream);
+        if (s != ADB_OK) return s;
+        // the left handle's own results as soon as its chunk is done
+        ADB_CUDA(cudaStreamWaitEvent(L->d2h_stream, L->cev[kChunks + c], 0));
+        s = download_async(L, f0, nc, kpsL ? kpsL + (size_t)f0 * cap : nullptr, descL ? descL + (size_t)f0 * cap * 32 : nullptr, cap, L->h_counts + f0,
+                           L->d2h_stream);
+        if (s != ADB_OK) return s;
+        // the matcher of the chunk runs on its own stream behind both extractions of the chunk (on either handle's stream it would hold
+        // up that handle's next chunk: measured 49 instead of 37 ms per 2048 pairs); its results follow on the left download stream
+        ADB_CUDA(cudaStreamWaitEvent(L->stereo_stream, L->cev[kChunks + c], 0));
+        ADB_CUDA(cudaStreamWaitEvent(L->stereo_stream, R->cev[kChunks + c], 0));
+        s = adb_stereo_match_range(L, R, f0, nc, mb, mbf, L->stereo_stream);
+        if (s != ADB_OK) return s;
+        ADB_CUDA(cudaEventRecord(L->sev[c], L->stereo_stream));
+        ADB_CUDA(cudaStreamWaitEvent(L->d2h_stream, L->sev[c], 0));
+        s = adb_stereo_download_range(L, f0, nc, ur, dp, bi, bd, cap, L->d2h_stream);
+        if (s != ADB_OK) return s;
+    }
+    // later calls on the left handle's stream (and adb_orb_sync) must see the matcher's results too
+    ADB_CUDA(cudaEventRecord(L->sev[kChunks - 1], L->stereo_stream));
+    ADB_CUDA(cudaStreamWaitEvent(L->stream, L->sev[kChunks - 1], 0));
+    s = chunk_finish(R, n, cap, countsR);
+    if (s != ADB_OK) return s;
+    return chunk_finish(L, n, cap, countsL);
 }
 
 adb_status adb_orb_get_pyramid(adb_orb_t h, int32_t frame, int32_t level, int32_t which, uint8_t* dst, int32_t dpitch) {

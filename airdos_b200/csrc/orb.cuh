@@ -76,7 +76,9 @@ struct adb_orb {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // chunked host-buffer calls: upload / download streams
-    cudaEvent_t cev[17] = {};                                  // [0..7] chunk uploaded, [8..15] chunk computed, [16] entry fence
+    cudaEvent_t cev[65] = {};                                  // [0..31] chunk uploaded, [32..63] chunk computed, [64] entry fence
+    cudaEvent_t sev[32] = {};                                  // stereo chunk pipeline: chunk matched (left handle)
+    cudaStream_t stereo_stream = nullptr;                      // ... and the stream its matcher runs on
     adb::LevelDev* d_levels = nullptr;
     uint32_t* d_cell_table = nullptr;   // [ncells_total] level << 24 | row << 12 | col, then [ncells_total] the warp kernel's cell order
     float4* d_pattern = nullptr;        // [8][32] rBRIEF tests as floats {x0, y0, x1, y1}, lane-major
@@ -119,3 +121,7 @@ struct adb_orb {
     int32_t* h_counts = nullptr; // pinned
     int32_t* h_status = nullptr; // pinned
 };
+
+// internal (C++ linkage), match.cu: stereo matching / result download of a frame range on a given stream
+adb_status adb_stereo_match_range(adb_orb* L, adb_orb* R, int f0, int n, float mb, float mbf, cudaStream_t st);
+adb_status adb_stereo_download_range(adb_orb* L, int f0, int n, float* ur, float* dp, int32_t* bi, int32_t* bd, int cap, cudaStream_t st);

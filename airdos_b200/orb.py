@@ -387,6 +387,28 @@ def compute_stereo_matches(left: ORBextractor, right: ORBextractor, n_frames: in
     return ur, dp, bi, bd
 
 
+def stereo_frames_batch(left: ORBextractor, right: ORBextractor, images_left: np.ndarray, images_right: np.ndarray, mb: float, mbf: float,
+                        masks_left: np.ndarray | None = None, masks_right: np.ndarray | None = None, out_left: HostResults | None = None,
+                        out_right: HostResults | None = None, out_stereo: HostStereo | None = None):
+    """The stereo Frame constructor's hot part (src/Frame.cc:80-100) for F stereo pairs in host memory, as one chunk pipeline:
+    -> ((kps, desc, counts) left, (kps, desc, counts) right, (uRight, depth, best_idx, best_dist))."""
+    images_left = np.ascontiguousarray(images_left, np.uint8); images_right = np.ascontiguousarray(images_right, np.uint8)
+    assert images_left.shape == images_right.shape
+    f, h, w = images_left.shape
+    cap = left.capacity
+    out_left = out_left or HostResults(f, cap); out_right = out_right or HostResults(f, cap); out_stereo = out_stereo or HostStereo(f, cap)
+    if masks_left is not None:
+        masks_left = np.ascontiguousarray(masks_left, np.uint8); masks_right = np.ascontiguousarray(masks_right, np.uint8)
+        assert masks_left.shape == images_left.shape and masks_right.shape == images_left.shape
+    kl, dl, cl = out_left.kps[:f], out_left.desc[:f], out_left.counts[:f]
+    kr, dr, cr = out_right.kps[:f], out_right.desc[:f], out_right.counts[:f]
+    ur, dp, bi, bd = out_stereo.u_right[:f], out_stereo.depth[:f], out_stereo.best_idx[:f], out_stereo.best_dist[:f]
+    check(lib().adb_stereo_frames_batch(left._h, right._h, f, ptr(images_left), ptr(images_right), h * w, w, h, w, ptr(masks_left), ptr(masks_right),
+                                        h * w, w, ptr(kl), ptr(dl), ptr(cl), ptr(kr), ptr(dr), ptr(cr), cap, mb, mbf, ptr(ur), ptr(dp), ptr(bi), ptr(bd)))
+    left._after_call(w, h); right._after_call(w, h)
+    return (kl, dl, cl), (kr, dr, cr), (ur, dp, bi, bd)
+
+
 def stereo_match_device(left: ORBextractor, right: ORBextractor, n_frames: int, mb: float, mbf: float):
     """Device-resident ComputeStereoMatches (asynchronous on the left handle's stream)."""
     check(lib().adb_stereo_match_device(left._h, right._h, n_frames, mb, mbf))

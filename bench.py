@@ -391,12 +391,9 @@ def main():
     npL, npR = hostL.numpy(), hostR.numpy()
 
     def e2e_step():
-        # the reference runs the two extractors on two host threads (src/Frame.cc:81-84); ctypes drops the GIL
-        tR = threading.Thread(target=exR.extract_batch, args=(npR,), kwargs={"out": outR})
-        tR.start()
-        exL.extract_batch(npL, out=outL)
-        tR.join()
-        adb.compute_stereo_matches(exL, exR, P, mb, mbf, out=outS)
+        # the stereo Frame constructor's hot part (src/Frame.cc:80-100: both extractions, then ComputeStereoMatches) through the one
+        # C-ABI call that stands for it: host images in, key-points / descriptors / stereo matches out, chunk-pipelined inside
+        adb.stereo_frames_batch(exL, exR, npL, npR, mb, mbf, out_left=outL, out_right=outR, out_stereo=outS)
         return int(outL.counts.sum() + outR.counts.sum())
 
     for _ in range(2):
@@ -444,11 +441,7 @@ def main():
         npmL, npmR = mLh.numpy(), mRh.numpy()
 
         def e2e_mstep():
-            tR = threading.Thread(target=exR.extract_batch, args=(npR, npmR), kwargs={"out": outR})
-            tR.start()
-            exL.extract_batch(npL, npmL, out=outL)
-            tR.join()
-            adb.compute_stereo_matches(exL, exR, P, mb, mbf, out=outS)
+            adb.stereo_frames_batch(exL, exR, npL, npR, mb, mbf, npmL, npmR, out_left=outL, out_right=outR, out_stereo=outS)
             return int(outL.counts.sum() + outR.counts.sum())
 
         for _ in range(2):

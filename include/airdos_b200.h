@@ -327,6 +327,18 @@ adb_status adb_stereo_match_device(adb_orb_t left, adb_orb_t right, int32_t n_fr
 adb_status adb_stereo_results_device(adb_orb_t left, const float** d_u_right, const float** d_depth,
                                      const int32_t** d_best_idx, const int32_t** d_best_dist);
 
+/* The hot part of the stereo Frame constructor (src/Frame.cc:80-100: ExtractORB(0, imLeft) and ExtractORB(1, imRight) on two
+ * threads, then ComputeStereoMatches()) for n_frames stereo pairs in HOST memory, as one pipeline: per chunk of frames the two
+ * uploads, the two extractions, the stereo matcher of the chunk and the downloads of everything the chunk produced overlap with
+ * the neighbouring chunks.  Arguments as in adb_orb_extract_batch (left / right images share one geometry; masks for both images or
+ * for neither) and adb_stereo_match; the results are identical to adb_orb_extract_batch(left) + adb_orb_extract_batch(right) +
+ * adb_stereo_match, which is also what batches below 32 frames run. */
+adb_status adb_stereo_frames_batch(adb_orb_t left, adb_orb_t right, int32_t n_frames, const uint8_t* images_left, const uint8_t* images_right,
+                                   size_t frame_stride, int32_t w, int32_t h, int32_t pitch, const uint8_t* masks_left, const uint8_t* masks_right,
+                                   size_t mask_frame_stride, int32_t mask_pitch, adb_keypoint* kps_left, uint8_t* desc_left, int32_t* counts_left,
+                                   adb_keypoint* kps_right, uint8_t* desc_right, int32_t* counts_right, int32_t cap, float mb, float mbf,
+                                   float* u_right, float* depth, int32_t* best_idx, int32_t* best_dist);
+
 
 /* ---------------------------------------------------------------------------------------
  * Bundle adjustment: Optimizer::LocalBundleAdjustment (src/Optimizer.cc:431-731) and

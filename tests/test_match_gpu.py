@@ -88,3 +88,33 @@ def test_distinctive_descriptors_match_oracle(adb, oracle_mod):
     with pytest.raises(adb.AdbError):                       # more observations than ADB_MAX_OBSERVATIONS: refused, never truncated
         adb.compute_distinctive_descriptors(m, np.zeros((129, 32), np.uint8), np.array([0, 129], np.int32))
     m.close()
+
+
+@pytest.mark.parametrize("n,masked", [(40, False), (40, True), (3, False)])
+def test_stereo_frames_batch_equals_the_three_calls(n, masked):
+    """adb_stereo_frames_batch (the stereo Frame constructor's hot part as one chunk pipeline, src/Frame.cc:80-100) returns exactly what
+    adb_orb_extract_batch x 2 + adb_stereo_match return: key-points, descriptors, counts, uRight / depth bit patterns, best index /
+    distance -- chunked (40 frames) and below the chunking threshold (3 frames)."""
+    import airdos_b200 as adb
+    from airdos_b200 import synth
+    w, h = 640, 480
+    pairs = [synth.make_stereo_pair(300 + i, w, h) for i in range(4)]
+    L = np.stack([pairs[i % 4][0] for i in range(n)]); R = np.stack([pairs[i % 4][1] for i in range(n)])
+    mL = np.stack([synth.make_mask(310 + i % 3, w, h, 3) for i in range(n)]) if masked else None
+    mR = np.stack([synth.make_mask(320 + i % 3, w, h, 3) for i in range(n)]) if masked else None
+    mbf = synth.BF; mb = mbf / synth.FX
+    exL = adb.ORBextractor(1500, 1.2, 8, 12, 7, w, h, max_batch=n); exR = adb.ORBextractor(1500, 1.2, 8, 12, 7, w, h, max_batch=n)
+    (kl, dl, cl), (kr, dr, cr), (ur, dp, bi, bd) = adb.stereo_frames_batch(exL, exR, L, R, mb, mbf, mL, mR)
+    kl, dl, cl, kr, dr, cr, ur, dp, bi, bd = [a.copy() for a in (kl, dl, cl, kr, dr, cr, ur, dp, bi, bd)]
+    a = adb.ORBextractor(1500, 1.2, 8, 12, 7, w, h, max_batch=n); b = adb.ORBextractor(1500, 1.2, 8, 12, 7, w, h, max_batch=n)
+    kl2, dl2, cl2 = a.extract_batch(L, mL); kr2, dr2, cr2 = b.extract_batch(R, mR)
+    ur2, dp2, bi2, bd2 = adb.compute_stereo_matches(a, b, n, mb, mbf)
+    assert (cl == cl2).all() and (cr == cr2).all() and cl.min() > 0
+    for f in range(n):
+        assert kl[f, :cl[f]].tobytes() == kl2[f, :cl[f]].tobytes() and (dl[f, :cl[f]] == dl2[f, :cl[f]]).all(), f
+        assert kr[f, :cr[f]].tobytes() == kr2[f, :cr[f]].tobytes() and (dr[f, :cr[f]] == dr2[f, :cr[f]]).all(), f
+        for x, y in ((ur, ur2), (dp, dp2), (bi, bi2), (bd, bd2)):
+            assert (x[f, :cl[f]].view(np.uint32) == y[f, :cl[f]].view(np.uint32)).all(), f
+    assert (dp > 0).sum() > 100 * n
+    for e in (exL, exR, a, b):
+        e.close()
