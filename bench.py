@@ -212,8 +212,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--pairs", type=int, default=2048,
-                    help="stereo pairs per step per GPU (2048 pairs = 4096 frames = 53 ms per step: 20 steps give a timed region above one second)")
+    ap.add_argument("--pairs", type=int, default=3072,
+                    help="stereo pairs per step per GPU (3072 pairs = 6144 frames = 54 ms per step: 20 steps give a timed region above one second)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--gather", default="fused", choices=["fused", "fused_p2p", "nccl"],
