@@ -2,23 +2,24 @@
 //
 // Replaces ORB_SLAM2::ORBextractor (src/ORBextractor.cc) for a batch of F frames:
 //
-//   pyr_resize_strip_kernel  ComputePyramid                src/ORBextractor.cc:1121-1156
-//   fast_cells_kernel        per-cell FAST + ini/min rule  src/ORBextractor.cc:791-840
-//   quadtree_kernel          DistributeOctTree             src/ORBextractor.cc:541-765
-//   orient_describe_kernel   IC_Angle + GaussianBlur + computeOrbDescriptor
-//                                                          src/ORBextractor.cc:78-148, 1099-1104
+//   pyr_resize_strip_kernel   ComputePyramid (+ the mask pyramid)   src/ORBextractor.cc:1121-1156
+//   erode10_tile_kernel       cv::erode of the mask                 src/ORBextractor.cc:1130-1131
+//   fast_cells_warp_kernel    per-cell FAST + ini/min rule          src/ORBextractor.cc:791-840   (fast_cells_kernel: fallback)
+//   quadtree_kernel           DistributeOctTree                     src/ORBextractor.cc:541-765
+//   blur7_level_kernel        GaussianBlur 7x7 of every level       src/ORBextractor.cc:1099-1100
+//   orient_describe_kernel    IC_Angle + computeOrbDescriptor       src/ORBextractor.cc:78-148, 1101-1104
 //
-// None of these is a translation of the reference's loops: the per-cell detector objects
-// become one CTA per cell fed by a TMA box load, the std::list quad-tree becomes a level
-// synchronous pass over a flat key array with node ids equal to the reference's creation
-// order (which is what fixes its output order), and the whole-level blur becomes a 43x43
-// patch staged by TMA per key-point.  The arithmetic (fixed-point resize and blur, FAST score,
-// float32 atan polynomial without contraction) is the one pinned in oracle/orb_oracle.cpp.
+// None of these is a translation of the reference's loops: the per-cell detector objects become one WARP per cell fed by a TMA box
+// load (column walk, scores and NMS in registers, ordered ballot emission), the std::list quad-tree becomes a level-synchronous pass
+// over a flat key array with node ids equal to the reference's creation order (which is what fixes its output order), the level blur
+// is a shuffle-based register pipeline without shared memory, and a key-point's descriptor reads two TMA boxes (level, blurred
+// level).  The arithmetic (fixed-point resize and blur, FAST score, float32 atan polynomial without contraction) is the one pinned in
+// oracle/orb_oracle.cpp.
 //
-// Data layout in HBM: level l of all frames is one [max_batch][h_l][pitch_l] u8 array, pitch a
-// multiple of 16 B so each level is a 3-D TMA tensor {w, h, frame}.  No 19-px border is stored:
-// nothing on this path reads it (FAST starts at pixel 19; IC-angle / rBRIEF stay inside the
-// ROI; the blur reflects at the ROI edge because the reference blurs a clone of the ROI).
+// Data layout in HBM: level l of all frames is one [max_batch][h_l][pitch_l] u8 array, pitch a multiple of 16 B so each level is a
+// 3-D TMA tensor {w, h, frame}; the blurred pyramid has the same layout.  No 19-px border is stored: nothing on this path reads it
+// (FAST starts at pixel 19; IC-angle / rBRIEF stay inside the ROI; the blur reflects at the ROI edge because the reference blurs a
+// clone of the ROI).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -930,10 +931,9 @@ __global__ void __launch_bounds__(kQtThreads) quadtree_kernel(const LevelDev* __
 }
 
 // =========================================================================================
-// Orientation + descriptor, one warp per key-point.  A 48 x 43-byte box around the key-point
-// arrives by TMA (out-of-image bytes zero-filled, then mirrored per BORDER_REFLECT_101 at the
-// ROI edge); IC-angle on the raw patch; 7x7 fixed-point Gaussian on the 37 x 37 core; the 256
-// rotated tests read the blurred core.
+// Orientation + descriptor, one warp per key-point (orient_describe_kernel, below the level blur it reads).  Two 64-byte-wide boxes
+// around the key-point arrive by TMA on one mbarrier: 31 rows of the level (the r = 15 disc of IC_Angle) and 37 rows of the blurred
+// level (the 256 rotated tests reach +-18 px); both lie inside the level because key-points sit >= 19 px from its edges.
 // =========================================================================================
 // GaussianBlur(7 x 7, sigma 2, BORDER_REFLECT_101) of a whole pyramid level (src/ORBextractor.cc:1099-1100: the reference blurs a clone
 // of the level ROI once per level).  Fixed point {18,34,48,56,48,34,18} / 256 on both axes, (v + 2^15) >> 16: integer and exact, so

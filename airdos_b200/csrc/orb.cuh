@@ -12,9 +12,8 @@ constexpr int kMinBorder = 16;   // EDGE_THRESHOLD-3 src/ORBextractor.cc:775
 constexpr int kCellBoxWMax = 96; // FAST cell tile: 15 B alignment slack + cell + 6 px, rounded up to 16 B
                                  // (TMA needs the box origin 16-byte aligned in x: measured on B200, tools/probe)
 constexpr int kCellBoxHMax = 66;
-constexpr int kPatchBoxW = 64;   // descriptor patch: 43 x 43 px (+-18 sample reach, +-3 blur reach) + <= 15 B alignment slack
-constexpr int kPatchBoxH = 43;
-constexpr int kPatchR = 21;
+constexpr int kPatchBoxW = 64;   // descriptor boxes: 64 B rows = 43 px (key-point column at byte 21 + alignment slack <= 15) ...
+constexpr int kPatchR = 21;      // ... fetched from the 16-B aligned column at or left of x - 21
 
 // Per-level constants, one array per handle in device memory.
 struct LevelDev {
