@@ -1081,6 +1081,8 @@ struct DescSmem {
     uint32_t ic_wu[16][8];                            // IC_Angle row tables by |v|: signed weights u of word k (0 outside the disc)
     uint32_t ic_m[16][8];                             // ... and the disc mask as 0 / 1 bytes
     uint64_t bar[kDescWarps];
+    uint4 gdesc[kDescWarps * 2];                      // fused gather: the CTA's 8 descriptors (256 B) ...
+    uint4 gkp[kDescWarps * 6 / 4];                    // ... and 8 key-point records (192 B), sent as 16-byte stores by warp 0
 };
 
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c) {   // sum of unsigned bytes of a times signed bytes of b
@@ -1090,6 +1092,12 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c) {   // 
 }
 
 // one 32-bit store of the fused all-gather: a plain store to a peer-mapped address, or multimem.st to an NVLS multicast address
+__device__ __forceinline__ void gather_store_u128(void* p, uint4 v, int multicast) {
+    if (multicast)
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                     "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+    else *reinterpret_cast<uint4*>(p) = v;
+}
 __device__ __forceinline__ void gather_store_u32(uint32_t* p, uint32_t v, int multicast) {
     if (multicast) asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     else *p = v;
@@ -1140,7 +1148,13 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
         counts[f] = total;
         for (int g = 0; g < gather.n; ++g) gather_store_u32(reinterpret_cast<uint32_t*>(gather.counts[g] + f), (uint32_t)total, gather.multicast);   // over NVLink
     }
-    if (lvl < 0 || i >= cap) return;
+    // fused gather in 16-byte stores: the CTA's 8 consecutive records are staged in shared memory and leave from warp 0 (rows of the
+    // result arrays must then start 16-byte aligned: capacity a multiple of 8; else the word-granular path below)
+    const bool gvec = gather.n > 0 && (cap & 7) == 0;
+    if (lvl < 0 || i >= cap) {
+        if (gvec) asm volatile("bar.sync 1, %0;" ::"n"(kDescWarps * 32));   // meets the staging barrier of the CTA's working warps
+        return;
+    }
     const LevelDev& L = levels[lvl];
     const uint32_t e = list[(size_t)f * list_total + L.list_base + (i - base)];
     const int cx = e & 0xFFF, cy = (e >> 12) & 0xFFF, resp = e >> 24;
@@ -1217,9 +1231,28 @@ __global__ void __launch_bounds__(kDescWarps * 32) orient_describe_kernel(const 
     kp.octave = lvl;
     if (lane == 0) kps[(size_t)f * cap + i] = kp;
     // fused all-gather: the record also goes to every peer's buffer (or once to the NVLS multicast mapping, which the switch
-    // replicates) as 32-bit words -- lanes 0..7 one word of the descriptor each, lanes 0..5 one word of the key-point: one store
-    // instruction and one NVLink write per destination for each half of the record (multimem.st has no byte form)
-    if (gather.n > 0) {
+    // replicates).  Fallback for odd capacities: 32-bit words -- lanes 0..7 one word of the descriptor each, lanes 0..5 one word of
+    // the key-point (multimem.st has no byte form)
+    if (gvec) {
+        reinterpret_cast<uint8_t*>(sm.gdesc)[warp * 32 + lane] = (uint8_t)byte;
+        if (lane < 6)
+            reinterpret_cast<uint32_t*>(sm.gkp)[warp * 6 + lane] = lane == 0 ? __float_as_uint(kp.x) : lane == 1 ? __float_as_uint(kp.y)
+                                                                   : lane == 2 ? __float_as_uint(kp.size) : lane == 3 ? __float_as_uint(kp.angle)
+                                                                   : lane == 4 ? __float_as_uint(kp.response) : (uint32_t)kp.octave;
+        asm volatile("bar.sync 1, %0;" ::"n"(kDescWarps * 32));
+        if (warp == 0 && lane < 28) {            // warp 0 holds the CTA's first record, so it is here whenever any warp of the CTA is
+            const int nrec = min(min(total, cap) - (int)blockIdx.x * kDescWarps, kDescWarps);   // records of this CTA that exist
+            const size_t rec0 = (size_t)f * cap + (size_t)blockIdx.x * kDescWarps;
+            const bool isd = lane < 16;
+            const int chunk = isd ? lane : lane - 16;                                         // 16-byte chunk of the 256 / 192 bytes
+            const bool live = (isd ? chunk / 2 : chunk * 16 / 24) < nrec;                      // the record its first byte belongs to
+            const uint4 v = isd ? sm.gdesc[chunk] : sm.gkp[chunk];
+            if (live)
+                for (int g = 0; g < gather.n; ++g)
+                    gather_store_u128(isd ? (void*)(gather.desc[g] + rec0 * 32 + chunk * 16) : (void*)((uint8_t*)gather.kps[g] + rec0 * 24 + chunk * 16), v,
+                                      gather.multicast);
+        }
+    } else if (gather.n > 0) {
         uint32_t w = byte | (__shfl_down_sync(0xFFFFFFFFu, byte, 1) << 8) | (__shfl_down_sync(0xFFFFFFFFu, byte, 2) << 16) |
                      (__shfl_down_sync(0xFFFFFFFFu, byte, 3) << 24);                // valid in lanes 0, 4, 8, ...
         w = __shfl_sync(0xFFFFFFFFu, w, (lane & 7) * 4);                           // lanes 0..7: word `lane` of the descriptor

@@ -230,15 +230,18 @@ def test_full_size_batch_properties(adb, oracle_mod):
     ex.close()
 
 
-def test_fused_gather_targets(adb, oracle_mod):
+@pytest.mark.parametrize("nfeat", [1000, 1003])
+def test_fused_gather_targets(adb, oracle_mod, nfeat):
     """adb_orb_set_gather: the descriptor kernel also stores every record into the given target buffers (on one GPU
-    the 'peers' are two local buffers; over NVLink they are peer-mapped symmetric memory, exercised by bench.py --gpus 2)."""
+    the 'peers' are two local buffers; over NVLink they are peer-mapped symmetric memory, exercised by bench.py --gpus 2).
+    1000 features: capacity 1024, records leave as staged 16-byte stores; 1003: odd capacity, the word-granular path."""
     import torch
     from airdos_b200 import synth
     F = 3
     imgs = np.stack([synth.make_stereo_pair(50 + f)[0] for f in range(F)])
-    ex = adb.ORBextractor(1000, 1.2, 8, 12, 7, 640, 480, max_batch=F)
+    ex = adb.ORBextractor(nfeat, 1.2, 8, 12, 7, 640, 480, max_batch=F)
     cap = ex.capacity
+    assert (cap % 8 == 0) == (nfeat == 1000)
     tk = [torch.zeros(F, cap, 24, dtype=torch.uint8, device="cuda") for _ in range(2)]
     td = [torch.zeros(F, cap, 32, dtype=torch.uint8, device="cuda") for _ in range(2)]
     tc = [torch.zeros(F, dtype=torch.int32, device="cuda") for _ in range(2)]
