@@ -1,0 +1,70 @@
+// cv_shim.h -- TEST INFRASTRUCTURE: the few pieces of the OpenCV C++ API that the reference's matcher statements touch (OpenCV's
+// C++ headers are not in this image), with OpenCV's semantics: reference-counted Mat views (row / rowRange / colRange share
+// storage), convertTo u8 -> f32, float Mat arithmetic element by element, norm(a, b, NORM_L1) accumulated in double.  Only used by
+// oracle/ref_match.cpp to compile functions taken from /root/reference/src unmodified.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#define CV_8U 0
+#define CV_32F 5
+
+namespace cv {
+enum { NORM_L1 = 2 };
+struct Point2f { float x = 0, y = 0; };
+struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
+
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    Mat() {}
+    Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(int r, int c, int type, const void* data) { create(r, c, type); std::memcpy(buf_->data(), data, (size_t)r * step_); }
+    static Mat ones(int r, int c, int type) {
+        Mat m(r, c, type);
+        for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) { if (type == CV_32F) m.at<float>(i, j) = 1.f; else m.at<unsigned char>(i, j) = 1; }
+        return m;
+    }
+    int type() const { return type_; }
+    bool empty() const { return rows == 0 || cols == 0; }
+    Mat row(int i) const { return rowRange(i, i + 1); }
+    Mat rowRange(int a, int b) const { Mat m = *this; m.off_ += (size_t)a * step_; m.rows = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m = *this; m.off_ += (size_t)a * esz(); m.cols = b - a; return m; }
+    template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(buf_->data() + off_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
+    template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(buf_->data() + off_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
+    template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(buf_->data() + off_ + (size_t)r * step_); }
+    void convertTo(Mat& dst, int type) const {          // u8 / f32 -> f32 (dst may be *this)
+        Mat out(rows, cols, type);
+        for (int i = 0; i < rows; ++i)
+            for (int j = 0; j < cols; ++j) out.at<float>(i, j) = type_ == CV_32F ? at<float>(i, j) : (float)at<unsigned char>(i, j);
+        dst = out;
+    }
+private:
+    size_t esz() const { return type_ == CV_32F ? 4 : 1; }
+    void create(int r, int c, int type) {
+        rows = r; cols = c; type_ = type; step_ = (size_t)c * esz(); off_ = 0;
+        buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * step_);
+    }
+    std::shared_ptr<std::vector<unsigned char>> buf_;
+    size_t off_ = 0, step_ = 0;
+    int type_ = CV_8U;
+};
+inline Mat operator*(float s, const Mat& m) {
+    Mat o(m.rows, m.cols, CV_32F);
+    for (int i = 0; i < m.rows; ++i) for (int j = 0; j < m.cols; ++j) o.at<float>(i, j) = s * m.at<float>(i, j);
+    return o;
+}
+inline Mat operator-(const Mat& a, const Mat& b) {
+    Mat o(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) o.at<float>(i, j) = a.at<float>(i, j) - b.at<float>(i, j);
+    return o;
+}
+inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {   // OpenCV: normDiffL1_<float, double>
+    double s = 0;
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) s += std::fabs(a.at<float>(i, j) - b.at<float>(i, j));
+    return s;
+}
+}  // namespace cv

@@ -118,3 +118,24 @@ def test_stereo_frames_batch_equals_the_three_calls(n, masked):
     assert (dp > 0).sum() > 100 * n
     for e in (exL, exR, a, b):
         e.close()
+
+
+@pytest.mark.parametrize("ci", [0, 2])
+def test_cuda_stereo_equals_the_reference_function(ci):
+    """CUDA extraction + stereo matcher on the images of tests/golden/stereo_ref.npz against mvuRight / mvDepth computed by the
+    reference's own Frame::ComputeStereoMatches (src/Frame.cc:829-1003, compiled from /root/reference: oracle/ref_match.cpp)."""
+    import os
+    import airdos_b200 as adb
+    from airdos_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stereo_ref.npz"))
+    seed, w, h, nf, ini, mn = [int(v) for v in g[f"c{ci}_params"]]
+    il, ir = g[f"c{ci}_left"], g[f"c{ci}_right"]
+    exL = adb.ORBextractor(nf, 1.2, 8, ini, mn, w, h); exR = adb.ORBextractor(nf, 1.2, 8, ini, mn, w, h)
+    _, _, cl = exL.extract_batch(il[None]); exR.extract_batch(ir[None])
+    mbf = synth.BF; mb = mbf / synth.FX
+    ur, dp, _, _ = adb.compute_stereo_matches(exL, exR, 1, mb, mbf)
+    n = int(cl[0])
+    assert n == len(g[f"c{ci}_u_right"])
+    assert (ur[0, :n].view(np.uint32) == g[f"c{ci}_u_right"].view(np.uint32)).all()
+    assert (dp[0, :n].view(np.uint32) == g[f"c{ci}_depth"].view(np.uint32)).all()
+    exL.close(); exR.close()
