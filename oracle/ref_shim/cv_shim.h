@@ -33,6 +33,19 @@ public:
     Mat row(int i) const { return rowRange(i, i + 1); }
     Mat rowRange(int a, int b) const { Mat m = *this; m.off_ += (size_t)a * step_; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m = *this; m.off_ += (size_t)a * esz(); m.cols = b - a; return m; }
+    Mat col(int j) const { return colRange(j, j + 1); }
+    Mat t() const {                                       // materialised transpose (f32)
+        Mat o(cols, rows, CV_32F);
+        for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) o.at<float>(j, i) = at<float>(i, j);
+        return o;
+    }
+    Mat clone() const {
+        Mat o(rows, cols, type_);
+        for (int i = 0; i < rows; ++i) std::memcpy(o.buf_->data() + (size_t)i * o.step_, buf_->data() + off_ + (size_t)i * step_, (size_t)cols * esz());
+        return o;
+    }
+    template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }                 // vectors: element i
+    template <class T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(buf_->data() + off_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
     template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(buf_->data() + off_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
     template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(buf_->data() + off_ + (size_t)r * step_); }
@@ -62,6 +75,28 @@ inline Mat operator-(const Mat& a, const Mat& b) {
     for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) o.at<float>(i, j) = a.at<float>(i, j) - b.at<float>(i, j);
     return o;
 }
+// Matrix products of float matrices as cv::gemm evaluates the MatExpr `alpha * A * B (+ C)` for small matrices
+// (GEMMSingleMul<float, double>): the dot products and the addition of C in double, one rounding to float at the end.
+struct MatScaled { Mat m; double alpha; };
+struct MatMul {
+    Mat a, b; double alpha;
+    Mat eval(const Mat* c) const {
+        Mat o(a.rows, b.cols, CV_32F);
+        for (int i = 0; i < a.rows; ++i)
+            for (int j = 0; j < b.cols; ++j) {
+                double s = 0;
+                for (int k = 0; k < a.cols; ++k) s += (double)a.at<float>(i, k) * (double)b.at<float>(k, j);
+                o.at<float>(i, j) = (float)(alpha * s + (c ? (double)c->at<float>(i, j) : 0.0));
+            }
+        return o;
+    }
+    operator Mat() const { return eval(nullptr); }
+};
+inline MatScaled operator-(const Mat& m) { return MatScaled{m, -1.0}; }
+inline MatMul operator*(const Mat& a, const Mat& b) { return MatMul{a, b, 1.0}; }
+inline MatMul operator*(const MatScaled& a, const Mat& b) { return MatMul{a.m, b, a.alpha}; }
+inline Mat operator+(const MatMul& ab, const Mat& c) { return ab.eval(&c); }
+
 inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {   // OpenCV: normDiffL1_<float, double>
     double s = 0;
     for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) s += std::fabs(a.at<float>(i, j) - b.at<float>(i, j));

@@ -89,5 +89,5 @@ if __name__ == "__main__":
     os.makedirs("profiles", exist_ok=True)
     note = os.environ.get("NCU_NOTE", f"{tag}")
     if os.path.exists(ll):
-        launch_shares(ll, f"profiles/{tag}_launch_shares.csv", f"{tag}: launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (default 2048 pairs per step; ORB step + masked + BA + search sections)")
+        launch_shares(ll, f"profiles/{tag}_launch_shares.csv", f"{tag}: launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (default 3072 pairs per step; ORB step + masked + BA + search sections)")
     full_summary(reps, f"profiles/{tag}_ncu_full_summary.csv", f"profiles/{tag}_dram_traffic.json", note)
