@@ -111,3 +111,22 @@ def test_bow_searches_on_device(adb, oracle_mod, mode):
     one = m.search_by_bow([probs[2]])[0]
     assert one[0] == got[2][0] and (one[1] == got[2][1]).all()
     m.close()
+
+
+@pytest.mark.parametrize("kind,i", [("last", 0), ("last", 1), ("last", 2), ("last", 3), ("last", 4), ("map", 0), ("map", 1), ("map", 2)])
+def test_cuda_search_equals_the_reference_function(adb, kind, i):
+    """CUDA searches against tests/golden/search_ref.npz: nmatches and final mvpMapPoints computed by the reference's own
+    ORBmatcher::SearchByProjection functions (src/ORBmatcher.cc:45-129, 1328-1470; compiled from /root/reference, oracle/ref_match.cpp)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_search_golden", os.path.join(root, "oracle", "gen_ref_search_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(root, "tests", "golden", "search_ref.npz"))
+    pr = g.last_problem(g.LAST_CASES[i]) if kind == "last" else g.map_problem(g.MAP_CASES[i])
+    assert g.problem_crc(pr) == int(gold[f"{kind}{i}_crc"])
+    m = adb.ORBmatcher(0.9 if kind == "last" else float(pr["nn_ratio"]), True)
+    n, km, _, _ = m.SearchByProjection(pr)
+    assert n == int(gold[f"{kind}{i}_n"])
+    assert (np.where(km >= 0, km, -1) == gold[f"{kind}{i}_kp_match"]).all()
+    m.close()
