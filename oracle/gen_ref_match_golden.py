@@ -38,6 +38,18 @@ def ref_stereo(L, kl, dl, kr, dr, pyr_l, pyr_r, scale, mb, mbf):
     return ur, dp
 
 
+def distinct_case(rng, n_points=300):
+    """Observation sets of n_points map points: CSR (descriptors [total, 32], point_ptr)."""
+    lens = rng.integers(0, 40, n_points); lens[:4] = [0, 1, 2, 128]
+    ptr = np.zeros(n_points + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    base = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+    desc = np.repeat(base, lens, axis=0)
+    flip = rng.random(desc.shape) < 0.04
+    desc = (desc ^ (flip * rng.integers(1, 256, desc.shape)).astype(np.uint8)).astype(np.uint8)
+    desc[ptr[5]:ptr[6]] = desc[ptr[5]]                            # all identical: every median is 0, the first row wins
+    return np.ascontiguousarray(desc), ptr
+
+
 CASES = [  # (seed, width, height, nfeatures, iniTh, minTh)
     (0, 640, 480, 1000, 12, 7), (7, 640, 480, 2000, 20, 7), (11, 320, 240, 500, 20, 7), (23, 752, 480, 1200, 12, 7)]
 
@@ -68,6 +80,13 @@ def main():
     L.ref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
     out["dd_pairs"] = d
     out["dd_dist"] = np.array([L.ref_descriptor_distance(P(np.ascontiguousarray(x[0])), P(np.ascontiguousarray(x[1]))) for x in d], np.int32)
+    # MapPoint::ComputeDistinctiveDescriptors on seeded observation sets (0, 1, 2, 128 observations, all-identical rows, noisy copies)
+    desc, ptr = distinct_case(np.random.default_rng(20261018))
+    chosen = np.full((len(ptr) - 1, 32), 0xAB, np.uint8)          # untouched where the point has no observation
+    L.ref_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_distinctive(P(desc), P(ptr), len(ptr) - 1, P(chosen))
+    out["distinct_crc"] = np.array([zlib.crc32(desc.tobytes()), zlib.crc32(ptr.tobytes())], np.int64)
+    out["distinct_chosen"] = chosen
     path = os.path.join(ROOT, "tests", "golden", "stereo_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

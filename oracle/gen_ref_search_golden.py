@@ -23,6 +23,8 @@ LAST_CASES = [  # (seed, n_kp, n_q, th, last_dz, mono, check_orientation): forwa
     (9, 2500, 2000, 10.0, 0.02, 0, 0)]
 MAP_CASES = [  # (seed, n_kp, n_q, th, nn_ratio)
     (15, 2000, 1500, 1.0, 0.8), (16, 3000, 3000, 3.0, 0.8), (17, 2000, 1800, 5.0, 0.6)]
+LOCAL_CASES = [  # Tracking::SearchLocalPoints: isInFrustum + PredictScale + SearchByProjection(F, vpMapPoints, th): (seed, n_kp, n_q, th, nn_ratio)
+    (25, 2000, 2500, 1.0, 0.8), (26, 3000, 3000, 3.0, 0.8), (27, 1500, 2000, 5.0, 0.8)]
 
 
 def P(a):
@@ -66,6 +68,37 @@ def map_problem(case):
     return out
 
 
+def local_problem(case, ow=None):
+    """Local map points before the visibility test.  `ow`: the camera centre as the reference's UpdatePoseMatrices derives it from Tcw
+    (float gemm); the generator asks the reference for it, the tests take it from the fixture."""
+    from airdos_b200 import synth
+    seed, n_kp, n_q, th, nn = case
+    pr = synth.make_tracking_problem(seed, n_kp=n_kp, n_q=n_q)
+    pm = synth.tracking_problem_as_local_map(pr, seed=seed, nn_ratio=nn, th=th)
+    if ow is not None:
+        pm["ow"] = np.asarray(ow, np.float32)
+    return pm
+
+
+def ref_local(L, pm):
+    from airdos_b200.capi import KP_DTYPE
+    kps = np.ascontiguousarray(pm["kps"], KP_DTYPE); nk = len(kps); nq = len(pm["q_flags"])
+    fx, fy, cx, cy, mbf, mb = [float(v) for v in pm["cam"]]
+    mnx, mny, mxx, mxy = [float(v) for v in pm["bounds"]]
+    sf = np.ascontiguousarray(pm["scale_factors"], np.float32)
+    a = [np.ascontiguousarray(pm[k], t) for k, t in (("u_right", np.float32), ("desc", np.uint8), ("taken", np.uint8), ("tcw_cur", np.float32),
+                                                     ("mp_xw", np.float32), ("mp_normal", np.float32), ("mp_min_distance", np.float32),
+                                                     ("mp_max_distance", np.float32), ("q_desc", np.uint8), ("q_flags", np.uint8))]
+    km = np.zeros(nk, np.int32); inview = np.zeros(nq, np.uint8); track = np.zeros((nq, 4), np.float32); level = np.zeros(nq, np.int32); ow = np.zeros(3, np.float32)
+    L.ref_search_local_map.restype = C.c_int
+    L.ref_search_local_map.argtypes = ([C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 +
+                                       [C.c_float] * 9 + [C.c_void_p] * 5)
+    n = L.ref_search_local_map(P(kps), P(a[0]), P(a[1]), P(a[2]), nk, mnx, mny, mxx, mxy, P(sf), len(sf), P(a[3]), nq, P(a[4]), P(a[5]), P(a[6]), P(a[7]),
+                               P(a[8]), P(a[9]), fx, fy, cx, cy, mbf, float(pm["view_cos_limit"]), float(pm["log_scale_factor"]), float(pm["th"]),
+                               float(pm["nn_ratio"]), P(km), P(inview), P(track), P(level), P(ow))
+    return int(n), km, inview, track, level, ow
+
+
 def ref_last(L, pr):
     from airdos_b200.capi import KP_DTYPE
     kps = np.ascontiguousarray(pr["kps"], KP_DTYPE); nk = len(kps); nq = len(pr["q_flags"])
@@ -102,7 +135,7 @@ def ref_map(L, pr):
 
 def problem_crc(pr):
     keys = [k for k in ("kps", "u_right", "desc", "taken", "q_desc", "q_angle", "q_flags", "last_xw", "last_octave", "tcw_cur", "tcw_last", "q_u", "q_v",
-                        "q_ur", "q_radius", "view_cos", "level") if k in pr]
+                        "q_ur", "q_radius", "view_cos", "level", "mp_xw", "mp_normal", "mp_min_distance", "mp_max_distance") if k in pr]
     return crc(*[pr[k] for k in keys])
 
 
@@ -110,7 +143,7 @@ def main():
     import oracle
     oracle.build()
     L = C.CDLL(LIB)
-    out = {"last_cases": np.array(LAST_CASES, np.float64), "map_cases": np.array(MAP_CASES, np.float64)}
+    out = {"last_cases": np.array(LAST_CASES, np.float64), "map_cases": np.array(MAP_CASES, np.float64), "local_cases": np.array(LOCAL_CASES, np.float64)}
     for i, case in enumerate(LAST_CASES):
         pr = last_problem(case)
         n, km = ref_last(L, pr)
@@ -121,6 +154,12 @@ def main():
         n, km = ref_map(L, pr)
         out[f"map{i}_n"] = np.int32(n); out[f"map{i}_kp_match"] = km; out[f"map{i}_crc"] = np.int64(problem_crc(pr))
         print(f"map-point case {i}: {n} matches of {len(pr['q_flags'])} map points")
+    for i, case in enumerate(LOCAL_CASES):
+        pm = local_problem(case)
+        n, km, inview, track, level, ow = ref_local(L, pm)
+        out[f"local{i}_n"] = np.int32(n); out[f"local{i}_kp_match"] = km; out[f"local{i}_crc"] = np.int64(problem_crc(pm))
+        out[f"local{i}_in_view"] = inview; out[f"local{i}_track"] = track; out[f"local{i}_level"] = level; out[f"local{i}_ow"] = ow
+        print(f"local-map case {i}: {int(inview.sum())} of {len(inview)} points in view, {n} matches; |ow - float64 ow| = {np.abs(ow - pm['ow']).max():.2e}")
     path = os.path.join(ROOT, "tests", "golden", "search_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

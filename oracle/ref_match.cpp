@@ -12,6 +12,8 @@
 #include <cassert>
 #include <climits>
 #include <cmath>
+#include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -21,19 +23,28 @@ namespace ORB_SLAM2 {
 using namespace std;   // src/Frame.cc and src/ORBmatcher.cc both open with it
 
 class Frame;
+class KeyFrame;
 class MapPoint {                         // include/MapPoint.h: what the matcher reads of a map point
 public:
     cv::Mat GetWorldPos() { return mWorldPos.clone(); }         // src/MapPoint.cc:79-83
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }     // src/MapPoint.cc:312-316
     int Observations() { return nObs; }                         // src/MapPoint.cc:134-138
     bool isBad() { return mbBad; }
+    cv::Mat GetNormal() { return mNormalVector.clone(); }       // src/MapPoint.cc:85-89
+    float GetMinDistanceInvariance();
+    float GetMaxDistanceInvariance();
+    int PredictScale(const float& currentDist, Frame* pF);
+    void ComputeDistinctiveDescriptors();
     // variables used by the tracking (include/MapPoint.h:87-94)
     float mTrackProjX, mTrackProjY, mTrackProjXR;
     bool mbTrackInView;
     int mnTrackScaleLevel;
     float mTrackViewCos;
     // stand-in state
-    cv::Mat mWorldPos, mDescriptor;
+    cv::Mat mWorldPos, mDescriptor, mNormalVector;
+    float mfMinDistance = 0, mfMaxDistance = 0;                 // include/MapPoint.h:141-142
+    std::mutex mMutexPos, mMutexFeatures;
+    std::map<KeyFrame*, size_t> mObservations;                  // include/MapPoint.h:111
     int nObs = 0;
     bool mbBad = false;
     int id = -1;                          // index of the query this point stands for (-100: a point the frame held on entry)
@@ -45,10 +56,13 @@ public:
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
 protected:
+    bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrame* pKF);
     float RadiusByViewingCos(const float& viewCos);
     void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     float mfNNratio;
@@ -63,12 +77,18 @@ public:
     std::vector<cv::Mat> mvImagePyramid;
 };
 
+}  // namespace ORB_SLAM2
+namespace DBoW2 { typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector; }   // Thirdparty/DBoW2/DBoW2/FeatureVector.h:25-26
+namespace ORB_SLAM2 {
+
 #define FRAME_GRID_ROWS 48               // include/Frame.h:41-42
 #define FRAME_GRID_COLS 64
 
 class Frame {                            // include/Frame.h: the members the extracted functions touch, with the reference's names
 public:
     void ComputeStereoMatches();
+    void UpdatePoseMatrices();
+    bool isInFrustum(MapPoint* pMP, float viewingCosLimit);
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
     void AssignFeaturesToGrid();
@@ -83,10 +103,32 @@ public:
     std::vector<bool> mvbOutlier;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    DBoW2::FeatureVector mFeatVec;
     cv::Mat mTcw;
+    cv::Mat mRcw, mtcw, mRwc, mOw;
+    float mfLogScaleFactor;
     int mnScaleLevels;
     vector<float> mvScaleFactors, mvInvScaleFactors;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+class KeyFrame {                         // include/KeyFrame.h: what the two vocabulary-bucket searches read of a key-frame
+public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }          // src/KeyFrame.cc:258-262
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }        // src/KeyFrame.cc:264-268
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
+    bool isBad() { return false; }
+    float fx, fy, cx, cy;
+    int N;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<float> mvScaleFactors, mvLevelSigma2;
+    // stand-in state
+    std::vector<MapPoint*> mvpMapPoints;
+    cv::Mat Ow, Rcw, tcw;
 };
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
@@ -131,7 +173,7 @@ void ref_stereo_match(const RefKp* kl, const uint8_t* dl, int nl_kp, const RefKp
 namespace {
 struct CurFrame {
     ORB_SLAM2::Frame F;
-    std::vector<ORB_SLAM2::MapPoint> held;
+    std::unique_ptr<ORB_SLAM2::MapPoint[]> held;       // (a MapPoint owns a mutex: not movable)
     CurFrame(const RefKp* kps, const float* u_right, const uint8_t* desc, const uint8_t* taken, int n_kp, float minX, float minY, float maxX,
              float maxY, const float* scale, int nlevels) {
         using namespace ORB_SLAM2;
@@ -145,7 +187,7 @@ struct CurFrame {
         Frame::mnMinX = minX; Frame::mnMinY = minY; Frame::mnMaxX = maxX; Frame::mnMaxY = maxY;
         Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);     // src/Frame.cc:113-114
         Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
-        held.resize(n_kp);
+        held.reset(new MapPoint[n_kp]);
         F.mvpMapPoints.assign(n_kp, static_cast<MapPoint*>(nullptr));
         for (int i = 0; i < n_kp; ++i)
             if (taken && taken[i]) { held[i].nObs = 1; held[i].id = -100; F.mvpMapPoints[i] = &held[i]; }
@@ -204,6 +246,130 @@ int ref_search_map_points(const RefKp* kps, const float* u_right, const uint8_t*
     const int n = matcher.SearchByProjection(cur.F, vp, th);
     cur.result(kp_match);
     return n;
+}
+
+// Tracking::SearchLocalPoints' hot part (src/Tracking.cc:1319-1343): Frame::isInFrustum(pMP, 0.5) with MapPoint::PredictScale for every
+// local map point that reaches the test (flags bit 0), then SearchByProjection(F, vpMapPoints, th).  The camera centre is the one the
+// reference's own UpdatePoseMatrices derives from Tcw (returned in ow_out so that the oracle can be given the same value).
+int ref_search_local_map(const RefKp* kps, const float* u_right, const uint8_t* desc, const uint8_t* taken, int n_kp, float minX, float minY, float maxX,
+                         float maxY, const float* scale, int nlevels, const float* tcw16, int n_q, const float* xw, const float* normal,
+                         const float* min_distance, const float* max_distance, const uint8_t* q_desc, const uint8_t* q_flags, float fx, float fy, float cx,
+                         float cy, float mbf, float view_cos_limit, float log_scale_factor, float th, float nn_ratio, int32_t* kp_match, uint8_t* in_view,
+                         float* track4, int32_t* level, float* ow_out) {
+    using namespace ORB_SLAM2;
+    CurFrame cur(kps, u_right, desc, taken, n_kp, minX, minY, maxX, maxY, scale, nlevels);
+    Frame& F = cur.F;
+    Frame::fx = fx; Frame::fy = fy; Frame::cx = cx; Frame::cy = cy;
+    F.mbf = mbf; F.mfLogScaleFactor = log_scale_factor;
+    F.mTcw = cv::Mat(4, 4, CV_32F, tcw16);
+    F.UpdatePoseMatrices();
+    for (int k = 0; k < 3; ++k) ow_out[k] = F.mOw.at<float>(k);
+    std::vector<MapPoint> mps(n_q);
+    std::vector<MapPoint*> vp;
+    for (int i = 0; i < n_q; ++i) {
+        MapPoint& m = mps[i];
+        m.id = i; m.nObs = (q_flags[i] & 2) ? 1 : 0;
+        m.mWorldPos = cv::Mat(3, 1, CV_32F, xw + 3 * i); m.mNormalVector = cv::Mat(3, 1, CV_32F, normal + 3 * i);
+        m.mfMinDistance = min_distance[i]; m.mfMaxDistance = max_distance[i];
+        m.mDescriptor = cv::Mat(1, 32, CV_8U, q_desc + 32 * i);
+        m.mbTrackInView = false; m.mTrackProjX = m.mTrackProjY = m.mTrackProjXR = m.mTrackViewCos = 0.f; m.mnTrackScaleLevel = -1;
+        if (q_flags[i] & 1) F.isInFrustum(&m, view_cos_limit);
+        in_view[i] = m.mbTrackInView ? 1 : 0;
+        track4[4 * i] = m.mTrackProjX; track4[4 * i + 1] = m.mTrackProjY; track4[4 * i + 2] = m.mTrackProjXR; track4[4 * i + 3] = m.mTrackViewCos;
+        level[i] = m.mnTrackScaleLevel;
+        vp.push_back(&m);
+    }
+    ORBmatcher matcher(nn_ratio, true);
+    const int n = matcher.SearchByProjection(F, vp, th);
+    cur.result(kp_match);
+    return n;
+}
+
+// The two vocabulary-bucket searches on the problem dicts of airdos_b200/synth.py::make_bow_problem.  fv*_node / fv*_ptr / fv*_idx:
+// the FeatureVector of each side as (ascending node ids, CSR of feature indices) -- nodes present on one side only included, so the
+// reference's lower_bound walk is exercised.
+namespace {
+DBoW2::FeatureVector make_fv(const int32_t* node, const int32_t* ptr, const int32_t* idx, int n_nodes) {
+    DBoW2::FeatureVector fv;
+    for (int j = 0; j < n_nodes; ++j) fv[(unsigned)node[j]] = std::vector<unsigned int>(idx + ptr[j], idx + ptr[j + 1]);
+    return fv;
+}
+void fill_kf(ORB_SLAM2::KeyFrame& kf, const RefKp* kps, const uint8_t* desc, int n) {
+    kf.N = n; kf.mvKeysUn.resize(n);
+    for (int i = 0; i < n; ++i) { kf.mvKeysUn[i].pt.x = kps[i].x; kf.mvKeysUn[i].pt.y = kps[i].y; kf.mvKeysUn[i].angle = kps[i].angle; kf.mvKeysUn[i].octave = kps[i].octave; }
+    kf.mDescriptors = cv::Mat(n, 32, CV_8U, desc);
+}
+}  // namespace
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)   src/ORBmatcher.cc:159-288
+// side 1 = the key-frame (flags1: key-points that hold a good map point), side 2 = the frame; match21[i2] = key-frame index or -1
+int ref_search_by_bow(const RefKp* k1, const uint8_t* d1, const uint8_t* flags1, int n1, const RefKp* k2, const uint8_t* d2, int n2, const int32_t* node1,
+                      const int32_t* ptr1, const int32_t* idx1, int nn1, const int32_t* node2, const int32_t* ptr2, const int32_t* idx2, int nn2, float nn_ratio,
+                      int check_ori, int32_t* match21) {
+    using namespace ORB_SLAM2;
+    KeyFrame kf; fill_kf(kf, k1, d1, n1);
+    std::vector<MapPoint> mps(n1);
+    kf.mvpMapPoints.assign(n1, static_cast<MapPoint*>(nullptr));
+    for (int i = 0; i < n1; ++i) { mps[i].id = i; if (flags1[i]) kf.mvpMapPoints[i] = &mps[i]; }
+    kf.mFeatVec = make_fv(node1, ptr1, idx1, nn1);
+    Frame F;
+    F.N = n2; F.mvKeys.resize(n2);
+    for (int i = 0; i < n2; ++i) { F.mvKeys[i].angle = k2[i].angle; F.mvKeys[i].octave = k2[i].octave; F.mvKeys[i].pt.x = k2[i].x; F.mvKeys[i].pt.y = k2[i].y; }
+    F.mDescriptors = cv::Mat(n2, 32, CV_8U, d2);
+    F.mFeatVec = make_fv(node2, ptr2, idx2, nn2);
+    std::vector<MapPoint*> matches;
+    ORBmatcher matcher(nn_ratio, check_ori != 0);
+    const int n = matcher.SearchByBoW(&kf, F, matches);
+    for (int i = 0; i < n2; ++i) match21[i] = matches[i] ? matches[i]->id : -1;
+    return n;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)   src/ORBmatcher.cc:657-823 (+ CheckDistEpipolarLine :140-157)
+// flags: key-points that already hold a map point (skipped); cam2 = fx, fy, cx, cy of key-frame 2; ow1 / r2w / t2w give the epipole
+int ref_search_for_triangulation(const RefKp* k1, const float* ur1, const uint8_t* d1, const uint8_t* has_mp1, int n1, const RefKp* k2, const float* ur2,
+                                 const uint8_t* d2, const uint8_t* has_mp2, int n2, const int32_t* node1, const int32_t* ptr1, const int32_t* idx1, int nn1,
+                                 const int32_t* node2, const int32_t* ptr2, const int32_t* idx2, int nn2, const float* f12_9, const float* ow1_3,
+                                 const float* r2w_9, const float* t2w_3, const float* cam2_4, const float* scale2, const float* sigma2_2, int nlevels,
+                                 float nn_ratio, int check_ori, int only_stereo, int32_t* match12) {
+    using namespace ORB_SLAM2;
+    KeyFrame a, b; fill_kf(a, k1, d1, n1); fill_kf(b, k2, d2, n2);
+    a.mvuRight.assign(ur1, ur1 + n1); b.mvuRight.assign(ur2, ur2 + n2);
+    std::vector<MapPoint> m1(n1), m2(n2);
+    a.mvpMapPoints.assign(n1, static_cast<MapPoint*>(nullptr)); b.mvpMapPoints.assign(n2, static_cast<MapPoint*>(nullptr));
+    for (int i = 0; i < n1; ++i) if (has_mp1[i]) a.mvpMapPoints[i] = &m1[i];
+    for (int i = 0; i < n2; ++i) if (has_mp2[i]) b.mvpMapPoints[i] = &m2[i];
+    a.mFeatVec = make_fv(node1, ptr1, idx1, nn1); b.mFeatVec = make_fv(node2, ptr2, idx2, nn2);
+    a.Ow = cv::Mat(3, 1, CV_32F, ow1_3);
+    b.Rcw = cv::Mat(3, 3, CV_32F, r2w_9); b.tcw = cv::Mat(3, 1, CV_32F, t2w_3);
+    b.fx = cam2_4[0]; b.fy = cam2_4[1]; b.cx = cam2_4[2]; b.cy = cam2_4[3];
+    b.mvScaleFactors.assign(scale2, scale2 + nlevels); b.mvLevelSigma2.assign(sigma2_2, sigma2_2 + nlevels);
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher matcher(nn_ratio, check_ori != 0);
+    const int n = matcher.SearchForTriangulation(&a, &b, cv::Mat(3, 3, CV_32F, f12_9), pairs, only_stereo != 0);
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (const auto& pr : pairs) match12[pr.first] = (int32_t)pr.second;
+    return n;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:245-310) for n_points map points; the observations of point p are the
+// descriptors desc[point_ptr[p] .. point_ptr[p + 1]), one per key-frame.  The reference walks std::map<KeyFrame*, size_t>, i.e. in
+// ADDRESS order of the key-frames: they are allocated as one array here, so that order is the order given.
+void ref_distinctive(const uint8_t* desc, const int32_t* point_ptr, int n_points, uint8_t* out_desc) {
+    using namespace ORB_SLAM2;
+    int max_obs = 1;
+    for (int p = 0; p < n_points; ++p) max_obs = std::max(max_obs, point_ptr[p + 1] - point_ptr[p]);
+    std::unique_ptr<KeyFrame[]> kfs(new KeyFrame[max_obs]);
+    for (int p = 0; p < n_points; ++p) {
+        const int n = point_ptr[p + 1] - point_ptr[p];
+        MapPoint mp;
+        mp.mDescriptor = cv::Mat(1, 32, CV_8U, out_desc + 32 * p);          // left as it is when there is no observation
+        for (int k = 0; k < n; ++k) {
+            kfs[k].mDescriptors = cv::Mat(1, 32, CV_8U, desc + 32 * (size_t)(point_ptr[p] + k));
+            mp.mObservations[&kfs[k]] = 0;
+        }
+        mp.ComputeDistinctiveDescriptors();
+        std::memcpy(out_desc + 32 * p, mp.mDescriptor.ptr<uint8_t>(), 32);
+    }
 }
 
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {

@@ -44,6 +44,11 @@ public:
         for (int i = 0; i < rows; ++i) std::memcpy(o.buf_->data() + (size_t)i * o.step_, buf_->data() + off_ + (size_t)i * step_, (size_t)cols * esz());
         return o;
     }
+    double dot(const Mat& o) const {                      // cv::Mat::dot on float data: dotProd_<float> accumulates in double
+        double s = 0;
+        for (int i = 0; i < rows; ++i) for (int j = 0; j < cols; ++j) s += (double)at<float>(i, j) * (double)o.at<float>(i, j);
+        return s;
+    }
     template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }                 // vectors: element i
     template <class T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(buf_->data() + off_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
@@ -97,6 +102,11 @@ inline MatMul operator*(const Mat& a, const Mat& b) { return MatMul{a, b, 1.0}; 
 inline MatMul operator*(const MatScaled& a, const Mat& b) { return MatMul{a.m, b, a.alpha}; }
 inline Mat operator+(const MatMul& ab, const Mat& c) { return ab.eval(&c); }
 
+inline double norm(const Mat& a) {                      // NORM_L2 of a float matrix: squares accumulated in double (normL2_<float, double>)
+    double s = 0;
+    for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) s += (double)a.at<float>(i, j) * (double)a.at<float>(i, j);
+    return std::sqrt(s);
+}
 inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {   // OpenCV: normDiffL1_<float, double>
     double s = 0;
     for (int i = 0; i < a.rows; ++i) for (int j = 0; j < a.cols; ++j) s += std::fabs(a.at<float>(i, j) - b.at<float>(i, j));

@@ -139,3 +139,22 @@ def test_cuda_stereo_equals_the_reference_function(ci):
     assert (ur[0, :n].view(np.uint32) == g[f"c{ci}_u_right"].view(np.uint32)).all()
     assert (dp[0, :n].view(np.uint32) == g[f"c{ci}_depth"].view(np.uint32)).all()
     exL.close(); exR.close()
+
+
+def test_cuda_distinctive_descriptor_equals_the_reference_function(adb):
+    """adb_distinctive_descriptors against the descriptors the reference's own MapPoint::ComputeDistinctiveDescriptors
+    (src/MapPoint.cc:245-310, compiled from /root/reference) left in mDescriptor: tests/golden/stereo_ref.npz."""
+    import importlib.util
+    import os
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_match_golden", os.path.join(root, "oracle", "gen_ref_match_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(root, "tests", "golden", "stereo_ref.npz"))
+    desc, ptr = g.distinct_case(np.random.default_rng(20261018))
+    assert [zlib.crc32(desc.tobytes()), zlib.crc32(ptr.tobytes())] == [int(v) for v in gold["distinct_crc"]]
+    m = adb.ORBmatcher()
+    bi, bd = adb.compute_distinctive_descriptors(m, desc, ptr)
+    has = ptr[1:] > ptr[:-1]
+    assert (bd[has] == gold["distinct_chosen"][has]).all() and (bi[~has] == -1).all()
+    m.close()

@@ -52,6 +52,26 @@ def test_oracle_hamming_equals_the_reference_function(gold, oracle_mod):
     assert (gold["dd_dist"][:8] == 0).all() and (gold["dd_dist"][8:16] == 256).all()
 
 
+def _gen():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_ref_match_golden", os.path.join(ROOT, "oracle", "gen_ref_match_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    return g
+
+
+def test_oracle_distinctive_descriptor_equals_the_reference_function(gold, oracle_mod):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:245-310) of the reference itself on 300 observation sets: the
+    descriptor it leaves in mDescriptor is the one the oracle's index points at."""
+    desc, ptr = _gen().distinct_case(np.random.default_rng(20261018))
+    assert [zlib.crc32(desc.tobytes()), zlib.crc32(ptr.tobytes())] == [int(v) for v in gold["distinct_crc"]]
+    best = oracle_mod.distinctive(desc, ptr)
+    for p in range(len(ptr) - 1):
+        if ptr[p + 1] == ptr[p]:
+            assert best[p] == -1 and (gold["distinct_chosen"][p] == 0xAB).all()
+        else:
+            assert (desc[ptr[p] + best[p]] == gold["distinct_chosen"][p]).all(), p
+
+
 @pytest.mark.skipif(not (os.path.exists(REF_LIB) and os.path.isdir("/root/reference")), reason="reference tree / oracle/_ref not present (GPU box)")
 def test_fixture_is_what_the_reference_library_computes_now(gold, oracle_mod):
     import importlib.util

@@ -130,3 +130,46 @@ def test_cuda_search_equals_the_reference_function(adb, kind, i):
     assert n == int(gold[f"{kind}{i}_n"])
     assert (np.where(km >= 0, km, -1) == gold[f"{kind}{i}_kp_match"]).all()
     m.close()
+
+
+def test_cuda_bow_searches_equal_the_reference_functions(adb):
+    """CUDA vocabulary-bucket searches against tests/golden/bow_ref.npz: nmatches and the match tables computed by the reference's
+    own ORBmatcher::SearchByBoW / SearchForTriangulation (src/ORBmatcher.cc:159-288, 657-823; compiled from /root/reference)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_bow_golden", os.path.join(root, "oracle", "gen_ref_bow_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(root, "tests", "golden", "bow_ref.npz"))
+    probs = [g.problem(c) for c in g.CASES]
+    for i, pr in enumerate(probs):
+        assert g.problem_crc(pr) == int(gold[f"c{i}_crc"])
+    m = adb.ORBmatcher(0.7, True)
+    got = m.search_by_bow(probs)
+    for i, (n, match) in enumerate(got):
+        assert n == int(gold[f"c{i}_n"]) and (match == gold[f"c{i}_match"]).all(), i
+    m.close()
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_cuda_local_map_search_equals_the_reference_functions(adb, i):
+    """Tracking::SearchLocalPoints' hot part on the device against tests/golden/search_ref.npz: mbTrackInView, mTrackProjX / Y / XR /
+    mTrackViewCos (bit patterns), mnTrackScaleLevel, final mvpMapPoints and nmatches computed by the reference's own Frame::isInFrustum
+    (src/Frame.cc:587-643), MapPoint::PredictScale (src/MapPoint.cc:405-420) and SearchByProjection(F, vpMapPoints, th)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_search_golden", os.path.join(root, "oracle", "gen_ref_search_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(root, "tests", "golden", "search_ref.npz"))
+    pm = g.local_problem(g.LOCAL_CASES[i], gold[f"local{i}_ow"])
+    assert g.problem_crc(pm) == int(gold[f"local{i}_crc"])
+    m = adb.ORBmatcher(float(pm["nn_ratio"]), True)
+    got = m.SearchByProjection(pm)
+    n, km, track, level = got[0], got[1], got[4], got[5]
+    assert n == int(gold[f"local{i}_n"])
+    assert (np.where(km >= 0, km, -1) == gold[f"local{i}_kp_match"]).all()
+    assert ((level >= 0) == (gold[f"local{i}_in_view"] > 0)).all()
+    assert (level == gold[f"local{i}_level"]).all()
+    assert (track.view(np.uint32) == gold[f"local{i}_track"].view(np.uint32)).all()
+    m.close()
