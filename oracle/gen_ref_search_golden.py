@@ -23,6 +23,8 @@ LAST_CASES = [  # (seed, n_kp, n_q, th, last_dz, mono, check_orientation): forwa
     (9, 2500, 2000, 10.0, 0.02, 0, 0)]
 MAP_CASES = [  # (seed, n_kp, n_q, th, nn_ratio)
     (15, 2000, 1500, 1.0, 0.8), (16, 3000, 3000, 3.0, 0.8), (17, 2000, 1800, 5.0, 0.6)]
+FUSE_CASES = [  # ORBmatcher::Fuse(pKF, vpMapPoints, th): (seed, n_kp, n_q, th)
+    (35, 2000, 3000, 3.0), (36, 3000, 2500, 4.0), (37, 1500, 2000, 2.5)]
 LOCAL_CASES = [  # Tracking::SearchLocalPoints: isInFrustum + PredictScale + SearchByProjection(F, vpMapPoints, th): (seed, n_kp, n_q, th, nn_ratio)
     (25, 2000, 2500, 1.0, 0.8), (26, 3000, 3000, 3.0, 0.8), (27, 1500, 2000, 5.0, 0.8)]
 
@@ -99,6 +101,34 @@ def ref_local(L, pm):
     return int(n), km, inview, track, level, ow
 
 
+def fuse_problem(case, ow=None):
+    from airdos_b200 import synth
+    seed, n_kp, n_q, th = case
+    pr = synth.make_tracking_problem(seed, n_kp=n_kp, n_q=n_q, dup_frac=0.3)
+    pf = synth.tracking_problem_as_fuse(pr, seed=seed, th=th)
+    if ow is not None:
+        pf["ow"] = np.asarray(ow, np.float32)
+    return pf
+
+
+def ref_fuse(L, pf):
+    from airdos_b200.capi import KP_DTYPE
+    kps = np.ascontiguousarray(pf["kps"], KP_DTYPE); nk = len(kps); nq = len(pf["q_flags"])
+    fx, fy, cx, cy, mbf, mb = [float(v) for v in pf["cam"]]
+    mnx, mny, mxx, mxy = [float(v) for v in pf["bounds"]]
+    sf = np.ascontiguousarray(pf["scale_factors"], np.float32); isg = np.ascontiguousarray(pf["inv_level_sigma2"], np.float32)
+    a = [np.ascontiguousarray(pf[k], t) for k, t in (("u_right", np.float32), ("desc", np.uint8), ("tcw_cur", np.float32), ("mp_xw", np.float32),
+                                                     ("mp_normal", np.float32), ("mp_min_distance", np.float32), ("mp_max_distance", np.float32),
+                                                     ("q_desc", np.uint8), ("q_flags", np.uint8))]
+    fused = np.zeros(nq, np.int32); ow = np.zeros(3, np.float32)
+    L.ref_fuse.restype = C.c_int
+    L.ref_fuse.argtypes = ([C.c_void_p] * 3 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6 +
+                           [C.c_float] * 7 + [C.c_void_p, C.c_void_p])
+    n = L.ref_fuse(P(kps), P(a[0]), P(a[1]), nk, mnx, mny, mxx, mxy, P(sf), P(isg), len(sf), P(a[2]), nq, P(a[3]), P(a[4]), P(a[5]), P(a[6]), P(a[7]), P(a[8]),
+                   fx, fy, cx, cy, mbf, float(pf["log_scale_factor"]), float(pf["th"]), P(fused), P(ow))
+    return int(n), fused, ow
+
+
 def ref_last(L, pr):
     from airdos_b200.capi import KP_DTYPE
     kps = np.ascontiguousarray(pr["kps"], KP_DTYPE); nk = len(kps); nq = len(pr["q_flags"])
@@ -143,7 +173,8 @@ def main():
     import oracle
     oracle.build()
     L = C.CDLL(LIB)
-    out = {"last_cases": np.array(LAST_CASES, np.float64), "map_cases": np.array(MAP_CASES, np.float64), "local_cases": np.array(LOCAL_CASES, np.float64)}
+    out = {"last_cases": np.array(LAST_CASES, np.float64), "map_cases": np.array(MAP_CASES, np.float64), "local_cases": np.array(LOCAL_CASES, np.float64),
+           "fuse_cases": np.array(FUSE_CASES, np.float64)}
     for i, case in enumerate(LAST_CASES):
         pr = last_problem(case)
         n, km = ref_last(L, pr)
@@ -154,6 +185,11 @@ def main():
         n, km = ref_map(L, pr)
         out[f"map{i}_n"] = np.int32(n); out[f"map{i}_kp_match"] = km; out[f"map{i}_crc"] = np.int64(problem_crc(pr))
         print(f"map-point case {i}: {n} matches of {len(pr['q_flags'])} map points")
+    for i, case in enumerate(FUSE_CASES):
+        pf = fuse_problem(case)
+        n, fused, ow = ref_fuse(L, pf)
+        out[f"fuse{i}_n"] = np.int32(n); out[f"fuse{i}_fused_with"] = fused; out[f"fuse{i}_crc"] = np.int64(problem_crc(pf)); out[f"fuse{i}_ow"] = ow
+        print(f"fuse case {i}: {n} of {len(fused)} map points fused")
     for i, case in enumerate(LOCAL_CASES):
         pm = local_problem(case)
         n, km, inview, track, level, ow = ref_local(L, pm)

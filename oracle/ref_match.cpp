@@ -1,13 +1,18 @@
-// ref_match.cpp -- TEST INFRASTRUCTURE: the reference's own stereo matcher, compiled from /root/reference.
-//   src/Frame.cc       void Frame::ComputeStereoMatches()           (the whole function body, unmodified)
-//   src/ORBmatcher.cc  int ORBmatcher::DescriptorDistance(...)      (the whole function body, unmodified)
-// The two files cannot be compiled as they are (OpenCV, Eigen, DBoW2, Pangolin headers are absent and the rest of each file needs
-// them), so the build step (oracle/Makefile, target _ref/libref_match.so) copies the text of exactly these two function
-// definitions out of the reference tree into oracle/_ref/match_snippets.inc (git-ignored, never committed:
-// oracle/extract_ref_fn.py) and this file compiles that text between stand-in declarations of the classes it is a member of:
-// the members the statements read and write, with the reference's names and types, and oracle/ref_shim/cv_shim.h for the
-// handful of cv::Mat / cv::KeyPoint operations.  oracle/gen_ref_match_golden.py runs it on seeded stereo pairs and writes
-// tests/golden/stereo_ref.npz, which pins oracle/match_oracle.cpp (and through it the CUDA matcher) to the literal reference.
+// ref_match.cpp -- TEST INFRASTRUCTURE: the reference's own matcher-side functions, compiled from /root/reference.
+//   src/Frame.cc       ComputeStereoMatches, AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, UpdatePoseMatrices, isInFrustum
+//   src/ORBmatcher.cc  DescriptorDistance, RadiusByViewingCos, ComputeThreeMaxima, CheckDistEpipolarLine, SearchByProjection(Frame&,
+//                      vector<MapPoint*>&, th), SearchByProjection(Frame&, const Frame&, th, bMono), SearchByBoW(KeyFrame*, Frame&, ...),
+//                      SearchForTriangulation, Fuse(KeyFrame*, vector<MapPoint*>&, th)
+//   src/MapPoint.cc    GetMinDistanceInvariance, GetMaxDistanceInvariance, PredictScale (both overloads), ComputeDistinctiveDescriptors
+//   src/KeyFrame.cc    GetFeaturesInArea, IsInImage
+// -- every one the whole function definition, unmodified.  The files cannot be compiled as they are (OpenCV, Eigen, DBoW2, Pangolin
+// headers are absent and the rest of each file needs them), so the build step (oracle/Makefile, target _ref/libref_match.so) copies the
+// text of exactly these definitions out of the reference tree into oracle/_ref/match_snippets.inc (git-ignored, never committed:
+// oracle/extract_ref_fn.py) and this file compiles that text between stand-in declarations of the classes they are members of: the
+// members the statements read and write, with the reference's names and types, oracle/ref_shim/cv_shim.h for the handful of cv::Mat /
+// cv::KeyPoint operations, std::map for DBoW2::FeatureVector.  The map surgery at the end of Fuse is recorded, not performed.
+// oracle/gen_ref_{match,search,bow}_golden.py run the extern "C" wrappers below on seeded inputs and write tests/golden/
+// {stereo,search,bow}_ref.npz, which pin oracle/match_oracle.cpp (and through it, and directly, the CUDA kernels) to the literal reference.
 #include <algorithm>
 #include <cassert>
 #include <climits>
@@ -34,7 +39,13 @@ public:
     float GetMinDistanceInvariance();
     float GetMaxDistanceInvariance();
     int PredictScale(const float& currentDist, Frame* pF);
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
     void ComputeDistinctiveDescriptors();
+    // the map surgery at the end of ORBmatcher::Fuse is only RECORDED (it belongs to the host side): which key-point this point was fused with
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }   // src/MapPoint.cc:220-224
+    void AddObservation(KeyFrame* pKF, size_t idx) { mObservations[pKF] = idx; fused_with = (int)idx; }
+    void Replace(MapPoint* pMP);
+    int fused_with = -1;
     // variables used by the tracking (include/MapPoint.h:87-94)
     float mTrackProjX, mTrackProjY, mTrackProjXR;
     bool mbTrackInView;
@@ -58,6 +69,7 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo);
+    int Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -114,11 +126,22 @@ public:
 class KeyFrame {                         // include/KeyFrame.h: what the two vocabulary-bucket searches read of a key-frame
 public:
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }          // src/KeyFrame.cc:258-262
-    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }        // src/KeyFrame.cc:264-268
+    MapPoint* GetMapPoint(const size_t& idx) { last_asked = (int)idx; return mvpMapPoints[idx]; }   // src/KeyFrame.cc:264-268
     cv::Mat GetCameraCenter() { return Ow.clone(); }
     cv::Mat GetRotation() { return Rcw.clone(); }
     cv::Mat GetTranslation() { return tcw.clone(); }
     bool isBad() { return false; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }   // src/KeyFrame.cc:218-222
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
+    bool IsInImage(const float& x, const float& y) const;
+    float mbf, mfLogScaleFactor;
+    int mnScaleLevels;
+    std::vector<float> mvInvLevelSigma2;
+    int mnGridCols, mnGridRows;
+    float mfGridElementWidthInv, mfGridElementHeightInv;
+    int mnMinX, mnMinY, mnMaxX, mnMaxY;                             // include/KeyFrame.h:187-190 (const int there)
+    std::vector<std::vector<std::vector<size_t> > > mGrid;
+    int last_asked = -1;                                            // stand-in: the key-point index of the last GetMapPoint call
     float fx, fy, cx, cy;
     int N;
     std::vector<cv::KeyPoint> mvKeysUn;
@@ -130,6 +153,12 @@ public:
     std::vector<MapPoint*> mvpMapPoints;
     cv::Mat Ow, Rcw, tcw;
 };
+static KeyFrame* g_fuse_kf = nullptr;   // the key-frame of the running Fuse call (for the surgery record)
+// pMP->Replace(pMPinKF) / pMPinKF->Replace(pMP): either way the NEW point (id >= 0) and the key-point just asked for are fused
+void MapPoint::Replace(MapPoint* pMP) {
+    MapPoint* incoming = id >= 0 && fused_with < 0 ? this : pMP;
+    incoming->fused_with = g_fuse_kf->last_asked;
+}
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
@@ -300,6 +329,50 @@ void fill_kf(ORB_SLAM2::KeyFrame& kf, const RefKp* kps, const uint8_t* desc, int
     kf.mDescriptors = cv::Mat(n, 32, CV_8U, desc);
 }
 }  // namespace
+
+// ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, th)   src/ORBmatcher.cc:825-975, with KeyFrame::GetFeaturesInArea /
+// IsInImage (src/KeyFrame.cc:589-633) and MapPoint::PredictScale(dist, KeyFrame*) (src/MapPoint.cc:388-403).  The key-frame holds no map
+// point on entry; the surgery calls at the end are recorded, not performed: fused_with[i] = key-point that map point i was fused with, or -1.
+int ref_fuse(const RefKp* kps, const float* u_right, const uint8_t* desc, int n_kp, float minX, float minY, float maxX, float maxY, const float* scale,
+             const float* inv_sigma2, int nlevels, const float* tcw16, int n_q, const float* xw, const float* normal, const float* min_distance,
+             const float* max_distance, const uint8_t* q_desc, const uint8_t* q_flags, float fx, float fy, float cx, float cy, float mbf,
+             float log_scale_factor, float th, int32_t* fused_with, float* ow_out) {
+    using namespace ORB_SLAM2;
+    CurFrame cur(kps, u_right, desc, nullptr, n_kp, minX, minY, maxX, maxY, scale, nlevels);      // builds the grid the key-frame copies
+    Frame& F = cur.F;
+    F.mTcw = cv::Mat(4, 4, CV_32F, tcw16);
+    F.UpdatePoseMatrices();
+    KeyFrame kf; fill_kf(kf, kps, desc, n_kp);
+    kf.mvuRight.assign(u_right, u_right + n_kp);
+    kf.fx = fx; kf.fy = fy; kf.cx = cx; kf.cy = cy; kf.mbf = mbf; kf.mfLogScaleFactor = log_scale_factor; kf.mnScaleLevels = nlevels;
+    kf.mvScaleFactors.assign(scale, scale + nlevels); kf.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + nlevels);
+    kf.mnGridCols = FRAME_GRID_COLS; kf.mnGridRows = FRAME_GRID_ROWS;                              // src/KeyFrame.cc:33-44
+    kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    kf.mnMinX = Frame::mnMinX; kf.mnMinY = Frame::mnMinY; kf.mnMaxX = Frame::mnMaxX; kf.mnMaxY = Frame::mnMaxY;
+    kf.mGrid.resize(kf.mnGridCols);                                                               // src/KeyFrame.cc:52-58
+    for (int i = 0; i < kf.mnGridCols; i++) {
+        kf.mGrid[i].resize(kf.mnGridRows);
+        for (int j = 0; j < kf.mnGridRows; j++) kf.mGrid[i][j] = F.mGrid[i][j];
+    }
+    kf.Rcw = F.mRcw.clone(); kf.tcw = F.mtcw.clone(); kf.Ow = F.mOw.clone();                        // KeyFrame::SetPose, src/KeyFrame.cc:68-84
+    for (int k = 0; k < 3; ++k) ow_out[k] = kf.Ow.at<float>(k);
+    kf.mvpMapPoints.assign(n_kp, static_cast<MapPoint*>(nullptr));
+    std::unique_ptr<MapPoint[]> mps(new MapPoint[n_q]);
+    std::vector<MapPoint*> vp(n_q, static_cast<MapPoint*>(nullptr));
+    for (int i = 0; i < n_q; ++i) {
+        MapPoint& m = mps[i];
+        m.id = i; m.nObs = (q_flags[i] & 2) ? 1 : 0;
+        m.mWorldPos = cv::Mat(3, 1, CV_32F, xw + 3 * i); m.mNormalVector = cv::Mat(3, 1, CV_32F, normal + 3 * i);
+        m.mfMinDistance = min_distance[i]; m.mfMaxDistance = max_distance[i];
+        m.mDescriptor = cv::Mat(1, 32, CV_8U, q_desc + 32 * i);
+        if (q_flags[i] & 1) vp[i] = &m;
+    }
+    g_fuse_kf = &kf;
+    ORBmatcher matcher(0.6, true);
+    const int n = matcher.Fuse(&kf, vp, th);
+    for (int i = 0; i < n_q; ++i) fused_with[i] = mps[i].fused_with;
+    return n;
+}
 
 // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)   src/ORBmatcher.cc:159-288
 // side 1 = the key-frame (flags1: key-points that hold a good map point), side 2 = the frame; match21[i2] = key-frame index or -1

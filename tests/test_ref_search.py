@@ -58,6 +58,19 @@ def test_oracle_frustum_and_local_map_search_equal_the_reference_functions(gold,
     assert n == int(gold[f"local{i}_n"]) and (np.where(km >= 0, km, -1) == gold[f"local{i}_kp_match"]).all()
 
 
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_oracle_fuse_search_equals_the_reference_function(gold, oracle_mod, i):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:825-975) with KeyFrame::GetFeaturesInArea / IsInImage
+    (src/KeyFrame.cc:589-633) and MapPoint::PredictScale(dist, KeyFrame*) (src/MapPoint.cc:388-403) of the reference itself; its map
+    surgery (Replace / AddObservation / AddMapPoint) is recorded by the stand-ins: which key-point every map point was fused with."""
+    g = _gen()
+    pf = g.fuse_problem(g.FUSE_CASES[i], gold[f"fuse{i}_ow"])
+    assert g.problem_crc(pf) == int(gold[f"fuse{i}_crc"]), "synthetic generator drifted: regenerate the fixture"
+    n, km, bi, bd, _ = oracle_mod.search_by_projection(pf)
+    assert n == int(gold[f"fuse{i}_n"]) and n > 500
+    assert (np.where(bd <= 50, bi, -1) == gold[f"fuse{i}_fused_with"]).all()
+
+
 @pytest.mark.skipif(not (os.path.exists(REF_LIB) and os.path.isdir("/root/reference")), reason="reference tree / oracle/_ref not present (GPU box)")
 def test_fixture_is_what_the_reference_library_computes_now(gold, oracle_mod):
     import ctypes as C

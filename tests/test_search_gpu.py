@@ -173,3 +173,23 @@ def test_cuda_local_map_search_equals_the_reference_functions(adb, i):
     assert (level == gold[f"local{i}_level"]).all()
     assert (track.view(np.uint32) == gold[f"local{i}_track"].view(np.uint32)).all()
     m.close()
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_cuda_fuse_search_equals_the_reference_function(adb, i):
+    """The fuse mode of adb_search_by_projection against tests/golden/search_ref.npz: nFused and the key-point every map point was
+    fused with by the reference's own ORBmatcher::Fuse (src/ORBmatcher.cc:825-975, compiled from /root/reference)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_search_golden", os.path.join(root, "oracle", "gen_ref_search_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(root, "tests", "golden", "search_ref.npz"))
+    pf = g.fuse_problem(g.FUSE_CASES[i], gold[f"fuse{i}_ow"])
+    assert g.problem_crc(pf) == int(gold[f"fuse{i}_crc"])
+    m = adb.ORBmatcher(0.6, True)
+    got = m.SearchByProjection(pf)
+    n, bi, bd = got[0], got[2], got[3]
+    assert n == int(gold[f"fuse{i}_n"])
+    assert (np.where(bd <= 50, bi, -1) == gold[f"fuse{i}_fused_with"]).all()
+    m.close()
