@@ -56,6 +56,8 @@ def orb_lib() -> C.CDLL:
                                            C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orb_oracle_params.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        lib.orb_oracle_tables.argtypes = [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 7
+        lib.orb_oracle_orient_describe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib._typed = True
     return lib
 
@@ -123,6 +125,29 @@ def orb_params(nfeatures: int, scale: float, nlevels: int, w: int, h: int):
     sc = np.zeros(nlevels, np.float32); um = np.zeros(16, np.int32)
     orb_lib().orb_oracle_params(nfeatures, scale, nlevels, w, h, _p(lw), _p(lh), _p(q), _p(sc), _p(um))
     return {"w": lw, "h": lh, "quota": q, "scale": sc, "umax": um}
+
+
+def orb_tables(nfeatures: int, scale: float, nlevels: int, lib=None, prefix: str = "orb_oracle"):
+    """Constructor tables (src/ORBextractor.cc:411-472 + the pattern :151-409).  `lib` / `prefix` let the reference-built library
+    (oracle/_ref/libref_orb.so, prefix "ref") be called through the same signature."""
+    f = np.float32
+    sc, isc, s2, is2 = (np.zeros(nlevels, f) for _ in range(4))
+    q = np.zeros(nlevels, np.int32); um = np.zeros(16, np.int32); pat = np.zeros(1024, np.int32)
+    fn = orb_lib().orb_oracle_tables if lib is None else getattr(lib, "ref_extractor_tables")
+    fn.argtypes = [C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 7
+    fn(nfeatures, scale, nlevels, _p(sc), _p(isc), _p(s2), _p(is2), _p(q), _p(um), _p(pat))
+    return {"scale": sc, "inv_scale": isc, "sigma2": s2, "inv_sigma2": is2, "quota": q, "umax": um, "pattern": pat.reshape(512, 2)}
+
+
+def orient_describe(img: np.ndarray, blurred: np.ndarray, xy: np.ndarray, lib=None):
+    """IC_Angle + computeOrbDescriptor (src/ORBextractor.cc:78-148) at level coordinates xy [n, 2] -> (angle [n] f32, desc [n, 32] u8)."""
+    img = np.ascontiguousarray(img, np.uint8); blurred = np.ascontiguousarray(blurred, np.uint8); xy = np.ascontiguousarray(xy, np.float32)
+    h, w = img.shape
+    ang = np.zeros(len(xy), np.float32); desc = np.zeros((len(xy), 32), np.uint8)
+    fn = orb_lib().orb_oracle_orient_describe if lib is None else getattr(lib, "ref_orient_describe")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn(_p(img), _p(blurred), w, h, len(xy), _p(xy), _p(ang), _p(desc))
+    return ang, desc
 
 
 def orb_extract(img: np.ndarray, mask: np.ndarray | None = None, nfeatures: int = 1000, scale: float = 1.2,

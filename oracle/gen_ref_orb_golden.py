@@ -40,6 +40,53 @@ def make_case(i):
     return cand, w, h, n
 
 
+TABLE_CONFIGS = [(2000, 1.2, 8), (1000, 1.2, 8), (1500, 1.2, 8), (500, 1.5, 5), (3000, 1.1, 12), (1200, 2.0, 4), (700, 1.3, 1)]
+N_DESC_CASES = 6
+
+
+def make_desc_case(i):
+    """A level image (noise, smooth gradients + noise, or blocks: flat regions exercise the t0 < t1 ties and the zero-moment angle),
+    and key-point positions kept 19 pixels inside like the extractor's."""
+    rng = np.random.default_rng(91000 + i)
+    w, h = int(rng.integers(80, 400)), int(rng.integers(60, 300))
+    if i % 3 == 0:
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    elif i % 3 == 1:
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.clip(128 + 90 * np.sin(xx / 9.0 + i) * np.cos(yy / 7.0) + rng.normal(0, 6, (h, w)), 0, 255).astype(np.uint8)
+    else:
+        img = np.kron(rng.integers(0, 4, ((h + 15) // 16, (w + 15) // 16)) * 80, np.ones((16, 16), int))[:h, :w].astype(np.uint8)
+    n = int(rng.integers(50, 600))
+    xy = np.stack([rng.integers(19, w - 19, n), rng.integers(19, h - 19, n)], 1).astype(np.float32)
+    return img, xy
+
+
+def tables_main(L):
+    """tests/golden/extractor_tables_ref.npz: the reference's own constructor (src/ORBextractor.cc:411-472: scale / sigma^2 tables, quotas,
+    umax, and the pattern it copies from bit_pattern_31_ :151-409) and its IC_Angle / computeOrbDescriptor (:78-148) on seeded images."""
+    import oracle
+    out = {}
+    same = 0
+    for c, (nf, sf, nl) in enumerate(TABLE_CONFIGS):
+        r = oracle.orb_tables(nf, sf, nl, lib=L); o = oracle.orb_tables(nf, sf, nl)
+        same += int(all((r[k].view(np.int32) == o[k].view(np.int32)).all() for k in r))
+        for k, v in r.items():
+            if k != "pattern" or c == 0:
+                out[f"t{c}_{k}"] = v
+    dsame = 0
+    for i in range(N_DESC_CASES):
+        img, xy = make_desc_case(i)
+        bl = oracle.blur7(img)
+        ra, rd = oracle.orient_describe(img, bl, xy, lib=L); oa, od = oracle.orient_describe(img, bl, xy)
+        dsame += int((ra.view(np.int32) == oa.view(np.int32)).all() and (rd == od).all())
+        out[f"d{i}_angle"] = ra; out[f"d{i}_desc"] = rd
+    print(f"tables: oracle equals the reference constructor in {same} of {len(TABLE_CONFIGS)} configurations; "
+          f"IC_Angle / computeOrbDescriptor bit-identical in {dsame} of {N_DESC_CASES} images")
+    path = os.path.join(ROOT, "tests", "golden", "extractor_tables_ref.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     import oracle
     oracle.build()
@@ -60,6 +107,7 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "quadtree_ref.npz")
     np.savez_compressed(path, crc=np.array(crcs, np.int64), count=np.array(counts, np.int32), same_with_stock_malloc=np.int32(same_malloc), **keep)
     print("wrote", path, os.path.getsize(path), "bytes")
+    tables_main(L)
 
 
 if __name__ == "__main__":

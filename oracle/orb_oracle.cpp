@@ -641,6 +641,31 @@ void orb_oracle_params(int nfeatures, float sf, int nlevels, int w, int h, int32
     for (int v = 0; v <= kHalfPatch; ++v) umax16[v] = ex.umax[v];
 }
 
+// Constructor tables as the reference's getters return them (include/ORBextractor.h:63-85, src/ORBextractor.cc:411-472): scale factors,
+// their inverses, sigma^2 = scale^2 and its inverse, per-level quotas, umax, and the 512 (x, y) pattern points (:151-409).
+void orb_oracle_tables(int nfeatures, float sf, int nlevels, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* quota,
+                       int32_t* umax16, int32_t* pattern1024) {
+    Extractor ex(nfeatures, sf, nlevels, 20, 7);
+    for (int l = 0; l < nlevels; ++l) {
+        scale[l] = ex.scale[l]; inv_scale[l] = ex.invScale[l];
+        sigma2[l] = ex.scale[l] * ex.scale[l]; inv_sigma2[l] = 1.0f / sigma2[l];
+        quota[l] = ex.quota[l];
+    }
+    for (int v = 0; v <= kHalfPatch; ++v) umax16[v] = ex.umax[v];
+    for (int i = 0; i < 512; ++i) { pattern1024[2 * i] = kPatX[i]; pattern1024[2 * i + 1] = kPatY[i]; }
+}
+
+// IC_Angle + computeOrbDescriptor (src/ORBextractor.cc:78-148) for n key-points at level coordinates xy of one level image (tight pitch w)
+// and its blurred copy; the caller keeps the points 19 pixels inside.
+void orb_oracle_orient_describe(const uint8_t* img, const uint8_t* blurred, int w, int h, int n, const float* xy, float* angle_out, uint8_t* desc_out) {
+    (void)h;
+    Extractor ex(2000, 1.2f, 8, 20, 7);
+    for (int i = 0; i < n; ++i) {
+        angle_out[i] = ic_angle(img, w, xy[2 * i], xy[2 * i + 1], ex.umax);
+        rbrief(blurred, w, xy[2 * i], xy[2 * i + 1], angle_out[i], desc_out + 32 * i);
+    }
+}
+
 // Full extractor.  kps: cap records of 24 B; desc: cap x 32 B.  Optional outputs:
 //   pyr_out   -- the nlevels ROIs packed back to back (tight pitch = level width)
 //   cand_counts[nlevels] -- number of FAST candidates per level before distribution

@@ -46,9 +46,7 @@ void operator delete[](void* p) noexcept { if (p && !in_arena(p)) std::free(p); 
 void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
 void operator delete[](void* p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
 
-namespace cv {
-struct Point2i { int x = 0, y = 0; Point2i() {} Point2i(int x_, int y_) : x(x_), y(y_) {} };
-}
+#define CV_PI 3.1415926535897932384626433832795
 
 namespace ORB_SLAM2 {
 using namespace std;
@@ -64,13 +62,35 @@ public:
     bool bNoMore;
 };
 
-class ORBextractor {     // include/ORBextractor.h:51-112: the one member function under test
+class ORBextractor {     // include/ORBextractor.h:51-112: the constructor, DistributeOctTree and the members they touch
 public:
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
     std::vector<cv::KeyPoint> DistributeOctTree(const std::vector<cv::KeyPoint>& vToDistributeKeys, const int& minX, const int& maxX, const int& minY,
                                                 const int& maxY, const int& nFeatures, const int& level);
-    int nfeatures = 2000;   // include/ORBextractor.h:95 (DistributeOctTree only reserves with it)
+    std::vector<cv::Mat> mvImagePyramid;
+    std::vector<cv::Mat> mvMaskPyramid;     // AirDOS addition (include/ORBextractor.h)
+    std::vector<cv::Point> pattern;
+    int nfeatures;
+    double scaleFactor;
+    int nlevels;
+    int iniThFAST;
+    int minThFAST;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<int> umax;
+    std::vector<float> mvScaleFactor;
+    std::vector<float> mvInvScaleFactor;
+    std::vector<float> mvLevelSigma2;
+    std::vector<float> mvInvLevelSigma2;
 };
 
+const int PATCH_SIZE = 31;         // src/ORBextractor.cc:72-74
+const int HALF_PATCH_SIZE = 15;
+const int EDGE_THRESHOLD = 19;
+const float factorPI = (float)(CV_PI/180.f);   // src/ORBextractor.cc:108
+
+// static int bit_pattern_31_[256*4] = { ... }   src/ORBextractor.cc:151-409, taken from the reference tree like the functions
+#include "_ref/orb_pattern.inc"
+;
 #include "_ref/orb_snippets.inc"
 
 }  // namespace ORB_SLAM2
@@ -87,7 +107,7 @@ int ref_distribute(const float* cand, int m, int minX, int maxX, int minY, int m
     {
     std::vector<cv::KeyPoint> v(m);
     for (int i = 0; i < m; ++i) { v[i].pt.x = cand[3 * i]; v[i].pt.y = cand[3 * i + 1]; v[i].response = cand[3 * i + 2]; }
-    ORB_SLAM2::ORBextractor ex;
+    ORB_SLAM2::ORBextractor ex(2000, 1.2f, 8, 20, 7);
     const std::vector<cv::KeyPoint> r = ex.DistributeOctTree(v, minX, maxX, minY, maxY, N, 0);
     const int n = std::min((int)r.size(), cap);
     for (int i = 0; i < n; ++i) { out[3 * i] = r[i].pt.x; out[3 * i + 1] = r[i].pt.y; out[3 * i + 2] = r[i].response; }
@@ -95,6 +115,33 @@ int ref_distribute(const float* cand, int m, int minX, int maxX, int minY, int m
     }
     g_monotonic = false;
     return total;
+}
+
+// ORBextractor::ORBextractor (src/ORBextractor.cc:411-472): scale factors, sigma^2, per-level quotas, umax and the pattern as the reference
+// builds them.  out arrays: [nlevels] each; umax16: [16]; pattern1024: 512 (x, y) pairs
+void ref_extractor_tables(int nfeatures, float scale_factor, int nlevels, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota,
+                          int* umax16, int* pattern1024) {
+    ORB_SLAM2::ORBextractor ex(nfeatures, scale_factor, nlevels, 20, 7);
+    for (int l = 0; l < nlevels; ++l) {
+        scale[l] = ex.mvScaleFactor[l]; inv_scale[l] = ex.mvInvScaleFactor[l]; sigma2[l] = ex.mvLevelSigma2[l]; inv_sigma2[l] = ex.mvInvLevelSigma2[l];
+        quota[l] = ex.mnFeaturesPerLevel[l];
+    }
+    for (int v = 0; v < 16; ++v) umax16[v] = ex.umax[v];
+    for (int i = 0; i < 512; ++i) { pattern1024[2 * i] = ex.pattern[i].x; pattern1024[2 * i + 1] = ex.pattern[i].y; }
+}
+
+// IC_Angle (src/ORBextractor.cc:78-105) and computeOrbDescriptor (:109-148) for n key-points at integer level coordinates (x, y) of one
+// level image `img` (orientation) and its blurred copy `blurred` (descriptor).  angle_out: degrees; desc_out: [n][32]
+void ref_orient_describe(const uint8_t* img, const uint8_t* blurred, int w, int h, int n, const float* xy, float* angle_out, uint8_t* desc_out) {
+    using namespace ORB_SLAM2;
+    ORBextractor ex(2000, 1.2f, 8, 20, 7);
+    const cv::Mat I(h, w, CV_8U, img), B(h, w, CV_8U, blurred);
+    for (int i = 0; i < n; ++i) {
+        cv::KeyPoint kp; kp.pt.x = xy[2 * i]; kp.pt.y = xy[2 * i + 1];
+        kp.angle = IC_Angle(I, kp.pt, ex.umax);
+        angle_out[i] = kp.angle;
+        computeOrbDescriptor(kp, B, &ex.pattern[0], desc_out + 32 * i);
+    }
 }
 
 }  // extern "C"

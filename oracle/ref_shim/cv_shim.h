@@ -14,12 +14,35 @@
 
 namespace cv {
 enum { NORM_L1 = 2 };
-struct Point2f { float x = 0, y = 0; };
+struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+struct Point { int x = 0, y = 0; Point() {} Point(int x_, int y_) : x(x_), y(y_) {} };
+typedef Point Point2i;
+typedef unsigned char uchar;
+// cvRound / cvFloor / cvCeil as OpenCV's SSE2 builds do them: nearest-even (cvtsd2si), floor, ceil
+inline int cvRound(double v) { return (int)std::lrint(v); }
+inline int cvRound(float v) { return (int)std::lrint(v); }
+inline int cvRound(int v) { return v; }
+inline int cvFloor(double v) { return (int)std::floor(v); }
+inline int cvCeil(double v) { return (int)std::ceil(v); }
+// cv::fastAtan2 (modules/core/src/mathfuncs_core.simd.hpp, atan_f32): degrees, 7th-order polynomial, all in float
+inline float fastAtan2(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float ax = std::abs(x), ay = std::abs(y);
+    float a, c, c2;
+    if (ax >= ay) { c = ay / (ax + (float)2.2204460492503131e-16); c2 = c * c; a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    else { c = ax / (ay + (float)2.2204460492503131e-16); c2 = c * c; a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
 struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
 
 class Mat {
 public:
     int rows = 0, cols = 0;
+    size_t step = 0;                                      // bytes per row (public in OpenCV: MatStep)
+    size_t step1() const { return step / (type_ == CV_32F ? 4 : 1); }
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(int r, int c, int type, const void* data) { create(r, c, type); std::memcpy(buf_->data(), data, (size_t)r * step_); }
@@ -63,7 +86,7 @@ public:
 private:
     size_t esz() const { return type_ == CV_32F ? 4 : 1; }
     void create(int r, int c, int type) {
-        rows = r; cols = c; type_ = type; step_ = (size_t)c * esz(); off_ = 0;
+        rows = r; cols = c; type_ = type; step_ = (size_t)c * esz(); off_ = 0; step = step_;
         buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * step_);
     }
     std::shared_ptr<std::vector<unsigned char>> buf_;

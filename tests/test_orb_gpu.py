@@ -123,6 +123,25 @@ def test_five_argument_constructor_provisions_lazily(adb, oracle_mod):
     ex.close()
 
 
+def test_getters_equal_the_reference_constructor_tables(adb):
+    """GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares and the per-level quotas of the
+    handle against tests/golden/extractor_tables_ref.npz = the members the reference's own constructor fills (src/ORBextractor.cc:411-472,
+    compiled from /root/reference by oracle/ref_orb.cpp), as bit patterns."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_orb_golden", os.path.join(root, "oracle", "gen_ref_orb_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(root, "tests", "golden", "extractor_tables_ref.npz"))
+    for c, (nf, sf, nl) in enumerate(g.TABLE_CONFIGS):
+        ex = adb.ORBextractor(nf, sf, nl, 20, 7)
+        assert ex.GetLevels() == nl
+        for name, got in (("scale", ex.GetScaleFactors()), ("inv_scale", ex.GetInverseScaleFactors()), ("sigma2", ex.GetScaleSigmaSquares()),
+                          ("inv_sigma2", ex.GetInverseScaleSigmaSquares())):
+            assert np.asarray(got, np.float32).tobytes() == gold[f"t{c}_{name}"].tobytes(), (nf, sf, nl, name)
+        assert list(ex.quotas()) == list(gold[f"t{c}_quota"]), (nf, sf, nl)
+        ex.close()
+
+
 def test_chunked_masked_host_batch_equals_single_calls(adb, oracle_mod):
     """A host batch of >= 32 frames runs as a chunk pipeline (upload / kernels / download overlapped), with the masks
     (the reference passes one with every frame: src/Frame.cc:551-571) uploaded, eroded and resized chunk by chunk.  The result

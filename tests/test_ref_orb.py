@@ -45,3 +45,45 @@ def test_fixture_is_what_the_reference_library_computes_now():
         cand, w, h, n = g.make_case(i)
         a = g.ref_distribute(L, cand, 0, w, 0, h, n, 1)
         assert len(a) == int(gold["count"][i]) and zlib.crc32(a.tobytes()) == int(gold["crc"][i])
+
+
+TABLES = os.path.join(ROOT, "tests", "golden", "extractor_tables_ref.npz")
+
+
+def test_oracle_constructor_tables_equal_the_reference_constructor(oracle_mod):
+    """tests/golden/extractor_tables_ref.npz holds what ORBextractor::ORBextractor (src/ORBextractor.cc:411-472, compiled from /root/reference)
+    leaves in mvScaleFactor / mvInvScaleFactor / mvLevelSigma2 / mvInvLevelSigma2 / mnFeaturesPerLevel / umax / pattern (the last copied
+    from bit_pattern_31_, :151-409) for seven configurations; the oracle's tables are the same bit patterns."""
+    g = _gen()
+    gold = np.load(TABLES)
+    for c, (nf, sf, nl) in enumerate(g.TABLE_CONFIGS):
+        o = oracle_mod.orb_tables(nf, sf, nl)
+        for k, v in o.items():
+            if k == "pattern" and c > 0:
+                continue
+            assert v.tobytes() == gold[f"t{c}_{k}"].tobytes(), (nf, sf, nl, k)
+
+
+def test_oracle_orientation_and_descriptor_equal_the_reference_functions(oracle_mod):
+    """IC_Angle and computeOrbDescriptor (src/ORBextractor.cc:78-148, compiled from /root/reference with cv::fastAtan2 / cvRound restated
+    in oracle/ref_shim/cv_shim.h) on noise, smooth and block images: angles equal as bit patterns, descriptors byte for byte."""
+    g = _gen()
+    gold = np.load(TABLES)
+    for i in range(g.N_DESC_CASES):
+        img, xy = g.make_desc_case(i)
+        a, d = oracle_mod.orient_describe(img, oracle_mod.blur7(img), xy)
+        assert a.tobytes() == gold[f"d{i}_angle"].tobytes(), i
+        assert (d == gold[f"d{i}_desc"]).all(), i
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_LIB) and os.path.isdir("/root/reference")), reason="reference tree / oracle/_ref not present (GPU box)")
+def test_tables_fixture_is_what_the_reference_library_computes_now(oracle_mod):
+    import ctypes as C
+    g = _gen()
+    gold = np.load(TABLES)
+    L = C.CDLL(REF_LIB)
+    r = oracle_mod.orb_tables(*g.TABLE_CONFIGS[4], lib=L)
+    assert all(r[k].tobytes() == gold[f"t4_{k}"].tobytes() for k in r if k != "pattern")
+    img, xy = g.make_desc_case(2)
+    a, d = oracle_mod.orient_describe(img, oracle_mod.blur7(img), xy, lib=L)
+    assert a.tobytes() == gold["d2_angle"].tobytes() and (d == gold["d2_desc"]).all()
