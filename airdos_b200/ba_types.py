@@ -118,9 +118,13 @@ class PoseBatch:
         self.c = s
 
 
+LEAF_RECORD = 122   # ADB_BA_LEAF_RECORD
+
+
 class LeafIO(C.Structure):
     """adb_ba_leaf_io (include/airdos_b200.h): inputs / outputs of the leaf-arithmetic pinning hook."""
     _fields_ = [("n", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("bf", C.c_double),
                 ("pose_q", C.c_void_p), ("pose_t", C.c_void_p), ("x", C.c_void_p), ("obs", C.c_void_p), ("pose_update", C.c_void_p),
                 ("joint_a", C.c_void_p), ("joint_b", C.c_void_p), ("bone", C.c_void_p),
-                ("motion_q", C.c_void_p), ("motion_t", C.c_void_p), ("motion_dt", C.c_void_p), ("motion_update", C.c_void_p), ("out", C.c_void_p)]
+                ("motion_q", C.c_void_p), ("motion_t", C.c_void_p), ("motion_dt", C.c_void_p), ("motion_update", C.c_void_p), ("out", C.c_void_p),
+                ("huber_delta", C.c_void_p), ("huber_e2", C.c_void_p)]

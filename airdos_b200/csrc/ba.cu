@@ -158,8 +158,11 @@ __device__ inline void reproj_jacobians(const Cam& C, const double* R, const dou
         for (int i = 12; i < 18; ++i) Jj[i] = 0;
     }
 }
+// RobustKernelHuber::robustify (Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:78-92).  The reference keeps delta^2 in a FLOAT member
+// (core/robust_kernel_impl.h:84 `float dsqr;`, set by setDelta :65-69 from the double product): both the inlier test and rho(e) use the
+// rounded value, pinned by tests/test_ref_lm.py against the compiled reference function.
 __device__ inline void huber(double delta, bool robust, double e2, double* rho0, double* rho1) {
-    const double dsqr = delta * delta;
+    const double dsqr = (double)(float)(delta * delta);
     if (!robust || e2 <= dsqr) { *rho0 = e2; *rho1 = 1.0; }
     else { const double s = sqrt(e2); *rho0 = 2 * s * delta - dsqr; *rho1 = delta / s; }
 }
@@ -1111,13 +1114,14 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
 //   [0,3) stereo error  [3,12) d e / d point  [12,30) d e / d pose      (Edge(Stereo)SE3ProjectXYZ; mono: rows 0-1 of the same at +30)
 //   [30,33) [33,42) [42,60) the same for the monocular edge            [60,63) [63,81) stereo OnlyPose error / Jacobian
 //   [81,84) [84,102) mono OnlyPose   [102,106) [106,109) pose oplus q, t   [109] rigidity error   [110,113) motion error
-//   [113,117) [117,120) motion oplus q, t
-constexpr int kLeafRecord = 120;
+//   [113,117) [117,120) motion oplus q, t   [120] [121] Huber rho(e2), rho'(e2) for (huber_delta, huber_e2) -- zeros when not given
+constexpr int kLeafRecord = 122;
+static_assert(kLeafRecord == ADB_BA_LEAF_RECORD, "record width");
 __global__ void ba_leaf_kernel(int n, Cam C, const double* __restrict__ pose_q, const double* __restrict__ pose_t, const double* __restrict__ X,
                                const double* __restrict__ obs, const double* __restrict__ pose_update, const double* __restrict__ joint_a,
                                const double* __restrict__ joint_b, const double* __restrict__ bone, const double* __restrict__ motion_q,
                                const double* __restrict__ motion_t, const double* __restrict__ motion_dt, const double* __restrict__ motion_update,
-                               double* __restrict__ out) {
+                               const double* __restrict__ huber_delta, const double* __restrict__ huber_e2, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double* o = out + (size_t)kLeafRecord * i;
@@ -1149,6 +1153,8 @@ __global__ void ba_leaf_kernel(int n, Cam C, const double* __restrict__ pose_q, 
     double Rm[9];
     motion_error_qt(motion_q + 4 * i, motion_t + 3 * i, motion_dt[i], joint_a + 3 * i, joint_b + 3 * i, o + 110, Rm);
     motion_oplus(motion_q + 4 * i, motion_t + 3 * i, motion_update + 6 * i, o + 113, o + 117);
+    o[120] = o[121] = 0.0;
+    if (huber_delta) huber(huber_delta[i], true, huber_e2[i], o + 120, o + 121);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1811,21 +1817,23 @@ adb_status adb_ba_leaf_eval(adb_ba_t s, const adb_ba_leaf_io* io) {
     ADB_CHECK(s && io && io->n >= 1 && io->out, ADB_ERR_INVALID, "null argument");
     ADB_CUDA(cudaSetDevice(s->device));
     const int n = io->n;
-    const double* src[12] = {io->pose_q, io->pose_t, io->x, io->obs, io->pose_update, io->joint_a, io->joint_b, io->bone, io->motion_q, io->motion_t, io->motion_dt,
-                             io->motion_update};
-    const int width[12] = {4, 3, 3, 3, 6, 3, 3, 1, 4, 3, 1, 6};
+    const double* src[14] = {io->pose_q, io->pose_t, io->x, io->obs, io->pose_update, io->joint_a, io->joint_b, io->bone, io->motion_q, io->motion_t, io->motion_dt,
+                             io->motion_update, io->huber_delta, io->huber_e2};
+    const int width[14] = {4, 3, 3, 3, 6, 3, 3, 1, 4, 3, 1, 6, 1, 1};
+    ADB_CHECK((io->huber_delta == nullptr) == (io->huber_e2 == nullptr), ADB_ERR_INVALID, "huber_delta and huber_e2 go together");
+    const int n_in = io->huber_delta ? 14 : 12;
     size_t total = 0;
-    for (int k = 0; k < 12; ++k) { ADB_CHECK(src[k], ADB_ERR_INVALID, "null input array %d", k); total += (size_t)width[k] * n; }
+    for (int k = 0; k < n_in; ++k) { ADB_CHECK(src[k], ADB_ERR_INVALID, "null input array %d", k); total += (size_t)width[k] * n; }
     adb_status r;
     if ((r = s->work.ensure((total + (size_t)kLeafRecord * n) * sizeof(double))) != ADB_OK) return r;
     double* d = s->work.as<double>();
-    const double* dev[12];
-    for (int k = 0; k < 12; ++k) {
+    const double* dev[14] = {};
+    for (int k = 0; k < n_in; ++k) {
         ADB_CUDA(cudaMemcpyAsync(d, src[k], (size_t)width[k] * n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         dev[k] = d; d += (size_t)width[k] * n;
     }
     ba_leaf_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, Cam{io->fx, io->fy, io->cx, io->cy, io->bf}, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7],
-                                                          dev[8], dev[9], dev[10], dev[11], d);
+                                                          dev[8], dev[9], dev[10], dev[11], dev[12], dev[13], d);
     ++s->launches;
     ADB_CUDA(cudaGetLastError());
     ADB_CUDA(cudaMemcpyAsync(io->out, d, (size_t)kLeafRecord * n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

@@ -463,10 +463,11 @@ int64_t adb_ba_launch_count(adb_ba_t s);
 /* Pinning hook for the tests: evaluates the device implementations of the reference's LEAF arithmetic on arrays of n inputs --
  * Edge(Stereo)SE3ProjectXYZ[OnlyPose]::computeError / linearizeOplus (types_six_dof_expmap.cpp:103-364), VertexSE3Expmap::oplusImpl
  * (types_six_dof_expmap.h:73-76), EdgeRigidBodyDouble::computeError (include/g2o_edge_rigidbody.h:139-149),
- * LandmarkMotionTernaryEdge::computeError (include/g2o_dyn_slam3d.h:65-76), VertexSE3::oplusImpl (include/g2o_vertex_se3.h:113-122) --
- * so that they can be compared with tests/golden/ba_leaf_ref.npz (values produced by those reference sources themselves).
+ * LandmarkMotionTernaryEdge::computeError (include/g2o_dyn_slam3d.h:65-76), VertexSE3::oplusImpl (include/g2o_vertex_se3.h:113-122),
+ * RobustKernelHuber::robustify (core/robust_kernel_impl.cpp:78-92) --
+ * so that they can be compared with tests/golden/ba_leaf_ref.npz / lm_ref.npz (values produced by those reference sources themselves).
  * All arrays are host memory, doubles; out = n records of ADB_BA_LEAF_RECORD doubles (layout: airdos_b200/csrc/ba.cu, ba_leaf_kernel). */
-#define ADB_BA_LEAF_RECORD 120
+#define ADB_BA_LEAF_RECORD 122
 typedef struct adb_ba_leaf_io {
     int32_t n;
     double fx, fy, cx, cy, bf;
@@ -474,6 +475,9 @@ typedef struct adb_ba_leaf_io {
     const double* joint_a; const double* joint_b; const double* bone;                                             /* [n][3|3|1] */
     const double* motion_q; const double* motion_t; const double* motion_dt; const double* motion_update;         /* [n][4|3|1|6] */
     double* out;
+    /* optional (both or neither, may be NULL): out[120], out[121] = rho(e2), rho'(e2) of RobustKernelHuber::robustify after setDelta(delta)
+     * (Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:65-92; delta^2 is kept in a float there, core/robust_kernel_impl.h:84) */
+    const double* huber_delta; const double* huber_e2;                                                            /* [n] */
 } adb_ba_leaf_io;
 adb_status adb_ba_leaf_eval(adb_ba_t s, const adb_ba_leaf_io* io);
 

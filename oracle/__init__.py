@@ -427,3 +427,99 @@ def pose_optimize(cam: dict, frames: list):
     lib.ba_oracle_pose_optimize.argtypes = [C.POINTER(T.PoseProblem)]
     lib.ba_oracle_pose_optimize(C.byref(pb.c))
     return pb
+
+
+# ------------------------------------------------------------------------------------------
+# The oracle's LM steps one by one (ba_oracle_lm_*), and the hook table oracle/ref_lm.cpp drives them through
+_LM_HOOKS = ("compute_errors", "chi2", "build", "layout", "vectors", "set_lambda", "solve", "update", "push", "pop", "discard_top")
+
+
+class LmHooks(C.Structure):
+    _fields_ = [("ctx", C.c_void_p)] + [(n, C.c_void_p) for n in _LM_HOOKS]
+
+
+class LmSession:
+    """One round of the oracle's solver (Solver of oracle/ba_oracle.cpp) on a copy of `problem_dict`, opened at the initial state."""
+
+    def __init__(self, problem_dict: dict, options=None, robust: bool = True):
+        from airdos_b200 import ba_types as T
+        lib = ba_lib()
+        lib.ba_oracle_lm_open.restype = C.c_void_p
+        lib.ba_oracle_lm_open.argtypes = [C.POINTER(T.BAProblem), C.POINTER(T.BAOptions), C.c_int]
+        lib.ba_oracle_lm_close.argtypes = [C.c_void_p]
+        lib.ba_oracle_lm_optimize.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.ba_oracle_lm_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.lib = lib
+        self.p = T.Problem(problem_dict)
+        self.o = options or ba_default_options()
+        self.h = lib.ba_oracle_lm_open(C.byref(self.p.c), C.byref(self.o), int(robust))
+
+    def hooks(self) -> LmHooks:
+        return LmHooks(self.h, *[C.cast(getattr(self.lib, "ba_oracle_lm_" + n), C.c_void_p) for n in _LM_HOOKS])
+
+    def optimize(self, iterations: int, cap: int = 512):
+        """The oracle's own loop (Solver::optimize) -> (iterations run, rows [(lambda, chi2 before, chi2 after, accepted)], final lambda)."""
+        tr = np.zeros((cap, 5)); n = C.c_int(); lam = C.c_double()
+        it = self.lib.ba_oracle_lm_optimize(self.h, iterations, _p(tr), cap, C.byref(n), C.byref(lam))
+        return it, tr[:n.value][:, [0, 1, 2, 4]].copy(), lam.value
+
+    def state(self) -> np.ndarray:
+        n = self.lib.ba_oracle_lm_state(self.h, None, 0)
+        a = np.zeros(n)
+        self.lib.ba_oracle_lm_state(self.h, _p(a), n)
+        return a
+
+    def close(self):
+        if self.h:
+            self.lib.ba_oracle_lm_close(self.h); self.h = None
+
+
+def ref_lm_optimize(ref_lib, session: LmSession, iterations: int, cap: int = 512):
+    """The REFERENCE's SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve (oracle/_ref/libref_lm.so) over the session's
+    arithmetic -> (iterations run, rows, final lambda, number of computeActiveErrors calls, the constructor's tau)."""
+    ref_lib.ref_lm_optimize.argtypes = [C.POINTER(LmHooks), C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    hk = session.hooks()
+    rows = np.zeros((cap, 4)); n = C.c_int(); lam = C.c_double(); ne = C.c_int(); tau = C.c_double()
+    it = ref_lib.ref_lm_optimize(C.byref(hk), iterations, session.o.max_trials, _p(rows), cap, C.byref(n), C.byref(lam), C.byref(ne), C.byref(tau))
+    return it, rows[:n.value].copy(), lam.value, ne.value, tau.value
+
+
+def edge_quadratic_form(dim, Ji, Jj, er, w0, delta, robust, pose_fixed=False, lib=None):
+    """One reprojection edge's contribution to the normal equations -> (hl 3x3, gl 3, hp 6x6, gp 6, w 6x3); `lib` = libref_lm.so runs the
+    reference's BaseBinaryEdge::constructQuadraticForm instead of the oracle's."""
+    Ji = np.ascontiguousarray(Ji, np.float64); Jj = np.ascontiguousarray(Jj, np.float64); er = np.ascontiguousarray(er, np.float64)
+    out = [np.zeros(9), np.zeros(3), np.zeros(36), np.zeros(6), np.zeros(18)]
+    vp = C.c_void_p
+    if lib is None:
+        f = ba_lib().ba_oracle_edge_quadratic_form
+        f.argtypes = [C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_int] + [vp] * 5
+        f(dim, _p(Ji), _p(Jj), _p(er), w0, delta, int(robust), _p(out[0]), _p(out[1]), None if pose_fixed else _p(out[2]), _p(out[3]), _p(out[4]))
+    else:
+        f = lib.ref_binary_quadratic_form
+        f.argtypes = [C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int] + [vp] * 5
+        f(dim, _p(Ji), _p(Jj), _p(er), w0, delta, int(robust), 0, int(pose_fixed), *[_p(x) for x in out])
+    return out
+
+
+def pose_quadratic_form(dim, J, er, w0, delta, robust, lib=None):
+    """One OnlyPose edge's contribution (h 6x6, g 6); `lib` = libref_lm.so runs BaseUnaryEdge::constructQuadraticForm."""
+    J = np.ascontiguousarray(J, np.float64); er = np.ascontiguousarray(er, np.float64)
+    h, g = np.zeros(36), np.zeros(6)
+    f = ba_lib().ba_oracle_pose_quadratic_form if lib is None else lib.ref_unary_quadratic_form
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    f(dim, _p(J), _p(er), w0, delta, int(robust), _p(h), _p(g))
+    return h, g
+
+
+def huber(delta: float, e2: float, lib=None):
+    """RobustKernelHuber::robustify -> (rho, rho'); `lib` = libref_lm.so runs the reference's function."""
+    if lib is not None:
+        r = np.zeros(3)
+        lib.ref_huber.argtypes = [C.c_double, C.c_double, C.c_void_p]
+        lib.ref_huber(delta, e2, _p(r))
+        return r[0], r[1]
+    f = ba_lib().ba_oracle_huber
+    f.argtypes = [C.c_double, C.c_double, C.c_void_p]
+    r = np.zeros(2)
+    f(delta, e2, _p(r))
+    return r[0], r[1]

@@ -159,7 +159,9 @@ inline void motion_edge_jacobians(const double* Rm, double dt, double* J1, doubl
     Jm[0] = dt; Jm[7] = dt; Jm[14] = dt;
 }
 
+// RobustKernelHuber keeps delta^2 in a FLOAT member (core/robust_kernel_impl.h:84 `float dsqr;`, setDelta :65-69)
 struct Huber { double delta, dsqr; };
+inline Huber make_huber(double d) { return Huber{d, (double)(float)(d * d)}; }
 inline void robustify(const Huber& h, bool robust, double e2, double* rho0, double* rho1) {
     if (!robust || e2 <= h.dsqr) { *rho0 = e2; *rho1 = 1.0; }
     else { const double s = std::sqrt(e2); *rho0 = 2 * s * h.delta - h.dsqr; *rho1 = h.delta / s; }
@@ -197,6 +199,46 @@ inline void reproj_jacobians(const adb_ba_problem& P, const double* R, const dou
         Jj[12] = Jj[0] - bf * y / z2; Jj[13] = Jj[1] + bf * x / z2; Jj[14] = Jj[2]; Jj[15] = Jj[3]; Jj[16] = 0; Jj[17] = Jj[5] - bf / z2;
     } else {
         for (int i = 12; i < 18; ++i) Jj[i] = 0;
+    }
+}
+
+// BaseBinaryEdge::constructQuadraticForm (Thirdparty/g2o/g2o/core/base_binary_edge.hpp:55-117) for one reprojection edge with
+// information w0 * I: vertex 0 = the point (Ji, dim x 3), vertex 1 = the pose (Jj, dim x 6), rows beyond dim zero.  The robust
+// branch scales the information and the right-hand side by rho'(chi2) (core/base_edge.h:96-102: the second-order term is commented
+// out in the reference).  Outputs are this edge's CONTRIBUTIONS: hl = Ji^T w Ji, gl = -Ji^T w e, hp = Jj^T w Jj, gp = -Jj^T w e,
+// w63 = Jj^T w Ji (the pose x point block; g2o stores its transpose).  hp == nullptr: the pose is fixed (hp / gp / w63 untouched).
+inline void edge_quadratic_form(int dim, const double* Ji, const double* Jj, const double* er, double w0, const Huber& hub, bool robust,
+                                double* hl, double* gl, double* hp, double* gp, double* w63) {
+    double r0, r1;
+    const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+    robustify(hub, robust, c, &r0, &r1);
+    const double w = r1 * w0;
+    const double wr[3] = {-w0 * er[0] * r1, -w0 * er[1] * r1, -w0 * er[2] * r1};
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * w * Ji[k * 3 + j];
+            hl[i * 3 + j] = s;
+        }
+        double s = 0;
+        for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * wr[k];
+        gl[i] = s;
+    }
+    if (!hp) return;
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) {
+            double s = 0;
+            for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * w * Jj[k * 6 + j];
+            hp[i * 6 + j] = s;
+        }
+        double s = 0;
+        for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * wr[k];
+        gp[i] = s;
+        for (int j = 0; j < 3; ++j) {
+            double t = 0;
+            for (int k = 0; k < dim; ++k) t += Jj[k * 6 + i] * w * Ji[k * 3 + j];
+            w63[i * 3 + j] = t;
+        }
     }
 }
 
@@ -270,7 +312,7 @@ struct Solver {
         chi_e.assign(p.n_edges, 0); chi_j.assign(p.n_joint_edges, 0); chi_r.assign(p.n_rigid_edges, 0); chi_m.assign(p.n_motion_edges, 0);
     }
 
-    Huber huber(double d) const { return Huber{d, d * d}; }
+    Huber huber(double d) const { return make_huber(d); }
 
     // SparseOptimizer::initializeOptimization(level 0): active vertices = non-fixed vertices with an active edge
     void build_layout() {
@@ -376,32 +418,17 @@ struct Solver {
             double er[3], Xc[3], Ji[9], Jj[18];
             const int dim = reproj_error(P, &R[9 * ip], &pt[3 * ip], &X[3 * il], &P.edge_obs[3 * e], er, Xc);
             reproj_jacobians(P, &R[9 * ip], Xc, dim, Ji, Jj);
-            const double w0 = P.edge_info[e];
-            const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
-            robustify(huber(dim == 3 ? O.huber_stereo : O.huber_mono), robust, c, &r0, &r1);
-            const double w = r1 * w0;
-            const double wr[3] = {-w0 * er[0] * r1, -w0 * er[1] * r1, -w0 * er[2] * r1};
-            // point block
-            for (int i = 0; i < 3; ++i) {
-                for (int j = 0; j < 3; ++j) {
-                    double s = 0;
-                    for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * w * Ji[k * 3 + j];
-                    Hll[(size_t)9 * il + i * 3 + j] += s;
-                }
-                double s = 0;
-                for (int k = 0; k < dim; ++k) s += Ji[k * 3 + i] * wr[k];
-                bl[(size_t)3 * il + i] += s;
-            }
             const int op = off_pose[ip];
+            double hl[9], gl[3], hp[36], gp[6];
+            edge_quadratic_form(dim, Ji, Jj, er, P.edge_info[e], huber(dim == 3 ? O.huber_stereo : O.huber_mono), robust, hl, gl,
+                                op >= 0 ? hp : nullptr, gp, &W[(size_t)18 * e]);
+            for (int i = 0; i < 9; ++i) Hll[(size_t)9 * il + i] += hl[i];
+            for (int i = 0; i < 3; ++i) bl[(size_t)3 * il + i] += gl[i];
             if (op >= 0) {
-                add_block(op, 6, Jj, op, 6, Jj, dim, w);
-                add_rhs(op, 6, Jj, dim, wr);
-                for (int i = 0; i < 6; ++i)
-                    for (int j = 0; j < 3; ++j) {
-                        double s = 0;
-                        for (int k = 0; k < dim; ++k) s += Jj[k * 6 + i] * w * Ji[k * 3 + j];
-                        W[(size_t)18 * e + i * 3 + j] = s;
-                    }
+                for (int i = 0; i < 6; ++i) {
+                    for (int j = 0; j < 6; ++j) H[(size_t)(op + i) * n_dense + op + j] += hp[i * 6 + j];
+                    b[op + i] += gp[i];
+                }
             }
         }
         for (int e = 0; e < P.n_joint_edges; ++e) {
@@ -729,6 +756,91 @@ int ba_oracle_first_step(adb_ba_problem* prob, const adb_ba_options* opt, double
     std::memcpy(x_l, S.x_l.data(), S.x_l.size() * 8);
     return S.n_dense;
 }
+
+void ba_oracle_huber(double delta, double e2, double* rho2) { robustify(make_huber(delta), true, e2, rho2, rho2 + 1); }
+// one reprojection edge's quadratic form (what Solver::build_system adds for it); hp may be NULL for a fixed pose
+void ba_oracle_edge_quadratic_form(int dim, const double* Ji, const double* Jj, const double* er, double w0, double delta, int robust,
+                                   double* hl, double* gl, double* hp, double* gp, double* w63) {
+    edge_quadratic_form(dim, Ji, Jj, er, w0, make_huber(delta), robust != 0, hl, gl, hp, gp, w63);
+}
+
+// ---- the solver's steps one by one, for oracle/ref_lm.cpp: the reference's OWN OptimizationAlgorithmLevenberg::solve and
+// SparseOptimizer::optimize (compiled from /root/reference) drive these through function pointers, so that the control flow of
+// Solver::optimize above can be held against the literal reference on the same arithmetic.
+struct LmSession {
+    Solver S;
+    struct Snap { std::vector<double> pq, pt, X, J, D, mq, mt; };
+    std::vector<Snap> stack;
+    double chi = 0;
+    LmSession(adb_ba_problem& p, const adb_ba_options& o) : S(p, o) {}
+};
+void* ba_oracle_lm_open(adb_ba_problem* prob, const adb_ba_options* opt, int robust) {
+    LmSession* h = new LmSession(*prob, *opt);
+    h->S.robust = robust != 0;
+    h->S.build_layout();
+    return h;
+}
+void ba_oracle_lm_close(void* h) { delete (LmSession*)h; }
+void ba_oracle_lm_compute_errors(void* h) { LmSession* s = (LmSession*)h; s->chi = s->S.evaluate(); }   // computeActiveErrors
+double ba_oracle_lm_chi2(void* h) { return ((LmSession*)h)->chi; }                                       // activeRobustChi2
+void ba_oracle_lm_build(void* h) { ((LmSession*)h)->S.build_system(); }                                  // Solver::buildSystem
+// indexMapping(): the dimension of every active vertex in solver order (key-frames, bone lengths, motions, joints, map points)
+int ba_oracle_lm_layout(void* h, int32_t* dims, int cap) {
+    const Solver& S = ((LmSession*)h)->S;
+    int n = 0;
+    auto put = [&](int d) { if (n < cap) dims[n] = d; ++n; };
+    for (int i = 0; i < S.P.n_poses; ++i) if (S.off_pose[i] >= 0) put(6);
+    for (int i = 0; i < S.P.n_dists; ++i) if (S.off_dist[i] >= 0) put(1);
+    for (int i = 0; i < S.P.n_motions; ++i) if (S.off_motion[i] >= 0) put(6);
+    for (int i = 0; i < S.P.n_joints; ++i) if (S.off_joint[i] >= 0) put(3);
+    for (int l = 0; l < S.P.n_points; ++l) if (S.act_point[l]) put(3);
+    return n;
+}
+// the whole solution vector x, right-hand side b and Hessian diagonal in that order; returns the vector size
+int ba_oracle_lm_vectors(void* h, double* x, double* b, double* diag, int cap) {
+    const Solver& S = ((LmSession*)h)->S;
+    int n = 0;
+    for (int i = 0; i < S.n_dense; ++i, ++n)
+        if (n < cap) { if (x) x[n] = S.x_d.empty() ? 0.0 : S.x_d[i]; if (b) b[n] = S.b[i]; if (diag) diag[n] = S.H[(size_t)i * S.n_dense + i]; }
+    for (int l = 0; l < S.P.n_points; ++l) {
+        if (!S.act_point[l]) continue;
+        for (int k = 0; k < 3; ++k, ++n)
+            if (n < cap) { if (x) x[n] = S.x_l.empty() ? 0.0 : S.x_l[3 * l + k]; if (b) b[n] = S.bl[3 * l + k]; if (diag) diag[n] = S.Hll[(size_t)9 * l + 4 * k]; }
+    }
+    return n;
+}
+void ba_oracle_lm_set_lambda(void* h, double lambda) { ((LmSession*)h)->S.lambda = lambda; }             // Solver::setLambda
+int ba_oracle_lm_solve(void* h) { return ((LmSession*)h)->S.solve_trial() ? 1 : 0; }                     // Solver::solve
+void ba_oracle_lm_update(void* h) { ((LmSession*)h)->S.apply_update(); }                                 // SparseOptimizer::update(x)
+void ba_oracle_lm_push(void* h) {
+    LmSession* s = (LmSession*)h;
+    s->stack.push_back(LmSession::Snap{s->S.pq, s->S.pt, s->S.X, s->S.J, s->S.D, s->S.mq, s->S.mt});
+}
+void ba_oracle_lm_pop(void* h) {
+    LmSession* s = (LmSession*)h;
+    LmSession::Snap& t = s->stack.back();
+    s->S.pq = t.pq; s->S.pt = t.pt; s->S.X = t.X; s->S.J = t.J; s->S.D = t.D; s->S.mq = t.mq; s->S.mt = t.mt;
+    s->stack.pop_back();
+}
+void ba_oracle_lm_discard_top(void* h) { ((LmSession*)h)->stack.pop_back(); }
+// the oracle's own loop on the session (Solver::optimize): trace rows of ADB_BA_TRACE_COLS; returns iterations run
+int ba_oracle_lm_optimize(void* h, int iterations, double* trace, int trace_cap, int* trace_len, double* lambda_final) {
+    LmSession* s = (LmSession*)h;
+    adb_ba_result res{};
+    res.trace = trace; res.trace_cap = trace_cap;
+    double chi = 0;
+    const int it = s->S.optimize(iterations, nullptr, &res, &chi);
+    *trace_len = s->S.trace_len; *lambda_final = s->S.lambda;
+    return it;
+}
+// current estimates, concatenated (poses q | t, points, joints, bone lengths, motions q | t); returns the length
+int ba_oracle_lm_state(void* h, double* out, int cap) {
+    const Solver& S = ((LmSession*)h)->S;
+    int n = 0;
+    for (const std::vector<double>* v : {&S.pq, &S.pt, &S.X, &S.J, &S.D, &S.mq, &S.mt})
+        for (double d : *v) { if (n < cap) out[n] = d; ++n; }
+    return n;
+}
 }
 
 // ---------------------------------------------------------------------------------------
@@ -756,6 +868,19 @@ inline void pose_edge_jac(const adb_pose_problem& P, const double* Xc, bool ster
     else for (int i = 12; i < 18; ++i) J[i] = 0;
 }
 
+// BaseUnaryEdge::constructQuadraticForm (Thirdparty/g2o/g2o/core/base_unary_edge.hpp:40-69) for one OnlyPose edge, information w0 * I:
+// h = J^T (rho' w0) J, g = -rho' J^T w0 e: this edge's contribution to the 6 x 6 system
+inline void pose_edge_quadratic_form(int dim, const double* J, const double* er, double w0, const Huber& hub, bool robust, double* h, double* g) {
+    double r0, r1;
+    const double c = er[0] * (w0 * er[0]) + er[1] * (w0 * er[1]) + er[2] * (w0 * er[2]);
+    robustify(hub, robust, c, &r0, &r1);
+    const double w = r1 * w0;
+    for (int u = 0; u < 6; ++u) {
+        for (int v = 0; v < 6; ++v) { double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + u] * w * J[k * 6 + v]; h[u * 6 + v] = s; }
+        double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + u] * (-w0 * er[k] * r1); g[u] = s;
+    }
+}
+
 int pose_optimize_one(const adb_pose_problem& P, int f) {
     const int a = P.frame_ptr[f], n = P.frame_ptr[f + 1] - a;
     std::vector<PoseEdge> E(n);
@@ -766,8 +891,7 @@ int pose_optimize_one(const adb_pose_problem& P, int f) {
         P.outlier[a + i] = 0;
     }
     if (n < 3) return 0;
-    const Huber hm{(double)(float)std::sqrt(5.991), 0}, hs{(double)(float)std::sqrt(7.815), 0};
-    const Huber hmono{hm.delta, hm.delta * hm.delta}, hstereo{hs.delta, hs.delta * hs.delta};
+    const Huber hmono = make_huber((double)(float)std::sqrt(5.991)), hstereo = make_huber((double)(float)std::sqrt(7.815));
     double q0[4], t0[3];
     std::memcpy(q0, P.pose_q + 4 * f, sizeof(q0)); std::memcpy(t0, P.pose_t + 3 * f, sizeof(t0));
     double q[4], t[3];
@@ -799,20 +923,17 @@ int pose_optimize_one(const adb_pose_problem& P, int f) {
             for (int it = 0; it < 10; ++it) {
                 double current = evaluate(q, t);
                 const double ini = current;
-                double H[36] = {0}, b[6] = {0}, R[9], r0, r1;
+                double H[36] = {0}, b[6] = {0}, R[9];
                 quat_to_rot(q, R);
                 for (int i = 0; i < n; ++i) {
                     if (level[i]) continue;
                     double er[3], Xc[3], J[18];
                     pose_edge_error(P, R, t, E[i], er, Xc);
                     pose_edge_jac(P, Xc, E[i].stereo, J);
-                    const int dim = E[i].stereo ? 3 : 2;
-                    robustify(E[i].stereo ? hstereo : hmono, robust, chi[i], &r0, &r1);
-                    const double w = r1 * E[i].w;
-                    for (int u = 0; u < 6; ++u) {
-                        for (int v = 0; v < 6; ++v) { double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + u] * w * J[k * 6 + v]; H[u * 6 + v] += s; }
-                        double s = 0; for (int k = 0; k < dim; ++k) s += J[k * 6 + u] * (-E[i].w * er[k] * r1); b[u] += s;
-                    }
+                    double h[36], g[6];
+                    pose_edge_quadratic_form(E[i].stereo ? 3 : 2, J, er, E[i].w, E[i].stereo ? hstereo : hmono, robust, h, g);
+                    for (int u = 0; u < 36; ++u) H[u] += h[u];
+                    for (int u = 0; u < 6; ++u) b[u] += g[u];
                 }
                 if (it == 0) { double m = 0; for (int u = 0; u < 6; ++u) m = std::max(m, std::fabs(H[u * 7])); lambda = 1e-5 * m; ni = 2; nbad_it = 0; }
                 double rho = 0; int qn = 0;
@@ -867,6 +988,9 @@ int pose_optimize_one(const adb_pose_problem& P, int f) {
 }
 }  // namespace
 
+extern "C" void ba_oracle_pose_quadratic_form(int dim, const double* J, const double* er, double w0, double delta, int robust, double* h, double* g) {
+    pose_edge_quadratic_form(dim, J, er, w0, make_huber(delta), robust != 0, h, g);
+}
 extern "C" int ba_oracle_pose_optimize(adb_pose_problem* P) {
     for (int f = 0; f < P->n_frames; ++f) P->n_inliers[f] = pose_optimize_one(*P, f);
     return ADB_OK;

@@ -88,6 +88,7 @@ public:
     S x() const { return m_[0]; } S y() const { return m_[1]; } S z() const { return m_[2]; }
     void fill(S v) { for (int i = 0; i < R * C; ++i) m_[i] = v; }
     void setZero() { fill(S(0)); }
+    Matrix& noalias() { return *this; }
     void setIdentity() { setZero(); for (int i = 0; i < (R < C ? R : C); ++i) (*this)(i, i) = S(1); }
     static Matrix Zero() { return Matrix(); }
     static Matrix Zero(int, int) { return Matrix(); }

@@ -13,19 +13,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RTOL = 1e-11
 
 
-def _eval(opt, g, X):
+def _eval(opt, g, X, huber=None):
     from airdos_b200 import ba_types as T
     from airdos_b200.capi import check, lib, ptr
     n = len(X)
     keep = [np.ascontiguousarray(a, np.float64) for a in (g["pose_q"], g["pose_t"], X, g["obs"], g["pose_update"], g["joint_a"], g["joint_b"], g["bone"],
                                                           g["motion_q"], g["motion_t"], g["motion_dt"], g["motion_update"])]
-    out = np.zeros((n, 120))
+    out = np.zeros((n, T.LEAF_RECORD))
     io = T.LeafIO()
     io.n = n
     io.fx, io.fy, io.cx, io.cy, io.bf = [float(v) for v in g["cam"]]
     for name, a in zip(("pose_q", "pose_t", "x", "obs", "pose_update", "joint_a", "joint_b", "bone", "motion_q", "motion_t", "motion_dt", "motion_update"), keep):
         setattr(io, name, a.ctypes.data)
     io.out = out.ctypes.data
+    if huber is not None:
+        hd, he = (np.ascontiguousarray(a, np.float64) for a in huber)
+        assert len(hd) == n and len(he) == n
+        io.huber_delta, io.huber_e2 = hd.ctypes.data, he.ctypes.data
     check(lib().adb_ba_leaf_eval(opt._s, C.byref(io)))
     return out
 
@@ -67,4 +71,23 @@ def test_cuda_leaf_arithmetic_matches_the_reference():
     _close(o[:, 63:81], g["onlypose_stereo_J"], np.abs(g["onlypose_stereo_J"]).max(1, keepdims=True) + 1)
     _close(o[:, 81:83], g["onlypose_mono_err"], obs_scale + np.abs(g["onlypose_mono_err"]))
     _close(o[:, 84:96], g["onlypose_mono_J"], np.abs(g["onlypose_mono_J"]).max(1, keepdims=True) + 1)
+    opt.close()
+
+
+def test_cuda_huber_kernel_matches_the_reference_function():
+    """The device Huber weight against RobustKernelHuber::robustify of the reference (Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:65-92,
+    compiled from /root/reference by oracle/ref_lm.cpp; tests/golden/lm_ref.npz): rho(e2) and rho'(e2) for the deltas the Optimizer sets and
+    squared errors on both sides of delta^2 -- including the values between the double delta^2 and the FLOAT `dsqr` member the reference
+    compares with (core/robust_kernel_impl.h:84), where a double dsqr would classify differently."""
+    from airdos_b200 import ba
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ba_leaf_ref.npz")))
+    lm = np.load(os.path.join(ROOT, "tests", "golden", "lm_ref.npz"))
+    hd, he, rho = lm["huber_delta"], lm["huber_e2"], lm["huber_rho"]
+    n = len(g["pose_q"])
+    opt = ba.Optimizer()
+    for a in range(0, len(hd), n):
+        m = min(n, len(hd) - a)
+        d = np.ones(n); e = np.ones(n); d[:m] = hd[a:a + m]; e[:m] = he[a:a + m]
+        o = _eval(opt, g, g["X"], (d, e))
+        assert (o[:m, 120] == rho[a:a + m, 0]).all() and (o[:m, 121] == rho[a:a + m, 1]).all()
     opt.close()
