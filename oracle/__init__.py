@@ -523,3 +523,61 @@ def huber(delta: float, e2: float, lib=None):
     r = np.zeros(2)
     f(delta, e2, _p(r))
     return r[0], r[1]
+
+
+# ------------------------------------------------------------------------------------------
+# oracle/ref_lba.cpp: the reference's Optimizer::LocalBundleAdjustment over the oracle's solver session
+class _LbaBackend(C.Structure):
+    _fields_ = [("steps", LmHooks)] + [(n, C.c_void_p) for n in ("open", "close", "set_levels", "state", "lm_optimize", "default_options")]
+
+
+class _LbaIO(C.Structure):
+    _fields_ = [("n_kf", C.c_int32), ("kf_id", C.c_void_p), ("kf_tcw", C.c_void_p), ("n_covisible", C.c_int32), ("covisible", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("n_levels", C.c_int32), ("inv_level_sigma2", C.c_void_p),
+                ("n_mp", C.c_int32), ("mp_id", C.c_void_p), ("mp_pos", C.c_void_p),
+                ("n_obs", C.c_int32), ("obs_kf", C.c_void_p), ("obs_mp", C.c_void_p), ("obs_uvr", C.c_void_p), ("obs_octave", C.c_void_p),
+                ("kf_tcw_out", C.c_void_p), ("mp_pos_out", C.c_void_p), ("erased", C.c_void_p), ("erased_cap", C.c_int32), ("n_erased", C.c_int32),
+                ("mp_updates", C.c_void_p)]
+
+
+def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict):
+    """Runs the reference's Optimizer::LocalBundleAdjustment (oracle/_ref/libref_lba.so) on window `w` (kf_id, kf_tcw [n,4,4] f32, covisible,
+    fx fy cx cy bf, inv_level_sigma2, mp_id, mp_pos [m,3] f32, obs_kf, obs_mp, obs_uvr [o,3] f32, obs_octave; key-frame 0 = pKF), its
+    solver steps being the oracle's and its LM control the reference's (libref_lm.so).  Returns the function's outputs and the problem /
+    trial rows the stand-in optimizer recorded (a dict in make_ba_problem layout, usable with ba_solve)."""
+    lib = ba_lib()
+    be = _LbaBackend()
+    be.steps = LmHooks(None, *[C.cast(getattr(lib, "ba_oracle_lm_" + n), C.c_void_p) for n in _LM_HOOKS])
+    for n, f in (("open", lib.ba_oracle_lm_open), ("close", lib.ba_oracle_lm_close), ("set_levels", lib.ba_oracle_lm_set_levels),
+                 ("state", lib.ba_oracle_lm_state), ("lm_optimize", lm_lib.ref_lm_optimize), ("default_options", lib.ba_oracle_default_options)):
+        setattr(be, n, C.cast(f, C.c_void_p))
+    a = lambda k, t: np.ascontiguousarray(w[k], t)
+    kf_id, tcw, cov = a("kf_id", np.int32), a("kf_tcw", np.float32), a("covisible", np.int32)
+    sig, mp_id, mp_pos = a("inv_level_sigma2", np.float32), a("mp_id", np.int32), a("mp_pos", np.float32)
+    okf, omp, uvr, octv = a("obs_kf", np.int32), a("obs_mp", np.int32), a("obs_uvr", np.float32), a("obs_octave", np.int32)
+    tcw_out = np.zeros_like(tcw); pos_out = np.zeros_like(mp_pos); erased = np.zeros((len(okf), 2), np.int32); upd = np.zeros(len(mp_id), np.int32)
+    io = _LbaIO(len(kf_id), _p(kf_id), _p(tcw), len(cov), _p(cov), w["fx"], w["fy"], w["cx"], w["cy"], w["bf"], len(sig), _p(sig),
+                len(mp_id), _p(mp_id), _p(mp_pos), len(okf), _p(okf), _p(omp), _p(uvr), _p(octv), _p(tcw_out), _p(pos_out), _p(erased), len(erased), 0, _p(upd))
+    rec = C.c_void_p()
+    lba_lib.ref_lba_run.argtypes = [C.POINTER(_LbaBackend), C.POINTER(_LbaIO), C.POINTER(C.c_void_p)]
+    lba_lib.ref_lba_record_f64.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lba_lib.ref_lba_record_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lba_lib.ref_lba_record_free.argtypes = [C.c_void_p]
+    rc = lba_lib.ref_lba_run(C.byref(be), C.byref(io), C.byref(rec))
+    assert rc == 0
+
+    def f64(which):
+        n = lba_lib.ref_lba_record_f64(rec, which, None, 0); v = np.zeros(n); lba_lib.ref_lba_record_f64(rec, which, _p(v), n); return v
+
+    def i32(which):
+        n = lba_lib.ref_lba_record_i32(rec, which, None, 0); v = np.zeros(n, np.int32); lba_lib.ref_lba_record_i32(rec, which, _p(v), n); return v
+
+    cam = f64(7)
+    prob = dict(fx=cam[0], fy=cam[1], cx=cam[2], cy=cam[3], bf=cam[4], pose_q=f64(0).reshape(-1, 4), pose_t=f64(1).reshape(-1, 3),
+                points=f64(2).reshape(-1, 3), edge_obs=f64(3).reshape(-1, 3), edge_info=f64(4), edge_pose=i32(0), edge_point=i32(1),
+                pose_fixed=i32(6).astype(np.uint8))
+    out = dict(kf_tcw=tcw_out, mp_pos=pos_out, erased=erased[:io.n_erased].copy(), mp_updates=upd, problem=prob, rows=f64(5).reshape(-1, 4),
+               final_state=f64(6), pose_id=i32(2), point_id=i32(3), round_iterations=i32(4), round_robust=i32(5), huber=(cam[5], cam[6]))
+    lba_lib.ref_lba_record_free(rec)
+    return out

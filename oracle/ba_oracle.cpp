@@ -781,6 +781,12 @@ void* ba_oracle_lm_open(adb_ba_problem* prob, const adb_ba_options* opt, int rob
     return h;
 }
 void ba_oracle_lm_close(void* h) { delete (LmSession*)h; }
+// levels of the static edges (1 = excluded, like setLevel(1) + initializeOptimization(0)); the layout is rebuilt
+void ba_oracle_lm_set_levels(void* h, const uint8_t* lvl_e) {
+    Solver& S = ((LmSession*)h)->S;
+    for (int e = 0; e < S.P.n_edges; ++e) S.lvl_e[e] = lvl_e[e];
+    S.build_layout();
+}
 void ba_oracle_lm_compute_errors(void* h) { LmSession* s = (LmSession*)h; s->chi = s->S.evaluate(); }   // computeActiveErrors
 double ba_oracle_lm_chi2(void* h) { return ((LmSession*)h)->chi; }                                       // activeRobustChi2
 void ba_oracle_lm_build(void* h) { ((LmSession*)h)->S.build_system(); }                                  // Solver::buildSystem

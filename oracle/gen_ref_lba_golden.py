@@ -1,0 +1,83 @@
+"""Writes tests/golden/lba_ref.npz: results of the REFERENCE's own Optimizer::LocalBundleAdjustment (src/Optimizer.cc:431-731, the whole
+function compiled from /root/reference by `make -C oracle ref`, oracle/ref_lba.cpp) on seeded windows.  The function runs with the
+reference's own g2o vertex / edge types (gates: chi2(), isDepthPositive()), Converter functions and Levenberg-Marquardt control
+(oracle/ref_lm.cpp); its solver steps are the oracle's (see ref_lba.cpp's header).  The fixture keeps the window, the problem the
+function built (vertex order, fixed flags, edges, information, Huber deltas), every LM trial, the final estimates, the erase list and
+the poses / positions it wrote back.  Run in the build container (needs /root/reference):
+
+    python oracle/gen_ref_lba_golden.py
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+# (seed, local key-frames, points, fixed observers, mono fraction, key-frame with mnId 0 inside the window, point noise)
+CASES = [(3, 8, 300, 2, 0.2, True, 0.0), (4, 6, 200, 0, 0.0, True, 0.0), (5, 10, 400, 3, 0.5, False, 0.0), (6, 5, 150, 1, 1.0, False, 0.0),
+         (7, 7, 250, 2, 0.3, True, 0.6)]
+
+
+def make_window(i):
+    """A covisibility window in the reference's terms: key-frame 0 is pKF (the newest), `covisible` its neighbours, the remaining key-frames
+    are found by the function itself through the observations (fixed cameras).  Poses go through float 4 x 4 matrices (KeyFrame::GetPose),
+    positions through float vectors, key-points carry the octave whose mvInvLevelSigma2 becomes the edge information."""
+    import oracle
+    from airdos_b200 import synth
+    seed, n_kf, n_pts, n_fixed, mono, zero_in, pn = CASES[i]
+    d = synth.make_ba_problem(n_kf, n_pts, 5, seed=seed, mono_frac=mono, n_fixed_extra=n_fixed)
+    rng = np.random.default_rng(seed)
+    d["points"] = d["points"] + rng.normal(0, pn, d["points"].shape)
+    K = len(d["pose_t"])
+    cur = n_kf - 1
+    order = [cur] + [k for k in range(n_kf) if k != cur] + list(range(n_kf, K))
+    pos = {k: j for j, k in enumerate(order)}
+    ids = np.array([(k if zero_in else k + 3) * 2 for k in order], np.int32)       # mnId 0 (when present) is fixed by the function itself
+    lib = oracle.ba_lib()
+    lib.ba_oracle_pose_to_tcw.argtypes = [C.c_void_p] * 3
+    tcw = np.zeros((K, 4, 4), np.float32)
+    for j, k in enumerate(order):
+        q = np.ascontiguousarray(d["pose_q"][k]); t = np.ascontiguousarray(d["pose_t"][k]); T = np.zeros(16, np.float32)
+        lib.ba_oracle_pose_to_tcw(q.ctypes.data, t.ctypes.data, T.ctypes.data)
+        tcw[j] = T.reshape(4, 4)
+    sig = oracle.orb_tables(2000, 1.2, 8)["inv_sigma2"]                             # mvInvLevelSigma2 as the extractor's constructor leaves it
+    octave = np.array([int(np.argmin(np.abs(sig - np.float32(w)))) for w in d["edge_info"]], np.int32)
+    return dict(kf_id=ids, kf_tcw=tcw, covisible=np.arange(1, n_kf, dtype=np.int32), fx=d["fx"], fy=d["fy"], cx=d["cx"], cy=d["cy"], bf=d["bf"],
+                inv_level_sigma2=sig, mp_id=np.arange(len(d["points"]), dtype=np.int32) * 3 + 1, mp_pos=d["points"].astype(np.float32),
+                obs_kf=np.array([pos[k] for k in d["edge_pose"]], np.int32), obs_mp=d["edge_point"].astype(np.int32),
+                obs_uvr=d["edge_obs"].astype(np.float32), obs_octave=octave)
+
+
+def main():
+    import oracle
+    oracle.build()
+    LM = C.CDLL(os.path.join(REF, "libref_lm.so")); LBA = C.CDLL(os.path.join(REF, "libref_lba.so"))
+    out = {}
+    for i in range(len(CASES)):
+        w = make_window(i)
+        r = oracle.ref_local_bundle_adjustment(LBA, LM, w)
+        o = oracle.ba_default_options(); o.huber_mono, o.huber_stereo = r["huber"]
+        p, res, st = oracle.ba_solve(r["problem"], o)
+        fs = np.concatenate([p["pose_q"].ravel(), p["pose_t"].ravel(), p["points"].ravel()])
+        tr = res.trace_rows[:, [0, 1, 2, 4]]
+        flagged = np.flatnonzero(res.edge_outlier)
+        print(f"window {i}: {len(r['pose_id'])} key-frames ({int(r['problem']['pose_fixed'].sum())} fixed), {len(r['point_id'])} points, "
+              f"{len(r['problem']['edge_pose'])} edges, rounds {list(r['round_iterations'])} robust {list(r['round_robust'])}, {len(r['rows'])} trials, "
+              f"{len(r['erased'])} erased | oracle: status {st}, trials identical {tr.shape == r['rows'].shape and bool((tr == r['rows']).all())}, "
+              f"state identical {bool((fs == r['final_state']).all())}, outliers {len(flagged)}")
+        for k in ("kf_tcw", "mp_pos", "erased", "mp_updates", "rows", "final_state", "pose_id", "point_id", "round_iterations", "round_robust"):
+            out[f"w{i}_{k}"] = r[k]
+        out[f"w{i}_huber"] = np.array(r["huber"])
+        for k, v in r["problem"].items():
+            out[f"w{i}_p_{k}"] = np.asarray(v)
+    path = os.path.join(ROOT, "tests", "golden", "lba_ref.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

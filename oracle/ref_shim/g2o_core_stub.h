@@ -27,8 +27,29 @@ struct OptimizableGraph {
         virtual void oplusImpl(const double* update) = 0;
         virtual void setToOriginImpl() = 0;
         void updateCache() {}
+        // graph bookkeeping the Optimizer functions set (core/optimizable_graph.h: id, fixed, marginalized); used by oracle/ref_lba.cpp
+        int id() const { return _id; }
+        void setId(int i) { _id = i; }
+        bool fixed() const { return _fixed; }
+        void setFixed(bool f) { _fixed = f; }
+        bool marginalized() const { return _marginalized; }
+        void setMarginalized(bool m) { _marginalized = m; }
+    protected:
+        int _id = -1;
+        bool _fixed = false, _marginalized = false;
     };
 };
+#ifdef G2O_STUB_WITH_GRAPH_MEMBERS
+class RobustKernel {                        // core/robust_kernel.h:50-70
+public:
+    virtual ~RobustKernel() {}
+    virtual void robustify(double squaredError, Eigen::Vector3d& rho) const = 0;
+    virtual void setDelta(double delta) { _delta = delta; }
+    double delta() const { return _delta; }
+protected:
+    double _delta = 1.0;
+};
+#endif
 
 template <int D, typename T> class BaseVertex : public OptimizableGraph::Vertex {
 public:
@@ -53,6 +74,16 @@ public:
     const InformationType& information() const { return _information; }
     void setVertex(size_t i, HyperGraph::Vertex* v) { if (_vertices.size() <= i) _vertices.resize(i + 1, nullptr); _vertices[i] = v; }
     std::vector<HyperGraph::Vertex*> _vertices;
+#ifdef G2O_STUB_WITH_GRAPH_MEMBERS              // what Optimizer::LocalBundleAdjustment touches on an edge (oracle/ref_lba.cpp)
+    void setInformation(const InformationType& i) { _information = i; }
+    int level() const { return _level; }
+    void setLevel(int l) { _level = l; }
+    RobustKernel* robustKernel() const { return _robustKernel; }
+    void setRobustKernel(RobustKernel* k) { _robustKernel = k; }
+#include "_ref/lm_edge_inline.inc"             // chi2(), robustInformation(): the reference's inline bodies (core/base_edge.h:58-61, 96-102)
+    int _level = 0;
+    RobustKernel* _robustKernel = nullptr;
+#endif
 protected:
     Measurement _measurement;
     InformationType _information;

@@ -181,3 +181,40 @@ def test_dumped_dynamic_window_replays(opt, oracle_mod, tmp_path):
     assert np.abs(pg["joints"] - po["joints"]).max() < 1e-4 and np.abs(pg["dists"] - po["dists"]).max() < 1e-4
     assert (rg.redge_outlier == ro.redge_outlier).all() and (rg.medge_outlier == ro.medge_outlier).all()
     assert rg.c.chi2_round[0] < rg.c.chi2_initial
+
+
+def test_local_ba_against_the_reference_function(opt):
+    """adb_ba_solve against tests/golden/lba_ref.npz = the reference's own Optimizer::LocalBundleAdjustment (src/Optimizer.cc:431-731, whole
+    function compiled from /root/reference: oracle/ref_lba.cpp) on five covisibility windows: the problems are the ones that function
+    built; the erase list (outlier flags) must be identical, every LM trial must take the same accept / reject decision with lambda and
+    chi2 within 1e-6 relative, the final estimates within 1e-9, and the poses written back through the converter (float 4 x 4) equal."""
+    import os
+    from airdos_b200 import ba
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "lba_ref.npz"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("test_ref_lba", os.path.join(root, "tests", "test_ref_lba.py"))
+    helper = importlib.util.module_from_spec(spec); spec.loader.exec_module(helper)
+    i = 0
+    while f"w{i}_rows" in gold.files:
+        prob = {k[len(f"w{i}_p_"):]: (gold[k].item() if gold[k].ndim == 0 else gold[k]) for k in gold.files if k.startswith(f"w{i}_p_")}
+        pg, rg, sg = opt.LocalBundleAdjustment(prob)
+        assert sg == 0
+        rows = gold[f"w{i}_rows"]
+        tg = rg.trace_rows
+        assert len(tg) == len(rows) and (tg[:, 4] == rows[:, 3]).all(), i
+        assert np.allclose(tg[:, :3], rows[:, :3], rtol=1e-6), i
+        assert list(rg.c.iterations_run) == list(gold[f"w{i}_round_iterations"])
+        state = np.concatenate([pg["pose_q"].ravel(), pg["pose_t"].ravel(), pg["points"].ravel()])
+        assert np.abs(state - gold[f"w{i}_final_state"]).max() < 1e-9, i
+        # the erase list: (key-frame, map point) pairs in the reference's order, rebuilt from the outlier flags
+        assert (helper.erase_list_from_flags(gold, i, rg.edge_outlier) == gold[f"w{i}_erased"]).all(), i
+        # written-back poses of the free key-frames
+        n_free = int((prob["pose_fixed"] == 0).sum())
+        hits = 0
+        for j in range(len(prob["pose_fixed"])):
+            T = ba.pose_to_tcw(pg["pose_q"].reshape(-1, 4)[j], pg["pose_t"].reshape(-1, 3)[j])
+            hits += int(any(np.abs(T - G).max() < 1e-6 for G in gold[f"w{i}_kf_tcw"]))
+        assert hits >= n_free, i
+        i += 1
+    assert i == 5

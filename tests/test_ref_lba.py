@@ -1,0 +1,126 @@
+"""Pins the LocalBundleAdjustment schedule of oracle/ba_oracle.cpp (ba_oracle_solve) to the LITERAL reference: tests/golden/lba_ref.npz
+holds what the reference's own Optimizer::LocalBundleAdjustment (src/Optimizer.cc:431-731, the whole function compiled from
+/root/reference: oracle/ref_lba.cpp) does on five seeded covisibility windows -- which key-frames it frees and fixes, the edges it
+builds (information from mvInvLevelSigma2[octave], Huber deltas sqrt(5.991) / sqrt(7.815) as floats), optimize(5) with the kernel,
+the chi2 / depth gate with the reference's own edge types, optimize(10) without kernel and without the gated edges, the erase list and
+the poses / positions written back through Converter.  Its LM control is the reference's too (oracle/ref_lm.cpp); its solver steps are
+the oracle's.  ba_oracle_solve on the problem the function built must give every LM trial, the final estimates and the erase list
+bit for bit; oracle/gen_ref_lba_golden.py wrote the fixture."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "lba_ref.npz")
+REF = os.path.join(ROOT, "oracle", "_ref")
+HAVE_REF = os.path.exists(os.path.join(REF, "libref_lba.so")) and os.path.isdir("/root/reference")
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("gen_ref_lba_golden", os.path.join(ROOT, "oracle", "gen_ref_lba_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    return g
+
+
+def fixture_problem(gold, i):
+    return {k[len(f"w{i}_p_"):]: (gold[k].item() if gold[k].ndim == 0 else gold[k]) for k in gold.files if k.startswith(f"w{i}_p_")}
+
+
+def erase_list_from_flags(gold, i, flags):
+    """(key-frame index, map-point index) pairs in the reference's order: monocular edges first, then stereo (src/Optimizer.cc:672-700)."""
+    p = fixture_problem(gold, i)
+    g = _gen()
+    w = g.make_window(i)
+    kf_of = {int(v): j for j, v in enumerate(w["kf_id"])}; mp_of = {int(v): j for j, v in enumerate(w["mp_id"])}
+    max_kf = int(w["kf_id"].max())
+    mono = p["edge_obs"][:, 2] < 0
+    pairs = []
+    for sel in (mono, ~mono):
+        for e in np.flatnonzero(sel & (flags != 0)):
+            pairs.append((kf_of[int(gold[f"w{i}_pose_id"][p["edge_pose"][e]])], mp_of[int(gold[f"w{i}_point_id"][p["edge_point"][e]]) - max_kf - 1]))
+    return np.array(pairs, np.int32).reshape(-1, 2)
+
+
+def test_oracle_schedule_equals_the_reference_function(oracle_mod):
+    gold = np.load(GOLD)
+    g = _gen()
+    for i in range(len(g.CASES)):
+        prob = fixture_problem(gold, i)
+        o = oracle_mod.ba_default_options()
+        assert (o.huber_mono, o.huber_stereo) == tuple(gold[f"w{i}_huber"])           # thHuberMono / thHuberStereo (:538-539)
+        assert [o.robust[0], o.robust[1]] == list(gold[f"w{i}_round_robust"])          # kernel in round 1, setRobustKernel(0) before round 2
+        p, res, st = oracle_mod.ba_solve(prob, o)
+        assert st == 0
+        assert [res.c.iterations_run[0], res.c.iterations_run[1]] == list(gold[f"w{i}_round_iterations"]), i
+        tr = res.trace_rows[:, [0, 1, 2, 4]]
+        assert tr.shape == gold[f"w{i}_rows"].shape and (tr == gold[f"w{i}_rows"]).all(), i
+        state = np.concatenate([p["pose_q"].ravel(), p["pose_t"].ravel(), p["points"].ravel()])
+        assert (state == gold[f"w{i}_final_state"]).all(), i
+        assert (erase_list_from_flags(gold, i, res.edge_outlier) == gold[f"w{i}_erased"]).all(), i
+
+
+def test_written_back_poses_and_positions(oracle_mod):
+    """KeyFrame::SetPose(Converter::toCvMat(SE3Quat)) and MapPoint::SetWorldPos(Converter::toCvMat(Vector3d)) of the function against the
+    oracle's converters on the oracle's result; key-frames the function fixed keep their pose, every local point is updated once."""
+    import ctypes as C
+    gold = np.load(GOLD)
+    g = _gen()
+    lib = oracle_mod.ba_lib()
+    lib.ba_oracle_pose_to_tcw.argtypes = [C.c_void_p] * 3
+    for i in range(len(g.CASES)):
+        w = g.make_window(i)
+        prob = fixture_problem(gold, i)
+        p, res, st = oracle_mod.ba_solve(prob)
+        kf_of = {int(v): j for j, v in enumerate(w["kf_id"])}
+        n_local = 1 + len(w["covisible"])
+        for j, vid in enumerate(gold[f"w{i}_pose_id"]):
+            k = kf_of[int(vid)]
+            T = np.zeros(16, np.float32)
+            q = np.ascontiguousarray(p["pose_q"][j]); t = np.ascontiguousarray(p["pose_t"][j])
+            lib.ba_oracle_pose_to_tcw(q.ctypes.data, t.ctypes.data, T.ctypes.data)
+            if k < n_local:
+                assert (T.reshape(4, 4) == gold[f"w{i}_kf_tcw"][k]).all(), (i, k)
+            else:                                                      # fixed cameras are never written back (:712-718 walks lLocalKeyFrames)
+                assert (gold[f"w{i}_kf_tcw"][k] == w["kf_tcw"][k]).all()
+        mp_of = {int(v): j for j, v in enumerate(w["mp_id"])}
+        max_kf = int(w["kf_id"].max())
+        seen = np.zeros(len(w["mp_id"]), bool)
+        for l, vid in enumerate(gold[f"w{i}_point_id"]):
+            m = mp_of[int(vid) - max_kf - 1]
+            seen[m] = True
+            assert (p["points"][l].astype(np.float32) == gold[f"w{i}_mp_pos"][m]).all(), (i, m)
+        assert (gold[f"w{i}_mp_updates"] == seen.astype(np.int32)).all()              # UpdateNormalAndDepth once per local point
+        assert (gold[f"w{i}_mp_pos"][~seen] == w["mp_pos"][~seen]).all()
+
+
+def test_problem_the_function_built(oracle_mod):
+    """Vertex order (ascending id), the fixed flags (mnId == 0 and the cameras outside the covisibility list), edge information and the
+    stereo / mono split of the recorded problem follow from the window."""
+    gold = np.load(GOLD)
+    g = _gen()
+    for i in range(len(g.CASES)):
+        w = g.make_window(i)
+        p = fixture_problem(gold, i)
+        pid = gold[f"w{i}_pose_id"]
+        assert (np.diff(pid) > 0).all() and (np.diff(gold[f"w{i}_point_id"]) > 0).all()
+        kf_of = {int(v): j for j, v in enumerate(w["kf_id"])}
+        n_local = 1 + len(w["covisible"])
+        want_fixed = np.array([int(v) == 0 or kf_of[int(v)] >= n_local for v in pid])
+        assert (p["pose_fixed"].astype(bool) == want_fixed).all(), i
+        assert set(np.unique(p["edge_info"].astype(np.float32))) <= set(w["inv_level_sigma2"])
+        assert len(p["edge_pose"]) == len(w["obs_kf"])                                # every observation of a local point became an edge
+        assert int((p["edge_obs"][:, 2] < 0).sum()) == int((w["obs_uvr"][:, 2] < 0).sum())   # mvuRight < 0 -> EdgeSE3ProjectXYZ
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree / oracle/_ref not present (GPU box)")
+def test_fixture_is_what_the_reference_library_computes_now(oracle_mod):
+    import ctypes as C
+    g = _gen()
+    gold = np.load(GOLD)
+    LM = C.CDLL(os.path.join(REF, "libref_lm.so")); LBA = C.CDLL(os.path.join(REF, "libref_lba.so"))
+    for i in (1, 4):
+        r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, g.make_window(i))
+        for k in ("kf_tcw", "mp_pos", "erased", "rows", "final_state"):
+            assert (r[k] == gold[f"w{i}_{k}"]).all(), (i, k)
