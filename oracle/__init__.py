@@ -528,7 +528,8 @@ def huber(delta: float, e2: float, lib=None):
 # ------------------------------------------------------------------------------------------
 # oracle/ref_lba.cpp: the reference's Optimizer::LocalBundleAdjustment over the oracle's solver session
 class _LbaBackend(C.Structure):
-    _fields_ = [("steps", LmHooks)] + [(n, C.c_void_p) for n in ("open", "close", "set_levels", "state", "lm_optimize", "default_options")]
+    _fields_ = ([("steps", LmHooks)] + [(n, C.c_void_p) for n in ("open", "close", "set_levels", "state", "lm_optimize", "default_options")] +
+                [("pose_steps", LmHooks)] + [(n, C.c_void_p) for n in ("pose_open", "pose_close", "pose_state")])
 
 
 class _LbaIO(C.Structure):
@@ -546,12 +547,7 @@ def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict):
     fx fy cx cy bf, inv_level_sigma2, mp_id, mp_pos [m,3] f32, obs_kf, obs_mp, obs_uvr [o,3] f32, obs_octave; key-frame 0 = pKF), its
     solver steps being the oracle's and its LM control the reference's (libref_lm.so).  Returns the function's outputs and the problem /
     trial rows the stand-in optimizer recorded (a dict in make_ba_problem layout, usable with ba_solve)."""
-    lib = ba_lib()
-    be = _LbaBackend()
-    be.steps = LmHooks(None, *[C.cast(getattr(lib, "ba_oracle_lm_" + n), C.c_void_p) for n in _LM_HOOKS])
-    for n, f in (("open", lib.ba_oracle_lm_open), ("close", lib.ba_oracle_lm_close), ("set_levels", lib.ba_oracle_lm_set_levels),
-                 ("state", lib.ba_oracle_lm_state), ("lm_optimize", lm_lib.ref_lm_optimize), ("default_options", lib.ba_oracle_default_options)):
-        setattr(be, n, C.cast(f, C.c_void_p))
+    be = _lba_backend(lm_lib)
     a = lambda k, t: np.ascontiguousarray(w[k], t)
     kf_id, tcw, cov = a("kf_id", np.int32), a("kf_tcw", np.float32), a("covisible", np.int32)
     sig, mp_id, mp_pos = a("inv_level_sigma2", np.float32), a("mp_id", np.int32), a("mp_pos", np.float32)
@@ -581,3 +577,66 @@ def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict):
                final_state=f64(6), pose_id=i32(2), point_id=i32(3), round_iterations=i32(4), round_robust=i32(5), huber=(cam[5], cam[6]))
     lba_lib.ref_lba_record_free(rec)
     return out
+
+
+class _PoseIO(C.Structure):
+    _fields_ = [("tcw", C.c_void_p), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("n_levels", C.c_int32), ("inv_level_sigma2", C.c_void_p), ("n", C.c_int32), ("uvr", C.c_void_p), ("octave", C.c_void_p),
+                ("xw", C.c_void_p), ("has_point", C.c_void_p), ("outlier", C.c_void_p), ("tcw_out", C.c_void_p), ("n_inliers", C.c_int32)]
+
+
+def _lba_backend(lm_lib):
+    lib = ba_lib()
+    lib.ba_oracle_lm_open.restype = C.c_void_p
+    lib.ba_oracle_pose_lm_open.restype = C.c_void_p
+    be = _LbaBackend()
+    be.steps = LmHooks(None, *[C.cast(getattr(lib, "ba_oracle_lm_" + n), C.c_void_p) for n in _LM_HOOKS])
+    be.pose_steps = LmHooks(None, *[C.cast(getattr(lib, "ba_oracle_pose_lm_" + n), C.c_void_p) for n in _LM_HOOKS])
+    for n, f in (("open", lib.ba_oracle_lm_open), ("close", lib.ba_oracle_lm_close), ("set_levels", lib.ba_oracle_lm_set_levels),
+                 ("state", lib.ba_oracle_lm_state), ("lm_optimize", lm_lib.ref_lm_optimize), ("default_options", lib.ba_oracle_default_options),
+                 ("pose_open", lib.ba_oracle_pose_lm_open), ("pose_close", lib.ba_oracle_pose_lm_close), ("pose_state", lib.ba_oracle_pose_lm_state)):
+        setattr(be, n, C.cast(f, C.c_void_p))
+    return be
+
+
+def ref_pose_optimization(lba_lib, lm_lib, fr: dict):
+    """Runs the reference's Optimizer::PoseOptimization (oracle/_ref/libref_lba.so) on frame `fr` (tcw [4,4] f32, fx fy cx cy bf,
+    inv_level_sigma2, uvr [n,3] f32, octave [n], xw [n,3] f32, has_point [n]) over the oracle's pose session and the reference's LM control.
+    Returns mvbOutlier, the return value, the pose written back and what the stand-in optimizer recorded."""
+    be = _lba_backend(lm_lib)
+    a = lambda k, t: np.ascontiguousarray(fr[k], t)
+    tcw, sig, uvr, octv, xw, has = a("tcw", np.float32), a("inv_level_sigma2", np.float32), a("uvr", np.float32), a("octave", np.int32), a("xw", np.float32), a("has_point", np.uint8)
+    n = len(octv)
+    outl = np.zeros(max(n, 1), np.uint8); tcw_out = np.zeros((4, 4), np.float32)
+    io = _PoseIO(_p(tcw), fr["fx"], fr["fy"], fr["cx"], fr["cy"], fr["bf"], len(sig), _p(sig), n, _p(uvr), _p(octv), _p(xw), _p(has), _p(outl), _p(tcw_out), 0)
+    rec = C.c_void_p()
+    lba_lib.ref_pose_run.argtypes = [C.POINTER(_LbaBackend), C.POINTER(_PoseIO), C.POINTER(C.c_void_p)]
+    for f in (lba_lib.ref_lba_record_f64, lba_lib.ref_lba_record_i32, lba_lib.ref_lba_record_f32):
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lba_lib.ref_lba_record_free.argtypes = [C.c_void_p]
+    assert lba_lib.ref_pose_run(C.byref(be), C.byref(io), C.byref(rec)) == 0
+
+    def get(fn, which, dt):
+        m = fn(rec, which, None, 0); v = np.zeros(m, dt); fn(rec, which, _p(v), m); return v
+
+    cam = get(lba_lib.ref_lba_record_f64, 7, np.float64)
+    out = dict(outlier=outl[:n].copy(), n_inliers=io.n_inliers, tcw=tcw_out, rows=get(lba_lib.ref_lba_record_f64, 5, np.float64).reshape(-1, 4),
+               final_state=get(lba_lib.ref_lba_record_f64, 6, np.float64), round_iterations=get(lba_lib.ref_lba_record_i32, 4, np.int32),
+               round_robust=get(lba_lib.ref_lba_record_i32, 5, np.int32), round_active=get(lba_lib.ref_lba_record_i32, 7, np.int32),
+               cam=dict(fx=cam[0], fy=cam[1], cx=cam[2], cy=cam[3], bf=cam[4]),
+               frame=dict(pose_q=get(lba_lib.ref_lba_record_f64, 0, np.float64), pose_t=get(lba_lib.ref_lba_record_f64, 1, np.float64),
+                          xw=get(lba_lib.ref_lba_record_f32, 0, np.float32).reshape(-1, 3), obs=get(lba_lib.ref_lba_record_f32, 1, np.float32).reshape(-1, 3),
+                          inv_sigma2=get(lba_lib.ref_lba_record_f32, 2, np.float32)))
+    lba_lib.ref_lba_record_free(rec)
+    return out
+
+
+def pose_optimize_traced(cam: dict, frame: dict):
+    """The oracle's four-round PoseOptimization on one frame with its LM trials -> (PoseBatch, rows [(lambda, chi2 before, after, accepted)])."""
+    from airdos_b200 import ba_types as T
+    pb = T.PoseBatch(cam, [frame])
+    lib = ba_lib()
+    lib.ba_oracle_pose_optimize_traced.argtypes = [C.POINTER(T.PoseProblem), C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rows = np.zeros((512, 4)); n = C.c_int()
+    lib.ba_oracle_pose_optimize_traced(C.byref(pb.c), 0, _p(rows), 512, C.byref(n))
+    return pb, rows[:n.value].copy()

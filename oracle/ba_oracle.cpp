@@ -24,6 +24,7 @@
 // rigidity Jacobian, D.5 motion prior = identity (the caller passes it), D.6 d(error)/d(motion
 // translation) = delta_t * I with a zero rotation block.
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -887,115 +888,193 @@ inline void pose_edge_quadratic_form(int dim, const double* J, const double* er,
     }
 }
 
-int pose_optimize_one(const adb_pose_problem& P, int f) {
-    const int a = P.frame_ptr[f], n = P.frame_ptr[f + 1] - a;
-    std::vector<PoseEdge> E(n);
-    for (int i = 0; i < n; ++i) {
-        for (int k = 0; k < 3; ++k) { E[i].X[k] = (double)P.xw[3 * (size_t)(a + i) + k]; E[i].obs[k] = (double)P.obs[3 * (size_t)(a + i) + k]; }
-        E[i].w = (double)P.inv_sigma2[a + i];
-        E[i].stereo = !(P.obs[3 * (size_t)(a + i) + 2] < 0);
-        P.outlier[a + i] = 0;
-    }
-    if (n < 3) return 0;
-    const Huber hmono = make_huber((double)(float)std::sqrt(5.991)), hstereo = make_huber((double)(float)std::sqrt(7.815));
-    double q0[4], t0[3];
-    std::memcpy(q0, P.pose_q + 4 * f, sizeof(q0)); std::memcpy(t0, P.pose_t + 3 * f, sizeof(t0));
-    double q[4], t[3];
-    std::vector<uint8_t> level(n, 0);
-    std::vector<double> chi(n, 0.0);
+// One frame of PoseOptimization as solver steps (the same split as Solver above: evaluate / build / solve / update / push / pop), so that
+// both the loop below and the reference's own control flow (oracle/ref_lm.cpp, ref_lba.cpp) can drive it.
+struct PoseSolver {
+    const adb_pose_problem& P;
+    int f, a, n;
+    std::vector<PoseEdge> E;
+    std::vector<uint8_t> level;
+    std::vector<double> chi;
     bool robust = true;
+    Huber hmono = make_huber((double)(float)std::sqrt(5.991)), hstereo = make_huber((double)(float)std::sqrt(7.815));
+    double q[4], t[3];
+    double H[36], b[6], x[6], lambda = 0, ni = 2;
+    std::vector<std::array<double, 7>> stack;
+    std::vector<double> trace;   // (lambda, chi2 before, chi2 after, accepted) per trial
+
+    PoseSolver(const adb_pose_problem& p, int frame) : P(p), f(frame), a(p.frame_ptr[frame]), n(p.frame_ptr[frame + 1] - p.frame_ptr[frame]) {
+        E.resize(n);
+        for (int i = 0; i < n; ++i) {
+            for (int k = 0; k < 3; ++k) { E[i].X[k] = (double)P.xw[3 * (size_t)(a + i) + k]; E[i].obs[k] = (double)P.obs[3 * (size_t)(a + i) + k]; }
+            E[i].w = (double)P.inv_sigma2[a + i];
+            E[i].stereo = !(P.obs[3 * (size_t)(a + i) + 2] < 0);
+        }
+        level.assign(n, 0); chi.assign(n, 0.0);
+        std::memcpy(q, P.pose_q + 4 * f, sizeof(q)); std::memcpy(t, P.pose_t + 3 * f, sizeof(t));
+        std::memset(H, 0, sizeof(H)); std::memset(b, 0, sizeof(b)); std::memset(x, 0, sizeof(x));
+    }
+    int n_active() const { int c = 0; for (int i = 0; i < n; ++i) c += !level[i]; return c; }
+    double evaluate() {          // computeActiveErrors + activeRobustChi2 at the current pose
+        double R[9], s = 0, r0, r1;
+        quat_to_rot(q, R);
+        for (int i = 0; i < n; ++i) {
+            if (level[i]) continue;
+            double er[3], Xc[3];
+            pose_edge_error(P, R, t, E[i], er, Xc);
+            const double c = er[0] * (E[i].w * er[0]) + er[1] * (E[i].w * er[1]) + er[2] * (E[i].w * er[2]);
+            chi[i] = c;
+            robustify(E[i].stereo ? hstereo : hmono, robust, c, &r0, &r1);
+            s += r0;
+        }
+        return s;
+    }
+    void build_system() {
+        std::memset(H, 0, sizeof(H)); std::memset(b, 0, sizeof(b));
+        double R[9];
+        quat_to_rot(q, R);
+        for (int i = 0; i < n; ++i) {
+            if (level[i]) continue;
+            double er[3], Xc[3], J[18];
+            pose_edge_error(P, R, t, E[i], er, Xc);
+            pose_edge_jac(P, Xc, E[i].stereo, J);
+            double h[36], g[6];
+            pose_edge_quadratic_form(E[i].stereo ? 3 : 2, J, er, E[i].w, E[i].stereo ? hstereo : hmono, robust, h, g);
+            for (int u = 0; u < 36; ++u) H[u] += h[u];
+            for (int u = 0; u < 6; ++u) b[u] += g[u];
+        }
+    }
+    double max_diag() const { double m = 0; for (int u = 0; u < 6; ++u) m = std::max(m, std::fabs(H[u * 7])); return m; }
+    bool solve_trial() {         // (H + lambda I) x = b by dense Cholesky (g2o: LinearSolverDense)
+        std::vector<double> S(H, H + 36);
+        for (int u = 0; u < 6; ++u) S[u * 7] += lambda;
+        std::memcpy(x, b, sizeof(x));
+        if (!cholesky(S, 6)) return false;
+        chol_solve(S, 6, x);
+        return true;
+    }
+    void apply_update() { pose_oplus(q, t, x); }
+    double scale_term() const { double s = 0; for (int u = 0; u < 6; ++u) s += x[u] * (lambda * x[u] + b[u]); return s; }
+    void push() { stack.push_back({q[0], q[1], q[2], q[3], t[0], t[1], t[2]}); }
+    void pop() { const auto& v = stack.back(); for (int k = 0; k < 4; ++k) q[k] = v[k]; for (int k = 0; k < 3; ++k) t[k] = v[4 + k]; stack.pop_back(); }
+    void discard_top() { stack.pop_back(); }
+
+    // SparseOptimizer::optimize(iterations) + OptimizationAlgorithmLevenberg::solve, as Solver::optimize
+    int optimize(int iterations) {
+        int nbad_it = 0, it_run = 0;
+        for (int it = 0; it < iterations; ++it) {
+            double current = evaluate();
+            const double ini = current;
+            build_system();
+            if (it == 0) { lambda = 1e-5 * max_diag(); ni = 2; nbad_it = 0; }
+            double rho = 0; int qn = 0;
+            do {
+                push();
+                const bool ok = solve_trial();
+                if (ok) apply_update();
+                double temp = evaluate();
+                if (!ok) temp = std::numeric_limits<double>::max();
+                rho = current - temp;
+                double scale = ok ? scale_term() : 0.0;
+                scale += 1e-3;
+                rho /= scale;
+                const bool good = rho > 0 && std::isfinite(temp);
+                trace.insert(trace.end(), {lambda, current, temp, good ? 1.0 : 0.0});
+                if (good) {
+                    double alpha = 1. - std::pow((2 * rho - 1), 3);
+                    alpha = std::min(alpha, 2. / 3.);
+                    lambda *= std::max(1. / 3., alpha); ni = 2; current = temp;
+                    discard_top();
+                } else { lambda *= ni; ni *= 2; pop(); }
+                ++qn;
+            } while (rho < 0 && qn < 10);
+            ++it_run;
+            if (qn == 10 || rho == 0) break;
+            if ((ini - current) * 1e3 < ini) ++nbad_it; else nbad_it = 0;
+            if (nbad_it >= 3) break;
+        }
+        return it_run;
+    }
+};
+
+int pose_optimize_one(const adb_pose_problem& P, int f, std::vector<double>* trace_out = nullptr) {
+    PoseSolver S(P, f);
+    const int a = S.a, n = S.n;
+    for (int i = 0; i < n; ++i) P.outlier[a + i] = 0;
+    if (n < 3) return 0;
+    double q0[4], t0[3];
+    std::memcpy(q0, S.q, sizeof(q0)); std::memcpy(t0, S.t, sizeof(t0));
     int nBad = 0;
     for (int round = 0; round < 4; ++round) {
-        std::memcpy(q, q0, sizeof(q)); std::memcpy(t, t0, sizeof(t));
-        int nact = 0;
-        for (int i = 0; i < n; ++i) nact += !level[i];
-        auto evaluate = [&](const double* qq, const double* tt) {
-            double R[9], s = 0, r0, r1;
-            quat_to_rot(qq, R);
-            for (int i = 0; i < n; ++i) {
-                if (level[i]) continue;
-                double er[3], Xc[3];
-                pose_edge_error(P, R, tt, E[i], er, Xc);
-                const double c = er[0] * (E[i].w * er[0]) + er[1] * (E[i].w * er[1]) + er[2] * (E[i].w * er[2]);
-                chi[i] = c;
-                robustify(E[i].stereo ? hstereo : hmono, robust, c, &r0, &r1);
-                s += r0;
-            }
-            return s;
-        };
-        if (nact > 0) {   // optimizer.optimize(10) with 0 active vertices returns immediately
-            double lambda = 0, ni = 2;
-            int nbad_it = 0;
-            for (int it = 0; it < 10; ++it) {
-                double current = evaluate(q, t);
-                const double ini = current;
-                double H[36] = {0}, b[6] = {0}, R[9];
-                quat_to_rot(q, R);
-                for (int i = 0; i < n; ++i) {
-                    if (level[i]) continue;
-                    double er[3], Xc[3], J[18];
-                    pose_edge_error(P, R, t, E[i], er, Xc);
-                    pose_edge_jac(P, Xc, E[i].stereo, J);
-                    double h[36], g[6];
-                    pose_edge_quadratic_form(E[i].stereo ? 3 : 2, J, er, E[i].w, E[i].stereo ? hstereo : hmono, robust, h, g);
-                    for (int u = 0; u < 36; ++u) H[u] += h[u];
-                    for (int u = 0; u < 6; ++u) b[u] += g[u];
-                }
-                if (it == 0) { double m = 0; for (int u = 0; u < 6; ++u) m = std::max(m, std::fabs(H[u * 7])); lambda = 1e-5 * m; ni = 2; nbad_it = 0; }
-                double rho = 0; int qn = 0;
-                do {
-                    std::vector<double> S(H, H + 36);
-                    for (int u = 0; u < 6; ++u) S[u * 7] += lambda;
-                    double x[6]; std::memcpy(x, b, sizeof(x));
-                    const bool ok = cholesky(S, 6);
-                    double qn4[4], tn[3];
-                    std::memcpy(qn4, q, sizeof(qn4)); std::memcpy(tn, t, sizeof(tn));
-                    if (ok) { chol_solve(S, 6, x); pose_oplus(qn4, tn, x); }
-                    double temp = evaluate(qn4, tn);
-                    if (!ok) temp = std::numeric_limits<double>::max();
-                    rho = current - temp;
-                    double scale = 0;
-                    if (ok) for (int u = 0; u < 6; ++u) scale += x[u] * (lambda * x[u] + b[u]);
-                    scale += 1e-3;
-                    rho /= scale;
-                    if (rho > 0 && std::isfinite(temp)) {
-                        double alpha = 1. - std::pow((2 * rho - 1), 3);
-                        alpha = std::min(alpha, 2. / 3.);
-                        lambda *= std::max(1. / 3., alpha); ni = 2; current = temp;
-                        std::memcpy(q, qn4, sizeof(q)); std::memcpy(t, tn, sizeof(t));
-                    } else { lambda *= ni; ni *= 2; }
-                    ++qn;
-                } while (rho < 0 && qn < 10);
-                if (qn == 10 || rho == 0) break;
-                if ((ini - current) * 1e3 < ini) ++nbad_it; else nbad_it = 0;
-                if (nbad_it >= 3) break;
-            }
-        }
+        std::memcpy(S.q, q0, sizeof(q0)); std::memcpy(S.t, t0, sizeof(t0));   // vSE3->setEstimate(Converter::toSE3Quat(pFrame->mTcw)) (:341)
+        if (S.n_active() > 0) S.optimize(10);   // optimizer.optimize(10) with 0 active vertices returns immediately
         // classification (src/Optimizer.cc:361-416): outlier edges are re-evaluated at the round's final pose,
         // inlier edges keep the error of the last evaluated trial; float comparison
         double R[9];
-        quat_to_rot(q, R);
+        quat_to_rot(S.q, R);
         nBad = 0;
         for (int i = 0; i < n; ++i) {
             if (P.outlier[a + i]) {
                 double er[3], Xc[3];
-                pose_edge_error(P, R, t, E[i], er, Xc);
-                chi[i] = er[0] * (E[i].w * er[0]) + er[1] * (E[i].w * er[1]) + er[2] * (E[i].w * er[2]);
+                pose_edge_error(P, R, S.t, S.E[i], er, Xc);
+                S.chi[i] = er[0] * (S.E[i].w * er[0]) + er[1] * (S.E[i].w * er[1]) + er[2] * (S.E[i].w * er[2]);
             }
-            const float c = (float)chi[i];
-            if (c > (E[i].stereo ? 7.815f : 5.991f)) { P.outlier[a + i] = 1; level[i] = 1; ++nBad; }
-            else { P.outlier[a + i] = 0; level[i] = 0; }
+            const float c = (float)S.chi[i];
+            if (c > (S.E[i].stereo ? 7.815f : 5.991f)) { P.outlier[a + i] = 1; S.level[i] = 1; ++nBad; }
+            else { P.outlier[a + i] = 0; S.level[i] = 0; }
         }
-        if (round == 2) robust = false;
+        if (round == 2) S.robust = false;
         if (n < 10) break;
     }
-    std::memcpy(P.pose_q + 4 * f, q, sizeof(q)); std::memcpy(P.pose_t + 3 * f, t, sizeof(t));
+    std::memcpy(P.pose_q + 4 * f, S.q, sizeof(S.q)); std::memcpy(P.pose_t + 3 * f, S.t, sizeof(S.t));
+    if (trace_out) *trace_out = S.trace;
     return n - nBad;
 }
 }  // namespace
 
 extern "C" void ba_oracle_pose_quadratic_form(int dim, const double* J, const double* er, double w0, double delta, int robust, double* h, double* g) {
     pose_edge_quadratic_form(dim, J, er, w0, make_huber(delta), robust != 0, h, g);
+}
+// ---- PoseSolver's steps one by one for oracle/ref_lm.cpp / ref_lba.cpp (same contract as ba_oracle_lm_*)
+extern "C" {
+struct PoseSession { PoseSolver S; double chi = 0; PoseSession(const adb_pose_problem& p, int f) : S(p, f) {} };
+// level: [n] 1 = excluded (setLevel(1)); robust: Huber kernel on the active edges
+void* ba_oracle_pose_lm_open(adb_pose_problem* P, int frame, const uint8_t* level, int robust) {
+    PoseSession* h = new PoseSession(*P, frame);
+    for (int i = 0; i < h->S.n; ++i) h->S.level[i] = level ? level[i] : 0;
+    h->S.robust = robust != 0;
+    return h;
+}
+void ba_oracle_pose_lm_close(void* h) { delete (PoseSession*)h; }
+void ba_oracle_pose_lm_compute_errors(void* h) { PoseSession* s = (PoseSession*)h; s->chi = s->S.evaluate(); }
+double ba_oracle_pose_lm_chi2(void* h) { return ((PoseSession*)h)->chi; }
+void ba_oracle_pose_lm_build(void* h) { ((PoseSession*)h)->S.build_system(); }
+int ba_oracle_pose_lm_layout(void*, int32_t* dims, int cap) { if (cap > 0) dims[0] = 6; return 1; }
+int ba_oracle_pose_lm_vectors(void* h, double* x, double* b, double* diag, int cap) {
+    const PoseSolver& S = ((PoseSession*)h)->S;
+    for (int u = 0; u < 6 && u < cap; ++u) { if (x) x[u] = S.x[u]; if (b) b[u] = S.b[u]; if (diag) diag[u] = S.H[u * 7]; }
+    return 6;
+}
+void ba_oracle_pose_lm_set_lambda(void* h, double lambda) { ((PoseSession*)h)->S.lambda = lambda; }
+int ba_oracle_pose_lm_solve(void* h) { return ((PoseSession*)h)->S.solve_trial() ? 1 : 0; }
+void ba_oracle_pose_lm_update(void* h) { ((PoseSession*)h)->S.apply_update(); }
+void ba_oracle_pose_lm_push(void* h) { ((PoseSession*)h)->S.push(); }
+void ba_oracle_pose_lm_pop(void* h) { ((PoseSession*)h)->S.pop(); }
+void ba_oracle_pose_lm_discard_top(void* h) { ((PoseSession*)h)->S.discard_top(); }
+int ba_oracle_pose_lm_state(void* h, double* out, int cap) {       // q (x y z w), t
+    const PoseSolver& S = ((PoseSession*)h)->S;
+    for (int k = 0; k < 7 && k < cap; ++k) out[k] = k < 4 ? S.q[k] : S.t[k - 4];
+    return 7;
+}
+// the oracle's whole four-round schedule on one frame with the LM trials of all rounds: rows of (lambda, chi2 before, chi2 after, accepted)
+int ba_oracle_pose_optimize_traced(adb_pose_problem* P, int frame, double* rows, int row_cap, int* n_rows) {
+    std::vector<double> tr;
+    const int inl = pose_optimize_one(*P, frame, &tr);
+    *n_rows = (int)tr.size() / 4;
+    for (size_t i = 0; i < tr.size() && (int)i < 4 * row_cap; ++i) rows[i] = tr[i];
+    P->n_inliers[frame] = inl;
+    return inl;
+}
 }
 extern "C" int ba_oracle_pose_optimize(adb_pose_problem* P) {
     for (int f = 0; f < P->n_frames; ++f) P->n_inliers[f] = pose_optimize_one(*P, f);

@@ -59,6 +59,11 @@ struct ref_lba_backend {       // the oracle's session functions + the reference
     int (*lm_optimize)(const ref_lm_hooks*, int iterations, int max_trials, double* rows, int row_cap, int* n_rows, double* lambda_final,
                        int* n_error_evaluations, double* tau);
     void (*default_options)(adb_ba_options*);
+    // PoseOptimization: the oracle's one-frame pose session (ba_oracle_pose_lm_*)
+    ref_lm_hooks pose_steps;
+    void* (*pose_open)(adb_pose_problem*, int frame, const uint8_t* level, int robust);
+    void (*pose_close)(void*);
+    int (*pose_state)(void*, double*, int);
 };
 }
 
@@ -76,6 +81,7 @@ private:
 // solver construction as Optimizer.cc writes it: the objects only have to exist
 template <typename T> struct LinearSolver {};
 template <typename T> struct LinearSolverEigen : LinearSolver<T> {};
+template <typename T> struct LinearSolverDense : LinearSolver<T> {};
 struct BlockSolver_6_3 {
     typedef Eigen::Matrix<double, 6, 6> PoseMatrixType;
     typedef LinearSolver<PoseMatrixType> LinearSolverType;
@@ -90,6 +96,9 @@ struct LbaRecord {             // what the stand-in saw: the first round's probl
     double cam[5] = {0, 0, 0, 0, 0}, huber_mono = 0, huber_stereo = 0;
     std::vector<int32_t> round_iterations, round_robust;
     std::vector<double> final_state;
+    // PoseOptimization: the frame's correspondences as the function turned them into edges, and the active count of every round
+    std::vector<float> xw, obs, inv_sigma2;
+    std::vector<int32_t> round_active;
 };
 
 class SparseOptimizer {
@@ -98,18 +107,26 @@ public:
     LbaRecord* rec = nullptr;
     std::map<int, HyperGraph::Vertex*> vmap;
     struct EdgeRef { EdgeSE3ProjectXYZ* mono; EdgeStereoSE3ProjectXYZ* stereo; };
-    std::vector<EdgeRef> edges;          // insertion order = g2o's internal edge ids = the order of _activeEdges
+    std::vector<EdgeRef> ba_edges;       // insertion order = g2o's internal edge ids = the order of _activeEdges
+    struct PoseEdgeRef { EdgeSE3ProjectXYZOnlyPose* mono; EdgeStereoSE3ProjectXYZOnlyPose* stereo; };
+    std::vector<PoseEdgeRef> pose_edges;
+    struct EdgeCount { size_t n; size_t size() const { return n; } };
+    EdgeCount edges() const { return EdgeCount{ba_edges.size() + pose_edges.size()}; }   // optimizer.edges().size() (:418)
     int active_level = 0;
     bool* stop = nullptr;
 
     void setAlgorithm(OptimizationAlgorithmLevenberg*) {}
     void setForceStopFlag(bool* f) { stop = f; }
     bool addVertex(OptimizableGraph::Vertex* v) { vmap[v->id()] = v; return true; }
-    bool addEdge(EdgeSE3ProjectXYZ* e) { edges.push_back(EdgeRef{e, nullptr}); return true; }
-    bool addEdge(EdgeStereoSE3ProjectXYZ* e) { edges.push_back(EdgeRef{nullptr, e}); return true; }
+    bool addEdge(EdgeSE3ProjectXYZ* e) { ba_edges.push_back(EdgeRef{e, nullptr}); return true; }
+    bool addEdge(EdgeStereoSE3ProjectXYZ* e) { ba_edges.push_back(EdgeRef{nullptr, e}); return true; }
+    bool addEdge(EdgeSE3ProjectXYZOnlyPose* e) { pose_edges.push_back(PoseEdgeRef{e, nullptr}); return true; }
+    bool addEdge(EdgeStereoSE3ProjectXYZOnlyPose* e) { pose_edges.push_back(PoseEdgeRef{nullptr, e}); return true; }
     HyperGraph::Vertex* vertex(int id) { auto it = vmap.find(id); return it == vmap.end() ? nullptr : it->second; }
     bool initializeOptimization(int level = 0) { active_level = level; return true; }
-    int optimize(int iterations);
+    int optimize(int iterations) { return pose_edges.empty() ? optimize_ba(iterations) : optimize_pose(iterations); }
+    int optimize_ba(int iterations);
+    int optimize_pose(int iterations);
 
     // ---- session plumbing
     struct Run {
@@ -130,9 +147,9 @@ public:
             for (size_t l = 0; l < nx; ++l) points[l]->setEstimate(Eigen::Vector3d(s[7 * np + 3 * l], s[7 * np + 3 * l + 1], s[7 * np + 3 * l + 2]));
         }
         void real_errors() {   // g2o's computeActiveErrors on the real edges (core/sparse_optimizer.cpp:70-97): active edges only
-            for (size_t e = 0; e < self->edges.size(); ++e) {
+            for (size_t e = 0; e < self->ba_edges.size(); ++e) {
                 if (lvl[e]) continue;
-                if (self->edges[e].mono) self->edges[e].mono->computeError(); else self->edges[e].stereo->computeError();
+                if (self->ba_edges[e].mono) self->ba_edges[e].mono->computeError(); else self->ba_edges[e].stereo->computeError();
             }
         }
     };
@@ -149,7 +166,8 @@ public:
     static void h_discard(void* c) { Run* r = (Run*)c; r->self->be->steps.discard_top(r->session); }
 };
 
-int SparseOptimizer::optimize(int iterations) {
+int SparseOptimizer::optimize_ba(int iterations) {
+    const std::vector<EdgeRef>& edges = ba_edges;
     Run run; run.self = this;
     std::map<HyperGraph::Vertex*, int> pose_index, point_index;
     for (auto& kv : vmap) {      // g2o orders the vertices of the index mapping by id (std::map: ascending)
@@ -219,6 +237,94 @@ int SparseOptimizer::optimize(int iterations) {
     be->close(run.session);
     return it;
 }
+
+// ---- PoseOptimization: one pose vertex (id 0), unary OnlyPose edges
+struct PoseRun {
+    SparseOptimizer* self; void* session; VertexSE3Expmap* pose; std::vector<uint8_t> lvl;
+    void sync() {
+        double s[7];
+        self->be->pose_state(session, s, 7);
+        SE3Quat T = pose->estimate();
+        T.setRotation(Eigen::Quaterniond(s[3], s[0], s[1], s[2]));
+        T.setTranslation(Eigen::Vector3d(s[4], s[5], s[6]));
+        pose->setEstimate(T);
+    }
+    void real_errors() {
+        for (size_t e = 0; e < self->pose_edges.size(); ++e) {
+            if (lvl[e]) continue;
+            if (self->pose_edges[e].mono) self->pose_edges[e].mono->computeError(); else self->pose_edges[e].stereo->computeError();
+        }
+    }
+    static void h_compute(void* c) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.compute_errors(r->session); r->real_errors(); }
+    static double h_chi2(void* c) { PoseRun* r = (PoseRun*)c; return r->self->be->pose_steps.chi2(r->session); }
+    static void h_build(void* c) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.build(r->session); }
+    static int h_layout(void* c, int32_t* d, int n) { PoseRun* r = (PoseRun*)c; return r->self->be->pose_steps.layout(r->session, d, n); }
+    static int h_vectors(void* c, double* x, double* b, double* dg, int n) { PoseRun* r = (PoseRun*)c; return r->self->be->pose_steps.vectors(r->session, x, b, dg, n); }
+    static void h_lambda(void* c, double l) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.set_lambda(r->session, l); }
+    static int h_solve(void* c) { PoseRun* r = (PoseRun*)c; return r->self->be->pose_steps.solve(r->session); }
+    static void h_update(void* c) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.update(r->session); r->sync(); }
+    static void h_push(void* c) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.push(r->session); }
+    static void h_pop(void* c) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.pop(r->session); r->sync(); }
+    static void h_discard(void* c) { PoseRun* r = (PoseRun*)c; r->self->be->pose_steps.discard_top(r->session); }
+};
+
+int SparseOptimizer::optimize_pose(int iterations) {
+    PoseRun run; run.self = this;
+    run.pose = dynamic_cast<VertexSE3Expmap*>(vertex(0));
+    const int n = (int)pose_edges.size();
+    std::vector<float> xw(3 * n), obs(3 * n), w(n);
+    std::vector<uint8_t> outl(std::max(n, 1), 0);
+    run.lvl.assign(n, 0);
+    adb_pose_problem P{};
+    int n_active = 0, n_kernel = 0;
+    for (int e = 0; e < n; ++e) {
+        const PoseEdgeRef& r = pose_edges[e];
+        if (r.mono) {
+            for (int k = 0; k < 3; ++k) xw[3 * e + k] = (float)r.mono->Xw[k];
+            obs[3 * e] = (float)r.mono->measurement()[0]; obs[3 * e + 1] = (float)r.mono->measurement()[1]; obs[3 * e + 2] = -1.f;
+            w[e] = (float)r.mono->information()(0, 0);
+            P.fx = r.mono->fx; P.fy = r.mono->fy; P.cx = r.mono->cx; P.cy = r.mono->cy;
+        } else {
+            for (int k = 0; k < 3; ++k) { xw[3 * e + k] = (float)r.stereo->Xw[k]; obs[3 * e + k] = (float)r.stereo->measurement()[k]; }
+            w[e] = (float)r.stereo->information()(0, 0);
+            P.fx = r.stereo->fx; P.fy = r.stereo->fy; P.cx = r.stereo->cx; P.cy = r.stereo->cy; P.bf = r.stereo->bf;
+        }
+        const int level = r.mono ? r.mono->level() : r.stereo->level();
+        RobustKernel* k = r.mono ? r.mono->robustKernel() : r.stereo->robustKernel();
+        run.lvl[e] = level != active_level;
+        if (!run.lvl[e]) { ++n_active; n_kernel += k != nullptr; }
+    }
+    if (n_kernel != 0 && n_kernel != n_active) return -2;
+    if (rec) {
+        if (rec->round_active.empty()) { rec->xw = xw; rec->obs = obs; rec->inv_sigma2 = w; rec->cam[0] = P.fx; rec->cam[1] = P.fy; rec->cam[2] = P.cx; rec->cam[3] = P.cy; rec->cam[4] = P.bf; }
+        rec->round_active.push_back(n_active);
+    }
+    if (n_active == 0) {         // initializeOptimization leaves no active vertex: optimize() returns -1 (core/sparse_optimizer.cpp:356-359)
+        if (rec) { rec->round_iterations.push_back(-1); rec->round_robust.push_back(0); }
+        return -1;
+    }
+    const SE3Quat& T = run.pose->estimate();
+    double pq[4] = {T.rotation().x(), T.rotation().y(), T.rotation().z(), T.rotation().w()}, pt[3] = {T.translation()[0], T.translation()[1], T.translation()[2]};
+    if (rec && rec->pose_q.empty()) { rec->pose_q.assign(pq, pq + 4); rec->pose_t.assign(pt, pt + 3); }
+    int32_t fptr[2] = {0, n}, inl = 0;
+    P.n_frames = 1; P.frame_ptr = fptr; P.pose_q = pq; P.pose_t = pt; P.xw = xw.data(); P.obs = obs.data(); P.inv_sigma2 = w.data();
+    P.outlier = outl.data(); P.n_inliers = &inl;
+    run.session = be->pose_open(&P, 0, run.lvl.data(), n_kernel != 0);
+    ref_lm_hooks hk{&run, PoseRun::h_compute, PoseRun::h_chi2, PoseRun::h_build, PoseRun::h_layout, PoseRun::h_vectors, PoseRun::h_lambda, PoseRun::h_solve,
+                    PoseRun::h_update, PoseRun::h_push, PoseRun::h_pop, PoseRun::h_discard};
+    std::vector<double> rows(4 * 512);
+    int n_rows = 0, n_eval = 0; double lam = 0, tau = 0;
+    const int it = be->lm_optimize(&hk, iterations, 10, rows.data(), 512, &n_rows, &lam, &n_eval, &tau);
+    run.sync();
+    if (rec) {
+        rec->rows.insert(rec->rows.end(), rows.begin(), rows.begin() + 4 * (size_t)std::min(n_rows, 512));
+        rec->round_iterations.push_back(it); rec->round_robust.push_back(n_kernel != 0);
+        rec->final_state.resize(7);
+        be->pose_state(run.session, rec->final_state.data(), 7);
+    }
+    be->pose_close(run.session);
+    return it;
+}
 }  // namespace g2o
 
 namespace ORB_SLAM2 {
@@ -255,6 +361,20 @@ public:
     void SetWorldPos(const cv::Mat& p) { pos = p.clone(); }
     void UpdateNormalAndDepth() { ++n_updates; }
     void EraseObservation(KeyFrame*) {}
+    static std::mutex mGlobalMutex;
+};
+std::mutex MapPoint::mGlobalMutex;
+class Frame {                    // include/Frame.h: the members PoseOptimization touches
+public:
+    cv::Mat mTcw;
+    int N = 0;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<float> mvuRight;
+    std::vector<bool> mvbOutlier;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<float> mvInvLevelSigma2;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
+    void SetPose(cv::Mat Tcw) { mTcw = Tcw.clone(); }
 };
 int KeyFrame::erase_seq = 0;
 class Map { public: std::mutex mMutexMapUpdate; };
@@ -286,10 +406,11 @@ namespace g2o {
 using namespace ::g2o;
 struct SparseOptimizer : ::g2o::SparseOptimizer { SparseOptimizer() { be = g_backend; rec = g_record; } };
 }
-using ORB_SLAM2::KeyFrame; using ORB_SLAM2::MapPoint; using ORB_SLAM2::Map; using ORB_SLAM2::Converter;
+using ORB_SLAM2::KeyFrame; using ORB_SLAM2::MapPoint; using ORB_SLAM2::Map; using ORB_SLAM2::Converter; using ORB_SLAM2::Frame;
 class Optimizer {
 public:
     static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap);
+    static int PoseOptimization(Frame* pFrame);
 };
 #include "_ref/lba_snippets.inc"
 }  // namespace lba_scope
@@ -350,6 +471,47 @@ int ref_lba_run(const ref_lba_backend* be, ref_lba_io* io, void** rec_out) {
     return 0;
 }
 
+struct ref_pose_io {
+    const float* tcw;                  /* [16] Frame::mTcw */
+    float fx, fy, cx, cy, bf;
+    int32_t n_levels; const float* inv_level_sigma2;
+    int32_t n; const float* uvr; const int32_t* octave; const float* xw; const uint8_t* has_point;   /* key-points; xw / has_point: mvpMapPoints */
+    uint8_t* outlier;                  /* [n] mvbOutlier after the call */
+    float* tcw_out;                    /* [16] */
+    int32_t n_inliers;                 /* the function's return value */
+};
+// the literal Optimizer::PoseOptimization (src/Optimizer.cc:232-429) on one frame
+int ref_pose_run(const ref_lba_backend* be, ref_pose_io* io, void** rec_out) {
+    using namespace ORB_SLAM2;
+    Frame F;
+    F.mTcw = cv::Mat(4, 4, CV_32F, io->tcw);
+    F.N = io->n; F.fx = io->fx; F.fy = io->fy; F.cx = io->cx; F.cy = io->cy; F.mbf = io->bf;
+    F.mvInvLevelSigma2.assign(io->inv_level_sigma2, io->inv_level_sigma2 + io->n_levels);
+    std::vector<MapPoint> mps(io->n);
+    for (int i = 0; i < io->n; ++i) {
+        cv::KeyPoint kp; kp.pt.x = io->uvr[3 * i]; kp.pt.y = io->uvr[3 * i + 1]; kp.octave = io->octave[i];
+        F.mvKeysUn.push_back(kp); F.mvuRight.push_back(io->uvr[3 * i + 2]); F.mvbOutlier.push_back(true);
+        mps[i].pos = cv::Mat(3, 1, CV_32F, io->xw + 3 * i);
+        F.mvpMapPoints.push_back(io->has_point[i] ? &mps[i] : nullptr);
+    }
+    g2o::LbaRecord* rec = new g2o::LbaRecord;
+    g_backend = be; g_record = rec;
+    io->n_inliers = lba_scope::Optimizer::PoseOptimization(&F);
+    g_backend = nullptr; g_record = nullptr;
+    for (int i = 0; i < io->n; ++i) io->outlier[i] = F.mvbOutlier[i] ? 1 : 0;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) io->tcw_out[4 * i + j] = F.mTcw.at<float>(i, j);
+    *rec_out = rec;
+    return 0;
+}
+// which = 0 xw, 1 obs, 2 inv_sigma2
+int ref_lba_record_f32(void* h, int which, float* out, int cap) {
+    g2o::LbaRecord* r = (g2o::LbaRecord*)h;
+    const std::vector<float>* v[3] = {&r->xw, &r->obs, &r->inv_sigma2};
+    const std::vector<float>& a = *v[which];
+    for (size_t i = 0; i < a.size() && (int)i < cap; ++i) out[i] = a[i];
+    return (int)a.size();
+}
+
 // record accessors: which = 0 pose_q, 1 pose_t, 2 points, 3 edge_obs, 4 edge_info, 5 rows, 6 final_state, 7 cam + huber (7 doubles)
 int ref_lba_record_f64(void* h, int which, double* out, int cap) {
     g2o::LbaRecord* r = (g2o::LbaRecord*)h;
@@ -359,11 +521,11 @@ int ref_lba_record_f64(void* h, int which, double* out, int cap) {
     for (size_t i = 0; i < a.size() && (int)i < cap; ++i) out[i] = a[i];
     return (int)a.size();
 }
-// which = 0 edge_pose, 1 edge_point, 2 pose_id, 3 point_id, 4 round_iterations, 5 round_robust, 6 pose_fixed
+// which = 0 edge_pose, 1 edge_point, 2 pose_id, 3 point_id, 4 round_iterations, 5 round_robust, 6 pose_fixed, 7 round_active
 int ref_lba_record_i32(void* h, int which, int32_t* out, int cap) {
     g2o::LbaRecord* r = (g2o::LbaRecord*)h;
     std::vector<int32_t> fx(r->pose_fixed.begin(), r->pose_fixed.end());
-    const std::vector<int32_t>* v[7] = {&r->edge_pose, &r->edge_point, &r->pose_id, &r->point_id, &r->round_iterations, &r->round_robust, &fx};
+    const std::vector<int32_t>* v[8] = {&r->edge_pose, &r->edge_point, &r->pose_id, &r->point_id, &r->round_iterations, &r->round_robust, &fx, &r->round_active};
     const std::vector<int32_t>& a = *v[which];
     for (size_t i = 0; i < a.size() && (int)i < cap; ++i) out[i] = a[i];
     return (int)a.size();

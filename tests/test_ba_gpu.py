@@ -218,3 +218,32 @@ def test_local_ba_against_the_reference_function(opt):
         assert hits >= n_free, i
         i += 1
     assert i == 5
+
+
+def test_pose_optimization_against_the_reference_function(opt):
+    """adb_pose_optimize against tests/golden/pose_ref.npz = the reference's own Optimizer::PoseOptimization (src/Optimizer.cc:232-429, whole
+    function compiled from /root/reference: oracle/ref_lba.cpp) on the frames that function turned into edges: mvbOutlier and the return
+    value identical, the pose within 1e-9 of the reference run, the written-back float Tcw equal within one float ulp.  All frames of
+    the fixture go through ONE batched call (the kernel's CTA-per-frame layout)."""
+    import importlib.util, os
+    from airdos_b200 import ba
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "pose_ref.npz"))
+    spec = importlib.util.spec_from_file_location("test_ref_pose", os.path.join(root, "tests", "test_ref_pose.py"))
+    helper = importlib.util.module_from_spec(spec); spec.loader.exec_module(helper)
+    items = [(tag, cam, fr) for tag, cam, fr in helper.fixture_frames(gold) if len(fr["pose_q"])]
+    assert len(items) >= 16
+    cam0 = items[0][1]
+    assert all(c == cam0 for _, c, _ in items)
+    pb = opt.PoseOptimization(cam0, [fr for _, _, fr in items])
+    for k, (tag, cam, fr) in enumerate(items):
+        a, b = int(pb.frame_ptr[k]), int(pb.frame_ptr[k + 1])
+        n_edges = len(fr["xw"])
+        assert b - a == n_edges
+        has = np.ones(len(gold[f"{tag}_outlier"]), bool); has[::11] = False      # the generator's null map points (oracle/gen_ref_pose_golden.py)
+        assert (pb.outlier[a:b] == gold[f"{tag}_outlier"][has]).all(), tag
+        assert int(pb.n_inliers[k]) == int(gold[f"{tag}_n_inliers"]), tag
+        st = np.concatenate([pb.pose_q[k], pb.pose_t[k]])
+        assert np.abs(st - gold[f"{tag}_final_state"]).max() < 1e-9, tag
+        T = ba.pose_to_tcw(pb.pose_q[k], pb.pose_t[k])
+        assert np.abs(T - gold[f"{tag}_tcw"]).max() <= 1e-6 * max(1.0, np.abs(gold[f"{tag}_tcw"]).max()), tag
