@@ -542,11 +542,13 @@ class _LbaIO(C.Structure):
                 ("mp_updates", C.c_void_p)]
 
 
-def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict):
+def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict, global_ba=None):
     """Runs the reference's Optimizer::LocalBundleAdjustment (oracle/_ref/libref_lba.so) on window `w` (kf_id, kf_tcw [n,4,4] f32, covisible,
     fx fy cx cy bf, inv_level_sigma2, mp_id, mp_pos [m,3] f32, obs_kf, obs_mp, obs_uvr [o,3] f32, obs_octave; key-frame 0 = pKF), its
     solver steps being the oracle's and its LM control the reference's (libref_lm.so).  Returns the function's outputs and the problem /
-    trial rows the stand-in optimizer recorded (a dict in make_ba_problem layout, usable with ba_solve)."""
+    trial rows the stand-in optimizer recorded (a dict in make_ba_problem layout, usable with ba_solve).
+    global_ba = (nIterations, nLoopKF, bRobust) runs Optimizer::BundleAdjustment (what GlobalBundleAdjustemnt calls) on ALL key-frames and
+    points of `w` instead; with nLoopKF != 0 the outputs are mTcwGBA / mPosGBA and mp_updates holds mnBAGlobalForKF."""
     be = _lba_backend(lm_lib)
     a = lambda k, t: np.ascontiguousarray(w[k], t)
     kf_id, tcw, cov = a("kf_id", np.int32), a("kf_tcw", np.float32), a("covisible", np.int32)
@@ -560,7 +562,11 @@ def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict):
     lba_lib.ref_lba_record_f64.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lba_lib.ref_lba_record_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lba_lib.ref_lba_record_free.argtypes = [C.c_void_p]
-    rc = lba_lib.ref_lba_run(C.byref(be), C.byref(io), C.byref(rec))
+    if global_ba is None:
+        rc = lba_lib.ref_lba_run(C.byref(be), C.byref(io), C.byref(rec))
+    else:
+        lba_lib.ref_gba_run.argtypes = [C.POINTER(_LbaBackend), C.POINTER(_LbaIO), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        rc = lba_lib.ref_gba_run(C.byref(be), C.byref(io), int(global_ba[0]), int(global_ba[1]), int(global_ba[2]), C.byref(rec))
     assert rc == 0
 
     def f64(which):

@@ -52,6 +52,39 @@ def make_window(i):
                 obs_uvr=d["edge_obs"].astype(np.float32), obs_octave=octave)
 
 
+# Optimizer::BundleAdjustment (src/Optimizer.cc:60-230, called by GlobalBundleAdjustemnt :52-58): (window case, nIterations, nLoopKF, bRobust)
+GBA_CASES = [(0, 10, 0, True), (1, 5, 0, False), (2, 20, 7, True), (3, 10, 0, True)]
+
+
+def make_gba_window(j):
+    """The window of case GBA_CASES[j][0] plus one map point nobody observes (the function removes its vertex, :178-180)."""
+    w = make_window(GBA_CASES[j][0])
+    w = dict(w)
+    w["mp_id"] = np.concatenate([w["mp_id"], [int(w["mp_id"].max()) + 5]]).astype(np.int32)
+    w["mp_pos"] = np.concatenate([w["mp_pos"], [[1.0, 2.0, 30.0]]]).astype(np.float32)
+    return w
+
+
+def gba_main(LBA, LM, out):
+    import oracle
+    for j, (c, its, loop_kf, robust) in enumerate(GBA_CASES):
+        w = make_gba_window(j)
+        r = oracle.ref_local_bundle_adjustment(LBA, LM, w, global_ba=(its, loop_kf, robust))
+        o = oracle.ba_global_options(its, robust)
+        p, res, st = oracle.ba_solve(r["problem"], o)
+        fs = np.concatenate([p["pose_q"].ravel(), p["pose_t"].ravel(), p["points"].ravel()])
+        tr = res.trace_rows[:, [0, 1, 2, 4]]
+        print(f"global BA {j}: {len(r['pose_id'])} key-frames ({int(r['problem']['pose_fixed'].sum())} fixed), {len(r['point_id'])} points, "
+              f"{len(r['problem']['edge_pose'])} edges, {its} iterations asked, {list(r['round_iterations'])} run, robust {list(r['round_robust'])}, "
+              f"Huber deltas {r['huber']} (oracle {o.huber_mono, o.huber_stereo}) | oracle: trials identical "
+              f"{tr.shape == r['rows'].shape and bool((tr == r['rows']).all())}, state identical {bool((fs == r['final_state']).all())}")
+        for k in ("kf_tcw", "mp_pos", "mp_updates", "rows", "final_state", "pose_id", "point_id", "round_iterations", "round_robust"):
+            out[f"g{j}_{k}"] = r[k]
+        out[f"g{j}_huber"] = np.array(r["huber"])
+        for k, v in r["problem"].items():
+            out[f"g{j}_p_{k}"] = np.asarray(v)
+
+
 def main():
     import oracle
     oracle.build()
@@ -74,6 +107,7 @@ def main():
         out[f"w{i}_huber"] = np.array(r["huber"])
         for k, v in r["problem"].items():
             out[f"w{i}_p_{k}"] = np.asarray(v)
+    gba_main(LBA, LM, out)
     path = os.path.join(ROOT, "tests", "golden", "lba_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -118,6 +118,7 @@ public:
     void setAlgorithm(OptimizationAlgorithmLevenberg*) {}
     void setForceStopFlag(bool* f) { stop = f; }
     bool addVertex(OptimizableGraph::Vertex* v) { vmap[v->id()] = v; return true; }
+    bool removeVertex(OptimizableGraph::Vertex* v) { vmap.erase(v->id()); return true; }     // a point without edges (src/Optimizer.cc:178-180)
     bool addEdge(EdgeSE3ProjectXYZ* e) { ba_edges.push_back(EdgeRef{e, nullptr}); return true; }
     bool addEdge(EdgeStereoSE3ProjectXYZ* e) { ba_edges.push_back(EdgeRef{nullptr, e}); return true; }
     bool addEdge(EdgeSE3ProjectXYZOnlyPose* e) { pose_edges.push_back(PoseEdgeRef{e, nullptr}); return true; }
@@ -332,7 +333,8 @@ using namespace std;
 class MapPoint;
 class KeyFrame {                 // include/KeyFrame.h: the members LocalBundleAdjustment touches
 public:
-    long unsigned int mnId = 0, mnBALocalForKF = 0, mnBAFixedForKF = 0;
+    long unsigned int mnId = 0, mnBALocalForKF = 0, mnBAFixedForKF = 0, mnBAGlobalForKF = 0;
+    cv::Mat mTcwGBA;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<float> mvuRight;
     std::vector<float> mvInvLevelSigma2;
@@ -351,7 +353,8 @@ public:
 };
 class MapPoint {                 // include/MapPoint.h
 public:
-    long unsigned int mnId = 0, mnBALocalForKF = 0;
+    long unsigned int mnId = 0, mnBALocalForKF = 0, mnBAGlobalForKF = 0;
+    cv::Mat mPosGBA;
     std::map<KeyFrame*, size_t> observations;
     cv::Mat pos;
     int n_updates = 0;
@@ -411,6 +414,8 @@ class Optimizer {
 public:
     static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap);
     static int PoseOptimization(Frame* pFrame);
+    static void BundleAdjustment(const std::vector<KeyFrame*>& vpKFs, const std::vector<MapPoint*>& vpMP, int nIterations, bool* pbStopFlag,
+                                 const unsigned long nLoopKF, const bool bRobust);
 };
 #include "_ref/lba_snippets.inc"
 }  // namespace lba_scope
@@ -433,40 +438,76 @@ struct ref_lba_io {
     int32_t* mp_updates;               /* [n_mp] UpdateNormalAndDepth calls */
 };
 
-// runs the literal function on the window; *rec_out receives a handle for ref_lba_record_* (free with ref_lba_record_free)
+namespace {
+struct Window {
+    std::vector<ORB_SLAM2::KeyFrame> kfs;        // one block: addresses ascend with the index (std::map<KeyFrame*, size_t> iterates by address)
+    std::vector<ORB_SLAM2::MapPoint> mps;
+    explicit Window(const ref_lba_io* io) : kfs(io->n_kf), mps(io->n_mp) {
+        using namespace ORB_SLAM2;
+        for (int k = 0; k < io->n_kf; ++k) {
+            KeyFrame& K = kfs[k];
+            K.mnId = io->kf_id[k]; K.mnBALocalForKF = K.mnBAFixedForKF = (unsigned long)-1;
+            K.fx = io->fx; K.fy = io->fy; K.cx = io->cx; K.cy = io->cy; K.mbf = io->bf;
+            K.mvInvLevelSigma2.assign(io->inv_level_sigma2, io->inv_level_sigma2 + io->n_levels);
+            K.Tcw = cv::Mat(4, 4, CV_32F, io->kf_tcw + 16 * k);
+        }
+        for (int i = 0; i < io->n_covisible; ++i) kfs[0].covisible.push_back(&kfs[io->covisible[i]]);
+        for (int m = 0; m < io->n_mp; ++m) { mps[m].mnId = io->mp_id[m]; mps[m].mnBALocalForKF = (unsigned long)-1; mps[m].pos = cv::Mat(3, 1, CV_32F, io->mp_pos + 3 * m); }
+        for (int o = 0; o < io->n_obs; ++o) {
+            KeyFrame& K = kfs[io->obs_kf[o]];
+            cv::KeyPoint kp; kp.pt.x = io->obs_uvr[3 * o]; kp.pt.y = io->obs_uvr[3 * o + 1]; kp.octave = io->obs_octave[o];
+            const size_t idx = K.mvKeysUn.size();
+            K.mvKeysUn.push_back(kp); K.mvuRight.push_back(io->obs_uvr[3 * o + 2]); K.matches.push_back(&mps[io->obs_mp[o]]);
+            mps[io->obs_mp[o]].observations[&K] = idx;
+        }
+    }
+    void results(ref_lba_io* io, bool gba) {
+        for (int k = 0; k < io->n_kf; ++k) {
+            const cv::Mat& T = gba ? kfs[k].mTcwGBA : kfs[k].Tcw;
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) io->kf_tcw_out[16 * k + 4 * i + j] = T.empty() ? 0.f : T.at<float>(i, j);
+        }
+        for (int m = 0; m < io->n_mp; ++m) {
+            const cv::Mat& X = gba ? mps[m].mPosGBA : mps[m].pos;
+            for (int i = 0; i < 3; ++i) io->mp_pos_out[3 * m + i] = X.empty() ? 0.f : X.at<float>(i);
+            io->mp_updates[m] = gba ? (int)mps[m].mnBAGlobalForKF : mps[m].n_updates;
+        }
+        // the erase list in the function's own order (vToErase: mono edges first, then stereo, :672-700)
+        std::vector<std::pair<int, std::pair<int, int>>> er;
+        for (int k = 0; k < io->n_kf; ++k) for (auto& p : kfs[k].erased) er.push_back({p.first, {k, (int)(p.second - mps.data())}});
+        std::sort(er.begin(), er.end());
+        io->n_erased = (int)er.size();
+        for (int i = 0; i < io->n_erased && i < io->erased_cap; ++i) { io->erased[2 * i] = er[i].second.first; io->erased[2 * i + 1] = er[i].second.second; }
+    }
+};
+}  // namespace
+
+// runs the literal Optimizer::LocalBundleAdjustment on the window; *rec_out receives a handle for ref_lba_record_* (free with ref_lba_record_free)
 int ref_lba_run(const ref_lba_backend* be, ref_lba_io* io, void** rec_out) {
     using namespace ORB_SLAM2;
-    std::vector<KeyFrame> kfs(io->n_kf);          // one block: addresses ascend with the index (std::map<KeyFrame*, size_t> iterates by address)
-    std::vector<MapPoint> mps(io->n_mp);
-    for (int k = 0; k < io->n_kf; ++k) {
-        KeyFrame& K = kfs[k];
-        K.mnId = io->kf_id[k]; K.mnBALocalForKF = K.mnBAFixedForKF = (unsigned long)-1;
-        K.fx = io->fx; K.fy = io->fy; K.cx = io->cx; K.cy = io->cy; K.mbf = io->bf;
-        K.mvInvLevelSigma2.assign(io->inv_level_sigma2, io->inv_level_sigma2 + io->n_levels);
-        K.Tcw = cv::Mat(4, 4, CV_32F, io->kf_tcw + 16 * k);
-    }
-    for (int i = 0; i < io->n_covisible; ++i) kfs[0].covisible.push_back(&kfs[io->covisible[i]]);
-    for (int m = 0; m < io->n_mp; ++m) { mps[m].mnId = io->mp_id[m]; mps[m].mnBALocalForKF = (unsigned long)-1; mps[m].pos = cv::Mat(3, 1, CV_32F, io->mp_pos + 3 * m); }
-    for (int o = 0; o < io->n_obs; ++o) {
-        KeyFrame& K = kfs[io->obs_kf[o]];
-        cv::KeyPoint kp; kp.pt.x = io->obs_uvr[3 * o]; kp.pt.y = io->obs_uvr[3 * o + 1]; kp.octave = io->obs_octave[o];
-        const size_t idx = K.mvKeysUn.size();
-        K.mvKeysUn.push_back(kp); K.mvuRight.push_back(io->obs_uvr[3 * o + 2]); K.matches.push_back(&mps[io->obs_mp[o]]);
-        mps[io->obs_mp[o]].observations[&K] = idx;
-    }
+    Window W(io);
     g2o::LbaRecord* rec = new g2o::LbaRecord;
     g_backend = be; g_record = rec; KeyFrame::erase_seq = 0;
     Map map;
-    lba_scope::Optimizer::LocalBundleAdjustment(&kfs[0], nullptr, &map);
+    lba_scope::Optimizer::LocalBundleAdjustment(&W.kfs[0], nullptr, &map);
     g_backend = nullptr; g_record = nullptr;
-    for (int k = 0; k < io->n_kf; ++k) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) io->kf_tcw_out[16 * k + 4 * i + j] = kfs[k].Tcw.at<float>(i, j);
-    for (int m = 0; m < io->n_mp; ++m) { for (int i = 0; i < 3; ++i) io->mp_pos_out[3 * m + i] = mps[m].pos.at<float>(i); io->mp_updates[m] = mps[m].n_updates; }
-    // the erase list in the function's own order (vToErase: mono edges first, then stereo, :672-700)
-    std::vector<std::pair<int, std::pair<int, int>>> er;
-    for (int k = 0; k < io->n_kf; ++k) for (auto& p : kfs[k].erased) er.push_back({p.first, {k, (int)(p.second - mps.data())}});
-    std::sort(er.begin(), er.end());
-    io->n_erased = (int)er.size();
-    for (int i = 0; i < io->n_erased && i < io->erased_cap; ++i) { io->erased[2 * i] = er[i].second.first; io->erased[2 * i + 1] = er[i].second.second; }
+    W.results(io, false);
+    *rec_out = rec;
+    return 0;
+}
+// the literal Optimizer::BundleAdjustment (src/Optimizer.cc:60-230; what GlobalBundleAdjustemnt :52-58 calls) on all key-frames / points of
+// the window: nLoopKF == 0 writes poses / positions back, otherwise into mTcwGBA / mPosGBA with mnBAGlobalForKF = nLoopKF (mp_updates then
+// returns mnBAGlobalForKF per point)
+int ref_gba_run(const ref_lba_backend* be, ref_lba_io* io, int n_iterations, int n_loop_kf, int robust, void** rec_out) {
+    using namespace ORB_SLAM2;
+    Window W(io);
+    g2o::LbaRecord* rec = new g2o::LbaRecord;
+    g_backend = be; g_record = rec; KeyFrame::erase_seq = 0;
+    std::vector<KeyFrame*> vk; std::vector<MapPoint*> vm;
+    for (auto& k : W.kfs) vk.push_back(&k);
+    for (auto& m : W.mps) vm.push_back(&m);
+    lba_scope::Optimizer::BundleAdjustment(vk, vm, n_iterations, nullptr, (unsigned long)n_loop_kf, robust != 0);
+    g_backend = nullptr; g_record = nullptr;
+    W.results(io, n_loop_kf != 0);
     *rec_out = rec;
     return 0;
 }

@@ -52,6 +52,7 @@ public:
         return m;
     }
     int type() const { return type_; }
+    void copyTo(Mat& dst) const { dst = clone(); }
     bool empty() const { return rows == 0 || cols == 0; }
     Mat row(int i) const { return rowRange(i, i + 1); }
     Mat rowRange(int a, int b) const { Mat m = *this; m.off_ += (size_t)a * step_; m.rows = b - a; return m; }
@@ -83,12 +84,12 @@ public:
             for (int j = 0; j < cols; ++j) out.at<float>(i, j) = type_ == CV_32F ? at<float>(i, j) : (float)at<unsigned char>(i, j);
         dst = out;
     }
-private:
-    size_t esz() const { return type_ == CV_32F ? 4 : 1; }
     void create(int r, int c, int type) {
         rows = r; cols = c; type_ = type; step_ = (size_t)c * esz(); off_ = 0; step = step_;
         buf_ = std::make_shared<std::vector<unsigned char>>((size_t)r * step_);
     }
+private:
+    size_t esz() const { return type_ == CV_32F ? 4 : 1; }
     std::shared_ptr<std::vector<unsigned char>> buf_;
     size_t off_ = 0, step_ = 0;
     int type_ = CV_8U;

@@ -247,3 +247,24 @@ def test_pose_optimization_against_the_reference_function(opt):
         assert np.abs(st - gold[f"{tag}_final_state"]).max() < 1e-9, tag
         T = ba.pose_to_tcw(pb.pose_q[k], pb.pose_t[k])
         assert np.abs(T - gold[f"{tag}_tcw"]).max() <= 1e-6 * max(1.0, np.abs(gold[f"{tag}_tcw"]).max()), tag
+
+
+def test_global_ba_against_the_reference_function(opt):
+    """Optimizer.GlobalBundleAdjustemnt (adb_ba_solve with adb_ba_global_options) against the reference's own Optimizer::BundleAdjustment
+    (src/Optimizer.cc:60-230, compiled from /root/reference; tests/golden/lba_ref.npz, g-cases): robust and plain, 5 / 10 / 20 iterations,
+    a window without any fixed key-frame: same accept / reject decisions, lambda and chi2 within 1e-6, final state within 1e-8."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "lba_ref.npz"))
+    spec = importlib.util.spec_from_file_location("gen_ref_lba_golden", os.path.join(root, "oracle", "gen_ref_lba_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    for j, (c, its, loop_kf, robust) in enumerate(g.GBA_CASES):
+        prob = {k[len(f"g{j}_p_"):]: (gold[k].item() if gold[k].ndim == 0 else gold[k]) for k in gold.files if k.startswith(f"g{j}_p_")}
+        pg, rg, sg = opt.GlobalBundleAdjustemnt(prob, its, None, robust)
+        assert sg == 0
+        rows = gold[f"g{j}_rows"]
+        tg = rg.trace_rows
+        assert len(tg) == len(rows) and (tg[:, 4] == rows[:, 3]).all(), j
+        assert np.allclose(tg[:, :3], rows[:, :3], rtol=1e-6), j
+        state = np.concatenate([pg["pose_q"].ravel(), pg["pose_t"].ravel(), pg["points"].ravel()])
+        assert np.abs(state - gold[f"g{j}_final_state"]).max() < 1e-8, j

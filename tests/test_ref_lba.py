@@ -124,3 +124,43 @@ def test_fixture_is_what_the_reference_library_computes_now(oracle_mod):
         r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, g.make_window(i))
         for k in ("kf_tcw", "mp_pos", "erased", "rows", "final_state"):
             assert (r[k] == gold[f"w{i}_{k}"]).all(), (i, k)
+
+
+def gba_problem(gold, j):
+    return {k[len(f"g{j}_p_"):]: (gold[k].item() if gold[k].ndim == 0 else gold[k]) for k in gold.files if k.startswith(f"g{j}_p_")}
+
+
+def test_oracle_global_ba_equals_the_reference_function(oracle_mod):
+    """Optimizer::BundleAdjustment (src/Optimizer.cc:60-230, what GlobalBundleAdjustemnt calls), the whole function compiled from
+    /root/reference: one round of nIterations with thHuber2D = sqrt(5.99) (not 5.991) / thHuber3D = sqrt(7.815) or no kernel, all key-frames,
+    mnId 0 fixed, unobserved points removed.  ba_oracle_solve with ba_global_options on the problem it built: trials and final state
+    bit for bit; results land in the poses (nLoopKF == 0) or in mTcwGBA / mPosGBA with mnBAGlobalForKF = nLoopKF."""
+    import ctypes as C
+    gold = np.load(GOLD)
+    g = _gen()
+    lib = oracle_mod.ba_lib()
+    lib.ba_oracle_pose_to_tcw.argtypes = [C.c_void_p] * 3
+    for j, (c, its, loop_kf, robust) in enumerate(g.GBA_CASES):
+        w = g.make_gba_window(j)
+        prob = gba_problem(gold, j)
+        o = oracle_mod.ba_global_options(its, robust)
+        if robust:
+            assert (o.huber_mono, o.huber_stereo) == tuple(gold[f"g{j}_huber"])
+            assert o.huber_mono == float(np.float32(np.sqrt(5.99)))
+        p, res, st = oracle_mod.ba_solve(prob, o)
+        assert st == 0 and [res.c.iterations_run[0]] == list(gold[f"g{j}_round_iterations"]) and res.c.iterations_run[1] == 0
+        assert list(gold[f"g{j}_round_robust"]) == [int(robust)]
+        tr = res.trace_rows[:, [0, 1, 2, 4]]
+        assert tr.shape == gold[f"g{j}_rows"].shape and (tr == gold[f"g{j}_rows"]).all(), j
+        assert (np.concatenate([p["pose_q"].ravel(), p["pose_t"].ravel(), p["points"].ravel()]) == gold[f"g{j}_final_state"]).all(), j
+        # every key-frame is a vertex, only mnId 0 is fixed; the unobserved point is not in the problem
+        assert len(gold[f"g{j}_pose_id"]) == len(w["kf_id"]) and (prob["pose_fixed"].astype(bool) == (gold[f"g{j}_pose_id"] == 0)).all()
+        assert len(gold[f"g{j}_point_id"]) == len(w["mp_id"]) - 1
+        kf_of = {int(v): k for k, v in enumerate(w["kf_id"])}
+        for i, vid in enumerate(gold[f"g{j}_pose_id"]):
+            T = np.zeros(16, np.float32)
+            q = np.ascontiguousarray(p["pose_q"][i]); t = np.ascontiguousarray(p["pose_t"][i])
+            lib.ba_oracle_pose_to_tcw(q.ctypes.data, t.ctypes.data, T.ctypes.data)
+            assert (T.reshape(4, 4) == gold[f"g{j}_kf_tcw"][kf_of[int(vid)]]).all(), (j, i)
+        upd = gold[f"g{j}_mp_updates"]
+        assert (upd[:-1] == (loop_kf if loop_kf else 1)).all() and upd[-1] == 0          # mnBAGlobalForKF / UpdateNormalAndDepth; removed point untouched
