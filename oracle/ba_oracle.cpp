@@ -13,13 +13,21 @@
 //   VertexSE3 / VertexDistanceDouble / EdgeRigidBodyDouble / LandmarkMotionTernaryEdge
 //                                                            include/g2o_vertex_se3.h, g2o_vertex_distance.h,
 //                                                            g2o_edge_rigidbody.h, g2o_dyn_slam3d.h
-// Parity pinning: the reference ships no tests or golden vectors for BA and cannot be compiled here
-// (needs Eigen).  The restatement is pinned instead by (a) finite-difference checks of every
-// Jacobian, (b) an independent numpy normal-equation solve of the same linearised system and
-// (c) convergence to the known optimum of noise-free problems (tests/test_oracle_ba.py).  The
-// iteration-exact lambda / chi2 trace is therefore "parity unpinned" against the literal
-// reference: the reduced system is solved by a dense Cholesky instead of Eigen's
-// SimplicialLDLT / LDLT, which agrees to rounding.
+// Parity pinning.  The reference ships no tests or golden vectors for BA; it is pinned by the reference's own
+// functions compiled here from /root/reference against stand-ins (Eigen / OpenCV proper are absent):
+//   leaf arithmetic      g2o / AirDOS type sources unmodified (oracle/ref_leaf.cpp)            -> tests/golden/ba_leaf_ref.npz, 1e-12
+//   LM control           optimization_algorithm_levenberg.cpp whole + SparseOptimizer::optimize (oracle/ref_lm.cpp), run over the steps of
+//                        Solver / PoseSolver below through function pointers                   -> lm_ref.npz: trials, lambda, state bit for bit
+//   Huber kernel         RobustKernelHuber::setDelta / robustify (float dsqr member)           -> lm_ref.npz, bit for bit
+//   quadratic form       BaseBinaryEdge / BaseUnaryEdge::constructQuadraticForm                -> lm_ref.npz, 1e-12
+//   schedules and gates  Optimizer::LocalBundleAdjustment, ::BundleAdjustment, ::PoseOptimization whole, with the reference's edge types,
+//                        Converter and LM control over this file's solver steps (oracle/ref_lba.cpp) -> lba_ref.npz, pose_ref.npz: every
+//                        trial, final state, erase list / mvbOutlier / return value bit for bit
+// What stays "parity unpinned" against the literal reference: BlockSolver::buildSystem / solve (the Schur complement and the order of
+// its sums) and the linear solvers -- they need Eigen proper; the reduced system is solved by a dense Cholesky instead of Eigen's
+// SimplicialLDLT / LDLT, which agrees to rounding -- and LocalBundleAdjustmentHumanTrajactory's schedule (its rigidity / motion Jacobians
+// are undefined in the reference, D.4 / D.6).  Those are pinned mathematically: finite-difference Jacobians, an independent numpy
+// normal-equation solve and an independent numpy LM trajectory (tests/test_oracle_ba.py).
 // Conventions for the reference's ill-defined corners: D.4 analytic
 // rigidity Jacobian, D.5 motion prior = identity (the caller passes it), D.6 d(error)/d(motion
 // translation) = delta_t * I with a zero rotation block.
