@@ -529,7 +529,7 @@ def huber(delta: float, e2: float, lib=None):
 # oracle/ref_lba.cpp: the reference's Optimizer::LocalBundleAdjustment over the oracle's solver session
 class _LbaBackend(C.Structure):
     _fields_ = ([("steps", LmHooks)] + [(n, C.c_void_p) for n in ("open", "close", "set_levels", "state", "lm_optimize", "default_options")] +
-                [("pose_steps", LmHooks)] + [(n, C.c_void_p) for n in ("pose_open", "pose_close", "pose_state")])
+                [("pose_steps", LmHooks)] + [(n, C.c_void_p) for n in ("pose_open", "pose_close", "pose_state", "set_levels4")])
 
 
 class _LbaIO(C.Structure):
@@ -542,7 +542,19 @@ class _LbaIO(C.Structure):
                 ("mp_updates", C.c_void_p)]
 
 
-def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict, global_ba=None):
+class _HumanIO(C.Structure):
+    _fields_ = [("n_traj", C.c_int32), ("traj_id", C.c_void_p), ("traj_track_id", C.c_void_p), ("traj_n_poses", C.c_void_p),
+                ("rigid_id", C.c_void_p), ("rigid_dist", C.c_void_p),
+                ("n_hp", C.c_int32), ("hp_id", C.c_void_p), ("hp_traj", C.c_void_p), ("hp_ref_kf", C.c_void_p), ("hp_time", C.c_void_p),
+                ("key_id", C.c_void_p), ("key_pos", C.c_void_p), ("key_uvr", C.c_void_p),
+                ("n_current", C.c_int32), ("current_hp", C.c_void_p),
+                ("sigma_static", C.c_float), ("sigma_human", C.c_float), ("sigma_rigidity", C.c_float), ("sigma_motion", C.c_float),
+                ("th_motion", C.c_float), ("th_rigidity", C.c_float),
+                ("key_pos_out", C.c_void_p), ("key_flags", C.c_void_p), ("pair_flags", C.c_void_p), ("traj_out", C.c_void_p), ("traj_motion", C.c_void_p),
+                ("n_optimized_tracks", C.c_int32)]
+
+
+def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict, global_ba=None, humans: dict | None = None):
     """Runs the reference's Optimizer::LocalBundleAdjustment (oracle/_ref/libref_lba.so) on window `w` (kf_id, kf_tcw [n,4,4] f32, covisible,
     fx fy cx cy bf, inv_level_sigma2, mp_id, mp_pos [m,3] f32, obs_kf, obs_mp, obs_uvr [o,3] f32, obs_octave; key-frame 0 = pKF), its
     solver steps being the oracle's and its LM control the reference's (libref_lm.so).  Returns the function's outputs and the problem /
@@ -562,7 +574,23 @@ def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict, global_ba=None):
     lba_lib.ref_lba_record_f64.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lba_lib.ref_lba_record_i32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lba_lib.ref_lba_record_free.argtypes = [C.c_void_p]
-    if global_ba is None:
+    hout = None
+    if humans is not None:
+        hh = {k: np.ascontiguousarray(humans[k], t) for k, t in (("traj_id", np.int32), ("traj_track_id", np.int32), ("traj_n_poses", np.int32),
+              ("rigid_id", np.int32), ("rigid_dist", np.float32), ("hp_id", np.int32), ("hp_traj", np.int32), ("hp_ref_kf", np.int32), ("hp_time", np.float64),
+              ("key_id", np.int32), ("key_pos", np.float32), ("key_uvr", np.float32), ("current_hp", np.int32))}
+        nt, nh = len(hh["traj_id"]), len(hh["hp_id"])
+        hout = dict(key_pos=np.zeros((nh, 14, 3), np.float32), key_flags=np.zeros((nh, 14, 5), np.uint8), pair_flags=np.zeros((nh, 14, 2), np.uint8),
+                    traj_out=np.zeros((nt, 2), np.int32), traj_motion=np.zeros((nt, 4, 4), np.float32))
+        hio = _HumanIO(nt, _p(hh["traj_id"]), _p(hh["traj_track_id"]), _p(hh["traj_n_poses"]), _p(hh["rigid_id"]), _p(hh["rigid_dist"]),
+                       nh, _p(hh["hp_id"]), _p(hh["hp_traj"]), _p(hh["hp_ref_kf"]), _p(hh["hp_time"]), _p(hh["key_id"]), _p(hh["key_pos"]), _p(hh["key_uvr"]),
+                       len(hh["current_hp"]), _p(hh["current_hp"]), 1.0, humans["sigma_human"], humans["sigma_rigidity"], humans["sigma_motion"],
+                       humans["th_motion"], humans["th_rigidity"], _p(hout["key_pos"]), _p(hout["key_flags"]), _p(hout["pair_flags"]), _p(hout["traj_out"]),
+                       _p(hout["traj_motion"]), 0)
+        lba_lib.ref_hba_run.argtypes = [C.POINTER(_LbaBackend), C.POINTER(_LbaIO), C.POINTER(_HumanIO), C.POINTER(C.c_void_p)]
+        rc = lba_lib.ref_hba_run(C.byref(be), C.byref(io), C.byref(hio), C.byref(rec))
+        hout["n_optimized_tracks"] = hio.n_optimized_tracks
+    elif global_ba is None:
         rc = lba_lib.ref_lba_run(C.byref(be), C.byref(io), C.byref(rec))
     else:
         lba_lib.ref_gba_run.argtypes = [C.POINTER(_LbaBackend), C.POINTER(_LbaIO), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -581,6 +609,23 @@ def ref_local_bundle_adjustment(lba_lib, lm_lib, w: dict, global_ba=None):
                 pose_fixed=i32(6).astype(np.uint8))
     out = dict(kf_tcw=tcw_out, mp_pos=pos_out, erased=erased[:io.n_erased].copy(), mp_updates=upd, problem=prob, rows=f64(5).reshape(-1, 4),
                final_state=f64(6), pose_id=i32(2), point_id=i32(3), round_iterations=i32(4), round_robust=i32(5), huber=(cam[5], cam[6]))
+    if humans is not None:
+        lba_lib.ref_lba_record_named.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
+
+        def named(name, dt=np.float64):
+            m = lba_lib.ref_lba_record_named(rec, name.encode(), None, 0)
+            v = np.zeros(max(m, 0)); lba_lib.ref_lba_record_named(rec, name.encode(), _p(v), len(v))
+            return v.astype(dt)
+
+        for k in ("joints", "dists", "motion_q", "motion_t", "jedge_obs", "jedge_info", "redge_info", "medge_dt", "medge_info"):
+            prob[k] = named(k)
+        for k in ("jedge_pose", "jedge_joint", "redge_i", "redge_j", "redge_dist", "medge_p1", "medge_p2", "medge_motion"):
+            prob[k] = named(k, np.int32)
+        prob["joints"] = prob["joints"].reshape(-1, 3); prob["motion_q"] = prob["motion_q"].reshape(-1, 4); prob["motion_t"] = prob["motion_t"].reshape(-1, 3)
+        prob["jedge_obs"] = prob["jedge_obs"].reshape(-1, 3)
+        out.update(humans=hout, joint_id=named("joint_id", np.int32), dist_id=named("dist_id", np.int32), motion_id=named("motion_id", np.int32),
+                   edge_kind=named("edge_kind", np.int32), edge_final_chi2=named("edge_final_chi2"), edge_final_depth_positive=named("edge_final_depth_positive", np.int32),
+                   huber_rigid=float(named("huber_rigid")[0]), huber_motion=float(named("huber_motion")[0]))
     lba_lib.ref_lba_record_free(rec)
     return out
 
@@ -600,7 +645,8 @@ def _lba_backend(lm_lib):
     be.pose_steps = LmHooks(None, *[C.cast(getattr(lib, "ba_oracle_pose_lm_" + n), C.c_void_p) for n in _LM_HOOKS])
     for n, f in (("open", lib.ba_oracle_lm_open), ("close", lib.ba_oracle_lm_close), ("set_levels", lib.ba_oracle_lm_set_levels),
                  ("state", lib.ba_oracle_lm_state), ("lm_optimize", lm_lib.ref_lm_optimize), ("default_options", lib.ba_oracle_default_options),
-                 ("pose_open", lib.ba_oracle_pose_lm_open), ("pose_close", lib.ba_oracle_pose_lm_close), ("pose_state", lib.ba_oracle_pose_lm_state)):
+                 ("pose_open", lib.ba_oracle_pose_lm_open), ("pose_close", lib.ba_oracle_pose_lm_close), ("pose_state", lib.ba_oracle_pose_lm_state),
+                 ("set_levels4", lib.ba_oracle_lm_set_levels4)):
         setattr(be, n, C.cast(f, C.c_void_p))
     return be
 

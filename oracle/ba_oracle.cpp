@@ -783,6 +783,15 @@ struct LmSession {
     double chi = 0;
     LmSession(adb_ba_problem& p, const adb_ba_options& o) : S(p, o) {}
 };
+// the same for all four edge kinds (any pointer may be NULL = all active)
+void ba_oracle_lm_set_levels4(void* h, const uint8_t* lvl_e, const uint8_t* lvl_j, const uint8_t* lvl_r, const uint8_t* lvl_m) {
+    Solver& S = ((LmSession*)h)->S;
+    for (int e = 0; e < S.P.n_edges; ++e) S.lvl_e[e] = lvl_e ? lvl_e[e] : 0;
+    for (int e = 0; e < S.P.n_joint_edges; ++e) S.lvl_j[e] = lvl_j ? lvl_j[e] : 0;
+    for (int e = 0; e < S.P.n_rigid_edges; ++e) S.lvl_r[e] = lvl_r ? lvl_r[e] : 0;
+    for (int e = 0; e < S.P.n_motion_edges; ++e) S.lvl_m[e] = lvl_m ? lvl_m[e] : 0;
+    S.build_layout();
+}
 void* ba_oracle_lm_open(adb_ba_problem* prob, const adb_ba_options* opt, int robust) {
     LmSession* h = new LmSession(*prob, *opt);
     h->S.robust = robust != 0;

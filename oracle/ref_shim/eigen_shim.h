@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstddef>
 #include <iostream>
+#include <vector>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 
@@ -157,6 +158,26 @@ template <typename S, int R, int C, int Opt> Matrix<S, R, C, Opt> Matrix<S, R, C
     return o;
 }
 
+// run-time sized matrix: only what Optimizer.cc does with its `Eigen::MatrixXd Info` objects (Identity, element access, scaling, and the
+// conversion to the fixed-size information matrix of the edge it is handed to)
+class MatrixXd {
+    std::vector<double> v_; int r_ = 0, c_ = 0;
+public:
+    MatrixXd() {}
+    MatrixXd(int r, int c) : v_((size_t)r * c, 0.0), r_(r), c_(c) {}
+    static MatrixXd Identity(int r, int c) { MatrixXd m(r, c); for (int i = 0; i < (r < c ? r : c); ++i) m(i, i) = 1.0; return m; }
+    int rows() const { return r_; }
+    int cols() const { return c_; }
+    double& operator()(int r, int c) { return v_[(size_t)c * r_ + r]; }
+    double operator()(int r, int c) const { return v_[(size_t)c * r_ + r]; }
+    template <int R, int C, int O> operator Matrix<double, R, C, O>() const {
+        assert(R == r_ && C == c_);
+        Matrix<double, R, C, O> m; for (int r = 0; r < R; ++r) for (int c = 0; c < C; ++c) m(r, c) = (*this)(r, c); return m;
+    }
+};
+inline MatrixXd operator*(double k, const MatrixXd& m) { MatrixXd o(m.rows(), m.cols()); for (int r = 0; r < m.rows(); ++r) for (int c = 0; c < m.cols(); ++c) o(r, c) = k * m(r, c); return o; }
+inline MatrixXd operator*(const MatrixXd& m, double k) { return k * m; }
+
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 4, 1> Vector4d;
@@ -259,6 +280,7 @@ public:
     typedef Matrix<S, 3, 3> ConstLinearPart;
     Transform() { m_.setIdentity(); }
     explicit Transform(const Quaternion<S>& q) { m_.setIdentity(); *this = q.toRotationMatrix(); }
+    explicit Transform(const Matrix<S, 4, 4>& m) : m_(m) {}
     static Transform Identity() { return Transform(); }
     Transform& operator=(const Matrix<S, 3, 3>& r) {   // Transform = linear part: translation zero, last row (0 0 0 1)
         m_.setIdentity();

@@ -270,3 +270,30 @@ def test_global_ba_against_the_reference_function(opt):
         state = np.concatenate([pg["pose_q"].ravel(), pg["pose_t"].ravel(), pg["points"].ravel()])
         tol = 1e-7 if prob["pose_fixed"].any() else 1e-5
         assert np.abs(state - gold[f"g{j}_final_state"]).max() < tol, (j, float(np.abs(state - gold[f"g{j}_final_state"]).max()))
+
+
+def test_dynamic_ba_against_the_reference_function(opt):
+    """adb_ba_solve on the articulated windows of tests/golden/lba_ref.npz (h-cases) = the reference's own
+    Optimizer::LocalBundleAdjustmentHumanTrajactory (src/Optimizer.cc:1496-2222, compiled from /root/reference: oracle/ref_lba.cpp) over the
+    AirDOS edge types: all four outlier sets identical, the same accept / reject sequence, lambda / chi2 within 1e-6, estimates within
+    1e-7 (joints / bone lengths / motions included)."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "lba_ref.npz"))
+    spec = importlib.util.spec_from_file_location("gen_ref_lba_golden", os.path.join(root, "oracle", "gen_ref_lba_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    for c in range(len(g.HBA_CASES)):
+        prob = {k[len(f"h{c}_p_"):]: (gold[k].item() if gold[k].ndim == 0 else gold[k]) for k in gold.files if k.startswith(f"h{c}_p_")}
+        pg, rg, sg = opt.LocalBundleAdjustmentHumanTrajactory(prob)
+        assert sg == 0
+        rows = gold[f"h{c}_rows"]
+        tg = rg.trace_rows
+        assert len(tg) == len(rows) and (tg[:, 4] == rows[:, 3]).all(), c
+        assert np.allclose(tg[:, :3], rows[:, :3], rtol=1e-6), c
+        state = np.concatenate([np.asarray(pg[k]).ravel() for k in ("pose_q", "pose_t", "points", "joints", "dists", "motion_q", "motion_t")])
+        assert np.abs(state - gold[f"h{c}_final_state"]).max() < 1e-7, (c, float(np.abs(state - gold[f"h{c}_final_state"]).max()))
+        kind, chi, dep = gold[f"h{c}_edge_kind"], gold[f"h{c}_edge_final_chi2"], gold[f"h{c}_edge_final_depth_positive"]
+        assert (rg.edge_outlier == ((chi > 7.815) | (dep == 0))[kind == 1]).all(), c
+        assert (rg.jedge_outlier == ((chi > 7.815) | (dep == 0))[kind == 2]).all(), c
+        assert (rg.redge_outlier == (chi > g.HBA_SIGMAS["th_rigidity"])[kind == 3]).all(), c
+        assert (rg.medge_outlier == (chi > g.HBA_SIGMAS["th_motion"])[kind == 4]).all(), c

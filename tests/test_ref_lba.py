@@ -124,6 +124,14 @@ def test_fixture_is_what_the_reference_library_computes_now(oracle_mod):
         r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, g.make_window(i))
         for k in ("kf_tcw", "mp_pos", "erased", "rows", "final_state"):
             assert (r[k] == gold[f"w{i}_{k}"]).all(), (i, k)
+    j = 2
+    r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, g.make_gba_window(j), global_ba=g.GBA_CASES[j][1:])
+    assert (r["rows"] == gold[f"g{j}_rows"]).all() and (r["final_state"] == gold[f"g{j}_final_state"]).all() and (r["kf_tcw"] == gold[f"g{j}_kf_tcw"]).all()
+    c = 1
+    w, hum = g.make_human_window(c)
+    r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, w, humans=hum)
+    assert (r["rows"] == gold[f"h{c}_rows"]).all() and (r["final_state"] == gold[f"h{c}_final_state"]).all()
+    assert (r["edge_final_chi2"] == gold[f"h{c}_edge_final_chi2"]).all() and (r["humans"]["key_flags"] == gold[f"h{c}_hum_key_flags"]).all()
 
 
 def gba_problem(gold, j):
@@ -164,3 +172,79 @@ def test_oracle_global_ba_equals_the_reference_function(oracle_mod):
             assert (T.reshape(4, 4) == gold[f"g{j}_kf_tcw"][kf_of[int(vid)]]).all(), (j, i)
         upd = gold[f"g{j}_mp_updates"]
         assert (upd[:-1] == (loop_kf if loop_kf else 1)).all() and upd[-1] == 0          # mnBAGlobalForKF / UpdateNormalAndDepth; removed point untouched
+
+
+def hba_problem(gold, c):
+    return {k[len(f"h{c}_p_"):]: (gold[k].item() if gold[k].ndim == 0 else gold[k]) for k in gold.files if k.startswith(f"h{c}_p_")}
+
+
+def test_oracle_dynamic_ba_equals_the_reference_function(oracle_mod):
+    """Optimizer::LocalBundleAdjustmentHumanTrajactory (src/Optimizer.cc:1496-2222), the whole function compiled from /root/reference with
+    the AirDOS vertex / edge types (VertexDistanceDouble, VertexSE3, EdgeRigidBodyDouble, LandmarkMotionTernaryEdge: their computeError and
+    chi2() decide the gates) and stand-ins of MapHumanTrajectory / MapHumanPose / MapHumanKey / Rigidbody / Map: which trajectories and
+    poses enter (thLongTrajectory, reference key-frame inside the window), vertex ids by kind, the joint / rigidity / motion edges with
+    SigmaHuman / SigmaRigidity / SigmaMotion and the kernels sqrt(7.815) / thRanSacRigidity / sqrt(thRanSacMotion), optimize(5), the four
+    gates + setRobustKernel(0), optimize(10), and the epilogue.  The Jacobians of the rigidity and motion edges are the oracle's
+    (conventions D.4 / D.6: the reference's are undefined); everything else of the run is the reference's.  ba_oracle_solve on the
+    problem the function built: every LM trial, the final estimates and all four outlier sets bit for bit."""
+    gold = np.load(GOLD)
+    g = _gen()
+    seen = set()
+    for c in range(len(g.HBA_CASES)):
+        prob = hba_problem(gold, c)
+        o = oracle_mod.ba_default_options()
+        hub = gold[f"h{c}_huber"]
+        assert hub[1] == o.huber_stereo
+        if len(prob["redge_i"]):
+            assert (hub[2], hub[3]) == (o.huber_rigid, o.huber_motion) == (1.0, 2.0)      # rk->setDelta(thRanSacRigidity), sqrt(thRanSacMotion) as float
+            assert (o.chi2_rigid, o.chi2_motion) == (g.HBA_SIGMAS["th_rigidity"], g.HBA_SIGMAS["th_motion"])
+        p, res, st = oracle_mod.ba_solve(prob, o)
+        assert st == 0 and [res.c.iterations_run[0], res.c.iterations_run[1]] == list(gold[f"h{c}_round_iterations"])
+        tr = res.trace_rows[:, [0, 1, 2, 4]]
+        assert tr.shape == gold[f"h{c}_rows"].shape and (tr == gold[f"h{c}_rows"]).all(), c
+        state = np.concatenate([p[k].ravel() for k in ("pose_q", "pose_t", "points", "joints", "dists", "motion_q", "motion_t")])
+        assert state.shape == gold[f"h{c}_final_state"].shape and (state == gold[f"h{c}_final_state"]).all(), c
+        kind, chi, dep = gold[f"h{c}_edge_kind"], gold[f"h{c}_edge_final_chi2"], gold[f"h{c}_edge_final_depth_positive"]
+        assert ((kind == 1) | (kind == 2) | (kind == 3) | (kind == 4)).all()             # the function builds stereo edges only
+        assert (res.edge_outlier == ((chi > 7.815) | (dep == 0))[kind == 1]).all(), c
+        assert int(res.edge_outlier.sum()) == len(gold[f"h{c}_erased"])
+        assert (res.jedge_outlier == ((chi > 7.815) | (dep == 0))[kind == 2]).all(), c
+        assert (res.redge_outlier == (chi > g.HBA_SIGMAS["th_rigidity"])[kind == 3]).all(), c
+        assert (res.medge_outlier == (chi > g.HBA_SIGMAS["th_motion"])[kind == 4]).all(), c
+        # the epilogue's bookkeeping follows the same flags: one HumanKeyPair per rigidity edge, mnBadTrack per motion outlier
+        pf = gold[f"h{c}_hum_pair_flags"]
+        assert int(pf[:, :, 0].sum()) == int(res.redge_outlier.sum()) and int(pf[:, :, 1].sum()) == int((res.redge_outlier == 0).sum())
+        assert int(gold[f"h{c}_hum_traj_out"][:, 0].sum()) == int(res.medge_outlier.sum())
+        if len(prob["redge_i"]):
+            assert (gold[f"h{c}_hum_traj_out"][:, 1] == 1).all() and int(gold[f"h{c}_hum_n_optimized_tracks"]) == len(gold[f"h{c}_motion_id"])
+            seen.add("articulated")
+        else:
+            seen.add("short trajectories left out")
+        if res.redge_outlier.any(): seen.add("rigidity outliers")
+        if res.medge_outlier.any(): seen.add("motion outliers")
+        if (tr[:, 3] == 0).any(): seen.add("rejected trial")
+    assert seen >= {"articulated", "short trajectories left out", "rigidity outliers", "motion outliers", "rejected trial"}
+
+
+def test_dynamic_ba_writes_back_joints_and_motion(oracle_mod):
+    """MapHumanPose::SetHumanKeyPos(Converter::toCvMat(vertex estimate)) for every key whose vertex exists, mTMotion = the motion vertex."""
+    gold = np.load(GOLD)
+    g = _gen()
+    for c in range(len(g.HBA_CASES)):
+        prob = hba_problem(gold, c)
+        if not len(prob["redge_i"]):
+            continue
+        w, hum = g.make_human_window(c)
+        p, res, st = oracle_mod.ba_solve(prob, oracle_mod.ba_default_options())
+        key_of = {int(v): i for i, v in enumerate(hum["key_id"].ravel())}
+        max_mt = int(gold[f"h{c}_motion_id"].max())
+        out = gold[f"h{c}_hum_key_pos"].reshape(-1, 3)
+        touched = np.zeros(len(out), bool)
+        for l, vid in enumerate(gold[f"h{c}_joint_id"]):
+            i = key_of[int(vid) - max_mt - 1]
+            touched[i] = True
+            assert (p["joints"][l].astype(np.float32) == out[i]).all(), (c, l)
+        assert (out[~touched] == hum["key_pos"].reshape(-1, 3)[~touched]).all()           # keys without a vertex keep their position
+        for m in range(len(gold[f"h{c}_motion_id"])):
+            T = gold[f"h{c}_hum_traj_motion"][m]
+            assert np.abs(T[:3, 3] - p["motion_t"][m]).max() < 1e-6 and T[3, 3] == 1
