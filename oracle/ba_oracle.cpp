@@ -20,13 +20,13 @@
 //                        Solver / PoseSolver below through function pointers                   -> lm_ref.npz: trials, lambda, state bit for bit
 //   Huber kernel         RobustKernelHuber::setDelta / robustify (float dsqr member)           -> lm_ref.npz, bit for bit
 //   quadratic form       BaseBinaryEdge / BaseUnaryEdge::constructQuadraticForm                -> lm_ref.npz, 1e-12
-//   schedules and gates  Optimizer::LocalBundleAdjustment, ::BundleAdjustment, ::PoseOptimization whole, with the reference's edge types,
+//   schedules and gates  Optimizer::LocalBundleAdjustment, ::BundleAdjustment, ::PoseOptimization, ::LocalBundleAdjustmentHumanTrajactory whole, with the reference's edge types,
 //                        Converter and LM control over this file's solver steps (oracle/ref_lba.cpp) -> lba_ref.npz, pose_ref.npz: every
 //                        trial, final state, erase list / mvbOutlier / return value bit for bit
 // What stays "parity unpinned" against the literal reference: BlockSolver::buildSystem / solve (the Schur complement and the order of
 // its sums) and the linear solvers -- they need Eigen proper; the reduced system is solved by a dense Cholesky instead of Eigen's
-// SimplicialLDLT / LDLT, which agrees to rounding -- and LocalBundleAdjustmentHumanTrajactory's schedule (its rigidity / motion Jacobians
-// are undefined in the reference, D.4 / D.6).  Those are pinned mathematically: finite-difference Jacobians, an independent numpy
+// SimplicialLDLT / LDLT, which agrees to rounding -- and the rigidity / motion Jacobians (undefined in the reference, D.4 / D.6).  Those
+// are pinned mathematically: finite-difference Jacobians, an independent numpy
 // normal-equation solve and an independent numpy LM trajectory (tests/test_oracle_ba.py).
 // Conventions for the reference's ill-defined corners: D.4 analytic
 // rigidity Jacobian, D.5 motion prior = identity (the caller passes it), D.6 d(error)/d(motion
