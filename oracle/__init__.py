@@ -692,3 +692,30 @@ def pose_optimize_traced(cam: dict, frame: dict):
     rows = np.zeros((512, 4)); n = C.c_int()
     lib.ba_oracle_pose_optimize_traced(C.byref(pb.c), 0, _p(rows), 512, C.byref(n))
     return pb, rows[:n.value].copy()
+
+
+# ------------------------------------------------------------------------------------------
+# oracle/ref_orb.cpp: the reference's ORBextractor::operator() over the oracle's pixel primitives
+class _OrbPrims(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("border101", "erode10", "resize", "blur7", "fast")]
+
+
+def ref_orb_extract(ref_lib, img: np.ndarray, mask: np.ndarray | None = None, nfeatures: int = 1000, scale: float = 1.2, nlevels: int = 8,
+                    ini_th: int = 20, min_th: int = 7, monotonic: bool = True):
+    """ORBextractor::operator() / ComputePyramid / ComputeKeyPointsOctTree of the reference (oracle/_ref/libref_orb.so) with cv::resize,
+    copyMakeBorder, erode, GaussianBlur and FastFeatureDetector landing in the oracle's primitives -> (key-points KP_DTYPE, descriptors, pyramid)."""
+    lib = orb_lib()
+    pr = _OrbPrims(*[C.cast(getattr(lib, "orb_oracle_" + n), C.c_void_p) for n in ("border101", "erode10", "resize", "blur7", "fast")])
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    cap = nfeatures * 2 + 64
+    kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+    p = orb_params(nfeatures, scale, nlevels, w, h)
+    pyr = np.zeros(int((p["w"].astype(np.int64) * p["h"]).sum()), np.uint8)
+    ref_lib.ref_orb_extract.argtypes = [C.POINTER(_OrbPrims), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    n = ref_lib.ref_orb_extract(C.byref(pr), _p(img), w, h, None if m is None else _p(m), nfeatures, scale, nlevels, ini_th, min_th, _p(kps), _p(desc), cap,
+                                _p(pyr), int(monotonic))
+    assert n >= 0
+    return kps[:n].copy(), desc[:n].copy(), pyr

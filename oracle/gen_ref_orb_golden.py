@@ -87,6 +87,45 @@ def tables_main(L):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+# ORBextractor::operator() as a whole: (width, height, nfeatures, iniThFAST, minThFAST, person mask, image seed)
+EXTRACT_CASES = [(640, 480, 1000, 20, 7, False, 1), (640, 480, 2000, 20, 7, True, 2), (320, 240, 500, 12, 7, True, 3), (752, 480, 1500, 20, 7, False, 4),
+                 (200, 150, 300, 20, 7, True, 5), (640, 360, 1500, 30, 3, False, 6), (1241, 376, 2000, 20, 7, True, 7)]
+
+
+def make_extract_case(i):
+    from airdos_b200 import synth
+    w, h, nf, ini, mn, masked, seed = EXTRACT_CASES[i]
+    img = synth.make_stereo_pair(seed, w, h)[0]
+    msk = synth.make_human_mask(seed, w, h, 2) if masked else None
+    return img, msk, nf, ini, mn
+
+
+def extract_main(L):
+    """tests/golden/extractor_ref.npz: the reference's own ORBextractor::operator() / ComputePyramid / ComputeKeyPointsOctTree /
+    computeOrientation / computeDescriptors (src/ORBextractor.cc:474-481, 767-864, 1040-1156; whole definitions compiled from /root/reference)
+    on seeded images, their OpenCV calls landing in the oracle's primitives (oracle/ref_orb.cpp)."""
+    import oracle
+    out = {}
+    same = 0
+    for i in range(len(EXTRACT_CASES)):
+        img, msk, nf, ini, mn = make_extract_case(i)
+        k, d, pyr = oracle.ref_orb_extract(L, img, msk, nf, 1.2, 8, ini, mn)
+        o = oracle.orb_extract(img, msk, nf, 1.2, 8, ini, mn, want_pyramid=True)
+        ok = len(k) == len(o["kps"]) and k.tobytes() == o["kps"].tobytes() and bool((d == o["desc"]).all()) and \
+            bool((pyr == np.concatenate([l.ravel() for l in o["pyramid"]])).all())
+        same += int(ok)
+        out[f"e{i}_n"] = np.int32(len(k)); out[f"e{i}_kps_crc"] = np.int64(zlib.crc32(k.tobytes())); out[f"e{i}_desc_crc"] = np.int64(zlib.crc32(d.tobytes()))
+        out[f"e{i}_pyr_crc"] = np.int64(zlib.crc32(pyr.tobytes()))
+        out[f"e{i}_per_level"] = np.bincount(k["octave"], minlength=8).astype(np.int32)
+        if i in (2, 4):
+            out[f"e{i}_kps"] = k; out[f"e{i}_desc"] = d
+        print(f"extract {i}: {EXTRACT_CASES[i]} -> {len(k)} key-points, per level {list(out[f'e{i}_per_level'])}: oracle {'identical' if ok else 'DIFFERENT'}")
+    print(f"operator(): the oracle equals the reference function in {same} of {len(EXTRACT_CASES)} images (key-points, descriptors, pyramid: bit for bit)")
+    path = os.path.join(ROOT, "tests", "golden", "extractor_ref.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     import oracle
     oracle.build()
@@ -108,6 +147,7 @@ def main():
     np.savez_compressed(path, crc=np.array(crcs, np.int64), count=np.array(counts, np.int32), same_with_stock_malloc=np.int32(same_malloc), **keep)
     print("wrote", path, os.path.getsize(path), "bytes")
     tables_main(L)
+    extract_main(L)
 
 
 if __name__ == "__main__":

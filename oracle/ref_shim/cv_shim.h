@@ -36,6 +36,9 @@ inline float fastAtan2(float y, float x) {
     if (y < 0) a = 360.f - a;
     return a;
 }
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} bool operator==(const Size& o) const { return width == o.width && height == o.height; } };
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+inline Point2f& operator*=(Point2f& p, float s) { p.x *= s; p.y *= s; return p; }
 struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
 
 class Mat {
@@ -45,6 +48,23 @@ public:
     size_t step1() const { return step / (type_ == CV_32F ? 4 : 1); }
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(Size sz, int type) { create(sz.height, sz.width, type); }
+    // Mat::zeros(...) is a MatExpr in OpenCV: assigning it to a Mat of the same size and type fills that Mat's OWN storage (a row
+    // range of another matrix stays a view of it: src/ORBextractor.cc:1045, 1100-1101)
+    struct ZerosExpr { int rows, cols, type; };
+    static ZerosExpr zeros(int r, int c, int type) { return ZerosExpr{r, c, type}; }
+    Mat(const ZerosExpr& z) { create(z.rows, z.cols, z.type); }
+    Mat& operator=(const ZerosExpr& z) {
+        if (rows != z.rows || cols != z.cols || type_ != z.type || !buf_) create(z.rows, z.cols, z.type);
+        for (int i = 0; i < rows; ++i) std::memset(buf_->data() + off_ + (size_t)i * step_, 0, (size_t)cols * esz());
+        return *this;
+    }
+    Mat operator()(const Rect& r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
+    Size size() const { return Size(cols, rows); }
+    Mat getMat() const { return *this; }                 // InputArray / OutputArray are plain Mat references here
+    void release() { *this = Mat(); }
+    unsigned char* ptr(int r) { return buf_->data() + off_ + (size_t)r * step_; }
+    unsigned char* ptr_mut(int r) const { return buf_->data() + off_ + (size_t)r * step_; }
     Mat(int r, int c, int type, const void* data) { create(r, c, type); std::memcpy(buf_->data(), data, (size_t)r * step_); }
     static Mat ones(int r, int c, int type) {
         Mat m(r, c, type);

@@ -38,6 +38,29 @@ def test_cuda_matches_golden_fixture(adb, path):
     ex.close()
 
 
+def test_cuda_matches_the_reference_operator():
+    """adb_orb_extract against tests/golden/extractor_ref.npz = the reference's own ORBextractor::operator() (with ComputePyramid,
+    ComputeKeyPointsOctTree, DistributeOctTree, IC_Angle, computeOrbDescriptor: whole definitions compiled from /root/reference,
+    oracle/ref_orb.cpp; OpenCV calls = the cv2-pinned primitives) on seven seeded images: key-points (all six fields, angle bit patterns
+    included), descriptors and the pyramid bit for bit."""
+    import importlib.util, zlib
+    import airdos_b200 as adb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_ref_orb_golden", os.path.join(root, "oracle", "gen_ref_orb_golden.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    gold = np.load(os.path.join(GOLDEN, "extractor_ref.npz"))
+    for i in range(len(g.EXTRACT_CASES)):
+        img, msk, nf, ini, mn = g.make_extract_case(i)
+        ex = adb.ORBextractor(nf, 1.2, 8, ini, mn, img.shape[1], img.shape[0])
+        kps, desc = ex(img, msk)
+        assert len(kps) == int(gold[f"e{i}_n"]), i
+        assert zlib.crc32(kps.tobytes()) == int(gold[f"e{i}_kps_crc"]) and zlib.crc32(np.ascontiguousarray(desc).tobytes()) == int(gold[f"e{i}_desc_crc"]), i
+        assert zlib.crc32(np.concatenate([p.ravel() for p in ex.pyramid(0)]).tobytes()) == int(gold[f"e{i}_pyr_crc"]), i
+        if f"e{i}_kps" in gold.files:
+            assert kps.tobytes() == gold[f"e{i}_kps"].tobytes() and (desc == gold[f"e{i}_desc"]).all()
+        ex.close()
+
+
 @pytest.mark.parametrize("w,h,nf,ini,mn,masked", [(640, 480, 1000, 12, 7, False), (640, 480, 2000, 12, 7, False),
                                                   (640, 480, 1000, 12, 7, True), (640, 360, 1500, 12, 7, False),
                                                   (320, 240, 500, 20, 7, True), (333, 251, 700, 20, 7, False),

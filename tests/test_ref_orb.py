@@ -87,3 +87,39 @@ def test_tables_fixture_is_what_the_reference_library_computes_now(oracle_mod):
     img, xy = g.make_desc_case(2)
     a, d = oracle_mod.orient_describe(img, oracle_mod.blur7(img), xy, lib=L)
     assert a.tobytes() == gold["d2_angle"].tobytes() and (d == gold["d2_desc"]).all()
+
+
+EXTRACT = os.path.join(ROOT, "tests", "golden", "extractor_ref.npz")
+
+
+def test_oracle_extractor_equals_the_reference_operator(oracle_mod):
+    """tests/golden/extractor_ref.npz: the reference's own ORBextractor::operator(), ComputePyramid, ComputeKeyPointsOctTree, computeOrientation
+    and computeDescriptors (src/ORBextractor.cc:474-481, 767-864, 1040-1156: whole definitions compiled from /root/reference, oracle/ref_orb.cpp)
+    on seven seeded images (VGA, QVGA, 752 x 480, 640 x 360, a 200 x 150 image whose top levels are empty, a 1241 x 376 image with three
+    quad-tree roots; with and without a person mask; three threshold pairs).  Their five OpenCV calls land in the oracle's primitives,
+    everything else -- the in-place ROI / border handling of the pyramid, the resized mask pyramid, the cell grid and the ini / min
+    threshold rule, the quad-tree, the orientation, the per-level blur and descriptors, the final scaling and the output order -- is the
+    reference's.  The oracle's extract() gives the same key-points, descriptors and pyramid bit for bit."""
+    g = _gen()
+    gold = np.load(EXTRACT)
+    for i in range(len(g.EXTRACT_CASES)):
+        img, msk, nf, ini, mn = g.make_extract_case(i)
+        o = oracle_mod.orb_extract(img, msk, nf, 1.2, 8, ini, mn, want_pyramid=True)
+        assert len(o["kps"]) == int(gold[f"e{i}_n"]), i
+        assert zlib.crc32(o["kps"].tobytes()) == int(gold[f"e{i}_kps_crc"]) and zlib.crc32(o["desc"].tobytes()) == int(gold[f"e{i}_desc_crc"]), i
+        assert zlib.crc32(np.concatenate([l.ravel() for l in o["pyramid"]]).tobytes()) == int(gold[f"e{i}_pyr_crc"]), i
+        assert (np.bincount(o["kps"]["octave"], minlength=8) == gold[f"e{i}_per_level"]).all()
+        if f"e{i}_kps" in gold.files:
+            assert o["kps"].tobytes() == gold[f"e{i}_kps"].tobytes() and (o["desc"] == gold[f"e{i}_desc"]).all()
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_LIB) and os.path.isdir("/root/reference")), reason="reference tree / oracle/_ref not present (GPU box)")
+def test_extractor_fixture_is_what_the_reference_library_computes_now(oracle_mod):
+    import ctypes as C
+    g = _gen()
+    gold = np.load(EXTRACT)
+    L = C.CDLL(REF_LIB)
+    for i in (2, 4):
+        img, msk, nf, ini, mn = g.make_extract_case(i)
+        k, d, pyr = oracle_mod.ref_orb_extract(L, img, msk, nf, 1.2, 8, ini, mn)
+        assert k.tobytes() == gold[f"e{i}_kps"].tobytes() and (d == gold[f"e{i}_desc"]).all() and zlib.crc32(pyr.tobytes()) == int(gold[f"e{i}_pyr_crc"])
