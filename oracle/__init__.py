@@ -511,6 +511,27 @@ def pose_quadratic_form(dim, J, er, w0, delta, robust, lib=None):
     return h, g
 
 
+def multi_quadratic_form(dim, dims, Js, er, w0, delta, robust, lib=None):
+    """A three-vertex edge's (rigidity: dim 1, vertices 3 + 3 + 1; motion: dim 3, vertices 3 + 3 + 6) contribution to the normal equations as a
+    dense (sum dims)^2 matrix and a right-hand side; `lib` = libref_lm.so runs the reference's BaseMultiEdge::constructQuadraticForm."""
+    Js = [np.ascontiguousarray(J, np.float64) for J in Js]
+    er = np.ascontiguousarray(er, np.float64)
+    n = int(sum(dims)); H = np.zeros((n, n)); b = np.zeros(n)
+    d = np.array(dims, np.int32)
+    ptrs = (C.c_void_p * len(Js))(*[J.ctypes.data for J in Js])
+    vp = C.c_void_p
+    if lib is None:
+        f = ba_lib().ba_oracle_multi_quadratic_form
+        f.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp]
+        f(dim, len(dims), _p(d), ptrs, _p(er), w0, delta, int(robust), _p(H), _p(b))
+    else:
+        fx = np.zeros(len(dims), np.uint8)
+        f = lib.ref_multi_quadratic_form
+        f.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp]
+        f(dim, len(dims), _p(d), ptrs, _p(er), w0, delta, int(robust), _p(fx), _p(H), _p(b))
+    return H, b
+
+
 def huber(delta: float, e2: float, lib=None):
     """RobustKernelHuber::robustify -> (rho, rho'); `lib` = libref_lm.so runs the reference's function."""
     if lib is not None:

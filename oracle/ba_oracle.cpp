@@ -251,6 +251,19 @@ inline void edge_quadratic_form(int dim, const double* Ji, const double* Jj, con
     }
 }
 
+// one block of BaseMultiEdge::computeQuadraticForm (Thirdparty/g2o/g2o/core/base_multi_edge.hpp:170-222): A^T (w I) B for Jacobians given
+// row-major dim x da / dim x db, and A^T wr for the right-hand side
+inline double block_entry(int da, const double* A, int i, int db, const double* B, int j, int dim, double w) {
+    double s = 0;
+    for (int k = 0; k < dim; ++k) s += A[k * da + i] * w * B[k * db + j];
+    return s;
+}
+inline double rhs_entry(int da, const double* A, int i, int dim, const double* wr) {
+    double s = 0;
+    for (int k = 0; k < dim; ++k) s += A[k * da + i] * wr[k];
+    return s;
+}
+
 inline bool inv3(const double* A, double* B) {   // Eigen fixed-size inverse (cofactors)
     const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
     const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
@@ -345,19 +358,11 @@ struct Solver {
     void add_block(int oa, int da, const double* A, int ob, int db, const double* B, int dim, double w) {
         if (oa < 0 || ob < 0) return;
         for (int i = 0; i < da; ++i)
-            for (int j = 0; j < db; ++j) {
-                double s = 0;
-                for (int k = 0; k < dim; ++k) s += A[k * da + i] * w * B[k * db + j];
-                H[(size_t)(oa + i) * n_dense + ob + j] += s;
-            }
+            for (int j = 0; j < db; ++j) H[(size_t)(oa + i) * n_dense + ob + j] += block_entry(da, A, i, db, B, j, dim, w);
     }
     void add_rhs(int oa, int da, const double* A, int dim, const double* wr) {   // b += A^T * wr
         if (oa < 0) return;
-        for (int i = 0; i < da; ++i) {
-            double s = 0;
-            for (int k = 0; k < dim; ++k) s += A[k * da + i] * wr[k];
-            b[oa + i] += s;
-        }
+        for (int i = 0; i < da; ++i) b[oa + i] += rhs_entry(da, A, i, dim, wr);
     }
 
     // computeActiveErrors + activeRobustChi2 on an arbitrary state (the current trial state is *this)
@@ -766,6 +771,25 @@ int ba_oracle_first_step(adb_ba_problem* prob, const adb_ba_options* opt, double
     return S.n_dense;
 }
 
+// a multi-vertex edge's quadratic form the way Solver::build_system accumulates rigidity / motion edges: nv vertices of dimensions dims[],
+// Jacobians Js[v] row-major dim x dims[v], information w0 * I, Huber(delta) if robust.  H: dense (sum dims)^2 row-major, b: sum dims
+void ba_oracle_multi_quadratic_form(int dim, int nv, const int32_t* dims, const double* const* Js, const double* er, double w0, double delta, int robust,
+                                    double* H, double* b) {
+    double r0, r1, c = 0;
+    for (int k = 0; k < dim; ++k) c += er[k] * (w0 * er[k]);
+    robustify(make_huber(delta), robust != 0, c, &r0, &r1);
+    const double w = r1 * w0;
+    double wr[3] = {0, 0, 0};
+    for (int k = 0; k < dim; ++k) wr[k] = -w0 * er[k] * r1;
+    int n = 0; std::vector<int> off(nv);
+    for (int v = 0; v < nv; ++v) { off[v] = n; n += dims[v]; }
+    for (int u = 0; u < nv; ++u) {
+        for (int i = 0; i < dims[u]; ++i) b[off[u] + i] = rhs_entry(dims[u], Js[u], i, dim, wr);
+        for (int v = 0; v < nv; ++v)
+            for (int i = 0; i < dims[u]; ++i)
+                for (int j = 0; j < dims[v]; ++j) H[(size_t)(off[u] + i) * n + off[v] + j] = block_entry(dims[u], Js[u], i, dims[v], Js[v], j, dim, w);
+    }
+}
 void ba_oracle_huber(double delta, double e2, double* rho2) { robustify(make_huber(delta), true, e2, rho2, rho2 + 1); }
 // one reprojection edge's quadratic form (what Solver::build_system adds for it); hp may be NULL for a fixed pose
 void ba_oracle_edge_quadratic_form(int dim, const double* Ji, const double* Jj, const double* er, double w0, double delta, int robust,

@@ -53,6 +53,18 @@ def make_qf_case(t):
     return dim, Ji, Jj, er, w0, delta, robust, fixed
 
 
+N_MULTI = 300
+
+
+def make_multi_case(t):
+    """A rigidity edge (1 residual; joint, joint, bone length) or a motion edge (3 residuals; joint, joint, SE3 motion) with random Jacobians."""
+    rng = np.random.default_rng(94000 + t)
+    dim, dims = (1, [3, 3, 1]) if t & 1 else (3, [3, 3, 6])
+    Js = [rng.normal(0, 3, (dim, d)) for d in dims]
+    er = np.zeros(3); er[:dim] = rng.normal(0, rng.choice([0.05, 1, 5]), dim)
+    return dim, dims, Js, er, 20.0, (1.0 if dim == 1 else 2.0), (t >> 1) & 1
+
+
 def huber_inputs():
     """The deltas the Optimizer sets (float thHuber* promoted to double, src/Optimizer.cc:95-96, 538-539, 742-744) x squared errors around
     delta^2: far inside, far outside, and a fine sweep across [delta^2 - 1e-6, delta^2 + 1e-6] which contains both the double delta^2
@@ -102,6 +114,14 @@ def main():
             worst = max(worst, float(np.abs(x - y).max() / max(np.abs(x).max(), 1e-300)))
         out[f"qf{t}"] = np.concatenate(list(r) + list(ru))
     print(f"quadratic forms: {N_QF} edges (binary + unary), worst relative difference oracle vs reference {worst:.3g}")
+    worst = 0.0
+    for t in range(N_MULTI):
+        c = make_multi_case(t)
+        Hr, br = oracle.multi_quadratic_form(*c, lib=L)
+        Ho, bo = oracle.multi_quadratic_form(*c)
+        worst = max(worst, float(np.abs(Hr - Ho).max() / max(np.abs(Hr).max(), 1e-300)), float(np.abs(br - bo).max() / max(np.abs(br).max(), 1e-300)))
+        out[f"mq{t}"] = np.concatenate([Hr.ravel(), br])
+    print(f"multi-edge quadratic forms: {N_MULTI} rigidity / motion edges, worst relative difference oracle vs reference {worst:.3g}")
     path = os.path.join(ROOT, "tests", "golden", "lm_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -9,6 +9,7 @@
 //   BaseEdge::chi2 / robustInformation    core/base_edge.h:58-61, 96-102
 //   BaseBinaryEdge::constructQuadraticForm  core/base_binary_edge.hpp:54-117
 //   BaseUnaryEdge::constructQuadraticForm   core/base_unary_edge.hpp:40-69
+//   BaseMultiEdge::constructQuadraticForm / computeQuadraticForm   core/base_multi_edge.hpp:35-49, 170-222   (rigidity / motion edges)
 // The function texts are taken out of the reference tree at build time (oracle/extract_ref_fn.py -> oracle/_ref/lm_*.inc) and
 // compiled between stand-in declarations of the classes they are members of (same member names and types as the reference's
 // headers, which themselves need Eigen proper and all of g2o core).  What the stand-ins do NOT restate is the arithmetic
@@ -79,12 +80,18 @@ struct LmLog {     // what the stand-ins observe of a run: one row per trial = (
     double lambda = 0, before = 0, after = 0;
 };
 
+struct QVertexBase { virtual ~QVertexBase() {} };
 class OptimizableGraph {
 public:
-    struct Vertex {
+    struct Vertex : QVertexBase {
         int dim = 0; const double* diag = nullptr;
         int dimension() const { return dim; }
         double hessian(int i, int j) const { return i == j ? diag[i] : 0.0; }
+        // the multi-edge writes through raw pointers (core/optimizable_graph.h: hessianData / bData)
+        bool fixed_ = false; std::vector<double> H, b;
+        bool fixed() const { return fixed_; }
+        double* hessianData() { return H.data(); }
+        double* bData() { return b.data(); }
     };
     typedef std::vector<Vertex*> VertexContainer;
 };
@@ -215,7 +222,6 @@ private:
 };
 
 // ---- edges: the members constructQuadraticForm touches (core/base_edge.h, base_binary_edge.h, base_unary_edge.h)
-struct QVertexBase { virtual ~QVertexBase() {} };
 template <int D> struct QVertex : QVertexBase {
     static const int Dimension = D;
     bool fixed_ = false;
@@ -267,8 +273,27 @@ public:
     JacobianXiOplusType _jacobianOplusXi;
 };
 
+template <int D, typename E> class BaseMultiEdge : public BaseEdge<D, E> {      // core/base_multi_edge.h:53-108
+public:
+    typedef typename BaseEdge<D, E>::InformationType InformationType;
+    typedef typename BaseEdge<D, E>::ErrorVector ErrorVector;
+    typedef Eigen::MatrixXd JacobianType;
+    typedef Eigen::Map<Eigen::MatrixXd> HessianBlockType;
+    struct HessianHelper { Eigen::Map<Eigen::MatrixXd> matrix; bool transposed; HessianHelper() : matrix(nullptr, 0, 0), transposed(false) {} };
+    using BaseEdge<D, E>::_vertices; using BaseEdge<D, E>::_information; using BaseEdge<D, E>::_error;
+    void constructQuadraticForm();
+    void computeQuadraticForm(const InformationType& omega, const ErrorVector& weightedError);
+    std::vector<HessianHelper> _hessian;
+    std::vector<JacobianType> _jacobianOplus;
+};
+
 using namespace Eigen;
 #include "_ref/lm_huber.inc"
+namespace internal { inline int computeUpperTriangleIndex(int i, int j) { int elemsUpToCol = ((j - 1) * j) / 2; return elemsUpToCol + i; } }   // base_multi_edge.hpp:27-33
+template <int D, typename E>
+#include "_ref/lm_multi_cqf.inc"
+template <int D, typename E>
+#include "_ref/lm_multi_compute.inc"
 template <int D, typename E, typename VertexXiType, typename VertexXjType>
 #include "_ref/lm_binary_cqf.inc"
 template <int D, typename E, typename VertexXiType>
@@ -314,9 +339,61 @@ template <int D> void run_unary(const double* J, const double* er, double w0, do
     e.constructQuadraticForm();
     for (int i = 0; i < 6; ++i) { g[i] = pose.b_(i); for (int j = 0; j < 6; ++j) h[i * 6 + j] = pose.A_(i, j); }
 }
+template <int D> void run_multi(int nv, const int32_t* dims, const double* const* Js, const double* er, double w0, double delta, int robust, const uint8_t* fixed,
+                                double* H, double* b) {
+    using namespace g2o;
+    std::vector<OptimizableGraph::Vertex> vs(nv);
+    BaseMultiEdge<D, Eigen::Matrix<double, D, 1>> e;
+    int n = 0; std::vector<int> off(nv);
+    for (int v = 0; v < nv; ++v) { off[v] = n; n += dims[v]; }
+    for (int v = 0; v < nv; ++v) {
+        vs[v].dim = dims[v]; vs[v].fixed_ = fixed && fixed[v]; vs[v].H.assign((size_t)dims[v] * dims[v], 0.0); vs[v].b.assign(dims[v], 0.0);
+        e._vertices.push_back(&vs[v]);
+        Eigen::MatrixXd J(D, dims[v]);
+        for (int k = 0; k < D; ++k) for (int j = 0; j < dims[v]; ++j) J(k, j) = Js[v][k * dims[v] + j];
+        e._jacobianOplus.push_back(J);
+    }
+    // off-diagonal blocks: upper triangle, column-major maps into scratch (g2o maps them into the solver's block matrix: mapHessianMemory)
+    std::vector<std::vector<double>> blocks((size_t)nv * (nv - 1) / 2);
+    e._hessian.resize(blocks.size());
+    for (int j = 1; j < nv; ++j)
+        for (int i = 0; i < j; ++i) {
+            const int idx = internal::computeUpperTriangleIndex(i, j);
+            blocks[idx].assign((size_t)dims[i] * dims[j], 0.0);
+            e._hessian[idx].matrix = Eigen::Map<Eigen::MatrixXd>(blocks[idx].data(), dims[i], dims[j]);
+        }
+    RobustKernelHuber rk;
+    if (robust) { rk.setDelta(delta); e._robustKernel = &rk; }
+    for (int k = 0; k < D; ++k) { e._error(k) = er[k]; e._information(k, k) = w0; }
+    e.constructQuadraticForm();
+    for (int i = 0; i < n * n; ++i) H[i] = 0;
+    for (int v = 0; v < nv; ++v) {
+        for (int i = 0; i < dims[v]; ++i) {
+            b[off[v] + i] = vs[v].b[i];
+            for (int j = 0; j < dims[v]; ++j) H[(size_t)(off[v] + i) * n + off[v] + j] = vs[v].H[(size_t)j * dims[v] + i];
+        }
+    }
+    for (int j = 1; j < nv; ++j)
+        for (int i = 0; i < j; ++i) {
+            const std::vector<double>& B = blocks[internal::computeUpperTriangleIndex(i, j)];
+            for (int r = 0; r < dims[i]; ++r)
+                for (int c = 0; c < dims[j]; ++c) {
+                    H[(size_t)(off[i] + r) * n + off[j] + c] = B[(size_t)c * dims[i] + r];
+                    H[(size_t)(off[j] + c) * n + off[i] + r] = B[(size_t)c * dims[i] + r];      // the solver reads the block and its transpose
+                }
+        }
+}
 }  // namespace
 
 extern "C" {
+
+// BaseMultiEdge<dim>::constructQuadraticForm for nv vertices (dims[], fixed[]), Jacobians Js[v] row-major dim x dims[v]: H dense (sum dims)^2
+// row-major with the diagonal blocks the vertices received and both triangles of the off-diagonal blocks, b the right-hand sides
+void ref_multi_quadratic_form(int dim, int nv, const int32_t* dims, const double* const* Js, const double* er, double w0, double delta, int robust,
+                              const uint8_t* fixed, double* H, double* b) {
+    if (dim == 1) run_multi<1>(nv, dims, Js, er, w0, delta, robust, fixed, H, b);
+    else run_multi<3>(nv, dims, Js, er, w0, delta, robust, fixed, H, b);
+}
 
 // RobustKernelHuber::robustify after setDelta(delta): rho[3]
 void ref_huber(double delta, double e2, double* rho) {

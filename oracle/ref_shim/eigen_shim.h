@@ -174,7 +174,18 @@ public:
         assert(R == r_ && C == c_);
         Matrix<double, R, C, O> m; for (int r = 0; r < R; ++r) for (int c = 0; c < C; ++c) m(r, c) = (*this)(r, c); return m;
     }
+    // what BaseMultiEdge::computeQuadraticForm does with its run-time sized Jacobians (core/base_multi_edge.hpp:170-222)
+    template <int R, int C, int O> MatrixXd(const Matrix<double, R, C, O>& m) : v_((size_t)R * C), r_(R), c_(C) { for (int r = 0; r < R; ++r) for (int c = 0; c < C; ++c) (*this)(r, c) = m(r, c); }
+    MatrixXd transpose() const { MatrixXd t(c_, r_); for (int r = 0; r < r_; ++r) for (int c = 0; c < c_; ++c) t(c, r) = (*this)(r, c); return t; }
+    MatrixXd operator*(const MatrixXd& b) const {
+        assert(c_ == b.r_);
+        MatrixXd o(r_, b.c_);
+        for (int r = 0; r < r_; ++r) for (int c = 0; c < b.c_; ++c) { double s = 0; for (int k = 0; k < c_; ++k) s += (*this)(r, k) * b(k, c); o(r, c) = s; }
+        return o;
+    }
+    template <int R, int C, int O> MatrixXd operator*(const Matrix<double, R, C, O>& b) const { return *this * MatrixXd(b); }
 };
+typedef MatrixXd VectorXd;
 inline MatrixXd operator*(double k, const MatrixXd& m) { MatrixXd o(m.rows(), m.cols()); for (int r = 0; r < m.rows(); ++r) for (int c = 0; c < m.cols(); ++c) o(r, c) = k * m(r, c); return o; }
 inline MatrixXd operator*(const MatrixXd& m, double k) { return k * m; }
 
@@ -202,6 +213,17 @@ public:
         Matrix<double, BR, BC> b; for (int r = 0; r < BR; ++r) for (int c = 0; c < BC; ++c) b(r, c) = p_[(c0 + c) * rows() + r0 + r]; return b;
     }
     template <int N> Matrix<double, N, 1> head() const { Matrix<double, N, 1> h; for (int i = 0; i < N; ++i) h(i) = p_[i]; return h; }
+};
+
+// Map<MatrixXd>(ptr, rows, cols) / Map<VectorXd>(ptr, n): column-major view that the multi-edge accumulates into
+template <int MapOptions> class Map<MatrixXd, MapOptions> {
+    double* p_; int r_, c_;
+public:
+    Map(double* p, int r, int c) : p_(p), r_(r), c_(c) {}
+    Map(double* p, int n) : p_(p), r_(n), c_(1) {}
+    Map& noalias() { return *this; }
+    Map& operator+=(const MatrixXd& m) { assert(m.rows() == r_ && m.cols() == c_); for (int c = 0; c < c_; ++c) for (int r = 0; r < r_; ++r) p_[(size_t)c * r_ + r] += m(r, c); return *this; }
+    double operator()(int r, int c) const { return p_[(size_t)c * r_ + r]; }
 };
 
 // Eigen::Quaternion: coefficients stored x, y, z, w; constructor order w, x, y, z

@@ -79,6 +79,19 @@ def test_oracle_quadratic_forms_equal_the_reference_edges(oracle_mod):
         assert len(got) == len(ref)
 
 
+def test_oracle_multi_edge_quadratic_forms_equal_the_reference(oracle_mod):
+    """BaseMultiEdge::constructQuadraticForm / computeQuadraticForm (core/base_multi_edge.hpp:35-49, 170-222) of the reference on 300 seeded
+    rigidity (1 x [3 | 3 | 1]) and motion (3 x [3 | 3 | 6]) edges, kernel on / off: the diagonal blocks the three vertices receive, the
+    three off-diagonal blocks and the right-hand sides against what Solver::build_system accumulates for such an edge, 1e-12."""
+    g = _gen()
+    gold = np.load(GOLD)
+    for t in range(g.N_MULTI):
+        H, b = oracle_mod.multi_quadratic_form(*g.make_multi_case(t))
+        ref = gold[f"mq{t}"]
+        got = np.concatenate([H.ravel(), b])
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), t
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="reference tree / oracle/_ref not present (GPU box)")
 def test_fixture_is_what_the_reference_library_computes_now(oracle_mod):
     import ctypes as C
