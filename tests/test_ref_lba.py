@@ -248,3 +248,39 @@ def test_dynamic_ba_writes_back_joints_and_motion(oracle_mod):
         for m in range(len(gold[f"h{c}_motion_id"])):
             T = gold[f"h{c}_hum_traj_motion"][m]
             assert np.abs(T[:3, 3] - p["motion_t"][m]).max() < 1e-6 and T[3, 3] == 1
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree / oracle/_ref not present (GPU box)")
+def test_reference_function_at_baseline_config4_size(oracle_mod):
+    """BASELINE.json configs[3] (50 key-frames, 20 000 map points, 120 000 stereo edges): the reference's own LocalBundleAdjustment run live
+    (nothing this large is stored) against ba_oracle_solve on the problem it built: every trial, the final state and the erase list."""
+    import ctypes as C
+    g = _gen()
+    LM = C.CDLL(os.path.join(REF, "libref_lm.so")); LBA = C.CDLL(os.path.join(REF, "libref_lba.so"))
+    from airdos_b200 import synth
+    d = synth.make_ba_problem(50, 20000, 6, seed=4000)
+    assert len(d["edge_pose"]) == 120000
+    K = len(d["pose_t"]); cur = K - 1
+    order = [cur] + [k for k in range(K) if k != cur]
+    pos = {k: j for j, k in enumerate(order)}
+    lib = oracle_mod.ba_lib()
+    lib.ba_oracle_pose_to_tcw.argtypes = [C.c_void_p] * 3
+    tcw = np.zeros((K, 4, 4), np.float32)
+    for j, k in enumerate(order):
+        q = np.ascontiguousarray(d["pose_q"][k]); t = np.ascontiguousarray(d["pose_t"][k]); T = np.zeros(16, np.float32)
+        lib.ba_oracle_pose_to_tcw(q.ctypes.data, t.ctypes.data, T.ctypes.data)
+        tcw[j] = T.reshape(4, 4)
+    sig = oracle_mod.orb_tables(2000, 1.2, 8)["inv_sigma2"]
+    octave = np.argmin(np.abs(sig[None, :] - d["edge_info"].astype(np.float32)[:, None]), axis=1).astype(np.int32)
+    w = dict(kf_id=np.array([k * 2 for k in order], np.int32), kf_tcw=tcw, covisible=np.arange(1, K, dtype=np.int32), fx=d["fx"], fy=d["fy"], cx=d["cx"], cy=d["cy"],
+             bf=d["bf"], inv_level_sigma2=sig, mp_id=np.arange(len(d["points"]), dtype=np.int32) * 3 + 1, mp_pos=d["points"].astype(np.float32),
+             obs_kf=np.array([pos[k] for k in d["edge_pose"]], np.int32), obs_mp=d["edge_point"].astype(np.int32), obs_uvr=d["edge_obs"].astype(np.float32),
+             obs_octave=octave)
+    r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, w)
+    prob = r["problem"]
+    assert len(prob["edge_pose"]) == 120000 and len(r["pose_id"]) == 50 and len(r["point_id"]) == 20000
+    p, res, st = oracle_mod.ba_solve(prob)
+    tr = res.trace_rows[:, [0, 1, 2, 4]]
+    assert st == 0 and tr.shape == r["rows"].shape and (tr == r["rows"]).all()
+    assert (np.concatenate([p["pose_q"].ravel(), p["pose_t"].ravel(), p["points"].ravel()]) == r["final_state"]).all()
+    assert int(res.edge_outlier.sum()) == len(r["erased"]) > 1000
