@@ -99,8 +99,9 @@ def make_human_window(c):
     touch them are skipped).  Trajectories of 3 poses are not longer than Map::thLongTrajectory and are left out by the function."""
     import oracle
     from airdos_b200 import synth
-    seed, n_kf, n_pts, n_fixed, H, S, n_displaced, outside = HBA_CASES[c]
-    d = synth.make_ba_problem(n_kf, n_pts, 5, seed=seed, mono_frac=0.0, n_fixed_extra=n_fixed, humans=H, human_poses=S)
+    seed, n_kf, n_pts, n_fixed, H, S, n_displaced, outside = HBA_CASES[c][:8]
+    obs_per_point = HBA_CASES[c][8] if len(HBA_CASES[c]) > 8 else 5
+    d = synth.make_ba_problem(n_kf, n_pts, obs_per_point, seed=seed, mono_frac=0.0, n_fixed_extra=n_fixed, humans=H, human_poses=S)
     d["edge_obs"][:, 2] = np.where(d["edge_obs"][:, 2] < 0, 0.25, d["edge_obs"][:, 2])
     rng = np.random.default_rng(seed + 500)
     for j in rng.choice(len(d["joints"]), n_displaced, replace=False):

@@ -284,3 +284,26 @@ def test_reference_function_at_baseline_config4_size(oracle_mod):
     assert st == 0 and tr.shape == r["rows"].shape and (tr == r["rows"]).all()
     assert (np.concatenate([p["pose_q"].ravel(), p["pose_t"].ravel(), p["points"].ravel()]) == r["final_state"]).all()
     assert int(res.edge_outlier.sum()) == len(r["erased"]) > 1000
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree / oracle/_ref not present (GPU box)")
+def test_reference_dynamic_function_at_baseline_config5_size(oracle_mod):
+    """BASELINE.json configs[4] (80 key-frames, 30 000 map points, 180 000 stereo edges, 16 skeletons = 4 trajectories x 4 poses: 224 joints,
+    56 bone lengths, 4 motions): the reference's own LocalBundleAdjustmentHumanTrajactory run live against ba_oracle_solve."""
+    import ctypes as C
+    g = _gen()
+    LM = C.CDLL(os.path.join(REF, "libref_lm.so")); LBA = C.CDLL(os.path.join(REF, "libref_lba.so"))
+    g.HBA_CASES.append((5000, 80, 30000, 0, 4, 4, 3, False, 6))
+    w, hum = g.make_human_window(len(g.HBA_CASES) - 1)
+    r = oracle_mod.ref_local_bundle_adjustment(LBA, LM, w, humans=hum)
+    prob = r["problem"]
+    assert (len(prob["edge_pose"]), len(r["joint_id"]), len(r["dist_id"]), len(r["motion_id"])) == (180000, 224, 56, 4)
+    assert (len(prob["jedge_pose"]), len(prob["redge_i"]), len(prob["medge_p1"])) == (224, 224, 60)
+    p, res, st = oracle_mod.ba_solve(prob, g.hba_options(oracle_mod, r))
+    tr = res.trace_rows[:, [0, 1, 2, 4]]
+    assert st == 0 and tr.shape == r["rows"].shape and (tr == r["rows"]).all()
+    state = np.concatenate([p[k].ravel() for k in ("pose_q", "pose_t", "points", "joints", "dists", "motion_q", "motion_t")])
+    assert (state == r["final_state"]).all()
+    kind, chi, dep = r["edge_kind"], r["edge_final_chi2"], r["edge_final_depth_positive"]
+    assert (res.edge_outlier == ((chi > 7.815) | (dep == 0))[kind == 1]).all() and (res.jedge_outlier == ((chi > 7.815) | (dep == 0))[kind == 2]).all()
+    assert (res.redge_outlier == (chi > 1.0)[kind == 3]).all() and (res.medge_outlier == (chi > 4.0)[kind == 4]).all()
