@@ -951,7 +951,7 @@ __device__ inline bool chol6_solve(const double* H, double lambda, const double*
 __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A, double* __restrict__ chi_scratch, uint8_t* __restrict__ lvl_scratch) {
     __shared__ double scratch[(kPoseThreads / 32) * 28], red[28];
     __shared__ double sq[4], st[3], tq[4], tt[3], sH[36], sb[6];
-    __shared__ double s_lambda, s_ni, s_current, s_rho;
+    __shared__ double s_lambda, s_ni, s_current, s_rho, s_den;
     __shared__ int s_flag, s_nbad_it, s_q;
     const int f = blockIdx.x, tid = threadIdx.x;
     const int a = A.frame_ptr[f], n = A.frame_ptr[f + 1] - a;
@@ -1040,7 +1040,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
                         else { for (int k = 0; k < 4; ++k) tq[k] = sq[k]; for (int k = 0; k < 3; ++k) tt[k] = st[k]; }
                         double scale = 0;
                         if (ok) for (int k = 0; k < 6; ++k) scale += x[k] * (s_lambda * x[k] + sb[k]);
-                        s_rho = scale + 1e-3;      // denominator, completed below
+                        s_den = scale + 1e-3;      // denominator of rho (its own word: the other threads may still be reading s_rho of the previous trial)
                         s_flag = ok ? 1 : 0;
                     }
                     __syncthreads();
@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseArgs A,
                     double temp = evaluate(qq, tt2);
                     if (tid == 0) {
                         if (!s_flag) temp = DBL_MAX;
-                        const double rho = (s_current - temp) / s_rho;
+                        const double rho = (s_current - temp) / s_den;
                         if (rho > 0 && isfinite(temp)) {
                             double alpha = 1. - pow((2 * rho - 1), 3.0);
                             alpha = fmin(alpha, 2. / 3.);

@@ -108,6 +108,7 @@ __device__ __forceinline__ bool factor_chain(TileSmem& T, int jb, int lane) {
         for (int u = p + 1; u < kCholSB; ++u) r[u] = fma(-t, L[u][p], r[u]);
         if (lane == 0) T.isd[j0 + p] = isd;
     }
+    __syncwarp();   // lanes j0 .. j0 + 7 overwrite the rows every lane read above (racecheck: write-after-read inside the warp)
 #pragma unroll
     for (int p = 0; p < kCholSB; ++p) { T.Tb[lane][j0 + p] = r[p]; T.Vb[jb & 1][lane][p] = r[p]; }
     return bad;
