@@ -323,7 +323,11 @@ __global__ void __launch_bounds__(kDistinctThreads) distinctive_kernel(const uin
     __shared__ int s_best;               // median << 8 | row, reduced with atomicMin
     const int p = blockIdx.x, tid = threadIdx.x;
     const int a = point_ptr[p], N = point_ptr[p + 1] - a;
-    if (N <= 0) { if (tid == 0) best_idx[p] = -1; return; }
+    if (N <= 0) {   // a point nobody observes (src/MapPoint.cc:259 returns before touching mDescriptor): index -1, the caller keeps its descriptor; the slot is zeroed
+        if (tid == 0) best_idx[p] = -1;
+        if (best_desc && tid < 32) best_desc[(size_t)p * 32 + tid] = 0;
+        return;
+    }
     if (tid == 0) s_best = INT_MAX;
     for (int e = tid; e < N * N; e += kDistinctThreads) {
         const int i = e / N, j = e - i * N;
@@ -498,10 +502,15 @@ adb_status adb_stereo_match_range(adb_orb* L, adb_orb* R, int f0, int n, float m
     const size_t per = (size_t)L->cfg.max_batch * L->capacity;
     if (!L->d_uright) {
         ADB_CUDA(cudaMalloc(&L->d_uright, per * 4));
+        ADB_CUDA(cudaMemset(L->d_uright, 0, per * 4));   // slots past a frame's count travel to the host with the row
         ADB_CUDA(cudaMalloc(&L->d_depth, per * 4));
+        ADB_CUDA(cudaMemset(L->d_depth, 0, per * 4));
         ADB_CUDA(cudaMalloc(&L->d_best_idx, per * 4));
+        ADB_CUDA(cudaMemset(L->d_best_idx, 0, per * 4));
         ADB_CUDA(cudaMalloc(&L->d_best_dist, per * 4));
+        ADB_CUDA(cudaMemset(L->d_best_dist, 0, per * 4));
         ADB_CUDA(cudaMalloc(&L->d_sad, per * 4));
+        ADB_CUDA(cudaDeviceSynchronize());   // the fills above run on the legacy stream; the handles' streams do not wait for it
     }
     StereoLevels sl;
     memset(&sl, 0, sizeof(sl));

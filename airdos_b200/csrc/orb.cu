@@ -1399,6 +1399,9 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     for (int l = 0; l < nl; ++l) {
         LevelHost& lh = h->lv[l];
         ADB_CUDA(cudaMalloc(&lh.img, (size_t)B * lh.d.frame_stride));
+        // the kernels load whole aligned words, so they touch the pitch padding right of column w - 1 (never selected into a
+        // result): give those bytes a defined value once, at provisioning time (compute-sanitizer initcheck)
+        ADB_CUDA(cudaMemset(lh.img, 0, (size_t)B * lh.d.frame_stride));
         if (l > 0) {
             std::vector<int2> cx, cy;
             linear_coeffs(h->lv[l - 1].d.w, lh.d.w, cx);
@@ -1455,6 +1458,9 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
     ADB_CUDA(cudaMemset(h->d_status, 0, 4));
     ADB_CUDA(cudaMalloc(&h->d_kps, (size_t)B * h->capacity * sizeof(adb_keypoint)));
     ADB_CUDA(cudaMalloc(&h->d_desc, (size_t)B * h->capacity * 32));
+    // the downloads move whole capacity rows without waiting for the counts: slots past a frame's count must not carry stale device memory
+    ADB_CUDA(cudaMemset(h->d_kps, 0, (size_t)B * h->capacity * sizeof(adb_keypoint)));
+    ADB_CUDA(cudaMemset(h->d_desc, 0, (size_t)B * h->capacity * 32));
     ADB_CUDA(cudaMalloc(&h->d_counts, (size_t)B * 4));
     ADB_CUDA(cudaMemset(h->d_counts, 0, (size_t)B * 4));
     ADB_CUDA(cudaMallocHost(&h->h_counts, (size_t)B * 4));
@@ -1464,6 +1470,7 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
         const LevelDev& d = h->lv[l].d;
         const size_t bp = (size_t)((d.w + 15) & ~15);
         ADB_CUDA(cudaMalloc(&h->lv[l].blur, (size_t)B * bp * d.h));
+        ADB_CUDA(cudaMemset(h->lv[l].blur, 0, (size_t)B * bp * d.h));
         adb_status s = encode_tma_u8_3d(&h->blur_maps.m[l], h->lv[l].blur, d.w, d.h, B, bp, bp * d.h, kPatchBoxW, kBlBoxH);
         if (s != ADB_OK) return s;
         BlurLevels& bl = h->blur_levels;
@@ -1493,15 +1500,21 @@ static adb_status create_impl(const adb_orb_config* cfg, adb_orb* h) {
             ADB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
     ADB_CUDA(cudaFuncSetAttribute(orient_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem) + 128));
+    ADB_CUDA(cudaDeviceSynchronize());   // the provisioning fills ran on the legacy stream; the handle's own stream does not wait for it
     return ADB_OK;
 }
 
 static adb_status ensure_mask_buffers(adb_orb* h) {
     for (auto& l : h->lv)
-        if (!l.mask) ADB_CUDA(cudaMalloc(&l.mask, (size_t)h->cfg.max_batch * l.d.mframe_stride));
+        if (!l.mask) {
+            ADB_CUDA(cudaMalloc(&l.mask, (size_t)h->cfg.max_batch * l.d.mframe_stride));
+            ADB_CUDA(cudaMemset(l.mask, 0, (size_t)h->cfg.max_batch * l.d.mframe_stride));   // pitch padding, as for the image levels
+        }
     if (!h->mask_stage) {   // host-buffer calls: the caller's masks land here before the erosion (kept for the life of the handle)
         const size_t p0 = (size_t)((h->cfg.width + 15) & ~15);
         ADB_CUDA(cudaMalloc(&h->mask_stage, (size_t)h->cfg.max_batch * p0 * h->cfg.height));
+        ADB_CUDA(cudaMemset(h->mask_stage, 0, (size_t)h->cfg.max_batch * p0 * h->cfg.height));
+        ADB_CUDA(cudaDeviceSynchronize());
     }
     return ADB_OK;
 }

@@ -705,6 +705,7 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
             m->scratch_bytes = 0;
             const size_t want = total + total / 4;
             ADB_CUDA(cudaMalloc(&m->d_scratch, want));
+            ADB_CUDA(cudaMemsetAsync(m->d_scratch, 0, want, m->stream));   // alignment gaps and device-only work arrays sit inside the downloaded range
             ADB_CUDA(cudaMallocHost(&m->h_scratch, want));
             m->scratch_bytes = want;
         }
@@ -817,6 +818,7 @@ adb_status adb_search_by_bow(adb_matcher_t m, adb_bow_search* probs, int32_t n) 
             m->scratch_bytes = 0;
             const size_t want = total + total / 4;
             ADB_CUDA(cudaMalloc(&m->d_scratch, want));
+            ADB_CUDA(cudaMemsetAsync(m->d_scratch, 0, want, m->stream));   // alignment gaps and device-only work arrays sit inside the downloaded range
             ADB_CUDA(cudaMallocHost(&m->h_scratch, want));
             m->scratch_bytes = want;
         }
