@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) erode10_tile_kernel(const uint8_t* __rest
     const int x0 = blockIdx.x * kErTW, y0 = blockIdx.y * kErTH, f = blockIdx.z;
     const uint8_t* sp = src + (size_t)f * sfstride;
     const bool aligned = (((uintptr_t)sp | (uintptr_t)spitch) & 3) == 0;
+    int mixed = 0;                                                  // bit 0: a word that is not all 255, bit 1: a word that is not all 0
     for (int i = threadIdx.x; i < IWW * IH; i += 256) {
         const int r = i / IWW, cw = i - r * IWW, yy = y0 - kErR0 + r, xx = x0 - 8 + 4 * cw;
         uint32_t v = 0xFFFFFFFFu;                                   // outside the image = 255 (cv::erode's border value)
@@ -186,8 +187,15 @@ __global__ void __launch_bounds__(256) erode10_tile_kernel(const uint8_t* __rest
             }
         }
         tile[r][cw] = v;
+        mixed |= (v != 0xFFFFFFFFu ? 1 : 0) | (v != 0u ? 2 : 0);
     }
-    __syncthreads();
+    // A constant input tile (halo included: a superset of every window of the tile) erodes to the same constant.  Segmentation masks
+    // are 255 almost everywhere (src/Frame.cc:551-571: 0 only on the person), so most tiles leave here with one load and one store pass.
+    const bool not255 = __syncthreads_or(mixed & 1) != 0;           // (the barrier the row pass needs anyway; the vote is a logical OR, one per bit)
+    const bool not0 = __syncthreads_or(mixed & 2) != 0;
+    const bool constant = !(not255 && not0);
+    const uint32_t cval = not255 ? 0u : 0xFFFFFFFFu;
+    if (!constant) {                                                // block-uniform: the barriers inside are reached by all or none
     const uint8_t* tb = reinterpret_cast<const uint8_t*>(&tile[0][0]);
     uint8_t* rb = reinterpret_cast<uint8_t*>(&rmin[0][0]);
     // rows: a thread owns a run of 16 outputs of one row (8 runs per row, 41 rows = 328 runs)
@@ -215,13 +223,14 @@ __global__ void __launch_bounds__(256) erode10_tile_kernel(const uint8_t* __rest
         for (int k = 0; k < kErRun; ++k) ob[(size_t)(r0 + k) * (kErTW / 4 + 1) * 4 + c] = (uint8_t)o[k];
     }
     __syncthreads();
+    }
     // store: 32 x 32 words per tile, coalesced; byte-wise only at a ragged right edge or an unaligned destination
     uint8_t* dp = dst + (size_t)(f0 + f) * dfstride;
     const bool daligned = (((uintptr_t)dp | (uintptr_t)dpitch) & 3) == 0;
     for (int i = threadIdx.x; i < kErTH * (kErTW / 4); i += 256) {
         const int r = i / (kErTW / 4), cw = i - r * (kErTW / 4), y = y0 + r, x = x0 + 4 * cw;
         if (y >= h || x >= w) continue;
-        const uint32_t v = outt[r][cw];
+        const uint32_t v = constant ? cval : outt[r][cw];
         if (daligned && x + 3 < w) *reinterpret_cast<uint32_t*>(dp + (size_t)y * dpitch + x) = v;
         else for (int k = 0; k < 4 && x + k < w; ++k) dp[(size_t)y * dpitch + x + k] = (uint8_t)(v >> (8 * k));
     }

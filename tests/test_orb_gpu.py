@@ -104,6 +104,29 @@ def test_ini_min_rule_both_ends_of_the_slot(adb, oracle_mod, ini, mn):
     ex.close()
 
 
+def test_erosion_constant_tile_path_and_general_values(adb, oracle_mod):
+    """cv::erode(mask, ones(10, 10)) (src/ORBextractor.cc:1130-1131): the level-0 mask the extractor keeps equals the oracle's erosion
+    byte for byte -- for masks whose 128 x 32 tiles are all constant (all 255, all 0: the kernel's load-and-store-only path), for
+    rectangles (constant and mixed tiles side by side, borders where the outside counts as 255), for single zero pixels next to
+    tile seams and image corners, and for a grey-valued noise mask (no constant tile, a true minimum rather than an AND)."""
+    from airdos_b200 import synth
+    w, h = 640, 480
+    img = synth.make_stereo_pair(35, w, h)[0]
+    rng = np.random.default_rng(36)
+    dots = np.full((h, w), 255, np.uint8)
+    for y, x in ((0, 0), (h - 1, w - 1), (31, 127), (32, 128), (36, 133), (250, 383), (251, 384), (479, 0), (5, 639)):
+        dots[y, x] = 0
+    big = np.full((h, w), 255, np.uint8); big[40:420, 100:560] = 0                   # holds whole all-zero tiles, halo included
+    masks = [np.full((h, w), 255, np.uint8), np.zeros((h, w), np.uint8), synth.make_mask(37, w, h, 3), big, dots,
+             rng.integers(0, 256, (h, w), dtype=np.uint8), synth.make_human_mask(38, w, h)]
+    ex = adb.ORBextractor(800, 1.2, 8, 20, 7, w, h)
+    for i, m in enumerate(masks):
+        ex(img, m)
+        got = ex.pyramid(0, which=1)[0]
+        assert got.shape == (h, w) and (got == oracle_mod.erode10(m)).all(), i
+    ex.close()
+
+
 def test_cta_per_cell_fallback_kernel_agrees(adb, oracle_mod, monkeypatch):
     """ADB_FAST_CTA=1 selects the CTA-per-cell FAST kernel (the path for cells wider than the warp kernel's three column tiles)."""
     from airdos_b200 import synth
