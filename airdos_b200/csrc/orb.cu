@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
         cp[t] = smem_u32(tile) + 3 * kBW + (iniX & 15) + 3 + min(col, iw - 1);
     }
     // NMS of the row above the one just scored (z = its scores; zlow for the flush step) and ordered emission of the kept corners
-    auto nms_emit = [&](const int t, const uint32_t z, const int yr) {
+    // (mv: single-tile instance only -- this lane's mask byte of row yr, loaded at the top of the row step; the wide-cell instance reads it on demand)
+    auto nms_emit = [&](const int t, const uint32_t z, const int yr, const uint32_t mv) {
         const uint32_t v = zB[t], vert = max(zA[t], z);
         const uint32_t c3 = max(vert, v);
         uint32_t cl = __shfl_up_sync(0xFFFFFFFFu, c3, 1), cr = __shfl_down_sync(0xFFFFFFFFu, c3, 1);
@@ -529,7 +530,10 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
         if (lane == 31) cr = 0;
         bool keep = decide[t] && v > max(max(cl, cr), vert);
         zA[t] = v; zB[t] = z;
-        if (kMasked) { if (keep) keep = ml[(size_t)yr * mpitch + t * kFwStep] != 0; }
+        if (kMasked) {
+            if (NT == 1) keep = keep && mv != 0;
+            else if (keep) keep = ml[(size_t)yr * mpitch + t * kFwStep] != 0;
+        }
         const uint32_t balK = __ballot_sync(0xFFFFFFFFu, keep);
         if (balK) {
             const bool isA = keep && v >= zini;
@@ -552,8 +556,14 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
             rawp += kBW;
         };
         for (int r = 0; r < 6; ++r) convert_row(ring0 + (uint32_t)r * (kRingPitch * 4));
+        // masked: the mask byte under this lane's column of row y - 1 (the row nms_emit decides) is loaded unconditionally at the top of the
+        // step and used ~100 instructions later -- one LDG and a pointer increment per row instead of a divergent branch around an on-demand
+        // load in each of the nine inlined emitters (+16 % warp instructions).  Lanes right of the cell read its last column (never decided).
+        const uint8_t* mrow = kMasked ? ml - lane + min(lane, iw - 1) - mpitch : nullptr;
         auto step = [&](auto jc, const int y) {
             constexpr int J = decltype(jc)::value;
+            uint32_t mv = 1;
+            if (kMasked) { mv = *mrow; mrow += (uint32_t)mpitch; }
             convert_row(ring0 + ((J + 6) & 7) * (kRingPitch * 4));                             // box row y + 6, the last one row y needs
             __syncwarp();
             const uint32_t v = lds_u8<((J + 3) & 7) * kRingPitch * 4>(rb);                    // low byte of the centre word
@@ -561,7 +571,7 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
             load_ring_words<J>(rb, ring);
             const uint32_t r = fast_best_packed(ring) + v * 0xFFFFu;                           // halves: A + 256 - v, (255 - B) + 1 + v
             const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[0]);
-            nms_emit(0, z, y - 1);
+            nms_emit(0, z, y - 1, mv);
         };
         for (int y0 = 0; y0 < ih; y0 += 8) {
 #define ADB_STEP(J) if (y0 + J >= ih) break; step(std::integral_constant<int, J>{}, y0 + J);
@@ -578,14 +588,14 @@ __global__ void __launch_bounds__(kFwWarps * 32, NT == 1 ? 6 : 4) fast_cells_war
                 const uint32_t r = fast_best_packed(ring);
                 const uint32_t z = min(max(max(r & 0xFFFFu, r >> 16), zlow), zcap[t]);
                 cp[t] += kBW;
-                nms_emit(t, z, y - 1);
+                nms_emit(t, z, y - 1, 1u);
             }
         }
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         if (t > 0 && t >= nt) break;
-        nms_emit(t, zlow, ih - 1);
+        nms_emit(t, zlow, ih - 1, (kMasked && NT == 1) ? (uint32_t)ml[(ptrdiff_t)(ih - 1) * mpitch + (min(lane, iw - 1) - lane)] : 1u);
     }
     const int cntA = (int)(idxA - slot0), cntB = (int)(slot0 + (uint32_t)L.slotcap - 1u - idxB);
     if (lane == 0) *cnt_out = (uint16_t)(cntA ? cntA : (cntB ? (cntB | 0x8000) : 0));
