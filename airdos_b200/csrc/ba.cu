@@ -1780,6 +1780,7 @@ adb_status adb_pose_optimize(adb_ba_t s, adb_pose_problem* P) {
     ADB_CUDA(cudaSetDevice(s->device));
     const int F = P->n_frames, n = P->frame_ptr[F];
     ADB_CHECK(n >= 0 && P->frame_ptr[0] == 0, ADB_ERR_INVALID, "bad frame_ptr");
+    for (int f = 0; f < F; ++f) ADB_CHECK(P->frame_ptr[f + 1] >= P->frame_ptr[f], ADB_ERR_INVALID, "frame_ptr is not monotone at %d", f);
     cudaStream_t st = s->stream;
     // reuse BA buffers as scratch: e_pose = frame_ptr, pq/pt[0] = poses, e_obs = xw | obs | inv_sigma2 (float), chi_e[0], flag, e_level, off_pose = n_inliers
     adb_status r;

@@ -425,6 +425,13 @@ adb_status adb_match_best2(adb_matcher_t m, const uint8_t* q, int32_t nq, const 
                            const int32_t* cand_idx, int32_t* best_idx, int32_t* best_d, int32_t* second_d) {
     ADB_CHECK(m && best_idx && best_d && second_d, ADB_ERR_INVALID, "null argument");
     if (nq <= 0) return ADB_OK;
+    ADB_CHECK(nt >= 0 && (!cand_off || cand_idx), ADB_ERR_INVALID, "bad sizes");
+    if (cand_off) {   // candidate lists index the train descriptors on the device: offsets monotone from 0, indices inside [0, nt)
+        ADB_CHECK(cand_off[0] == 0, ADB_ERR_INVALID, "cand_off must start at 0");
+        for (int i = 0; i < nq; ++i) ADB_CHECK(cand_off[i + 1] >= cand_off[i], ADB_ERR_INVALID, "cand_off is not monotone at %d", i);
+        for (int c = 0; c < cand_off[nq]; ++c)
+            ADB_CHECK(cand_idx[c] >= 0 && cand_idx[c] < nt, ADB_ERR_INVALID, "cand_idx[%d] = %d outside [0, %d)", c, cand_idx[c], nt);
+    }
     ADB_CUDA(cudaSetDevice(m->device));
     const int ncand = cand_off ? cand_off[nq] : 0;
     uint8_t *dq = nullptr, *dt = nullptr;
@@ -461,6 +468,7 @@ adb_status adb_distinctive_descriptors(adb_matcher_t m, const uint8_t* desc, con
     ADB_CHECK(m && point_ptr && best_idx, ADB_ERR_INVALID, "null argument");
     if (n_points <= 0) return ADB_OK;
     const int n = point_ptr[n_points];
+    ADB_CHECK(point_ptr[0] >= 0, ADB_ERR_INVALID, "point_ptr starts below 0");
     int maxN = 0;
     for (int p = 0; p < n_points; ++p) {
         ADB_CHECK(point_ptr[p + 1] >= point_ptr[p], ADB_ERR_INVALID, "point_ptr is not monotone at %d", p);

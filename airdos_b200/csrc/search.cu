@@ -624,6 +624,15 @@ adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* probs, int
                   "problem %d: last-frame projection inputs missing", p);
         ADB_CHECK(!s.check_orientation || s.q_angle || s.fuse, ADB_ERR_INVALID, "problem %d: q_angle missing", p);
         ADB_CHECK(!s.fuse || (s.mp_xw && s.inv_level_sigma2), ADB_ERR_INVALID, "problem %d: fuse needs the map-point inputs and inv_level_sigma2", p);
+        // level numbers that index the per-level tables on the device (a bad one from the shim must not read past them)
+        if (s.last_xw)
+            for (int i = 0; i < s.n_q; ++i)
+                ADB_CHECK(s.last_octave[i] >= 0 && s.last_octave[i] < s.n_levels, ADB_ERR_INVALID, "problem %d: last_octave[%d] = %d outside [0, %d)", p, i,
+                          s.last_octave[i], s.n_levels);
+        if (s.fuse)
+            for (int i = 0; i < s.n_kp; ++i)
+                ADB_CHECK(s.kps[i].octave >= 0 && s.kps[i].octave < s.n_levels, ADB_ERR_INVALID, "problem %d: key-point %d has octave %d outside [0, %d)", p, i,
+                          s.kps[i].octave, s.n_levels);
         max_nk = std::max(max_nk, s.n_kp); max_nq = std::max(max_nq, s.n_q);
     }
     // two passes over the same layout code: size, then copy
@@ -770,7 +779,18 @@ adb_status adb_search_by_bow(adb_matcher_t m, adb_bow_search* probs, int32_t n) 
         ADB_CHECK(s.mode == 0 || (s.f12 && s.scale_factors2 && s.level_sigma2_2 && s.n_levels > 0 && (s.n1 == 0 || s.u_right1) &&
                                   (s.n2 == 0 || (s.u_right2 && s.flags2))), ADB_ERR_INVALID, "problem %d: triangulation inputs missing", p);
         const int nq = s.n_buckets ? s.b_ptr1[s.n_buckets] : 0, nt = s.n_buckets ? s.b_ptr2[s.n_buckets] : 0;
-        ADB_CHECK(nq <= ADB_SEARCH_MAX && nt <= ADB_SEARCH_MAX, ADB_ERR_INVALID, "problem %d: bucket lists longer than the frames", p);
+        ADB_CHECK(nq >= 0 && nt >= 0 && nq <= ADB_SEARCH_MAX && nt <= ADB_SEARCH_MAX, ADB_ERR_INVALID, "problem %d: bucket lists longer than the frames", p);
+        ADB_CHECK(s.n_buckets == 0 || (s.b_ptr1[0] == 0 && s.b_ptr2[0] == 0), ADB_ERR_INVALID, "problem %d: bucket pointers must start at 0", p);
+        for (int b = 0; b < s.n_buckets; ++b)
+            ADB_CHECK(s.b_ptr1[b + 1] >= s.b_ptr1[b] && s.b_ptr2[b + 1] >= s.b_ptr2[b], ADB_ERR_INVALID, "problem %d: bucket pointers are not monotone at %d", p, b);
+        for (int a = 0; a < nq; ++a)
+            ADB_CHECK(s.b_idx1[a] >= 0 && s.b_idx1[a] < s.n1, ADB_ERR_INVALID, "problem %d: b_idx1[%d] = %d outside [0, %d)", p, a, s.b_idx1[a], s.n1);
+        for (int a = 0; a < nt; ++a)
+            ADB_CHECK(s.b_idx2[a] >= 0 && s.b_idx2[a] < s.n2, ADB_ERR_INVALID, "problem %d: b_idx2[%d] = %d outside [0, %d)", p, a, s.b_idx2[a], s.n2);
+        if (s.mode == 1)
+            for (int i = 0; i < s.n2; ++i)
+                ADB_CHECK(s.kps2[i].octave >= 0 && s.kps2[i].octave < s.n_levels, ADB_ERR_INVALID, "problem %d: key-point %d of side 2 has octave %d outside [0, %d)",
+                          p, i, s.kps2[i].octave, s.n_levels);
         for (int b = 0; b < s.n_buckets; ++b) {
             ADB_CHECK(s.b_ptr2[b + 1] - s.b_ptr2[b] <= 8191, ADB_ERR_INVALID, "problem %d: vocabulary node with more than 8191 features", p);
             for (int a = s.b_ptr1[b]; a < s.b_ptr1[b + 1]; ++a) qb[p].push_back(b);

@@ -264,7 +264,9 @@ typedef struct adb_proj_search {
     int32_t n_matches;             /* return value of the reference function */
 } adb_proj_search;
 #define ADB_SEARCH_MAX 8192
-/* Runs n_problems independent searches (one thread block each). */
+/* Runs n_problems independent searches (one thread block each).  Sizes, required pointers and every number that indexes a
+ * per-level table on the device (last_octave; the key-points' octaves when fuse != 0) are checked on the host first:
+ * ADB_ERR_INVALID, nothing launched. */
 adb_status adb_search_by_projection(adb_matcher_t m, adb_proj_search* problems, int32_t n_problems);
 /* Device time in ms of the kernels of the last adb_search_by_projection call. */
 adb_status adb_search_last_ms(adb_matcher_t m, float* ms);
@@ -311,6 +313,8 @@ typedef struct adb_bow_search {
     int32_t* match12;              /* mode 1, [n1]: vMatches12 (index in side 2 or -1) */
     int32_t n_matches;
 } adb_bow_search;
+/* The bucket pointers (start at 0, monotone), the bucket indices (inside [0, n1) / [0, n2)) and, in mode 1, the octaves of side 2
+ * (inside [0, n_levels)) are checked on the host first: ADB_ERR_INVALID, nothing launched. */
 adb_status adb_search_by_bow(adb_matcher_t m, adb_bow_search* problems, int32_t n_problems);
 
 /* Frame::ComputeStereoMatches()  (src/Frame.cc:829-1003) for the n_frames frames resident in

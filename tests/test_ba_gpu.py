@@ -187,7 +187,10 @@ def test_local_ba_against_the_reference_function(opt):
     """adb_ba_solve against tests/golden/lba_ref.npz = the reference's own Optimizer::LocalBundleAdjustment (src/Optimizer.cc:431-731, whole
     function compiled from /root/reference: oracle/ref_lba.cpp) on five covisibility windows: the problems are the ones that function
     built; the erase list (outlier flags) must be identical, every LM trial must take the same accept / reject decision with lambda and
-    chi2 within 1e-6 relative, the final estimates within 1e-9, and the poses written back through the converter (float 4 x 4) equal."""
+    chi2 within 1e-6 relative, the final estimates within 1e-7, and the poses written back through the converter (float 4 x 4) equal.
+    (1e-7, not tighter: the Schur complement and chi2 are accumulated with FP64 atomics, so the summation order -- and with it the last
+    bits of every LM step -- changes from run to run; over 15 iterations the weakest-constrained points of a window moved by up to 1.7e-9
+    between otherwise identical runs (gpurun_out/r2l).  The north-star bar is 1e-4.)"""
     import os
     from airdos_b200 import ba
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -206,7 +209,7 @@ def test_local_ba_against_the_reference_function(opt):
         assert np.allclose(tg[:, :3], rows[:, :3], rtol=1e-6), i
         assert list(rg.c.iterations_run) == list(gold[f"w{i}_round_iterations"])
         state = np.concatenate([pg["pose_q"].ravel(), pg["pose_t"].ravel(), pg["points"].ravel()])
-        assert np.abs(state - gold[f"w{i}_final_state"]).max() < 1e-9, i
+        assert np.abs(state - gold[f"w{i}_final_state"]).max() < 1e-7, (i, float(np.abs(state - gold[f"w{i}_final_state"]).max()))
         # the erase list: (key-frame, map point) pairs in the reference's order, rebuilt from the outlier flags
         assert (helper.erase_list_from_flags(gold, i, rg.edge_outlier) == gold[f"w{i}_erased"]).all(), i
         # written-back poses of the free key-frames

@@ -36,6 +36,13 @@ def test_best2_all_pairs_lists_ties_and_empty(adb, oracle_mod):
     perm = rng.permutation(len(t))
     bi, bd, _ = m.best2(t[perm], t)
     assert (bd == 0).all() and (t[bi] == t[perm]).all()
+    # candidate lists index the train descriptors on the device: an index outside [0, nt) or a non-monotone offset is refused
+    bad_idx = idx.copy(); bad_idx[11] = len(t)
+    bad_off = off.copy(); bad_off[5] = bad_off[6] + 1
+    for o, i in ((off, bad_idx), (bad_off, idx)):
+        with pytest.raises(adb.AdbError) as e:
+            m.best2(q, t, o, i)
+        assert e.value.status == 1
     m.close()
 
 

@@ -95,6 +95,37 @@ def test_fuse_candidate_search_on_device(adb, oracle_mod):
     m.close()
 
 
+def test_bad_level_numbers_and_bucket_indices_are_refused(adb):
+    """Numbers from the shim that index device tables are range-checked on the host (ADB_ERR_INVALID, nothing launched): the last frame's
+    octaves and the KeyFrame's octaves of Fuse index the per-level tables; the vocabulary bucket lists index the key-point arrays."""
+    m = adb.ORBmatcher(0.9, True)
+    pr = synth.make_tracking_problem(60, n_kp=600, n_q=500)
+    for bad in (-1, len(pr["scale_factors"])):
+        q = dict(pr); q["last_octave"] = np.array(pr["last_octave"], np.int32).copy(); q["last_octave"][7] = bad
+        with pytest.raises(adb.AdbError) as e:
+            m.SearchByProjection(q)
+        assert e.value.status == 1
+    pf = synth.tracking_problem_as_fuse(synth.make_tracking_problem(61, n_kp=600, n_q=800), seed=61, th=3.0)
+    pf["kps"] = pf["kps"].copy(); pf["kps"]["octave"][3] = len(pf["scale_factors"])
+    with pytest.raises(adb.AdbError) as e:
+        m.search_by_projection([pf])
+    assert e.value.status == 1
+    for mode, key, val in ((0, "b_idx1", 10 ** 6), (0, "b_idx2", -1), (1, "b_idx2", 10 ** 6)):
+        pb = synth.make_bow_problem(62, mode, n1=700, n2=800, n_nodes=80)
+        pb[key] = np.array(pb[key], np.int32).copy(); pb[key][5] = val
+        with pytest.raises(adb.AdbError) as e:
+            m.search_by_bow([pb])
+        assert e.value.status == 1
+    pb = synth.make_bow_problem(63, 0, n1=700, n2=800, n_nodes=80)
+    pb["b_ptr1"] = np.array(pb["b_ptr1"], np.int32).copy(); pb["b_ptr1"][3] = pb["b_ptr1"][4] + 1      # not monotone
+    with pytest.raises(adb.AdbError) as e:
+        m.search_by_bow([pb])
+    assert e.value.status == 1
+    # the matcher is still usable afterwards
+    assert m.SearchByProjection(pr)[0] > 0
+    m.close()
+
+
 @pytest.mark.parametrize("mode", [0, 1], ids=["SearchByBoW", "SearchForTriangulation"])
 def test_bow_searches_on_device(adb, oracle_mod, mode):
     m = adb.ORBmatcher(0.7, True)
