@@ -190,7 +190,8 @@ def test_local_ba_against_the_reference_function(opt):
     chi2 within 1e-6 relative, the final estimates within 1e-7, and the poses written back through the converter (float 4 x 4) equal.
     (1e-7, not tighter: the Schur complement and chi2 are accumulated with FP64 atomics, so the summation order -- and with it the last
     bits of every LM step -- changes from run to run; over 15 iterations the weakest-constrained points of a window moved by up to 1.7e-9
-    between otherwise identical runs (gpurun_out/r2l).  The north-star bar is 1e-4.)"""
+    between otherwise identical runs (gpurun_out/r2l); tools/ba_noise_sensitivity.py reproduces the amplification with the oracle on the CPU
+    (1-ulp input noise -> up to 2.5e-9 on windows 0 and 4).  The north-star bar is 1e-4.)"""
     import os
     from airdos_b200 import ba
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
