@@ -84,13 +84,13 @@ def run(device: int = 0, steps: int = 5, with_cpu: bool = True, n_kf: int = 50, 
     gf = nd ** 3 / 3 / (solve_ms * 1e-3) / 1e9
     out["roofline"] = {"bound": "hbm", "kernel": "ba_point/pose_linearize + ba_schur_block + ba_backsub + ba_eval", "achieved": alg / (sparse_ms * 1e-3) / 1e9,
                        "peak": peak, "unit": "GB/s", "frac": alg / (sparse_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src,
-                       "note": "L2-resident after the first trial (DRAM traffic per trial is a fraction of the algorithmic bytes: profiles/r2_*): latency / L2 bound, not HBM bound",
+                       "note": "L2-resident after the first trial (DRAM traffic per trial is a fraction of the algorithmic bytes: profiles/r2c_ncu_full_summary.csv, ba_* rows): latency / L2 bound, not HBM bound",
                        "reduced_solve": {"kernel": "chol_cluster_kernel (one launch, one cluster)", "n": nd, "cluster_ctas": cluster, "ms_per_trial": solve_ms,
                                          "bound": "tensor (FP64 DMMA m8n8k4)", "achieved": gf, "unit": "GFLOP/s",
                                          "peak_cluster": DMMA_GFLOPS_PER_SM * cluster, "frac_of_cluster_peak": gf / (DMMA_GFLOPS_PER_SM * cluster),
                                          "peak_chip": DMMA_GFLOPS_PER_SM * 148, "frac_of_chip_peak": gf / (DMMA_GFLOPS_PER_SM * 148),
                                          "note": "n dependent pivots: the chain of 32x32 diagonal factorisations bounds the solve, not FLOP/s; tensor-pipe "
-                                                 "utilisation from ncu in profiles/r2_ncu_ba_summary.csv; cuSOLVER potrf+potrs on the same box: tools/chol_bench.py"}}
+                                                 "utilisation from ncu in profiles/r2c_ncu_full_summary.csv (chol_cluster_kernel rows: pipe_tensor_* columns); cuSOLVER potrf+potrs on the same box: tools/chol_bench.py, profiles/r2c_chol_vs_cusolver.jsonl"}}
     # parity on the reference's own 5 + 10 schedule, and the CPU baseline (oracle port, 1 thread like g2o without OpenMP)
     if with_cpu:
         import oracle

@@ -32,3 +32,20 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_roofline_traffic_comes_from_the_unmasked_capture():
+    """`roofline.traffic` is scaled from the committed ncu capture of the UNMASKED extractor kernels (profiles/r2c_dram_traffic.json),
+    never from whichever *_dram_traffic.json happens to be newest on disk (profiles/r2j_masked_* holds the masked instances under the same
+    kernel names: twice the DRAM bytes)."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    t, src = bench.dram_traffic("fast_cells_warp_kernel", 3072)
+    cap = json.load(open(os.path.join(ROOT, "profiles", bench.TRAFFIC_CAPTURE)))
+    assert src == "profiles/r2c_dram_traffic.json"
+    assert t == sum(e["dram_bytes"] for e in cap["fast_cells_warp_kernel"][:2]) / 128.0 * 3072
+    alg = 3072 * (950532 + 102400)          # one pyramid read + the candidate slots written, per frame (DESIGN.md section 4): same order
+    assert 0.5 * alg < t < 1.5 * alg
+    assert bench.dram_traffic("pyr_resize_strip_kernel", 3072) == (None, None)      # seven launches per call: not a per-launch figure
+    assert bench.dram_traffic("no_such_kernel", 3072) == (None, None)
