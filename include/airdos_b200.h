@@ -168,7 +168,8 @@ adb_status adb_matcher_destroy(adb_matcher_t m);
  * (src/ORBmatcher.cc:85-114, 216-225 and the other nine call sites): for query q the candidates
  * are targets cand_idx[cand_off[q] .. cand_off[q+1]) in list order (cand_off == NULL: all nt
  * targets 0..nt-1).  Update rule: strict '<', i.e. the first candidate in list order wins
- * ties.  Outputs start at best = second = 256, idx = -1.  Host buffers. */
+ * ties.  Outputs start at best = second = 256, idx = -1.  Host buffers.  The host variant checks the lists first (cand_off
+ * monotone from 0, every cand_idx inside [0, nt)): ADB_ERR_INVALID; the device variant trusts lists that are already in HBM. */
 adb_status adb_match_best2(adb_matcher_t m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt,
                            const int32_t* cand_off, const int32_t* cand_idx,
                            int32_t* best_idx, int32_t* best_d, int32_t* second_d);
@@ -181,7 +182,9 @@ adb_status adb_match_best2_device(adb_matcher_t m, const uint8_t* q_desc, int32_
  * descriptors of all observations, point p owning rows point_ptr[p] .. point_ptr[p+1]).  Per point the observation whose
  * sorted Hamming distances to all observations of the point (itself included) have the least median (element
  * 0.5 * (N - 1)) wins, the first one on ties.  best_idx[p] = index within the point's rows (-1: no observations);
- * best_desc (optional) receives the winning 32 bytes.  At most ADB_MAX_OBSERVATIONS rows per point.  Host buffers. */
+ * best_desc (optional) receives the winning 32 bytes (32 zero bytes for a point without observations: the reference returns
+ * before touching mDescriptor, src/MapPoint.cc:259, so the caller keeps its old descriptor when best_idx[p] is -1).
+ * At most ADB_MAX_OBSERVATIONS rows per point.  Host buffers. */
 #define ADB_MAX_OBSERVATIONS 128
 adb_status adb_distinctive_descriptors(adb_matcher_t m, const uint8_t* desc, const int32_t* point_ptr, int32_t n_points,
                                        int32_t* best_idx, uint8_t* best_desc);
