@@ -39,9 +39,15 @@ def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     import airdos_b200 as adb
-    with pytest.raises(adb.AdbError) as e:
-        adb.ORBextractor(1000, 1.2, 8, 12, 7)
-    assert e.value.status == 2   # ADB_ERR_NO_DEVICE
+    from airdos_b200 import ba
+    # every way into the library fails loudly without a device: the lazily provisioned and the sized extractor, the matcher, the
+    # optimizer and the stand-alone dense solve -- none of them computes anything on the host
+    for make in (lambda: adb.ORBextractor(1000, 1.2, 8, 12, 7), lambda: adb.ORBextractor(1000, 1.2, 8, 12, 7, 640, 480),
+                 lambda: adb.ORBmatcher(), lambda: ba.Optimizer(), lambda: ba.dense_solve(np.eye(4), np.ones(4))):
+        with pytest.raises(adb.AdbError) as e:
+            make()
+        assert e.value.status == 2   # ADB_ERR_NO_DEVICE
+        assert "no CUDA device" in str(e.value)
 
 
 def test_product_package_never_imports_the_oracle():
