@@ -106,6 +106,33 @@ def dram_traffic(kernel: str, frames: int):
     return None, None
 
 
+ISSUE_CAPTURE = "r2c_ncu_full_summary.csv"
+
+
+def issue_roofline(kernel: str, frames: int, kernel_ms: float, sm_mhz, n_sms: int = 148):
+    """The bound that actually holds for the FAST kernel ("integer ALU is the realistic limiter for FAST -- report
+    both"): executed warp-instructions per second against the SMs' issue rate (4 schedulers x 1 warp-instruction per clock each).
+    The instruction count comes from the committed ncu capture (smsp__inst_executed.sum of the single-tile + the wide-cell instance at
+    128 frames per launch, profiles/r2c_ncu_full_summary.csv), the time is this run's.  -> dict, or None when the capture is missing."""
+    try:
+        import csv
+        rows = list(csv.reader(l for l in open(os.path.join(ROOT, "profiles", ISSUE_CAPTURE)) if not l.startswith("#")))
+        h = rows[0]
+        ki, wi, ai = h.index("kernel"), h.index("warp_instructions"), h.index("pipe_alu_pct")
+        mine = [r for r in rows[1:] if r[ki] == kernel][:2]
+        if not mine or not kernel_ms or kernel_ms <= 0:
+            return None
+        inst = sum(float(r[wi]) for r in mine) / 128.0 * frames
+        clk = float(sm_mhz) * 1e6 if sm_mhz else 1965e6
+        peak = n_sms * 4 * clk
+        return {"bound": "issue", "achieved": inst / (kernel_ms * 1e-3) / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s",
+                "frac": inst / (kernel_ms * 1e-3) / peak, "warp_instructions_per_launch": inst,
+                "alu_pipe_pct_in_capture": [float(r[ai]) for r in mine], "source": "profiles/" + ISSUE_CAPTURE,
+                "note": "instruction count from the committed ncu capture (128 frames per launch), time and clock from this run"}
+    except Exception:
+        return None
+
+
 def cpu_reference_run(pairs_arr, threads, steps, warmup):
     """Reference CPU path (oracle port) on the host cores: kp/s over `steps` passes of the sample.  The SAME routine serves the
     `cpu_baseline` leg of our arm and `--impl reference`: at least one full warm pass (thread pool, page faults, clocks), then
@@ -390,6 +417,7 @@ def main():
                         "tools/probe/pipe_probe.cu) + 17 LDS + 17 IMAD per 32 pixels of ~120 warp-instructions in all; the HBM fraction is "
                         "reported because the contract asks for it, DRAM traffic ~= algorithmic bytes (no re-reads)",
                 "kernel_ms": float(stage[dom]),
+                "issue_roofline": issue_roofline(names[dom].split("(")[0], P, float(stage[dom]), (clocks or {}).get("sm_mhz")),
                 "stage_ms": {n: float(s) for n, s in zip(names, stage)},
                 "pipeline_achieved_GBps": BYTES_PER_FRAME * 2 * P / (ms_step * 1e-3) / 1e9,
                 "pipeline_frac": BYTES_PER_FRAME * 2 * P / (ms_step * 1e-3) / 1e9 / peak}

@@ -49,3 +49,16 @@ def test_roofline_traffic_comes_from_the_unmasked_capture():
     assert 0.5 * alg < t < 1.5 * alg
     assert bench.dram_traffic("pyr_resize_strip_kernel", 3072) == (None, None)      # seven launches per call: not a per-launch figure
     assert bench.dram_traffic("no_such_kernel", 3072) == (None, None)
+
+
+def test_issue_roofline_of_the_fast_kernel():
+    """The secondary roofline of the dominant kernel (issue slots) is computed from the committed ncu capture and the
+    live stage time; a missing kernel or a zero time gives None, never an exception inside the bench."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.issue_roofline("fast_cells_warp_kernel", 3072, 11.2, 1965.0)
+    assert r["bound"] == "issue" and abs(r["peak"] - 148 * 4 * 1.965) < 1e-6
+    assert 0.6 < r["frac"] < 0.8 and abs(r["achieved"] / r["peak"] - r["frac"]) < 1e-12      # ncu: 70.7 % issue-active on the same kernel
+    assert bench.issue_roofline("fast_cells_warp_kernel", 3072, 11.2, None)["peak"] == r["peak"]        # nominal clock when nvidia-smi gave none
+    assert bench.issue_roofline("no_such_kernel", 3072, 11.2, 1965.0) is None
+    assert bench.issue_roofline("fast_cells_warp_kernel", 3072, 0.0, 1965.0) is None
