@@ -3,9 +3,10 @@
 The CUDA solver accumulates the Schur complement and chi2 with FP64 atomics, so the summation order -- and the last bits of every LM
 step -- differ from run to run.  This script measures the amplification the LM schedule applies to such noise: it re-solves every window
 of tests/golden/lba_ref.npz with the oracle after multiplying the initial points / translations by (1 + k * 2.2e-16), k in {-1, 0, 1},
-and prints the largest change of the final state.  The tolerances of tests/test_ba_gpu.py sit >= 14x above these numbers
+and prints the largest change of the final state.  The tolerances of tests/test_ba_gpu.py sit >= 30x above these numbers
 (static windows: up to 2.5e-9 -> 1e-7; articulated windows: 2.5e-11 -> 1e-7; global BA with a fixed key-frame: 6.5e-11 -> 1e-7;
-gauge-free global BA, 20 iterations: 7e-6 -> 1e-4 = the north-star bar).
+gauge-free global BA, 20 iterations: up to 3.4e-5 over 60 draws, all of it in a handful of far points -- quaternions 2e-9, translations
+1.3e-7 -- hence the per-block bars 1e-6 / 1e-5 / 1e-3 of that test).
 
 usage: PYTHONPATH=. python tools/ba_noise_sensitivity.py"""
 import importlib.util
