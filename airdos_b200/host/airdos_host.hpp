@@ -11,6 +11,7 @@
 // No computation happens here: every method forwards to libairdos_b200.so and throws
 // std::runtime_error on a non-OK status only where the reference would have asserted.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -167,6 +168,34 @@ public:
         return problem.n_matches;
     }
 
+    // SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:657-823): the mode-1 form of the call above
+    // by its reference name; vMatchedPairs = {(i, problem.match12[i]) : match12[i] >= 0}.
+    int SearchForTriangulation(adb_bow_search& problem) {
+        problem.mode = 1;
+        return SearchByBoW(problem);
+    }
+
+    // Fuse(pKF, vpMapPoints, th) (src/ORBmatcher.cc:825-975), search half: the shim fills the KeyFrame side and the mp_* arrays of an
+    // adb_proj_search; q_best_idx[i] >= 0 && q_best_dist[i] <= TH_LOW says "fuse map point i into key-point q_best_idx[i]"; the Replace /
+    // AddObservation bookkeeping of :948-968 stays with the caller.  Returns nFused.
+    int Fuse(adb_proj_search& problem, float th = 3.0f) {
+        problem.fuse = 1; problem.th = th; problem.use_ratio = 0; problem.check_orientation = 0;
+        airdos::check(adb_search_by_projection(m_, &problem, 1), "ORBmatcher::Fuse");
+        return problem.n_matches;
+    }
+
+    // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:245-310) for a batch of map points: observations' descriptors row-wise in
+    // `descriptors`, point p owning rows point_ptr[p] .. point_ptr[p + 1]); best_idx[p] = winning row within the point (-1: no observations,
+    // the caller keeps mDescriptor), best_desc = the winning 32 bytes per point.
+    void ComputeDistinctiveDescriptors(const uint8_t* descriptors, const std::vector<int32_t>& point_ptr, std::vector<int32_t>& best_idx,
+                                       std::vector<uint8_t>& best_desc) {
+        const int n_points = point_ptr.empty() ? 0 : (int)point_ptr.size() - 1;
+        best_idx.assign(n_points, -1); best_desc.assign((size_t)n_points * 32, 0);
+        if (n_points == 0) return;
+        airdos::check(adb_distinctive_descriptors(m_, descriptors, point_ptr.data(), n_points, best_idx.data(), best_desc.data()),
+                      "MapPoint::ComputeDistinctiveDescriptors");
+    }
+
 protected:
     float mfNNratio;
     bool mbCheckOrientation;
@@ -190,6 +219,18 @@ public:
         if (st == ADB_ERR_STOPPED) return false;
         airdos::check(st, "Optimizer::LocalBundleAdjustment");
         return true;
+    }
+    // int Optimizer::PoseOptimization(Frame* pFrame) (src/Optimizer.cc:232-429), batched: the shim fills one adb_pose_problem for the
+    // frames it wants optimised (per frame: Tcw as quaternion + translation, the map points' world positions, observations, invSigma2);
+    // outlier[] = mvbOutlier, the poses are updated in place.  Returns the reference's return value (nInitialCorrespondences - nBad) of the
+    // first frame; problem.n_inliers holds it for every frame.
+    static int PoseOptimization(adb_pose_problem& problem, int device = 0) {
+        adb_ba_t s = nullptr;
+        airdos::check(adb_ba_create(device, &s), "Optimizer");
+        const adb_status st = adb_pose_optimize(s, &problem);
+        adb_ba_destroy(s);
+        airdos::check(st, "Optimizer::PoseOptimization");
+        return problem.n_frames > 0 ? problem.n_inliers[0] : 0;
     }
     // Optimizer::GlobalBundleAdjustemnt(pMap, nIterations, pbStopFlag, nLoopKF, bRobust) / BundleAdjustment
     // (src/Optimizer.cc:52-230): all key-frames and map points, one round, no gating.

@@ -26,6 +26,17 @@ def test_host_mirror_compiles_links_and_refuses_without_gpu():
     assert out.returncode == 0 and "NO_DEVICE" in out.stdout, out.stdout + out.stderr
 
 
+def test_host_mirror_header_is_self_contained(tmp_path):
+    """A translation unit that includes nothing but airdos_host.hpp compiles cleanly (C++14, the reference's standard is C++11 + lambdas the
+    mirror does not need; -Wall -Wextra -Werror): every forwarder -- extractor, matcher (BestTwo, stereo, the guided searches, Fuse,
+    distinctive descriptors), optimizer (local / global / human BA, PoseOptimization) -- type-checks against the C-ABI header."""
+    src = tmp_path / "only_header.cpp"
+    src.write_text('#include "airdos_b200/host/airdos_host.hpp"\nint main() { return 0; }\n')
+    for std in ("c++14", "c++17"):
+        out = subprocess.run(["g++", "-std=" + std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + ROOT, str(src)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+
+
 @pytest.mark.gpu
 def test_host_mirror_matches_python_path(tmp_path):
     import airdos_b200 as adb
