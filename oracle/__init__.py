@@ -473,6 +473,48 @@ class LmSession:
         if self.h:
             self.lib.ba_oracle_lm_close(self.h); self.h = None
 
+    # -- one trial step by step, and the system it solves (for the Schur-complement pin, oracle/ref_schur.cpp)
+    def linearize(self):
+        """computeActiveErrors + buildSystem at the current state."""
+        self.lib.ba_oracle_lm_compute_errors.argtypes = [C.c_void_p]; self.lib.ba_oracle_lm_build.argtypes = [C.c_void_p]
+        self.lib.ba_oracle_lm_compute_errors(self.h); self.lib.ba_oracle_lm_build(self.h)
+
+    def system(self) -> dict:
+        """The assembled normal equations of a static window in BlockSolver_6_3's block form (ba_oracle_lm_system)."""
+        f = self.lib.ba_oracle_lm_system
+        f.argtypes = [C.c_void_p] * 8
+        sz = np.zeros(3, np.int32)
+        if not f(self.h, _p(sz), None, None, None, None, None, None):
+            raise ValueError("the window has articulated vertices")
+        np_, nl, ne = (int(v) for v in sz)
+        d = dict(n_poses=np_, n_points=nl, edge_pose=np.zeros(ne, np.int32), edge_point=np.zeros(ne, np.int32), W=np.zeros((ne, 6, 3)),
+                 Hpp=np.zeros((np_, 6, 6)), Hll=np.zeros((nl, 3, 3)), b=np.zeros(6 * np_ + 3 * nl))
+        f(self.h, _p(sz), _p(d["edge_pose"]), _p(d["edge_point"]), _p(d["W"]), _p(d["Hpp"]), _p(d["Hll"]), _p(d["b"]))
+        return d
+
+    def solve(self, lam: float):
+        """Solver::setLambda + Solver::solve (the oracle's Schur complement, Cholesky and back-substitution) -> (ok, x of the whole system)."""
+        self.lib.ba_oracle_lm_set_lambda.argtypes = [C.c_void_p, C.c_double]; self.lib.ba_oracle_lm_solve.argtypes = [C.c_void_p]
+        self.lib.ba_oracle_lm_vectors.argtypes = [C.c_void_p] * 4 + [C.c_int]
+        self.lib.ba_oracle_lm_set_lambda(self.h, float(lam))
+        ok = bool(self.lib.ba_oracle_lm_solve(self.h))
+        n = self.lib.ba_oracle_lm_vectors(self.h, None, None, None, 0)
+        x = np.zeros(n)
+        self.lib.ba_oracle_lm_vectors(self.h, _p(x), None, None, n)
+        return ok, x
+
+
+def ref_schur_solve(ref_lib, system: dict, lam: float):
+    """The REFERENCE's BlockSolver<BlockSolverTraits<6, 3>>::solve() (oracle/_ref/libref_schur.so: core/block_solver.hpp:353-483 compiled
+    from /root/reference) on `system` (LmSession.system()) with `lam` on both diagonals -> (ok, x, Hschur dense, bschur).  The linear
+    solver behind the reduced system is a plain Cholesky, not the reference's LDLT."""
+    npz, nl, ne = system["n_poses"], system["n_points"], len(system["edge_pose"])
+    ref_lib.ref_schur_solve.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 3
+    x = np.zeros(6 * npz + 3 * nl); hs = np.zeros((6 * npz, 6 * npz)); bs = np.zeros(6 * npz)
+    keep = [np.ascontiguousarray(system[k]) for k in ("edge_pose", "edge_point", "W", "Hpp", "Hll", "b")]
+    ok = ref_lib.ref_schur_solve(npz, nl, ne, *[_p(a) for a in keep], float(lam), _p(x), _p(hs), _p(bs))
+    return bool(ok), x, hs, bs
+
 
 def ref_lm_optimize(ref_lib, session: LmSession, iterations: int, cap: int = 512):
     """The REFERENCE's SparseOptimizer::optimize + OptimizationAlgorithmLevenberg::solve (oracle/_ref/libref_lm.so) over the session's

@@ -23,11 +23,15 @@
 //   schedules and gates  Optimizer::LocalBundleAdjustment, ::BundleAdjustment, ::PoseOptimization, ::LocalBundleAdjustmentHumanTrajactory whole, with the reference's edge types,
 //                        Converter and LM control over this file's solver steps (oracle/ref_lba.cpp) -> lba_ref.npz, pose_ref.npz: every
 //                        trial, final state, erase list / mvbOutlier / return value bit for bit
-// What stays "parity unpinned" against the literal reference: BlockSolver::buildSystem / solve (the Schur complement and the order of
-// its sums) and the linear solvers -- they need Eigen proper; the reduced system is solved by a dense Cholesky instead of Eigen's
-// SimplicialLDLT / LDLT, which agrees to rounding -- and the rigidity / motion Jacobians (undefined in the reference, D.4 / D.6).  Those
-// are pinned mathematically: finite-difference Jacobians, an independent numpy
-// normal-equation solve and an independent numpy LM trajectory (tests/test_oracle_ba.py).
+//   Schur complement     BlockSolver<Traits>::solve() whole (core/block_solver.hpp:353-483: marginalisation of the landmarks, reduced
+//                        right-hand side, landmark back-substitution), compiled between stand-in block containers (oracle/ref_schur.cpp)
+//                        on the systems Solver::build_system assembles                          -> schur_ref.npz: the whole update x within
+//                        1e-12 (measured 2.5e-14), the oracle's pose update satisfies the reference's reduced system to 3e-15
+// What stays "parity unpinned" against the literal reference: the linear solver behind the reduced system -- it needs Eigen proper; the
+// reduced system is solved by a dense Cholesky instead of Eigen's SimplicialLDLT / LDLT, which agrees to rounding (the residual check of
+// schur_ref.npz involves no factorisation) -- and the rigidity / motion Jacobians (undefined in the reference, D.4 / D.6).  Those are
+// pinned mathematically: finite-difference Jacobians, an independent numpy normal-equation solve and an independent numpy LM trajectory
+// (tests/test_oracle_ba.py).
 // Conventions for the reference's ill-defined corners: D.4 analytic
 // rigidity Jacobian, D.5 motion prior = identity (the caller passes it), D.6 d(error)/d(motion
 // translation) = delta_t * I with a zero rotation block.
@@ -856,6 +860,38 @@ int ba_oracle_lm_vectors(void* h, double* x, double* b, double* diag, int cap) {
             if (n < cap) { if (x) x[n] = S.x_l.empty() ? 0.0 : S.x_l[3 * l + k]; if (b) b[n] = S.bl[3 * l + k]; if (diag) diag[n] = S.Hll[(size_t)9 * l + 4 * k]; }
     }
     return n;
+}
+// The assembled normal equations of a STATIC window (no articulated vertices) in the block form BlockSolver_6_3 holds them, for the
+// pin of the Schur complement against the reference's own BlockSolver::solve (oracle/ref_schur.cpp): free poses and active points
+// renumbered densely in solver order; per active edge on a free pose its (pose, point) pair and 6 x 3 block W (row major); the diagonal
+// 6 x 6 pose blocks, the 3 x 3 point blocks, b = [poses | points].  Any output pointer may be NULL; sizes[3] = {free poses, active
+// points, edges with a free pose}.  Returns 0 when the window has articulated vertices.
+int ba_oracle_lm_system(void* h, int32_t* sizes, int32_t* edge_pose, int32_t* edge_point, double* W, double* Hpp, double* Hll, double* b) {
+    const Solver& S = ((LmSession*)h)->S;
+    if (S.P.n_joints || S.P.n_dists || S.P.n_motions) return 0;
+    std::vector<int> pt_idx(S.P.n_points, -1);
+    int np = 0, nl = 0, ne = 0;
+    for (int i = 0; i < S.P.n_poses; ++i) if (S.off_pose[i] >= 0) ++np;
+    for (int l = 0; l < S.P.n_points; ++l) if (S.act_point[l]) pt_idx[l] = nl++;
+    for (int e = 0; e < S.P.n_edges; ++e) {
+        if (S.lvl_e[e] || S.off_pose[S.P.edge_pose[e]] < 0) continue;
+        if (edge_pose) edge_pose[ne] = S.off_pose[S.P.edge_pose[e]] / 6;
+        if (edge_point) edge_point[ne] = pt_idx[S.P.edge_point[e]];
+        if (W) std::memcpy(W + (size_t)18 * ne, &S.W[(size_t)18 * e], 18 * sizeof(double));
+        ++ne;
+    }
+    if (Hpp)
+        for (int i = 0; i < np; ++i)
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) Hpp[(size_t)36 * i + 6 * r + c] = S.H[(size_t)(6 * i + r) * S.n_dense + 6 * i + c];
+    for (int l = 0; l < S.P.n_points; ++l) {
+        if (!S.act_point[l]) continue;
+        if (Hll) std::memcpy(Hll + (size_t)9 * pt_idx[l], &S.Hll[(size_t)9 * l], 9 * sizeof(double));
+        if (b) for (int k = 0; k < 3; ++k) b[S.n_dense + 3 * pt_idx[l] + k] = S.bl[3 * l + k];
+    }
+    if (b) for (int i = 0; i < S.n_dense; ++i) b[i] = S.b[i];
+    if (sizes) { sizes[0] = np; sizes[1] = nl; sizes[2] = ne; }
+    return 1;
 }
 void ba_oracle_lm_set_lambda(void* h, double lambda) { ((LmSession*)h)->S.lambda = lambda; }             // Solver::setLambda
 int ba_oracle_lm_solve(void* h) { return ((LmSession*)h)->S.solve_trial() ? 1 : 0; }                     // Solver::solve
