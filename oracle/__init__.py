@@ -492,6 +492,19 @@ class LmSession:
         f(self.h, _p(sz), _p(d["edge_pose"]), _p(d["edge_point"]), _p(d["W"]), _p(d["Hpp"]), _p(d["Hll"]), _p(d["b"]))
         return d
 
+    def system_x(self) -> dict:
+        """The same for any window (articulated ones included) in BlockSolverX's form: the non-marginalised vertices with their widths and
+        the dense block H over them, the map points as landmarks (ba_oracle_lm_system_x)."""
+        f = self.lib.ba_oracle_lm_system_x
+        f.argtypes = [C.c_void_p] * 9
+        sz = np.zeros(4, np.int32)
+        f(self.h, _p(sz), None, None, None, None, None, None, None)
+        nb, nl, ne, nd = (int(v) for v in sz)
+        d = dict(n_points=nl, n_dense=nd, dims=np.zeros(nb, np.int32), edge_block=np.zeros(ne, np.int32), edge_point=np.zeros(ne, np.int32),
+                 W=np.zeros((ne, 6, 3)), H=np.zeros((nd, nd)), Hll=np.zeros((nl, 3, 3)), b=np.zeros(nd + 3 * nl))
+        f(self.h, _p(sz), _p(d["dims"]), _p(d["edge_block"]), _p(d["edge_point"]), _p(d["W"]), _p(d["H"]), _p(d["Hll"]), _p(d["b"]))
+        return d
+
     def solve(self, lam: float):
         """Solver::setLambda + Solver::solve (the oracle's Schur complement, Cholesky and back-substitution) -> (ok, x of the whole system)."""
         self.lib.ba_oracle_lm_set_lambda.argtypes = [C.c_void_p, C.c_double]; self.lib.ba_oracle_lm_solve.argtypes = [C.c_void_p]
@@ -513,6 +526,17 @@ def ref_schur_solve(ref_lib, system: dict, lam: float):
     x = np.zeros(6 * npz + 3 * nl); hs = np.zeros((6 * npz, 6 * npz)); bs = np.zeros(6 * npz)
     keep = [np.ascontiguousarray(system[k]) for k in ("edge_pose", "edge_point", "W", "Hpp", "Hll", "b")]
     ok = ref_lib.ref_schur_solve(npz, nl, ne, *[_p(a) for a in keep], float(lam), _p(x), _p(hs), _p(bs))
+    return bool(ok), x, hs, bs
+
+
+def ref_schur_solve_x(ref_lib, system: dict, lam: float):
+    """The same function instantiated as BlockSolverX (run-time block sizes: what LocalBundleAdjustmentHumanTrajactory uses) on
+    LmSession.system_x() -> (ok, x, Hschur dense, bschur)."""
+    nb, nl, ne, nd = len(system["dims"]), system["n_points"], len(system["edge_block"]), system["n_dense"]
+    ref_lib.ref_schur_solve_x.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 3
+    x = np.zeros(nd + 3 * nl); hs = np.zeros((nd, nd)); bs = np.zeros(nd)
+    keep = [np.ascontiguousarray(system[k]) for k in ("dims", "edge_block", "edge_point", "W", "H", "Hll", "b")]
+    ok = ref_lib.ref_schur_solve_x(nb, _p(keep[0]), nl, ne, *[_p(a) for a in keep[1:]], float(lam), _p(x), _p(hs), _p(bs))
     return bool(ok), x, hs, bs
 
 

@@ -25,7 +25,8 @@
 //                        trial, final state, erase list / mvbOutlier / return value bit for bit
 //   Schur complement     BlockSolver<Traits>::solve() whole (core/block_solver.hpp:353-483: marginalisation of the landmarks, reduced
 //                        right-hand side, landmark back-substitution), compiled between stand-in block containers (oracle/ref_schur.cpp)
-//                        on the systems Solver::build_system assembles                          -> schur_ref.npz: the whole update x within
+//                        on the systems Solver::build_system assembles, as BlockSolver_6_3 (static windows) and as BlockSolverX
+//                        (articulated windows: run-time block widths 6 / 3 / 1)                 -> schur_ref.npz: the whole update x within
 //                        1e-12 (measured 2.5e-14), the oracle's pose update satisfies the reference's reduced system to 3e-15
 // What stays "parity unpinned" against the literal reference: the linear solver behind the reduced system -- it needs Eigen proper; the
 // reduced system is solved by a dense Cholesky instead of Eigen's SimplicialLDLT / LDLT, which agrees to rounding (the residual check of
@@ -891,6 +892,37 @@ int ba_oracle_lm_system(void* h, int32_t* sizes, int32_t* edge_pose, int32_t* ed
     }
     if (b) for (int i = 0; i < S.n_dense; ++i) b[i] = S.b[i];
     if (sizes) { sizes[0] = np; sizes[1] = nl; sizes[2] = ne; }
+    return 1;
+}
+// The same for ANY window, articulated ones included, in the form BlockSolverX holds it: the non-marginalised vertices (key-frames 6,
+// bone lengths 1, motions 6, joints 3, in solver order) with the whole dense block H over them (n_dense^2, symmetric), the map points
+// as the marginalised landmarks.  sizes[4] = {non-marginalised vertices, active points, edges with a free pose, n_dense}.
+int ba_oracle_lm_system_x(void* h, int32_t* sizes, int32_t* dims, int32_t* edge_block, int32_t* edge_point, double* W, double* H, double* Hll,
+                          double* b) {
+    const Solver& S = ((LmSession*)h)->S;
+    std::vector<int> pt_idx(S.P.n_points, -1);
+    int nb = 0, nl = 0, ne = 0;
+    auto put = [&](int d) { if (dims) dims[nb] = d; ++nb; };
+    for (int i = 0; i < S.P.n_poses; ++i) if (S.off_pose[i] >= 0) put(6);
+    for (int i = 0; i < S.P.n_dists; ++i) if (S.off_dist[i] >= 0) put(1);
+    for (int i = 0; i < S.P.n_motions; ++i) if (S.off_motion[i] >= 0) put(6);
+    for (int i = 0; i < S.P.n_joints; ++i) if (S.off_joint[i] >= 0) put(3);
+    for (int l = 0; l < S.P.n_points; ++l) if (S.act_point[l]) pt_idx[l] = nl++;
+    for (int e = 0; e < S.P.n_edges; ++e) {
+        if (S.lvl_e[e] || S.off_pose[S.P.edge_pose[e]] < 0) continue;
+        if (edge_block) edge_block[ne] = S.off_pose[S.P.edge_pose[e]] / 6;      // the key-frames come first and are all 6 wide
+        if (edge_point) edge_point[ne] = pt_idx[S.P.edge_point[e]];
+        if (W) std::memcpy(W + (size_t)18 * ne, &S.W[(size_t)18 * e], 18 * sizeof(double));
+        ++ne;
+    }
+    if (H) std::memcpy(H, S.H.data(), (size_t)S.n_dense * S.n_dense * sizeof(double));
+    for (int l = 0; l < S.P.n_points; ++l) {
+        if (!S.act_point[l]) continue;
+        if (Hll) std::memcpy(Hll + (size_t)9 * pt_idx[l], &S.Hll[(size_t)9 * l], 9 * sizeof(double));
+        if (b) for (int k = 0; k < 3; ++k) b[S.n_dense + 3 * pt_idx[l] + k] = S.bl[3 * l + k];
+    }
+    if (b) for (int i = 0; i < S.n_dense; ++i) b[i] = S.b[i];
+    if (sizes) { sizes[0] = nb; sizes[1] = nl; sizes[2] = ne; sizes[3] = S.n_dense; }
     return 1;
 }
 void ba_oracle_lm_set_lambda(void* h, double lambda) { ((LmSession*)h)->S.lambda = lambda; }             // Solver::setLambda

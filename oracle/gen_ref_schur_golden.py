@@ -29,6 +29,30 @@ SCHUR_CASES = [
 ]
 
 
+# articulated windows through BlockSolverX: (seed, key-frames, points, observations per point, trajectories, poses per trajectory, lambdas)
+SCHUR_X_CASES = [
+    (201, 10, 600, 5, 2, 4, (1.0, 1e2)),
+    (202, 16, 1500, 6, 3, 5, (1.0,)),
+    (203, 6, 200, 4, 1, 3, (1.0, 1e-2)),
+]
+
+
+def open_session_x(oracle, i):
+    from airdos_b200 import synth
+    seed, kf, pts, obs, tracks, poses, _ = SCHUR_X_CASES[i]
+    d = synth.make_ba_problem(kf, pts, obs, seed=seed, humans=tracks, human_poses=poses)
+    rng = np.random.default_rng(seed)
+    d["points"] = d["points"] + rng.normal(0, 0.02, d["points"].shape)
+    d["joints"] = d["joints"] + rng.normal(0, 0.01, d["joints"].shape)
+    s = oracle.LmSession(d, None, True)
+    s.linearize()
+    return s
+
+
+def first_lambda_x(system):
+    return 1e-5 * max(float(np.abs(np.diag(system["H"])).max()), float(np.abs(np.einsum("kii->ki", system["Hll"])).max()))
+
+
 def make_schur_case(i):
     """-> (problem dict, robust, edge levels or None)"""
     from airdos_b200 import synth
@@ -75,6 +99,24 @@ def main():
             out[f"c{i}_{k}_lambda"] = np.float64(lam0 * mult)
             out[f"c{i}_{k}_x"] = x; out[f"c{i}_{k}_bschur"] = bs; out[f"c{i}_{k}_hschur"] = hs
         out[f"c{i}_sizes"] = np.array([sysd["n_poses"], sysd["n_points"], len(sysd["edge_pose"])], np.int32)
+        s.close()
+    for i, case in enumerate(SCHUR_X_CASES):
+        s = open_session_x(oracle, i)
+        sysd = s.system_x()
+        lam0 = first_lambda_x(sysd)
+        for k, mult in enumerate(case[6]):
+            ok, x, hs, bs = oracle.ref_schur_solve_x(lib, sysd, lam0 * mult)
+            ok_o, x_o = s.solve(lam0 * mult)
+            assert ok and ok_o
+            rel = float(np.abs(x - x_o).max() / np.abs(x).max())
+            res = float(np.abs(hs @ x_o[:len(bs)] - bs).max() / np.abs(bs).max())
+            print(f"articulated case {i} lambda x{mult:g}: vertex widths {np.bincount(sysd['dims'])[[6, 1, 3]].tolist()} (6 / 1 / 3 wide), reduced order "
+                  f"{sysd['n_dense']}, {sysd['n_points']} points | oracle vs reference: |dx| / |x| = {rel:.2e}, residual = {res:.2e}")
+            out[f"x{i}_{k}_lambda"] = np.float64(lam0 * mult)
+            out[f"x{i}_{k}_x"] = x; out[f"x{i}_{k}_bschur"] = bs
+            if len(bs) <= 450:                                       # (the reduced matrix of the largest case would double the fixture)
+                out[f"x{i}_{k}_hschur_upper"] = hs[np.triu_indices(len(bs))]
+        out[f"x{i}_sizes"] = np.array([len(sysd["dims"]), sysd["n_points"], len(sysd["edge_block"]), sysd["n_dense"]], np.int32)
         s.close()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "schur_ref.npz"), **out)
     print("wrote tests/golden/schur_ref.npz")

@@ -83,6 +83,55 @@ template <int R, int K, int C> Mat<R, C> operator*(const Mat<R, K>& a, const Mat
     return o;
 }
 
+// ---- run-time sized matrix (Eigen::MatrixXd / VectorXd of BlockSolverX) with the same operations -----------------------------------
+struct MatX {
+    int r = 0, c = 0;
+    std::vector<double> m;
+    MatX() {}
+    explicit MatX(int n) : r(n), c(1), m((size_t)n, 0.0) {}
+    MatX(int r_, int c_) : r(r_), c(c_), m((size_t)r_ * c_, 0.0) {}
+    int rows() const { return r; }
+    int cols() const { return c; }
+    double& operator()(int i, int j) { return m[(size_t)j * r + i]; }
+    double operator()(int i, int j) const { return m[(size_t)j * r + i]; }
+    double& operator[](int i) { return m[i]; }
+    double operator[](int i) const { return m[i]; }
+    MatX& noalias() { return *this; }
+    MatX transpose() const { MatX t(c, r); for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) t(j, i) = (*this)(i, j); return t; }
+    MatX& operator-=(const MatX& o) { assert(o.r == r && o.c == c); for (size_t i = 0; i < m.size(); ++i) m[i] -= o.m[i]; return *this; }
+    MatX& operator+=(const MatX& o) { assert(o.r == r && o.c == c); for (size_t i = 0; i < m.size(); ++i) m[i] += o.m[i]; return *this; }
+    MatX inverse() const {
+        assert(r == 3 && c == 3 && "only the landmark block is inverted");
+        Mat<3, 3> a;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a(i, j) = (*this)(i, j);
+        const Mat<3, 3> inv = a.inverse();
+        MatX o(3, 3);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o(i, j) = inv(i, j);
+        return o;
+    }
+    struct MapType {
+        double* p; int n;
+        MapType(double* p_, int n_) : p(p_), n(n_) {}
+        MapType& noalias() { return *this; }
+        MapType& operator+=(const MatX& o) { assert(o.c == 1 && o.r == n); for (int i = 0; i < n; ++i) p[i] += o.m[i]; return *this; }
+    };
+};
+inline MatX operator*(const MatX& a, const MatX& b) {
+    assert(a.c == b.r);
+    MatX o(a.r, b.c);
+    for (int c = 0; c < b.c; ++c)
+        for (int r = 0; r < a.r; ++r) {
+            double s = a(r, 0) * b(0, c);
+            for (int k = 1; k < a.c; ++k) s += a(r, k) * b(k, c);
+            o(r, c) = s;
+        }
+    return o;
+}
+template <int R, int C> inline Mat<R, C>* new_block(const Mat<R, C>*, int, int) { return new Mat<R, C>(); }
+inline MatX* new_block(const MatX*, int r, int c) { return new MatX(r, c); }
+template <int R, int C> inline void zero_block(Mat<R, C>& b) { b = Mat<R, C>(); }
+inline void zero_block(MatX& b) { std::fill(b.m.begin(), b.m.end(), 0.0); }
+
 // ---- containers ------------------------------------------------------------------------------------------------------------------
 template <class M> class SparseBlockMatrix {
 public:
@@ -91,7 +140,7 @@ public:
     ~SparseBlockMatrix() { for (auto& col : _blockCols) for (auto& kv : col) delete kv.second; }
     int rows() const { return _rowBlockIndices.size() ? _rowBlockIndices.back() : 0; }
     int cols() const { return _colBlockIndices.size() ? _colBlockIndices.back() : 0; }
-    int rowBaseOfBlock(int r) const { return r ? _rowBlockIndices[r - 1] : 0; }
+    int rowBaseOfBlock(int r) const { return r ? _rowBlockIndices[r - 1] : 0; }      // (r = number of blocks gives the total, used for block sizes)
     int colBaseOfBlock(int c) const { return c ? _colBlockIndices[c - 1] : 0; }
     const std::vector<IntBlockMap>& blockCols() const { return _blockCols; }
     std::vector<IntBlockMap>& blockCols() { return _blockCols; }
@@ -99,11 +148,11 @@ public:
         auto it = _blockCols[c].find(r);
         if (it != _blockCols[c].end()) return it->second;
         if (!alloc) return nullptr;
-        M* b = new M();
+        M* b = new_block((const M*)nullptr, rowBaseOfBlock(r + 1) - rowBaseOfBlock(r), colBaseOfBlock(c + 1) - colBaseOfBlock(c));
         _blockCols[c][r] = b;
         return b;
     }
-    void clear() { for (auto& col : _blockCols) for (auto& kv : col) *kv.second = M(); }           // keeps the pattern (sparse_block_matrix.hpp:38-57, dealloc = false)
+    void clear() { for (auto& col : _blockCols) for (auto& kv : col) zero_block(*kv.second); }     // keeps the pattern (sparse_block_matrix.hpp:38-57, dealloc = false)
     bool add(SparseBlockMatrix* dest) const {                                                     // sparse_block_matrix.hpp:204-236: dest's blocks += ours
         for (size_t c = 0; c < _blockCols.size(); ++c)
             for (const auto& kv : _blockCols[c]) *dest->block(kv.first, (int)c, true) += *kv.second;
@@ -223,6 +272,15 @@ template <int p, int l> struct BlockSolverTraits {
     typedef LinearSolver<PoseMatrixType> LinearSolverType;
 };
 
+template <> struct BlockSolverTraits<-1, -1> {    // BlockSolverX (core/block_solver.h:74-92: Eigen::Dynamic everywhere)
+    typedef MatX PoseMatrixType;
+    typedef MatX LandmarkMatrixType;
+    typedef MatX PoseLandmarkMatrixType;
+    typedef MatX PoseVectorType;
+    typedef MatX LandmarkVectorType;
+    typedef LinearSolver<PoseMatrixType> LinearSolverType;
+};
+
 // the members solve() touches, named and typed as core/block_solver.h:95-182 declares them
 template <typename Traits> class BlockSolver {
 public:
@@ -316,5 +374,73 @@ extern "C" int ref_schur_solve(int n_poses, int n_points, int n_edges, const int
                     }
     }
     if (bschur) for (int i = 0; i < np; ++i) bschur[i] = bs[i];
+    return ok ? 1 : 0;
+}
+
+// The same through BlockSolverX = BlockSolver<BlockSolverTraits<Dynamic, Dynamic>> (what the AirDOS window uses: key-frames 6, bone lengths 1,
+// motions 6 and joints 3 wide stay in the reduced system, the map points are marginalised; src/Optimizer.cc:1508-1516): n_blocks
+// non-marginalised vertices of widths dims[], their dense symmetric H (n_dense^2: diagonal blocks and the pose-joint / joint-joint / ...
+// couplings of the articulated edges), edges (block of the key-frame, point) with their 6 x 3 W, Hll, b, lambda.
+extern "C" int ref_schur_solve_x(int n_blocks, const int* dims, int n_points, int n_edges, const int* edge_block, const int* edge_point, const double* W,
+                                 const double* H, const double* Hll, const double* b, double lambda, double* x, double* hschur, double* bschur) {
+    using namespace g2o;
+    typedef BlockSolverTraits<-1, -1> T;
+    std::vector<int> pidx(n_blocks), lidx(n_points);
+    int nd = 0;
+    for (int i = 0; i < n_blocks; ++i) { nd += dims[i]; pidx[i] = nd; }
+    for (int l = 0; l < n_points; ++l) lidx[l] = 3 * (l + 1);
+    BlockSolver<T> S;
+    SparseBlockMatrix<MatX> hpp(pidx, pidx), hs(pidx, pidx), hll(lidx, lidx);
+    SparseBlockMatrixDiagonal<MatX> dinv(lidx);
+    SparseBlockMatrixCCS<MatX> hpl(pidx, lidx), hst(pidx, pidx);
+    std::vector<MatX> wblocks(n_edges, MatX(6, 3));
+    // Hpp: the upper block triangle; a coupling block exists where an edge joins the two vertices = where H is not identically zero
+    for (int i = 0; i < n_blocks; ++i)
+        for (int j = i; j < n_blocks; ++j) {
+            const int r0 = hpp.rowBaseOfBlock(i), c0 = hpp.colBaseOfBlock(j);
+            bool any = i == j;
+            for (int r = 0; r < dims[i] && !any; ++r) for (int c = 0; c < dims[j]; ++c) any |= H[(size_t)(r0 + r) * nd + c0 + c] != 0.0;
+            if (!any) continue;
+            MatX* m = hpp.block(i, j, true);
+            for (int r = 0; r < dims[i]; ++r) for (int c = 0; c < dims[j]; ++c) (*m)(r, c) = H[(size_t)(r0 + r) * nd + c0 + c];
+            if (i == j) for (int r = 0; r < dims[i]; ++r) (*m)(r, r) += lambda;
+        }
+    for (int l = 0; l < n_points; ++l) {
+        MatX* m = hll.block(l, l, true);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) (*m)(r, c) = Hll[(size_t)9 * l + 3 * r + c];
+        for (int r = 0; r < 3; ++r) (*m)(r, r) += lambda;
+    }
+    for (int e = 0; e < n_edges; ++e) {
+        for (int r = 0; r < 6; ++r) for (int c = 0; c < 3; ++c) wblocks[e](r, c) = W[(size_t)18 * e + 3 * r + c];
+        hpl.blockCols()[edge_point[e]].push_back(SparseBlockMatrixCCS<MatX>::RowBlock(edge_block[e], &wblocks[e]));
+    }
+    for (auto& col : hpl.blockCols()) std::sort(col.begin(), col.end());
+    for (size_t c = 0; c < hpp.blockCols().size(); ++c) for (auto& kv : hpp.blockCols()[c]) hs.block(kv.first, (int)c, true);
+    for (const auto& col : hpl.blockCols())
+        for (size_t a = 0; a < col.size(); ++a)
+            for (size_t c2 = a; c2 < col.size(); ++c2) hs.block(col[a].row, col[c2].row, true);
+    for (size_t c = 0; c < hs.blockCols().size(); ++c)
+        for (auto& kv : hs.blockCols()[c]) hst.blockCols()[kv.first].push_back(SparseBlockMatrixCCS<MatX>::RowBlock((int)c, kv.second));
+    for (auto& col : hst.blockCols()) std::sort(col.begin(), col.end());
+    const int nl = 3 * n_points;
+    std::vector<double> coeff((size_t)nd + nl, 0.0), bcopy(b, b + nd + nl), bs((size_t)std::max(nd, 1), 0.0);
+    LinearSolver<MatX> ls;
+    S._Hpp = &hpp; S._Hll = &hll; S._Hschur = &hs; S._DInvSchur = &dinv; S._HplCCS = &hpl; S._HschurTransposedCCS = &hst; S._linearSolver = &ls;
+    S._coefficients = coeff.data(); S._bschur = bs.data(); S._x = x; S._b = bcopy.data(); S._sizePoses = nd; S._sizeLandmarks = nl;
+    for (int i = 0; i < nd + nl; ++i) x[i] = 0.0;
+    const bool ok = S.solve();
+    if (hschur) {
+        for (size_t i = 0; i < (size_t)nd * nd; ++i) hschur[i] = 0.0;
+        for (size_t c = 0; c < hs.blockCols().size(); ++c)
+            for (const auto& kv : hs.blockCols()[c]) {
+                const int r0 = hs.rowBaseOfBlock(kv.first), c0 = hs.colBaseOfBlock((int)c);
+                for (int r = 0; r < kv.second->rows(); ++r)
+                    for (int cc = 0; cc < kv.second->cols(); ++cc) {
+                        hschur[(size_t)(r0 + r) * nd + c0 + cc] = (*kv.second)(r, cc);
+                        hschur[(size_t)(c0 + cc) * nd + r0 + r] = (*kv.second)(r, cc);
+                    }
+            }
+    }
+    if (bschur) for (int i = 0; i < nd; ++i) bschur[i] = bs[i];
     return ok ? 1 : 0;
 }

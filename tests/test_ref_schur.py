@@ -2,7 +2,8 @@
 to the LITERAL reference: tests/golden/schur_ref.npz holds what the reference's own BlockSolver<BlockSolverTraits<6, 3>>::solve()
 (Thirdparty/g2o/g2o/core/block_solver.hpp:353-483, compiled from /root/reference: oracle/ref_schur.cpp; oracle/gen_ref_schur_golden.py wrote
 the fixture) computes on the normal equations of six seeded static windows (stereo / monocular mixes, fixed key-frames, edges switched
-off so that points drop out, with and without the kernel) at two damping values each.
+off so that points drop out, with and without the kernel) at two damping values each, and -- instantiated as BlockSolverX -- on three
+articulated windows (key-frames, motions, joints and bone lengths in the reduced system).
 
 The per-edge blocks that go INTO those equations are pinned in tests/test_ref_lm.py (constructQuadraticForm); the LM control around them
 likewise; what is not the reference's is the factorisation of the reduced matrix (Eigen's LDLT there, a Cholesky in both the oracle and
@@ -58,6 +59,32 @@ def test_oracle_schur_solve_equals_the_reference_block_solver(oracle_mod):
     assert dropped >= 1                                          # at least one window where switched-off edges removed points from the system
 
 
+def test_oracle_schur_solve_equals_the_reference_block_solver_x(oracle_mod):
+    """The same for the AirDOS windows: BlockSolverX (run-time block widths: key-frames and motions 6, joints 3, bone lengths 1 stay in the
+    reduced system with their couplings from the rigidity / motion / joint edges, map points are marginalised; src/Optimizer.cc:1508-1516)
+    on three articulated windows, reduced order up to 780."""
+    g = _gen()
+    gold = np.load(GOLD)
+    for i, case in enumerate(g.SCHUR_X_CASES):
+        s = g.open_session_x(oracle_mod, i)
+        sysd = s.system_x()
+        assert list(gold[f"x{i}_sizes"]) == [len(sysd["dims"]), sysd["n_points"], len(sysd["edge_block"]), sysd["n_dense"]], i
+        assert set(np.unique(sysd["dims"])) == {1, 3, 6}
+        for k in range(len(case[6])):
+            lam = float(gold[f"x{i}_{k}_lambda"])
+            assert lam == g.first_lambda_x(sysd) * case[6][k]
+            ok, x = s.solve(lam)
+            xr, bs = gold[f"x{i}_{k}_x"], gold[f"x{i}_{k}_bschur"]
+            assert ok and x.shape == xr.shape
+            assert np.abs(x - xr).max() <= 1e-12 * np.abs(xr).max(), (i, k, float(np.abs(x - xr).max() / np.abs(xr).max()))   # measured <= 1e-14
+            if f"x{i}_{k}_hschur_upper" in gold.files:
+                n = len(bs)
+                hs = np.zeros((n, n)); hs[np.triu_indices(n)] = gold[f"x{i}_{k}_hschur_upper"]
+                hs = hs + np.triu(hs, 1).T
+                assert np.abs(hs @ x[:n] - bs).max() <= 1e-12 * np.abs(bs).max(), (i, k)
+        s.close()
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="needs oracle/_ref/libref_schur.so built from /root/reference (build container only)")
 def test_fixture_is_what_the_reference_code_computes_now(oracle_mod):
     """Live: the reference's solve() compiled here reproduces the committed fixture bit for bit (same compiler, same inputs)."""
@@ -70,4 +97,11 @@ def test_fixture_is_what_the_reference_code_computes_now(oracle_mod):
         for k in range(len(case[7])):
             ok, x, hs, bs = oracle_mod.ref_schur_solve(lib, sysd, float(gold[f"c{i}_{k}_lambda"]))
             assert ok and (x == gold[f"c{i}_{k}_x"]).all() and (bs == gold[f"c{i}_{k}_bschur"]).all() and (hs == gold[f"c{i}_{k}_hschur"]).all(), (i, k)
+        s.close()
+    for i, case in enumerate(g.SCHUR_X_CASES):
+        s = g.open_session_x(oracle_mod, i)
+        sysd = s.system_x()
+        for k in range(len(case[6])):
+            ok, x, hs, bs = oracle_mod.ref_schur_solve_x(lib, sysd, float(gold[f"x{i}_{k}_lambda"]))
+            assert ok and (x == gold[f"x{i}_{k}_x"]).all() and (bs == gold[f"x{i}_{k}_bschur"]).all(), (i, k)
         s.close()
